@@ -1,0 +1,214 @@
+/*
+ * o3r.h — C ABI of the B200-native reconstruction hot path
+ * (disparity filter -> Q reprojection -> rigid transform -> VoxelGrid downsample -> global-cloud merge).
+ *
+ * This is the drop-in boundary for pk17r/online_3d_reconstruction.  The reference has no FFI of its
+ * own; the seam is the set of `Pose` member calls listed below (file:line are relative to the
+ * reference root).  Every entry point takes plain pointers and sizes, returns an int status
+ * (0 = ok, <0 = error, message via o3r_last_error) and never throws across the boundary; the
+ * reference's per-frame catch-all (pose.cpp:620-635) maps any failure to "empty cloud + message",
+ * which is what a caller gets by treating a negative status as n_out = 0.
+ *
+ * There is NO CPU fallback behind this interface: every compute entry point runs hand-written
+ * sm_100a CUDA kernels and fails with O3R_ERR_CUDA when no usable device is present.
+ */
+#ifndef O3R_H
+#define O3R_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define O3R_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------- */
+#define O3R_OK               0
+#define O3R_ERR_INVALID     -1   /* bad argument / parameter combination                        */
+#define O3R_ERR_CUDA        -2   /* CUDA runtime error or no device                             */
+#define O3R_ERR_CAPACITY    -3   /* caller's output buffer too small (n_out still reports need) */
+#define O3R_ERR_UNSUPPORTED -4   /* operation not available in the context's merge mode         */
+#define O3R_ERR_NOMEM       -5
+
+/* ---- record types -------------------------------------------------------------------------- */
+
+/* pcl::PointXYZRGB as it crosses the boundary: the reference's 32-byte PCL
+ * record carries 16 bytes of information; colour is 0x00RRGGBB packed exactly as
+ * pose_functions.cpp:1083/1120 does from the BGR Vec3b (alpha byte 0). */
+typedef struct o3r_point {
+    float    x, y, z;
+    uint32_t rgb;
+} o3r_point;
+
+/* disparity sample formats.  U8 is the reference's native format (pose_functions.cpp:548,1104);
+ * F64 is the plane-fitted image of --use_segment_labels (pose_functions.cpp:905,1102);
+ * U16 (value / disp_divisor, the commented variant at pose_functions.cpp:1102) and F32 are the
+ * north-star extensions. */
+enum { O3R_DISP_U8 = 0, O3R_DISP_U16 = 1, O3R_DISP_F32 = 2, O3R_DISP_F64 = 3 };
+
+/* blur applied when blur_kernel > 1 (pose_functions.cpp:1040-1047).  The reference's live filter is
+ * cv::bilateralFilter (not built yet); north_star names median and box. */
+enum { O3R_BLUR_MEDIAN = 0, O3R_BLUR_BOX = 1 };
+
+/* how the global cloud is kept */
+enum {
+    O3R_MERGE_ACCUMULATE = 0, /* per-cell accumulators keyed by the combined-grid key, merged every
+                                 cycle; o3r_cloud_transform is unsupported                         */
+    O3R_MERGE_RETAIN     = 1  /* cloud_big kept as points (pose.cpp:434); o3r_cloud_transform
+                                 applies tf_icp in place (pose.cpp:353); one-shot voxelisation     */
+};
+
+/* Read-only configuration: the `Pose` members the path reads (pose.h:93-98,108,118,126-128,149,168). */
+typedef struct o3r_params {
+    int      rows, cols;              /* pose.h:95 (set from the first image, pose_functions.cpp:636) */
+    int      cols_start_aft_cutout;   /* pose.h:95 = cols / cutout_ratio (pose_functions.cpp:638)     */
+    int      bounding_box;            /* pose.h:94 (20)                                               */
+    double   min_disparity;           /* pose.h:93 (64): valid iff (double)disp > min_disparity       */
+    double   Q[16];                   /* pose.h:128, row-major 4x4 double                             */
+    int      jump_pixels;             /* pose.h:96: 0 = keypoints only, 1 = dense grid, J = stride    */
+    int      blur_kernel;             /* pose.h:98: <= 1 = off                                         */
+    int      blur_mode;               /* O3R_BLUR_*                                                    */
+    double   voxel_size;              /* pose.h:118                                                    */
+    unsigned min_points_per_voxel;    /* pose.h:108 (combined grid only, pose_functions.cpp:1693)     */
+    int      dont_downsample;         /* pose.h:149                                                    */
+    int      use_segment_labels;      /* pose.h:168: disparity is F64, or labels + plane coefficients */
+    double   disp_divisor;            /* U16 only: disp = (double)raw / disp_divisor (200.0)          */
+    int      merge_mode;              /* O3R_MERGE_*                                                   */
+    int      device;                  /* CUDA device ordinal                                           */
+    int      max_batch_frames;        /* frames the context sizes its staging buffers for (>=1)       */
+} o3r_params;
+
+/* One frame of input: what createAndTransformPtCloud reads from acceptedImageDataVec[i]
+ * (pose.cpp:596-607, pose_functions.cpp:1035-1051).  Pointers are host or device memory according
+ * to the entry point used. */
+typedef struct o3r_frame {
+    const void*    disp;          /* rows x cols samples of disp_type, row stride disp_step BYTES  */
+    size_t         disp_step;
+    const uint8_t* bgr;           /* rows x cols x 3 (cv::Mat CV_8UC3, BGR), row stride bgr_step    */
+    size_t         bgr_step;
+    const uint8_t* labels;        /* optional rows x cols u8 segment labels (with plane_coef)       */
+    size_t         labels_step;
+    const double*  plane_coef;    /* optional [n_planes][3] = (a,b,c): disp = a*x + b*y + c for
+                                     label l = index+1; label 0 / label > n_planes -> 0.0
+                                     (pose_functions.cpp:968-971)                                   */
+    int            n_planes;
+    const float*   kp_xy;         /* optional ORB keypoints, n_kp pairs (x,y) (pose_functions.cpp:1059) */
+    int            n_kp;
+    float          T[16];         /* t_mat_FeatureMatched, row-major float 4x4 (pose.h:83)          */
+} o3r_frame;
+
+typedef struct o3r_ctx o3r_ctx;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+
+/* Replaces: construction of the read-only Pose state after populateData (pose.cpp:23-127). */
+int  o3r_create(const o3r_params* params, o3r_ctx** out_ctx);
+void o3r_destroy(o3r_ctx* ctx);
+const char* o3r_last_error(const o3r_ctx* ctx);   /* ctx may be NULL: last create() error */
+int  o3r_version(void);
+
+/* ---- per-frame path --------------------------------------------------------------------------- */
+
+/* Replaces: void Pose::createAndTransformPtCloud(int, PointCloud::Ptr&)  pose.cpp:596-636
+ *   = createSingleImgPtCloud (pose_functions.cpp:1030-1134) + transformPtCloud (:1358-1362)
+ *   + downsamplePtCloud(cloud,false) (:1654-1709, VoxelGrid leaf voxel_size/5; SOR not built yet).
+ * Host pointers in `frame`; `out` is a host buffer of `cap` records; *n_out = records produced
+ * (also set on O3R_ERR_CAPACITY).  Output order is the reference's: keypoints then row-major grid
+ * (dont_downsample) or ascending VoxelGrid index.  Thread-safe per ctx (internally serialised). */
+int o3r_frame_cloud(o3r_ctx* ctx, const o3r_frame* frame, int disp_type,
+                    o3r_point* out, size_t cap, size_t* n_out);
+
+/* Replaces: the cycle's fan-out + ordered concat + append, pose.cpp:361-434:
+ *   for each accepted frame createAndTransformPtCloud, concatenate in frame order, cloud_big.insert.
+ * Runs the n frames as one batched launch sequence and appends/merges the result into the
+ * resident cloud.  Host pointers; copies are issued from pinned staging and overlap compute.
+ * If frame_counts != NULL it receives each frame's output record count (n entries). */
+int o3r_frames_cloud(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_type,
+                     uint32_t* frame_counts);
+
+/* Same as o3r_frames_cloud but every pointer inside `frames` is DEVICE memory on ctx's device and
+ * nothing is copied (the inputs-resident-in-HBM measurement).  T is still read from host. */
+int o3r_frames_cloud_dev(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_type,
+                         uint32_t* frame_counts);
+
+/* Copies the last batch's concatenated per-frame clouds (what was appended) to the host. */
+int o3r_last_batch_points(o3r_ctx* ctx, o3r_point* out, size_t cap, size_t* n_out);
+
+/* ---- global cloud ----------------------------------------------------------------------------- */
+
+/* Replaces: transformPtCloud(cloud_big, cloud_big, tf_icp)  pose.cpp:350-354 (RETAIN mode only). */
+int o3r_cloud_transform(o3r_ctx* ctx, const float T[16]);
+
+/* Replaces: cloud_big->insert(end, ...) pose.cpp:434 for points produced elsewhere
+ * (e.g. the --downsample tool reading a PLY, pose.cpp:71-77).  Host pointer. */
+int o3r_cloud_append(o3r_ctx* ctx, const o3r_point* pts, size_t n);
+
+/* Replaces: PointCloud::Ptr Pose::downsamplePtCloud(PointCloud::Ptr&, bool combinedPtCloud=true)
+ *   pose_functions.cpp:1654-1709, callers pose.cpp:530 (final), :645 (preview), :77 (--downsample).
+ * z += 500, VoxelGrid leaf (v, v, 1000), min_points_per_voxel, z -= 500; output ascending voxel
+ * index.  With dont_downsample the cloud itself is returned (pose.cpp:535).  The resident cloud is
+ * left untouched.  `out` may be NULL with cap = 0 to query the size. */
+int o3r_cloud_downsample(o3r_ctx* ctx, o3r_point* out, size_t cap, size_t* n_out);
+
+/* Number of resident records (cells in ACCUMULATE mode, points in RETAIN mode) and clear. */
+int o3r_cloud_size(o3r_ctx* ctx, size_t* n);
+int o3r_cloud_clear(o3r_ctx* ctx);
+
+/* ---- stand-alone stages (parity probes; same kernels as above) ------------------------------- */
+
+/* pcl::VoxelGrid<PointXYZRGB>::filter on a host cloud: leaf (lx,ly,lz) as PCL's setLeafSize floats,
+ * min_points as setMinimumPointsNumberPerVoxel.  Optional outputs: keys[n_out] = the 64-bit absolute
+ * cell key (SURVEY §8a row VG), counts[n_out] = points per emitted voxel, *passthrough = 1 when PCL's
+ * int32 overflow guard returned the input unchanged. */
+int o3r_voxel_grid(o3r_ctx* ctx, const o3r_point* pts, size_t n, float lx, float ly, float lz,
+                   unsigned min_points, o3r_point* out, size_t cap, size_t* n_out,
+                   uint64_t* keys, uint32_t* counts, int* passthrough);
+
+/* The blur stage alone on a u8 plane (pose_functions.cpp:1040-1047 with blur_mode). Host pointers. */
+int o3r_blur_u8(o3r_ctx* ctx, const uint8_t* src, size_t src_step, int rows, int cols,
+                int kernel, int mode, uint8_t* dst, size_t dst_step);
+
+/* Per-pixel validity mask of the grid scan (1 byte per scanned pixel, row-major over the ROI
+ * samples) for one frame — the bit-exact mask contract of north_star. Host pointers. */
+int o3r_frame_mask(o3r_ctx* ctx, const o3r_frame* frame, int disp_type,
+                   uint8_t* mask, size_t cap, size_t* n_scanned);
+
+/* ---- multi-GPU exchange ---------------------------------------------------------- */
+
+/* Cell record exchanged between ranks: partial sums on the combined grid. */
+typedef struct o3r_cell {
+    uint64_t key;            /* (k+2^20)<<42 | (j+2^20)<<21 | (i+2^20) */
+    float    sx, sy, sz;     /* sums of x, y, z+500 (float)            */
+    uint32_t n;              /* points in the partial                   */
+    uint32_t sr, sg, sb;     /* colour sums                             */
+    uint32_t pad;
+} o3r_cell;                  /* 40 bytes */
+
+/* Pre-reduce the last batch on the combined grid and bucket the partial cells by
+ * owner = hash64(key) % world.  `send` is a DEVICE buffer of `cap` cells; counts[world] (host)
+ * receives the cells per owner, bucket r starting at sum(counts[0..r)).  ACCUMULATE mode,
+ * contexts created with defer_merge (see o3r_set_defer_merge). */
+int o3r_exchange_pack(o3r_ctx* ctx, int world, o3r_cell* send_dev, size_t cap, uint32_t* counts);
+
+/* Merge `n` received partial cells (DEVICE buffer, any order) into the resident shard. */
+int o3r_exchange_merge(o3r_ctx* ctx, const o3r_cell* recv_dev, size_t n);
+
+/* When set, o3r_frames_cloud* keeps the batch's per-frame clouds but does not merge them into the
+ * resident cloud; the caller runs o3r_exchange_pack / o3r_exchange_merge instead. */
+int o3r_set_defer_merge(o3r_ctx* ctx, int defer);
+
+/* ---- introspection ----------------------------------------------------------------------------- */
+
+/* Kernel launches issued by this context so far (bench.py's gpu_launches). */
+uint64_t o3r_launch_count(const o3r_ctx* ctx);
+/* The CUDA stream all work of the context is issued on (a cudaStream_t) — for event timing. */
+void* o3r_stream(o3r_ctx* ctx);
+/* Blocks until all work issued on the context's stream has completed. */
+int o3r_sync(o3r_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* O3R_H */

@@ -1,0 +1,57 @@
+"""Generates tests/golden/*.npz from the reference's shipped artefacts (run in the build container,
+where /root/reference exists; the GPU box only sees the committed .npz files).
+
+    python tests/golden/make_golden.py
+
+Sources (relative to /root/reference/build):
+  disparities/{1248,1249,1251}.png, segmentlabels/{same}.png, images/1248.png  real 1280x720 frames
+  output/log.txt:39-46,64          valid-pixel counts + variances the reference logged for them
+  output/medianBlurred_{15,31}.png cv::medianBlur outputs of images/1248.png written by the reference
+  cloud.ply                        a combined-grid VoxelGrid output of the reference (voxel_size 0.05)
+Decoding PNGs needs cv2 (present in the build container only).
+"""
+import os
+
+import cv2
+import numpy as np
+
+R = "/root/reference/build/"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    # --- real frames + the numbers the reference logged for them (log.txt) ---
+    nums = [1248, 1249, 1251]
+    disp = np.stack([cv2.imread(R + f"disparities/{n}.png", cv2.IMREAD_GRAYSCALE) for n in nums])
+    labels = np.stack([cv2.imread(R + f"segmentlabels/{n}.png", cv2.IMREAD_GRAYSCALE) for n in nums])
+    bgr1248 = cv2.imread(R + "images/1248.png")
+    np.savez_compressed(
+        os.path.join(OUT, "real_frames.npz"), img_nums=np.array(nums), disp=disp, labels=labels, bgr1248=bgr1248,
+        # log.txt:39,40,42 "index i disp_img_var V plane_fitted_disp_img_var P"; :45,46,64 "point_clout_pts"
+        disp_img_var=np.array([2.27913, 2.64813, 2.08488]),
+        plane_fitted_disp_img_var=np.array([1.63692, 1.49152, 1.64115]),
+        point_cloud_pts=np.array([747674, 747512, 747783]))
+    # --- median blur: crops of the reference's own outputs (top-left corner: exercises the border) ---
+    img = cv2.imread(R + "images/1248.png")
+    m15 = cv2.imread(R + "output/medianBlurred_15.png")
+    m31 = cv2.imread(R + "output/medianBlurred_31.png")
+    np.savez_compressed(os.path.join(OUT, "median_ref.npz"),
+                        src=img[:200, :280, 1].copy(),          # green channel, input crop incl. halo
+                        out15=m15[:160, :240, 1].copy(), out31=m31[:160, :240, 1].copy(),
+                        src_br=img[-200:, -280:, 2].copy(),     # bottom-right corner, red channel
+                        out15_br=m15[-160:, -240:, 2].copy(), out31_br=m31[-160:, -240:, 2].copy())
+    # --- cloud.ply vertices ---
+    raw = open(R + "cloud.ply", "rb").read()
+    h = raw.index(b"end_header\n") + len(b"end_header\n")
+    n = 55940
+    v = np.frombuffer(raw[h:h + 15 * n], dtype=np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"),
+                                                         ("r", "u1"), ("g", "u1"), ("b", "u1")]))
+    np.savez_compressed(os.path.join(OUT, "cloud_ply.npz"), header=np.frombuffer(raw[:h], dtype=np.uint8),
+                        xyz=np.stack([v["x"], v["y"], v["z"]], 1), rgb=np.stack([v["r"], v["g"], v["b"]], 1),
+                        trailer=np.frombuffer(raw[h + 15 * n:], dtype=np.uint8))
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,177 @@
+"""Pins the CPU oracle against the artefacts the reference ships.
+
+The reference has no tests; these are its de-facto golden vectors (tests/golden/make_golden.py).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+from online_3d_reconstruction_b200 import abi
+
+
+@pytest.fixture(scope="module")
+def real(golden_dir):
+    return np.load(os.path.join(golden_dir, "real_frames.npz"))
+
+
+def test_disp_variance_matches_reference_log(real):
+    """getVariance on raw u8 disparity == build/output/log.txt:39-42 (6 significant figures)."""
+    p = abi.make_params(jump_pixels=1)
+    for i in range(3):
+        v = ob.get_variance(p, real["disp"][i], False)
+        assert f"{v:.6g}" == f"{real['disp_img_var'][i]:.6g}"
+
+
+def test_plane_fit_variance_and_mask_count_match_reference_log(real):
+    """createPlaneFittedDisparityImages + getVariance(planeFitted) and the valid-pixel count of
+    createSingleImgPtCloud (jump_pixels=1, --use_segment_labels) == log.txt:39-46,64."""
+    p = abi.make_params(jump_pixels=1, voxel_size=0.05, use_segment_labels=True)
+    bgr = real["bgr1248"]
+    for i in range(3):
+        coef, f64 = ob.plane_fit(p, real["labels"][i], real["disp"][i])
+        v = ob.get_variance(p, f64, True)
+        assert f"{v:.6g}" == f"{real['plane_fitted_disp_img_var'][i]:.6g}"
+        keep = []
+        fr = abi.make_frame(f64, bgr, np.eye(4), keep=keep)
+        pts, mask = ob.create_single_img_pt_cloud(p, fr, abi.DISP_F64, want_mask=True)
+        assert len(pts) == int(real["point_cloud_pts"][i]) == int(mask.sum())
+        # labels + per-label (a,b,c) evaluated in place is the same image
+        fr2 = abi.make_frame(None, bgr, np.eye(4), labels=real["labels"][i], plane_coef=coef, keep=keep)
+        pts2 = ob.create_single_img_pt_cloud(p, fr2, abi.DISP_F64)
+        assert np.array_equal(pts, pts2)
+
+
+def test_median_matches_reference_outputs(golden_dir):
+    """cv::medianBlur(images/1248.png, 15|31) as written by the reference (output/medianBlurred_*.png)."""
+    g = np.load(os.path.join(golden_dir, "median_ref.npz"))
+    for k in (15, 31):
+        out = ob.blur_u8(g["src"], k, abi.BLUR_MEDIAN)
+        assert np.array_equal(out[:160, :240], g[f"out{k}"])
+        out = ob.blur_u8(g["src_br"], k, abi.BLUR_MEDIAN)
+        assert np.array_equal(out[-160:, -240:], g[f"out{k}_br"])
+
+
+def test_median_rejects_even_kernel():
+    src = np.zeros((8, 8), np.uint8)
+    with pytest.raises(RuntimeError):
+        ob.blur_u8(src, 4, abi.BLUR_MEDIAN)
+
+
+def test_box_small_cases():
+    """cv::blur model: anchor k/2, BORDER_REFLECT_101, round-half-even."""
+    src = np.arange(25, dtype=np.uint8).reshape(5, 5) * 10
+    out = ob.blur_u8(src, 3, abi.BLUR_BOX)
+    pad = np.pad(src.astype(np.int64), 1, mode="reflect")
+    S = sum(pad[dy:dy + 5, dx:dx + 5] for dy in range(3) for dx in range(3))
+    q, r = np.divmod(S, 9)
+    exp = q + (2 * r > 9)
+    assert np.array_equal(out, exp.astype(np.uint8))
+    # even kernel: window [x-1, x] for k=2, ties go to even
+    src = np.array([[0, 1, 0, 1]] * 2, dtype=np.uint8)
+    out = ob.blur_u8(src, 2, abi.BLUR_BOX)
+    # sums: reflect101 of col -1 is col 1 -> S = 2*(src[x-1]+src[x]); x=0: 2*(1+0)=2 -> 0.5 -> 0
+    assert out.tolist() == [[0, 0, 0, 0]] * 2
+
+
+def _ply_points(golden_dir):
+    g = np.load(os.path.join(golden_dir, "cloud_ply.npz"))
+    pts = np.zeros(len(g["xyz"]), dtype=abi.POINT)
+    pts["x"], pts["y"], pts["z"] = g["xyz"].T
+    rgb = g["rgb"].astype(np.uint32)
+    pts["rgb"] = (rgb[:, 0] << 16) | (rgb[:, 1] << 8) | rgb[:, 2]
+    return pts
+
+
+def test_combined_voxelgrid_reproduces_reference_cloud_ply(golden_dir):
+    """build/cloud.ply is a combined-grid VoxelGrid output (voxel_size 0.05): one point per XY cell in
+    ascending (j, i) order with every z on the float(+500, -500) lattice.  Re-voxelising it — in the
+    original or any shuffled order — must return it bit-exactly (order, cell function, z round trip)."""
+    pts = _ply_points(golden_dir)
+    p = abi.make_params(voxel_size=0.05, min_points_per_voxel=1)
+    out = ob.downsample_pt_cloud(p, pts, True)
+    assert np.array_equal(out, pts)
+    perm = np.random.default_rng(0).permutation(len(pts))
+    assert np.array_equal(ob.downsample_pt_cloud(p, pts[perm], True), pts)
+    # keys strictly increasing in the shipped order
+    sh = pts.copy()
+    sh["z"] += np.float32(500)
+    _, keys, counts, pt = ob.voxel_grid(sh, (0.05, 0.05, 1000.0), 1)
+    assert not pt and np.all(np.diff(keys.astype(np.int64)) > 0) and np.all(counts == 1)
+
+
+def test_min_points_per_voxel(golden_dir):
+    pts = _ply_points(golden_dir)[:2000]
+    dup = np.concatenate([pts, pts[::2]])
+    p = abi.make_params(voxel_size=0.05, min_points_per_voxel=2)
+    out = ob.downsample_pt_cloud(p, dup, True)
+    assert np.array_equal(out, pts[::2])
+
+
+def test_author_known_answer_frame():
+    """build/disparities/pointCloud.m:36-48: disparity 128 everywhere, 142 in rows 99..199 x cols 199..399;
+    image green, red in the block.  Z = Q23 / (Q32 * d)."""
+    disp = np.full((720, 1280), 128, np.uint8)
+    disp[99:200, 199:400] = 142
+    bgr = np.zeros((720, 1280, 3), np.uint8)
+    bgr[:, :, 1] = 255
+    bgr[99:200, 199:400, 1] = 0
+    bgr[99:200, 199:400, 2] = 255
+    p = abi.make_params(jump_pixels=1, dont_downsample=True)
+    keep = []
+    pts = ob.create_single_img_pt_cloud(p, abi.make_frame(disp, bgr, np.eye(4), keep=keep), abi.DISP_U8)
+    assert len(pts) == 748000
+    f, a = abi.Q_CAM13[11], abi.Q_CAM13[14]
+    z = pts["z"].reshape(680, 1100)
+    assert np.all(z[100 - 20:200 - 20, 200 - 160:400 - 160] == np.float32(f / (a * 142)))
+    assert z[0, 0] == np.float32(f / (a * 128)) and abs(float(z[0, 0]) - 19.608) < 1e-3
+    rgb = pts["rgb"].reshape(680, 1100)
+    assert rgb[0, 0] == 0x00FF00 and rgb[100, 100] == 0xFF0000
+    # first scanned pixel is (x0=160, y=20)
+    assert pts["x"][0] == np.float32((160 + abi.Q_CAM13[3]) * (1.0 / (a * 128)))
+
+
+def test_voxelgrid_overflow_guard_passthrough():
+    """PCL: dx*dy*dz > INT32_MAX -> 'Leaf size is too small', output = input."""
+    rng = np.random.default_rng(1)
+    pts = np.zeros(1000, dtype=abi.POINT)
+    pts["x"], pts["y"], pts["z"] = (rng.uniform(0, 10, (3, 1000))).astype(np.float32)
+    out, keys, counts, passthrough = ob.voxel_grid(pts, (0.002, 0.002, 0.002), 0)
+    assert passthrough and np.array_equal(out, pts) and np.all(counts == 1)
+    out, _, counts, passthrough = ob.voxel_grid(pts, (0.5, 0.5, 0.5), 0)
+    assert not passthrough and counts.sum() == 1000 and len(out) < 1000
+
+
+def test_empty_inputs():
+    pts = np.zeros(0, dtype=abi.POINT)
+    out, keys, counts, pt = ob.voxel_grid(pts, (0.1, 0.1, 0.1), 0)
+    assert len(out) == 0 and not pt
+    p = abi.make_params(jump_pixels=1, dont_downsample=True)
+    keep = []
+    fr = abi.make_frame(np.zeros((720, 1280), np.uint8), np.zeros((720, 1280, 3), np.uint8), np.eye(4), keep=keep)
+    assert len(ob.create_and_transform_pt_cloud(p, fr, abi.DISP_U8)) == 0
+
+
+def test_generate_tmat_structure():
+    """generateTmat (pose_functions.cpp:1178-1356): identity attitude -> known closed form; bad norm throws."""
+    T = ob.generate_tmat(1.0, 2.0, 3.0, 0.0, 0.0, 0.0, 1.0)
+    assert T[3].tolist() == [0, 0, 0, 1]
+    R = T[:3, :3].astype(np.float64)
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-6) and abs(abs(np.linalg.det(R)) - 1) < 1e-6
+    # camera looks down: image z (depth) maps to world -z
+    assert T[2, 2] < -0.99
+    with pytest.raises(ValueError):
+        ob.generate_tmat(0, 0, 0, 0.5, 0.5, 0.5, 0.9)
+    # float product is left-to-right row*col accumulation
+    a = np.random.default_rng(0).normal(size=(4, 4)).astype(np.float32)
+    b = np.random.default_rng(1).normal(size=(4, 4)).astype(np.float32)
+    m = ob.mat4_mul(a, b)
+    exp = np.zeros((4, 4), np.float32)
+    for i in range(4):
+        for j in range(4):
+            s = np.float32(a[i, 0] * b[0, j])
+            for k in range(1, 4):
+                s = np.float32(s + np.float32(a[i, k] * b[k, j]))
+            exp[i, j] = s
+    assert np.array_equal(m, exp)
