@@ -109,6 +109,11 @@ void o3r_destroy(o3r_ctx* ctx);
 const char* o3r_last_error(const o3r_ctx* ctx);   /* ctx may be NULL: last create() error */
 int  o3r_version(void);
 
+/* Page-locked host memory for image buffers handed to the host-pointer entry points: copies from it run
+ * at full PCIe rate and asynchronously (what cv::cuda::HostMem would give the reference's cv::Mat). */
+void* o3r_host_alloc(size_t bytes);
+void  o3r_host_free(void* p);
+
 /* ---- per-frame path --------------------------------------------------------------------------- */
 
 /* Replaces: void Pose::createAndTransformPtCloud(int, PointCloud::Ptr&)  pose.cpp:596-636

@@ -1,7 +1,7 @@
 """ctypes mirror of include/o3r.h (struct layouts, enums, numpy record dtypes).
 
-Pure declarations: no library is loaded here, so the oracle binding in tests/ can share the
-struct definitions without the product ever touching oracle/.
+Pure declarations: no library is loaded here, so the checker's binding in tests/ can share the
+struct definitions while the product never touches the checker.
 """
 import ctypes as C
 

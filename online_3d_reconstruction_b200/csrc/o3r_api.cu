@@ -1,0 +1,954 @@
+// o3r_api.cu — C ABI (include/o3r.h) over the sm_100a kernels.  No CPU fallback: every compute entry
+// point launches CUDA kernels on the context's stream and fails with O3R_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "blur.cuh"
+#include "common.cuh"
+#include "sort.cuh"
+#include "stage_a.cuh"
+#include "voxel.cuh"
+
+using namespace o3r;
+
+namespace {
+
+std::string g_create_err;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+    cudaError_t ensure(size_t bytes, cudaStream_t st = nullptr, size_t preserve = 0) {
+        if (bytes <= cap) return cudaSuccess;
+        size_t want = std::max(bytes, cap + cap / 2);
+        want = (want + 255) & ~(size_t)255;
+        void* np = nullptr;
+        cudaError_t e = cudaMalloc(&np, want);
+        if (e != cudaSuccess) return e;
+        if (p && preserve) {
+            e = cudaMemcpyAsync(np, p, preserve, cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return e;
+            cudaStreamSynchronize(st);
+        }
+        if (p) cudaFree(p);
+        p = np;
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+enum { CNT_PTS = 0, CNT_VOX = 1, CNT_CYC = 2, CNT_NEW = 3, CNT_EMIT = 4, CNT_NEWSCAN = 5, CNT_N = 16 };
+
+}  // namespace
+
+struct o3r_ctx {
+    o3r_params p;
+    std::mutex mu;
+    std::string err;
+    uint64_t launches = 0;
+    cudaStream_t st = nullptr;
+    int nx = 0, ny = 0;
+    uint32_t npix = 0;
+    int canon = 0;
+    float leaf_f = 0, inv_f = 0, leaf_c = 0, inv_c = 0, inv_cz = 0;
+    int defer_merge = 0;
+    DevBuf lut_r, lut_z;
+    // input staging (host-pointer entry points)
+    DevBuf d_disp, d_bgr, d_labels, d_coef, d_kp;
+    DevBuf d_frames, d_blur, d_blurjobs;
+    // per-batch work buffers
+    DevBuf tile_cnt, tile_off, bbox, frame_off, grids, counters, pts, sortbuf, hist, plan_all, plan_v2, ghist;
+    DevBuf head_cnt, head_off, vox, vox_off, seg2, tmat, mask;
+    uint32_t* h_counters = nullptr;   // pinned
+    uint32_t* h_offs = nullptr;       // pinned, frame offsets readback
+    size_t h_offs_cap = 0;
+    // last batch
+    int last_n = 0;
+    size_t last_total = 0;
+    bool last_is_vox = false;
+    std::vector<uint32_t> last_off;
+    // resident cloud: accumulators (ACCUMULATE) ...
+    DevBuf res_keys[2], res_acc[2], res_rgb[2];
+    int res_cur = 0;
+    uint32_t n_res = 0;
+    DevBuf ckey, cacc, crgb, new_cnt, new_off, new_keys, okeys;
+    uint32_t n_cyc = 0;
+    // ... or points (RETAIN / dont_downsample)
+    DevBuf cloud;
+    size_t n_cloud = 0;
+
+    bool retain() const { return p.dont_downsample || p.merge_mode == O3R_MERGE_RETAIN; }
+    int fail(int code, const std::string& m) { err = m; return code; }
+    int fail_cuda(cudaError_t e, const char* what, int line) {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s [o3r_api.cu:%d]", (int)e, cudaGetErrorString(e), what, line);
+        err = buf;
+        return O3R_ERR_CUDA;
+    }
+};
+
+#define CU(call)                                                              \
+    do {                                                                      \
+        cudaError_t e_ = (call);                                              \
+        if (e_ != cudaSuccess) return ctx->fail_cuda(e_, #call, __LINE__);    \
+    } while (0)
+
+#define LAUNCH(kernel, grid, block, smem, ...)                                \
+    do {                                                                      \
+        kernel<<<grid, block, smem, ctx->st>>>(__VA_ARGS__);                  \
+        ++ctx->launches;                                                      \
+        cudaError_t e_ = cudaGetLastError();                                  \
+        if (e_ != cudaSuccess) return ctx->fail_cuda(e_, #kernel, __LINE__);  \
+    } while (0)
+
+namespace {
+
+inline uint32_t cdiv(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
+inline size_t disp_elem(int t) { return t == O3R_DISP_U8 ? 1 : t == O3R_DISP_U16 ? 2 : t == O3R_DISP_F32 ? 4 : 8; }
+
+int read_counters(o3r_ctx* ctx) {
+    CU(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return O3R_OK;
+}
+
+// ---- radix sort driver -----------------------------------------------------------------------------------------
+template <typename KeyT>
+int sort_pairs(o3r_ctx* ctx, KeyT* k0, KeyT* k1, uint32_t* v0, uint32_t* v1, const uint32_t* seg_off, int n_seg,
+               size_t per_seg_cap, const SortPlan* plan, int passes, int iota_first) {
+    const uint32_t tiles_ub = std::max(1u, cdiv(per_seg_cap, kRsTile));
+    CU(ctx->hist.ensure((size_t)n_seg * kRsBins * tiles_ub * 4));
+    uint32_t* hist = ctx->hist.as<uint32_t>();
+    const dim3 grid(tiles_ub, n_seg);
+    for (int p = 0; p < passes; ++p) {
+        LAUNCH((k_rs_hist<KeyT>), grid, kThreads, 0, k0, k1, seg_off, plan, p, tiles_ub, hist);
+        LAUNCH(k_rs_scan, n_seg, kThreads, 0, seg_off, plan, p, tiles_ub, hist);
+        LAUNCH((k_rs_scatter<KeyT>), grid, kThreads, rs_scatter_smem<KeyT>(), k0, k1, v0, v1, seg_off, plan, p,
+               tiles_ub, hist, iota_first);
+    }
+    return O3R_OK;
+}
+
+// ---- engine 1: VoxelGrid on segments whose leaf indices already sit in sortbuf keys0 ----------------------------
+struct SortU32 { uint32_t *k0, *k1, *v0, *v1; };
+
+int carve_sort_u32(o3r_ctx* ctx, size_t n, SortU32& s) {
+    const size_t n4 = (n + 63) & ~(size_t)63;
+    CU(ctx->sortbuf.ensure(n4 * 16));
+    s.k0 = ctx->sortbuf.as<uint32_t>();
+    s.k1 = s.k0 + n4; s.v0 = s.k1 + n4; s.v1 = s.v0 + n4;
+    return O3R_OK;
+}
+
+int ensure_plan_all(o3r_ctx* ctx, int n_seg) {
+    if (ctx->plan_all.cap >= (size_t)n_seg * sizeof(SortPlan)) return O3R_OK;
+    const int n = std::max(n_seg, 64);
+    std::vector<SortPlan> pl(n);
+    for (auto& q : pl) {
+        for (int p = 0; p < kMaxPasses; ++p) { q.active[p] = p < 4; q.in_parity[p] = (uint8_t)(p & 1); }
+        q.final_parity = 0; q.n_active = 4;
+    }
+    CU(ctx->plan_all.ensure((size_t)n * sizeof(SortPlan)));
+    CU(cudaMemcpyAsync(ctx->plan_all.p, pl.data(), (size_t)n * sizeof(SortPlan), cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return O3R_OK;
+}
+
+// sorts + reduces; out/out_off sized by the caller.  CNT_VOX receives the total.
+int vg_sorted_reduce(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const uint32_t* seg_off, int n_seg,
+                     size_t per_seg_cap, const GridParams* grids, float ix, float iy, float iz, uint32_t min_points,
+                     int z_shift, float4* out, uint32_t* out_off, uint64_t* out_keys, uint32_t* out_counts) {
+    int rc = ensure_plan_all(ctx, n_seg);
+    if (rc) return rc;
+    const SortPlan* plan = ctx->plan_all.as<SortPlan>();
+    rc = sort_pairs<uint32_t>(ctx, sb.k0, sb.k1, sb.v0, sb.v1, seg_off, n_seg, per_seg_cap, plan, 4, 1);
+    if (rc) return rc;
+    VgArgs A;
+    A.keys0 = sb.k0; A.keys1 = sb.k1; A.vals0 = sb.v0; A.vals1 = sb.v1;
+    A.seg_off = seg_off; A.plan = plan; A.grids = grids; A.pts = pts;
+    A.tiles_ub = std::max(1u, cdiv(per_seg_cap, kTileV));
+    A.min_points = min_points; A.z_shift = z_shift;
+    A.lx_inv = ix; A.ly_inv = iy; A.lz_inv = iz;
+    const size_t nt = (size_t)A.tiles_ub * n_seg;
+    CU(ctx->head_cnt.ensure(nt * 4));
+    CU(ctx->head_off.ensure(nt * 4));
+    const dim3 grid(A.tiles_ub, n_seg);
+    uint32_t* cnt = ctx->counters.as<uint32_t>();
+    LAUNCH(k_vg_heads, grid, kThreads, 0, A, ctx->head_cnt.as<uint32_t>());
+    LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->head_cnt.as<uint32_t>(), ctx->head_off.as<uint32_t>(), (uint32_t)nt,
+           cnt + CNT_VOX);
+    LAUNCH(k_vg_reduce, grid, kThreads, 0, A, ctx->head_off.as<uint32_t>(), cnt + CNT_VOX, out, out_off, n_seg,
+           out_keys, out_counts);
+    return O3R_OK;
+}
+
+// ---- engine 2: merge `n` items (points or partial cells) into the resident accumulators --------------------------
+struct SortU64 { uint64_t *k0, *k1; uint32_t *v0, *v1; };
+
+int carve_sort_u64(o3r_ctx* ctx, size_t n, SortU64& s) {
+    const size_t n4 = (n + 63) & ~(size_t)63;
+    CU(ctx->sortbuf.ensure(n4 * 24));
+    s.k0 = ctx->sortbuf.as<uint64_t>();
+    s.k1 = s.k0 + n4;
+    s.v0 = reinterpret_cast<uint32_t*>(s.k1 + n4);
+    s.v1 = s.v0 + n4;
+    return O3R_OK;
+}
+
+// Builds the cycle's cell list (ckey/cacc/crgb, n_cyc) from items, continuing from the resident sums when
+// `use_resident`.  Leaves h_counters[CNT_CYC], [CNT_NEW] valid.
+template <typename Items>
+int acc_build_cycle(o3r_ctx* ctx, const Items& items, const float4* pts, const o3r_cell* cells, size_t n,
+                    bool use_resident) {
+    uint32_t* cnt = ctx->counters.as<uint32_t>();
+    ctx->n_cyc = 0;
+    ctx->h_counters[CNT_CYC] = ctx->h_counters[CNT_NEW] = 0;
+    if (n == 0) return O3R_OK;
+    if (n >= (1ull << 32)) return ctx->fail(O3R_ERR_INVALID, "batch too large for 32-bit indices");
+    SortU64 sb;
+    int rc = carve_sort_u64(ctx, n, sb);
+    if (rc) return rc;
+    CU(ctx->seg2.ensure(16));
+    CU(ctx->ghist.ensure(kMaxPasses * kRsBins * 4));
+    CU(ctx->plan_v2.ensure(sizeof(SortPlan)));
+    const uint32_t seg_h[2] = {0u, (uint32_t)n};
+    CU(cudaMemcpyAsync(ctx->seg2.p, seg_h, 8, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemsetAsync(ctx->ghist.p, 0, kMaxPasses * kRsBins * 4, ctx->st));
+    CU(cudaMemsetAsync(cnt + CNT_NEW, 0, 4, ctx->st));
+    const uint32_t* seg = ctx->seg2.as<uint32_t>();
+    const uint32_t gk = std::min<uint32_t>(cdiv(n, kThreads), 148 * 8);
+    if (pts)
+        LAUNCH(k_acc_key_pts, gk, kThreads, 0, pts, seg + 1, ctx->inv_c, ctx->inv_c, ctx->inv_cz, sb.k0, sb.v0,
+               ctx->ghist.as<uint32_t>());
+    else
+        LAUNCH(k_acc_key_cells, gk, kThreads, 0, cells, (uint32_t)n, sb.k0, sb.v0, ctx->ghist.as<uint32_t>());
+    SortPlan* plan = ctx->plan_v2.as<SortPlan>();
+    LAUNCH(k_rs_plan, 1, kThreads, 0, ctx->ghist.as<uint32_t>(), seg, kMaxPasses, plan);
+    rc = sort_pairs<uint64_t>(ctx, sb.k0, sb.k1, sb.v0, sb.v1, seg, 1, n, plan, kMaxPasses, 0);
+    if (rc) return rc;
+    AccArgs A;
+    A.keys0 = sb.k0; A.keys1 = sb.k1; A.vals0 = sb.v0; A.vals1 = sb.v1;
+    A.seg_off = seg; A.plan = plan;
+    A.tiles_ub = cdiv(n, kTileV);
+    const int cur = ctx->res_cur;
+    A.res_keys = ctx->res_keys[cur].as<uint64_t>();
+    A.res_acc = ctx->res_acc[cur].as<float4>();
+    A.res_rgb = ctx->res_rgb[cur].as<uint4>();
+    A.n_res = use_resident ? ctx->n_res : 0u;
+    CU(ctx->head_cnt.ensure((size_t)A.tiles_ub * 4));
+    CU(ctx->head_off.ensure((size_t)A.tiles_ub * 4));
+    CU(ctx->ckey.ensure(n * 8));
+    CU(ctx->cacc.ensure(n * 16));
+    CU(ctx->crgb.ensure(n * 16));
+    LAUNCH(k_acc_heads, A.tiles_ub, kThreads, 0, A, ctx->head_cnt.as<uint32_t>());
+    LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->head_cnt.as<uint32_t>(), ctx->head_off.as<uint32_t>(), A.tiles_ub,
+           cnt + CNT_CYC);
+    LAUNCH((k_acc_reduce<Items>), A.tiles_ub, kThreads, 0, A, items, ctx->head_off.as<uint32_t>(),
+           ctx->ckey.as<uint64_t>(), ctx->cacc.as<float4>(), ctx->crgb.as<uint4>(), cnt + CNT_NEW);
+    rc = read_counters(ctx);
+    if (rc) return rc;
+    ctx->n_cyc = ctx->h_counters[CNT_CYC];
+    return O3R_OK;
+}
+
+// Applies the cycle's cell list to the resident shard: in-place update of found cells, sorted insert of new ones.
+int acc_apply_cycle(o3r_ctx* ctx) {
+    const uint32_t n_cyc = ctx->n_cyc, n_new = ctx->h_counters[CNT_NEW];
+    if (n_cyc == 0) return O3R_OK;
+    uint32_t* cnt = ctx->counters.as<uint32_t>();
+    const int cur = ctx->res_cur, nxt = cur ^ 1;
+    const uint32_t tiles = cdiv(n_cyc, kTileV);
+    CU(ctx->new_cnt.ensure((size_t)tiles * 4));
+    CU(ctx->new_off.ensure((size_t)tiles * 4));
+    LAUNCH(k_acc_update, tiles, kThreads, 0, n_cyc, ctx->cacc.as<float4>(), ctx->crgb.as<uint4>(),
+           ctx->res_acc[cur].as<float4>(), ctx->res_rgb[cur].as<uint4>(), ctx->new_cnt.as<uint32_t>());
+    if (n_new == 0) return O3R_OK;
+    const size_t tot = (size_t)ctx->n_res + n_new;
+    if (tot >= (1ull << 32)) return ctx->fail(O3R_ERR_NOMEM, "resident shard exceeds 2^32 cells");
+    CU(ctx->res_keys[nxt].ensure(tot * 8));
+    CU(ctx->res_acc[nxt].ensure(tot * 16));
+    CU(ctx->res_rgb[nxt].ensure(tot * 16));
+    CU(ctx->new_keys.ensure((size_t)n_new * 8));
+    LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->new_cnt.as<uint32_t>(), ctx->new_off.as<uint32_t>(), tiles,
+           cnt + CNT_NEWSCAN);
+    LAUNCH(k_acc_place_new, tiles, kThreads, 0, n_cyc, ctx->ckey.as<uint64_t>(), ctx->cacc.as<float4>(),
+           ctx->crgb.as<uint4>(), ctx->new_off.as<uint32_t>(), ctx->res_keys[cur].as<uint64_t>(), ctx->n_res,
+           ctx->res_keys[nxt].as<uint64_t>(), ctx->res_acc[nxt].as<float4>(), ctx->res_rgb[nxt].as<uint4>(),
+           ctx->new_keys.as<uint64_t>());
+    if (ctx->n_res) {
+        const uint32_t g = std::min<uint32_t>(cdiv(ctx->n_res, kThreads), 148 * 16);
+        LAUNCH(k_acc_place_old, g, kThreads, 0, ctx->n_res, ctx->res_keys[cur].as<uint64_t>(),
+               ctx->res_acc[cur].as<float4>(), ctx->res_rgb[cur].as<uint4>(), ctx->new_keys.as<uint64_t>(), n_new,
+               ctx->res_keys[nxt].as<uint64_t>(), ctx->res_acc[nxt].as<float4>(), ctx->res_rgb[nxt].as<uint4>());
+    }
+    ctx->res_cur = nxt;
+    ctx->n_res = (uint32_t)tot;
+    return O3R_OK;
+}
+
+int acc_merge_points(o3r_ctx* ctx, const float4* pts, size_t n) {
+    AccItemsPts items{pts};
+    int rc = acc_build_cycle(ctx, items, pts, nullptr, n, true);
+    if (rc) return rc;
+    return acc_apply_cycle(ctx);
+}
+
+int cloud_append_dev(o3r_ctx* ctx, const float4* pts, size_t n) {
+    if (n == 0) return O3R_OK;
+    CU(ctx->cloud.ensure((ctx->n_cloud + n) * 16, ctx->st, ctx->n_cloud * 16));
+    CU(cudaMemcpyAsync(ctx->cloud.as<float4>() + ctx->n_cloud, pts, n * 16, cudaMemcpyDeviceToDevice, ctx->st));
+    ctx->n_cloud += n;
+    return O3R_OK;
+}
+
+// ---- the batched per-frame path ------------------------------------------------------------------------------------
+struct BatchOpts {
+    bool merge = true;          // append / merge into the resident cloud
+    uint8_t* mask_dev = nullptr;  // optional validity mask output
+    bool mask_only = false;
+};
+
+template <int DT>
+int launch_stage_a(o3r_ctx* ctx, const AParams& P, int n, const BatchOpts& opt, SortU32& sb, size_t cap_batch) {
+    const FrameDev* fr = ctx->d_frames.as<FrameDev>();
+    const dim3 grid(P.tiles_per_frame, n);
+    uint32_t* cnt = ctx->counters.as<uint32_t>();
+    LAUNCH(k_bbox_init, cdiv((size_t)n * 6, kThreads), kThreads, 0, ctx->bbox.as<uint32_t>(), n);
+    LAUNCH((k_pre<DT>), grid, kThreads, 0, P, fr, ctx->tile_cnt.as<uint32_t>(), ctx->bbox.as<uint32_t>(), opt.mask_dev);
+    if (opt.mask_only) return O3R_OK;
+    LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->tile_cnt.as<uint32_t>(), ctx->tile_off.as<uint32_t>(),
+           (uint32_t)((size_t)P.tiles_per_frame * n), cnt + CNT_PTS);
+    LAUNCH(k_a_post, cdiv(n + 1, kThreads), kThreads, 0, n, P.tiles_per_frame, ctx->tile_off.as<uint32_t>(),
+           cnt + CNT_PTS, ctx->bbox.as<uint32_t>(), ctx->inv_f, ctx->inv_f, ctx->inv_f, P.want_keys,
+           ctx->frame_off.as<uint32_t>(), ctx->grids.as<GridParams>());
+    LAUNCH((k_emit<DT>), grid, kThreads, 0, P, fr, ctx->tile_off.as<uint32_t>(), ctx->frame_off.as<uint32_t>(),
+           ctx->grids.as<GridParams>(), ctx->pts.as<float4>(), sb.k0);
+    (void)cap_batch;
+    return O3R_OK;
+}
+
+// `frames` hold DEVICE pointers.
+int frames_cloud_dev_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_type, uint32_t* frame_counts,
+                          const BatchOpts& opt) {
+    const o3r_params& p = ctx->p;
+    if (n <= 0) { ctx->last_n = 0; ctx->last_total = 0; return O3R_OK; }
+    if (n > 65535) return ctx->fail(O3R_ERR_INVALID, "too many frames in one batch");
+    if (disp_type < 0 || disp_type > 3) return ctx->fail(O3R_ERR_INVALID, "bad disp_type");
+    const bool label_mode = p.use_segment_labels && frames[0].labels && frames[0].plane_coef;
+    if (p.use_segment_labels && !label_mode && disp_type != O3R_DISP_F64)
+        return ctx->fail(O3R_ERR_INVALID, "use_segment_labels needs an F64 disparity plane or labels + plane_coef");
+    const bool blur = p.blur_kernel > 1;
+    if (blur) {  // cv::bilateralFilter / medianBlur reject CV_64F: the reference throws and yields an empty cloud
+        if (disp_type != O3R_DISP_U8 || p.use_segment_labels)
+            return ctx->fail(O3R_ERR_INVALID, "blur_kernel > 1 requires u8 disparity (OpenCV rejects CV_64F)");
+        if (p.blur_mode == O3R_BLUR_MEDIAN && (p.blur_kernel & 1) == 0)
+            return ctx->fail(O3R_ERR_INVALID, "median blur needs an odd blur_kernel (cv::medianBlur asserts)");
+        if (p.blur_mode != O3R_BLUR_MEDIAN && p.blur_mode != O3R_BLUR_BOX)
+            return ctx->fail(O3R_ERR_INVALID, "unknown blur_mode");
+        if (p.blur_kernel > kBlurMaxK) return ctx->fail(O3R_ERR_INVALID, "blur_kernel too large (max 127)");
+    }
+    const int J = p.jump_pixels;
+    int max_kp = 0;
+    if (J != 1)
+        for (int i = 0; i < n; ++i) max_kp = std::max(max_kp, frames[i].kp_xy ? frames[i].n_kp : 0);
+
+    AParams P;
+    memset(&P, 0, sizeof(P));
+    P.rows = p.rows; P.cols = p.cols; P.x0 = p.cols_start_aft_cutout; P.bb = p.bounding_box; P.J = J;
+    P.nx = ctx->nx; P.ny = ctx->ny; P.npix = ctx->npix;
+    P.kp_tiles = (int)cdiv((size_t)max_kp, kTileA);
+    P.tiles_per_frame = P.kp_tiles + (int)cdiv(P.npix, kTileA);
+    P.label_mode = label_mode;
+    P.canon = ctx->canon;
+    P.use_lut = ctx->canon && disp_type == O3R_DISP_U8 && !label_mode;
+    P.thr_i = (int)std::floor(p.min_disparity);
+    P.min_disp = p.min_disparity; P.div = p.disp_divisor;
+    for (int i = 0; i < 16; ++i) P.q[i] = p.Q[i];
+    P.lut_r = ctx->lut_r.as<double>(); P.lut_z = ctx->lut_z.as<float>();
+    P.want_keys = !p.dont_downsample && !opt.mask_only;
+    P.want_bbox = P.want_keys;
+    if (P.tiles_per_frame == 0) {  // nothing to scan (J == 0 and no keypoints)
+        ctx->last_n = n; ctx->last_total = 0; ctx->last_off.assign(n + 1, 0);
+        if (frame_counts) std::fill(frame_counts, frame_counts + n, 0u);
+        return O3R_OK;
+    }
+
+    // frame descriptors
+    const size_t es = disp_elem(disp_type);
+    const size_t blur_step = ((size_t)p.cols + 15) & ~(size_t)15;
+    if (blur) CU(ctx->d_blur.ensure((size_t)n * p.rows * blur_step));
+    std::vector<FrameDev> fd(n);
+    std::vector<BlurJob> jobs(blur ? n : 0);
+    bool vec = (J == 1) && (ctx->nx % 4 == 0) && (P.x0 % 4 == 0) && !label_mode;
+    for (int i = 0; i < n; ++i) {
+        const o3r_frame& f = frames[i];
+        if (!f.bgr || (!f.disp && !label_mode)) return ctx->fail(O3R_ERR_INVALID, "frame without disparity/colour");
+        FrameDev& d = fd[i];
+        d.disp = (const uint8_t*)f.disp; d.disp_step = f.disp_step;
+        d.bgr = f.bgr; d.bgr_step = f.bgr_step;
+        d.labels = label_mode ? f.labels : nullptr; d.labels_step = f.labels_step;
+        d.plane_coef = label_mode ? f.plane_coef : nullptr; d.n_planes = label_mode ? f.n_planes : 0;
+        d.kp_xy = (J != 1) ? f.kp_xy : nullptr; d.n_kp = (J != 1 && f.kp_xy) ? f.n_kp : 0;
+        for (int k = 0; k < 12; ++k) d.T[k] = f.T[k];
+        if (blur) {
+            jobs[i].src = d.disp; jobs[i].sstep = d.disp_step;
+            jobs[i].dst = ctx->d_blur.as<uint8_t>() + (size_t)i * p.rows * blur_step; jobs[i].dstep = blur_step;
+            d.disp = jobs[i].dst; d.disp_step = blur_step;
+        }
+        if (!label_mode)
+            vec = vec && ((uintptr_t)d.disp % 16 == 0) && (d.disp_step % (4 * es) == 0);
+        vec = vec && ((uintptr_t)d.bgr % 4 == 0) && (d.bgr_step % 4 == 0);
+    }
+    P.vec = vec;
+    CU(ctx->d_frames.ensure((size_t)n * sizeof(FrameDev)));
+    CU(cudaMemcpyAsync(ctx->d_frames.p, fd.data(), (size_t)n * sizeof(FrameDev), cudaMemcpyHostToDevice, ctx->st));
+    if (blur) {
+        CU(ctx->d_blurjobs.ensure((size_t)n * sizeof(BlurJob)));
+        CU(cudaMemcpyAsync(ctx->d_blurjobs.p, jobs.data(), (size_t)n * sizeof(BlurJob), cudaMemcpyHostToDevice, ctx->st));
+        const int rx0 = P.x0, rx1 = p.cols - p.bounding_box, ry0 = p.bounding_box, ry1 = p.rows - p.bounding_box;
+        if (rx1 > rx0 && ry1 > ry0) {
+            const dim3 g(cdiv(rx1 - rx0, kBlurStrip), cdiv(ry1 - ry0, kBlurRows), n);
+            const size_t sm = blur_smem(p.blur_kernel, p.blur_mode);
+            if (p.blur_mode == O3R_BLUR_MEDIAN)
+                LAUNCH((k_blur<O3R_BLUR_MEDIAN>), g, kBlurRows, sm, ctx->d_blurjobs.as<BlurJob>(), p.rows, p.cols,
+                       p.blur_kernel, rx0, ry0, rx1, ry1);
+            else
+                LAUNCH((k_blur<O3R_BLUR_BOX>), g, kBlurRows, sm, ctx->d_blurjobs.as<BlurJob>(), p.rows, p.cols,
+                       p.blur_kernel, rx0, ry0, rx1, ry1);
+        }
+    }
+
+    // work buffers
+    const size_t per_frame_cap = (size_t)P.npix + (size_t)max_kp;
+    const size_t cap_batch = per_frame_cap * n;
+    if (cap_batch >= (1ull << 32)) return ctx->fail(O3R_ERR_INVALID, "batch exceeds 2^32 samples; use fewer frames");
+    const size_t n_tiles = (size_t)P.tiles_per_frame * n;
+    CU(ctx->tile_cnt.ensure(n_tiles * 4));
+    CU(ctx->tile_off.ensure(n_tiles * 4));
+    CU(ctx->bbox.ensure((size_t)n * 6 * 4));
+    CU(ctx->frame_off.ensure((size_t)(n + 1) * 4));
+    CU(ctx->grids.ensure((size_t)n * sizeof(GridParams)));
+    SortU32 sb{nullptr, nullptr, nullptr, nullptr};
+    if (!opt.mask_only) {
+        CU(ctx->pts.ensure(cap_batch * 16));
+        if (P.want_keys) { int rc = carve_sort_u32(ctx, cap_batch, sb); if (rc) return rc; }
+    }
+    int rc;
+    switch (disp_type) {
+        case O3R_DISP_U8: rc = launch_stage_a<O3R_DISP_U8>(ctx, P, n, opt, sb, cap_batch); break;
+        case O3R_DISP_U16: rc = launch_stage_a<O3R_DISP_U16>(ctx, P, n, opt, sb, cap_batch); break;
+        case O3R_DISP_F32: rc = launch_stage_a<O3R_DISP_F32>(ctx, P, n, opt, sb, cap_batch); break;
+        default: rc = launch_stage_a<O3R_DISP_F64>(ctx, P, n, opt, sb, cap_batch); break;
+    }
+    if (rc || opt.mask_only) return rc;
+
+    const uint32_t* off_dev = ctx->frame_off.as<uint32_t>();
+    ctx->last_is_vox = false;
+    if (P.want_keys) {  // per-frame VoxelGrid, leaf voxel_size / 5 (pose_functions.cpp:1698)
+        CU(ctx->vox.ensure(cap_batch * 16));
+        CU(ctx->vox_off.ensure((size_t)(n + 1) * 4));
+        rc = vg_sorted_reduce(ctx, sb, ctx->pts.as<float4>(), ctx->frame_off.as<uint32_t>(), n, per_frame_cap,
+                              ctx->grids.as<GridParams>(), ctx->inv_f, ctx->inv_f, ctx->inv_f, 0, 0,
+                              ctx->vox.as<float4>(), ctx->vox_off.as<uint32_t>(), nullptr, nullptr);
+        if (rc) return rc;
+        off_dev = ctx->vox_off.as<uint32_t>();
+        ctx->last_is_vox = true;
+    }
+    // per-frame output offsets back to the host (the one sync of the frame path)
+    if (ctx->h_offs_cap < (size_t)n + 1) {
+        if (ctx->h_offs) cudaFreeHost(ctx->h_offs);
+        ctx->h_offs_cap = std::max<size_t>(n + 1, 256);
+        CU(cudaMallocHost((void**)&ctx->h_offs, ctx->h_offs_cap * 4));
+    }
+    CU(cudaMemcpyAsync(ctx->h_offs, off_dev, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->last_off.assign(ctx->h_offs, ctx->h_offs + n + 1);
+    ctx->last_n = n;
+    ctx->last_total = ctx->last_off[n];
+    if (frame_counts)
+        for (int i = 0; i < n; ++i) frame_counts[i] = ctx->last_off[i + 1] - ctx->last_off[i];
+    if (!opt.merge || ctx->defer_merge) return O3R_OK;
+    const float4* outp = ctx->last_is_vox ? ctx->vox.as<float4>() : ctx->pts.as<float4>();
+    if (ctx->retain()) return cloud_append_dev(ctx, outp, ctx->last_total);
+    return acc_merge_points(ctx, outp, ctx->last_total);
+}
+
+// copies the frames' inputs to device staging and rewrites the pointers
+int stage_frames(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_type, std::vector<o3r_frame>& dev) {
+    const o3r_params& p = ctx->p;
+    const size_t es = disp_elem(disp_type);
+    const size_t dstep = (((size_t)p.cols * es) + 15) & ~(size_t)15, dplane = dstep * p.rows;
+    const size_t cstep = (((size_t)p.cols * 3) + 15) & ~(size_t)15, cplane = cstep * p.rows;
+    const size_t lstep = ((size_t)p.cols + 15) & ~(size_t)15, lplane = lstep * p.rows;
+    const bool label_mode = p.use_segment_labels && n > 0 && frames[0].labels && frames[0].plane_coef;
+    size_t kp_total = 0, coef_total = 0;
+    for (int i = 0; i < n; ++i) {
+        kp_total += (frames[i].kp_xy && frames[i].n_kp > 0) ? (size_t)frames[i].n_kp * 2 : 0;
+        coef_total += (label_mode && frames[i].n_planes > 0) ? (size_t)frames[i].n_planes * 3 : 0;
+    }
+    if (!label_mode) CU(ctx->d_disp.ensure(dplane * n));
+    CU(ctx->d_bgr.ensure(cplane * n));
+    if (label_mode) { CU(ctx->d_labels.ensure(lplane * n)); CU(ctx->d_coef.ensure(std::max<size_t>(coef_total, 1) * 8)); }
+    if (kp_total) CU(ctx->d_kp.ensure(kp_total * 4));
+    dev.assign(frames, frames + n);
+    size_t kp_at = 0, coef_at = 0;
+    for (int i = 0; i < n; ++i) {
+        const o3r_frame& f = frames[i];
+        o3r_frame& d = dev[i];
+        if (!f.bgr || (!f.disp && !label_mode)) return ctx->fail(O3R_ERR_INVALID, "frame without disparity/colour");
+        if (!label_mode) {
+            uint8_t* dd = ctx->d_disp.as<uint8_t>() + dplane * i;
+            CU(cudaMemcpy2DAsync(dd, dstep, f.disp, f.disp_step, (size_t)p.cols * es, p.rows, cudaMemcpyHostToDevice, ctx->st));
+            d.disp = dd; d.disp_step = dstep;
+        } else {
+            uint8_t* dl = ctx->d_labels.as<uint8_t>() + lplane * i;
+            CU(cudaMemcpy2DAsync(dl, lstep, f.labels, f.labels_step, (size_t)p.cols, p.rows, cudaMemcpyHostToDevice, ctx->st));
+            d.labels = dl; d.labels_step = lstep;
+            double* dc = ctx->d_coef.as<double>() + coef_at;
+            if (f.n_planes > 0)
+                CU(cudaMemcpyAsync(dc, f.plane_coef, (size_t)f.n_planes * 24, cudaMemcpyHostToDevice, ctx->st));
+            d.plane_coef = dc; coef_at += (size_t)std::max(f.n_planes, 0) * 3;
+            d.disp = nullptr;
+        }
+        uint8_t* dc = ctx->d_bgr.as<uint8_t>() + cplane * i;
+        CU(cudaMemcpy2DAsync(dc, cstep, f.bgr, f.bgr_step, (size_t)p.cols * 3, p.rows, cudaMemcpyHostToDevice, ctx->st));
+        d.bgr = dc; d.bgr_step = cstep;
+        if (f.kp_xy && f.n_kp > 0) {
+            float* dk = ctx->d_kp.as<float>() + kp_at;
+            CU(cudaMemcpyAsync(dk, f.kp_xy, (size_t)f.n_kp * 8, cudaMemcpyHostToDevice, ctx->st));
+            d.kp_xy = dk; kp_at += (size_t)f.n_kp * 2;
+        } else {
+            d.kp_xy = nullptr; d.n_kp = 0;
+        }
+    }
+    return O3R_OK;
+}
+
+int copy_out(o3r_ctx* ctx, const float4* src, size_t n, o3r_point* out, size_t cap, size_t* n_out) {
+    if (n_out) *n_out = n;
+    if (!out && cap == 0) return O3R_OK;
+    if (cap < n) return ctx->fail(O3R_ERR_CAPACITY, "output buffer too small");
+    if (n) {
+        CU(cudaMemcpyAsync(out, src, n * 16, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+    }
+    return O3R_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+int o3r_version(void) { return O3R_VERSION; }
+
+const char* o3r_last_error(const o3r_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int o3r_create(const o3r_params* params, o3r_ctx** out_ctx) {
+    if (!params || !out_ctx) { g_create_err = "null argument"; return O3R_ERR_INVALID; }
+    *out_ctx = nullptr;
+    const o3r_params& p = *params;
+    if (p.rows <= 0 || p.cols <= 0 || p.bounding_box < 0 || p.cols_start_aft_cutout < 0 || p.jump_pixels < 0 ||
+        !(p.voxel_size > 0) || p.max_batch_frames < 1) {
+        g_create_err = "invalid o3r_params";
+        return O3R_ERR_INVALID;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= p.device) {
+        g_create_err = std::string("no usable CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)";
+        return O3R_ERR_CUDA;
+    }
+    e = cudaSetDevice(p.device);
+    if (e != cudaSuccess) { g_create_err = cudaGetErrorString(e); return O3R_ERR_CUDA; }
+    o3r_ctx* ctx = new o3r_ctx();
+    ctx->p = p;
+    const int J = p.jump_pixels;
+    if (J > 0) {  // pose_functions.cpp:1094-1128
+        ctx->ny = std::max(0, (p.rows - 2 * p.bounding_box + J - 1) / J);
+        ctx->nx = std::max(0, (p.cols - p.bounding_box - p.cols_start_aft_cutout + J - 1) / J);
+    }
+    ctx->npix = (uint32_t)ctx->nx * (uint32_t)ctx->ny;
+    const double* Q = p.Q;
+    ctx->canon = Q[1] == 0 && Q[2] == 0 && Q[4] == 0 && Q[6] == 0 && Q[8] == 0 && Q[9] == 0 && Q[10] == 0 &&
+                 Q[12] == 0 && Q[13] == 0;
+    ctx->leaf_f = (float)(p.voxel_size / 5);          // pose_functions.cpp:1698
+    ctx->inv_f = 1.0f / ctx->leaf_f;                  // PCL: inverse_leaf_size_ = Ones / leaf_size_
+    ctx->leaf_c = (float)p.voxel_size;                // pose_functions.cpp:1694
+    ctx->inv_c = 1.0f / ctx->leaf_c;
+    ctx->inv_cz = 1.0f / 1000.0f;
+    auto bail = [&](cudaError_t er, const char* what) {
+        g_create_err = std::string(what) + ": " + cudaGetErrorString(er);
+        o3r_destroy(ctx);
+        return O3R_ERR_CUDA;
+    };
+    if ((e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+    if ((e = cudaMallocHost((void**)&ctx->h_counters, CNT_N * 4)) != cudaSuccess) return bail(e, "pinned");
+    if ((e = ctx->counters.ensure(CNT_N * 4)) != cudaSuccess) return bail(e, "counters");
+    if ((e = cudaMemsetAsync(ctx->counters.p, 0, CNT_N * 4, ctx->st)) != cudaSuccess) return bail(e, "memset");
+    // 1/(q14*d+q15) and (float)(q11 * that) for u8 disparities
+    double lr[256];
+    float lz[256];
+    for (int d = 0; d < 256; ++d) {
+        const double v3 = Q[14] * (double)d + Q[15];
+        lr[d] = 1.0 / v3;
+        lz[d] = (float)(Q[11] * lr[d]);
+    }
+    if ((e = ctx->lut_r.ensure(sizeof(lr))) != cudaSuccess) return bail(e, "lut");
+    if ((e = ctx->lut_z.ensure(sizeof(lz))) != cudaSuccess) return bail(e, "lut");
+    cudaMemcpyAsync(ctx->lut_r.p, lr, sizeof(lr), cudaMemcpyHostToDevice, ctx->st);
+    cudaMemcpyAsync(ctx->lut_z.p, lz, sizeof(lz), cudaMemcpyHostToDevice, ctx->st);
+    if ((e = cudaStreamSynchronize(ctx->st)) != cudaSuccess) return bail(e, "init sync");
+    e = cudaFuncSetAttribute(k_rs_scatter<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)rs_scatter_smem<uint64_t>());
+    if (e != cudaSuccess) return bail(e, "smem attr (is this an sm_100a device?)");
+    e = cudaFuncSetAttribute(k_rs_scatter<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)rs_scatter_smem<uint32_t>());
+    if (e != cudaSuccess) return bail(e, "smem attr");
+    const int bs = (int)blur_smem(kBlurMaxK, O3R_BLUR_MEDIAN);
+    cudaFuncSetAttribute(k_blur<O3R_BLUR_MEDIAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs);
+    cudaFuncSetAttribute(k_blur<O3R_BLUR_BOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs);
+    *out_ctx = ctx;
+    return O3R_OK;
+}
+
+void o3r_destroy(o3r_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->p.device);
+    if (ctx->st) cudaStreamSynchronize(ctx->st);
+    DevBuf* bufs[] = {&ctx->lut_r, &ctx->lut_z, &ctx->d_disp, &ctx->d_bgr, &ctx->d_labels, &ctx->d_coef, &ctx->d_kp,
+                      &ctx->d_frames, &ctx->d_blur, &ctx->d_blurjobs, &ctx->tile_cnt, &ctx->tile_off, &ctx->bbox,
+                      &ctx->frame_off, &ctx->grids, &ctx->counters, &ctx->pts, &ctx->sortbuf, &ctx->hist,
+                      &ctx->plan_all, &ctx->plan_v2, &ctx->ghist, &ctx->head_cnt, &ctx->head_off, &ctx->vox,
+                      &ctx->vox_off, &ctx->seg2, &ctx->tmat, &ctx->mask, &ctx->res_keys[0], &ctx->res_keys[1],
+                      &ctx->res_acc[0], &ctx->res_acc[1], &ctx->res_rgb[0], &ctx->res_rgb[1], &ctx->ckey, &ctx->cacc,
+                      &ctx->crgb, &ctx->new_cnt, &ctx->new_off, &ctx->new_keys, &ctx->okeys, &ctx->cloud};
+    for (DevBuf* b : bufs) b->release();
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_offs) cudaFreeHost(ctx->h_offs);
+    if (ctx->st) cudaStreamDestroy(ctx->st);
+    delete ctx;
+}
+
+uint64_t o3r_launch_count(const o3r_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* o3r_stream(o3r_ctx* ctx) { return ctx ? (void*)ctx->st : nullptr; }
+
+int o3r_sync(o3r_ctx* ctx) {
+    if (!ctx) return O3R_ERR_INVALID;
+    CU(cudaStreamSynchronize(ctx->st));
+    return O3R_OK;
+}
+
+int o3r_set_defer_merge(o3r_ctx* ctx, int defer) {
+    if (!ctx) return O3R_ERR_INVALID;
+    ctx->defer_merge = defer != 0;
+    return O3R_OK;
+}
+
+void* o3r_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void o3r_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int o3r_frames_cloud_dev(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_type, uint32_t* frame_counts) {
+    if (!ctx || (n > 0 && !frames)) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    return frames_cloud_dev_impl(ctx, frames, n, disp_type, frame_counts, BatchOpts());
+}
+
+int o3r_frames_cloud(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_type, uint32_t* frame_counts) {
+    if (!ctx || (n > 0 && !frames)) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    std::vector<o3r_frame> dev;
+    int rc = stage_frames(ctx, frames, n, disp_type, dev);
+    if (rc) return rc;
+    return frames_cloud_dev_impl(ctx, dev.data(), n, disp_type, frame_counts, BatchOpts());
+}
+
+int o3r_frame_cloud(o3r_ctx* ctx, const o3r_frame* frame, int disp_type, o3r_point* out, size_t cap, size_t* n_out) {
+    if (!ctx || !frame) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    if (n_out) *n_out = 0;
+    std::vector<o3r_frame> dev;
+    int rc = stage_frames(ctx, frame, 1, disp_type, dev);
+    if (rc) return rc;
+    BatchOpts opt;
+    opt.merge = false;
+    rc = frames_cloud_dev_impl(ctx, dev.data(), 1, disp_type, nullptr, opt);
+    if (rc) return rc;
+    const float4* src = ctx->last_is_vox ? ctx->vox.as<float4>() : ctx->pts.as<float4>();
+    return copy_out(ctx, src, ctx->last_total, out, cap, n_out);
+}
+
+int o3r_frame_mask(o3r_ctx* ctx, const o3r_frame* frame, int disp_type, uint8_t* mask, size_t cap, size_t* n_scanned) {
+    if (!ctx || !frame) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    if (n_scanned) *n_scanned = ctx->npix;
+    if (!mask && cap == 0) return O3R_OK;
+    if (cap < ctx->npix) return ctx->fail(O3R_ERR_CAPACITY, "mask buffer too small");
+    if (ctx->npix == 0) return O3R_OK;
+    std::vector<o3r_frame> dev;
+    int rc = stage_frames(ctx, frame, 1, disp_type, dev);
+    if (rc) return rc;
+    CU(ctx->mask.ensure(ctx->npix));
+    BatchOpts opt;
+    opt.merge = false; opt.mask_only = true; opt.mask_dev = ctx->mask.as<uint8_t>();
+    rc = frames_cloud_dev_impl(ctx, dev.data(), 1, disp_type, nullptr, opt);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(mask, ctx->mask.p, ctx->npix, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return O3R_OK;
+}
+
+int o3r_last_batch_points(o3r_ctx* ctx, o3r_point* out, size_t cap, size_t* n_out) {
+    if (!ctx) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    const float4* src = ctx->last_is_vox ? ctx->vox.as<float4>() : ctx->pts.as<float4>();
+    return copy_out(ctx, src, ctx->last_total, out, cap, n_out);
+}
+
+int o3r_cloud_transform(o3r_ctx* ctx, const float T[16]) {
+    if (!ctx || !T) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    if (!ctx->retain())
+        return ctx->fail(O3R_ERR_UNSUPPORTED,
+                         "o3r_cloud_transform needs O3R_MERGE_RETAIN: accumulated cells cannot be re-binned");
+    if (ctx->n_cloud == 0) return O3R_OK;
+    CU(ctx->tmat.ensure(64));
+    CU(cudaMemcpyAsync(ctx->tmat.p, T, 48, cudaMemcpyHostToDevice, ctx->st));
+    const uint32_t g = std::min<uint32_t>(cdiv(ctx->n_cloud, kThreads), 148 * 16);
+    LAUNCH(k_transform_pts, g, kThreads, 0, ctx->cloud.as<float4>(), ctx->n_cloud, ctx->tmat.as<float>());
+    return O3R_OK;
+}
+
+int o3r_cloud_append(o3r_ctx* ctx, const o3r_point* pts, size_t n) {
+    if (!ctx || (n && !pts)) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    if (n == 0) return O3R_OK;
+    if (ctx->retain()) {
+        CU(ctx->cloud.ensure((ctx->n_cloud + n) * 16, ctx->st, ctx->n_cloud * 16));
+        CU(cudaMemcpyAsync(ctx->cloud.as<float4>() + ctx->n_cloud, pts, n * 16, cudaMemcpyHostToDevice, ctx->st));
+        ctx->n_cloud += n;
+        return O3R_OK;
+    }
+    CU(ctx->vox.ensure(n * 16));
+    CU(cudaMemcpyAsync(ctx->vox.p, pts, n * 16, cudaMemcpyHostToDevice, ctx->st));
+    ctx->last_n = 0; ctx->last_total = 0;   // the batch buffer was overwritten
+    return acc_merge_points(ctx, ctx->vox.as<float4>(), n);
+}
+
+int o3r_cloud_size(o3r_ctx* ctx, size_t* n) {
+    if (!ctx || !n) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    *n = ctx->retain() ? ctx->n_cloud : ctx->n_res;
+    return O3R_OK;
+}
+
+int o3r_cloud_clear(o3r_ctx* ctx) {
+    if (!ctx) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->n_cloud = 0; ctx->n_res = 0;
+    return O3R_OK;
+}
+
+// engine 1 on an arbitrary device cloud of one segment
+static int voxel_grid_dev(o3r_ctx* ctx, const float4* pts, size_t n, float ix, float iy, float iz, uint32_t min_points,
+                          int z_shift, float4* out, uint64_t* out_keys, uint32_t* out_counts, size_t* n_out,
+                          int* passthrough) {
+    if (n >= (1ull << 32)) return ctx->fail(O3R_ERR_INVALID, "cloud too large for 32-bit indices");
+    uint32_t* cnt = ctx->counters.as<uint32_t>();
+    CU(ctx->seg2.ensure(16));
+    const uint32_t seg_h[2] = {0u, (uint32_t)n};
+    CU(cudaMemcpyAsync(ctx->seg2.p, seg_h, 8, cudaMemcpyHostToDevice, ctx->st));
+    const uint32_t* seg = ctx->seg2.as<uint32_t>();
+    CU(ctx->bbox.ensure(6 * 4));
+    CU(ctx->grids.ensure(sizeof(GridParams)));
+    CU(ctx->vox_off.ensure(2 * 4));
+    SortU32 sb;
+    int rc = carve_sort_u32(ctx, n, sb);
+    if (rc) return rc;
+    const uint32_t tiles = cdiv(n, kTileV);
+    LAUNCH(k_bbox_init, 1, kThreads, 0, ctx->bbox.as<uint32_t>(), 1);
+    LAUNCH(k_bbox_pts, dim3(tiles, 1), kThreads, 0, pts, seg, z_shift, ctx->bbox.as<uint32_t>());
+    LAUNCH(k_grid_params, 1, 32, 0, 1, ctx->bbox.as<uint32_t>(), ix, iy, iz, ctx->grids.as<GridParams>());
+    LAUNCH(k_vg_key, dim3(std::min<uint32_t>(cdiv(n, kThreads), 148 * 16), 1), kThreads, 0, pts, seg,
+           ctx->grids.as<GridParams>(), z_shift, sb.k0);
+    rc = vg_sorted_reduce(ctx, sb, pts, seg, 1, n, ctx->grids.as<GridParams>(), ix, iy, iz, min_points, z_shift, out,
+                          ctx->vox_off.as<uint32_t>(), out_keys, out_counts);
+    if (rc) return rc;
+    GridParams g;
+    CU(cudaMemcpyAsync(&g, ctx->grids.p, sizeof(g), cudaMemcpyDeviceToHost, ctx->st));
+    rc = read_counters(ctx);
+    if (rc) return rc;
+    (void)cnt;
+    *n_out = ctx->h_counters[CNT_VOX];
+    if (passthrough) *passthrough = g.passthrough;
+    return O3R_OK;
+}
+
+int o3r_cloud_downsample(o3r_ctx* ctx, o3r_point* out, size_t cap, size_t* n_out) {
+    if (!ctx) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    if (n_out) *n_out = 0;
+    if (ctx->p.dont_downsample)  // pose.cpp:533-536: cloud_small = cloud_big
+        return copy_out(ctx, ctx->cloud.as<float4>(), ctx->n_cloud, out, cap, n_out);
+    uint32_t* cnt = ctx->counters.as<uint32_t>();
+    if (ctx->retain()) {  // one-shot pcl::VoxelGrid over cloud_big, exactly pose_functions.cpp:1654-1709
+        if (ctx->n_cloud == 0) return O3R_OK;
+        // the batch output buffer is reused as the result buffer; the last batch is no longer retrievable
+        CU(ctx->ckey.ensure(ctx->n_cloud * 16));   // result points (<= n_cloud)
+        size_t m = 0;
+        int rc = voxel_grid_dev(ctx, ctx->cloud.as<float4>(), ctx->n_cloud, ctx->inv_c, ctx->inv_c, ctx->inv_cz,
+                                ctx->p.min_points_per_voxel, 1, ctx->ckey.as<float4>(), nullptr, nullptr, &m, nullptr);
+        if (rc) return rc;
+        return copy_out(ctx, ctx->ckey.as<float4>(), m, out, cap, n_out);
+    }
+    if (ctx->n_res == 0) return O3R_OK;
+    const int cur = ctx->res_cur;
+    const uint32_t tiles = cdiv(ctx->n_res, kTileV);
+    CU(ctx->new_cnt.ensure((size_t)tiles * 4));
+    CU(ctx->new_off.ensure((size_t)tiles * 4));
+    LAUNCH(k_acc_emit_cnt, tiles, kThreads, 0, ctx->n_res, ctx->res_acc[cur].as<float4>(), ctx->p.min_points_per_voxel,
+           ctx->new_cnt.as<uint32_t>());
+    LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->new_cnt.as<uint32_t>(), ctx->new_off.as<uint32_t>(), tiles, cnt + CNT_EMIT);
+    int rc = read_counters(ctx);
+    if (rc) return rc;
+    const size_t m = ctx->h_counters[CNT_EMIT];
+    if (n_out) *n_out = m;
+    if (!out && cap == 0) return O3R_OK;
+    if (cap < m) return ctx->fail(O3R_ERR_CAPACITY, "output buffer too small");
+    if (m == 0) return O3R_OK;
+    CU(ctx->cacc.ensure(m * 16));
+    LAUNCH(k_acc_emit, tiles, kThreads, 0, ctx->n_res, ctx->res_acc[cur].as<float4>(), ctx->res_rgb[cur].as<uint4>(),
+           ctx->p.min_points_per_voxel, ctx->new_off.as<uint32_t>(), ctx->cacc.as<float4>());
+    return copy_out(ctx, ctx->cacc.as<float4>(), m, out, cap, n_out);
+}
+
+int o3r_voxel_grid(o3r_ctx* ctx, const o3r_point* pts, size_t n, float lx, float ly, float lz, unsigned min_points,
+                   o3r_point* out, size_t cap, size_t* n_out, uint64_t* keys, uint32_t* counts, int* passthrough) {
+    if (!ctx || !n_out || (n && !pts)) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    *n_out = 0;
+    if (passthrough) *passthrough = 0;
+    if (n == 0) return O3R_OK;
+    if (!(lx > 0) || !(ly > 0) || !(lz > 0)) return ctx->fail(O3R_ERR_INVALID, "leaf size must be positive");
+    CU(ctx->pts.ensure(n * 16));
+    CU(ctx->vox.ensure(n * 16));
+    CU(ctx->ckey.ensure(n * 8));
+    CU(ctx->new_keys.ensure(n * 4));
+    ctx->last_n = 0; ctx->last_total = 0;
+    CU(cudaMemcpyAsync(ctx->pts.p, pts, n * 16, cudaMemcpyHostToDevice, ctx->st));
+    size_t m = 0;
+    int rc = voxel_grid_dev(ctx, ctx->pts.as<float4>(), n, 1.0f / lx, 1.0f / ly, 1.0f / lz, min_points, 0,
+                            ctx->vox.as<float4>(), ctx->ckey.as<uint64_t>(), ctx->new_keys.as<uint32_t>(), &m, passthrough);
+    if (rc) return rc;
+    *n_out = m;
+    if (!out && cap == 0) return O3R_OK;
+    if (cap < m) return ctx->fail(O3R_ERR_CAPACITY, "output buffer too small");
+    if (m) {
+        CU(cudaMemcpyAsync(out, ctx->vox.p, m * 16, cudaMemcpyDeviceToHost, ctx->st));
+        if (keys) CU(cudaMemcpyAsync(keys, ctx->ckey.p, m * 8, cudaMemcpyDeviceToHost, ctx->st));
+        if (counts) CU(cudaMemcpyAsync(counts, ctx->new_keys.p, m * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+    }
+    return O3R_OK;
+}
+
+int o3r_blur_u8(o3r_ctx* ctx, const uint8_t* src, size_t src_step, int rows, int cols, int kernel, int mode,
+                uint8_t* dst, size_t dst_step) {
+    if (!ctx || !src || !dst || rows <= 0 || cols <= 0) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    if (kernel < 1 || kernel > kBlurMaxK) return ctx->fail(O3R_ERR_INVALID, "kernel must be in 1..127");
+    if (mode == O3R_BLUR_MEDIAN && (kernel & 1) == 0)
+        return ctx->fail(O3R_ERR_INVALID, "median blur needs an odd kernel (cv::medianBlur asserts)");
+    if (mode != O3R_BLUR_MEDIAN && mode != O3R_BLUR_BOX) return ctx->fail(O3R_ERR_INVALID, "unknown blur mode");
+    const size_t step = ((size_t)cols + 15) & ~(size_t)15, plane = step * rows;
+    CU(ctx->d_disp.ensure(plane));
+    CU(ctx->d_blur.ensure(plane));
+    CU(ctx->d_blurjobs.ensure(sizeof(BlurJob)));
+    CU(cudaMemcpy2DAsync(ctx->d_disp.p, step, src, src_step, cols, rows, cudaMemcpyHostToDevice, ctx->st));
+    BlurJob job{ctx->d_disp.as<uint8_t>(), step, ctx->d_blur.as<uint8_t>(), step};
+    CU(cudaMemcpyAsync(ctx->d_blurjobs.p, &job, sizeof(job), cudaMemcpyHostToDevice, ctx->st));
+    const dim3 g(cdiv(cols, kBlurStrip), cdiv(rows, kBlurRows), 1);
+    const size_t sm = blur_smem(kernel, mode);
+    if (mode == O3R_BLUR_MEDIAN)
+        LAUNCH((k_blur<O3R_BLUR_MEDIAN>), g, kBlurRows, sm, ctx->d_blurjobs.as<BlurJob>(), rows, cols, kernel, 0, 0, cols, rows);
+    else
+        LAUNCH((k_blur<O3R_BLUR_BOX>), g, kBlurRows, sm, ctx->d_blurjobs.as<BlurJob>(), rows, cols, kernel, 0, 0, cols, rows);
+    CU(cudaMemcpy2DAsync(dst, dst_step, ctx->d_blur.p, step, cols, rows, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return O3R_OK;
+}
+
+int o3r_exchange_pack(o3r_ctx* ctx, int world, o3r_cell* send_dev, size_t cap, uint32_t* counts) {
+    if (!ctx || world < 1 || world > 256 || !counts) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    if (ctx->retain()) return ctx->fail(O3R_ERR_UNSUPPORTED, "exchange needs O3R_MERGE_ACCUMULATE");
+    std::fill(counts, counts + world, 0u);
+    if (!ctx->last_is_vox || ctx->last_total == 0) { ctx->n_cyc = 0; return O3R_OK; }
+    AccItemsPts items{ctx->vox.as<float4>()};
+    int rc = acc_build_cycle(ctx, items, ctx->vox.as<float4>(), nullptr, ctx->last_total, false);
+    if (rc) return rc;
+    const uint32_t n = ctx->n_cyc;
+    if (n == 0) return O3R_OK;
+    if (cap < n) return ctx->fail(O3R_ERR_CAPACITY, "send buffer too small");
+    // one stable radix pass on the owner id buckets the (key-sorted) cells by destination rank
+    SortU32 sb;
+    rc = carve_sort_u32(ctx, n, sb);
+    if (rc) return rc;
+    CU(ctx->okeys.ensure(256 * 4 + sizeof(SortPlan)));
+    uint32_t* ocnt = ctx->okeys.as<uint32_t>();
+    SortPlan* plan = reinterpret_cast<SortPlan*>(ocnt + 256);
+    SortPlan pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.active[0] = 1; pl.final_parity = 1; pl.n_active = 1;
+    CU(cudaMemsetAsync(ocnt, 0, 256 * 4, ctx->st));
+    CU(cudaMemcpyAsync(plan, &pl, sizeof(pl), cudaMemcpyHostToDevice, ctx->st));
+    const uint32_t seg_h[2] = {0u, n};
+    CU(cudaMemcpyAsync(ctx->seg2.p, seg_h, 8, cudaMemcpyHostToDevice, ctx->st));
+    const uint32_t g = std::min<uint32_t>(cdiv(n, kThreads), 148 * 8);
+    LAUNCH(k_owner, g, kThreads, 0, n, ctx->ckey.as<uint64_t>(), (uint32_t)world, sb.k0, sb.v0, ocnt);
+    rc = sort_pairs<uint32_t>(ctx, sb.k0, sb.k1, sb.v0, sb.v1, ctx->seg2.as<uint32_t>(), 1, n, plan, 1, 0);
+    if (rc) return rc;
+    LAUNCH(k_pack_cells, g, kThreads, 0, n, sb.v1, ctx->ckey.as<uint64_t>(), ctx->cacc.as<float4>(),
+           ctx->crgb.as<uint4>(), send_dev);
+    CU(cudaMemcpyAsync(counts, ocnt, (size_t)world * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return O3R_OK;
+}
+
+int o3r_exchange_merge(o3r_ctx* ctx, const o3r_cell* recv_dev, size_t n) {
+    if (!ctx || (n && !recv_dev)) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    if (ctx->retain()) return ctx->fail(O3R_ERR_UNSUPPORTED, "exchange needs O3R_MERGE_ACCUMULATE");
+    if (n == 0) return O3R_OK;
+    AccItemsCells items{recv_dev};
+    int rc = acc_build_cycle(ctx, items, nullptr, recv_dev, n, true);
+    if (rc) return rc;
+    return acc_apply_cycle(ctx);
+}
+
+}  // extern "C"

@@ -1,0 +1,164 @@
+"""Host-side mirror of the reference's `Pose` hot-path interface over the C-ABI (include/o3r.h).
+
+Method names follow the reference so the parity tests read like the reference's own call sites:
+
+    createAndTransformPtCloud   pose.cpp:596-636
+    createCycleClouds           pose.cpp:361-434   (the 7-thread fan-out + ordered concat + append)
+    transformPtCloud            pose.cpp:350-354   (cloud_big <- tf_icp * cloud_big)
+    downsamplePtCloud           pose_functions.cpp:1654-1709 (combinedPtCloud = true)
+
+Everything computes on the GPU through libo3r.so; numpy only carries buffers across the boundary.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi, lib
+
+
+class Pose:
+    """One reconstruction context (= the read-only `Pose` state after populateData + the global cloud)."""
+
+    def __init__(self, params=None, **kw):
+        self._L = lib.load()
+        self.params = params if params is not None else abi.make_params(**kw)
+        h = C.c_void_p()
+        rc = self._L.o3r_create(C.byref(self.params), C.byref(h))
+        if rc != 0:
+            raise lib.O3RError(rc, self._L.o3r_last_error(None).decode())
+        self._h = h
+
+    # -- plumbing ------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.o3r_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise lib.O3RError(rc, self._L.o3r_last_error(self._h).decode())
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def max_points_per_frame(self):
+        ny, nx = abi.scan_dims(self.params)
+        return ny * nx
+
+    def launch_count(self):
+        return int(self._L.o3r_launch_count(self._h))
+
+    def stream(self):
+        return self._L.o3r_stream(self._h)
+
+    def sync(self):
+        self._check(self._L.o3r_sync(self._h))
+
+    # -- per-frame path --------------------------------------------------------------------------------
+    def createAndTransformPtCloud(self, frame, disp_type=abi.DISP_U8):
+        """pose.cpp:596-636 for one accepted image -> structured array of abi.POINT."""
+        cap = max(1, self.max_points_per_frame + (frame.n_kp if self.params.jump_pixels != 1 else 0))
+        out = np.empty(cap, dtype=abi.POINT)
+        n = C.c_size_t(0)
+        self._check(self._L.o3r_frame_cloud(self._h, C.byref(frame), disp_type, out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def validityMask(self, frame, disp_type=abi.DISP_U8):
+        """The `disp > minDisparity` mask of the grid scan (pose_functions.cpp:1094-1107), row-major (ny, nx)."""
+        ny, nx = abi.scan_dims(self.params)
+        mask = np.zeros(max(1, ny * nx), dtype=np.uint8)
+        n = C.c_size_t(0)
+        self._check(self._L.o3r_frame_mask(self._h, C.byref(frame), disp_type, mask.ctypes.data, mask.size, C.byref(n)))
+        return mask[:n.value].reshape(ny, nx)
+
+    def createCycleClouds(self, frames, disp_type=abi.DISP_U8, device_pointers=False):
+        """pose.cpp:361-434: all accepted frames of a cycle, concatenated in order and appended to the
+        global cloud.  Returns the per-frame point counts."""
+        n = len(frames)
+        arr = frames if isinstance(frames, C.Array) else (abi.Frame * n)(*frames)
+        counts = np.zeros(max(n, 1), dtype=np.uint32)
+        fn = self._L.o3r_frames_cloud_dev if device_pointers else self._L.o3r_frames_cloud
+        self._check(fn(self._h, arr, n, disp_type, counts.ctypes.data))
+        return counts[:n]
+
+    def lastCyclePoints(self):
+        n = C.c_size_t(0)
+        self._check(self._L.o3r_last_batch_points(self._h, None, 0, C.byref(n)))
+        out = np.empty(max(1, n.value), dtype=abi.POINT)
+        self._check(self._L.o3r_last_batch_points(self._h, out.ctypes.data, out.size, C.byref(n)))
+        return out[:n.value]
+
+    # -- global cloud ------------------------------------------------------------------------------------
+    def transformPtCloud(self, T):
+        """pose.cpp:353 transformPtCloud(cloud_big, cloud_big, tf_icp) — RETAIN mode only."""
+        Tc = (C.c_float * 16)(*np.asarray(T, dtype=np.float32).reshape(16))
+        self._check(self._L.o3r_cloud_transform(self._h, Tc))
+
+    def appendPoints(self, pts):
+        pts = np.ascontiguousarray(pts, dtype=abi.POINT)
+        self._check(self._L.o3r_cloud_append(self._h, pts.ctypes.data, pts.size))
+
+    def cloudSize(self):
+        n = C.c_size_t(0)
+        self._check(self._L.o3r_cloud_size(self._h, C.byref(n)))
+        return n.value
+
+    def clearCloud(self):
+        self._check(self._L.o3r_cloud_clear(self._h))
+
+    def downsamplePtCloud(self, out=None):
+        """pose_functions.cpp:1654-1709 with combinedPtCloud = true on the global cloud (pose.cpp:530)."""
+        n = C.c_size_t(0)
+        if out is None:
+            self._check(self._L.o3r_cloud_downsample(self._h, None, 0, C.byref(n)))
+            out = np.empty(max(1, n.value), dtype=abi.POINT)
+        self._check(self._L.o3r_cloud_downsample(self._h, out.ctypes.data, out.size, C.byref(n)))
+        return out[:n.value]
+
+    # -- stand-alone stages --------------------------------------------------------------------------------
+    def voxelGrid(self, pts, leaf, min_points=0):
+        """pcl::VoxelGrid on a host cloud -> (points, keys u64, counts u32, passthrough)."""
+        pts = np.ascontiguousarray(pts, dtype=abi.POINT)
+        n = pts.size
+        out = np.empty(max(1, n), dtype=abi.POINT)
+        keys = np.empty(max(1, n), dtype=np.uint64)
+        counts = np.empty(max(1, n), dtype=np.uint32)
+        m, pt = C.c_size_t(0), C.c_int(0)
+        lx, ly, lz = (np.float32(v) for v in leaf)
+        self._check(self._L.o3r_voxel_grid(self._h, pts.ctypes.data, n, lx, ly, lz, min_points, out.ctypes.data,
+                                           out.size, C.byref(m), keys.ctypes.data, counts.ctypes.data, C.byref(pt)))
+        k = m.value
+        return out[:k].copy(), keys[:k].copy(), counts[:k].copy(), bool(pt.value)
+
+    def blur(self, src, kernel, mode):
+        src = np.ascontiguousarray(src, dtype=np.uint8)
+        dst = np.empty_like(src)
+        self._check(self._L.o3r_blur_u8(self._h, src.ctypes.data, src.strides[0], src.shape[0], src.shape[1], kernel,
+                                        mode, dst.ctypes.data, dst.strides[0]))
+        return dst
+
+    # -- multi-GPU exchange (device buffers are torch tensors owned by the caller) -----------------------------
+    def setDeferMerge(self, defer):
+        self._check(self._L.o3r_set_defer_merge(self._h, int(defer)))
+
+    def exchangePack(self, world, send_ptr, cap):
+        counts = np.zeros(world, dtype=np.uint32)
+        self._check(self._L.o3r_exchange_pack(self._h, world, send_ptr, cap, counts.ctypes.data))
+        return counts
+
+    def exchangeMerge(self, recv_ptr, n):
+        self._check(self._L.o3r_exchange_merge(self._h, recv_ptr, n))

@@ -549,4 +549,15 @@ int orc_plane_fit(const o3r_params* p, const uint8_t* labels, size_t labels_step
     return O3R_OK;
 }
 
+/* struct sizes as the C compiler lays them out (tests compare with the ctypes mirror) */
+size_t orc_sizeof(int which) {
+    switch (which) {
+        case 0: return sizeof(o3r_params);
+        case 1: return sizeof(o3r_frame);
+        case 2: return sizeof(o3r_point);
+        case 3: return sizeof(o3r_cell);
+        default: return 0;
+    }
+}
+
 }  /* extern "C" */

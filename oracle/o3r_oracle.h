@@ -78,6 +78,8 @@ double orc_get_variance(const o3r_params* p, const void* img, size_t step, int p
 /* 64-bit absolute cell key of one point on a grid (SURVEY §8a row VG). */
 uint64_t orc_cell_key(float x, float y, float z, float lx, float ly, float lz);
 
+size_t orc_sizeof(int which);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,392 @@
+"""GPU parity: the CUDA path (through the C-ABI, libo3r.so) against the CPU oracle on the same inputs.
+
+Bar (north_star): validity masks, voxel keys, per-voxel counts, colours and output ORDER bit-exact;
+coordinates / centroids within 1e-5 relative.  On one GPU the implementation is designed to be
+bit-exact for coordinates and centroids too (stable sort + in-order sums), and the tests assert that;
+the 1e-5 tolerance is only needed across ranks (test_exchange_two_ranks).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+from online_3d_reconstruction_b200 import abi, synth
+from online_3d_reconstruction_b200.pose import Pose
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(rows=120, cols=200)   # x0 = 25 (unaligned), ROI 155 x 80
+SMALL4 = dict(rows=128, cols=256)  # x0 = 32, nx = 204 -> vectorised path
+
+
+def _frames(seed, n, rows, cols, disp_type=abi.DISP_U8, keep=None, n_kp=0, traj_start=0):
+    seq = synth.sequence(seed, n, rows, cols, disp_type=disp_type, traj_start=traj_start)
+    rng = np.random.default_rng(seed + 1)
+    out = []
+    for d, img, T in seq:
+        kp = None
+        if n_kp:
+            kp = np.stack([rng.uniform(-5, cols + 5, n_kp), rng.uniform(-5, rows + 5, n_kp)], 1).astype(np.float32)
+        out.append(abi.make_frame(d, img, T, kp_xy=kp, keep=keep))
+    return out
+
+
+def _eq(a, b):
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if not np.array_equal(a, b):
+        bad = np.nonzero(a.view(np.uint32).reshape(-1, 4) != b.view(np.uint32).reshape(-1, 4))[0]
+        raise AssertionError(f"{len(np.unique(bad))} of {len(a)} records differ; first at {bad[0]}: {a[bad[0]]} vs {b[bad[0]]}")
+
+
+@pytest.fixture(scope="module")
+def real(golden_dir):
+    return np.load(os.path.join(golden_dir, "real_frames.npz"))
+
+
+# ---------------------------------------------------------------------------------------------- masks
+@pytest.mark.parametrize("J", [1, 3, 15])
+@pytest.mark.parametrize("geom", [SMALL, SMALL4])
+def test_mask_bit_exact(J, geom):
+    keep = []
+    p = abi.make_params(jump_pixels=J, **geom)
+    fr = _frames(11, 1, geom["rows"], geom["cols"], keep=keep)[0]
+    _, mask = ob.create_single_img_pt_cloud(p, fr, abi.DISP_U8, want_mask=True)
+    with Pose(p) as P:
+        got = P.validityMask(fr)
+    assert np.array_equal(got.ravel(), mask)
+
+
+def test_mask_counts_match_reference_log_720p(real):
+    """The reference logged 747674 / 747512 / 747783 valid pixels for frames 1248 / 1249 / 1251
+    (--use_segment_labels, jump_pixels 1): labels + per-label plane coefficients evaluated in the kernel."""
+    p = abi.make_params(jump_pixels=1, use_segment_labels=True, dont_downsample=True)
+    with Pose(p) as P:
+        for i in range(3):
+            coef, f64 = ob.plane_fit(p, real["labels"][i], real["disp"][i])
+            keep = []
+            fr = abi.make_frame(None, real["bgr1248"], np.eye(4), labels=real["labels"][i], plane_coef=coef, keep=keep)
+            m = P.validityMask(fr, abi.DISP_F64)
+            assert int(m.sum()) == int(real["point_cloud_pts"][i])
+            fr64 = abi.make_frame(f64, real["bgr1248"], np.eye(4), keep=keep)
+            pts = P.createAndTransformPtCloud(fr64, abi.DISP_F64)
+            exp = ob.create_and_transform_pt_cloud(p, fr64, abi.DISP_F64)
+            _eq(pts, exp)
+            _eq(P.createAndTransformPtCloud(fr, abi.DISP_F64), exp)
+
+
+# ------------------------------------------------------------------------------- points (no downsample)
+@pytest.mark.parametrize("J,n_kp", [(1, 0), (1, 50), (7, 300), (0, 1500), (15, 1500)])
+@pytest.mark.parametrize("geom", [SMALL, SMALL4])
+def test_points_bit_exact_dont_downsample(J, n_kp, geom):
+    keep = []
+    p = abi.make_params(jump_pixels=J, dont_downsample=True, **geom)
+    fr = _frames(5, 1, geom["rows"], geom["cols"], keep=keep, n_kp=n_kp)[0]
+    exp = ob.create_and_transform_pt_cloud(p, fr, abi.DISP_U8)
+    with Pose(p) as P:
+        got = P.createAndTransformPtCloud(fr)
+    _eq(got, exp)
+
+
+@pytest.mark.parametrize("disp_type", [abi.DISP_U16, abi.DISP_F32, abi.DISP_F64])
+@pytest.mark.parametrize("geom", [SMALL, SMALL4])
+def test_points_other_disparity_types(disp_type, geom):
+    keep = []
+    p = abi.make_params(jump_pixels=1, dont_downsample=True, **geom)
+    fr = _frames(6, 1, geom["rows"], geom["cols"], disp_type=disp_type, keep=keep)[0]
+    exp = ob.create_and_transform_pt_cloud(p, fr, disp_type)
+    with Pose(p) as P:
+        got = P.createAndTransformPtCloud(fr, disp_type)
+    assert len(exp) > 1000
+    _eq(got, exp)
+
+
+def test_points_generic_Q():
+    """A Q without the rectified-stereo sparsity takes the generic 4x4 path."""
+    keep = []
+    Q = list(abi.Q_CAM13)
+    Q[1], Q[6], Q[9], Q[12], Q[15] = 1e-3, -2e-3, 5e-4, 1e-5, 0.25
+    p = abi.make_params(jump_pixels=1, dont_downsample=True, Q=tuple(Q), **SMALL4)
+    fr = _frames(7, 1, SMALL4["rows"], SMALL4["cols"], keep=keep)[0]
+    exp = ob.create_and_transform_pt_cloud(p, fr, abi.DISP_U8)
+    with Pose(p) as P:
+        got = P.createAndTransformPtCloud(fr)
+    _eq(got, exp)
+
+
+def test_real_frame_720p_dense(real):
+    keep = []
+    p = abi.make_params(jump_pixels=1, voxel_size=0.05)
+    T = synth.trajectory(np.random.default_rng(3), 1)[0]
+    fr = abi.make_frame(real["disp"][0], real["bgr1248"], T, keep=keep)
+    exp = ob.create_and_transform_pt_cloud(p, fr, abi.DISP_U8)
+    with Pose(p) as P:
+        got = P.createAndTransformPtCloud(fr)
+    assert 200000 < len(exp) < 400000
+    _eq(got, exp)
+
+
+def test_empty_frame_and_empty_batch():
+    keep = []
+    p = abi.make_params(jump_pixels=1, **SMALL)
+    fr = abi.make_frame(np.zeros((120, 200), np.uint8), np.zeros((120, 200, 3), np.uint8), np.eye(4), keep=keep)
+    with Pose(p) as P:
+        assert len(P.createAndTransformPtCloud(fr)) == 0
+        assert P.createCycleClouds([fr]).tolist() == [0]
+        assert len(P.createCycleClouds([])) == 0
+        assert len(P.downsamplePtCloud()) == 0
+
+
+# ------------------------------------------------------------------------------------- per-frame VoxelGrid
+@pytest.mark.parametrize("voxel_size", [0.05, 0.1, 0.5])
+@pytest.mark.parametrize("geom", [SMALL, SMALL4])
+def test_per_frame_voxelgrid_bit_exact(voxel_size, geom):
+    keep = []
+    p = abi.make_params(jump_pixels=1, voxel_size=voxel_size, **geom)
+    fr = _frames(21, 1, geom["rows"], geom["cols"], keep=keep)[0]
+    exp = ob.create_and_transform_pt_cloud(p, fr, abi.DISP_U8)
+    with Pose(p) as P:
+        got = P.createAndTransformPtCloud(fr)
+    assert 0 < len(exp)
+    _eq(got, exp)
+
+
+def test_per_frame_voxelgrid_overflow_passthrough():
+    """voxel_size 0.01 -> leaf 0.002: PCL's int32 guard returns the input unchanged (config 5)."""
+    keep = []
+    p = abi.make_params(jump_pixels=1, voxel_size=0.01, **SMALL4)
+    fr = _frames(22, 1, SMALL4["rows"], SMALL4["cols"], keep=keep)[0]
+    p_nd = abi.make_params(jump_pixels=1, voxel_size=0.01, dont_downsample=True, **SMALL4)
+    raw = ob.create_and_transform_pt_cloud(p_nd, fr, abi.DISP_U8)
+    exp = ob.create_and_transform_pt_cloud(p, fr, abi.DISP_U8)
+    _eq(exp, raw)  # the oracle itself passes through
+    with Pose(p) as P:
+        got = P.createAndTransformPtCloud(fr)
+    _eq(got, exp)
+
+
+@pytest.mark.parametrize("leaf,min_points", [((0.05, 0.05, 0.05), 0), ((0.3, 0.2, 0.1), 2), ((0.05, 0.05, 1000.0), 3),
+                                             ((0.001, 0.001, 0.001), 0)])
+def test_voxel_grid_probe_keys_counts_points(leaf, min_points):
+    rng = np.random.default_rng(8)
+    n = 200000
+    pts = np.zeros(n, dtype=abi.POINT)
+    pts["x"] = rng.uniform(-8, 12, n).astype(np.float32)
+    pts["y"] = rng.uniform(-3, 9, n).astype(np.float32)
+    pts["z"] = rng.normal(0, 0.3, n).astype(np.float32)
+    pts["rgb"] = rng.integers(0, 1 << 24, n, dtype=np.uint32)
+    e_pts, e_keys, e_cnt, e_pass = ob.voxel_grid(pts, leaf, min_points)
+    with Pose(abi.make_params(**SMALL)) as P:
+        g_pts, g_keys, g_cnt, g_pass = P.voxelGrid(pts, leaf, min_points)
+    assert g_pass == e_pass
+    assert np.array_equal(g_keys, e_keys)
+    assert np.array_equal(g_cnt, e_cnt)
+    _eq(g_pts, e_pts)
+
+
+def test_voxel_grid_reproduces_reference_cloud_ply(golden_dir):
+    g = np.load(os.path.join(golden_dir, "cloud_ply.npz"))
+    pts = np.zeros(len(g["xyz"]), dtype=abi.POINT)
+    pts["x"], pts["y"], pts["z"] = g["xyz"].T
+    rgb = g["rgb"].astype(np.uint32)
+    pts["rgb"] = (rgb[:, 0] << 16) | (rgb[:, 1] << 8) | rgb[:, 2]
+    perm = np.random.default_rng(0).permutation(len(pts))
+    for mode in (abi.MERGE_RETAIN, abi.MERGE_ACCUMULATE):
+        with Pose(abi.make_params(voxel_size=0.05, min_points_per_voxel=1, merge_mode=mode, **SMALL)) as P:
+            P.appendPoints(pts[perm[:30000]])
+            P.appendPoints(pts[perm[30000:]])
+            _eq(P.downsamplePtCloud(), pts)
+
+
+# ------------------------------------------------------------------------------------------------- blur
+@pytest.mark.parametrize("mode,k", [(abi.BLUR_MEDIAN, 3), (abi.BLUR_MEDIAN, 15), (abi.BLUR_MEDIAN, 31),
+                                    (abi.BLUR_BOX, 2), (abi.BLUR_BOX, 5), (abi.BLUR_BOX, 30), (abi.BLUR_BOX, 31)])
+def test_blur_plane_bit_exact(mode, k):
+    rng = np.random.default_rng(k)
+    src = synth.make_frame_images(rng, 150, 210)[0]
+    exp = ob.blur_u8(src, k, mode)
+    with Pose(abi.make_params(**SMALL)) as P:
+        got = P.blur(src, k, mode)
+    assert np.array_equal(got, exp), int((got != exp).sum())
+
+
+def test_blur_matches_reference_median_outputs(golden_dir):
+    g = np.load(os.path.join(golden_dir, "median_ref.npz"))
+    with Pose(abi.make_params(**SMALL)) as P:
+        for k in (15, 31):
+            assert np.array_equal(P.blur(g["src"], k, abi.BLUR_MEDIAN)[:160, :240], g[f"out{k}"])
+            assert np.array_equal(P.blur(g["src_br"], k, abi.BLUR_MEDIAN)[-160:, -240:], g[f"out{k}_br"])
+
+
+@pytest.mark.parametrize("mode,k,J", [(abi.BLUR_MEDIAN, 7, 1), (abi.BLUR_BOX, 6, 1), (abi.BLUR_MEDIAN, 5, 4)])
+def test_blurred_frame_cloud(mode, k, J):
+    keep = []
+    p = abi.make_params(jump_pixels=J, voxel_size=0.05, blur_kernel=k, blur_mode=mode, **SMALL4)
+    fr = _frames(31, 1, SMALL4["rows"], SMALL4["cols"], keep=keep, n_kp=40)[0]
+    exp = ob.create_and_transform_pt_cloud(p, fr, abi.DISP_U8)
+    with Pose(p) as P:
+        got = P.createAndTransformPtCloud(fr)
+    _eq(got, exp)
+
+
+def test_blur_rejections():
+    keep = []
+    p = abi.make_params(jump_pixels=1, blur_kernel=4, blur_mode=abi.BLUR_MEDIAN, **SMALL)
+    fr = _frames(1, 1, 120, 200, keep=keep)[0]
+    from online_3d_reconstruction_b200.lib import O3RError
+    with Pose(p) as P, pytest.raises(O3RError):
+        P.createAndTransformPtCloud(fr)  # cv::medianBlur asserts on even ksize -> empty cloud in the reference
+
+
+# ---------------------------------------------------------------------------------- cycles + global cloud
+def _oracle_cycles(p, cycles):
+    cloud, n = None, 0
+    counts = []
+    for frames in cycles:
+        cloud, n, c = ob.run_cycle(p, frames, abi.DISP_U8, 4, cloud, n)
+        counts.append(c)
+    big = cloud[:n] if cloud is not None else np.zeros(0, abi.POINT)
+    return big, counts
+
+
+@pytest.mark.parametrize("mode", [abi.MERGE_ACCUMULATE, abi.MERGE_RETAIN])
+@pytest.mark.parametrize("min_pts", [1, 3])
+def test_cycles_merge_equals_one_shot_reference(mode, min_pts):
+    """pose.cpp:361-434 over three cycles, then pose.cpp:527-531: the incremental merge must equal the
+    reference's single final voxelisation of everything (keys, counts, colours, order AND centroids)."""
+    keep = []
+    geom = SMALL4
+    p = abi.make_params(jump_pixels=1, voxel_size=0.05, min_points_per_voxel=min_pts, merge_mode=mode, **geom)
+    cycles = [_frames(40, 4, geom["rows"], geom["cols"], keep=keep, traj_start=0),
+              _frames(41, 3, geom["rows"], geom["cols"], keep=keep, traj_start=4),
+              _frames(42, 4, geom["rows"], geom["cols"], keep=keep, traj_start=5)]
+    big, counts = _oracle_cycles(p, cycles)
+    exp = ob.downsample_pt_cloud(p, big, True)
+    with Pose(p) as P:
+        at = 0
+        for frames, c in zip(cycles, counts):
+            got_c = P.createCycleClouds(frames)
+            assert np.array_equal(got_c, c)
+            n = int(c.sum())
+            _eq(P.lastCyclePoints(), big[at:at + n])
+            at += n
+        got = P.downsamplePtCloud()
+    assert len(exp) > 100
+    _eq(got, exp)
+
+
+def test_dont_downsample_cycle_returns_cloud_big():
+    keep = []
+    p = abi.make_params(jump_pixels=2, dont_downsample=True, **SMALL)
+    cycles = [_frames(50, 3, 120, 200, keep=keep), _frames(51, 2, 120, 200, keep=keep, traj_start=3)]
+    big, _ = _oracle_cycles(p, cycles)
+    with Pose(p) as P:
+        for frames in cycles:
+            P.createCycleClouds(frames)
+        assert P.cloudSize() == len(big)
+        _eq(P.downsamplePtCloud(), big)
+
+
+def test_retain_mode_icp_retro_transform():
+    """pose.cpp:350-354: cloud_big is re-transformed by tf_icp every cycle before the new frames are appended."""
+    keep = []
+    geom = SMALL4
+    p = abi.make_params(jump_pixels=1, voxel_size=0.1, merge_mode=abi.MERGE_RETAIN, **geom)
+    cycles = [_frames(60, 3, geom["rows"], geom["cols"], keep=keep), _frames(61, 3, geom["rows"], geom["cols"], keep=keep, traj_start=3)]
+    tf = np.eye(4, dtype=np.float32)
+    c, s = np.float32(np.cos(0.01)), np.float32(np.sin(0.01))
+    tf[0, 0], tf[0, 1], tf[1, 0], tf[1, 1] = c, -s, s, c
+    tf[:3, 3] = [0.03, -0.02, 0.01]
+    cloud, n, _ = ob.run_cycle(p, cycles[0], abi.DISP_U8, 4)
+    cloud[:n] = ob.transform_pt_cloud(cloud[:n], tf)
+    cloud, n, _ = ob.run_cycle(p, cycles[1], abi.DISP_U8, 4, cloud, n)
+    exp = ob.downsample_pt_cloud(p, cloud[:n], True)
+    with Pose(p) as P:
+        P.createCycleClouds(cycles[0])
+        P.transformPtCloud(tf)
+        P.createCycleClouds(cycles[1])
+        _eq(P.downsamplePtCloud(), exp)
+    from online_3d_reconstruction_b200.lib import O3RError
+    with Pose(abi.make_params(jump_pixels=1, **geom)) as P, pytest.raises(O3RError):
+        P.transformPtCloud(tf)  # accumulate mode cannot re-bin
+
+
+def test_device_pointer_entry_point_matches_host_entry_point():
+    torch = pytest.importorskip("torch")
+    keep = []
+    geom = SMALL4
+    p = abi.make_params(jump_pixels=1, voxel_size=0.05, **geom)
+    seq = synth.sequence(70, 3, geom["rows"], geom["cols"])
+    host = [abi.make_frame(d, img, T, keep=keep) for d, img, T in seq]
+    dev = []
+    for d, img, T in seq:
+        td, ti = torch.from_numpy(d).cuda(), torch.from_numpy(img).cuda()
+        keep.extend([td, ti])
+        f = abi.Frame()
+        f.disp, f.disp_step = td.data_ptr(), d.strides[0]
+        f.bgr, f.bgr_step = ti.data_ptr(), img.strides[0]
+        f.T = host[len(dev)].T
+        dev.append(f)
+    torch.cuda.synchronize()
+    with Pose(p) as A, Pose(p) as B:
+        ca = A.createCycleClouds(host)
+        cb = B.createCycleClouds(dev, device_pointers=True)
+        assert np.array_equal(ca, cb)
+        _eq(A.downsamplePtCloud(), B.downsamplePtCloud())
+
+
+# -------------------------------------------------------------------------------------------- multi-GPU
+def test_exchange_two_ranks_equals_single_rank():
+    """SURVEY §8e on one device: two contexts act as two ranks (frames f mod 2), exchange hash-partitioned
+    partial cells, and the union of their shards must equal the single-rank result: keys, counts and colours
+    exactly, centroids within 1e-5 (cross-rank partial sums reassociate)."""
+    torch = pytest.importorskip("torch")
+    keep = []
+    geom = SMALL4
+    p = abi.make_params(jump_pixels=1, voxel_size=0.05, min_points_per_voxel=1, **geom)
+    cycles = [_frames(80, 6, geom["rows"], geom["cols"], keep=keep), _frames(81, 6, geom["rows"], geom["cols"], keep=keep, traj_start=6)]
+    with Pose(p) as S:
+        for frames in cycles:
+            S.createCycleClouds(frames)
+        single = S.downsamplePtCloud()
+    W = 2
+    ranks = [Pose(p) for _ in range(W)]
+    try:
+        for r in ranks:
+            r.setDeferMerge(True)
+        for frames in cycles:
+            sends, counts = [], []
+            for r, P in enumerate(ranks):
+                P.createCycleClouds(frames[r::W])
+                buf = torch.empty(len(frames) * P.max_points_per_frame * abi.CELL.itemsize // W + 64, dtype=torch.uint8, device="cuda")
+                c = P.exchangePack(W, buf.data_ptr(), buf.numel() // abi.CELL.itemsize)
+                sends.append(buf)
+                counts.append(c)
+            for r, P in enumerate(ranks):
+                parts = []
+                for s in range(W):
+                    off = int(counts[s][:r].sum()) * abi.CELL.itemsize
+                    parts.append(sends[s][off:off + int(counts[s][r]) * abi.CELL.itemsize])
+                recv = torch.cat(parts)
+                torch.cuda.synchronize()
+                P.exchangeMerge(recv.data_ptr(), recv.numel() // abi.CELL.itemsize)
+        shards = [P.downsamplePtCloud() for P in ranks]
+    finally:
+        for r in ranks:
+            r.close()
+    union = np.concatenate(shards)
+    leaf = (0.05, 0.05, 1000.0)
+    def keys_of(a):
+        sh = a.copy()
+        sh["z"] += np.float32(500)
+        return np.array([ob.cell_key(q["x"], q["y"], q["z"], leaf) for q in sh], dtype=np.uint64)
+    ku, ks = keys_of(union), keys_of(single)
+    order = np.argsort(ku, kind="stable")
+    union, ku = union[order], ku[order]
+    assert len(np.unique(ku)) == len(ku)            # disjoint ownership
+    assert np.array_equal(ku, ks)
+    assert np.array_equal(union["rgb"], single["rgb"])
+    for f, shift in (("x", 0.0), ("y", 0.0), ("z", 500.0)):
+        a, b = union[f].astype(np.float64) + shift, single[f].astype(np.float64) + shift
+        assert np.all(np.abs(a - b) <= 1e-5 * np.abs(b)), f
+    assert min(len(s) for s in shards) > 0.3 * len(single) / W
