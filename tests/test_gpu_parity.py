@@ -152,11 +152,12 @@ def test_per_frame_voxelgrid_bit_exact(voxel_size, geom):
 
 
 def test_per_frame_voxelgrid_overflow_passthrough():
-    """voxel_size 0.01 -> leaf 0.002: PCL's int32 guard returns the input unchanged (config 5)."""
+    """Leaf so small that dx*dy*dz > INT32_MAX: PCL's guard returns the input unchanged (what config 5's
+    voxel_size 0.01 does to a full 4K frame; the small test frame needs a smaller leaf to trip it)."""
     keep = []
-    p = abi.make_params(jump_pixels=1, voxel_size=0.01, **SMALL4)
+    p = abi.make_params(jump_pixels=1, voxel_size=0.002, **SMALL4)
     fr = _frames(22, 1, SMALL4["rows"], SMALL4["cols"], keep=keep)[0]
-    p_nd = abi.make_params(jump_pixels=1, voxel_size=0.01, dont_downsample=True, **SMALL4)
+    p_nd = abi.make_params(jump_pixels=1, voxel_size=0.002, dont_downsample=True, **SMALL4)
     raw = ob.create_and_transform_pt_cloud(p_nd, fr, abi.DISP_U8)
     exp = ob.create_and_transform_pt_cloud(p, fr, abi.DISP_U8)
     _eq(exp, raw)  # the oracle itself passes through
