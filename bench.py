@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the disparity -> voxel-cloud hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+A "step" is one reconstruction cycle of the reference (pose.cpp:361-434 + :527-531): seq_len = 50 accepted
+frames go through createAndTransformPtCloud (validity mask, Q reprojection, rigid transform, per-frame
+VoxelGrid at voxel_size/5), are merged into the global cloud, and the combined VoxelGrid cloud
+(voxel_size, min_points_per_voxel) is produced.  Workload at N = 1 is BASELINE.json configs[1]:
+1280x720 u8 disparity, --jump_pixels 1 --voxel_size 0.05 --min_points_per_voxel 1, synthetic uav720(seed=1002).
+StatisticalOutlierRemoval (pose_functions.cpp:1673-1686) is excluded on both the GPU and the CPU side
+(not built yet).
+
+Prints ONE JSON line (rank 0).  `value` times the cycle with inputs resident in HBM; `e2e` times the same
+cycle through the host-pointer C-ABI call from pinned host memory (H2D of every frame and D2H of the
+result inside the timed region); `roofline` is the dominant kernel's algorithmic bytes / its CUDA-event
+time; `cpu_baseline` is the CPU oracle (a port of the reference path) on the box's host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+from online_3d_reconstruction_b200 import abi, synth  # noqa: E402
+
+WORKLOADS = {
+    # name: (rows, cols, disp_type, J, voxel_size, min_pts, dont_downsample, frames/step, seed, Q scale)
+    "config2_semidense_720p": (720, 1280, abi.DISP_U8, 1, 0.05, 1, False, 50, 1002, 1.0),
+    "config3_dont_downsample_720p": (720, 1280, abi.DISP_U8, 1, 0.05, 1, True, 50, 1003, 1.0),
+    "config4_sweep_720p_v002": (720, 1280, abi.DISP_U8, 1, 0.02, 1, False, 50, 1004, 1.0),
+    "config5_4k_u16_v001": (2160, 3840, abi.DISP_U16, 1, 0.01, 1, False, 10, 1005, 3.0),
+    "config1_sparse_720p": (720, 1280, abi.DISP_U8, 15, 0.05, 1, False, 50, 1001, 1.0),
+}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+            t0 = time.time()  # NVML start-up holds driver locks: let it finish before anything is timed
+            while not self.rows and time.time() - t0 < 10:
+                time.sleep(0.05)
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax = float(r[2])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        hi = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(hi)) if hi else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_data(wl, rank, world, n_steps_total):
+    rows, cols, dt, J, v, mp, nd, F, seed, qs = WORKLOADS[wl]
+    seq = synth.sequence(seed + 101 * rank, F, rows, cols, disp_type=dt)
+    disp = [s[0] for s in seq]
+    bgr = [s[1] for s in seq]
+    # global cycle of world*F frames per step, frame j -> rank j % world: trajectory index s*world*F + j
+    Ts = synth.trajectory(np.random.default_rng(seed + 7919), n_steps_total * world * F)
+    T = [[Ts[s * world * F + (i * world + rank)] for i in range(F)] for s in range(n_steps_total)]
+    return disp, bgr, T
+
+
+def params_for(wl, device, merge_mode=abi.MERGE_ACCUMULATE):
+    rows, cols, dt, J, v, mp, nd, F, seed, qs = WORKLOADS[wl]
+    return abi.make_params(rows=rows, cols=cols, jump_pixels=J, voxel_size=v, min_points_per_voxel=mp,
+                           dont_downsample=nd, Q=synth.q_scaled(qs), device=device, max_batch_frames=F,
+                           merge_mode=merge_mode)
+
+
+def frames_array(disp_ptrs, disp_step, bgr_ptrs, bgr_step, Ts):
+    n = len(Ts)
+    arr = (abi.Frame * n)()
+    for i in range(n):
+        arr[i].disp, arr[i].disp_step = disp_ptrs[i], disp_step
+        arr[i].bgr, arr[i].bgr_step = bgr_ptrs[i], bgr_step
+        arr[i].T = (C.c_float * 16)(*Ts[i].reshape(16))
+    return arr
+
+
+# per-kernel algorithmic bytes of one step (what the kernel must read + write once), keyed by profile name
+def algorithmic_bytes(wl, n_valid, n_vox, n_cells_cycle, bd):
+    rows, cols, dt, J, v, mp, nd, F, seed, qs = WORKLOADS[wl]
+    p = params_for(wl, 0)
+    ny, nx = abi.scan_dims(p)
+    npix = ny * nx * F
+    return {
+        "k_pre": npix * bd,
+        "k_emit": npix * bd + npix * 3 + n_valid * (16 + (0 if nd else 4)),
+        "k_rs_hist_u32": 4 * n_valid * 4,
+        "k_rs_scatter_u32": n_valid * (12 + 3 * 16),
+        "k_vg_heads": n_valid * 4,
+        "k_vg_reduce": n_valid * (4 + 4 + 16) + n_vox * 16,
+        "k_acc_key_pts": n_vox * (16 + 12),
+        "k_acc_reduce": n_vox * (8 + 4 + 16) + n_cells_cycle * 40,
+    }
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from online_3d_reconstruction_b200.pose import Pose
+
+    wl = args.workload
+    rows, cols, dt, J, v, mp, nd, F, seed, qs = WORKLOADS[wl]
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    W, K = args.warmup, args.steps
+    disp, bgr, T = make_data(wl, rank, world, W + K)
+    bd = disp[0].dtype.itemsize
+    p = params_for(wl, local_rank)
+    P = Pose(p)
+    if world > 1:
+        P.setDeferMerge(True)
+    # inputs resident in HBM
+    d_disp = [torch.from_numpy(a).to(dev) for a in disp]
+    d_bgr = [torch.from_numpy(a).to(dev) for a in bgr]
+    # pinned host copies for the end-to-end leg
+    h_disp = [torch.from_numpy(a).pin_memory() for a in disp]
+    h_bgr = [torch.from_numpy(a).pin_memory() for a in bgr]
+    torch.cuda.synchronize()
+    fr_dev = [frames_array([t.data_ptr() for t in d_disp], disp[0].strides[0], [t.data_ptr() for t in d_bgr],
+                           bgr[0].strides[0], T[s]) for s in range(W + K)]
+    fr_host = [frames_array([t.data_ptr() for t in h_disp], disp[0].strides[0], [t.data_ptr() for t in h_bgr],
+                            bgr[0].strides[0], T[s]) for s in range(W + K)]
+    stream = torch.cuda.ExternalStream(P.stream(), device=dev)
+    ny, nx = abi.scan_dims(p)
+    cell_cap = F * ny * nx
+    send = torch.empty(cell_cap * abi.CELL.itemsize, dtype=torch.uint8, device=dev) if world > 1 else None
+    out_buf = np.empty(1, dtype=abi.POINT)
+    stats = {}
+
+    def exchange():
+        counts = P.exchangePack(world, send.data_ptr(), cell_cap)
+        sc = torch.from_numpy(counts.astype(np.int64)).to(dev)
+        rc = torch.empty_like(sc)
+        dist.all_to_all_single(rc, sc)
+        rcl = rc.tolist()
+        n_recv = int(sum(rcl))
+        recv = torch.empty(max(n_recv, 1) * abi.CELL.itemsize, dtype=torch.uint8, device=dev)
+        isz = abi.CELL.itemsize
+        dist.all_to_all_single(recv[:n_recv * isz], send[:int(counts.sum()) * isz],
+                               output_split_sizes=[c * isz for c in rcl],
+                               input_split_sizes=[int(c) * isz for c in counts])
+        torch.cuda.current_stream().synchronize()
+        P.exchangeMerge(recv.data_ptr(), n_recv)
+        stats["exchange_cells_sent"] = int(counts.sum())
+
+    def step(s, host):
+        nonlocal out_buf
+        counts = P.createCycleClouds(fr_host[s] if host else fr_dev[s], dt, device_pointers=not host)
+        if world > 1:
+            exchange()
+        need = P.cloudSize()
+        if out_buf.size < need:
+            out_buf = np.empty(int(need * 1.5) + 1024, dtype=abi.POINT)
+        out = P.downsamplePtCloud(out_buf)
+        stats["n_vox"] = int(counts.sum())
+        stats["n_out"] = len(out)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(host):
+        P.clearCloud()
+        for s in range(W):
+            step(s, host)
+        barrier()
+        l0 = P.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for s in range(W, W + K):
+            step(s, host)
+        e1.record(stream)
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms, wall], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = t.tolist()
+        return ms, wall, P.launch_count() - l0
+
+    timed(host=False)  # untimed pass: every buffer reaches its steady-state size
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ms, wall, launches = timed(host=False)
+    clk = clocks.stop()
+    cells_after_value = P.cloudSize()
+    ms_e2e, wall_e2e, _ = timed(host=True)
+    d2h = stats["n_out"] * 16 + F * 4
+
+    # per-kernel CUDA-event pass for the roofline
+    P.clearCloud()
+    for s in range(W):
+        step(s, False)
+    P.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    cells_before = P.cloudSize()
+    for s in range(W, W + K):
+        step(s, False)
+    e1.record(stream)
+    prof = P.profileRead()
+    ms_prof = e0.elapsed_time(e1)
+    P.profile(False)
+    new_cells_per_step = (P.cloudSize() - cells_before) / K
+
+    n_valid = int(sum(int((a[p.bounding_box:rows - p.bounding_box, p.cols_start_aft_cutout:cols - p.bounding_box][::J, ::J].astype(np.float64)
+                           / (p.disp_divisor if dt == abi.DISP_U16 else 1.0) > p.min_disparity).sum()) for a in disp))
+    alg = algorithmic_bytes(wl, n_valid, stats["n_vox"], max(new_cells_per_step, 1), bd)
+    peak, peak_src = peaks()
+    kern = sorted(prof.items(), key=lambda kv: -kv[1][1])
+    total_kernel_ms = sum(v[1] for v in prof.values())
+    top_name, (top_n, top_ms) = kern[0]
+    per_launch_ms = top_ms / top_n
+    roof = {"bound": "hbm", "kernel": top_name, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+            "launches_per_step": top_n / K, "avg_launch_ms": per_launch_ms,
+            "share_of_kernel_time": top_ms / total_kernel_ms, "traffic": None}
+    if top_name in alg:
+        per_launch_bytes = alg[top_name] / (top_n / K)
+        roof["achieved"] = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
+        roof["frac"] = roof["achieved"] / peak
+        roof["algorithmic_bytes_per_launch"] = per_launch_bytes
+    else:
+        roof["achieved"] = roof["frac"] = None
+    # whole-step view: compulsory bytes of the fused pipeline / step time
+    ny, nx = abi.scan_dims(p)
+    step_alg = F * (rows * cols * bd + 3 * ny * nx) + (16 * n_valid if nd else 20 * stats["n_vox"]) + 2 * 32 * new_cells_per_step
+    roof["pipeline_algorithmic_bytes_per_step"] = step_alg
+    roof["pipeline_frac_of_peak"] = step_alg / (ms / K * 1e-3) / 1e9 / peak
+    roof["kernels_ms_per_step"] = {k: round(v[1] / K, 4) for k, v in kern[:12]}
+    roof["profiled_step_ms"] = ms_prof / K
+
+    frames_total = world * F * K
+    res = {
+        "metric": "frames_per_sec", "value": frames_total / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {abi.DISP_U8: "u8", abi.DISP_U16: "u16", abi.DISP_F32: "f32"}[dt] + "->f64->f32",
+        "data": "synthetic", "mpoints_per_sec": world * n_valid * K / (ms * 1e-3) / 1e6,
+        "config": {"workload": wl, "frames_per_step_per_gpu": F, "frame": f"{cols}x{rows}", "jump_pixels": J,
+                   "voxel_size": v, "min_points_per_voxel": mp, "dont_downsample": nd, "seq_len": F,
+                   "valid_points_per_step_per_gpu": n_valid, "per_frame_voxels_per_step_per_gpu": stats["n_vox"],
+                   "resident_cells_after_timed_region": cells_after_value,
+                   "l2": f"inputs ({F * (rows * cols * bd + rows * cols * 3) / 1e6:.0f} MB/step) and intermediates exceed the 126 MB L2",
+                   "sor": "StatisticalOutlierRemoval excluded on GPU and CPU sides (not built)",
+                   "parallelism": f"frames f mod {world}; NCCL all-to-all of hash-partitioned cells" if world > 1 else "single GPU"},
+        "clocks": clk, "wall_ms_per_step": wall / K,
+        "e2e": {"value": frames_total / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e / K,
+                "h2d_bytes_per_step": int(F * (rows * cols * bd + rows * cols * 3)), "d2h_bytes_per_step": int(d2h),
+                "api": "o3r_frames_cloud(host pinned) + o3r_cloud_downsample(host)"},
+        "gpu_launches": int(launches), "roofline": roof,
+    }
+    if world > 1:
+        res["config"]["exchange_cells_sent_last_step"] = stats.get("exchange_cells_sent")
+    P.close()
+    return res, (disp, bgr, T)
+
+
+def cpu_cycle(wl, disp, bgr, Ts, threads):
+    """One step on the CPU oracle (port of the reference path): cycle + combined downsample. -> seconds"""
+    import oracle_binding as ob
+    rows, cols, dt, J, v, mp, nd, F, seed, qs = WORKLOADS[wl]
+    p = params_for(wl, 0)
+    keep = []
+    frames = [abi.make_frame(disp[i], bgr[i], Ts[i], keep=keep) for i in range(len(Ts))]
+    t0 = time.perf_counter()
+    cloud, n, counts = ob.run_cycle(p, frames, dt, threads)
+    if not nd:
+        ob.downsample_pt_cloud(p, cloud[:n], True)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path (the oracle port; the reference itself cannot be built
+    here: PCL/OpenCV/Boost/VTK absent) on all host cores.  Rank 0 only."""
+    if rank != 0:
+        return None
+    wl = args.workload
+    rows, cols, dt, J, v, mp, nd, F, seed, qs = WORKLOADS[wl]
+    W, K = args.warmup, args.steps
+    sample_frames = min(F, args.ref_frames)
+    disp, bgr, T = make_data(wl, 0, 1, W + K)
+    threads = os.cpu_count() or 1
+    for s in range(min(W, 1)):
+        cpu_cycle(wl, disp[:sample_frames], bgr[:sample_frames], T[s][:sample_frames], threads)
+    t = 0.0
+    for s in range(W, W + K):
+        t += cpu_cycle(wl, disp[:sample_frames], bgr[:sample_frames], T[s][:sample_frames], threads)
+    fps = sample_frames * K / t
+    return {"impl": "reference", "metric": "frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": t / K * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8->f64->f32", "data": "synthetic",
+            "config": {"workload": wl, "frames_per_step": sample_frames, "note": "CPU port of the reference path "
+                       "(oracle/, g++ -O2; the reference was built with no -O flag); SOR excluded"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                             "sample": f"{K} cycles of {sample_frames} frames + combined downsample each"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2_semidense_720p", choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-frames", type=int, default=50, help="frames per CPU-reference step (bounded sample)")
+    ap.add_argument("--cpu-baseline-frames", type=int, default=50)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        res = run_reference(args, rank, world)
+        if res is not None:
+            print(json.dumps(res), flush=True)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    res, (disp, bgr, T) = run_ours(args, rank, world, local_rank)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        wl = args.workload
+        n = min(len(disp), args.cpu_baseline_frames)
+        threads = os.cpu_count() or 1
+        cpu_cycle(wl, disp[:4], bgr[:4], T[0][:4], threads)  # warm
+        t = cpu_cycle(wl, disp[:n], bgr[:n], T[args.warmup][:n], threads)
+        res["cpu_baseline"] = {"value": n / t, "unit": "frames/s", "cores": threads, "kind": "port",
+                               "sample": f"1 cycle of {n} frames + combined downsample, {t:.2f} s, SOR excluded"}
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()

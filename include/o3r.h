@@ -206,6 +206,12 @@ int o3r_set_defer_merge(o3r_ctx* ctx, int defer);
 
 /* ---- introspection ----------------------------------------------------------------------------- */
 
+/* Per-kernel CUDA-event timing on the context's stream.  o3r_profile(ctx, 1) starts recording an event
+ * pair around every kernel launch; o3r_profile_read writes one line per kernel name,
+ * "name<TAB>launches<TAB>total_ms", into buf.  o3r_profile(ctx, 0) stops and clears. */
+int o3r_profile(o3r_ctx* ctx, int enable);
+int o3r_profile_read(o3r_ctx* ctx, char* buf, size_t cap);
+
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */
 uint64_t o3r_launch_count(const o3r_ctx* ctx);
 /* The CUDA stream all work of the context is issued on (a cudaStream_t) — for event timing. */

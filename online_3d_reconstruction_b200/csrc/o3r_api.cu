@@ -86,6 +86,16 @@ struct o3r_ctx {
     DevBuf cloud;
     size_t n_cloud = 0;
 
+    // optional per-kernel event timing (bench.py's roofline leg)
+    struct ProfRec { const char* name; cudaEvent_t a, b; };
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t ev_get() {
+        if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+
     bool retain() const { return p.dont_downsample || p.merge_mode == O3R_MERGE_RETAIN; }
     int fail(int code, const std::string& m) { err = m; return code; }
     int fail_cuda(cudaError_t e, const char* what, int line) {
@@ -102,13 +112,23 @@ struct o3r_ctx {
         if (e_ != cudaSuccess) return ctx->fail_cuda(e_, #call, __LINE__);    \
     } while (0)
 
-#define LAUNCH(kernel, grid, block, smem, ...)                                \
+#define LAUNCH_N(name, kernel, grid, block, smem, ...)                        \
     do {                                                                      \
+        cudaEvent_t pa_ = nullptr, pb_ = nullptr;                             \
+        if (ctx->profiling) {                                                 \
+            pa_ = ctx->ev_get(); pb_ = ctx->ev_get();                         \
+            cudaEventRecord(pa_, ctx->st);                                    \
+        }                                                                     \
         kernel<<<grid, block, smem, ctx->st>>>(__VA_ARGS__);                  \
         ++ctx->launches;                                                      \
         cudaError_t e_ = cudaGetLastError();                                  \
         if (e_ != cudaSuccess) return ctx->fail_cuda(e_, #kernel, __LINE__);  \
+        if (pa_) {                                                            \
+            cudaEventRecord(pb_, ctx->st);                                    \
+            ctx->prof.push_back({name, pa_, pb_});                            \
+        }                                                                     \
     } while (0)
+#define LAUNCH(kernel, grid, block, smem, ...) LAUNCH_N(#kernel, kernel, grid, block, smem, __VA_ARGS__)
 
 namespace {
 
@@ -122,19 +142,22 @@ int read_counters(o3r_ctx* ctx) {
 }
 
 // ---- radix sort driver -----------------------------------------------------------------------------------------
+// The caller provides ghist [n_seg][passes][256] (already filled) and plan.
 template <typename KeyT>
 int sort_pairs(o3r_ctx* ctx, KeyT* k0, KeyT* k1, uint32_t* v0, uint32_t* v1, const uint32_t* seg_off, int n_seg,
-               size_t per_seg_cap, const SortPlan* plan, int passes, int iota_first) {
+               size_t per_seg_cap, const SortPlan* plan, int passes, int iota_first, const uint32_t* ghist) {
     const uint32_t tiles_ub = std::max(1u, cdiv(per_seg_cap, kRsTile));
-    CU(ctx->hist.ensure((size_t)n_seg * kRsBins * tiles_ub * 4));
-    uint32_t* hist = ctx->hist.as<uint32_t>();
-    const dim3 grid(tiles_ub, n_seg);
-    for (int p = 0; p < passes; ++p) {
-        LAUNCH((k_rs_hist<KeyT>), grid, kThreads, 0, k0, k1, seg_off, plan, p, tiles_ub, hist);
-        LAUNCH(k_rs_scan, n_seg, kThreads, 0, seg_off, plan, p, tiles_ub, hist);
-        LAUNCH((k_rs_scatter<KeyT>), grid, kThreads, rs_scatter_smem<KeyT>(), k0, k1, v0, v1, seg_off, plan, p,
-               tiles_ub, hist, iota_first);
-    }
+    const size_t st_words = (size_t)n_seg * tiles_ub * kRsBins;
+    // status words for every pass + one ticket per pass, cleared with one memset
+    CU(ctx->hist.ensure((st_words * passes + 64) * 4));
+    CU(cudaMemsetAsync(ctx->hist.p, 0, (st_words * passes + 64) * 4, ctx->st));
+    uint32_t* status = ctx->hist.as<uint32_t>();
+    uint32_t* tickets = status + st_words * passes;
+    const uint32_t grid = tiles_ub * (uint32_t)n_seg;
+    for (int p = 0; p < passes; ++p)
+        LAUNCH_N(sizeof(KeyT) == 4 ? "k_rs_onesweep_u32" : "k_rs_onesweep_u64", (k_rs_onesweep<KeyT>), grid, kThreads,
+                 rs_scatter_smem<KeyT>(), k0, k1, v0, v1, seg_off, plan, p, passes, tiles_ub, ghist,
+                 status + st_words * p, tickets + p, iota_first);
     return O3R_OK;
 }
 
@@ -149,28 +172,19 @@ int carve_sort_u32(o3r_ctx* ctx, size_t n, SortU32& s) {
     return O3R_OK;
 }
 
-int ensure_plan_all(o3r_ctx* ctx, int n_seg) {
-    if (ctx->plan_all.cap >= (size_t)n_seg * sizeof(SortPlan)) return O3R_OK;
-    const int n = std::max(n_seg, 64);
-    std::vector<SortPlan> pl(n);
-    for (auto& q : pl) {
-        for (int p = 0; p < kMaxPasses; ++p) { q.active[p] = p < 4; q.in_parity[p] = (uint8_t)(p & 1); }
-        q.final_parity = 0; q.n_active = 4;
-    }
-    CU(ctx->plan_all.ensure((size_t)n * sizeof(SortPlan)));
-    CU(cudaMemcpyAsync(ctx->plan_all.p, pl.data(), (size_t)n * sizeof(SortPlan), cudaMemcpyHostToDevice, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
-    return O3R_OK;
-}
-
 // sorts + reduces; out/out_off sized by the caller.  CNT_VOX receives the total.
 int vg_sorted_reduce(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const uint32_t* seg_off, int n_seg,
                      size_t per_seg_cap, const GridParams* grids, float ix, float iy, float iz, uint32_t min_points,
                      int z_shift, float4* out, uint32_t* out_off, uint64_t* out_keys, uint32_t* out_counts) {
-    int rc = ensure_plan_all(ctx, n_seg);
-    if (rc) return rc;
-    const SortPlan* plan = ctx->plan_all.as<SortPlan>();
-    rc = sort_pairs<uint32_t>(ctx, sb.k0, sb.k1, sb.v0, sb.v1, seg_off, n_seg, per_seg_cap, plan, 4, 1);
+    CU(ctx->ghist.ensure((size_t)n_seg * 4 * kRsBins * 4));
+    CU(ctx->plan_all.ensure((size_t)n_seg * sizeof(SortPlan)));
+    CU(cudaMemsetAsync(ctx->ghist.p, 0, (size_t)n_seg * 4 * kRsBins * 4, ctx->st));
+    SortPlan* plan = ctx->plan_all.as<SortPlan>();
+    LAUNCH_N("k_rs_ghist_u32", (k_rs_ghist<uint32_t, 4>), dim3(std::max(1u, cdiv(per_seg_cap, kRsTile)), n_seg),
+             kThreads, 0, sb.k0, seg_off, ctx->ghist.as<uint32_t>());
+    LAUNCH(k_rs_plan, n_seg, kThreads, 0, ctx->ghist.as<uint32_t>(), seg_off, 4, plan);
+    int rc = sort_pairs<uint32_t>(ctx, sb.k0, sb.k1, sb.v0, sb.v1, seg_off, n_seg, per_seg_cap, plan, 4, 1,
+                                  ctx->ghist.as<uint32_t>());
     if (rc) return rc;
     VgArgs A;
     A.keys0 = sb.k0; A.keys1 = sb.k1; A.vals0 = sb.v0; A.vals1 = sb.v1;
@@ -233,7 +247,8 @@ int acc_build_cycle(o3r_ctx* ctx, const Items& items, const float4* pts, const o
         LAUNCH(k_acc_key_cells, gk, kThreads, 0, cells, (uint32_t)n, sb.k0, sb.v0, ctx->ghist.as<uint32_t>());
     SortPlan* plan = ctx->plan_v2.as<SortPlan>();
     LAUNCH(k_rs_plan, 1, kThreads, 0, ctx->ghist.as<uint32_t>(), seg, kMaxPasses, plan);
-    rc = sort_pairs<uint64_t>(ctx, sb.k0, sb.k1, sb.v0, sb.v1, seg, 1, n, plan, kMaxPasses, 0);
+    rc = sort_pairs<uint64_t>(ctx, sb.k0, sb.k1, sb.v0, sb.v1, seg, 1, n, plan, kMaxPasses, 0,
+                              ctx->ghist.as<uint32_t>());
     if (rc) return rc;
     AccArgs A;
     A.keys0 = sb.k0; A.keys1 = sb.k1; A.vals0 = sb.v0; A.vals1 = sb.v1;
@@ -252,7 +267,7 @@ int acc_build_cycle(o3r_ctx* ctx, const Items& items, const float4* pts, const o
     LAUNCH(k_acc_heads, A.tiles_ub, kThreads, 0, A, ctx->head_cnt.as<uint32_t>());
     LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->head_cnt.as<uint32_t>(), ctx->head_off.as<uint32_t>(), A.tiles_ub,
            cnt + CNT_CYC);
-    LAUNCH((k_acc_reduce<Items>), A.tiles_ub, kThreads, 0, A, items, ctx->head_off.as<uint32_t>(),
+    LAUNCH_N("k_acc_reduce", (k_acc_reduce<Items>), A.tiles_ub, kThreads, 0, A, items, ctx->head_off.as<uint32_t>(),
            ctx->ckey.as<uint64_t>(), ctx->cacc.as<float4>(), ctx->crgb.as<uint4>(), cnt + CNT_NEW);
     rc = read_counters(ctx);
     if (rc) return rc;
@@ -323,14 +338,14 @@ int launch_stage_a(o3r_ctx* ctx, const AParams& P, int n, const BatchOpts& opt, 
     const dim3 grid(P.tiles_per_frame, n);
     uint32_t* cnt = ctx->counters.as<uint32_t>();
     LAUNCH(k_bbox_init, cdiv((size_t)n * 6, kThreads), kThreads, 0, ctx->bbox.as<uint32_t>(), n);
-    LAUNCH((k_pre<DT>), grid, kThreads, 0, P, fr, ctx->tile_cnt.as<uint32_t>(), ctx->bbox.as<uint32_t>(), opt.mask_dev);
+    LAUNCH_N("k_pre", (k_pre<DT>), grid, kThreads, 0, P, fr, ctx->tile_cnt.as<uint32_t>(), ctx->bbox.as<uint32_t>(), opt.mask_dev);
     if (opt.mask_only) return O3R_OK;
     LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->tile_cnt.as<uint32_t>(), ctx->tile_off.as<uint32_t>(),
            (uint32_t)((size_t)P.tiles_per_frame * n), cnt + CNT_PTS);
     LAUNCH(k_a_post, cdiv(n + 1, kThreads), kThreads, 0, n, P.tiles_per_frame, ctx->tile_off.as<uint32_t>(),
            cnt + CNT_PTS, ctx->bbox.as<uint32_t>(), ctx->inv_f, ctx->inv_f, ctx->inv_f, P.want_keys,
            ctx->frame_off.as<uint32_t>(), ctx->grids.as<GridParams>());
-    LAUNCH((k_emit<DT>), grid, kThreads, 0, P, fr, ctx->tile_off.as<uint32_t>(), ctx->frame_off.as<uint32_t>(),
+    LAUNCH_N("k_emit", (k_emit<DT>), grid, kThreads, 0, P, fr, ctx->tile_off.as<uint32_t>(), ctx->frame_off.as<uint32_t>(),
            ctx->grids.as<GridParams>(), ctx->pts.as<float4>(), sb.k0);
     (void)cap_batch;
     return O3R_OK;
@@ -419,10 +434,10 @@ int frames_cloud_dev_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp
             const dim3 g(cdiv(rx1 - rx0, kBlurStrip), cdiv(ry1 - ry0, kBlurRows), n);
             const size_t sm = blur_smem(p.blur_kernel, p.blur_mode);
             if (p.blur_mode == O3R_BLUR_MEDIAN)
-                LAUNCH((k_blur<O3R_BLUR_MEDIAN>), g, kBlurRows, sm, ctx->d_blurjobs.as<BlurJob>(), p.rows, p.cols,
+                LAUNCH_N("k_blur_median", (k_blur<O3R_BLUR_MEDIAN>), g, kBlurRows, sm, ctx->d_blurjobs.as<BlurJob>(), p.rows, p.cols,
                        p.blur_kernel, rx0, ry0, rx1, ry1);
             else
-                LAUNCH((k_blur<O3R_BLUR_BOX>), g, kBlurRows, sm, ctx->d_blurjobs.as<BlurJob>(), p.rows, p.cols,
+                LAUNCH_N("k_blur_box", (k_blur<O3R_BLUR_BOX>), g, kBlurRows, sm, ctx->d_blurjobs.as<BlurJob>(), p.rows, p.cols,
                        p.blur_kernel, rx0, ry0, rx1, ry1);
         }
     }
@@ -608,10 +623,10 @@ int o3r_create(const o3r_params* params, o3r_ctx** out_ctx) {
     cudaMemcpyAsync(ctx->lut_r.p, lr, sizeof(lr), cudaMemcpyHostToDevice, ctx->st);
     cudaMemcpyAsync(ctx->lut_z.p, lz, sizeof(lz), cudaMemcpyHostToDevice, ctx->st);
     if ((e = cudaStreamSynchronize(ctx->st)) != cudaSuccess) return bail(e, "init sync");
-    e = cudaFuncSetAttribute(k_rs_scatter<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(k_rs_onesweep<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)rs_scatter_smem<uint64_t>());
     if (e != cudaSuccess) return bail(e, "smem attr (is this an sm_100a device?)");
-    e = cudaFuncSetAttribute(k_rs_scatter<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(k_rs_onesweep<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)rs_scatter_smem<uint32_t>());
     if (e != cudaSuccess) return bail(e, "smem attr");
     const int bs = (int)blur_smem(kBlurMaxK, O3R_BLUR_MEDIAN);
@@ -633,6 +648,8 @@ void o3r_destroy(o3r_ctx* ctx) {
                       &ctx->res_acc[0], &ctx->res_acc[1], &ctx->res_rgb[0], &ctx->res_rgb[1], &ctx->ckey, &ctx->cacc,
                       &ctx->crgb, &ctx->new_cnt, &ctx->new_off, &ctx->new_keys, &ctx->okeys, &ctx->cloud};
     for (DevBuf* b : bufs) b->release();
+    for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_offs) cudaFreeHost(ctx->h_offs);
     if (ctx->st) cudaStreamDestroy(ctx->st);
@@ -645,6 +662,42 @@ void* o3r_stream(o3r_ctx* ctx) { return ctx ? (void*)ctx->st : nullptr; }
 int o3r_sync(o3r_ctx* ctx) {
     if (!ctx) return O3R_ERR_INVALID;
     CU(cudaStreamSynchronize(ctx->st));
+    return O3R_OK;
+}
+
+int o3r_profile(o3r_ctx* ctx, int enable) {
+    if (!ctx) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaStreamSynchronize(ctx->st));
+    for (auto& r : ctx->prof) { ctx->ev_pool.push_back(r.a); ctx->ev_pool.push_back(r.b); }
+    ctx->prof.clear();
+    ctx->profiling = enable != 0;
+    return O3R_OK;
+}
+
+int o3r_profile_read(o3r_ctx* ctx, char* buf, size_t cap) {
+    if (!ctx || !buf || cap == 0) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaStreamSynchronize(ctx->st));
+    struct Agg { std::string name; uint64_t n; double ms; };
+    std::vector<Agg> agg;
+    for (auto& r : ctx->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        std::string nm = r.name;
+        size_t i = 0;
+        for (; i < agg.size(); ++i) if (agg[i].name == nm) break;
+        if (i == agg.size()) agg.push_back({nm, 0, 0.0});
+        agg[i].n += 1; agg[i].ms += ms;
+    }
+    std::string out;
+    char line[256];
+    for (auto& a : agg) {
+        snprintf(line, sizeof(line), "%s\t%llu\t%.6f\n", a.name.c_str(), (unsigned long long)a.n, a.ms);
+        out += line;
+    }
+    if (out.size() + 1 > cap) return ctx->fail(O3R_ERR_CAPACITY, "profile buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
     return O3R_OK;
 }
 
@@ -893,9 +946,9 @@ int o3r_blur_u8(o3r_ctx* ctx, const uint8_t* src, size_t src_step, int rows, int
     const dim3 g(cdiv(cols, kBlurStrip), cdiv(rows, kBlurRows), 1);
     const size_t sm = blur_smem(kernel, mode);
     if (mode == O3R_BLUR_MEDIAN)
-        LAUNCH((k_blur<O3R_BLUR_MEDIAN>), g, kBlurRows, sm, ctx->d_blurjobs.as<BlurJob>(), rows, cols, kernel, 0, 0, cols, rows);
+        LAUNCH_N("k_blur_median", (k_blur<O3R_BLUR_MEDIAN>), g, kBlurRows, sm, ctx->d_blurjobs.as<BlurJob>(), rows, cols, kernel, 0, 0, cols, rows);
     else
-        LAUNCH((k_blur<O3R_BLUR_BOX>), g, kBlurRows, sm, ctx->d_blurjobs.as<BlurJob>(), rows, cols, kernel, 0, 0, cols, rows);
+        LAUNCH_N("k_blur_box", (k_blur<O3R_BLUR_BOX>), g, kBlurRows, sm, ctx->d_blurjobs.as<BlurJob>(), rows, cols, kernel, 0, 0, cols, rows);
     CU(cudaMemcpy2DAsync(dst, dst_step, ctx->d_blur.p, step, cols, rows, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     return O3R_OK;
@@ -930,7 +983,7 @@ int o3r_exchange_pack(o3r_ctx* ctx, int world, o3r_cell* send_dev, size_t cap, u
     CU(cudaMemcpyAsync(ctx->seg2.p, seg_h, 8, cudaMemcpyHostToDevice, ctx->st));
     const uint32_t g = std::min<uint32_t>(cdiv(n, kThreads), 148 * 8);
     LAUNCH(k_owner, g, kThreads, 0, n, ctx->ckey.as<uint64_t>(), (uint32_t)world, sb.k0, sb.v0, ocnt);
-    rc = sort_pairs<uint32_t>(ctx, sb.k0, sb.k1, sb.v0, sb.v1, ctx->seg2.as<uint32_t>(), 1, n, plan, 1, 0);
+    rc = sort_pairs<uint32_t>(ctx, sb.k0, sb.k1, sb.v0, sb.v1, ctx->seg2.as<uint32_t>(), 1, n, plan, 1, 0, ocnt);
     if (rc) return rc;
     LAUNCH(k_pack_cells, g, kThreads, 0, n, sb.v1, ctx->ckey.as<uint64_t>(), ctx->cacc.as<float4>(),
            ctx->crgb.as<uint4>(), send_dev);

@@ -1,10 +1,11 @@
 // sort.cuh — hand-written segmented LSD radix sort of (key, u32 value) pairs, plus the exclusive-scan
 // kernels the pipeline uses.  No Thrust / CUB.
 //
-// 8-bit digits; one pass = k_rs_hist (per-tile digit histogram) -> k_rs_scan (digit-major exclusive
-// scan per segment) -> k_rs_scatter (stable in-tile ranking with warp match_any, exchange through
-// shared memory so that every digit run leaves the CTA as one coalesced burst).  Stability is what
-// makes the later per-voxel sums run in input order (bit-exact with the oracle's stable order).
+// 8-bit digits.  k_rs_ghist reads the keys once and builds every pass's whole-segment digit histogram;
+// each pass is then ONE kernel (k_rs_onesweep): stable in-tile ranking with warp match_any, tile offsets
+// by decoupled look-back, exchange through shared memory so that every digit run leaves the CTA as one
+// coalesced burst.  Stability is what makes the later per-voxel sums run in input order (bit-exact with
+// the oracle's stable order).
 //
 // Segments (one per frame for the per-frame grid, a single one for the combined grid) are described
 // by a device array seg_off[S+1]; launches are sized by a host upper bound and surplus CTAs exit.
@@ -78,108 +79,105 @@ __global__ void k_rs_plan(const uint32_t* __restrict__ ghist, const uint32_t* __
 template <typename KeyT>
 __device__ __forceinline__ uint32_t rs_digit(KeyT k, int shift) { return (uint32_t)(k >> shift) & 255u; }
 
-// ---- pass step 1: per-tile histogram -------------------------------------------------------------------------
-template <typename KeyT>
-__global__ void __launch_bounds__(kThreads) k_rs_hist(const KeyT* __restrict__ keys0, const KeyT* __restrict__ keys1,
-                                                      const uint32_t* __restrict__ seg_off,
-                                                      const SortPlan* __restrict__ plan, int pass, uint32_t tiles_ub,
-                                                      uint32_t* __restrict__ hist) {
-    __shared__ uint32_t sh[kRsBins];
+// ---- whole-segment digit histograms for every pass in one read of the keys ------------------------------------
+// ghist[S][PASSES][256]; must be zeroed by the caller.
+template <typename KeyT, int PASSES>
+__global__ void __launch_bounds__(kThreads) k_rs_ghist(const KeyT* __restrict__ keys, const uint32_t* __restrict__ seg_off,
+                                                       uint32_t* __restrict__ ghist) {
+    __shared__ uint32_t sh[PASSES * kRsBins];
     const int s = blockIdx.y;
     const uint32_t t = blockIdx.x;
-    if (!plan[s].active[pass]) return;
     const uint32_t beg = seg_off[s], n = seg_off[s + 1] - beg;
-    const uint32_t nt = (n + kRsTile - 1) / kRsTile;
-    if (t >= nt) return;
-    const KeyT* keys = (plan[s].in_parity[pass] ? keys1 : keys0) + beg;
-    const int shift = pass * 8, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    sh[threadIdx.x] = 0;
+    if (t * kRsTile >= n) return;
+    for (int i = threadIdx.x; i < PASSES * kRsBins; i += kThreads) sh[i] = 0;
     __syncthreads();
-#pragma unroll 4
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 2
     for (int r = 0; r < kRsItems; ++r) {
         const uint32_t i = t * kRsTile + warp * (32 * kRsItems) + r * 32 + lane;
         const bool valid = i < n;
         const unsigned vm = __ballot_sync(kFull, valid);
         if (valid) {
-            const uint32_t d = rs_digit(keys[i], shift);
-            const unsigned peers = __match_any_sync(vm, d);
-            if (lane == __ffs(peers) - 1) atomicAdd(&sh[d], (uint32_t)__popc(peers));
+            const KeyT k = keys[beg + i];
+#pragma unroll
+            for (int p = 0; p < PASSES; ++p) {
+                const uint32_t d = rs_digit(k, 8 * p);
+                const unsigned peers = __match_any_sync(vm, d);
+                if (lane == __ffs(peers) - 1) atomicAdd(&sh[p * kRsBins + d], (uint32_t)__popc(peers));
+            }
         }
     }
     __syncthreads();
-    hist[(size_t)s * kRsBins * tiles_ub + (size_t)threadIdx.x * nt + t] = sh[threadIdx.x];
+    for (int i = threadIdx.x; i < PASSES * kRsBins; i += kThreads)
+        if (sh[i]) atomicAdd(&ghist[(size_t)s * PASSES * kRsBins + i], sh[i]);
 }
 
-// ---- pass step 2: exclusive scan of the segment's [256][nt] histogram, digit-major ----------------------------
-__global__ void __launch_bounds__(kThreads) k_rs_scan(const uint32_t* __restrict__ seg_off,
-                                                      const SortPlan* __restrict__ plan, int pass, uint32_t tiles_ub,
-                                                      uint32_t* __restrict__ hist) {
-    __shared__ uint32_t sm[34];
-    const int s = blockIdx.x;
-    if (!plan[s].active[pass]) return;
-    const uint32_t n = seg_off[s + 1] - seg_off[s];
-    const uint32_t nt = (n + kRsTile - 1) / kRsTile;
-    const uint32_t len = nt * kRsBins;
-    uint32_t* h = hist + (size_t)s * kRsBins * tiles_ub;
-    uint32_t carry = 0;
-    for (uint32_t base = 0; base < len; base += kThreads * 4) {
-        const uint32_t i = base + threadIdx.x * 4;
-        uint32_t v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = (i + j < len) ? h[i + j] : 0u;
-        uint32_t tot;
-        uint32_t off = block_excl_scan(v[0] + v[1] + v[2] + v[3], sm, tot) + carry;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (i + j < len) h[i + j] = off;
-            off += v[j];
-        }
-        carry += tot;
-    }
-}
-
-// ---- pass step 3: stable rank + scatter -------------------------------------------------------------------------
-// Dynamic shared memory: cnt[kWarps][256] | dstart[256] | gbase[256] | keys[4096] | vals[4096]
+// ---- one radix pass in one kernel: stable in-tile rank, decoupled look-back for the tile's digit offsets ---------
+// ("onesweep"): every tile publishes its per-digit counts in status[seg][tile][256] (2 flag bits + 30 count
+// bits in one word), then each of the 256 threads walks back over the predecessors' words of ITS digit until it
+// meets an inclusive prefix.  Tiles take their index from an atomic ticket so a predecessor is always resident
+// or finished before anyone waits on it.
+// Dynamic shared memory: keys[4096] | vals[4096] | cnt[kWarps][256] | dstart[256] | gbase[256] | scan[34]
 template <typename KeyT>
 constexpr size_t rs_scatter_smem() {
-    return (size_t)(kWarps * kRsBins + 2 * kRsBins + 34) * 4 + (size_t)kRsTile * (sizeof(KeyT) + 4);
+    return (size_t)(kWarps * kRsBins + 2 * kRsBins + 34 + 2) * 4 + (size_t)kRsTile * (sizeof(KeyT) + 4);
+}
+
+constexpr uint32_t kStLocal = 1u << 30, kStGlobal = 2u << 30, kStMask = (1u << 30) - 1u;
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 template <typename KeyT>
-__global__ void __launch_bounds__(kThreads) k_rs_scatter(KeyT* __restrict__ keys0, KeyT* __restrict__ keys1,
-                                                         uint32_t* __restrict__ vals0, uint32_t* __restrict__ vals1,
-                                                         const uint32_t* __restrict__ seg_off,
-                                                         const SortPlan* __restrict__ plan, int pass, uint32_t tiles_ub,
-                                                         const uint32_t* __restrict__ hist, int iota_first) {
+__global__ void __launch_bounds__(kThreads) k_rs_onesweep(KeyT* __restrict__ keys0, KeyT* __restrict__ keys1,
+                                                          uint32_t* __restrict__ vals0, uint32_t* __restrict__ vals1,
+                                                          const uint32_t* __restrict__ seg_off,
+                                                          const SortPlan* __restrict__ plan, int pass, int passes,
+                                                          uint32_t tiles_ub, const uint32_t* __restrict__ ghist,
+                                                          uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
+                                                          int iota_first) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
-    const int s = blockIdx.y;
-    const uint32_t t = blockIdx.x;
-    const SortPlan pl = plan[s];
-    if (!pl.active[pass]) return;
-    const uint32_t beg = seg_off[s], n = seg_off[s + 1] - beg;
-    const uint32_t nt = (n + kRsTile - 1) / kRsTile;
-    if (t >= nt) return;
     KeyT* s_keys = reinterpret_cast<KeyT*>(rs_smem);
     uint32_t* s_vals = reinterpret_cast<uint32_t*>(rs_smem + (size_t)kRsTile * sizeof(KeyT));
     uint32_t* cnt = s_vals + kRsTile;            // [kWarps][256]
     uint32_t* dstart = cnt + kWarps * kRsBins;   // [256] tile-local start of each digit run
     uint32_t* gbase = dstart + kRsBins;          // [256] segment-relative destination of each digit run
     uint32_t* s_scan = gbase + kRsBins;          // [34]
+    uint32_t* s_ticket = s_scan + 34;
+
+    if (threadIdx.x == 0) *s_ticket = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t lin = *s_ticket;
+    const int s = lin / tiles_ub;
+    const uint32_t t = lin - (uint32_t)s * tiles_ub;
+    const SortPlan pl = plan[s];
+    if (!pl.active[pass]) return;
+    const uint32_t beg = seg_off[s], n = seg_off[s + 1] - beg;
+    const uint32_t nt = (n + kRsTile - 1) / kRsTile;
+    if (t >= nt) return;
 
     const int par = pl.in_parity[pass];
     const KeyT* kin = (par ? keys1 : keys0) + beg;
     const uint32_t* vin = (par ? vals1 : vals0) + beg;
     KeyT* kout = (par ? keys0 : keys1) + beg;
     uint32_t* vout = (par ? vals0 : vals1) + beg;
-    const bool iota = iota_first && pl.in_parity[pass] == 0 && pass == 0;  // values are the global index
-    (void)iota;
+    bool first = true;
+    for (int q = 0; q < pass; ++q) first = first && !pl.active[q];
+    const bool iota = iota_first && first;   // values are the global element index, not read from memory
     const int shift = pass * 8, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
 
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) cnt[w * kRsBins + threadIdx.x] = 0;
-    gbase[threadIdx.x] = hist[(size_t)s * kRsBins * tiles_ub + (size_t)threadIdx.x * nt + t];
-    __syncthreads();
+    // exclusive scan of the segment's digit histogram = where each digit's run starts in the segment
+    uint32_t tot;
+    const uint32_t dbase = block_excl_scan(ghist[((size_t)s * passes + pass) * kRsBins + threadIdx.x], s_scan, tot);
 
     KeyT key[kRsItems];
     uint32_t val[kRsItems];
@@ -191,7 +189,7 @@ __global__ void __launch_bounds__(kThreads) k_rs_scatter(KeyT* __restrict__ keys
         const uint32_t i = wbase + r * 32 + lane;
         const bool valid = i < n;
         key[r] = valid ? kin[i] : ~(KeyT)0;
-        val[r] = valid ? (iota_first && pass == 0 ? beg + i : vin[i]) : 0u;
+        val[r] = valid ? (iota ? beg + i : vin[i]) : 0u;
     }
     uint32_t* wc = cnt + warp * kRsBins;
 #pragma unroll
@@ -216,7 +214,26 @@ __global__ void __launch_bounds__(kThreads) k_rs_scatter(KeyT* __restrict__ keys
         cnt[w * kRsBins + threadIdx.x] = run;
         run += c;
     }
-    uint32_t tot;
+    // real items of this digit in this tile (padding only ever inflates digit 255)
+    uint32_t real = run;
+    if (threadIdx.x == kRsBins - 1) real -= (kRsTile - ntile);
+    // publish, look back
+    uint32_t* st = status + ((size_t)s * tiles_ub + t) * kRsBins + threadIdx.x;
+    uint32_t prefix = 0;
+    if (t == 0) {
+        st_volatile_u32(st, kStGlobal | real);
+    } else {
+        st_volatile_u32(st, kStLocal | real);
+        const uint32_t* pst = st - kRsBins;
+        for (uint32_t back = t; back > 0; --back, pst -= kRsBins) {
+            uint32_t v;
+            while (((v = ld_volatile_u32(pst)) >> 30) == 0u) __nanosleep(32);
+            prefix += v & kStMask;
+            if ((v >> 30) == 2u) break;
+        }
+        st_volatile_u32(st, kStGlobal | (prefix + real));
+    }
+    gbase[threadIdx.x] = dbase + prefix;
     const uint32_t ds = block_excl_scan(run, s_scan, tot);
     dstart[threadIdx.x] = ds;
     __syncthreads();

@@ -17,7 +17,7 @@ SYMBOLS = [
     "o3r_cloud_transform", "o3r_cloud_append", "o3r_cloud_downsample", "o3r_cloud_size", "o3r_cloud_clear",
     "o3r_voxel_grid", "o3r_blur_u8", "o3r_frame_mask",
     "o3r_exchange_pack", "o3r_exchange_merge", "o3r_set_defer_merge",
-    "o3r_launch_count", "o3r_stream", "o3r_sync",
+    "o3r_launch_count", "o3r_stream", "o3r_sync", "o3r_profile", "o3r_profile_read",
 ]
 
 _lib = None
@@ -71,5 +71,7 @@ def load():
     L.o3r_stream.argtypes = [vp]
     L.o3r_stream.restype = vp
     L.o3r_sync.argtypes = [vp]
+    L.o3r_profile.argtypes = [vp, C.c_int]
+    L.o3r_profile_read.argtypes = [vp, C.c_char_p, sz]
     _lib = L
     return L

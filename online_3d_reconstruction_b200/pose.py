@@ -68,6 +68,20 @@ class Pose:
     def sync(self):
         self._check(self._L.o3r_sync(self._h))
 
+    def profile(self, enable):
+        """Per-kernel CUDA-event timing on/off (clears the records)."""
+        self._check(self._L.o3r_profile(self._h, int(enable)))
+
+    def profileRead(self):
+        """-> {kernel name: (launches, total_ms)} since profile(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self._L.o3r_profile_read(self._h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.split("\t")
+            out[name.strip("()")] = (int(n), float(ms))
+        return out
+
     # -- per-frame path --------------------------------------------------------------------------------
     def createAndTransformPtCloud(self, frame, disp_type=abi.DISP_U8):
         """pose.cpp:596-636 for one accepted image -> structured array of abi.POINT."""
