@@ -46,7 +46,7 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-enum { CNT_PTS = 0, CNT_VOX = 1, CNT_CYC = 2, CNT_NEW = 3, CNT_EMIT = 4, CNT_NEWSCAN = 5, CNT_N = 16 };
+enum { CNT_PTS = 0, CNT_VOX = 1, CNT_CYC = 2, CNT_NEW = 3, CNT_EMIT = 4, CNT_NEWSCAN = 5, CNT_CELLBB = 16, CNT_N = 32 };
 
 }  // namespace
 
@@ -67,7 +67,7 @@ struct o3r_ctx {
     DevBuf d_frames, d_blur, d_blurjobs;
     // per-batch work buffers
     DevBuf tile_cnt, tile_off, bbox, frame_off, grids, counters, pts, sortbuf, hist, plan_all, plan_v2, ghist;
-    DevBuf head_cnt, head_off, vox, vox_off, seg2, tmat, mask;
+    DevBuf head_cnt, head_off, vox, vox_off, seg2, tmat, mask, runwork;
     uint32_t* h_counters = nullptr;   // pinned
     uint32_t* h_offs = nullptr;       // pinned, frame offsets readback
     size_t h_offs_cap = 0;
@@ -75,6 +75,8 @@ struct o3r_ctx {
     int last_n = 0;
     size_t last_total = 0;
     bool last_is_vox = false;
+    bool last_has_cellbb = false;
+    int last_cellbb[6] = {0, 0, 0, 0, 0, 0};
     std::vector<uint32_t> last_off;
     // resident cloud: accumulators (ACCUMULATE) ...
     DevBuf res_keys[2], res_acc[2], res_rgb[2];
@@ -175,7 +177,8 @@ int carve_sort_u32(o3r_ctx* ctx, size_t n, SortU32& s) {
 // sorts + reduces; out/out_off sized by the caller.  CNT_VOX receives the total.
 int vg_sorted_reduce(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const uint32_t* seg_off, int n_seg,
                      size_t per_seg_cap, const GridParams* grids, float ix, float iy, float iz, uint32_t min_points,
-                     int z_shift, float4* out, uint32_t* out_off, uint64_t* out_keys, uint32_t* out_counts) {
+                     int z_shift, float4* out, uint32_t* out_off, uint64_t* out_keys, uint32_t* out_counts,
+                     bool track_cells = false) {
     CU(ctx->ghist.ensure((size_t)n_seg * 4 * kRsBins * 4));
     CU(ctx->plan_all.ensure((size_t)n_seg * sizeof(SortPlan)));
     CU(cudaMemsetAsync(ctx->ghist.p, 0, (size_t)n_seg * 4 * kRsBins * 4, ctx->st));
@@ -200,37 +203,32 @@ int vg_sorted_reduce(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const u
     LAUNCH(k_vg_heads, grid, kThreads, 0, A, ctx->head_cnt.as<uint32_t>());
     LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->head_cnt.as<uint32_t>(), ctx->head_off.as<uint32_t>(), (uint32_t)nt,
            cnt + CNT_VOX);
-    LAUNCH(k_vg_reduce, grid, kThreads, 0, A, ctx->head_off.as<uint32_t>(), cnt + CNT_VOX, out, out_off, n_seg,
-           out_keys, out_counts);
+    if (min_points <= 1 && !out_keys && !out_counts) {
+        const size_t wbytes = 64 + (nt + 1) * sizeof(RunCarry);
+        CU(ctx->runwork.ensure(wbytes));
+        CU(cudaMemsetAsync(ctx->runwork.p, 0, wbytes, ctx->st));
+        if (track_cells) LAUNCH(k_cellbb_init, 1, 32, 0, reinterpret_cast<int*>(cnt + CNT_CELLBB));
+        LAUNCH(k_vg_reduce_w, (uint32_t)nt, kThreads, 0, A, ctx->head_off.as<uint32_t>(), cnt + CNT_VOX, out, out_off,
+               n_seg, ctx->runwork.as<uint32_t>(), reinterpret_cast<RunCarry*>(ctx->runwork.as<char>() + 64),
+               track_cells ? 1 : 0, ctx->inv_c, ctx->inv_cz, reinterpret_cast<int*>(cnt + CNT_CELLBB));
+    } else
+        LAUNCH(k_vg_reduce, grid, kThreads, 0, A, ctx->head_off.as<uint32_t>(), cnt + CNT_VOX, out, out_off, n_seg,
+               out_keys, out_counts);
     return O3R_OK;
 }
 
 // ---- engine 2: merge `n` items (points or partial cells) into the resident accumulators --------------------------
-struct SortU64 { uint64_t *k0, *k1; uint32_t *v0, *v1; };
+inline int bits_for(long long range) { int b = 0; while ((1ll << b) <= range) ++b; return b; }
 
-int carve_sort_u64(o3r_ctx* ctx, size_t n, SortU64& s) {
-    const size_t n4 = (n + 63) & ~(size_t)63;
-    CU(ctx->sortbuf.ensure(n4 * 24));
-    s.k0 = ctx->sortbuf.as<uint64_t>();
-    s.k1 = s.k0 + n4;
-    s.v0 = reinterpret_cast<uint32_t*>(s.k1 + n4);
-    s.v1 = s.v0 + n4;
-    return O3R_OK;
-}
-
-// Builds the cycle's cell list (ckey/cacc/crgb, n_cyc) from items, continuing from the resident sums when
-// `use_resident`.  Leaves h_counters[CNT_CYC], [CNT_NEW] valid.
-template <typename Items>
-int acc_build_cycle(o3r_ctx* ctx, const Items& items, const float4* pts, const o3r_cell* cells, size_t n,
-                    bool use_resident) {
+template <typename KeyT, typename Items>
+int acc_build_cycle_t(o3r_ctx* ctx, const Items& items, size_t n, bool use_resident, const KeyCodec& kc, int passes) {
     uint32_t* cnt = ctx->counters.as<uint32_t>();
-    ctx->n_cyc = 0;
-    ctx->h_counters[CNT_CYC] = ctx->h_counters[CNT_NEW] = 0;
-    if (n == 0) return O3R_OK;
-    if (n >= (1ull << 32)) return ctx->fail(O3R_ERR_INVALID, "batch too large for 32-bit indices");
-    SortU64 sb;
-    int rc = carve_sort_u64(ctx, n, sb);
-    if (rc) return rc;
+    const size_t n4 = (n + 63) & ~(size_t)63;
+    CU(ctx->sortbuf.ensure(n4 * (2 * sizeof(KeyT) + 8)));
+    KeyT* k0 = ctx->sortbuf.as<KeyT>();
+    KeyT* k1 = k0 + n4;
+    uint32_t* v0 = reinterpret_cast<uint32_t*>(k1 + n4);
+    uint32_t* v1 = v0 + n4;
     CU(ctx->seg2.ensure(16));
     CU(ctx->ghist.ensure(kMaxPasses * kRsBins * 4));
     CU(ctx->plan_v2.ensure(sizeof(SortPlan)));
@@ -240,20 +238,17 @@ int acc_build_cycle(o3r_ctx* ctx, const Items& items, const float4* pts, const o
     CU(cudaMemsetAsync(cnt + CNT_NEW, 0, 4, ctx->st));
     const uint32_t* seg = ctx->seg2.as<uint32_t>();
     const uint32_t gk = std::min<uint32_t>(cdiv(n, kThreads), 148 * 8);
-    if (pts)
-        LAUNCH(k_acc_key_pts, gk, kThreads, 0, pts, seg + 1, ctx->inv_c, ctx->inv_c, ctx->inv_cz, sb.k0, sb.v0,
-               ctx->ghist.as<uint32_t>());
-    else
-        LAUNCH(k_acc_key_cells, gk, kThreads, 0, cells, (uint32_t)n, sb.k0, sb.v0, ctx->ghist.as<uint32_t>());
+    LAUNCH_N("k_acc_key", (k_acc_key<KeyT, Items>), gk, kThreads, 0, items, (uint32_t)n, ctx->inv_c, ctx->inv_cz, kc, passes,
+             k0, v0, ctx->ghist.as<uint32_t>());
     SortPlan* plan = ctx->plan_v2.as<SortPlan>();
-    LAUNCH(k_rs_plan, 1, kThreads, 0, ctx->ghist.as<uint32_t>(), seg, kMaxPasses, plan);
-    rc = sort_pairs<uint64_t>(ctx, sb.k0, sb.k1, sb.v0, sb.v1, seg, 1, n, plan, kMaxPasses, 0,
-                              ctx->ghist.as<uint32_t>());
+    LAUNCH(k_rs_plan, 1, kThreads, 0, ctx->ghist.as<uint32_t>(), seg, passes, plan);
+    int rc = sort_pairs<KeyT>(ctx, k0, k1, v0, v1, seg, 1, n, plan, passes, 0, ctx->ghist.as<uint32_t>());
     if (rc) return rc;
-    AccArgs A;
-    A.keys0 = sb.k0; A.keys1 = sb.k1; A.vals0 = sb.v0; A.vals1 = sb.v1;
+    AccArgs<KeyT> A;
+    A.keys0 = k0; A.keys1 = k1; A.vals0 = v0; A.vals1 = v1;
     A.seg_off = seg; A.plan = plan;
     A.tiles_ub = cdiv(n, kTileV);
+    A.kc = kc;
     const int cur = ctx->res_cur;
     A.res_keys = ctx->res_keys[cur].as<uint64_t>();
     A.res_acc = ctx->res_acc[cur].as<float4>();
@@ -264,15 +259,53 @@ int acc_build_cycle(o3r_ctx* ctx, const Items& items, const float4* pts, const o
     CU(ctx->ckey.ensure(n * 8));
     CU(ctx->cacc.ensure(n * 16));
     CU(ctx->crgb.ensure(n * 16));
-    LAUNCH(k_acc_heads, A.tiles_ub, kThreads, 0, A, ctx->head_cnt.as<uint32_t>());
+    const size_t wbytes = 64 + ((size_t)A.tiles_ub + 1) * sizeof(RunCarry);
+    CU(ctx->runwork.ensure(wbytes));
+    CU(cudaMemsetAsync(ctx->runwork.p, 0, wbytes, ctx->st));
+    LAUNCH_N("k_acc_heads", (k_acc_heads<KeyT>), A.tiles_ub, kThreads, 0, A, ctx->head_cnt.as<uint32_t>());
     LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->head_cnt.as<uint32_t>(), ctx->head_off.as<uint32_t>(), A.tiles_ub,
            cnt + CNT_CYC);
-    LAUNCH_N("k_acc_reduce", (k_acc_reduce<Items>), A.tiles_ub, kThreads, 0, A, items, ctx->head_off.as<uint32_t>(),
-           ctx->ckey.as<uint64_t>(), ctx->cacc.as<float4>(), ctx->crgb.as<uint4>(), cnt + CNT_NEW);
+    LAUNCH_N("k_acc_reduce", (k_acc_reduce<KeyT, Items>), A.tiles_ub, kThreads, 0, A, items, ctx->head_off.as<uint32_t>(),
+             ctx->ckey.as<uint64_t>(), ctx->cacc.as<float4>(), ctx->crgb.as<uint4>(), cnt + CNT_NEW,
+             ctx->runwork.as<uint32_t>(), reinterpret_cast<RunCarry*>(ctx->runwork.as<char>() + 64));
     rc = read_counters(ctx);
     if (rc) return rc;
     ctx->n_cyc = ctx->h_counters[CNT_CYC];
     return O3R_OK;
+}
+
+// Builds the cycle's cell list (ckey/cacc/crgb, n_cyc) from items, continuing from the resident sums when
+// `use_resident`.  `bb` = {imin,jmin,kmin,imax,jmax,kmax} of the items' combined-grid cells when the caller already
+// knows it (host), else null.  Leaves h_counters[CNT_CYC], [CNT_NEW] valid.
+template <typename Items>
+int acc_build_cycle(o3r_ctx* ctx, const Items& items, size_t n, bool use_resident, const int* bb) {
+    uint32_t* cnt = ctx->counters.as<uint32_t>();
+    ctx->n_cyc = 0;
+    ctx->h_counters[CNT_CYC] = ctx->h_counters[CNT_NEW] = 0;
+    if (n == 0) return O3R_OK;
+    if (n >= (1ull << 32)) return ctx->fail(O3R_ERR_INVALID, "batch too large for 32-bit indices");
+    int hb[6];
+    if (!bb) {
+        LAUNCH(k_cellbb_init, 1, 32, 0, reinterpret_cast<int*>(cnt + CNT_CELLBB));
+        LAUNCH_N("k_acc_cellbb", (k_acc_cellbb<Items>), std::min<uint32_t>(cdiv(n, kThreads), 148 * 8), kThreads, 0, items,
+                 (uint32_t)n, ctx->inv_c, ctx->inv_cz, reinterpret_cast<int*>(cnt + CNT_CELLBB));
+        int rc = read_counters(ctx);
+        if (rc) return rc;
+        memcpy(hb, ctx->h_counters + CNT_CELLBB, sizeof(hb));
+        bb = hb;
+    }
+    const int lim = (1 << 20) - 1;
+    for (int a = 0; a < 3; ++a)
+        if (bb[a] < -lim || bb[3 + a] > lim || bb[3 + a] < bb[a])
+            return ctx->fail(O3R_ERR_INVALID, "cloud extends beyond +-2^20 combined-grid cells (or is not finite)");
+    KeyCodec kc;
+    kc.imin = bb[0]; kc.jmin = bb[1]; kc.kmin = bb[2];
+    kc.wi = bits_for((long long)bb[3] - bb[0]);
+    kc.wj = bits_for((long long)bb[4] - bb[1]);
+    const int total = kc.wi + kc.wj + bits_for((long long)bb[5] - bb[2]);
+    const int passes = std::max(1, (total + 7) / 8);
+    if (total <= 32) return acc_build_cycle_t<uint32_t, Items>(ctx, items, n, use_resident, kc, passes);
+    return acc_build_cycle_t<uint64_t, Items>(ctx, items, n, use_resident, kc, passes);
 }
 
 // Applies the cycle's cell list to the resident shard: in-place update of found cells, sorted insert of new ones.
@@ -310,9 +343,9 @@ int acc_apply_cycle(o3r_ctx* ctx) {
     return O3R_OK;
 }
 
-int acc_merge_points(o3r_ctx* ctx, const float4* pts, size_t n) {
+int acc_merge_points(o3r_ctx* ctx, const float4* pts, size_t n, const int* bb) {
     AccItemsPts items{pts};
-    int rc = acc_build_cycle(ctx, items, pts, nullptr, n, true);
+    int rc = acc_build_cycle(ctx, items, n, true, bb);
     if (rc) return rc;
     return acc_apply_cycle(ctx);
 }
@@ -473,7 +506,7 @@ int frames_cloud_dev_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp
         CU(ctx->vox_off.ensure((size_t)(n + 1) * 4));
         rc = vg_sorted_reduce(ctx, sb, ctx->pts.as<float4>(), ctx->frame_off.as<uint32_t>(), n, per_frame_cap,
                               ctx->grids.as<GridParams>(), ctx->inv_f, ctx->inv_f, ctx->inv_f, 0, 0,
-                              ctx->vox.as<float4>(), ctx->vox_off.as<uint32_t>(), nullptr, nullptr);
+                              ctx->vox.as<float4>(), ctx->vox_off.as<uint32_t>(), nullptr, nullptr, !ctx->retain());
         if (rc) return rc;
         off_dev = ctx->vox_off.as<uint32_t>();
         ctx->last_is_vox = true;
@@ -485,7 +518,12 @@ int frames_cloud_dev_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp
         CU(cudaMallocHost((void**)&ctx->h_offs, ctx->h_offs_cap * 4));
     }
     CU(cudaMemcpyAsync(ctx->h_offs, off_dev, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, ctx->st));
+    ctx->last_has_cellbb = ctx->last_is_vox && !ctx->retain();
+    if (ctx->last_has_cellbb)
+        CU(cudaMemcpyAsync(ctx->h_counters + CNT_CELLBB, ctx->counters.as<uint32_t>() + CNT_CELLBB, 24,
+                           cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
+    if (ctx->last_has_cellbb) memcpy(ctx->last_cellbb, ctx->h_counters + CNT_CELLBB, 24);
     ctx->last_off.assign(ctx->h_offs, ctx->h_offs + n + 1);
     ctx->last_n = n;
     ctx->last_total = ctx->last_off[n];
@@ -494,7 +532,7 @@ int frames_cloud_dev_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp
     if (!opt.merge || ctx->defer_merge) return O3R_OK;
     const float4* outp = ctx->last_is_vox ? ctx->vox.as<float4>() : ctx->pts.as<float4>();
     if (ctx->retain()) return cloud_append_dev(ctx, outp, ctx->last_total);
-    return acc_merge_points(ctx, outp, ctx->last_total);
+    return acc_merge_points(ctx, outp, ctx->last_total, ctx->last_has_cellbb ? ctx->last_cellbb : nullptr);
 }
 
 // copies the frames' inputs to device staging and rewrites the pointers
@@ -644,7 +682,7 @@ void o3r_destroy(o3r_ctx* ctx) {
                       &ctx->d_frames, &ctx->d_blur, &ctx->d_blurjobs, &ctx->tile_cnt, &ctx->tile_off, &ctx->bbox,
                       &ctx->frame_off, &ctx->grids, &ctx->counters, &ctx->pts, &ctx->sortbuf, &ctx->hist,
                       &ctx->plan_all, &ctx->plan_v2, &ctx->ghist, &ctx->head_cnt, &ctx->head_off, &ctx->vox,
-                      &ctx->vox_off, &ctx->seg2, &ctx->tmat, &ctx->mask, &ctx->res_keys[0], &ctx->res_keys[1],
+                      &ctx->vox_off, &ctx->seg2, &ctx->tmat, &ctx->mask, &ctx->runwork, &ctx->res_keys[0], &ctx->res_keys[1],
                       &ctx->res_acc[0], &ctx->res_acc[1], &ctx->res_rgb[0], &ctx->res_rgb[1], &ctx->ckey, &ctx->cacc,
                       &ctx->crgb, &ctx->new_cnt, &ctx->new_off, &ctx->new_keys, &ctx->okeys, &ctx->cloud};
     for (DevBuf* b : bufs) b->release();
@@ -804,8 +842,8 @@ int o3r_cloud_append(o3r_ctx* ctx, const o3r_point* pts, size_t n) {
     }
     CU(ctx->vox.ensure(n * 16));
     CU(cudaMemcpyAsync(ctx->vox.p, pts, n * 16, cudaMemcpyHostToDevice, ctx->st));
-    ctx->last_n = 0; ctx->last_total = 0;   // the batch buffer was overwritten
-    return acc_merge_points(ctx, ctx->vox.as<float4>(), n);
+    ctx->last_n = 0; ctx->last_total = 0; ctx->last_has_cellbb = false;   // the batch buffer was overwritten
+    return acc_merge_points(ctx, ctx->vox.as<float4>(), n, nullptr);
 }
 
 int o3r_cloud_size(o3r_ctx* ctx, size_t* n) {
@@ -962,7 +1000,7 @@ int o3r_exchange_pack(o3r_ctx* ctx, int world, o3r_cell* send_dev, size_t cap, u
     std::fill(counts, counts + world, 0u);
     if (!ctx->last_is_vox || ctx->last_total == 0) { ctx->n_cyc = 0; return O3R_OK; }
     AccItemsPts items{ctx->vox.as<float4>()};
-    int rc = acc_build_cycle(ctx, items, ctx->vox.as<float4>(), nullptr, ctx->last_total, false);
+    int rc = acc_build_cycle(ctx, items, ctx->last_total, false, ctx->last_has_cellbb ? ctx->last_cellbb : nullptr);
     if (rc) return rc;
     const uint32_t n = ctx->n_cyc;
     if (n == 0) return O3R_OK;
@@ -999,7 +1037,7 @@ int o3r_exchange_merge(o3r_ctx* ctx, const o3r_cell* recv_dev, size_t n) {
     if (ctx->retain()) return ctx->fail(O3R_ERR_UNSUPPORTED, "exchange needs O3R_MERGE_ACCUMULATE");
     if (n == 0) return O3R_OK;
     AccItemsCells items{recv_dev};
-    int rc = acc_build_cycle(ctx, items, nullptr, recv_dev, n, true);
+    int rc = acc_build_cycle(ctx, items, n, true, nullptr);
     if (rc) return rc;
     return acc_apply_cycle(ctx);
 }

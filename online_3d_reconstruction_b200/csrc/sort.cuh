@@ -79,6 +79,18 @@ __global__ void k_rs_plan(const uint32_t* __restrict__ ghist, const uint32_t* __
 template <typename KeyT>
 __device__ __forceinline__ uint32_t rs_digit(KeyT k, int shift) { return (uint32_t)(k >> shift) & 255u; }
 
+// shared-memory histogram update by the lanes of `vm`: one aggregated atomic when the whole warp agrees on the
+// digit (the constant high digits that would otherwise serialise), plain atomics otherwise
+__device__ __forceinline__ void hist_add(uint32_t* sh, uint32_t d, unsigned vm, int lane) {
+    int uniform;
+    __match_all_sync(vm, d, &uniform);
+    if (uniform) {
+        if (lane == __ffs(vm) - 1) atomicAdd(&sh[d], (uint32_t)__popc(vm));
+    } else {
+        atomicAdd(&sh[d], 1u);
+    }
+}
+
 // ---- whole-segment digit histograms for every pass in one read of the keys ------------------------------------
 // ghist[S][PASSES][256]; must be zeroed by the caller.
 template <typename KeyT, int PASSES>
@@ -100,11 +112,7 @@ __global__ void __launch_bounds__(kThreads) k_rs_ghist(const KeyT* __restrict__ 
         if (valid) {
             const KeyT k = keys[beg + i];
 #pragma unroll
-            for (int p = 0; p < PASSES; ++p) {
-                const uint32_t d = rs_digit(k, 8 * p);
-                const unsigned peers = __match_any_sync(vm, d);
-                if (lane == __ffs(peers) - 1) atomicAdd(&sh[p * kRsBins + d], (uint32_t)__popc(peers));
-            }
+            for (int p = 0; p < PASSES; ++p) hist_add(sh + p * kRsBins, rs_digit(k, 8 * p), vm, lane);
         }
     }
     __syncthreads();
@@ -125,17 +133,18 @@ constexpr size_t rs_scatter_smem() {
 
 constexpr uint32_t kStLocal = 1u << 30, kStGlobal = 2u << 30, kStMask = (1u << 30) - 1u;
 
+// flag + payload live in ONE word, so relaxed gpu-scope accesses are enough (no fence, no system scope)
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
     uint32_t v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
-    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 template <typename KeyT>
-__global__ void __launch_bounds__(kThreads) k_rs_onesweep(KeyT* __restrict__ keys0, KeyT* __restrict__ keys1,
+__global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? 4 : 3) k_rs_onesweep(KeyT* __restrict__ keys0, KeyT* __restrict__ keys1,
                                                           uint32_t* __restrict__ vals0, uint32_t* __restrict__ vals1,
                                                           const uint32_t* __restrict__ seg_off,
                                                           const SortPlan* __restrict__ plan, int pass, int passes,
@@ -180,16 +189,13 @@ __global__ void __launch_bounds__(kThreads) k_rs_onesweep(KeyT* __restrict__ key
     const uint32_t dbase = block_excl_scan(ghist[((size_t)s * passes + pass) * kRsBins + threadIdx.x], s_scan, tot);
 
     KeyT key[kRsItems];
-    uint32_t val[kRsItems];
-    uint16_t rank[kRsItems];
+    uint32_t rk[kRsItems / 2];   // two 16-bit in-warp ranks per word
     const uint32_t wbase = t * kRsTile + warp * (32 * kRsItems);
     const uint32_t ntile = min((uint32_t)kRsTile, n - t * kRsTile);
 #pragma unroll
     for (int r = 0; r < kRsItems; ++r) {
         const uint32_t i = wbase + r * 32 + lane;
-        const bool valid = i < n;
-        key[r] = valid ? kin[i] : ~(KeyT)0;
-        val[r] = valid ? (iota ? beg + i : vin[i]) : 0u;
+        key[r] = (i < n) ? kin[i] : ~(KeyT)0;
     }
     uint32_t* wc = cnt + warp * kRsBins;
 #pragma unroll
@@ -198,12 +204,19 @@ __global__ void __launch_bounds__(kThreads) k_rs_onesweep(KeyT* __restrict__ key
         // precede a real item inside any digit run
         const uint32_t d = rs_digit(key[r], shift);
         const unsigned peers = __match_any_sync(kFull, d);
-        const int leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if (lane == leader) { old = wc[d]; wc[d] = old + __popc(peers); }
-        old = __shfl_sync(kFull, old, leader);
-        rank[r] = (uint16_t)(old + __popc(peers & lt));
+        const uint32_t old = wc[d];                   // every peer reads the counter (broadcast) ...
         __syncwarp();
+        if ((peers & lt) == 0u) wc[d] = old + __popc(peers);   // ... then the lowest peer bumps it
+        __syncwarp();
+        const uint32_t rnk = old + __popc(peers & lt);
+        if (r & 1) rk[r >> 1] |= rnk << 16; else rk[r >> 1] = rnk;
+    }
+    // values are only needed for the exchange below: load them now so the latency hides behind the scans
+    uint32_t val[kRsItems];
+#pragma unroll
+    for (int r = 0; r < kRsItems; ++r) {
+        const uint32_t i = wbase + r * 32 + lane;
+        val[r] = (i < n) ? (iota ? beg + i : vin[i]) : 0u;
     }
     __syncthreads();
     // per digit: exclusive prefix over warps, tile total
@@ -233,22 +246,21 @@ __global__ void __launch_bounds__(kThreads) k_rs_onesweep(KeyT* __restrict__ key
         }
         st_volatile_u32(st, kStGlobal | (prefix + real));
     }
-    gbase[threadIdx.x] = dbase + prefix;
     const uint32_t ds = block_excl_scan(run, s_scan, tot);
     dstart[threadIdx.x] = ds;
+    gbase[threadIdx.x] = dbase + prefix - ds;   // destination of tile-local position i of this digit: gbase[d] + i
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < kRsItems; ++r) {
         const uint32_t d = rs_digit(key[r], shift);
-        const uint32_t pos = dstart[d] + wc[d] + rank[r];
+        const uint32_t pos = dstart[d] + wc[d] + ((rk[r >> 1] >> ((r & 1) * 16)) & 0xffffu);
         s_keys[pos] = key[r];
         s_vals[pos] = val[r];
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < ntile; i += kThreads) {
         const KeyT k = s_keys[i];
-        const uint32_t d = rs_digit(k, shift);
-        const uint32_t g = gbase[d] + (i - dstart[d]);
+        const uint32_t g = gbase[rs_digit(k, shift)] + i;
         kout[g] = k;
         vout[g] = s_vals[i];
     }

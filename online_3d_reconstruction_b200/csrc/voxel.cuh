@@ -194,104 +194,329 @@ __global__ void __launch_bounds__(kThreads) k_vg_reduce(VgArgs A, const uint32_t
 // every element its own run, so k_vg_reduce reproduces them — except that a centroid of one point is
 // sum/1 = the point and uint32(c/1) = c, i.e. bit-identical.  Nothing extra to do.
 
-// ---- engine 2: incremental merge on the combined grid -----------------------------------------------------------
-struct AccItemsPts {   // items are points of weight 1 (z gets +500)
-    const float4* pts;
-    __device__ __forceinline__ void add(uint32_t v, float& sx, float& sy, float& sz, uint32_t& n, uint32_t& sr,
-                                        uint32_t& sg, uint32_t& sb) const {
+// ---- CTA-cooperative run reduction (shared by both engines) --------------------------------------------------------
+// A CTA owns kTileV consecutive sorted elements.  All threads stage the tile's items into shared memory
+// (coalesced key/value loads, gathered item loads), then ONE thread per run adds the run's items strictly in
+// sorted (= input) order from shared memory — the oracle's sequential loop, so sums are bit-identical —
+// which costs only FADD latency, not memory latency.
+// A run that crosses a tile boundary is handed on: the tile where it is still open publishes its partial sums
+// (RunCarry, flag last), the next tile's carry thread waits for them, continues with its leading elements and
+// either emits the run or hands it on again.  Tiles take their index from an atomic ticket, so the tile being
+// waited for is always resident or finished.  Every run is emitted (no min-points filter here).
+struct RunCarry {
+    float sx, sy, sz;
+    uint32_t n, r, g, b, slot, tag, first;
+    uint32_t pad;
+    uint32_t flag;
+};  // 48 bytes
+
+template <typename KeyT>
+struct RunSmem {
+    float4 a[kTileV];   // x, y, z, n (uint bits)
+    uint4 c[kTileV];    // r, g, b, value (index of the item)
+    uint16_t hpos[kTileV + 2];
+    uint32_t scan[34];
+    uint32_t ticket;
+};
+
+// sequential sum of staged items [a, e): loads batched 4 at a time so only the FADD chain is serial
+template <typename KeyT>
+__device__ __forceinline__ void run_sum(const RunSmem<KeyT>& S, uint32_t a, uint32_t e, float& sx, float& sy, float& sz,
+                                        uint32_t& cn, uint32_t& cr, uint32_t& cg, uint32_t& cb) {
+    uint32_t i = a;
+    for (; i + 4 <= e; i += 4) {
+        float4 p[4];
+        uint4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { p[u] = S.a[i + u]; q[u] = S.c[i + u]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            sx = __fadd_rn(sx, p[u].x); sy = __fadd_rn(sy, p[u].y); sz = __fadd_rn(sz, p[u].z);
+            cn += __float_as_uint(p[u].w); cr += q[u].x; cg += q[u].y; cb += q[u].z;
+        }
+    }
+    for (; i < e; ++i) {
+        const float4 p = S.a[i];
+        const uint4 q = S.c[i];
+        sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z);
+        cn += __float_as_uint(p.w); cr += q.x; cg += q.y; cb += q.z;
+    }
+}
+
+__device__ __forceinline__ void carry_publish(RunCarry* c, float sx, float sy, float sz, uint32_t n, uint32_t r, uint32_t g,
+                                              uint32_t b, uint32_t slot, uint32_t tag, uint32_t first) {
+    c->sx = sx; c->sy = sy; c->sz = sz; c->n = n; c->r = r; c->g = g; c->b = b; c->slot = slot; c->tag = tag;
+    c->first = first;
+    __threadfence();
+    st_volatile_u32(&c->flag, 1u);
+}
+
+// `carry` points at this tile's RunCarry; carry[-1] is the previous tile of the same segment.
+template <typename KeyT, typename Pol>
+__device__ __forceinline__ void run_reduce_tile(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                uint32_t n, uint32_t t, uint32_t slot0, Pol& pol, RunSmem<KeyT>& S,
+                                                RunCarry* __restrict__ carry) {
+    const int tid = threadIdx.x;
+    const uint32_t wbase = t * kTileV;
+    const uint32_t wn = min((uint32_t)kTileV, n - wbase);
+    // ---- stage the tile
+    uint32_t flags = 0;
+    {
+        const uint32_t p0 = wbase + tid * 4;
+        KeyT prev = (p0 > 0 && p0 < n) ? keys[p0 - 1] : (KeyT)0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t pos = p0 + j;
+            if (pos < n) {
+                const KeyT key = keys[pos];
+                if (pos == 0 || key != prev) flags |= 1u << j;
+                prev = key;
+                const uint32_t v = vals[pos];
+                const int e = tid * 4 + j;
+                float x, y, z; uint32_t in, ir, ig, ib;
+                pol.load(v, x, y, z, in, ir, ig, ib);
+                S.a[e] = make_float4(x, y, z, __uint_as_float(in));
+                S.c[e] = make_uint4(ir, ig, ib, v);
+            }
+        }
+    }
+    uint32_t H;
+    uint32_t hoff = block_excl_scan((uint32_t)__popc(flags), S.scan, H);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (flags & (1u << j)) S.hpos[hoff++] = (uint16_t)(tid * 4 + j);
+    if (tid == 0) S.hpos[H] = (uint16_t)wn;
+    __syncthreads();
+    const bool more = wbase + wn < n;              // the segment continues after this tile
+    // ---- one thread per run whose head lies in the tile
+    for (uint32_t rI = tid; rI < H; rI += kThreads) {
+        const uint32_t a = S.hpos[rI], e = S.hpos[rI + 1];
+        const KeyT key = keys[wbase + a];
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        uint32_t cn = 0, cr = 0, cg = 0, cb = 0, tag = 0;
+        pol.start(key, sx, sy, sz, cn, cr, cg, cb, tag);
+        const uint32_t first_v = S.c[a].w;
+        run_sum(S, a, e, sx, sy, sz, cn, cr, cg, cb);
+        if (rI == H - 1 && more && keys[wbase + wn] == key)   // still open at the tile end: hand it on
+            carry_publish(carry, sx, sy, sz, cn, cr, cg, cb, slot0 + rI, tag, first_v);
+        else
+            pol.emit(slot0 + rI, key, sx, sy, sz, cn, cr, cg, cb, tag, first_v);
+    }
+    // ---- the run handed over by the previous tile: its elements are the tile's leading ones
+    const uint32_t lead = H ? S.hpos[0] : wn;
+    if (tid == kThreads - 1 && lead > 0) {
+        const RunCarry* pc = carry - 1;
+        while (ld_volatile_u32(&pc->flag) == 0u) __nanosleep(64);
+        __threadfence();
+        float sx = __ldcg(&pc->sx), sy = __ldcg(&pc->sy), sz = __ldcg(&pc->sz);
+        uint32_t cn = __ldcg(&pc->n), cr = __ldcg(&pc->r), cg = __ldcg(&pc->g), cb = __ldcg(&pc->b);
+        const uint32_t slot = __ldcg(&pc->slot), tag = __ldcg(&pc->tag), first_v = __ldcg(&pc->first);
+        run_sum(S, 0u, lead, sx, sy, sz, cn, cr, cg, cb);
+        const KeyT key = keys[wbase];
+        if (H == 0 && more && keys[wbase + wn] == key)
+            carry_publish(carry, sx, sy, sz, cn, cr, cg, cb, slot, tag, first_v);
+        else
+            pol.emit(slot, key, sx, sy, sz, cn, cr, cg, cb, tag, first_v);
+    }
+}
+
+// engine 1 policy: CentroidPoint of a VoxelGrid leaf.  Optionally tracks the range of combined-grid cells the
+// emitted centroids fall in (so the merge can sort compact keys).
+struct VgPol {
+    const float4* pts; float4* out; int z_shift; bool verbatim;
+    int want_cells; float icx, icz;
+    int mn[3], mx[3];
+    __device__ __forceinline__ void load(uint32_t v, float& x, float& y, float& z, uint32_t& n, uint32_t& r, uint32_t& g,
+                                         uint32_t& b) const {
         const float4 p = pts[v];
         const uint32_t c = __float_as_uint(p.w);
-        sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, __fadd_rn(p.z, 500.0f));
-        n += 1; sr += (c >> 16) & 255u; sg += (c >> 8) & 255u; sb += c & 255u;
+        x = p.x; y = p.y; z = z_shift ? __fadd_rn(p.z, 500.0f) : p.z;
+        n = 1; r = (c >> 16) & 255u; g = (c >> 8) & 255u; b = c & 255u;
+    }
+    __device__ __forceinline__ void start(uint32_t, float&, float&, float&, uint32_t&, uint32_t&, uint32_t&, uint32_t&,
+                                          uint32_t&) const {}
+    __device__ __forceinline__ void emit(uint32_t slot, uint32_t, float sx, float sy, float sz, uint32_t n, uint32_t r,
+                                         uint32_t g, uint32_t b, uint32_t, uint32_t first) {
+        float4 o;
+        if (verbatim) {   // PCL: output = *input_
+            o = pts[first];
+        } else {
+            const float fn = (float)n;
+            float cz = __fdiv_rn(sz, fn);
+            if (z_shift) cz = __fsub_rn(cz, 500.0f);
+            const uint32_t rgb = ((uint32_t)__fdiv_rn((float)r, fn) << 16) | ((uint32_t)__fdiv_rn((float)g, fn) << 8) |
+                                 (uint32_t)__fdiv_rn((float)b, fn);
+            o = make_float4(__fdiv_rn(sx, fn), __fdiv_rn(sy, fn), cz, __uint_as_float(rgb));
+        }
+        out[slot] = o;
+        if (want_cells) {
+            const int ci = (int)floorf(__fmul_rn(o.x, icx)), cj = (int)floorf(__fmul_rn(o.y, icx)),
+                      ck = (int)floorf(__fmul_rn(__fadd_rn(o.z, 500.0f), icz));
+            mn[0] = min(mn[0], ci); mx[0] = max(mx[0], ci);
+            mn[1] = min(mn[1], cj); mx[1] = max(mx[1], cj);
+            mn[2] = min(mn[2], ck); mx[2] = max(mx[2], ck);
+        }
+    }
+};
+
+// fast path of engine 1: every run is emitted (min_points <= 1), no key / count outputs.
+// Linear grid of tiles_ub * n_seg CTAs; work[0] is the ticket, carries follow.
+__global__ void __launch_bounds__(kThreads) k_vg_reduce_w(VgArgs A, const uint32_t* __restrict__ head_off,
+                                                          const uint32_t* __restrict__ head_total,
+                                                          float4* __restrict__ out, uint32_t* __restrict__ seg_out_off,
+                                                          int n_seg, uint32_t* __restrict__ ticket,
+                                                          RunCarry* __restrict__ carries, int want_cells, float icx,
+                                                          float icz, int* __restrict__ cellbb) {
+    __shared__ RunSmem<uint32_t> S;
+    __shared__ int s_bb[6];
+    if (threadIdx.x == 0) S.ticket = atomicAdd(ticket, 1u);
+    if (threadIdx.x < 6) s_bb[threadIdx.x] = threadIdx.x < 3 ? 0x7fffffff : (int)0x80000000;
+    __syncthreads();
+    const uint32_t lin = S.ticket;
+    const int s = lin / A.tiles_ub;
+    const uint32_t t = lin - (uint32_t)s * A.tiles_ub;
+    if (t == 0 && threadIdx.x == 0) {
+        seg_out_off[s] = head_off[(size_t)s * A.tiles_ub];
+        if (s == n_seg - 1) seg_out_off[n_seg] = *head_total;
+    }
+    const uint32_t beg = A.seg_off[s], n = A.seg_off[s + 1] - beg;
+    if (t * kTileV >= n) return;
+    const int par = A.plan[s].final_parity;
+    VgPol pol{A.pts, out, A.z_shift, A.grids && A.grids[s].passthrough, want_cells, icx, icz,
+              {0x7fffffff, 0x7fffffff, 0x7fffffff}, {(int)0x80000000, (int)0x80000000, (int)0x80000000}};
+    run_reduce_tile<uint32_t, VgPol>((par ? A.keys1 : A.keys0) + beg, (par ? A.vals1 : A.vals0) + beg, n, t,
+                                     head_off[(size_t)s * A.tiles_ub + t], pol, S, carries + lin);
+    if (want_cells) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int lo = __reduce_min_sync(kFull, pol.mn[a]), hi = __reduce_max_sync(kFull, pol.mx[a]);
+            if ((threadIdx.x & 31) == 0) { atomicMin(&s_bb[a], lo); atomicMax(&s_bb[3 + a], hi); }
+        }
+        __syncthreads();
+        if (threadIdx.x < 3) atomicMin(&cellbb[threadIdx.x], s_bb[threadIdx.x]);
+        else if (threadIdx.x < 6) atomicMax(&cellbb[threadIdx.x], s_bb[threadIdx.x]);
+    }
+}
+
+// ---- engine 2: incremental merge on the combined grid -----------------------------------------------------------
+// The cycle's items are sorted by a COMPACT key: cell coordinates relative to the cycle's minimum cell, packed
+// (k | j | i) into just the bits the cycle's extent needs (3 radix passes instead of 6-8 on the absolute key).
+// Field-wise subtraction of a constant keeps the (k, j, i) lexicographic order, so the sorted cycle list is in
+// the same order as the resident shard, which stores the absolute key.
+struct KeyCodec {
+    int imin, jmin, kmin;
+    int wi, wj;           // bit widths of the i and j fields
+    __device__ __forceinline__ uint64_t pack(int i, int j, int k) const {
+        return ((uint64_t)(uint32_t)(k - kmin) << (wi + wj)) | ((uint64_t)(uint32_t)(j - jmin) << wi) |
+               (uint64_t)(uint32_t)(i - imin);
+    }
+    __device__ __forceinline__ uint64_t to_abs(uint64_t c) const {
+        const long long B = 1 << 20;
+        const long long i = (long long)(c & ((1ull << wi) - 1ull)) + imin;
+        const long long j = (long long)((c >> wi) & ((1ull << wj) - 1ull)) + jmin;
+        const long long k = (long long)(c >> (wi + wj)) + kmin;
+        return ((uint64_t)(k + B) << 42) | ((uint64_t)(j + B) << 21) | (uint64_t)(i + B);
+    }
+};
+
+struct AccItemsPts {   // items are points of weight 1 (z gets +500)
+    const float4* pts;
+    __device__ __forceinline__ void get(uint32_t v, float& x, float& y, float& z, uint32_t& n, uint32_t& r, uint32_t& g,
+                                        uint32_t& b) const {
+        const float4 p = pts[v];
+        const uint32_t c = __float_as_uint(p.w);
+        x = p.x; y = p.y; z = __fadd_rn(p.z, 500.0f);
+        n = 1; r = (c >> 16) & 255u; g = (c >> 8) & 255u; b = c & 255u;
+    }
+    __device__ __forceinline__ void cell(uint32_t v, float ix, float iz, int& i, int& j, int& k) const {
+        const float4 p = pts[v];
+        i = (int)floorf(__fmul_rn(p.x, ix)); j = (int)floorf(__fmul_rn(p.y, ix));
+        k = (int)floorf(__fmul_rn(__fadd_rn(p.z, 500.0f), iz));
     }
 };
 struct AccItemsCells {  // items are partial cells received from other ranks
     const o3r_cell* cells;
-    __device__ __forceinline__ void add(uint32_t v, float& sx, float& sy, float& sz, uint32_t& n, uint32_t& sr,
-                                        uint32_t& sg, uint32_t& sb) const {
+    __device__ __forceinline__ void get(uint32_t v, float& x, float& y, float& z, uint32_t& n, uint32_t& r, uint32_t& g,
+                                        uint32_t& b) const {
         const o3r_cell c = cells[v];
-        sx = __fadd_rn(sx, c.sx); sy = __fadd_rn(sy, c.sy); sz = __fadd_rn(sz, c.sz);
-        n += c.n; sr += c.sr; sg += c.sg; sb += c.sb;
+        x = c.sx; y = c.sy; z = c.sz; n = c.n; r = c.sr; g = c.sg; b = c.sb;
+    }
+    __device__ __forceinline__ void cell(uint32_t v, float, float, int& i, int& j, int& k) const {
+        const uint64_t key = cells[v].key;
+        const int B = 1 << 20;
+        i = (int)(key & 0x1fffffu) - B; j = (int)((key >> 21) & 0x1fffffu) - B; k = (int)(key >> 42) - B;
     }
 };
 
-// keys of the cycle's points on the combined grid + whole-array digit histograms (for the sort plan)
-__global__ void __launch_bounds__(kThreads) k_acc_key_pts(const float4* __restrict__ pts, const uint32_t* __restrict__ n_ptr,
-                                                          float ix, float iy, float iz, uint64_t* __restrict__ keys,
-                                                          uint32_t* __restrict__ vals, uint32_t* __restrict__ ghist) {
-    __shared__ uint32_t sh[kMaxPasses * kRsBins];
-    for (int i = threadIdx.x; i < kMaxPasses * kRsBins; i += kThreads) sh[i] = 0;
-    __syncthreads();
-    const uint32_t n = *n_ptr;
-    const int lane = threadIdx.x & 31;
-    for (uint32_t base = blockIdx.x * kThreads; base < n; base += gridDim.x * kThreads) {
-        const uint32_t i = base + threadIdx.x;
-        const bool valid = i < n;
-        uint64_t k = 0;
-        if (valid) {
-            const float4 p = pts[i];
-            k = abs_cell_key(p.x, p.y, __fadd_rn(p.z, 500.0f), ix, iy, iz);
-            keys[i] = k;
-            vals[i] = i;
-        }
-        const unsigned vm = __ballot_sync(kFull, valid);
-        if (valid) {
+// range of combined-grid cells of n items (only when the range was not tracked upstream)
+template <typename Items>
+__global__ void __launch_bounds__(kThreads) k_acc_cellbb(Items items, uint32_t n, float ix, float iz, int* __restrict__ cellbb) {
+    int mn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, mx[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+    for (uint32_t v = blockIdx.x * kThreads + threadIdx.x; v < n; v += gridDim.x * kThreads) {
+        int c[3];
+        items.cell(v, ix, iz, c[0], c[1], c[2]);
 #pragma unroll
-            for (int p = 0; p < kMaxPasses; ++p) {
-                const uint32_t d = (uint32_t)(k >> (8 * p)) & 255u;
-                const unsigned peers = __match_any_sync(vm, d);
-                if (lane == __ffs(peers) - 1) atomicAdd(&sh[p * kRsBins + d], (uint32_t)__popc(peers));
-            }
-        }
+        for (int a = 0; a < 3; ++a) { mn[a] = min(mn[a], c[a]); mx[a] = max(mx[a], c[a]); }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < kMaxPasses * kRsBins; i += kThreads)
-        if (sh[i]) atomicAdd(&ghist[i], sh[i]);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int lo = __reduce_min_sync(kFull, mn[a]), hi = __reduce_max_sync(kFull, mx[a]);
+        if ((threadIdx.x & 31) == 0) { atomicMin(&cellbb[a], lo); atomicMax(&cellbb[3 + a], hi); }
+    }
 }
 
-__global__ void __launch_bounds__(kThreads) k_acc_key_cells(const o3r_cell* __restrict__ cells, uint32_t n,
-                                                            uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                            uint32_t* __restrict__ ghist) {
+__global__ void k_cellbb_init(int* cellbb) {
+    if (threadIdx.x < 6) cellbb[threadIdx.x] = threadIdx.x < 3 ? 0x7fffffff : (int)0x80000000;
+}
+
+// compact keys of the cycle's items + whole-array digit histograms for `passes` digits
+template <typename KeyT, typename Items>
+__global__ void __launch_bounds__(kThreads) k_acc_key(Items items, uint32_t n, float ix, float iz, KeyCodec kc, int passes,
+                                                      KeyT* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                      uint32_t* __restrict__ ghist) {
     __shared__ uint32_t sh[kMaxPasses * kRsBins];
-    for (int i = threadIdx.x; i < kMaxPasses * kRsBins; i += kThreads) sh[i] = 0;
+    for (int i = threadIdx.x; i < passes * kRsBins; i += kThreads) sh[i] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     for (uint32_t base = blockIdx.x * kThreads; base < n; base += gridDim.x * kThreads) {
-        const uint32_t i = base + threadIdx.x;
-        const bool valid = i < n;
-        uint64_t k = 0;
-        if (valid) { k = cells[i].key; keys[i] = k; vals[i] = i; }
-        const unsigned vm = __ballot_sync(kFull, valid);
+        const uint32_t v = base + threadIdx.x;
+        const bool valid = v < n;
+        KeyT k = 0;
         if (valid) {
-#pragma unroll
-            for (int p = 0; p < kMaxPasses; ++p) {
-                const uint32_t d = (uint32_t)(k >> (8 * p)) & 255u;
-                const unsigned peers = __match_any_sync(vm, d);
-                if (lane == __ffs(peers) - 1) atomicAdd(&sh[p * kRsBins + d], (uint32_t)__popc(peers));
-            }
+            int ci, cj, ck;
+            items.cell(v, ix, iz, ci, cj, ck);
+            k = (KeyT)kc.pack(ci, cj, ck);
+            keys[v] = k;
+            vals[v] = v;
         }
+        const unsigned vm = __ballot_sync(kFull, valid);
+        if (valid)
+            for (int p = 0; p < passes; ++p) hist_add(sh + p * kRsBins, (uint32_t)(k >> (8 * p)) & 255u, vm, lane);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kMaxPasses * kRsBins; i += kThreads)
+    for (int i = threadIdx.x; i < passes * kRsBins; i += kThreads)
         if (sh[i]) atomicAdd(&ghist[i], sh[i]);
 }
 
+template <typename KeyT>
 struct AccArgs {
-    const uint64_t* keys0; const uint64_t* keys1;
+    const KeyT* keys0; const KeyT* keys1;
     const uint32_t* vals0; const uint32_t* vals1;
     const uint32_t* seg_off;      // [2] = {0, n}
     const SortPlan* plan;         // [1]
     uint32_t tiles_ub;
-    // resident shard (sorted by key)
+    KeyCodec kc;
+    // resident shard (sorted by absolute key)
     const uint64_t* res_keys; float4* res_acc; uint4* res_rgb; uint32_t n_res;
 };
 
-__global__ void __launch_bounds__(kThreads) k_acc_heads(AccArgs A, uint32_t* __restrict__ head_cnt) {
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads) k_acc_heads(AccArgs<KeyT> A, uint32_t* __restrict__ head_cnt) {
     const uint32_t t = blockIdx.x;
     const uint32_t n = A.seg_off[1];
     uint32_t c = 0;
     if (t * kTileV < n) {
-        const uint64_t* keys = A.plan[0].final_parity ? A.keys1 : A.keys0;
+        const KeyT* keys = A.plan[0].final_parity ? A.keys1 : A.keys0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint32_t pos = t * kTileV + threadIdx.x * 4 + j;
@@ -307,56 +532,60 @@ __global__ void __launch_bounds__(kThreads) k_acc_heads(AccArgs A, uint32_t* __r
     if (threadIdx.x == 0) head_cnt[t] = s_c;
 }
 
-// One thread per run: look the cell up in the resident shard, continue its sums in input order.
-// Writes the cycle's cell list (sorted by key): ckey, cacc = {sx, sy, sz, n}, crgb = {sr, sg, sb, found_pos + 1}.
-template <typename Items>
-__global__ void __launch_bounds__(kThreads) k_acc_reduce(AccArgs A, Items items, const uint32_t* __restrict__ head_off,
+// engine 2 policy: look the cell up in the resident shard and continue its sums in input order.
+// Emits the cycle's cell list (sorted by key): ckey (absolute), cacc = {sx, sy, sz, n}, crgb = {sr, sg, sb, found_pos + 1}.
+template <typename KeyT, typename Items>
+struct AccPol {
+    Items items;
+    KeyCodec kc;
+    const uint64_t* res_keys; const float4* res_acc; const uint4* res_rgb; uint32_t n_res;
+    uint64_t* ckey; float4* cacc; uint4* crgb;
+    uint32_t* s_fresh;
+    __device__ __forceinline__ void load(uint32_t v, float& x, float& y, float& z, uint32_t& n, uint32_t& r, uint32_t& g,
+                                         uint32_t& b) const { items.get(v, x, y, z, n, r, g, b); }
+    __device__ __forceinline__ void start(KeyT ck, float& sx, float& sy, float& sz, uint32_t& n, uint32_t& r,
+                                          uint32_t& g, uint32_t& b, uint32_t& tag) const {
+        const uint64_t k = kc.to_abs((uint64_t)ck);
+        uint32_t lo = 0, hi = n_res;  // lower_bound in the resident keys
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (res_keys[mid] < k) lo = mid + 1; else hi = mid;
+        }
+        if (lo < n_res && res_keys[lo] == k) {
+            const float4 a = res_acc[lo];
+            const uint4 c = res_rgb[lo];
+            sx = a.x; sy = a.y; sz = a.z; n = __float_as_uint(a.w); r = c.x; g = c.y; b = c.z;
+            tag = lo + 1;
+        } else {
+            atomicAdd(s_fresh, 1u);
+        }
+    }
+    __device__ __forceinline__ void emit(uint32_t slot, KeyT ck, float sx, float sy, float sz, uint32_t n, uint32_t r,
+                                         uint32_t g, uint32_t b, uint32_t tag, uint32_t) const {
+        ckey[slot] = kc.to_abs((uint64_t)ck);
+        cacc[slot] = make_float4(sx, sy, sz, __uint_as_float(n));
+        crgb[slot] = make_uint4(r, g, b, tag);
+    }
+};
+
+template <typename KeyT, typename Items>
+__global__ void __launch_bounds__(kThreads) k_acc_reduce(AccArgs<KeyT> A, Items items, const uint32_t* __restrict__ head_off,
                                                          uint64_t* __restrict__ ckey, float4* __restrict__ cacc,
-                                                         uint4* __restrict__ crgb, uint32_t* __restrict__ n_new) {
-    __shared__ uint32_t s_scan[34];
-    const uint32_t t = blockIdx.x;
+                                                         uint4* __restrict__ crgb, uint32_t* __restrict__ n_new,
+                                                         uint32_t* __restrict__ ticket, RunCarry* __restrict__ carries) {
+    __shared__ RunSmem<KeyT> S;
+    __shared__ uint32_t s_fresh;
+    if (threadIdx.x == 0) { S.ticket = atomicAdd(ticket, 1u); s_fresh = 0; }
+    __syncthreads();
+    const uint32_t t = S.ticket;
     const uint32_t n = A.seg_off[1];
     if (t * kTileV >= n) return;
     const int par = A.plan[0].final_parity;
-    const uint64_t* keys = par ? A.keys1 : A.keys0;
-    const uint32_t* vals = par ? A.vals1 : A.vals0;
-    uint32_t flags = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const uint32_t pos = t * kTileV + threadIdx.x * 4 + j;
-        if (pos < n && (pos == 0 || keys[pos] != keys[pos - 1])) flags |= 1u << j;
-    }
-    uint32_t tot;
-    uint32_t o = head_off[t] + block_excl_scan((uint32_t)__popc(flags), s_scan, tot);
-    uint32_t fresh = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (!(flags & (1u << j))) continue;
-        const uint32_t pos = t * kTileV + threadIdx.x * 4 + j;
-        const uint64_t k = keys[pos];
-        uint32_t lo = 0, hi = A.n_res;  // lower_bound in the resident keys
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (A.res_keys[mid] < k) lo = mid + 1; else hi = mid;
-        }
-        const bool found = lo < A.n_res && A.res_keys[lo] == k;
-        float sx = 0.f, sy = 0.f, sz = 0.f;
-        uint32_t cn = 0, sr = 0, sg = 0, sb = 0;
-        if (found) {
-            const float4 a = A.res_acc[lo];
-            const uint4 c = A.res_rgb[lo];
-            sx = a.x; sy = a.y; sz = a.z; cn = __float_as_uint(a.w); sr = c.x; sg = c.y; sb = c.z;
-        } else {
-            ++fresh;
-        }
-        for (uint32_t q = pos; q < n && keys[q] == k; ++q) items.add(vals[q], sx, sy, sz, cn, sr, sg, sb);
-        ckey[o] = k;
-        cacc[o] = make_float4(sx, sy, sz, __uint_as_float(cn));
-        crgb[o] = make_uint4(sr, sg, sb, found ? lo + 1 : 0u);
-        ++o;
-    }
-    fresh = __reduce_add_sync(kFull, fresh);
-    if ((threadIdx.x & 31) == 0 && fresh) atomicAdd(n_new, fresh);
+    AccPol<KeyT, Items> pol{items, A.kc, A.res_keys, A.res_acc, A.res_rgb, A.n_res, ckey, cacc, crgb, &s_fresh};
+    run_reduce_tile<KeyT, AccPol<KeyT, Items>>(par ? A.keys1 : A.keys0, par ? A.vals1 : A.vals0, n, t, head_off[t], pol, S,
+                                               carries + t);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_fresh) atomicAdd(n_new, s_fresh);
 }
 
 // found cells: write the continued sums back in place; new cells: flag for compaction
