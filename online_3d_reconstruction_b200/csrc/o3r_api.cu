@@ -46,7 +46,7 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-enum { CNT_PTS = 0, CNT_VOX = 1, CNT_CYC = 2, CNT_NEW = 3, CNT_EMIT = 4, CNT_NEWSCAN = 5, CNT_CELLBB = 16, CNT_N = 32 };
+enum { CNT_PTS = 0, CNT_VOX = 1, CNT_CYC = 2, CNT_NEW = 3, CNT_EMIT = 4, CNT_NEWSCAN = 5, CNT_BASE = 6, CNT_CELLBB = 16, CNT_N = 32 };
 
 }  // namespace
 
@@ -55,7 +55,18 @@ struct o3r_ctx {
     std::mutex mu;
     std::string err;
     uint64_t launches = 0;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, st_copy = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;
+    int chunk_frames = 10, chunk_frames_dev = 1 << 30;
+    int gather_in_sort = 0;   // experiment: deliver points in sorted order from the last radix pass
+    cudaEvent_t chunk_event(size_t i) {
+        while (chunk_ev.size() <= i) {
+            cudaEvent_t e;
+            cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            chunk_ev.push_back(e);
+        }
+        return chunk_ev[i];
+    }
     int nx = 0, ny = 0;
     uint32_t npix = 0;
     int canon = 0;
@@ -67,7 +78,7 @@ struct o3r_ctx {
     DevBuf d_frames, d_blur, d_blurjobs;
     // per-batch work buffers
     DevBuf tile_cnt, tile_off, bbox, frame_off, grids, counters, pts, sortbuf, hist, plan_all, plan_v2, ghist;
-    DevBuf head_cnt, head_off, vox, vox_off, seg2, tmat, mask, runwork;
+    DevBuf head_cnt, head_off, vox, vox_off, seg2, tmat, mask, runwork, spts;
     uint32_t* h_counters = nullptr;   // pinned
     uint32_t* h_offs = nullptr;       // pinned, frame offsets readback
     size_t h_offs_cap = 0;
@@ -147,7 +158,8 @@ int read_counters(o3r_ctx* ctx) {
 // The caller provides ghist [n_seg][passes][256] (already filled) and plan.
 template <typename KeyT>
 int sort_pairs(o3r_ctx* ctx, KeyT* k0, KeyT* k1, uint32_t* v0, uint32_t* v1, const uint32_t* seg_off, int n_seg,
-               size_t per_seg_cap, const SortPlan* plan, int passes, int iota_first, const uint32_t* ghist) {
+               size_t per_seg_cap, const SortPlan* plan, int passes, int iota_first, const uint32_t* ghist,
+               const float4* gsrc = nullptr, float4* gdst = nullptr) {
     const uint32_t tiles_ub = std::max(1u, cdiv(per_seg_cap, kRsTile));
     const size_t st_words = (size_t)n_seg * tiles_ub * kRsBins;
     // status words for every pass + one ticket per pass, cleared with one memset
@@ -159,7 +171,7 @@ int sort_pairs(o3r_ctx* ctx, KeyT* k0, KeyT* k1, uint32_t* v0, uint32_t* v1, con
     for (int p = 0; p < passes; ++p)
         LAUNCH_N(sizeof(KeyT) == 4 ? "k_rs_onesweep_u32" : "k_rs_onesweep_u64", (k_rs_onesweep<KeyT>), grid, kThreads,
                  rs_scatter_smem<KeyT>(), k0, k1, v0, v1, seg_off, plan, p, passes, tiles_ub, ghist,
-                 status + st_words * p, tickets + p, iota_first);
+                 status + st_words * p, tickets + p, iota_first, gsrc, gdst);
     return O3R_OK;
 }
 
@@ -178,16 +190,23 @@ int carve_sort_u32(o3r_ctx* ctx, size_t n, SortU32& s) {
 int vg_sorted_reduce(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const uint32_t* seg_off, int n_seg,
                      size_t per_seg_cap, const GridParams* grids, float ix, float iy, float iz, uint32_t min_points,
                      int z_shift, float4* out, uint32_t* out_off, uint64_t* out_keys, uint32_t* out_counts,
-                     bool track_cells = false) {
+                     bool track_cells = false, const uint32_t* out_base = nullptr) {
     CU(ctx->ghist.ensure((size_t)n_seg * 4 * kRsBins * 4));
     CU(ctx->plan_all.ensure((size_t)n_seg * sizeof(SortPlan)));
     CU(cudaMemsetAsync(ctx->ghist.p, 0, (size_t)n_seg * 4 * kRsBins * 4, ctx->st));
     SortPlan* plan = ctx->plan_all.as<SortPlan>();
     LAUNCH_N("k_rs_ghist_u32", (k_rs_ghist<uint32_t, 4>), dim3(std::max(1u, cdiv(per_seg_cap, kRsTile)), n_seg),
              kThreads, 0, sb.k0, seg_off, ctx->ghist.as<uint32_t>());
-    LAUNCH(k_rs_plan, n_seg, kThreads, 0, ctx->ghist.as<uint32_t>(), seg_off, 4, plan);
+    LAUNCH(k_rs_plan, n_seg, kThreads, 0, ctx->ghist.as<uint32_t>(), seg_off, 4, plan, grids);
+    // the fast reduce streams the points in sorted order: the last radix pass gathers them into `spts`
+    const bool fast = min_points <= 1 && !out_keys && !out_counts;
+    float4* spts = nullptr;
+    if (fast && ctx->gather_in_sort) {
+        CU(ctx->spts.ensure((size_t)per_seg_cap * n_seg * 16));
+        spts = ctx->spts.as<float4>();
+    }
     int rc = sort_pairs<uint32_t>(ctx, sb.k0, sb.k1, sb.v0, sb.v1, seg_off, n_seg, per_seg_cap, plan, 4, 1,
-                                  ctx->ghist.as<uint32_t>());
+                                  ctx->ghist.as<uint32_t>(), pts, spts);
     if (rc) return rc;
     VgArgs A;
     A.keys0 = sb.k0; A.keys1 = sb.k1; A.vals0 = sb.v0; A.vals1 = sb.v1;
@@ -203,14 +222,13 @@ int vg_sorted_reduce(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const u
     LAUNCH(k_vg_heads, grid, kThreads, 0, A, ctx->head_cnt.as<uint32_t>());
     LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->head_cnt.as<uint32_t>(), ctx->head_off.as<uint32_t>(), (uint32_t)nt,
            cnt + CNT_VOX);
-    if (min_points <= 1 && !out_keys && !out_counts) {
+    if (fast) {
         const size_t wbytes = 64 + (nt + 1) * sizeof(RunCarry);
         CU(ctx->runwork.ensure(wbytes));
         CU(cudaMemsetAsync(ctx->runwork.p, 0, wbytes, ctx->st));
-        if (track_cells) LAUNCH(k_cellbb_init, 1, 32, 0, reinterpret_cast<int*>(cnt + CNT_CELLBB));
         LAUNCH(k_vg_reduce_w, (uint32_t)nt, kThreads, 0, A, ctx->head_off.as<uint32_t>(), cnt + CNT_VOX, out, out_off,
                n_seg, ctx->runwork.as<uint32_t>(), reinterpret_cast<RunCarry*>(ctx->runwork.as<char>() + 64),
-               track_cells ? 1 : 0, ctx->inv_c, ctx->inv_cz, reinterpret_cast<int*>(cnt + CNT_CELLBB));
+               track_cells ? 1 : 0, ctx->inv_c, ctx->inv_cz, reinterpret_cast<int*>(cnt + CNT_CELLBB), out_base, spts);
     } else
         LAUNCH(k_vg_reduce, grid, kThreads, 0, A, ctx->head_off.as<uint32_t>(), cnt + CNT_VOX, out, out_off, n_seg,
                out_keys, out_counts);
@@ -221,7 +239,7 @@ int vg_sorted_reduce(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const u
 inline int bits_for(long long range) { int b = 0; while ((1ll << b) <= range) ++b; return b; }
 
 template <typename KeyT, typename Items>
-int acc_build_cycle_t(o3r_ctx* ctx, const Items& items, size_t n, bool use_resident, const KeyCodec& kc, int passes) {
+int acc_build_cycle_t(o3r_ctx* ctx, Items items, size_t n, bool use_resident, const KeyCodec& kc, int passes) {
     uint32_t* cnt = ctx->counters.as<uint32_t>();
     const size_t n4 = (n + 63) & ~(size_t)63;
     CU(ctx->sortbuf.ensure(n4 * (2 * sizeof(KeyT) + 8)));
@@ -241,8 +259,16 @@ int acc_build_cycle_t(o3r_ctx* ctx, const Items& items, size_t n, bool use_resid
     LAUNCH_N("k_acc_key", (k_acc_key<KeyT, Items>), gk, kThreads, 0, items, (uint32_t)n, ctx->inv_c, ctx->inv_cz, kc, passes,
              k0, v0, ctx->ghist.as<uint32_t>());
     SortPlan* plan = ctx->plan_v2.as<SortPlan>();
-    LAUNCH(k_rs_plan, 1, kThreads, 0, ctx->ghist.as<uint32_t>(), seg, passes, plan);
-    int rc = sort_pairs<KeyT>(ctx, k0, k1, v0, v1, seg, 1, n, plan, passes, 0, ctx->ghist.as<uint32_t>());
+    LAUNCH(k_rs_plan, 1, kThreads, 0, ctx->ghist.as<uint32_t>(), seg, passes, plan, (const GridParams*)nullptr);
+    float4* spts = nullptr;
+    const float4* gsrc = nullptr;
+    if constexpr (Items::kGather) if (ctx->gather_in_sort) {   // the last radix pass delivers the points in sorted order
+        CU(ctx->spts.ensure(n * 16));
+        spts = ctx->spts.as<float4>();
+        items.spts = spts;
+        gsrc = items.pts;
+    }
+    int rc = sort_pairs<KeyT>(ctx, k0, k1, v0, v1, seg, 1, n, plan, passes, 0, ctx->ghist.as<uint32_t>(), gsrc, spts);
     if (rc) return rc;
     AccArgs<KeyT> A;
     A.keys0 = k0; A.keys1 = k1; A.vals0 = v0; A.vals1 = v1;
@@ -262,12 +288,13 @@ int acc_build_cycle_t(o3r_ctx* ctx, const Items& items, size_t n, bool use_resid
     const size_t wbytes = 64 + ((size_t)A.tiles_ub + 1) * sizeof(RunCarry);
     CU(ctx->runwork.ensure(wbytes));
     CU(cudaMemsetAsync(ctx->runwork.p, 0, wbytes, ctx->st));
-    LAUNCH_N("k_acc_heads", (k_acc_heads<KeyT>), A.tiles_ub, kThreads, 0, A, ctx->head_cnt.as<uint32_t>());
+    LAUNCH_N("k_acc_heads", (k_acc_heads<KeyT>), A.tiles_ub, kThreads, 0, A, v0, v1, ctx->head_cnt.as<uint32_t>(),
+             cnt + CNT_NEW);
     LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->head_cnt.as<uint32_t>(), ctx->head_off.as<uint32_t>(), A.tiles_ub,
            cnt + CNT_CYC);
     LAUNCH_N("k_acc_reduce", (k_acc_reduce<KeyT, Items>), A.tiles_ub, kThreads, 0, A, items, ctx->head_off.as<uint32_t>(),
-             ctx->ckey.as<uint64_t>(), ctx->cacc.as<float4>(), ctx->crgb.as<uint4>(), cnt + CNT_NEW,
-             ctx->runwork.as<uint32_t>(), reinterpret_cast<RunCarry*>(ctx->runwork.as<char>() + 64));
+             ctx->ckey.as<uint64_t>(), ctx->cacc.as<float4>(), ctx->crgb.as<uint4>(), ctx->runwork.as<uint32_t>(),
+             reinterpret_cast<RunCarry*>(ctx->runwork.as<char>() + 64));
     rc = read_counters(ctx);
     if (rc) return rc;
     ctx->n_cyc = ctx->h_counters[CNT_CYC];
@@ -344,7 +371,7 @@ int acc_apply_cycle(o3r_ctx* ctx) {
 }
 
 int acc_merge_points(o3r_ctx* ctx, const float4* pts, size_t n, const int* bb) {
-    AccItemsPts items{pts};
+    AccItemsPts items{pts, nullptr, nullptr};
     int rc = acc_build_cycle(ctx, items, n, true, bb);
     if (rc) return rc;
     return acc_apply_cycle(ctx);
@@ -365,28 +392,31 @@ struct BatchOpts {
     bool mask_only = false;
 };
 
+// stage A for one chunk of frames (descriptors at `fr`).  V1 mode: points + leaf indices into the chunk scratch.
+// dont_downsample mode: points straight into the batch buffer at the device-side running offset.
 template <int DT>
-int launch_stage_a(o3r_ctx* ctx, const AParams& P, int n, const BatchOpts& opt, SortU32& sb, size_t cap_batch) {
-    const FrameDev* fr = ctx->d_frames.as<FrameDev>();
+int launch_stage_a(o3r_ctx* ctx, const AParams& P, const FrameDev* fr, int n, const BatchOpts& opt, float4* pts_out,
+                   uint32_t* keys_out, const uint32_t* out_base, uint32_t* goff) {
     const dim3 grid(P.tiles_per_frame, n);
     uint32_t* cnt = ctx->counters.as<uint32_t>();
     LAUNCH(k_bbox_init, cdiv((size_t)n * 6, kThreads), kThreads, 0, ctx->bbox.as<uint32_t>(), n);
-    LAUNCH_N("k_pre", (k_pre<DT>), grid, kThreads, 0, P, fr, ctx->tile_cnt.as<uint32_t>(), ctx->bbox.as<uint32_t>(), opt.mask_dev);
+    LAUNCH_N("k_pre", (k_pre<DT>), grid, kThreads, 0, P, fr, ctx->tile_cnt.as<uint32_t>(), ctx->bbox.as<uint32_t>(),
+             opt.mask_dev);
     if (opt.mask_only) return O3R_OK;
     LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->tile_cnt.as<uint32_t>(), ctx->tile_off.as<uint32_t>(),
            (uint32_t)((size_t)P.tiles_per_frame * n), cnt + CNT_PTS);
     LAUNCH(k_a_post, cdiv(n + 1, kThreads), kThreads, 0, n, P.tiles_per_frame, ctx->tile_off.as<uint32_t>(),
            cnt + CNT_PTS, ctx->bbox.as<uint32_t>(), ctx->inv_f, ctx->inv_f, ctx->inv_f, P.want_keys,
-           ctx->frame_off.as<uint32_t>(), ctx->grids.as<GridParams>());
-    LAUNCH_N("k_emit", (k_emit<DT>), grid, kThreads, 0, P, fr, ctx->tile_off.as<uint32_t>(), ctx->frame_off.as<uint32_t>(),
-           ctx->grids.as<GridParams>(), ctx->pts.as<float4>(), sb.k0);
-    (void)cap_batch;
+           ctx->frame_off.as<uint32_t>(), ctx->grids.as<GridParams>(), out_base, goff);
+    LAUNCH_N("k_emit", (k_emit<DT>), grid, kThreads, 0, P, fr, ctx->tile_off.as<uint32_t>(),
+             ctx->frame_off.as<uint32_t>(), ctx->grids.as<GridParams>(), pts_out, keys_out, out_base);
     return O3R_OK;
 }
 
-// `frames` hold DEVICE pointers.
-int frames_cloud_dev_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_type, uint32_t* frame_counts,
-                          const BatchOpts& opt) {
+// The batched per-frame path.  `frames` hold host pointers (host_inputs: every frame is copied to device staging
+// on the copy stream, chunk by chunk, overlapping the previous chunk's kernels) or device pointers.
+int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_type, uint32_t* frame_counts,
+                      const BatchOpts& opt, bool host_inputs) {
     const o3r_params& p = ctx->p;
     if (n <= 0) { ctx->last_n = 0; ctx->last_total = 0; return O3R_OK; }
     if (n > 65535) return ctx->fail(O3R_ERR_INVALID, "too many frames in one batch");
@@ -406,8 +436,16 @@ int frames_cloud_dev_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp
     }
     const int J = p.jump_pixels;
     int max_kp = 0;
-    if (J != 1)
-        for (int i = 0; i < n; ++i) max_kp = std::max(max_kp, frames[i].kp_xy ? frames[i].n_kp : 0);
+    size_t kp_total = 0, coef_total = 0;
+    for (int i = 0; i < n; ++i) {
+        const o3r_frame& f = frames[i];
+        if (!f.bgr || (!f.disp && !label_mode)) return ctx->fail(O3R_ERR_INVALID, "frame without disparity/colour");
+        if (label_mode && (!f.labels || !f.plane_coef)) return ctx->fail(O3R_ERR_INVALID, "frame without labels");
+        const int nk = (J != 1 && f.kp_xy && f.n_kp > 0) ? f.n_kp : 0;
+        max_kp = std::max(max_kp, nk);
+        kp_total += (size_t)nk * 2;
+        coef_total += label_mode ? (size_t)std::max(f.n_planes, 0) * 3 : 0;
+    }
 
     AParams P;
     memset(&P, 0, sizeof(P));
@@ -430,31 +468,53 @@ int frames_cloud_dev_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp
         return O3R_OK;
     }
 
-    // frame descriptors
+    // ---- device copies of the inputs (host entry points) and frame descriptors
     const size_t es = disp_elem(disp_type);
-    const size_t blur_step = ((size_t)p.cols + 15) & ~(size_t)15;
+    const size_t dstep = (((size_t)p.cols * es) + 15) & ~(size_t)15, dplane = dstep * p.rows;
+    const size_t cstep = (((size_t)p.cols * 3) + 15) & ~(size_t)15, cplane = cstep * p.rows;
+    const size_t lstep = ((size_t)p.cols + 15) & ~(size_t)15, lplane = lstep * p.rows;
+    const size_t blur_step = lstep;
+    if (host_inputs) {
+        if (!label_mode) CU(ctx->d_disp.ensure(dplane * n));
+        CU(ctx->d_bgr.ensure(cplane * n));
+        if (label_mode) { CU(ctx->d_labels.ensure(lplane * n)); CU(ctx->d_coef.ensure(std::max<size_t>(coef_total, 1) * 8)); }
+        if (kp_total) CU(ctx->d_kp.ensure(kp_total * 4));
+    }
     if (blur) CU(ctx->d_blur.ensure((size_t)n * p.rows * blur_step));
     std::vector<FrameDev> fd(n);
     std::vector<BlurJob> jobs(blur ? n : 0);
     bool vec = (J == 1) && (ctx->nx % 4 == 0) && (P.x0 % 4 == 0) && !label_mode;
-    for (int i = 0; i < n; ++i) {
-        const o3r_frame& f = frames[i];
-        if (!f.bgr || (!f.disp && !label_mode)) return ctx->fail(O3R_ERR_INVALID, "frame without disparity/colour");
-        FrameDev& d = fd[i];
-        d.disp = (const uint8_t*)f.disp; d.disp_step = f.disp_step;
-        d.bgr = f.bgr; d.bgr_step = f.bgr_step;
-        d.labels = label_mode ? f.labels : nullptr; d.labels_step = f.labels_step;
-        d.plane_coef = label_mode ? f.plane_coef : nullptr; d.n_planes = label_mode ? f.n_planes : 0;
-        d.kp_xy = (J != 1) ? f.kp_xy : nullptr; d.n_kp = (J != 1 && f.kp_xy) ? f.n_kp : 0;
-        for (int k = 0; k < 12; ++k) d.T[k] = f.T[k];
-        if (blur) {
-            jobs[i].src = d.disp; jobs[i].sstep = d.disp_step;
-            jobs[i].dst = ctx->d_blur.as<uint8_t>() + (size_t)i * p.rows * blur_step; jobs[i].dstep = blur_step;
-            d.disp = jobs[i].dst; d.disp_step = blur_step;
+    {
+        size_t kp_at = 0, coef_at = 0;
+        for (int i = 0; i < n; ++i) {
+            const o3r_frame& f = frames[i];
+            FrameDev& d = fd[i];
+            const int nk = (J != 1 && f.kp_xy && f.n_kp > 0) ? f.n_kp : 0;
+            if (host_inputs) {
+                d.disp = label_mode ? nullptr : ctx->d_disp.as<uint8_t>() + dplane * i; d.disp_step = dstep;
+                d.bgr = ctx->d_bgr.as<uint8_t>() + cplane * i; d.bgr_step = cstep;
+                d.labels = label_mode ? ctx->d_labels.as<uint8_t>() + lplane * i : nullptr; d.labels_step = lstep;
+                d.plane_coef = label_mode ? ctx->d_coef.as<double>() + coef_at : nullptr;
+                d.kp_xy = nk ? ctx->d_kp.as<float>() + kp_at : nullptr;
+            } else {
+                d.disp = (const uint8_t*)f.disp; d.disp_step = f.disp_step;
+                d.bgr = f.bgr; d.bgr_step = f.bgr_step;
+                d.labels = label_mode ? f.labels : nullptr; d.labels_step = f.labels_step;
+                d.plane_coef = label_mode ? f.plane_coef : nullptr;
+                d.kp_xy = nk ? f.kp_xy : nullptr;
+            }
+            d.n_planes = label_mode ? std::max(f.n_planes, 0) : 0;
+            d.n_kp = nk;
+            kp_at += (size_t)nk * 2; coef_at += (size_t)d.n_planes * 3;
+            for (int k = 0; k < 12; ++k) d.T[k] = f.T[k];
+            if (blur) {
+                jobs[i].src = d.disp; jobs[i].sstep = d.disp_step;
+                jobs[i].dst = ctx->d_blur.as<uint8_t>() + (size_t)i * p.rows * blur_step; jobs[i].dstep = blur_step;
+                d.disp = jobs[i].dst; d.disp_step = blur_step;
+            }
+            if (!label_mode) vec = vec && ((uintptr_t)d.disp % 16 == 0) && (d.disp_step % (4 * es) == 0);
+            vec = vec && ((uintptr_t)d.bgr % 4 == 0) && (d.bgr_step % 4 == 0);
         }
-        if (!label_mode)
-            vec = vec && ((uintptr_t)d.disp % 16 == 0) && (d.disp_step % (4 * es) == 0);
-        vec = vec && ((uintptr_t)d.bgr % 4 == 0) && (d.bgr_step % 4 == 0);
     }
     P.vec = vec;
     CU(ctx->d_frames.ensure((size_t)n * sizeof(FrameDev)));
@@ -462,66 +522,106 @@ int frames_cloud_dev_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp
     if (blur) {
         CU(ctx->d_blurjobs.ensure((size_t)n * sizeof(BlurJob)));
         CU(cudaMemcpyAsync(ctx->d_blurjobs.p, jobs.data(), (size_t)n * sizeof(BlurJob), cudaMemcpyHostToDevice, ctx->st));
-        const int rx0 = P.x0, rx1 = p.cols - p.bounding_box, ry0 = p.bounding_box, ry1 = p.rows - p.bounding_box;
-        if (rx1 > rx0 && ry1 > ry0) {
-            const dim3 g(cdiv(rx1 - rx0, kBlurStrip), cdiv(ry1 - ry0, kBlurRows), n);
-            const size_t sm = blur_smem(p.blur_kernel, p.blur_mode);
-            if (p.blur_mode == O3R_BLUR_MEDIAN)
-                LAUNCH_N("k_blur_median", (k_blur<O3R_BLUR_MEDIAN>), g, kBlurRows, sm, ctx->d_blurjobs.as<BlurJob>(), p.rows, p.cols,
-                       p.blur_kernel, rx0, ry0, rx1, ry1);
-            else
-                LAUNCH_N("k_blur_box", (k_blur<O3R_BLUR_BOX>), g, kBlurRows, sm, ctx->d_blurjobs.as<BlurJob>(), p.rows, p.cols,
-                       p.blur_kernel, rx0, ry0, rx1, ry1);
+    }
+
+    // ---- buffers: batch-wide outputs, chunk-sized scratch
+    // host inputs: chunks let the copies overlap the kernels; device inputs: one launch sequence for the whole batch
+    const int chunk = std::max(1, std::min(n, host_inputs ? ctx->chunk_frames : ctx->chunk_frames_dev));
+    const size_t per_frame_cap = (size_t)P.npix + (size_t)max_kp;
+    const size_t cap_batch = per_frame_cap * n, cap_chunk = per_frame_cap * chunk;
+    if (cap_batch >= (1ull << 32)) return ctx->fail(O3R_ERR_INVALID, "batch exceeds 2^32 samples; use fewer frames");
+    const size_t n_tiles = (size_t)P.tiles_per_frame * chunk;
+    CU(ctx->tile_cnt.ensure(n_tiles * 4));
+    CU(ctx->tile_off.ensure(n_tiles * 4));
+    CU(ctx->bbox.ensure((size_t)chunk * 6 * 4));
+    CU(ctx->frame_off.ensure((size_t)(chunk + 1) * 4));
+    CU(ctx->grids.ensure((size_t)chunk * sizeof(GridParams)));
+    SortU32 sb{nullptr, nullptr, nullptr, nullptr};
+    uint32_t* cnt = ctx->counters.as<uint32_t>();
+    if (!opt.mask_only) {
+        CU(ctx->vox_off.ensure((size_t)(n + 1) * 4));
+        if (P.want_keys) {
+            CU(ctx->pts.ensure(cap_chunk * 16));
+            CU(ctx->vox.ensure(cap_batch * 16));
+            int rc = carve_sort_u32(ctx, cap_chunk, sb);
+            if (rc) return rc;
+            if (!ctx->retain()) LAUNCH(k_cellbb_init, 1, 32, 0, reinterpret_cast<int*>(cnt + CNT_CELLBB));
+        } else {
+            CU(ctx->pts.ensure(cap_batch * 16));
+        }
+        CU(cudaMemsetAsync(cnt + CNT_BASE, 0, 4, ctx->st));
+        CU(cudaMemsetAsync(ctx->vox_off.p, 0, 4, ctx->st));
+    }
+    ctx->last_is_vox = P.want_keys;
+    uint32_t* goff = ctx->vox_off.as<uint32_t>();
+
+    for (int f0 = 0; f0 < n; f0 += chunk) {
+        const int nc = std::min(chunk, n - f0);
+        if (host_inputs) {  // H2D of this chunk on the copy stream; the compute stream waits for its event only
+            for (int i = f0; i < f0 + nc; ++i) {
+                const o3r_frame& f = frames[i];
+                const FrameDev& d = fd[i];
+                if (!label_mode) {
+                    uint8_t* dst = ctx->d_disp.as<uint8_t>() + dplane * i;
+                    CU(cudaMemcpy2DAsync(dst, dstep, f.disp, f.disp_step, (size_t)p.cols * es, p.rows, cudaMemcpyHostToDevice, ctx->st_copy));
+                } else {
+                    CU(cudaMemcpy2DAsync((void*)d.labels, lstep, f.labels, f.labels_step, (size_t)p.cols, p.rows, cudaMemcpyHostToDevice, ctx->st_copy));
+                    if (d.n_planes) CU(cudaMemcpyAsync((void*)d.plane_coef, f.plane_coef, (size_t)d.n_planes * 24, cudaMemcpyHostToDevice, ctx->st_copy));
+                }
+                CU(cudaMemcpy2DAsync((void*)d.bgr, cstep, f.bgr, f.bgr_step, (size_t)p.cols * 3, p.rows, cudaMemcpyHostToDevice, ctx->st_copy));
+                if (d.n_kp) CU(cudaMemcpyAsync((void*)d.kp_xy, f.kp_xy, (size_t)d.n_kp * 8, cudaMemcpyHostToDevice, ctx->st_copy));
+            }
+            cudaEvent_t ev = ctx->chunk_event(f0 / chunk);
+            CU(cudaEventRecord(ev, ctx->st_copy));
+            CU(cudaStreamWaitEvent(ctx->st, ev, 0));
+        }
+        const FrameDev* fr = ctx->d_frames.as<FrameDev>() + f0;
+        if (blur) {
+            const int rx0 = P.x0, rx1 = p.cols - p.bounding_box, ry0 = p.bounding_box, ry1 = p.rows - p.bounding_box;
+            if (rx1 > rx0 && ry1 > ry0) {
+                const dim3 g(cdiv(rx1 - rx0, kBlurStrip), cdiv(ry1 - ry0, kBlurRows), nc);
+                const size_t sm = blur_smem(p.blur_kernel, p.blur_mode);
+                const BlurJob* bj = ctx->d_blurjobs.as<BlurJob>() + f0;
+                if (p.blur_mode == O3R_BLUR_MEDIAN)
+                    LAUNCH_N("k_blur_median", (k_blur<O3R_BLUR_MEDIAN>), g, kBlurRows, sm, bj, p.rows, p.cols, p.blur_kernel, rx0, ry0, rx1, ry1);
+                else
+                    LAUNCH_N("k_blur_box", (k_blur<O3R_BLUR_BOX>), g, kBlurRows, sm, bj, p.rows, p.cols, p.blur_kernel, rx0, ry0, rx1, ry1);
+            }
+        }
+        // stage A: V1 mode writes the chunk scratch; dont_downsample mode writes the batch buffer at the running base
+        float4* pts_out = ctx->pts.as<float4>();
+        const uint32_t* base_a = P.want_keys ? nullptr : cnt + CNT_BASE;
+        uint32_t* goff_a = P.want_keys ? nullptr : goff + f0;
+        int rc;
+        switch (disp_type) {
+            case O3R_DISP_U8: rc = launch_stage_a<O3R_DISP_U8>(ctx, P, fr, nc, opt, pts_out, sb.k0, base_a, goff_a); break;
+            case O3R_DISP_U16: rc = launch_stage_a<O3R_DISP_U16>(ctx, P, fr, nc, opt, pts_out, sb.k0, base_a, goff_a); break;
+            case O3R_DISP_F32: rc = launch_stage_a<O3R_DISP_F32>(ctx, P, fr, nc, opt, pts_out, sb.k0, base_a, goff_a); break;
+            default: rc = launch_stage_a<O3R_DISP_F64>(ctx, P, fr, nc, opt, pts_out, sb.k0, base_a, goff_a); break;
+        }
+        if (rc) return rc;
+        if (opt.mask_only) return O3R_OK;   // (single frame)
+        if (P.want_keys) {  // per-frame VoxelGrid, leaf voxel_size / 5 (pose_functions.cpp:1698), appended at the base
+            rc = vg_sorted_reduce(ctx, sb, ctx->pts.as<float4>(), ctx->frame_off.as<uint32_t>(), nc, per_frame_cap,
+                                  ctx->grids.as<GridParams>(), ctx->inv_f, ctx->inv_f, ctx->inv_f, 0, 0,
+                                  ctx->vox.as<float4>(), goff + f0, nullptr, nullptr, !ctx->retain(), cnt + CNT_BASE);
+            if (rc) return rc;
+            LAUNCH(k_add_base, 1, 32, 0, cnt + CNT_BASE, cnt + CNT_VOX, goff + f0 + nc);
+        } else {
+            LAUNCH(k_add_base, 1, 32, 0, cnt + CNT_BASE, cnt + CNT_PTS, goff + f0 + nc);
         }
     }
 
-    // work buffers
-    const size_t per_frame_cap = (size_t)P.npix + (size_t)max_kp;
-    const size_t cap_batch = per_frame_cap * n;
-    if (cap_batch >= (1ull << 32)) return ctx->fail(O3R_ERR_INVALID, "batch exceeds 2^32 samples; use fewer frames");
-    const size_t n_tiles = (size_t)P.tiles_per_frame * n;
-    CU(ctx->tile_cnt.ensure(n_tiles * 4));
-    CU(ctx->tile_off.ensure(n_tiles * 4));
-    CU(ctx->bbox.ensure((size_t)n * 6 * 4));
-    CU(ctx->frame_off.ensure((size_t)(n + 1) * 4));
-    CU(ctx->grids.ensure((size_t)n * sizeof(GridParams)));
-    SortU32 sb{nullptr, nullptr, nullptr, nullptr};
-    if (!opt.mask_only) {
-        CU(ctx->pts.ensure(cap_batch * 16));
-        if (P.want_keys) { int rc = carve_sort_u32(ctx, cap_batch, sb); if (rc) return rc; }
-    }
-    int rc;
-    switch (disp_type) {
-        case O3R_DISP_U8: rc = launch_stage_a<O3R_DISP_U8>(ctx, P, n, opt, sb, cap_batch); break;
-        case O3R_DISP_U16: rc = launch_stage_a<O3R_DISP_U16>(ctx, P, n, opt, sb, cap_batch); break;
-        case O3R_DISP_F32: rc = launch_stage_a<O3R_DISP_F32>(ctx, P, n, opt, sb, cap_batch); break;
-        default: rc = launch_stage_a<O3R_DISP_F64>(ctx, P, n, opt, sb, cap_batch); break;
-    }
-    if (rc || opt.mask_only) return rc;
-
-    const uint32_t* off_dev = ctx->frame_off.as<uint32_t>();
-    ctx->last_is_vox = false;
-    if (P.want_keys) {  // per-frame VoxelGrid, leaf voxel_size / 5 (pose_functions.cpp:1698)
-        CU(ctx->vox.ensure(cap_batch * 16));
-        CU(ctx->vox_off.ensure((size_t)(n + 1) * 4));
-        rc = vg_sorted_reduce(ctx, sb, ctx->pts.as<float4>(), ctx->frame_off.as<uint32_t>(), n, per_frame_cap,
-                              ctx->grids.as<GridParams>(), ctx->inv_f, ctx->inv_f, ctx->inv_f, 0, 0,
-                              ctx->vox.as<float4>(), ctx->vox_off.as<uint32_t>(), nullptr, nullptr, !ctx->retain());
-        if (rc) return rc;
-        off_dev = ctx->vox_off.as<uint32_t>();
-        ctx->last_is_vox = true;
-    }
-    // per-frame output offsets back to the host (the one sync of the frame path)
+    // ---- per-frame output offsets (+ the combined-grid cell range) back to the host: the one sync of the frame path
     if (ctx->h_offs_cap < (size_t)n + 1) {
         if (ctx->h_offs) cudaFreeHost(ctx->h_offs);
         ctx->h_offs_cap = std::max<size_t>(n + 1, 256);
         CU(cudaMallocHost((void**)&ctx->h_offs, ctx->h_offs_cap * 4));
     }
-    CU(cudaMemcpyAsync(ctx->h_offs, off_dev, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(ctx->h_offs, goff, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, ctx->st));
     ctx->last_has_cellbb = ctx->last_is_vox && !ctx->retain();
     if (ctx->last_has_cellbb)
-        CU(cudaMemcpyAsync(ctx->h_counters + CNT_CELLBB, ctx->counters.as<uint32_t>() + CNT_CELLBB, 24,
-                           cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(ctx->h_counters + CNT_CELLBB, cnt + CNT_CELLBB, 24, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     if (ctx->last_has_cellbb) memcpy(ctx->last_cellbb, ctx->h_counters + CNT_CELLBB, 24);
     ctx->last_off.assign(ctx->h_offs, ctx->h_offs + n + 1);
@@ -533,57 +633,6 @@ int frames_cloud_dev_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp
     const float4* outp = ctx->last_is_vox ? ctx->vox.as<float4>() : ctx->pts.as<float4>();
     if (ctx->retain()) return cloud_append_dev(ctx, outp, ctx->last_total);
     return acc_merge_points(ctx, outp, ctx->last_total, ctx->last_has_cellbb ? ctx->last_cellbb : nullptr);
-}
-
-// copies the frames' inputs to device staging and rewrites the pointers
-int stage_frames(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_type, std::vector<o3r_frame>& dev) {
-    const o3r_params& p = ctx->p;
-    const size_t es = disp_elem(disp_type);
-    const size_t dstep = (((size_t)p.cols * es) + 15) & ~(size_t)15, dplane = dstep * p.rows;
-    const size_t cstep = (((size_t)p.cols * 3) + 15) & ~(size_t)15, cplane = cstep * p.rows;
-    const size_t lstep = ((size_t)p.cols + 15) & ~(size_t)15, lplane = lstep * p.rows;
-    const bool label_mode = p.use_segment_labels && n > 0 && frames[0].labels && frames[0].plane_coef;
-    size_t kp_total = 0, coef_total = 0;
-    for (int i = 0; i < n; ++i) {
-        kp_total += (frames[i].kp_xy && frames[i].n_kp > 0) ? (size_t)frames[i].n_kp * 2 : 0;
-        coef_total += (label_mode && frames[i].n_planes > 0) ? (size_t)frames[i].n_planes * 3 : 0;
-    }
-    if (!label_mode) CU(ctx->d_disp.ensure(dplane * n));
-    CU(ctx->d_bgr.ensure(cplane * n));
-    if (label_mode) { CU(ctx->d_labels.ensure(lplane * n)); CU(ctx->d_coef.ensure(std::max<size_t>(coef_total, 1) * 8)); }
-    if (kp_total) CU(ctx->d_kp.ensure(kp_total * 4));
-    dev.assign(frames, frames + n);
-    size_t kp_at = 0, coef_at = 0;
-    for (int i = 0; i < n; ++i) {
-        const o3r_frame& f = frames[i];
-        o3r_frame& d = dev[i];
-        if (!f.bgr || (!f.disp && !label_mode)) return ctx->fail(O3R_ERR_INVALID, "frame without disparity/colour");
-        if (!label_mode) {
-            uint8_t* dd = ctx->d_disp.as<uint8_t>() + dplane * i;
-            CU(cudaMemcpy2DAsync(dd, dstep, f.disp, f.disp_step, (size_t)p.cols * es, p.rows, cudaMemcpyHostToDevice, ctx->st));
-            d.disp = dd; d.disp_step = dstep;
-        } else {
-            uint8_t* dl = ctx->d_labels.as<uint8_t>() + lplane * i;
-            CU(cudaMemcpy2DAsync(dl, lstep, f.labels, f.labels_step, (size_t)p.cols, p.rows, cudaMemcpyHostToDevice, ctx->st));
-            d.labels = dl; d.labels_step = lstep;
-            double* dc = ctx->d_coef.as<double>() + coef_at;
-            if (f.n_planes > 0)
-                CU(cudaMemcpyAsync(dc, f.plane_coef, (size_t)f.n_planes * 24, cudaMemcpyHostToDevice, ctx->st));
-            d.plane_coef = dc; coef_at += (size_t)std::max(f.n_planes, 0) * 3;
-            d.disp = nullptr;
-        }
-        uint8_t* dc = ctx->d_bgr.as<uint8_t>() + cplane * i;
-        CU(cudaMemcpy2DAsync(dc, cstep, f.bgr, f.bgr_step, (size_t)p.cols * 3, p.rows, cudaMemcpyHostToDevice, ctx->st));
-        d.bgr = dc; d.bgr_step = cstep;
-        if (f.kp_xy && f.n_kp > 0) {
-            float* dk = ctx->d_kp.as<float>() + kp_at;
-            CU(cudaMemcpyAsync(dk, f.kp_xy, (size_t)f.n_kp * 8, cudaMemcpyHostToDevice, ctx->st));
-            d.kp_xy = dk; kp_at += (size_t)f.n_kp * 2;
-        } else {
-            d.kp_xy = nullptr; d.n_kp = 0;
-        }
-    }
-    return O3R_OK;
 }
 
 int copy_out(o3r_ctx* ctx, const float4* src, size_t n, o3r_point* out, size_t cap, size_t* n_out) {
@@ -645,6 +694,10 @@ int o3r_create(const o3r_params* params, o3r_ctx** out_ctx) {
         return O3R_ERR_CUDA;
     };
     if ((e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+    if ((e = cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+    if (const char* cf = getenv("O3R_CHUNK_FRAMES")) ctx->chunk_frames = std::max(1, atoi(cf));
+    if (const char* cf = getenv("O3R_CHUNK_FRAMES_DEV")) ctx->chunk_frames_dev = std::max(1, atoi(cf));
+    if (const char* cf = getenv("O3R_GATHER_IN_SORT")) ctx->gather_in_sort = atoi(cf) != 0;
     if ((e = cudaMallocHost((void**)&ctx->h_counters, CNT_N * 4)) != cudaSuccess) return bail(e, "pinned");
     if ((e = ctx->counters.ensure(CNT_N * 4)) != cudaSuccess) return bail(e, "counters");
     if ((e = cudaMemsetAsync(ctx->counters.p, 0, CNT_N * 4, ctx->st)) != cudaSuccess) return bail(e, "memset");
@@ -667,6 +720,26 @@ int o3r_create(const o3r_params* params, o3r_ctx** out_ctx) {
     e = cudaFuncSetAttribute(k_rs_onesweep<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)rs_scatter_smem<uint32_t>());
     if (e != cudaSuccess) return bail(e, "smem attr");
+    // shared-memory carve-out per kernel (percent of the 228 KB array; the rest is L1).  Measured on B200:
+    // the run-reduce kernels gather points, so they want L1 as much as occupancy.
+    {
+        auto env_or = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
+        const int cv_vg = env_or("O3R_CARVEOUT_VG", 50), cv_acc = env_or("O3R_CARVEOUT_ACC", 50),
+                  cv_sort = env_or("O3R_CARVEOUT_SORT", 100), cv_emit = env_or("O3R_CARVEOUT_EMIT", -1);
+        cudaFuncSetAttribute(k_vg_reduce_w, cudaFuncAttributePreferredSharedMemoryCarveout, cv_vg);
+        cudaFuncSetAttribute(k_acc_reduce<uint32_t, AccItemsPts>, cudaFuncAttributePreferredSharedMemoryCarveout, cv_acc);
+        cudaFuncSetAttribute(k_acc_reduce<uint64_t, AccItemsPts>, cudaFuncAttributePreferredSharedMemoryCarveout, cv_acc);
+        cudaFuncSetAttribute(k_acc_reduce<uint32_t, AccItemsCells>, cudaFuncAttributePreferredSharedMemoryCarveout, cv_acc);
+        cudaFuncSetAttribute(k_acc_reduce<uint64_t, AccItemsCells>, cudaFuncAttributePreferredSharedMemoryCarveout, cv_acc);
+        cudaFuncSetAttribute(k_rs_onesweep<uint32_t>, cudaFuncAttributePreferredSharedMemoryCarveout, cv_sort);
+        cudaFuncSetAttribute(k_rs_onesweep<uint64_t>, cudaFuncAttributePreferredSharedMemoryCarveout, cv_sort);
+        if (cv_emit >= 0) {
+            cudaFuncSetAttribute(k_emit<O3R_DISP_U8>, cudaFuncAttributePreferredSharedMemoryCarveout, cv_emit);
+            cudaFuncSetAttribute(k_emit<O3R_DISP_U16>, cudaFuncAttributePreferredSharedMemoryCarveout, cv_emit);
+            cudaFuncSetAttribute(k_emit<O3R_DISP_F32>, cudaFuncAttributePreferredSharedMemoryCarveout, cv_emit);
+            cudaFuncSetAttribute(k_emit<O3R_DISP_F64>, cudaFuncAttributePreferredSharedMemoryCarveout, cv_emit);
+        }
+    }
     const int bs = (int)blur_smem(kBlurMaxK, O3R_BLUR_MEDIAN);
     cudaFuncSetAttribute(k_blur<O3R_BLUR_MEDIAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs);
     cudaFuncSetAttribute(k_blur<O3R_BLUR_BOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs);
@@ -677,12 +750,13 @@ int o3r_create(const o3r_params* params, o3r_ctx** out_ctx) {
 void o3r_destroy(o3r_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->p.device);
+    if (ctx->st_copy) cudaStreamSynchronize(ctx->st_copy);
     if (ctx->st) cudaStreamSynchronize(ctx->st);
     DevBuf* bufs[] = {&ctx->lut_r, &ctx->lut_z, &ctx->d_disp, &ctx->d_bgr, &ctx->d_labels, &ctx->d_coef, &ctx->d_kp,
                       &ctx->d_frames, &ctx->d_blur, &ctx->d_blurjobs, &ctx->tile_cnt, &ctx->tile_off, &ctx->bbox,
                       &ctx->frame_off, &ctx->grids, &ctx->counters, &ctx->pts, &ctx->sortbuf, &ctx->hist,
                       &ctx->plan_all, &ctx->plan_v2, &ctx->ghist, &ctx->head_cnt, &ctx->head_off, &ctx->vox,
-                      &ctx->vox_off, &ctx->seg2, &ctx->tmat, &ctx->mask, &ctx->runwork, &ctx->res_keys[0], &ctx->res_keys[1],
+                      &ctx->vox_off, &ctx->seg2, &ctx->tmat, &ctx->mask, &ctx->runwork, &ctx->spts, &ctx->res_keys[0], &ctx->res_keys[1],
                       &ctx->res_acc[0], &ctx->res_acc[1], &ctx->res_rgb[0], &ctx->res_rgb[1], &ctx->ckey, &ctx->cacc,
                       &ctx->crgb, &ctx->new_cnt, &ctx->new_off, &ctx->new_keys, &ctx->okeys, &ctx->cloud};
     for (DevBuf* b : bufs) b->release();
@@ -690,6 +764,8 @@ void o3r_destroy(o3r_ctx* ctx) {
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_offs) cudaFreeHost(ctx->h_offs);
+    for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
+    if (ctx->st_copy) cudaStreamDestroy(ctx->st_copy);
     if (ctx->st) cudaStreamDestroy(ctx->st);
     delete ctx;
 }
@@ -756,17 +832,14 @@ int o3r_frames_cloud_dev(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_
     if (!ctx || (n > 0 && !frames)) return O3R_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->p.device));
-    return frames_cloud_dev_impl(ctx, frames, n, disp_type, frame_counts, BatchOpts());
+    return frames_cloud_impl(ctx, frames, n, disp_type, frame_counts, BatchOpts(), false);
 }
 
 int o3r_frames_cloud(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_type, uint32_t* frame_counts) {
     if (!ctx || (n > 0 && !frames)) return O3R_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->p.device));
-    std::vector<o3r_frame> dev;
-    int rc = stage_frames(ctx, frames, n, disp_type, dev);
-    if (rc) return rc;
-    return frames_cloud_dev_impl(ctx, dev.data(), n, disp_type, frame_counts, BatchOpts());
+    return frames_cloud_impl(ctx, frames, n, disp_type, frame_counts, BatchOpts(), true);
 }
 
 int o3r_frame_cloud(o3r_ctx* ctx, const o3r_frame* frame, int disp_type, o3r_point* out, size_t cap, size_t* n_out) {
@@ -774,12 +847,9 @@ int o3r_frame_cloud(o3r_ctx* ctx, const o3r_frame* frame, int disp_type, o3r_poi
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->p.device));
     if (n_out) *n_out = 0;
-    std::vector<o3r_frame> dev;
-    int rc = stage_frames(ctx, frame, 1, disp_type, dev);
-    if (rc) return rc;
     BatchOpts opt;
     opt.merge = false;
-    rc = frames_cloud_dev_impl(ctx, dev.data(), 1, disp_type, nullptr, opt);
+    int rc = frames_cloud_impl(ctx, frame, 1, disp_type, nullptr, opt, true);
     if (rc) return rc;
     const float4* src = ctx->last_is_vox ? ctx->vox.as<float4>() : ctx->pts.as<float4>();
     return copy_out(ctx, src, ctx->last_total, out, cap, n_out);
@@ -793,13 +863,10 @@ int o3r_frame_mask(o3r_ctx* ctx, const o3r_frame* frame, int disp_type, uint8_t*
     if (!mask && cap == 0) return O3R_OK;
     if (cap < ctx->npix) return ctx->fail(O3R_ERR_CAPACITY, "mask buffer too small");
     if (ctx->npix == 0) return O3R_OK;
-    std::vector<o3r_frame> dev;
-    int rc = stage_frames(ctx, frame, 1, disp_type, dev);
-    if (rc) return rc;
     CU(ctx->mask.ensure(ctx->npix));
     BatchOpts opt;
     opt.merge = false; opt.mask_only = true; opt.mask_dev = ctx->mask.as<uint8_t>();
-    rc = frames_cloud_dev_impl(ctx, dev.data(), 1, disp_type, nullptr, opt);
+    int rc = frames_cloud_impl(ctx, frame, 1, disp_type, nullptr, opt, true);
     if (rc) return rc;
     CU(cudaMemcpyAsync(mask, ctx->mask.p, ctx->npix, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
@@ -999,7 +1066,7 @@ int o3r_exchange_pack(o3r_ctx* ctx, int world, o3r_cell* send_dev, size_t cap, u
     if (ctx->retain()) return ctx->fail(O3R_ERR_UNSUPPORTED, "exchange needs O3R_MERGE_ACCUMULATE");
     std::fill(counts, counts + world, 0u);
     if (!ctx->last_is_vox || ctx->last_total == 0) { ctx->n_cyc = 0; return O3R_OK; }
-    AccItemsPts items{ctx->vox.as<float4>()};
+    AccItemsPts items{ctx->vox.as<float4>(), nullptr, nullptr};
     int rc = acc_build_cycle(ctx, items, ctx->last_total, false, ctx->last_has_cellbb ? ctx->last_cellbb : nullptr);
     if (rc) return rc;
     const uint32_t n = ctx->n_cyc;
@@ -1036,7 +1103,7 @@ int o3r_exchange_merge(o3r_ctx* ctx, const o3r_cell* recv_dev, size_t n) {
     CU(cudaSetDevice(ctx->p.device));
     if (ctx->retain()) return ctx->fail(O3R_ERR_UNSUPPORTED, "exchange needs O3R_MERGE_ACCUMULATE");
     if (n == 0) return O3R_OK;
-    AccItemsCells items{recv_dev};
+    AccItemsCells items{recv_dev, nullptr, nullptr};
     int rc = acc_build_cycle(ctx, items, n, true, nullptr);
     if (rc) return rc;
     return acc_apply_cycle(ctx);

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kThreads) k_scan_u32(const uint32_t* __restric
 
 // ---- per-segment plan from whole-segment digit histograms ghist[S][passes][256] ---------------------------
 __global__ void k_rs_plan(const uint32_t* __restrict__ ghist, const uint32_t* __restrict__ seg_off, int passes,
-                          SortPlan* __restrict__ plan) {
+                          SortPlan* __restrict__ plan, const GridParams* __restrict__ grids) {
     __shared__ int s_trivial[kMaxPasses];
     const int s = blockIdx.x;
     const uint32_t n = seg_off[s + 1] - seg_off[s];
@@ -65,7 +65,7 @@ __global__ void k_rs_plan(const uint32_t* __restrict__ ghist, const uint32_t* __
         SortPlan pl;
         uint32_t par = 0, na = 0;
         for (int p = 0; p < kMaxPasses; ++p) {
-            const bool act = p < passes && n > 0 && !s_trivial[p];
+            const bool act = p < passes && n > 0 && !s_trivial[p] && !(grids && grids[s].passthrough);
             pl.active[p] = act;
             pl.in_parity[p] = (uint8_t)par;
             if (act) { par ^= 1u; ++na; }
@@ -150,7 +150,8 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? 4 : 3) k_rs_ones
                                                           const SortPlan* __restrict__ plan, int pass, int passes,
                                                           uint32_t tiles_ub, const uint32_t* __restrict__ ghist,
                                                           uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
-                                                          int iota_first) {
+                                                          int iota_first, const float4* __restrict__ gsrc,
+                                                          float4* __restrict__ gdst) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
     KeyT* s_keys = reinterpret_cast<KeyT*>(rs_smem);
     uint32_t* s_vals = reinterpret_cast<uint32_t*>(rs_smem + (size_t)kRsTile * sizeof(KeyT));
@@ -178,6 +179,11 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? 4 : 3) k_rs_ones
     uint32_t* vout = (par ? vals0 : vals1) + beg;
     bool first = true;
     for (int q = 0; q < pass; ++q) first = first && !pl.active[q];
+    bool last = true;
+    for (int q = pass + 1; q < passes; ++q) last = last && !pl.active[q];
+    // in the last active pass the 16-byte records the values point at can be delivered in sorted order
+    // (gdst[beg + rank] = gsrc[value]) instead of the values: 16 independent gathers per thread
+    const bool gather = last && gdst != nullptr;
     const bool iota = iota_first && first;   // values are the global element index, not read from memory
     const int shift = pass * 8, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
@@ -258,11 +264,22 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? 4 : 3) k_rs_ones
         s_vals[pos] = val[r];
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < ntile; i += kThreads) {
-        const KeyT k = s_keys[i];
-        const uint32_t g = gbase[rs_digit(k, shift)] + i;
-        kout[g] = k;
-        vout[g] = s_vals[i];
+    if (gather) {
+        float4* go = gdst + beg;
+#pragma unroll 4
+        for (uint32_t i = threadIdx.x; i < ntile; i += kThreads) {
+            const KeyT k = s_keys[i];
+            const uint32_t g = gbase[rs_digit(k, shift)] + i;
+            kout[g] = k;
+            go[g] = gsrc[s_vals[i]];
+        }
+    } else {
+        for (uint32_t i = threadIdx.x; i < ntile; i += kThreads) {
+            const KeyT k = s_keys[i];
+            const uint32_t g = gbase[rs_digit(k, shift)] + i;
+            kout[g] = k;
+            vout[g] = s_vals[i];
+        }
     }
 }
 

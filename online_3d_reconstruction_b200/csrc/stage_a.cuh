@@ -255,12 +255,16 @@ __global__ void __launch_bounds__(kThreads) k_pre(AParams P, const FrameDev* __r
 }
 
 // ---- after the tile scan: frame offsets + per-frame VoxelGrid parameters ------------------------------------
+// `goff` (optional): the batch-wide offsets of this chunk's frames = *out_base + chunk-local offset.
 __global__ void k_a_post(int n_frames, int tiles_per_frame, const uint32_t* __restrict__ tile_off,
                          const uint32_t* __restrict__ total, const uint32_t* __restrict__ bbox, float ix, float iy,
-                         float iz, int want_grid, uint32_t* __restrict__ frame_off, GridParams* __restrict__ grids) {
+                         float iz, int want_grid, uint32_t* __restrict__ frame_off, GridParams* __restrict__ grids,
+                         const uint32_t* __restrict__ out_base, uint32_t* __restrict__ goff) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f > n_frames) return;
-    frame_off[f] = (f == n_frames) ? *total : tile_off[(size_t)f * tiles_per_frame];
+    const uint32_t o = (f == n_frames) ? *total : tile_off[(size_t)f * tiles_per_frame];
+    frame_off[f] = o;
+    if (goff && f < n_frames) goff[f] = *out_base + o;
     if (f < n_frames && want_grid) grids[f] = make_grid(bbox + 6 * f, ix, iy, iz);
 }
 
@@ -270,7 +274,8 @@ __global__ void __launch_bounds__(kThreads) k_emit(AParams P, const FrameDev* __
                                                    const uint32_t* __restrict__ tile_off,
                                                    const uint32_t* __restrict__ frame_off,
                                                    const GridParams* __restrict__ grids,
-                                                   float4* __restrict__ pts, uint32_t* __restrict__ keys) {
+                                                   float4* __restrict__ pts, uint32_t* __restrict__ keys,
+                                                   const uint32_t* __restrict__ out_base) {
     __shared__ double rl[256];
     __shared__ float zl[256];
     __shared__ uint32_t s_scan[34];
@@ -318,6 +323,7 @@ __global__ void __launch_bounds__(kThreads) k_emit(AParams P, const FrameDev* __
     const uint32_t base = tile_off[(size_t)f * P.tiles_per_frame + tile];
     const bool pass = P.want_keys && grids[f].passthrough;
     const uint32_t fbase = frame_off[f];
+    if (out_base) pts += *out_base;   // batch-wide output position of this chunk
     for (uint32_t i = threadIdx.x; i < total; i += kThreads) {
         pts[base + i] = s_pts[i];
         if (P.want_keys) keys[base + i] = pass ? (base + i - fbase) : s_keys[i];  // passthrough: identity order

@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(kThreads) k_vg_reduce(VgArgs A, const uint32_t
     const uint32_t beg = A.seg_off[s], n = A.seg_off[s + 1] - beg;
     if (t * kTileV >= n) return;
     const int par = A.plan[s].final_parity;
+    const bool ident = A.plan[s].n_active == 0;   // nothing was sorted (pass-through / single-cell segment)
     const uint32_t* keys = (par ? A.keys1 : A.keys0) + beg;
     const uint32_t* vals = (par ? A.vals1 : A.vals0) + beg;
     uint32_t flags = 0;
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(kThreads) k_vg_reduce(VgArgs A, const uint32_t
         const uint32_t pos = t * kTileV + threadIdx.x * 4 + j;
         const uint32_t k = keys[pos];
         if (verbatim) {
-            const float4 p = A.pts[vals[pos]];
+            const float4 p = A.pts[ident ? beg + pos : vals[pos]];
             out[o] = p;
             if (out_keys) out_keys[o] = abs_cell_key(p.x, p.y, A.z_shift ? __fadd_rn(p.z, 500.0f) : p.z, A.lx_inv, A.ly_inv, A.lz_inv);
             if (out_counts) out_counts[o] = 1;
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(kThreads) k_vg_reduce(VgArgs A, const uint32_t
         uint32_t cnt = 0;
         float4 first = make_float4(0.f, 0.f, 0.f, 0.f);
         for (uint32_t q = pos; q < n && keys[q] == k; ++q) {
-            const float4 p = A.pts[vals[q]];
+            const float4 p = A.pts[ident ? beg + q : vals[q]];
             const float z = A.z_shift ? __fadd_rn(p.z, 500.0f) : p.z;
             if (cnt == 0) first = make_float4(p.x, p.y, z, 0.f);
             const uint32_t c = __float_as_uint(p.w);
@@ -210,36 +211,73 @@ struct RunCarry {
     uint32_t flag;
 };  // 48 bytes
 
-template <typename KeyT>
+// PACKED (point items, weight 1): a = {x, y, z, 0x00RRGGBB}.  Unpacked (partial cells): a = {x, y, z, n}, c = {r, g, b, -}.
+template <typename KeyT, bool PACKED>
 struct RunSmem {
-    float4 a[kTileV];   // x, y, z, n (uint bits)
-    uint4 c[kTileV];    // r, g, b, value (index of the item)
+    float4 a[kTileV];
+    uint4 c[PACKED ? 1 : kTileV];
     uint16_t hpos[kTileV + 2];
     uint32_t scan[34];
     uint32_t ticket;
 };
 
-// sequential sum of staged items [a, e): loads batched 4 at a time so only the FADD chain is serial
-template <typename KeyT>
-__device__ __forceinline__ void run_sum(const RunSmem<KeyT>& S, uint32_t a, uint32_t e, float& sx, float& sy, float& sz,
-                                        uint32_t& cn, uint32_t& cr, uint32_t& cg, uint32_t& cb) {
+// Sequential sum of staged items [a, e).  Only the three FADD chains are serial; the shared-memory loads of the
+// next batch are issued before the current batch is added.
+template <typename KeyT, bool PACKED>
+__device__ __forceinline__ void run_sum(const RunSmem<KeyT, PACKED>& S, uint32_t a, uint32_t e, float& sx, float& sy,
+                                        float& sz, uint32_t& cn, uint32_t& cr, uint32_t& cg, uint32_t& cb) {
+    constexpr int B = 4;
     uint32_t i = a;
-    for (; i + 4 <= e; i += 4) {
-        float4 p[4];
-        uint4 q[4];
+    if (PACKED) {
+        if (i + B <= e) {
+            float4 p[B];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { p[u] = S.a[i + u]; q[u] = S.c[i + u]; }
+            for (int u = 0; u < B; ++u) p[u] = S.a[i + u];
+            for (i += B; i + B <= e; i += B) {
+                float4 q[B];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            sx = __fadd_rn(sx, p[u].x); sy = __fadd_rn(sy, p[u].y); sz = __fadd_rn(sz, p[u].z);
-            cn += __float_as_uint(p[u].w); cr += q[u].x; cg += q[u].y; cb += q[u].z;
+                for (int u = 0; u < B; ++u) q[u] = S.a[i + u];
+#pragma unroll
+                for (int u = 0; u < B; ++u) {
+                    sx = __fadd_rn(sx, p[u].x); sy = __fadd_rn(sy, p[u].y); sz = __fadd_rn(sz, p[u].z);
+                    const uint32_t w = __float_as_uint(p[u].w);
+                    cr += (w >> 16) & 255u; cg += (w >> 8) & 255u; cb += w & 255u;
+                    p[u] = q[u];
+                }
+                cn += B;
+            }
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                sx = __fadd_rn(sx, p[u].x); sy = __fadd_rn(sy, p[u].y); sz = __fadd_rn(sz, p[u].z);
+                const uint32_t w = __float_as_uint(p[u].w);
+                cr += (w >> 16) & 255u; cg += (w >> 8) & 255u; cb += w & 255u;
+            }
+            cn += B;
         }
-    }
-    for (; i < e; ++i) {
-        const float4 p = S.a[i];
-        const uint4 q = S.c[i];
-        sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z);
-        cn += __float_as_uint(p.w); cr += q.x; cg += q.y; cb += q.z;
+        for (; i < e; ++i) {
+            const float4 p = S.a[i];
+            sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z);
+            const uint32_t w = __float_as_uint(p.w);
+            cn += 1; cr += (w >> 16) & 255u; cg += (w >> 8) & 255u; cb += w & 255u;
+        }
+    } else {
+        for (; i + 4 <= e; i += 4) {
+            float4 p[4];
+            uint4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { p[u] = S.a[i + u]; q[u] = S.c[i + u]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                sx = __fadd_rn(sx, p[u].x); sy = __fadd_rn(sy, p[u].y); sz = __fadd_rn(sz, p[u].z);
+                cn += __float_as_uint(p[u].w); cr += q[u].x; cg += q[u].y; cb += q[u].z;
+            }
+        }
+        for (; i < e; ++i) {
+            const float4 p = S.a[i];
+            const uint4 q = S.c[i];
+            sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z);
+            cn += __float_as_uint(p.w); cr += q.x; cg += q.y; cb += q.z;
+        }
     }
 }
 
@@ -253,9 +291,8 @@ __device__ __forceinline__ void carry_publish(RunCarry* c, float sx, float sy, f
 
 // `carry` points at this tile's RunCarry; carry[-1] is the previous tile of the same segment.
 template <typename KeyT, typename Pol>
-__device__ __forceinline__ void run_reduce_tile(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                                uint32_t n, uint32_t t, uint32_t slot0, Pol& pol, RunSmem<KeyT>& S,
-                                                RunCarry* __restrict__ carry) {
+__device__ __forceinline__ void run_reduce_tile(const KeyT* __restrict__ keys, uint32_t n, uint32_t t, uint32_t slot0,
+                                                Pol& pol, RunSmem<KeyT, Pol::kPacked>& S, RunCarry* __restrict__ carry) {
     const int tid = threadIdx.x;
     const uint32_t wbase = t * kTileV;
     const uint32_t wn = min((uint32_t)kTileV, n - wbase);
@@ -263,20 +300,39 @@ __device__ __forceinline__ void run_reduce_tile(const KeyT* __restrict__ keys, c
     uint32_t flags = 0;
     {
         const uint32_t p0 = wbase + tid * 4;
-        KeyT prev = (p0 > 0 && p0 < n) ? keys[p0 - 1] : (KeyT)0;
+        if (p0 + 3 < n) {   // full group: issue the four key/value loads, then the four gathers, then store
+            KeyT k4[4];
+            const KeyT prev = p0 > 0 ? keys[p0 - 1] : (KeyT)0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t pos = p0 + j;
-            if (pos < n) {
-                const KeyT key = keys[pos];
-                if (pos == 0 || key != prev) flags |= 1u << j;
-                prev = key;
-                const uint32_t v = vals[pos];
-                const int e = tid * 4 + j;
-                float x, y, z; uint32_t in, ir, ig, ib;
-                pol.load(v, x, y, z, in, ir, ig, ib);
-                S.a[e] = make_float4(x, y, z, __uint_as_float(in));
-                S.c[e] = make_uint4(ir, ig, ib, v);
+            for (int j = 0; j < 4; ++j) k4[j] = keys[p0 + j];
+            float4 ia[4];
+            uint4 ic[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pol.load(p0 + j, ia[j], ic[j]);
+            if (p0 == 0 || k4[0] != prev) flags |= 1u;
+#pragma unroll
+            for (int j = 1; j < 4; ++j)
+                if (k4[j] != k4[j - 1]) flags |= 1u << j;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                S.a[tid * 4 + j] = ia[j];
+                if (!Pol::kPacked) S.c[tid * 4 + j] = ic[j];
+            }
+        } else {
+            KeyT prev = (p0 > 0 && p0 < n) ? keys[p0 - 1] : (KeyT)0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t pos = p0 + j;
+                if (pos < n) {
+                    const KeyT key = keys[pos];
+                    if (pos == 0 || key != prev) flags |= 1u << j;
+                    prev = key;
+                    const int e = tid * 4 + j;
+                    float4 ia; uint4 ic;
+                    pol.load(pos, ia, ic);
+                    S.a[e] = ia;
+                    if (!Pol::kPacked) S.c[e] = ic;
+                }
             }
         }
     }
@@ -291,13 +347,14 @@ __device__ __forceinline__ void run_reduce_tile(const KeyT* __restrict__ keys, c
     // ---- one thread per run whose head lies in the tile
     for (uint32_t rI = tid; rI < H; rI += kThreads) {
         const uint32_t a = S.hpos[rI], e = S.hpos[rI + 1];
-        const KeyT key = keys[wbase + a];
+        const bool tail = rI == H - 1 && more;
+        const KeyT key = (Pol::kNeedsKey || tail) ? keys[wbase + a] : (KeyT)0;
         float sx = 0.f, sy = 0.f, sz = 0.f;
         uint32_t cn = 0, cr = 0, cg = 0, cb = 0, tag = 0;
-        pol.start(key, sx, sy, sz, cn, cr, cg, cb, tag);
-        const uint32_t first_v = S.c[a].w;
+        pol.start(wbase + a, sx, sy, sz, cn, cr, cg, cb, tag);
+        const uint32_t first_v = wbase + a;   // position of the run's first element
         run_sum(S, a, e, sx, sy, sz, cn, cr, cg, cb);
-        if (rI == H - 1 && more && keys[wbase + wn] == key)   // still open at the tile end: hand it on
+        if (tail && keys[wbase + wn] == key)   // still open at the tile end: hand it on
             carry_publish(carry, sx, sy, sz, cn, cr, cg, cb, slot0 + rI, tag, first_v);
         else
             pol.emit(slot0 + rI, key, sx, sy, sz, cn, cr, cg, cb, tag, first_v);
@@ -323,23 +380,24 @@ __device__ __forceinline__ void run_reduce_tile(const KeyT* __restrict__ keys, c
 // engine 1 policy: CentroidPoint of a VoxelGrid leaf.  Optionally tracks the range of combined-grid cells the
 // emitted centroids fall in (so the merge can sort compact keys).
 struct VgPol {
-    const float4* pts; float4* out; int z_shift; bool verbatim;
+    static constexpr bool kNeedsKey = false;
+    static constexpr bool kPacked = true;
+    const float4* spts;   // the segment's points in sorted order (null: gather pts[vals[pos]])
+    const float4* pts; const uint32_t* vals;
+    float4* out; int z_shift; bool verbatim;
     int want_cells; float icx, icz;
     int mn[3], mx[3];
-    __device__ __forceinline__ void load(uint32_t v, float& x, float& y, float& z, uint32_t& n, uint32_t& r, uint32_t& g,
-                                         uint32_t& b) const {
-        const float4 p = pts[v];
-        const uint32_t c = __float_as_uint(p.w);
-        x = p.x; y = p.y; z = z_shift ? __fadd_rn(p.z, 500.0f) : p.z;
-        n = 1; r = (c >> 16) & 255u; g = (c >> 8) & 255u; b = c & 255u;
+    __device__ __forceinline__ void load(uint32_t pos, float4& a, uint4&) const {
+        a = spts ? __ldcs(spts + pos) : pts[vals[pos]];
+        if (z_shift) a.z = __fadd_rn(a.z, 500.0f);
     }
     __device__ __forceinline__ void start(uint32_t, float&, float&, float&, uint32_t&, uint32_t&, uint32_t&, uint32_t&,
-                                          uint32_t&) const {}
+                                          uint32_t&) const {}   // sums start at zero
     __device__ __forceinline__ void emit(uint32_t slot, uint32_t, float sx, float sy, float sz, uint32_t n, uint32_t r,
                                          uint32_t g, uint32_t b, uint32_t, uint32_t first) {
         float4 o;
         if (verbatim) {   // PCL: output = *input_
-            o = pts[first];
+            o = spts ? spts[first] : pts[vals[first]];
         } else {
             const float fn = (float)n;
             float cz = __fdiv_rn(sz, fn);
@@ -361,13 +419,15 @@ struct VgPol {
 
 // fast path of engine 1: every run is emitted (min_points <= 1), no key / count outputs.
 // Linear grid of tiles_ub * n_seg CTAs; work[0] is the ticket, carries follow.
-__global__ void __launch_bounds__(kThreads) k_vg_reduce_w(VgArgs A, const uint32_t* __restrict__ head_off,
+__global__ void __launch_bounds__(kThreads, 5) k_vg_reduce_w(VgArgs A, const uint32_t* __restrict__ head_off,
                                                           const uint32_t* __restrict__ head_total,
                                                           float4* __restrict__ out, uint32_t* __restrict__ seg_out_off,
                                                           int n_seg, uint32_t* __restrict__ ticket,
                                                           RunCarry* __restrict__ carries, int want_cells, float icx,
-                                                          float icz, int* __restrict__ cellbb) {
-    __shared__ RunSmem<uint32_t> S;
+                                                          float icz, int* __restrict__ cellbb,
+                                                          const uint32_t* __restrict__ out_base,
+                                                          const float4* __restrict__ sorted_pts) {
+    __shared__ RunSmem<uint32_t, true> S;
     __shared__ int s_bb[6];
     if (threadIdx.x == 0) S.ticket = atomicAdd(ticket, 1u);
     if (threadIdx.x < 6) s_bb[threadIdx.x] = threadIdx.x < 3 ? 0x7fffffff : (int)0x80000000;
@@ -375,17 +435,22 @@ __global__ void __launch_bounds__(kThreads) k_vg_reduce_w(VgArgs A, const uint32
     const uint32_t lin = S.ticket;
     const int s = lin / A.tiles_ub;
     const uint32_t t = lin - (uint32_t)s * A.tiles_ub;
+    const uint32_t obase = out_base ? *out_base : 0u;   // batch-wide output position of this chunk
     if (t == 0 && threadIdx.x == 0) {
-        seg_out_off[s] = head_off[(size_t)s * A.tiles_ub];
-        if (s == n_seg - 1) seg_out_off[n_seg] = *head_total;
+        seg_out_off[s] = obase + head_off[(size_t)s * A.tiles_ub];
+        if (s == n_seg - 1 && !out_base) seg_out_off[n_seg] = *head_total;
     }
     const uint32_t beg = A.seg_off[s], n = A.seg_off[s + 1] - beg;
     if (t * kTileV >= n) return;
-    const int par = A.plan[s].final_parity;
-    VgPol pol{A.pts, out, A.z_shift, A.grids && A.grids[s].passthrough, want_cells, icx, icz,
+    const SortPlan pl = A.plan[s];
+    const int par = pl.final_parity;
+    // the last radix pass delivered the points in sorted order; a segment that needed no pass is already sorted
+    const float4* sp = pl.n_active ? (sorted_pts ? sorted_pts + beg : nullptr) : A.pts + beg;
+    VgPol pol{sp, A.pts, (par ? A.vals1 : A.vals0) + beg, out + obase, A.z_shift, A.grids && A.grids[s].passthrough,
+              want_cells, icx, icz,
               {0x7fffffff, 0x7fffffff, 0x7fffffff}, {(int)0x80000000, (int)0x80000000, (int)0x80000000}};
-    run_reduce_tile<uint32_t, VgPol>((par ? A.keys1 : A.keys0) + beg, (par ? A.vals1 : A.vals0) + beg, n, t,
-                                     head_off[(size_t)s * A.tiles_ub + t], pol, S, carries + lin);
+    run_reduce_tile<uint32_t, VgPol>((par ? A.keys1 : A.keys0) + beg, n, t, head_off[(size_t)s * A.tiles_ub + t], pol, S,
+                                     carries + lin);
     if (want_cells) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -421,12 +486,13 @@ struct KeyCodec {
 
 struct AccItemsPts {   // items are points of weight 1 (z gets +500)
     const float4* pts;
-    __device__ __forceinline__ void get(uint32_t v, float& x, float& y, float& z, uint32_t& n, uint32_t& r, uint32_t& g,
-                                        uint32_t& b) const {
-        const float4 p = pts[v];
-        const uint32_t c = __float_as_uint(p.w);
-        x = p.x; y = p.y; z = __fadd_rn(p.z, 500.0f);
-        n = 1; r = (c >> 16) & 255u; g = (c >> 8) & 255u; b = c & 255u;
+    const float4* spts;    // the same points in sorted order when the last radix pass gathered them, else null
+    const uint32_t* vals;  // sorted order -> point index (when spts is null)
+    static constexpr bool kGather = true;
+    static constexpr bool kPacked = true;
+    __device__ __forceinline__ void get(uint32_t pos, float4& a, uint4&) const {
+        a = spts ? __ldcs(spts + pos) : pts[vals[pos]];
+        a.z = __fadd_rn(a.z, 500.0f);
     }
     __device__ __forceinline__ void cell(uint32_t v, float ix, float iz, int& i, int& j, int& k) const {
         const float4 p = pts[v];
@@ -436,10 +502,14 @@ struct AccItemsPts {   // items are points of weight 1 (z gets +500)
 };
 struct AccItemsCells {  // items are partial cells received from other ranks
     const o3r_cell* cells;
-    __device__ __forceinline__ void get(uint32_t v, float& x, float& y, float& z, uint32_t& n, uint32_t& r, uint32_t& g,
-                                        uint32_t& b) const {
-        const o3r_cell c = cells[v];
-        x = c.sx; y = c.sy; z = c.sz; n = c.n; r = c.sr; g = c.sg; b = c.sb;
+    const float4* spts;    // unused
+    const uint32_t* vals;  // sorted order -> cell index
+    static constexpr bool kGather = false;
+    static constexpr bool kPacked = false;
+    __device__ __forceinline__ void get(uint32_t pos, float4& a, uint4& q) const {
+        const o3r_cell c = cells[vals[pos]];
+        a = make_float4(c.sx, c.sy, c.sz, __uint_as_float(c.n));
+        q = make_uint4(c.sr, c.sg, c.sb, 0u);
     }
     __device__ __forceinline__ void cell(uint32_t v, float, float, int& i, int& j, int& k) const {
         const uint64_t key = cells[v].key;
@@ -463,6 +533,11 @@ __global__ void __launch_bounds__(kThreads) k_acc_cellbb(Items items, uint32_t n
         const int lo = __reduce_min_sync(kFull, mn[a]), hi = __reduce_max_sync(kFull, mx[a]);
         if ((threadIdx.x & 31) == 0) { atomicMin(&cellbb[a], lo); atomicMax(&cellbb[3 + a], hi); }
     }
+}
+
+// after a chunk: advance the batch-wide output position and record it as the next frame's offset
+__global__ void k_add_base(uint32_t* base, const uint32_t* total, uint32_t* goff_end) {
+    if (threadIdx.x == 0) { *base += *total; *goff_end = *base; }
 }
 
 __global__ void k_cellbb_init(int* cellbb) {
@@ -510,54 +585,68 @@ struct AccArgs {
     const uint64_t* res_keys; float4* res_acc; uint4* res_rgb; uint32_t n_res;
 };
 
+// Counts the run heads of each tile and — fully in parallel, one thread per head — looks every head's cell up in
+// the resident shard.  The result (position + 1, or 0 for a new cell) is parked at the head's element position in
+// the ping-pong value buffer the sort left idle, where k_acc_reduce picks it up.
 template <typename KeyT>
-__global__ void __launch_bounds__(kThreads) k_acc_heads(AccArgs<KeyT> A, uint32_t* __restrict__ head_cnt) {
+__global__ void __launch_bounds__(kThreads) k_acc_heads(AccArgs<KeyT> A, uint32_t* __restrict__ vals0, uint32_t* __restrict__ vals1,
+                                                        uint32_t* __restrict__ head_cnt, uint32_t* __restrict__ n_new) {
     const uint32_t t = blockIdx.x;
     const uint32_t n = A.seg_off[1];
-    uint32_t c = 0;
+    uint32_t c = 0, fresh = 0;
     if (t * kTileV < n) {
-        const KeyT* keys = A.plan[0].final_parity ? A.keys1 : A.keys0;
+        const int par = A.plan[0].final_parity;
+        const KeyT* keys = par ? A.keys1 : A.keys0;
+        uint32_t* tags = par ? vals0 : vals1;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t pos = t * kTileV + threadIdx.x * 4 + j;
-            if (pos < n && (pos == 0 || keys[pos] != keys[pos - 1])) ++c;
+            const uint32_t pos = t * kTileV + j * kThreads + threadIdx.x;   // coalesced
+            if (pos < n) {
+                const KeyT ck = keys[pos];
+                if (pos == 0 || ck != keys[pos - 1]) {
+                    ++c;
+                    const uint64_t k = A.kc.to_abs((uint64_t)ck);
+                    uint32_t lo = 0, hi = A.n_res;  // lower_bound in the resident keys
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (A.res_keys[mid] < k) lo = mid + 1; else hi = mid;
+                    }
+                    const bool found = lo < A.n_res && A.res_keys[lo] == k;
+                    tags[pos] = found ? lo + 1 : 0u;
+                    if (!found) ++fresh;
+                }
+            }
         }
     }
     c = __reduce_add_sync(kFull, c);
-    __shared__ uint32_t s_c;
-    if (threadIdx.x == 0) s_c = 0;
+    fresh = __reduce_add_sync(kFull, fresh);
+    __shared__ uint32_t s_c, s_f;
+    if (threadIdx.x == 0) { s_c = 0; s_f = 0; }
     __syncthreads();
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_c, c);
+    if ((threadIdx.x & 31) == 0) { if (c) atomicAdd(&s_c, c); if (fresh) atomicAdd(&s_f, fresh); }
     __syncthreads();
-    if (threadIdx.x == 0) head_cnt[t] = s_c;
+    if (threadIdx.x == 0) { head_cnt[t] = s_c; if (s_f) atomicAdd(n_new, s_f); }
 }
 
 // engine 2 policy: look the cell up in the resident shard and continue its sums in input order.
 // Emits the cycle's cell list (sorted by key): ckey (absolute), cacc = {sx, sy, sz, n}, crgb = {sr, sg, sb, found_pos + 1}.
 template <typename KeyT, typename Items>
 struct AccPol {
+    static constexpr bool kNeedsKey = true;
+    static constexpr bool kPacked = Items::kPacked;
     Items items;
     KeyCodec kc;
-    const uint64_t* res_keys; const float4* res_acc; const uint4* res_rgb; uint32_t n_res;
+    const uint32_t* tags;   // per element position: resident position + 1 of a head's cell, 0 = new cell
+    const float4* res_acc; const uint4* res_rgb;
     uint64_t* ckey; float4* cacc; uint4* crgb;
-    uint32_t* s_fresh;
-    __device__ __forceinline__ void load(uint32_t v, float& x, float& y, float& z, uint32_t& n, uint32_t& r, uint32_t& g,
-                                         uint32_t& b) const { items.get(v, x, y, z, n, r, g, b); }
-    __device__ __forceinline__ void start(KeyT ck, float& sx, float& sy, float& sz, uint32_t& n, uint32_t& r,
+    __device__ __forceinline__ void load(uint32_t pos, float4& a, uint4& c) const { items.get(pos, a, c); }
+    __device__ __forceinline__ void start(uint32_t pos, float& sx, float& sy, float& sz, uint32_t& n, uint32_t& r,
                                           uint32_t& g, uint32_t& b, uint32_t& tag) const {
-        const uint64_t k = kc.to_abs((uint64_t)ck);
-        uint32_t lo = 0, hi = n_res;  // lower_bound in the resident keys
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (res_keys[mid] < k) lo = mid + 1; else hi = mid;
-        }
-        if (lo < n_res && res_keys[lo] == k) {
-            const float4 a = res_acc[lo];
-            const uint4 c = res_rgb[lo];
+        tag = tags[pos];
+        if (tag) {
+            const float4 a = res_acc[tag - 1];
+            const uint4 c = res_rgb[tag - 1];
             sx = a.x; sy = a.y; sz = a.z; n = __float_as_uint(a.w); r = c.x; g = c.y; b = c.z;
-            tag = lo + 1;
-        } else {
-            atomicAdd(s_fresh, 1u);
         }
     }
     __device__ __forceinline__ void emit(uint32_t slot, KeyT ck, float sx, float sy, float sz, uint32_t n, uint32_t r,
@@ -569,23 +658,22 @@ struct AccPol {
 };
 
 template <typename KeyT, typename Items>
-__global__ void __launch_bounds__(kThreads) k_acc_reduce(AccArgs<KeyT> A, Items items, const uint32_t* __restrict__ head_off,
+__global__ void __launch_bounds__(kThreads, 5) k_acc_reduce(AccArgs<KeyT> A, Items items, const uint32_t* __restrict__ head_off,
                                                          uint64_t* __restrict__ ckey, float4* __restrict__ cacc,
-                                                         uint4* __restrict__ crgb, uint32_t* __restrict__ n_new,
-                                                         uint32_t* __restrict__ ticket, RunCarry* __restrict__ carries) {
-    __shared__ RunSmem<KeyT> S;
-    __shared__ uint32_t s_fresh;
-    if (threadIdx.x == 0) { S.ticket = atomicAdd(ticket, 1u); s_fresh = 0; }
+                                                         uint4* __restrict__ crgb, uint32_t* __restrict__ ticket,
+                                                         RunCarry* __restrict__ carries) {
+    __shared__ RunSmem<KeyT, Items::kPacked> S;
+    if (threadIdx.x == 0) S.ticket = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint32_t t = S.ticket;
     const uint32_t n = A.seg_off[1];
     if (t * kTileV >= n) return;
-    const int par = A.plan[0].final_parity;
-    AccPol<KeyT, Items> pol{items, A.kc, A.res_keys, A.res_acc, A.res_rgb, A.n_res, ckey, cacc, crgb, &s_fresh};
-    run_reduce_tile<KeyT, AccPol<KeyT, Items>>(par ? A.keys1 : A.keys0, par ? A.vals1 : A.vals0, n, t, head_off[t], pol, S,
-                                               carries + t);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_fresh) atomicAdd(n_new, s_fresh);
+    const SortPlan pl = A.plan[0];
+    const int par = pl.final_parity;
+    items.vals = par ? A.vals1 : A.vals0;
+    if constexpr (Items::kGather) { if (!pl.n_active) items.spts = items.pts; }   // nothing was sorted: already in order
+    AccPol<KeyT, Items> pol{items, A.kc, par ? A.vals0 : A.vals1, A.res_acc, A.res_rgb, ckey, cacc, crgb};
+    run_reduce_tile<KeyT, AccPol<KeyT, Items>>(par ? A.keys1 : A.keys0, n, t, head_off[t], pol, S, carries + t);
 }
 
 // found cells: write the continued sums back in place; new cells: flag for compaction
