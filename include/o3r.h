@@ -157,6 +157,11 @@ int o3r_cloud_append(o3r_ctx* ctx, const o3r_point* pts, size_t n);
  * left untouched.  `out` may be NULL with cap = 0 to query the size. */
 int o3r_cloud_downsample(o3r_ctx* ctx, o3r_point* out, size_t cap, size_t* n_out);
 
+/* Same, but the result stays on the GPU: *dev_out points at *n_out records in device memory owned by the
+ * context (valid until the next call on it) — for consumers on the same device (a CUDA viewer, the next
+ * pipeline stage) and for the inputs-resident-in-HBM measurement. */
+int o3r_cloud_downsample_dev(o3r_ctx* ctx, const o3r_point** dev_out, size_t* n_out);
+
 /* Number of resident records (cells in ACCUMULATE mode, points in RETAIN mode) and clear. */
 int o3r_cloud_size(o3r_ctx* ctx, size_t* n);
 int o3r_cloud_clear(o3r_ctx* ctx);

@@ -962,43 +962,63 @@ static int voxel_grid_dev(o3r_ctx* ctx, const float4* pts, size_t n, float ix, f
     return O3R_OK;
 }
 
-int o3r_cloud_downsample(o3r_ctx* ctx, o3r_point* out, size_t cap, size_t* n_out) {
-    if (!ctx) return O3R_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    CU(cudaSetDevice(ctx->p.device));
-    if (n_out) *n_out = 0;
-    if (ctx->p.dont_downsample)  // pose.cpp:533-536: cloud_small = cloud_big
-        return copy_out(ctx, ctx->cloud.as<float4>(), ctx->n_cloud, out, cap, n_out);
+// downsamplePtCloud(cloud_big, true) into a device buffer: *res = result, *m = records
+static int cloud_downsample_dev(o3r_ctx* ctx, const float4** res, size_t* m) {
+    *res = nullptr; *m = 0;
+    if (ctx->p.dont_downsample) {  // pose.cpp:533-536: cloud_small = cloud_big
+        *res = ctx->cloud.as<float4>(); *m = ctx->n_cloud;
+        return O3R_OK;
+    }
     uint32_t* cnt = ctx->counters.as<uint32_t>();
     if (ctx->retain()) {  // one-shot pcl::VoxelGrid over cloud_big, exactly pose_functions.cpp:1654-1709
         if (ctx->n_cloud == 0) return O3R_OK;
-        // the batch output buffer is reused as the result buffer; the last batch is no longer retrievable
         CU(ctx->ckey.ensure(ctx->n_cloud * 16));   // result points (<= n_cloud)
-        size_t m = 0;
         int rc = voxel_grid_dev(ctx, ctx->cloud.as<float4>(), ctx->n_cloud, ctx->inv_c, ctx->inv_c, ctx->inv_cz,
-                                ctx->p.min_points_per_voxel, 1, ctx->ckey.as<float4>(), nullptr, nullptr, &m, nullptr);
+                                ctx->p.min_points_per_voxel, 1, ctx->ckey.as<float4>(), nullptr, nullptr, m, nullptr);
         if (rc) return rc;
-        return copy_out(ctx, ctx->ckey.as<float4>(), m, out, cap, n_out);
+        *res = ctx->ckey.as<float4>();
+        return O3R_OK;
     }
     if (ctx->n_res == 0) return O3R_OK;
     const int cur = ctx->res_cur;
     const uint32_t tiles = cdiv(ctx->n_res, kTileV);
     CU(ctx->new_cnt.ensure((size_t)tiles * 4));
     CU(ctx->new_off.ensure((size_t)tiles * 4));
+    CU(ctx->cacc.ensure((size_t)ctx->n_res * 16));
     LAUNCH(k_acc_emit_cnt, tiles, kThreads, 0, ctx->n_res, ctx->res_acc[cur].as<float4>(), ctx->p.min_points_per_voxel,
            ctx->new_cnt.as<uint32_t>());
     LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->new_cnt.as<uint32_t>(), ctx->new_off.as<uint32_t>(), tiles, cnt + CNT_EMIT);
-    int rc = read_counters(ctx);
-    if (rc) return rc;
-    const size_t m = ctx->h_counters[CNT_EMIT];
-    if (n_out) *n_out = m;
-    if (!out && cap == 0) return O3R_OK;
-    if (cap < m) return ctx->fail(O3R_ERR_CAPACITY, "output buffer too small");
-    if (m == 0) return O3R_OK;
-    CU(ctx->cacc.ensure(m * 16));
     LAUNCH(k_acc_emit, tiles, kThreads, 0, ctx->n_res, ctx->res_acc[cur].as<float4>(), ctx->res_rgb[cur].as<uint4>(),
            ctx->p.min_points_per_voxel, ctx->new_off.as<uint32_t>(), ctx->cacc.as<float4>());
-    return copy_out(ctx, ctx->cacc.as<float4>(), m, out, cap, n_out);
+    int rc = read_counters(ctx);
+    if (rc) return rc;
+    *m = ctx->h_counters[CNT_EMIT];
+    *res = ctx->cacc.as<float4>();
+    return O3R_OK;
+}
+
+int o3r_cloud_downsample(o3r_ctx* ctx, o3r_point* out, size_t cap, size_t* n_out) {
+    if (!ctx) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    if (n_out) *n_out = 0;
+    const float4* res;
+    size_t m;
+    int rc = cloud_downsample_dev(ctx, &res, &m);
+    if (rc) return rc;
+    return copy_out(ctx, res, m, out, cap, n_out);
+}
+
+int o3r_cloud_downsample_dev(o3r_ctx* ctx, const o3r_point** dev_out, size_t* n_out) {
+    if (!ctx || !n_out) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    const float4* res;
+    int rc = cloud_downsample_dev(ctx, &res, n_out);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->st));
+    if (dev_out) *dev_out = reinterpret_cast<const o3r_point*>(res);
+    return O3R_OK;
 }
 
 int o3r_voxel_grid(o3r_ctx* ctx, const o3r_point* pts, size_t n, float lx, float ly, float lz, unsigned min_points,

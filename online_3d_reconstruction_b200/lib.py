@@ -14,7 +14,8 @@ SO_PATH = os.path.join(_HERE, "libo3r.so")
 SYMBOLS = [
     "o3r_create", "o3r_destroy", "o3r_last_error", "o3r_version", "o3r_host_alloc", "o3r_host_free",
     "o3r_frame_cloud", "o3r_frames_cloud", "o3r_frames_cloud_dev", "o3r_last_batch_points",
-    "o3r_cloud_transform", "o3r_cloud_append", "o3r_cloud_downsample", "o3r_cloud_size", "o3r_cloud_clear",
+    "o3r_cloud_transform", "o3r_cloud_append", "o3r_cloud_downsample", "o3r_cloud_downsample_dev", "o3r_cloud_size",
+    "o3r_cloud_clear",
     "o3r_voxel_grid", "o3r_blur_u8", "o3r_frame_mask",
     "o3r_exchange_pack", "o3r_exchange_merge", "o3r_set_defer_merge",
     "o3r_launch_count", "o3r_stream", "o3r_sync", "o3r_profile", "o3r_profile_read",
@@ -57,6 +58,7 @@ def load():
     L.o3r_cloud_transform.argtypes = [vp, C.POINTER(C.c_float)]
     L.o3r_cloud_append.argtypes = [vp, vp, sz]
     L.o3r_cloud_downsample.argtypes = [vp, vp, sz, szp]
+    L.o3r_cloud_downsample_dev.argtypes = [vp, C.POINTER(vp), szp]
     L.o3r_cloud_size.argtypes = [vp, szp]
     L.o3r_cloud_clear.argtypes = [vp]
     L.o3r_voxel_grid.argtypes = [vp, vp, sz, C.c_float, C.c_float, C.c_float, C.c_uint, vp, sz, szp, vp, vp,

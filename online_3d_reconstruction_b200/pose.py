@@ -143,6 +143,12 @@ class Pose:
         self._check(self._L.o3r_cloud_downsample(self._h, out.ctypes.data, out.size, C.byref(n)))
         return out[:n.value]
 
+    def downsamplePtCloudDevice(self):
+        """Same as downsamplePtCloud but the result stays in device memory -> (device pointer, n records)."""
+        ptr, n = C.c_void_p(), C.c_size_t(0)
+        self._check(self._L.o3r_cloud_downsample_dev(self._h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
     # -- stand-alone stages --------------------------------------------------------------------------------
     def voxelGrid(self, pts, leaf, min_points=0):
         """pcl::VoxelGrid on a host cloud -> (points, keys u64, counts u32, passthrough)."""

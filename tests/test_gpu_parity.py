@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import oracle_binding as ob
-from online_3d_reconstruction_b200 import abi, synth
+from online_3d_reconstruction_b200 import abi, exchange, synth
 from online_3d_reconstruction_b200.pose import Pose
 
 pytestmark = pytest.mark.gpu
@@ -276,6 +276,22 @@ def test_cycles_merge_equals_one_shot_reference(mode, min_pts):
     _eq(got, exp)
 
 
+def test_downsample_device_result_matches_host_result():
+    torch = pytest.importorskip("torch")
+    keep = []
+    geom = SMALL4
+    p = abi.make_params(jump_pixels=1, voxel_size=0.05, **geom)
+    with Pose(p) as P:
+        P.createCycleClouds(_frames(45, 3, geom["rows"], geom["cols"], keep=keep))
+        host = P.downsamplePtCloud()
+        ptr, n = P.downsamplePtCloudDevice()
+        assert n == len(host)
+        class DevArr:   # wrap the raw device pointer for torch
+            __cuda_array_interface__ = {"shape": (n * 16,), "typestr": "|u1", "data": (ptr, True), "version": 2}
+        buf = torch.as_tensor(DevArr(), device="cuda").cpu().numpy().view(abi.POINT)
+        _eq(buf, host)
+
+
 def test_dont_downsample_cycle_returns_cloud_big():
     keep = []
     p = abi.make_params(jump_pixels=2, dont_downsample=True, **SMALL)
@@ -363,6 +379,10 @@ def test_exchange_two_ranks_equals_single_rank():
                 c = P.exchangePack(W, buf.data_ptr(), buf.numel() // abi.CELL.itemsize)
                 sends.append(buf)
                 counts.append(c)
+            for s, buf in enumerate(sends):   # the device buckets by the same hash the host mirror computes
+                sent = buf[:int(counts[s].sum()) * abi.CELL.itemsize].cpu().numpy().view(abi.CELL)
+                own = exchange.owner_of(sent["key"], W)
+                assert np.array_equal(own, np.repeat(np.arange(W), counts[s]))
             for r, P in enumerate(ranks):
                 parts = []
                 for s in range(W):
