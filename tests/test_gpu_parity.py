@@ -287,7 +287,7 @@ def test_downsample_device_result_matches_host_result():
         ptr, n = P.downsamplePtCloudDevice()
         assert n == len(host)
         class DevArr:   # wrap the raw device pointer for torch
-            __cuda_array_interface__ = {"shape": (n * 16,), "typestr": "|u1", "data": (ptr, True), "version": 2}
+            __cuda_array_interface__ = {"shape": (n * 16,), "typestr": "|u1", "data": (ptr, False), "version": 2}
         buf = torch.as_tensor(DevArr(), device="cuda").cpu().numpy().view(abi.POINT)
         _eq(buf, host)
 
