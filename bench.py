@@ -34,6 +34,9 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 
 from online_3d_reconstruction_b200 import abi, synth  # noqa: E402
 
+# (workload, kernel) -> DRAM bytes per launch from `ncu --set full` (see profiles/r01*_ncu_*.txt)
+NCU_TRAFFIC = {}
+
 WORKLOADS = {
     # name: (rows, cols, disp_type, J, voxel_size, min_pts, dont_downsample, frames/step, seed, Q scale)
     "config2_semidense_720p": (720, 1280, abi.DISP_U8, 1, 0.05, 1, False, 50, 1002, 1.0),
@@ -125,8 +128,10 @@ def frames_array(disp_ptrs, disp_step, bgr_ptrs, bgr_step, Ts):
     return arr
 
 
-# per-kernel algorithmic bytes of one step (what the kernel must read + write once), keyed by profile name
-def algorithmic_bytes(wl, n_valid, n_vox, n_cells_cycle, bd):
+# per-kernel algorithmic bytes of one step (what the kernel must read + write once), keyed by profile name.
+# n_valid = points after the mask, n_vox = per-frame voxels of the cycle, np1 / np2 = radix passes of the per-frame
+# index sort / the combined-grid key sort (7-8 bit digits: 28-bit index -> 4, 20-bit key -> 3).
+def algorithmic_bytes(wl, n_valid, n_vox, n_cells_cycle, bd, np1=4, np2=3):
     rows, cols, dt, J, v, mp, nd, F, seed, qs = WORKLOADS[wl]
     p = params_for(wl, 0)
     ny, nx = abi.scan_dims(p)
@@ -134,12 +139,14 @@ def algorithmic_bytes(wl, n_valid, n_vox, n_cells_cycle, bd):
     return {
         "k_pre": npix * bd,
         "k_emit": npix * bd + npix * 3 + n_valid * (16 + (0 if nd else 4)),
-        "k_rs_hist_u32": 4 * n_valid * 4,
-        "k_rs_scatter_u32": n_valid * (12 + 3 * 16),
+        "k_rs_ghist_u32": n_valid * 4,
+        # first pass reads keys only (values are the element index), every pass writes key + value
+        "k_rs_onesweep_u32": n_valid * (4 + 8) + (np1 - 1) * n_valid * 16 + np2 * n_vox * 16,
         "k_vg_heads": n_valid * 4,
-        "k_vg_reduce": n_valid * (4 + 4 + 16) + n_vox * 16,
-        "k_acc_key_pts": n_vox * (16 + 12),
-        "k_acc_reduce": n_vox * (8 + 4 + 16) + n_cells_cycle * 40,
+        "k_vg_reduce_w": n_valid * (4 + 4 + 16) + n_vox * 16,
+        "k_acc_key": n_vox * (16 + 8),
+        "k_acc_heads": n_vox * 4,
+        "k_acc_reduce": n_vox * (4 + 4 + 16) + n_cells_cycle * 40,
     }
 
 
@@ -269,12 +276,18 @@ def run_ours(args, rank, world, local_rank):
             "launches_per_step": top_n / K, "avg_launch_ms": per_launch_ms,
             "share_of_kernel_time": top_ms / total_kernel_ms, "traffic": None}
     if top_name in alg:
+        # launches that exit at once (planned-out radix passes) are included in the count: the per-launch figure
+        # is total algorithmic bytes of the kernel in a step / its launches in a step
         per_launch_bytes = alg[top_name] / (top_n / K)
         roof["achieved"] = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
         roof["frac"] = roof["achieved"] / peak
         roof["algorithmic_bytes_per_launch"] = per_launch_bytes
     else:
         roof["achieved"] = roof["frac"] = None
+    roof["per_kernel_frac_of_peak"] = {k: round(alg[k] / (v[1] / K * 1e-3) / 1e9 / peak, 4) for k, v in kern if k in alg}
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
+    # capture of this workload (profiles/), when one exists for this kernel
+    roof["traffic"] = NCU_TRAFFIC.get((wl, top_name))
     # whole-step view: compulsory bytes of the fused pipeline / step time
     ny, nx = abi.scan_dims(p)
     step_alg = F * (rows * cols * bd + 3 * ny * nx) + (16 * n_valid if nd else 20 * stats["n_vox"] + 2 * 32 * new_cells_per_step)

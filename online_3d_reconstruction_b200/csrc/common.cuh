@@ -31,6 +31,7 @@ struct GridParams {
     int mul1, mul2;     // divb_mul_[1], divb_mul_[2]
     int passthrough;    // PCL's int32 overflow guard tripped: output = input
     int empty;
+    int key_bits;       // live bits of the leaf index (= bits of div0*div1*div2 - 1)
 };
 
 // order-preserving float <-> uint mapping for atomicMin/atomicMax bbox reductions
@@ -110,6 +111,7 @@ __device__ __forceinline__ GridParams make_grid(const uint32_t* bb, float ix, fl
     G.inv[0] = ix; G.inv[1] = iy; G.inv[2] = iz;
     G.empty = (bb[0] == 0xffffffffu);   // untouched min => no points
     G.passthrough = 0;
+    G.key_bits = 1;
     G.mul1 = G.mul2 = 0;
     G.min_b[0] = G.min_b[1] = G.min_b[2] = 0;
     if (G.empty) return G;
@@ -129,6 +131,8 @@ __device__ __forceinline__ GridParams make_grid(const uint32_t* bb, float ix, fl
     }
     G.mul1 = div[0];
     G.mul2 = div[0] * div[1];
+    const long long cells = (long long)div[0] * div[1] * div[2];
+    G.key_bits = cells > 1 ? 64 - __clzll(cells - 1) : 1;
     return G;
 }
 

@@ -170,7 +170,7 @@ int sort_pairs(o3r_ctx* ctx, KeyT* k0, KeyT* k1, uint32_t* v0, uint32_t* v1, con
     const uint32_t grid = tiles_ub * (uint32_t)n_seg;
     for (int p = 0; p < passes; ++p)
         LAUNCH_N(sizeof(KeyT) == 4 ? "k_rs_onesweep_u32" : "k_rs_onesweep_u64", (k_rs_onesweep<KeyT>), grid, kThreads,
-                 rs_scatter_smem<KeyT>(), k0, k1, v0, v1, seg_off, plan, p, passes, tiles_ub, ghist,
+                 rs_scatter_smem<KeyT>(), k0, k1, v0, v1, seg_off, plan, p, tiles_ub, ghist,
                  status + st_words * p, tickets + p, iota_first, gsrc, gdst);
     return O3R_OK;
 }
@@ -191,13 +191,16 @@ int vg_sorted_reduce(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const u
                      size_t per_seg_cap, const GridParams* grids, float ix, float iy, float iz, uint32_t min_points,
                      int z_shift, float4* out, uint32_t* out_off, uint64_t* out_keys, uint32_t* out_counts,
                      bool track_cells = false, const uint32_t* out_base = nullptr) {
-    CU(ctx->ghist.ensure((size_t)n_seg * 4 * kRsBins * 4));
+    const size_t gh_bytes = (size_t)n_seg * kMaxPasses * kRsBins * 4;
+    CU(ctx->ghist.ensure(gh_bytes));
     CU(ctx->plan_all.ensure((size_t)n_seg * sizeof(SortPlan)));
-    CU(cudaMemsetAsync(ctx->ghist.p, 0, (size_t)n_seg * 4 * kRsBins * 4, ctx->st));
+    CU(cudaMemsetAsync(ctx->ghist.p, 0, gh_bytes, ctx->st));
     SortPlan* plan = ctx->plan_all.as<SortPlan>();
+    // digit layout from each segment's live index bits (<= 31 -> at most 4 passes)
+    LAUNCH(k_rs_layout, cdiv(n_seg, 64), 64, 0, n_seg, grids, 31, plan);
     LAUNCH_N("k_rs_ghist_u32", (k_rs_ghist<uint32_t, 4>), dim3(std::max(1u, cdiv(per_seg_cap, kRsTile)), n_seg),
-             kThreads, 0, sb.k0, seg_off, ctx->ghist.as<uint32_t>());
-    LAUNCH(k_rs_plan, n_seg, kThreads, 0, ctx->ghist.as<uint32_t>(), seg_off, 4, plan, grids);
+             kThreads, 0, sb.k0, seg_off, plan, ctx->ghist.as<uint32_t>());
+    LAUNCH(k_rs_plan, n_seg, kThreads, 0, ctx->ghist.as<uint32_t>(), seg_off, plan, grids);
     // the fast reduce streams the points in sorted order: the last radix pass gathers them into `spts`
     const bool fast = min_points <= 1 && !out_keys && !out_counts;
     float4* spts = nullptr;
@@ -239,7 +242,8 @@ int vg_sorted_reduce(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const u
 inline int bits_for(long long range) { int b = 0; while ((1ll << b) <= range) ++b; return b; }
 
 template <typename KeyT, typename Items>
-int acc_build_cycle_t(o3r_ctx* ctx, Items items, size_t n, bool use_resident, const KeyCodec& kc, int passes) {
+int acc_build_cycle_t(o3r_ctx* ctx, Items items, size_t n, bool use_resident, const KeyCodec& kc, int total_bits) {
+    const int passes = std::max(1, (total_bits + kRsMaxBits - 1) / kRsMaxBits);
     uint32_t* cnt = ctx->counters.as<uint32_t>();
     const size_t n4 = (n + 63) & ~(size_t)63;
     CU(ctx->sortbuf.ensure(n4 * (2 * sizeof(KeyT) + 8)));
@@ -256,10 +260,11 @@ int acc_build_cycle_t(o3r_ctx* ctx, Items items, size_t n, bool use_resident, co
     CU(cudaMemsetAsync(cnt + CNT_NEW, 0, 4, ctx->st));
     const uint32_t* seg = ctx->seg2.as<uint32_t>();
     const uint32_t gk = std::min<uint32_t>(cdiv(n, kThreads), 148 * 8);
-    LAUNCH_N("k_acc_key", (k_acc_key<KeyT, Items>), gk, kThreads, 0, items, (uint32_t)n, ctx->inv_c, ctx->inv_cz, kc, passes,
-             k0, v0, ctx->ghist.as<uint32_t>());
     SortPlan* plan = ctx->plan_v2.as<SortPlan>();
-    LAUNCH(k_rs_plan, 1, kThreads, 0, ctx->ghist.as<uint32_t>(), seg, passes, plan, (const GridParams*)nullptr);
+    LAUNCH(k_rs_layout, 1, 32, 0, 1, (const GridParams*)nullptr, total_bits, plan);
+    LAUNCH_N("k_acc_key", (k_acc_key<KeyT, Items>), gk, kThreads, 0, items, (uint32_t)n, ctx->inv_c, ctx->inv_cz, kc, plan,
+             k0, v0, ctx->ghist.as<uint32_t>());
+    LAUNCH(k_rs_plan, 1, kThreads, 0, ctx->ghist.as<uint32_t>(), seg, plan, (const GridParams*)nullptr);
     float4* spts = nullptr;
     const float4* gsrc = nullptr;
     if constexpr (Items::kGather) if (ctx->gather_in_sort) {   // the last radix pass delivers the points in sorted order
@@ -330,9 +335,8 @@ int acc_build_cycle(o3r_ctx* ctx, const Items& items, size_t n, bool use_residen
     kc.wi = bits_for((long long)bb[3] - bb[0]);
     kc.wj = bits_for((long long)bb[4] - bb[1]);
     const int total = kc.wi + kc.wj + bits_for((long long)bb[5] - bb[2]);
-    const int passes = std::max(1, (total + 7) / 8);
-    if (total <= 32) return acc_build_cycle_t<uint32_t, Items>(ctx, items, n, use_resident, kc, passes);
-    return acc_build_cycle_t<uint64_t, Items>(ctx, items, n, use_resident, kc, passes);
+    if (total <= 32) return acc_build_cycle_t<uint32_t, Items>(ctx, items, n, use_resident, kc, total);
+    return acc_build_cycle_t<uint64_t, Items>(ctx, items, n, use_resident, kc, total);
 }
 
 // Applies the cycle's cell list to the resident shard: in-place update of found cells, sorted insert of new ones.
@@ -1096,13 +1100,13 @@ int o3r_exchange_pack(o3r_ctx* ctx, int world, o3r_cell* send_dev, size_t cap, u
     SortU32 sb;
     rc = carve_sort_u32(ctx, n, sb);
     if (rc) return rc;
-    CU(ctx->okeys.ensure(256 * 4 + sizeof(SortPlan)));
-    uint32_t* ocnt = ctx->okeys.as<uint32_t>();
-    SortPlan* plan = reinterpret_cast<SortPlan*>(ocnt + 256);
+    CU(ctx->okeys.ensure((size_t)kMaxPasses * kRsBins * 4 + sizeof(SortPlan)));
+    uint32_t* ocnt = ctx->okeys.as<uint32_t>();   // laid out like ghist: the owner histogram is pass 0's
+    SortPlan* plan = reinterpret_cast<SortPlan*>(ocnt + kMaxPasses * kRsBins);
     SortPlan pl;
     memset(&pl, 0, sizeof(pl));
-    pl.active[0] = 1; pl.final_parity = 1; pl.n_active = 1;
-    CU(cudaMemsetAsync(ocnt, 0, 256 * 4, ctx->st));
+    pl.active_mask = 1; pl.final_parity = 1; pl.n_active = 1; pl.n_passes = 1; pl.bits[0] = 8;
+    CU(cudaMemsetAsync(ocnt, 0, (size_t)kMaxPasses * kRsBins * 4, ctx->st));
     CU(cudaMemcpyAsync(plan, &pl, sizeof(pl), cudaMemcpyHostToDevice, ctx->st));
     const uint32_t seg_h[2] = {0u, n};
     CU(cudaMemcpyAsync(ctx->seg2.p, seg_h, 8, cudaMemcpyHostToDevice, ctx->st));

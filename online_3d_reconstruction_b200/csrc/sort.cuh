@@ -1,16 +1,18 @@
 // sort.cuh — hand-written segmented LSD radix sort of (key, u32 value) pairs, plus the exclusive-scan
-// kernels the pipeline uses.  No Thrust / CUB.
+// kernel the pipeline uses.  No Thrust / CUB.
 //
-// 8-bit digits.  k_rs_ghist reads the keys once and builds every pass's whole-segment digit histogram;
-// each pass is then ONE kernel (k_rs_onesweep): stable in-tile ranking with warp match_any, tile offsets
-// by decoupled look-back, exchange through shared memory so that every digit run leaves the CTA as one
-// coalesced burst.  Stability is what makes the later per-voxel sums run in input order (bit-exact with
-// the oracle's stable order).
+// Digits are up to kRsMaxBits wide and sized per segment: k_rs_layout splits the segment's live key bits evenly
+// over the fewest passes (28-bit per-frame voxel index -> 7+7+7+7, 20-bit combined-grid key -> 7+7+6).
+// k_rs_ghist reads the keys once and builds every pass's whole-segment digit histogram; each pass is then
+// ONE kernel (k_rs_onesweep): stable in-tile ranking with warp match_any, tile offsets by decoupled
+// look-back, exchange through shared memory so that every digit run leaves the CTA as one coalesced burst.
+// Stability is what makes the later per-voxel sums run in input order (bit-exact with the oracle's stable
+// order).
 //
 // Segments (one per frame for the per-frame grid, a single one for the combined grid) are described
 // by a device array seg_off[S+1]; launches are sized by a host upper bound and surplus CTAs exit.
-// A per-segment SortPlan lets passes whose digit is constant over the segment be skipped entirely
-// (the 64-bit absolute cell keys of the combined grid have 4-6 such digits).
+// The per-segment SortPlan also skips passes whose digit is constant over the segment and whole
+// segments that need no sorting (PCL pass-through frames).
 #pragma once
 #include "common.cuh"
 
@@ -18,14 +20,21 @@ namespace o3r {
 
 constexpr int kRsItems = 16;
 constexpr int kRsTile = kThreads * kRsItems;  // 4096 pairs per CTA
-constexpr int kRsBins = 256;
+// Measured on B200 (r01): 10-bit digits save a pass (28-bit index: 3 instead of 4) but the per-tile bin work
+// (warps x bins counters to prefix, 4 look-backs per thread) makes each pass ~50 % slower; 8 bits wins.
+constexpr int kRsMaxBits = 8;
+constexpr int kRsBins = 1 << kRsMaxBits;      // bins at most per pass
+constexpr int kRsBpt = kRsBins / kThreads;    // bins per thread
 constexpr int kMaxPasses = 8;
 
 struct SortPlan {
-    uint8_t active[kMaxPasses];
-    uint8_t in_parity[kMaxPasses];   // which ping-pong buffer pass p reads
-    uint32_t final_parity;           // buffer holding the sorted result
+    uint32_t active_mask;    // bit p: pass p runs
+    uint32_t parity_mask;    // bit p: pass p reads ping-pong buffer 1
+    uint32_t final_parity;   // buffer holding the sorted result
     uint32_t n_active;
+    uint32_t n_passes;
+    uint8_t shift[kMaxPasses];
+    uint8_t bits[kMaxPasses];
 };
 
 // ---- generic single-segment exclusive scan (one CTA, coalesced, carry across iterations) ----------------
@@ -50,34 +59,59 @@ __global__ void __launch_bounds__(kThreads) k_scan_u32(const uint32_t* __restric
     if (threadIdx.x == 0 && total_out) *total_out = carry;
 }
 
-// ---- per-segment plan from whole-segment digit histograms ghist[S][passes][256] ---------------------------
-__global__ void k_rs_plan(const uint32_t* __restrict__ ghist, const uint32_t* __restrict__ seg_off, int passes,
+// ---- digit layout: split `key_bits` live bits into the fewest passes of <= 10 bits -------------------------------
+// key_bits comes from the segment's VoxelGrid (grids[s].key_bits) or is the same for all segments (fixed_bits).
+__global__ void k_rs_layout(int n_seg, const GridParams* __restrict__ grids, int fixed_bits, SortPlan* __restrict__ plan) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    int kb = grids ? grids[s].key_bits : fixed_bits;
+    kb = max(1, min(kb, 64));
+    const int np = (kb + kRsMaxBits - 1) / kRsMaxBits;
+    const int base = kb / np, rem = kb - base * np;
+    SortPlan pl;
+    pl.active_mask = pl.parity_mask = pl.final_parity = pl.n_active = 0;
+    pl.n_passes = np;
+    int sh = 0;
+    for (int p = 0; p < kMaxPasses; ++p) {
+        const int w = p < np ? base + (p < rem ? 1 : 0) : 0;
+        pl.shift[p] = (uint8_t)sh;
+        pl.bits[p] = (uint8_t)w;
+        sh += w;
+    }
+    plan[s] = pl;
+}
+
+// ---- which passes run: skip digits that are constant over the segment and segments that need no sorting ---------
+// ghist[S][kMaxPasses][kRsBins]
+__global__ void k_rs_plan(const uint32_t* __restrict__ ghist, const uint32_t* __restrict__ seg_off,
                           SortPlan* __restrict__ plan, const GridParams* __restrict__ grids) {
     __shared__ int s_trivial[kMaxPasses];
     const int s = blockIdx.x;
     const uint32_t n = seg_off[s + 1] - seg_off[s];
+    const int np = plan[s].n_passes;
     if (threadIdx.x < kMaxPasses) s_trivial[threadIdx.x] = 0;
     __syncthreads();
-    for (int p = 0; p < passes; ++p)
-        if (ghist[((size_t)s * passes + p) * kRsBins + threadIdx.x] == n) s_trivial[p] = 1;
+    for (int p = 0; p < np; ++p)
+        for (int b = threadIdx.x; b < kRsBins; b += kThreads)
+            if (ghist[((size_t)s * kMaxPasses + p) * kRsBins + b] == n) s_trivial[p] = 1;
     __syncthreads();
     if (threadIdx.x == 0) {
-        SortPlan pl;
-        uint32_t par = 0, na = 0;
+        uint32_t am = 0, pm = 0, par = 0, na = 0;
         for (int p = 0; p < kMaxPasses; ++p) {
-            const bool act = p < passes && n > 0 && !s_trivial[p] && !(grids && grids[s].passthrough);
-            pl.active[p] = act;
-            pl.in_parity[p] = (uint8_t)par;
+            const bool act = p < np && n > 0 && !s_trivial[p] && !(grids && grids[s].passthrough);
+            if (act) am |= 1u << p;
+            if (par) pm |= 1u << p;
             if (act) { par ^= 1u; ++na; }
         }
-        pl.final_parity = par;
-        pl.n_active = na;
-        plan[s] = pl;
+        plan[s].active_mask = am;
+        plan[s].parity_mask = pm;
+        plan[s].final_parity = par;
+        plan[s].n_active = na;
     }
 }
 
 template <typename KeyT>
-__device__ __forceinline__ uint32_t rs_digit(KeyT k, int shift) { return (uint32_t)(k >> shift) & 255u; }
+__device__ __forceinline__ uint32_t rs_digit(KeyT k, int shift, uint32_t mask) { return (uint32_t)(k >> shift) & mask; }
 
 // shared-memory histogram update by the lanes of `vm`: one aggregated atomic when the whole warp agrees on the
 // digit (the constant high digits that would otherwise serialise), plain atomics otherwise
@@ -92,16 +126,21 @@ __device__ __forceinline__ void hist_add(uint32_t* sh, uint32_t d, unsigned vm, 
 }
 
 // ---- whole-segment digit histograms for every pass in one read of the keys ------------------------------------
-// ghist[S][PASSES][256]; must be zeroed by the caller.
-template <typename KeyT, int PASSES>
+// ghist[S][kMaxPasses][kRsBins]; must be zeroed by the caller.  MAXP bounds the passes of this key type.
+template <typename KeyT, int MAXP>
 __global__ void __launch_bounds__(kThreads) k_rs_ghist(const KeyT* __restrict__ keys, const uint32_t* __restrict__ seg_off,
-                                                       uint32_t* __restrict__ ghist) {
-    __shared__ uint32_t sh[PASSES * kRsBins];
+                                                       const SortPlan* __restrict__ plan, uint32_t* __restrict__ ghist) {
+    __shared__ uint32_t sh[MAXP * kRsBins];
     const int s = blockIdx.y;
     const uint32_t t = blockIdx.x;
     const uint32_t beg = seg_off[s], n = seg_off[s + 1] - beg;
     if (t * kRsTile >= n) return;
-    for (int i = threadIdx.x; i < PASSES * kRsBins; i += kThreads) sh[i] = 0;
+    const int np = min((int)plan[s].n_passes, MAXP);
+    int shift[MAXP];
+    uint32_t mask[MAXP];
+#pragma unroll
+    for (int p = 0; p < MAXP; ++p) { shift[p] = plan[s].shift[p]; mask[p] = (1u << plan[s].bits[p]) - 1u; }
+    for (int i = threadIdx.x; i < MAXP * kRsBins; i += kThreads) sh[i] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll 2
@@ -112,23 +151,30 @@ __global__ void __launch_bounds__(kThreads) k_rs_ghist(const KeyT* __restrict__ 
         if (valid) {
             const KeyT k = keys[beg + i];
 #pragma unroll
-            for (int p = 0; p < PASSES; ++p) hist_add(sh + p * kRsBins, rs_digit(k, 8 * p), vm, lane);
+            for (int p = 0; p < MAXP; ++p)
+                if (p < np) hist_add(sh + p * kRsBins, rs_digit(k, shift[p], mask[p]), vm, lane);
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < PASSES * kRsBins; i += kThreads)
-        if (sh[i]) atomicAdd(&ghist[(size_t)s * PASSES * kRsBins + i], sh[i]);
+    for (int i = threadIdx.x; i < MAXP * kRsBins; i += kThreads)
+        if (sh[i]) atomicAdd(&ghist[(size_t)s * kMaxPasses * kRsBins + i], sh[i]);
 }
 
 // ---- one radix pass in one kernel: stable in-tile rank, decoupled look-back for the tile's digit offsets ---------
-// ("onesweep"): every tile publishes its per-digit counts in status[seg][tile][256] (2 flag bits + 30 count
-// bits in one word), then each of the 256 threads walks back over the predecessors' words of ITS digit until it
+// ("onesweep"): every tile publishes its per-digit counts in status[seg][tile][1024] (2 flag bits + 30 count
+// bits in one word), then each thread walks back over the predecessors' words of ITS digit(s) until it
 // meets an inclusive prefix.  Tiles take their index from an atomic ticket so a predecessor is always resident
 // or finished before anyone waits on it.
-// Dynamic shared memory: keys[4096] | vals[4096] | cnt[kWarps][256] | dstart[256] | gbase[256] | scan[34]
+// Dynamic shared memory: pairs[4096] (key, value) | cnt[kWarps][1024] u16 | gbase[1024] u32 | dstart[1024] u16 | scan
+template <typename KeyT>
+struct RsPair { KeyT k; uint32_t v; };
+template <>
+struct __align__(8) RsPair<uint32_t> { uint32_t k; uint32_t v; };
+
 template <typename KeyT>
 constexpr size_t rs_scatter_smem() {
-    return (size_t)(kWarps * kRsBins + 2 * kRsBins + 34 + 2) * 4 + (size_t)kRsTile * (sizeof(KeyT) + 4);
+    return (size_t)kRsTile * sizeof(RsPair<KeyT>) + (size_t)kWarps * kRsBins * 2 + (size_t)kRsBins * 4 + (size_t)kRsBins * 2 +
+           36 * 4;
 }
 
 constexpr uint32_t kStLocal = 1u << 30, kStGlobal = 2u << 30, kStMask = (1u << 30) - 1u;
@@ -144,21 +190,17 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
 }
 
 template <typename KeyT>
-__global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? 4 : 3) k_rs_onesweep(KeyT* __restrict__ keys0, KeyT* __restrict__ keys1,
-                                                          uint32_t* __restrict__ vals0, uint32_t* __restrict__ vals1,
-                                                          const uint32_t* __restrict__ seg_off,
-                                                          const SortPlan* __restrict__ plan, int pass, int passes,
-                                                          uint32_t tiles_ub, const uint32_t* __restrict__ ghist,
-                                                          uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
-                                                          int iota_first, const float4* __restrict__ gsrc,
-                                                          float4* __restrict__ gdst) {
+__global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? 4 : 3) k_rs_onesweep(
+    KeyT* __restrict__ keys0, KeyT* __restrict__ keys1, uint32_t* __restrict__ vals0, uint32_t* __restrict__ vals1,
+    const uint32_t* __restrict__ seg_off, const SortPlan* __restrict__ plan, int pass, uint32_t tiles_ub,
+    const uint32_t* __restrict__ ghist, uint32_t* __restrict__ status, uint32_t* __restrict__ ticket, int iota_first,
+    const float4* __restrict__ gsrc, float4* __restrict__ gdst) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
-    KeyT* s_keys = reinterpret_cast<KeyT*>(rs_smem);
-    uint32_t* s_vals = reinterpret_cast<uint32_t*>(rs_smem + (size_t)kRsTile * sizeof(KeyT));
-    uint32_t* cnt = s_vals + kRsTile;            // [kWarps][256]
-    uint32_t* dstart = cnt + kWarps * kRsBins;   // [256] tile-local start of each digit run
-    uint32_t* gbase = dstart + kRsBins;          // [256] segment-relative destination of each digit run
-    uint32_t* s_scan = gbase + kRsBins;          // [34]
+    RsPair<KeyT>* s_pairs = reinterpret_cast<RsPair<KeyT>*>(rs_smem);
+    uint16_t* cnt = reinterpret_cast<uint16_t*>(rs_smem + (size_t)kRsTile * sizeof(RsPair<KeyT>));   // [kWarps][1024]
+    uint32_t* gbase = reinterpret_cast<uint32_t*>(cnt + kWarps * kRsBins);   // [1024] destination of local position i: gbase[d] + i
+    uint16_t* dstart = reinterpret_cast<uint16_t*>(gbase + kRsBins);         // [1024] tile-local start of each digit run
+    uint32_t* s_scan = reinterpret_cast<uint32_t*>(dstart + kRsBins);        // [34]
     uint32_t* s_ticket = s_scan + 34;
 
     if (threadIdx.x == 0) *s_ticket = atomicAdd(ticket, 1u);
@@ -166,119 +208,184 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? 4 : 3) k_rs_ones
     const uint32_t lin = *s_ticket;
     const int s = lin / tiles_ub;
     const uint32_t t = lin - (uint32_t)s * tiles_ub;
-    const SortPlan pl = plan[s];
-    if (!pl.active[pass]) return;
+    const uint32_t amask = plan[s].active_mask;
+    if (!((amask >> pass) & 1u)) return;
     const uint32_t beg = seg_off[s], n = seg_off[s + 1] - beg;
     const uint32_t nt = (n + kRsTile - 1) / kRsTile;
     if (t >= nt) return;
 
-    const int par = pl.in_parity[pass];
+    const int par = (plan[s].parity_mask >> pass) & 1u;
+    const int shift = plan[s].shift[pass];
+    const uint32_t nb = 1u << plan[s].bits[pass], dmask = nb - 1u;
     const KeyT* kin = (par ? keys1 : keys0) + beg;
     const uint32_t* vin = (par ? vals1 : vals0) + beg;
     KeyT* kout = (par ? keys0 : keys1) + beg;
     uint32_t* vout = (par ? vals0 : vals1) + beg;
-    bool first = true;
-    for (int q = 0; q < pass; ++q) first = first && !pl.active[q];
-    bool last = true;
-    for (int q = pass + 1; q < passes; ++q) last = last && !pl.active[q];
-    // in the last active pass the 16-byte records the values point at can be delivered in sorted order
-    // (gdst[beg + rank] = gsrc[value]) instead of the values: 16 independent gathers per thread
-    const bool gather = last && gdst != nullptr;
+    const bool first = (amask & ((1u << pass) - 1u)) == 0u;   // no active pass before this one
+    const bool last = (amask >> (pass + 1)) == 0u;            // none after it
     const bool iota = iota_first && first;   // values are the global element index, not read from memory
-    const int shift = pass * 8, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // in the last active pass the 16-byte records the values point at can be delivered in sorted order
+    // (gdst[beg + rank] = gsrc[value]) instead of the values
+    const bool gather = last && gdst != nullptr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
+    const int b0 = threadIdx.x * kRsBpt;   // this thread's bin(s)
 
+    {   // zero the warp-private u16 counters
+        uint32_t* cz = reinterpret_cast<uint32_t*>(cnt);
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) cnt[w * kRsBins + threadIdx.x] = 0;
+        for (int i = 0; i < kWarps * kRsBins / 2 / kThreads; ++i) cz[i * kThreads + threadIdx.x] = 0u;
+    }
     // exclusive scan of the segment's digit histogram = where each digit's run starts in the segment
-    uint32_t tot;
-    const uint32_t dbase = block_excl_scan(ghist[((size_t)s * passes + pass) * kRsBins + threadIdx.x], s_scan, tot);
+    uint32_t dbase[kRsBpt];
+    {
+        const uint32_t* gh = ghist + ((size_t)s * kMaxPasses + pass) * kRsBins + b0;
+        uint32_t h[kRsBpt], sum = 0;
+#pragma unroll
+        for (int q = 0; q < kRsBpt; ++q) { h[q] = gh[q]; sum += h[q]; }
+        uint32_t tot;
+        uint32_t e = block_excl_scan(sum, s_scan, tot);
+#pragma unroll
+        for (int q = 0; q < kRsBpt; ++q) { dbase[q] = e; e += h[q]; }
+    }
 
     KeyT key[kRsItems];
     uint32_t rk[kRsItems / 2];   // two 16-bit in-warp ranks per word
     const uint32_t wbase = t * kRsTile + warp * (32 * kRsItems);
     const uint32_t ntile = min((uint32_t)kRsTile, n - t * kRsTile);
+    const bool full = ntile == (uint32_t)kRsTile;   // no bounds checks in a full tile
+    {
+        const KeyT* kp = kin + wbase + lane;
+        if (full) {
 #pragma unroll
-    for (int r = 0; r < kRsItems; ++r) {
-        const uint32_t i = wbase + r * 32 + lane;
-        key[r] = (i < n) ? kin[i] : ~(KeyT)0;
+            for (int r = 0; r < kRsItems; ++r) key[r] = kp[r * 32];
+        } else {
+#pragma unroll
+            for (int r = 0; r < kRsItems; ++r) key[r] = (wbase + r * 32 + lane < n) ? kp[r * 32] : ~(KeyT)0;
+        }
     }
-    uint32_t* wc = cnt + warp * kRsBins;
+    uint16_t* wc = cnt + warp * kRsBins;
 #pragma unroll
     for (int r = 0; r < kRsItems; ++r) {
-        // padding items carry digit 255 and sit at the very end of the tile order, so they never
+        // padding items carry the highest digit and sit at the very end of the tile order, so they never
         // precede a real item inside any digit run
-        const uint32_t d = rs_digit(key[r], shift);
+        const uint32_t d = rs_digit(key[r], shift, dmask);
         const unsigned peers = __match_any_sync(kFull, d);
         const uint32_t old = wc[d];                   // every peer reads the counter (broadcast) ...
         __syncwarp();
-        if ((peers & lt) == 0u) wc[d] = old + __popc(peers);   // ... then the lowest peer bumps it
+        if ((peers & lt) == 0u) wc[d] = (uint16_t)(old + __popc(peers));   // ... then the lowest peer bumps it
         __syncwarp();
         const uint32_t rnk = old + __popc(peers & lt);
         if (r & 1) rk[r >> 1] |= rnk << 16; else rk[r >> 1] = rnk;
     }
     // values are only needed for the exchange below: load them now so the latency hides behind the scans
     uint32_t val[kRsItems];
+    if (iota) {
 #pragma unroll
-    for (int r = 0; r < kRsItems; ++r) {
-        const uint32_t i = wbase + r * 32 + lane;
-        val[r] = (i < n) ? (iota ? beg + i : vin[i]) : 0u;
+        for (int r = 0; r < kRsItems; ++r) val[r] = beg + wbase + r * 32 + lane;
+    } else {
+        const uint32_t* vp = vin + wbase + lane;
+        if (full) {
+#pragma unroll
+            for (int r = 0; r < kRsItems; ++r) val[r] = vp[r * 32];
+        } else {
+#pragma unroll
+            for (int r = 0; r < kRsItems; ++r) val[r] = (wbase + r * 32 + lane < n) ? vp[r * 32] : 0u;
+        }
     }
     __syncthreads();
     // per digit: exclusive prefix over warps, tile total
-    uint32_t run = 0;
+    uint32_t run[kRsBpt];
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-        const uint32_t c = cnt[w * kRsBins + threadIdx.x];
-        cnt[w * kRsBins + threadIdx.x] = run;
-        run += c;
-    }
-    // real items of this digit in this tile (padding only ever inflates digit 255)
-    uint32_t real = run;
-    if (threadIdx.x == kRsBins - 1) real -= (kRsTile - ntile);
-    // publish, look back
-    uint32_t* st = status + ((size_t)s * tiles_ub + t) * kRsBins + threadIdx.x;
-    uint32_t prefix = 0;
-    if (t == 0) {
-        st_volatile_u32(st, kStGlobal | real);
-    } else {
-        st_volatile_u32(st, kStLocal | real);
-        const uint32_t* pst = st - kRsBins;
-        for (uint32_t back = t; back > 0; --back, pst -= kRsBins) {
-            uint32_t v;
-            while (((v = ld_volatile_u32(pst)) >> 30) == 0u) __nanosleep(32);
-            prefix += v & kStMask;
-            if ((v >> 30) == 2u) break;
+    for (int q = 0; q < kRsBpt; ++q) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t c = cnt[w * kRsBins + b0 + q];
+            cnt[w * kRsBins + b0 + q] = (uint16_t)acc;
+            acc += c;
         }
-        st_volatile_u32(st, kStGlobal | (prefix + real));
+        run[q] = acc;
     }
-    const uint32_t ds = block_excl_scan(run, s_scan, tot);
-    dstart[threadIdx.x] = ds;
-    gbase[threadIdx.x] = dbase + prefix - ds;   // destination of tile-local position i of this digit: gbase[d] + i
+    // publish, look back (padding only ever inflates the highest digit)
+    uint32_t prefix[kRsBpt];
+    {
+        uint32_t* st = status + ((size_t)s * tiles_ub + t) * kRsBins + b0;
+#pragma unroll
+        for (int q = 0; q < kRsBpt; ++q) {
+            prefix[q] = 0;
+            if ((uint32_t)(b0 + q) < nb) {
+                uint32_t real = run[q];
+                if ((uint32_t)(b0 + q) == nb - 1u) real -= (kRsTile - ntile);
+                st_volatile_u32(st + q, (t == 0 ? kStGlobal : kStLocal) | real);
+            }
+        }
+        if (t > 0) {
+#pragma unroll
+            for (int q = 0; q < kRsBpt; ++q) {
+                if ((uint32_t)(b0 + q) >= nb) continue;
+                uint32_t real = run[q];
+                if ((uint32_t)(b0 + q) == nb - 1u) real -= (kRsTile - ntile);
+                const uint32_t* pst = st + q - kRsBins;
+                uint32_t pf = 0;
+                for (uint32_t back = t; back > 0; --back, pst -= kRsBins) {
+                    uint32_t v;
+                    while (((v = ld_volatile_u32(pst)) >> 30) == 0u) __nanosleep(32);
+                    pf += v & kStMask;
+                    if ((v >> 30) == 2u) break;
+                }
+                prefix[q] = pf;
+                st_volatile_u32(st + q, kStGlobal | (pf + real));
+            }
+        }
+    }
+    {
+        uint32_t tot;
+        uint32_t rsum = 0;
+#pragma unroll
+        for (int q = 0; q < kRsBpt; ++q) rsum += run[q];
+        uint32_t ds = block_excl_scan(rsum, s_scan, tot);
+#pragma unroll
+        for (int q = 0; q < kRsBpt; ++q) {
+            dstart[b0 + q] = (uint16_t)ds;
+            gbase[b0 + q] = dbase[q] + prefix[q] - ds;
+            ds += run[q];
+        }
+    }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < kRsItems; ++r) {
-        const uint32_t d = rs_digit(key[r], shift);
-        const uint32_t pos = dstart[d] + wc[d] + ((rk[r >> 1] >> ((r & 1) * 16)) & 0xffffu);
-        s_keys[pos] = key[r];
-        s_vals[pos] = val[r];
+        const uint32_t d = rs_digit(key[r], shift, dmask);
+        const uint32_t pos = (uint32_t)dstart[d] + wc[d] + ((rk[r >> 1] >> ((r & 1) * 16)) & 0xffffu);
+        RsPair<KeyT> pr;
+        pr.k = key[r]; pr.v = val[r];
+        s_pairs[pos] = pr;
     }
     __syncthreads();
     if (gather) {
         float4* go = gdst + beg;
 #pragma unroll 4
         for (uint32_t i = threadIdx.x; i < ntile; i += kThreads) {
-            const KeyT k = s_keys[i];
-            const uint32_t g = gbase[rs_digit(k, shift)] + i;
-            kout[g] = k;
-            go[g] = gsrc[s_vals[i]];
+            const RsPair<KeyT> pr = s_pairs[i];
+            const uint32_t g = gbase[rs_digit(pr.k, shift, dmask)] + i;
+            kout[g] = pr.k;
+            go[g] = gsrc[pr.v];
+        }
+    } else if (full) {
+#pragma unroll
+        for (int r = 0; r < kRsItems; ++r) {
+            const uint32_t i = r * kThreads + threadIdx.x;
+            const RsPair<KeyT> pr = s_pairs[i];
+            const uint32_t g = gbase[rs_digit(pr.k, shift, dmask)] + i;
+            kout[g] = pr.k;
+            vout[g] = pr.v;
         }
     } else {
         for (uint32_t i = threadIdx.x; i < ntile; i += kThreads) {
-            const KeyT k = s_keys[i];
-            const uint32_t g = gbase[rs_digit(k, shift)] + i;
-            kout[g] = k;
-            vout[g] = s_vals[i];
+            const RsPair<KeyT> pr = s_pairs[i];
+            const uint32_t g = gbase[rs_digit(pr.k, shift, dmask)] + i;
+            kout[g] = pr.k;
+            vout[g] = pr.v;
         }
     }
 }

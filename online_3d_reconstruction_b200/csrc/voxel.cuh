@@ -544,13 +544,14 @@ __global__ void k_cellbb_init(int* cellbb) {
     if (threadIdx.x < 6) cellbb[threadIdx.x] = threadIdx.x < 3 ? 0x7fffffff : (int)0x80000000;
 }
 
-// compact keys of the cycle's items + whole-array digit histograms for `passes` digits
+// compact keys of the cycle's items + whole-array digit histograms for the plan's digit layout
 template <typename KeyT, typename Items>
-__global__ void __launch_bounds__(kThreads) k_acc_key(Items items, uint32_t n, float ix, float iz, KeyCodec kc, int passes,
-                                                      KeyT* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                      uint32_t* __restrict__ ghist) {
+__global__ void __launch_bounds__(kThreads) k_acc_key(Items items, uint32_t n, float ix, float iz, KeyCodec kc,
+                                                      const SortPlan* __restrict__ plan, KeyT* __restrict__ keys,
+                                                      uint32_t* __restrict__ vals, uint32_t* __restrict__ ghist) {
     __shared__ uint32_t sh[kMaxPasses * kRsBins];
-    for (int i = threadIdx.x; i < passes * kRsBins; i += kThreads) sh[i] = 0;
+    const int np = plan[0].n_passes;
+    for (int i = threadIdx.x; i < np * kRsBins; i += kThreads) sh[i] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     for (uint32_t base = blockIdx.x * kThreads; base < n; base += gridDim.x * kThreads) {
@@ -566,10 +567,11 @@ __global__ void __launch_bounds__(kThreads) k_acc_key(Items items, uint32_t n, f
         }
         const unsigned vm = __ballot_sync(kFull, valid);
         if (valid)
-            for (int p = 0; p < passes; ++p) hist_add(sh + p * kRsBins, (uint32_t)(k >> (8 * p)) & 255u, vm, lane);
+            for (int p = 0; p < np; ++p)
+                hist_add(sh + p * kRsBins, rs_digit(k, (int)plan[0].shift[p], (1u << plan[0].bits[p]) - 1u), vm, lane);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < passes * kRsBins; i += kThreads)
+    for (int i = threadIdx.x; i < np * kRsBins; i += kThreads)
         if (sh[i]) atomicAdd(&ghist[i], sh[i]);
 }
 
