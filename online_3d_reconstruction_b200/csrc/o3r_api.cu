@@ -59,6 +59,8 @@ struct o3r_ctx {
     std::vector<cudaEvent_t> chunk_ev;
     int chunk_frames = 10, chunk_frames_dev = 1 << 30;
     int gather_in_sort = 0;   // experiment: deliver points in sorted order from the last radix pass
+    int vg_short = 0;         // per-frame grid reduce: 1 = warp-level short-run kernel (instruction bound, 0.60 ms),
+                              // 0 = shared-memory staged kernel (L1 bound, 0.56 ms) — measured r01, config 2
     cudaEvent_t chunk_event(size_t i) {
         while (chunk_ev.size() <= i) {
             cudaEvent_t e;
@@ -225,7 +227,12 @@ int vg_sorted_reduce(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const u
     LAUNCH(k_vg_heads, grid, kThreads, 0, A, ctx->head_cnt.as<uint32_t>());
     LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->head_cnt.as<uint32_t>(), ctx->head_off.as<uint32_t>(), (uint32_t)nt,
            cnt + CNT_VOX);
-    if (fast) {
+    if (fast && ctx->vg_short && !spts && !z_shift) {   // (the combined grid has long runs: staged kernel)
+        // short runs (per-frame grid): warp-level reduce, no shared-memory staging, no carry chain
+        LAUNCH(k_vg_reduce_s, grid, kThreads, 0, A, ctx->head_off.as<uint32_t>(), out, out_off, track_cells ? 1 : 0,
+               ctx->inv_c, ctx->inv_cz, reinterpret_cast<int*>(cnt + CNT_CELLBB), out_base);
+        if (!out_base) LAUNCH(k_set_total, 1, 32, 0, out_off + n_seg, cnt + CNT_VOX);
+    } else if (fast) {
         const size_t wbytes = 64 + (nt + 1) * sizeof(RunCarry);
         CU(ctx->runwork.ensure(wbytes));
         CU(cudaMemsetAsync(ctx->runwork.p, 0, wbytes, ctx->st));
@@ -702,6 +709,7 @@ int o3r_create(const o3r_params* params, o3r_ctx** out_ctx) {
     if (const char* cf = getenv("O3R_CHUNK_FRAMES")) ctx->chunk_frames = std::max(1, atoi(cf));
     if (const char* cf = getenv("O3R_CHUNK_FRAMES_DEV")) ctx->chunk_frames_dev = std::max(1, atoi(cf));
     if (const char* cf = getenv("O3R_GATHER_IN_SORT")) ctx->gather_in_sort = atoi(cf) != 0;
+    if (const char* cf = getenv("O3R_VG_SHORT")) ctx->vg_short = atoi(cf) != 0;
     if ((e = cudaMallocHost((void**)&ctx->h_counters, CNT_N * 4)) != cudaSuccess) return bail(e, "pinned");
     if ((e = ctx->counters.ensure(CNT_N * 4)) != cudaSuccess) return bail(e, "counters");
     if ((e = cudaMemsetAsync(ctx->counters.p, 0, CNT_N * 4, ctx->st)) != cudaSuccess) return bail(e, "memset");

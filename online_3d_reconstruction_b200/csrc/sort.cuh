@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kThreads) k_rs_ghist(const KeyT* __restrict__ 
 // bits in one word), then each thread walks back over the predecessors' words of ITS digit(s) until it
 // meets an inclusive prefix.  Tiles take their index from an atomic ticket so a predecessor is always resident
 // or finished before anyone waits on it.
-// Dynamic shared memory: pairs[4096] (key, value) | cnt[kWarps][1024] u16 | gbase[1024] u32 | dstart[1024] u16 | scan
+// Dynamic shared memory: pairs[4096] (key, value) | cnt[kWarps][bins] u16 | gbase[bins] u32 | scan
 template <typename KeyT>
 struct RsPair { KeyT k; uint32_t v; };
 template <>
@@ -173,8 +173,7 @@ struct __align__(8) RsPair<uint32_t> { uint32_t k; uint32_t v; };
 
 template <typename KeyT>
 constexpr size_t rs_scatter_smem() {
-    return (size_t)kRsTile * sizeof(RsPair<KeyT>) + (size_t)kWarps * kRsBins * 2 + (size_t)kRsBins * 4 + (size_t)kRsBins * 2 +
-           36 * 4;
+    return (size_t)kRsTile * sizeof(RsPair<KeyT>) + (size_t)kWarps * kRsBins * 2 + (size_t)kRsBins * 4 + 36 * 4;
 }
 
 constexpr uint32_t kStLocal = 1u << 30, kStGlobal = 2u << 30, kStMask = (1u << 30) - 1u;
@@ -199,8 +198,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? 4 : 3) k_rs_ones
     RsPair<KeyT>* s_pairs = reinterpret_cast<RsPair<KeyT>*>(rs_smem);
     uint16_t* cnt = reinterpret_cast<uint16_t*>(rs_smem + (size_t)kRsTile * sizeof(RsPair<KeyT>));   // [kWarps][1024]
     uint32_t* gbase = reinterpret_cast<uint32_t*>(cnt + kWarps * kRsBins);   // [1024] destination of local position i: gbase[d] + i
-    uint16_t* dstart = reinterpret_cast<uint16_t*>(gbase + kRsBins);         // [1024] tile-local start of each digit run
-    uint32_t* s_scan = reinterpret_cast<uint32_t*>(dstart + kRsBins);        // [34]
+    uint32_t* s_scan = gbase + kRsBins;                                      // [34]
     uint32_t* s_ticket = s_scan + 34;
 
     if (threadIdx.x == 0) *s_ticket = atomicAdd(ticket, 1u);
@@ -347,8 +345,10 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? 4 : 3) k_rs_ones
         uint32_t ds = block_excl_scan(rsum, s_scan, tot);
 #pragma unroll
         for (int q = 0; q < kRsBpt; ++q) {
-            dstart[b0 + q] = (uint16_t)ds;
             gbase[b0 + q] = dbase[q] + prefix[q] - ds;
+            // fold the digit's tile-local start into every warp's prefix: one lookup per item in the exchange
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) cnt[w * kRsBins + b0 + q] += (uint16_t)ds;
             ds += run[q];
         }
     }
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? 4 : 3) k_rs_ones
 #pragma unroll
     for (int r = 0; r < kRsItems; ++r) {
         const uint32_t d = rs_digit(key[r], shift, dmask);
-        const uint32_t pos = (uint32_t)dstart[d] + wc[d] + ((rk[r >> 1] >> ((r & 1) * 16)) & 0xffffu);
+        const uint32_t pos = (uint32_t)wc[d] + ((rk[r >> 1] >> ((r & 1) * 16)) & 0xffffu);
         RsPair<KeyT> pr;
         pr.k = key[r]; pr.v = val[r];
         s_pairs[pos] = pr;
