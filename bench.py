@@ -35,7 +35,11 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 from online_3d_reconstruction_b200 import abi, synth  # noqa: E402
 
 # (workload, kernel) -> DRAM bytes per launch from `ncu --set full` (see profiles/r01*_ncu_*.txt)
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {
+    # profiles/r01f_ncu_full.txt: 7 launches per cycle (4 per-frame-index passes: 391.6, 547.3, 547.7, 548.0 MB;
+    # 3 combined-key passes: 369.6, 370.1, 371.0 MB) -> mean per launch
+    ("config2_semidense_720p", "k_rs_onesweep_u32"): 449.3e6,
+}
 
 WORKLOADS = {
     # name: (rows, cols, disp_type, J, voxel_size, min_pts, dont_downsample, frames/step, seed, Q scale)
