@@ -352,6 +352,40 @@ def test_device_pointer_entry_point_matches_host_entry_point():
         _eq(A.downsamplePtCloud(), B.downsamplePtCloud())
 
 
+# ------------------------------------------------------------------------- full-size properties (720p)
+def test_full_resolution_properties_720p():
+    """BASELINE configs[1] geometry (1280x720, jump_pixels 1, voxel_size 0.05), 8 frames in two cycles — too big for
+    the oracle to be quick, so size-independent properties are checked instead:
+      * the incremental merge (engine 2, ACCUMULATE) and the one-shot PCL-style voxelisation of the retained cloud
+        (engine 1, RETAIN) are independent code paths and must agree bit for bit,
+      * the combined cloud is strictly increasing in its (y-cell, x-cell) key with one point per cell,
+      * per-frame counts are consistent with the batch, and re-voxelising the result returns it unchanged."""
+    keep = []
+    frames = _frames(1002, 8, 720, 1280, keep=keep)
+    p_acc = abi.make_params(jump_pixels=1, voxel_size=0.05, min_points_per_voxel=1, merge_mode=abi.MERGE_ACCUMULATE)
+    p_ret = abi.make_params(jump_pixels=1, voxel_size=0.05, min_points_per_voxel=1, merge_mode=abi.MERGE_RETAIN)
+    with Pose(p_acc) as A, Pose(p_ret) as R:
+        ca = np.concatenate([A.createCycleClouds(frames[:5]), A.createCycleClouds(frames[5:])])
+        cr = np.concatenate([R.createCycleClouds(frames[:5]), R.createCycleClouds(frames[5:])])
+        assert np.array_equal(ca, cr) and np.all(ca > 300000) and np.all(ca <= 748000)
+        assert R.cloudSize() == int(cr.sum())
+        a, r = A.downsamplePtCloud(), R.downsamplePtCloud()
+        _eq(a, r)
+        assert A.cloudSize() == len(a) > 10000
+        # strictly increasing cell keys
+        sh = a.copy()
+        sh["z"] += np.float32(500)
+        inv = np.float32(1.0) / np.float32(0.05)
+        i = np.floor(sh["x"] * inv).astype(np.int64)
+        j = np.floor(sh["y"] * inv).astype(np.int64)
+        key = (j << 21) + i
+        assert np.all(np.diff(key) > 0)
+        # idempotence through the stand-alone probe (same leaf, same z shift)
+        again, _, counts, passthrough = A.voxelGrid(sh, (0.05, 0.05, 1000.0), 1)
+        assert not passthrough and np.all(counts == 1)
+        _eq(again, sh)
+
+
 # -------------------------------------------------------------------------------------------- multi-GPU
 def test_exchange_two_ranks_equals_single_rank():
     """SURVEY §8e on one device: two contexts act as two ranks (frames f mod 2), exchange hash-partitioned
