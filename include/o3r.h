@@ -133,6 +133,14 @@ int o3r_frame_cloud(o3r_ctx* ctx, const o3r_frame* frame, int disp_type,
 int o3r_frames_cloud(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_type,
                      uint32_t* frame_counts);
 
+/* Starts the host->device copies of a coming o3r_frames_cloud call (same frame pointers, same n) on the context's copy
+ * stream and returns at once; the copies overlap whatever the context is computing (input staging is double-buffered:
+ * one prefetch may be pending while the call before it is issued, e.g. prefetch(k+1); frames_cloud(k); ...).
+ * The reference loads every image into host RAM up front (populateData, pose_functions.cpp:624-744); this is the
+ * device-side equivalent for the next cycle.  The host buffers must stay valid and unchanged until that
+ * o3r_frames_cloud call returns.  A following o3r_frames_cloud with different frames simply ignores the prefetch. */
+int o3r_frames_prefetch(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_type);
+
 /* Same as o3r_frames_cloud but every pointer inside `frames` is DEVICE memory on ctx's device and
  * nothing is copied (the inputs-resident-in-HBM measurement).  T is still read from host. */
 int o3r_frames_cloud_dev(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_type,

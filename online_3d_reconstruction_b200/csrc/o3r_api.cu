@@ -9,6 +9,7 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <chrono>
 
 #include "blur.cuh"
 #include "common.cuh"
@@ -21,6 +22,13 @@ using namespace o3r;
 namespace {
 
 std::string g_create_err;
+
+inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+struct Tr {
+    bool on; double t; const char* where;
+    explicit Tr(const char* w) : on(getenv("O3R_TRACE") != nullptr), t(now_ms()), where(w) {}
+    void mark(const char* what) { if (!on) return; const double n = now_ms(); fprintf(stderr, "[o3r trace] %s/%s %.3f ms\n", where, what, n - t); t = n; }
+};
 
 struct DevBuf {
     void* p = nullptr;
@@ -46,7 +54,8 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-enum { CNT_PTS = 0, CNT_VOX = 1, CNT_CYC = 2, CNT_NEW = 3, CNT_EMIT = 4, CNT_NEWSCAN = 5, CNT_BASE = 6, CNT_CELLBB = 16, CNT_N = 32 };
+enum { CNT_PTS = 0, CNT_VOX = 1, CNT_CYC = 2, CNT_NEW = 3, CNT_EMIT = 4, CNT_NEWSCAN = 5, CNT_BASE = 6, CNT_NRES = 7, CNT_ZERO = 8,
+       CNT_CELLBB = 16, CNT_N = 32 };
 
 }  // namespace
 
@@ -76,7 +85,26 @@ struct o3r_ctx {
     int defer_merge = 0;
     DevBuf lut_r, lut_z;
     // input staging (host-pointer entry points)
-    DevBuf d_disp, d_bgr, d_labels, d_coef, d_kp;
+    // double-buffered: a prefetch of the next cycle's inputs fills one set while the kernels read the other
+    struct Staging { DevBuf disp, bgr, labels, coef, kp; } stg[2];
+    struct Prefetch {                   // one record per staging set
+        bool valid = false;
+        int n = 0, disp_type = 0;
+        uint64_t seq = 0;               // issue order (the older record is recycled when both are pending)
+        std::vector<const void*> sig;   // host pointers of the prefetched frames
+        cudaEvent_t ev = nullptr;
+    } prefetch[2];
+    uint64_t prefetch_seq = 0;
+    // a staging set that holds no pending prefetch (inputs of finished calls are free: every frame-path call returns
+    // only after its last input-reading kernel has completed)
+    int free_stage_set() {
+        if (!prefetch[0].valid) return 0;
+        if (!prefetch[1].valid) return 1;
+        const int s = prefetch[0].seq < prefetch[1].seq ? 0 : 1;
+        prefetch[s].valid = false;
+        return s;
+    }
+    DevBuf d_disp;   // scratch plane of o3r_blur_u8
     DevBuf d_frames, d_blur, d_blurjobs;
     // per-batch work buffers
     DevBuf tile_cnt, tile_off, bbox, frame_off, grids, counters, pts, sortbuf, hist, plan_all, plan_v2, ghist;
@@ -94,7 +122,13 @@ struct o3r_ctx {
     // resident cloud: accumulators (ACCUMULATE) ...
     DevBuf res_keys[2], res_acc[2], res_rgb[2];
     int res_cur = 0;
-    uint32_t n_res = 0;
+    // The exact resident cell count lives on the device (counters[CNT_NRES]); the host keeps an upper bound that is
+    // enough to size buffers and launches, and tightens it from an asynchronous read-back of the previous merge.
+    size_t n_res_ub = 0;
+    bool n_res_exact = true;
+    uint32_t* h_nres = nullptr;       // pinned
+    cudaEvent_t ev_nres = nullptr;
+    size_t n_cyc_ub = 0;
     DevBuf ckey, cacc, crgb, new_cnt, new_off, new_keys, okeys;
     uint32_t n_cyc = 0;
     // ... or points (RETAIN / dont_downsample)
@@ -148,6 +182,43 @@ struct o3r_ctx {
 namespace {
 
 inline uint32_t cdiv(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
+
+// Small host->device payloads (frame descriptors, segment bounds, plans) travel as KERNEL PARAMETERS, not through the
+// copy engine: a pageable cudaMemcpyAsync on the compute stream would queue behind a 184 MB input prefetch that
+// occupies the H2D engine, and the whole cycle would wait for it.
+struct SmallBlob { uint32_t w[960]; };   // 3840 bytes (kernel parameters are limited to 4 KB)
+__global__ void k_put_blob(uint32_t* __restrict__ dst, SmallBlob b, int n_words) {
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = b.w[i];
+}
+int upload_small(o3r_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    const size_t cap = sizeof(SmallBlob);
+    for (size_t at = 0; at < bytes; at += cap) {
+        const size_t nb = std::min(cap, bytes - at);
+        SmallBlob b;
+        memcpy(b.w, (const char*)src + at, nb);
+        if (nb % 4) memset((char*)b.w + nb, 0, 4 - nb % 4);
+        LAUNCH(k_put_blob, 1, 256, 0, reinterpret_cast<uint32_t*>((char*)dst + at), b, (int)((nb + 3) / 4));
+    }
+    return O3R_OK;
+}
+// Zero fills run as kernels on the compute stream for the same reason: cudaMemsetAsync may be served by a copy engine
+// and then queues behind an input prefetch.  `bytes` and `dst` are multiples of 4 (all callers clear u32 tables).
+__global__ void __launch_bounds__(kThreads) k_zero(uint32_t* __restrict__ dst, size_t n_words) {
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    const size_t n4 = ((uintptr_t)dst % 16 == 0) ? n_words / 4 : 0;
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (size_t j = i; j < n4; j += stride) d4[j] = make_uint4(0u, 0u, 0u, 0u);
+    for (size_t j = n4 * 4 + i; j < n_words; j += stride) dst[j] = 0u;
+}
+int zero_fill(o3r_ctx* ctx, void* dst, size_t bytes) {
+    if (bytes == 0) return O3R_OK;
+    const size_t words = (bytes + 3) / 4;
+    const uint32_t g = (uint32_t)std::min<size_t>((words / 4 + kThreads - 1) / kThreads + 1, 148 * 8);
+    LAUNCH(k_zero, g, kThreads, 0, reinterpret_cast<uint32_t*>(dst), words);
+    return O3R_OK;
+}
+#define ZERO(ptr, bytes) do { int rcz_ = zero_fill(ctx, (ptr), (bytes)); if (rcz_) return rcz_; } while (0)
 inline size_t disp_elem(int t) { return t == O3R_DISP_U8 ? 1 : t == O3R_DISP_U16 ? 2 : t == O3R_DISP_F32 ? 4 : 8; }
 
 int read_counters(o3r_ctx* ctx) {
@@ -166,7 +237,7 @@ int sort_pairs(o3r_ctx* ctx, KeyT* k0, KeyT* k1, uint32_t* v0, uint32_t* v1, con
     const size_t st_words = (size_t)n_seg * tiles_ub * kRsBins;
     // status words for every pass + one ticket per pass, cleared with one memset
     CU(ctx->hist.ensure((st_words * passes + 64) * 4));
-    CU(cudaMemsetAsync(ctx->hist.p, 0, (st_words * passes + 64) * 4, ctx->st));
+    ZERO(ctx->hist.p, (st_words * passes + 64) * 4);
     uint32_t* status = ctx->hist.as<uint32_t>();
     uint32_t* tickets = status + st_words * passes;
     const uint32_t grid = tiles_ub * (uint32_t)n_seg;
@@ -196,7 +267,7 @@ int vg_sorted_reduce(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const u
     const size_t gh_bytes = (size_t)n_seg * kMaxPasses * kRsBins * 4;
     CU(ctx->ghist.ensure(gh_bytes));
     CU(ctx->plan_all.ensure((size_t)n_seg * sizeof(SortPlan)));
-    CU(cudaMemsetAsync(ctx->ghist.p, 0, gh_bytes, ctx->st));
+    ZERO(ctx->ghist.p, gh_bytes);
     SortPlan* plan = ctx->plan_all.as<SortPlan>();
     // digit layout from each segment's live index bits (<= 31 -> at most 4 passes)
     LAUNCH(k_rs_layout, cdiv(n_seg, 64), 64, 0, n_seg, grids, 31, plan);
@@ -235,7 +306,7 @@ int vg_sorted_reduce(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const u
     } else if (fast) {
         const size_t wbytes = 64 + (nt + 1) * sizeof(RunCarry);
         CU(ctx->runwork.ensure(wbytes));
-        CU(cudaMemsetAsync(ctx->runwork.p, 0, wbytes, ctx->st));
+        ZERO(ctx->runwork.p, wbytes);
         LAUNCH(k_vg_reduce_w, (uint32_t)nt, kThreads, 0, A, ctx->head_off.as<uint32_t>(), cnt + CNT_VOX, out, out_off,
                n_seg, ctx->runwork.as<uint32_t>(), reinterpret_cast<RunCarry*>(ctx->runwork.as<char>() + 64),
                track_cells ? 1 : 0, ctx->inv_c, ctx->inv_cz, reinterpret_cast<int*>(cnt + CNT_CELLBB), out_base, spts);
@@ -253,7 +324,9 @@ int acc_build_cycle_t(o3r_ctx* ctx, Items items, size_t n, bool use_resident, co
     const int passes = std::max(1, (total_bits + kRsMaxBits - 1) / kRsMaxBits);
     uint32_t* cnt = ctx->counters.as<uint32_t>();
     const size_t n4 = (n + 63) & ~(size_t)63;
+    Tr tr("acc_build");
     CU(ctx->sortbuf.ensure(n4 * (2 * sizeof(KeyT) + 8)));
+    tr.mark("sortbuf.ensure");
     KeyT* k0 = ctx->sortbuf.as<KeyT>();
     KeyT* k1 = k0 + n4;
     uint32_t* v0 = reinterpret_cast<uint32_t*>(k1 + n4);
@@ -262,9 +335,9 @@ int acc_build_cycle_t(o3r_ctx* ctx, Items items, size_t n, bool use_resident, co
     CU(ctx->ghist.ensure(kMaxPasses * kRsBins * 4));
     CU(ctx->plan_v2.ensure(sizeof(SortPlan)));
     const uint32_t seg_h[2] = {0u, (uint32_t)n};
-    CU(cudaMemcpyAsync(ctx->seg2.p, seg_h, 8, cudaMemcpyHostToDevice, ctx->st));
-    CU(cudaMemsetAsync(ctx->ghist.p, 0, kMaxPasses * kRsBins * 4, ctx->st));
-    CU(cudaMemsetAsync(cnt + CNT_NEW, 0, 4, ctx->st));
+    { int rcu = upload_small(ctx, ctx->seg2.p, seg_h, 8); if (rcu) return rcu; }
+    ZERO(ctx->ghist.p, kMaxPasses * kRsBins * 4);
+    ZERO(cnt + CNT_NEW, 4);
     const uint32_t* seg = ctx->seg2.as<uint32_t>();
     const uint32_t gk = std::min<uint32_t>(cdiv(n, kThreads), 148 * 8);
     SortPlan* plan = ctx->plan_v2.as<SortPlan>();
@@ -272,6 +345,7 @@ int acc_build_cycle_t(o3r_ctx* ctx, Items items, size_t n, bool use_resident, co
     LAUNCH_N("k_acc_key", (k_acc_key<KeyT, Items>), gk, kThreads, 0, items, (uint32_t)n, ctx->inv_c, ctx->inv_cz, kc, plan,
              k0, v0, ctx->ghist.as<uint32_t>());
     LAUNCH(k_rs_plan, 1, kThreads, 0, ctx->ghist.as<uint32_t>(), seg, plan, (const GridParams*)nullptr);
+    tr.mark("key+plan");
     float4* spts = nullptr;
     const float4* gsrc = nullptr;
     if constexpr (Items::kGather) if (ctx->gather_in_sort) {   // the last radix pass delivers the points in sorted order
@@ -282,6 +356,7 @@ int acc_build_cycle_t(o3r_ctx* ctx, Items items, size_t n, bool use_resident, co
     }
     int rc = sort_pairs<KeyT>(ctx, k0, k1, v0, v1, seg, 1, n, plan, passes, 0, ctx->ghist.as<uint32_t>(), gsrc, spts);
     if (rc) return rc;
+    tr.mark("sort_pairs");
     AccArgs<KeyT> A;
     A.keys0 = k0; A.keys1 = k1; A.vals0 = v0; A.vals1 = v1;
     A.seg_off = seg; A.plan = plan;
@@ -291,15 +366,18 @@ int acc_build_cycle_t(o3r_ctx* ctx, Items items, size_t n, bool use_resident, co
     A.res_keys = ctx->res_keys[cur].as<uint64_t>();
     A.res_acc = ctx->res_acc[cur].as<float4>();
     A.res_rgb = ctx->res_rgb[cur].as<uint4>();
-    A.n_res = use_resident ? ctx->n_res : 0u;
+    A.n_res_ptr = cnt + (use_resident ? CNT_NRES : CNT_ZERO);
     CU(ctx->head_cnt.ensure((size_t)A.tiles_ub * 4));
     CU(ctx->head_off.ensure((size_t)A.tiles_ub * 4));
-    CU(ctx->ckey.ensure(n * 8));
-    CU(ctx->cacc.ensure(n * 16));
-    CU(ctx->crgb.ensure(n * 16));
+    // one record per cell of the cycle (<= n_cyc_ub <= n), reserved in big steps so steady-state cycles never reallocate
+    const size_t cyc_cap = std::max<size_t>(std::min<size_t>(n, ctx->n_cyc_ub ? ctx->n_cyc_ub : n), (size_t)1 << 20);
+    CU(ctx->ckey.ensure(cyc_cap * 8));
+    CU(ctx->cacc.ensure(cyc_cap * 16));
+    CU(ctx->crgb.ensure(cyc_cap * 16));
     const size_t wbytes = 64 + ((size_t)A.tiles_ub + 1) * sizeof(RunCarry);
     CU(ctx->runwork.ensure(wbytes));
-    CU(cudaMemsetAsync(ctx->runwork.p, 0, wbytes, ctx->st));
+    ZERO(ctx->runwork.p, wbytes);
+    tr.mark("ensures");
     LAUNCH_N("k_acc_heads", (k_acc_heads<KeyT>), A.tiles_ub, kThreads, 0, A, v0, v1, ctx->head_cnt.as<uint32_t>(),
              cnt + CNT_NEW);
     LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->head_cnt.as<uint32_t>(), ctx->head_off.as<uint32_t>(), A.tiles_ub,
@@ -307,9 +385,17 @@ int acc_build_cycle_t(o3r_ctx* ctx, Items items, size_t n, bool use_resident, co
     LAUNCH_N("k_acc_reduce", (k_acc_reduce<KeyT, Items>), A.tiles_ub, kThreads, 0, A, items, ctx->head_off.as<uint32_t>(),
              ctx->ckey.as<uint64_t>(), ctx->cacc.as<float4>(), ctx->crgb.as<uint4>(), ctx->runwork.as<uint32_t>(),
              reinterpret_cast<RunCarry*>(ctx->runwork.as<char>() + 64));
-    rc = read_counters(ctx);
-    if (rc) return rc;
-    ctx->n_cyc = ctx->h_counters[CNT_CYC];
+    tr.mark("heads+reduce");
+    return O3R_OK;
+}
+
+// Tightens the host's upper bound of the resident cell count from the read-back of the last merge.
+int refresh_nres(o3r_ctx* ctx, bool block) {
+    if (ctx->n_res_exact) return O3R_OK;
+    if (block) CU(cudaEventSynchronize(ctx->ev_nres));
+    else if (cudaEventQuery(ctx->ev_nres) != cudaSuccess) { cudaGetLastError(); return O3R_OK; }
+    ctx->n_res_ub = *ctx->h_nres;
+    ctx->n_res_exact = true;
     return O3R_OK;
 }
 
@@ -320,8 +406,10 @@ template <typename Items>
 int acc_build_cycle(o3r_ctx* ctx, const Items& items, size_t n, bool use_resident, const int* bb) {
     uint32_t* cnt = ctx->counters.as<uint32_t>();
     ctx->n_cyc = 0;
+    ctx->n_cyc_ub = 0;
     ctx->h_counters[CNT_CYC] = ctx->h_counters[CNT_NEW] = 0;
     if (n == 0) return O3R_OK;
+    { int rc = refresh_nres(ctx, false); if (rc) return rc; }
     if (n >= (1ull << 32)) return ctx->fail(O3R_ERR_INVALID, "batch too large for 32-bit indices");
     int hb[6];
     if (!bb) {
@@ -342,42 +430,59 @@ int acc_build_cycle(o3r_ctx* ctx, const Items& items, size_t n, bool use_residen
     kc.wi = bits_for((long long)bb[3] - bb[0]);
     kc.wj = bits_for((long long)bb[4] - bb[1]);
     const int total = kc.wi + kc.wj + bits_for((long long)bb[5] - bb[2]);
+    // the cycle cannot touch more cells than its cell range holds (nor more than it has items)
+    const double range_cells = ((double)bb[3] - bb[0] + 1) * ((double)bb[4] - bb[1] + 1) * ((double)bb[5] - bb[2] + 1);
+    ctx->n_cyc_ub = (size_t)std::min((double)n, range_cells);
     if (total <= 32) return acc_build_cycle_t<uint32_t, Items>(ctx, items, n, use_resident, kc, total);
     return acc_build_cycle_t<uint64_t, Items>(ctx, items, n, use_resident, kc, total);
 }
 
 // Applies the cycle's cell list to the resident shard: in-place update of found cells, sorted insert of new ones.
+// Entirely device-driven: the cycle's cell count, the number of new cells and the resident count are read from device
+// memory, launches and buffers are sized by host-known upper bounds, and nothing here waits for the GPU.
 int acc_apply_cycle(o3r_ctx* ctx) {
-    const uint32_t n_cyc = ctx->n_cyc, n_new = ctx->h_counters[CNT_NEW];
-    if (n_cyc == 0) return O3R_OK;
+    const size_t n_cyc_ub = ctx->n_cyc_ub;
+    if (n_cyc_ub == 0) return O3R_OK;
     uint32_t* cnt = ctx->counters.as<uint32_t>();
     const int cur = ctx->res_cur, nxt = cur ^ 1;
-    const uint32_t tiles = cdiv(n_cyc, kTileV);
+    const uint32_t tiles = cdiv(n_cyc_ub, kTileV);
+    const size_t tot_ub = ctx->n_res_ub + n_cyc_ub;
+    Tr tr("acc_apply");
+    if (tot_ub >= (1ull << 32)) return ctx->fail(O3R_ERR_NOMEM, "resident shard could exceed 2^32 cells");
     CU(ctx->new_cnt.ensure((size_t)tiles * 4));
     CU(ctx->new_off.ensure((size_t)tiles * 4));
-    LAUNCH(k_acc_update, tiles, kThreads, 0, n_cyc, ctx->cacc.as<float4>(), ctx->crgb.as<uint4>(),
+    // the shard grows a little every cycle: reserve in big steps (>= 4 M cells, doubling), a reallocation is a
+    // cudaMalloc + cudaFree = a device-wide sync of several ms in the middle of the cycle
+    if (ctx->res_keys[nxt].cap < tot_ub * 8 || ctx->res_acc[nxt].cap < tot_ub * 16 || ctx->res_rgb[nxt].cap < tot_ub * 16) {
+        const size_t cells = std::max<size_t>(2 * tot_ub, (size_t)1 << 22);
+        CU(ctx->res_keys[nxt].ensure(cells * 8));
+        CU(ctx->res_acc[nxt].ensure(cells * 16));
+        CU(ctx->res_rgb[nxt].ensure(cells * 16));
+    }
+    CU(ctx->new_keys.ensure(n_cyc_ub * 8));
+    if (tr.on) fprintf(stderr, "[o3r trace] n_res_ub %zu n_cyc_ub %zu\n", ctx->n_res_ub, n_cyc_ub);
+    tr.mark("ensures");
+    LAUNCH(k_acc_update, tiles, kThreads, 0, cnt + CNT_CYC, ctx->cacc.as<float4>(), ctx->crgb.as<uint4>(),
            ctx->res_acc[cur].as<float4>(), ctx->res_rgb[cur].as<uint4>(), ctx->new_cnt.as<uint32_t>());
-    if (n_new == 0) return O3R_OK;
-    const size_t tot = (size_t)ctx->n_res + n_new;
-    if (tot >= (1ull << 32)) return ctx->fail(O3R_ERR_NOMEM, "resident shard exceeds 2^32 cells");
-    CU(ctx->res_keys[nxt].ensure(tot * 8));
-    CU(ctx->res_acc[nxt].ensure(tot * 16));
-    CU(ctx->res_rgb[nxt].ensure(tot * 16));
-    CU(ctx->new_keys.ensure((size_t)n_new * 8));
     LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->new_cnt.as<uint32_t>(), ctx->new_off.as<uint32_t>(), tiles,
            cnt + CNT_NEWSCAN);
-    LAUNCH(k_acc_place_new, tiles, kThreads, 0, n_cyc, ctx->ckey.as<uint64_t>(), ctx->cacc.as<float4>(),
-           ctx->crgb.as<uint4>(), ctx->new_off.as<uint32_t>(), ctx->res_keys[cur].as<uint64_t>(), ctx->n_res,
+    LAUNCH(k_acc_place_new, tiles, kThreads, 0, cnt + CNT_CYC, ctx->ckey.as<uint64_t>(), ctx->cacc.as<float4>(),
+           ctx->crgb.as<uint4>(), ctx->new_off.as<uint32_t>(), ctx->res_keys[cur].as<uint64_t>(), cnt + CNT_NRES,
            ctx->res_keys[nxt].as<uint64_t>(), ctx->res_acc[nxt].as<float4>(), ctx->res_rgb[nxt].as<uint4>(),
            ctx->new_keys.as<uint64_t>());
-    if (ctx->n_res) {
-        const uint32_t g = std::min<uint32_t>(cdiv(ctx->n_res, kThreads), 148 * 16);
-        LAUNCH(k_acc_place_old, g, kThreads, 0, ctx->n_res, ctx->res_keys[cur].as<uint64_t>(),
-               ctx->res_acc[cur].as<float4>(), ctx->res_rgb[cur].as<uint4>(), ctx->new_keys.as<uint64_t>(), n_new,
+    if (ctx->n_res_ub) {
+        const uint32_t g = std::min<uint32_t>(cdiv(ctx->n_res_ub, kThreads), 148 * 16);
+        LAUNCH(k_acc_place_old, g, kThreads, 0, cnt + CNT_NRES, ctx->res_keys[cur].as<uint64_t>(),
+               ctx->res_acc[cur].as<float4>(), ctx->res_rgb[cur].as<uint4>(), ctx->new_keys.as<uint64_t>(), cnt + CNT_NEW,
                ctx->res_keys[nxt].as<uint64_t>(), ctx->res_acc[nxt].as<float4>(), ctx->res_rgb[nxt].as<uint4>());
     }
+    LAUNCH(k_acc_finish, 1, 32, 0, cnt + CNT_NRES, cnt + CNT_NEW);
     ctx->res_cur = nxt;
-    ctx->n_res = (uint32_t)tot;
+    ctx->n_res_ub = tot_ub;
+    ctx->n_res_exact = false;
+    CU(cudaMemcpyAsync(ctx->h_nres, cnt + CNT_NRES, 4, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaEventRecord(ctx->ev_nres, ctx->st));
+    tr.mark("launches");
     return O3R_OK;
 }
 
@@ -424,11 +529,89 @@ int launch_stage_a(o3r_ctx* ctx, const AParams& P, const FrameDev* fr, int n, co
     return O3R_OK;
 }
 
+// ---- input staging (host entry points) --------------------------------------------------------------------------------
+struct StageGeom { size_t es, dstep, dplane, cstep, cplane, lstep, lplane; };
+
+StageGeom stage_geom(const o3r_params& p, int disp_type) {
+    StageGeom G;
+    G.es = disp_elem(disp_type);
+    G.dstep = (((size_t)p.cols * G.es) + 15) & ~(size_t)15; G.dplane = G.dstep * p.rows;
+    G.cstep = (((size_t)p.cols * 3) + 15) & ~(size_t)15;     G.cplane = G.cstep * p.rows;
+    G.lstep = ((size_t)p.cols + 15) & ~(size_t)15;           G.lplane = G.lstep * p.rows;
+    return G;
+}
+
+void frames_signature(const o3r_frame* frames, int n, std::vector<const void*>& sig) {
+    sig.clear();
+    sig.reserve((size_t)n * 4);
+    for (int i = 0; i < n; ++i) {
+        sig.push_back(frames[i].disp); sig.push_back(frames[i].bgr);
+        sig.push_back(frames[i].labels); sig.push_back(frames[i].kp_xy);
+    }
+}
+
+// sizes staging set `set` for the frames and fills their device-side descriptors (everything but T)
+int stage_layout(o3r_ctx* ctx, const o3r_frame* frames, int n, bool label_mode, int J, const StageGeom& G, int set,
+                 std::vector<FrameDev>& fd) {
+    o3r_ctx::Staging& S = ctx->stg[set];
+    size_t kp_total = 0, coef_total = 0;
+    for (int i = 0; i < n; ++i) {
+        const o3r_frame& f = frames[i];
+        kp_total += (J != 1 && f.kp_xy && f.n_kp > 0) ? (size_t)f.n_kp * 2 : 0;
+        coef_total += label_mode ? (size_t)std::max(f.n_planes, 0) * 3 : 0;
+    }
+    if (!label_mode) CU(S.disp.ensure(G.dplane * n));
+    CU(S.bgr.ensure(G.cplane * n));
+    if (label_mode) { CU(S.labels.ensure(G.lplane * n)); CU(S.coef.ensure(std::max<size_t>(coef_total, 1) * 8)); }
+    if (kp_total) CU(S.kp.ensure(kp_total * 4));
+    size_t kp_at = 0, coef_at = 0;
+    for (int i = 0; i < n; ++i) {
+        const o3r_frame& f = frames[i];
+        FrameDev& d = fd[i];
+        const int nk = (J != 1 && f.kp_xy && f.n_kp > 0) ? f.n_kp : 0;
+        d.disp = label_mode ? nullptr : S.disp.as<uint8_t>() + G.dplane * i; d.disp_step = G.dstep;
+        d.bgr = S.bgr.as<uint8_t>() + G.cplane * i; d.bgr_step = G.cstep;
+        d.labels = label_mode ? S.labels.as<uint8_t>() + G.lplane * i : nullptr; d.labels_step = G.lstep;
+        d.plane_coef = label_mode ? S.coef.as<double>() + coef_at : nullptr;
+        d.kp_xy = nk ? S.kp.as<float>() + kp_at : nullptr;
+        d.n_planes = label_mode ? std::max(f.n_planes, 0) : 0;
+        d.n_kp = nk;
+        kp_at += (size_t)nk * 2; coef_at += (size_t)d.n_planes * 3;
+    }
+    return O3R_OK;
+}
+
+// issues the H2D copies of frames [f0, f0 + nc) on the copy stream
+int stage_copy(o3r_ctx* ctx, const o3r_frame* frames, const std::vector<FrameDev>& fd, int f0, int nc, bool label_mode,
+               const StageGeom& G) {
+    const o3r_params& p = ctx->p;
+    for (int i = f0; i < f0 + nc; ++i) {
+        const o3r_frame& f = frames[i];
+        const FrameDev& d = fd[i];
+        if (!label_mode) {
+            CU(cudaMemcpy2DAsync((void*)d.disp, G.dstep, f.disp, f.disp_step, (size_t)p.cols * G.es, p.rows,
+                                 cudaMemcpyHostToDevice, ctx->st_copy));
+        } else {
+            CU(cudaMemcpy2DAsync((void*)d.labels, G.lstep, f.labels, f.labels_step, (size_t)p.cols, p.rows,
+                                 cudaMemcpyHostToDevice, ctx->st_copy));
+            if (d.n_planes)
+                CU(cudaMemcpyAsync((void*)d.plane_coef, f.plane_coef, (size_t)d.n_planes * 24, cudaMemcpyHostToDevice, ctx->st_copy));
+        }
+        CU(cudaMemcpy2DAsync((void*)d.bgr, G.cstep, f.bgr, f.bgr_step, (size_t)p.cols * 3, p.rows, cudaMemcpyHostToDevice,
+                             ctx->st_copy));
+        if (d.n_kp) CU(cudaMemcpyAsync((void*)d.kp_xy, f.kp_xy, (size_t)d.n_kp * 8, cudaMemcpyHostToDevice, ctx->st_copy));
+    }
+    return O3R_OK;
+}
+
 // The batched per-frame path.  `frames` hold host pointers (host_inputs: every frame is copied to device staging
 // on the copy stream, chunk by chunk, overlapping the previous chunk's kernels) or device pointers.
 int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_type, uint32_t* frame_counts,
                       const BatchOpts& opt, bool host_inputs) {
     const o3r_params& p = ctx->p;
+    static const bool trace = getenv("O3R_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tr0 = now();
     if (n <= 0) { ctx->last_n = 0; ctx->last_total = 0; return O3R_OK; }
     if (n > 65535) return ctx->fail(O3R_ERR_INVALID, "too many frames in one batch");
     if (disp_type < 0 || disp_type > 3) return ctx->fail(O3R_ERR_INVALID, "bad disp_type");
@@ -481,63 +664,75 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
 
     // ---- device copies of the inputs (host entry points) and frame descriptors
     const size_t es = disp_elem(disp_type);
-    const size_t dstep = (((size_t)p.cols * es) + 15) & ~(size_t)15, dplane = dstep * p.rows;
-    const size_t cstep = (((size_t)p.cols * 3) + 15) & ~(size_t)15, cplane = cstep * p.rows;
-    const size_t lstep = ((size_t)p.cols + 15) & ~(size_t)15, lplane = lstep * p.rows;
-    const size_t blur_step = lstep;
+    const StageGeom G = stage_geom(p, disp_type);
+    const size_t blur_step = G.lstep;
+    // inputs already on their way (o3r_frames_prefetch of exactly these frames)?
+    bool prefetched = false;
+    int set = 0;
     if (host_inputs) {
-        if (!label_mode) CU(ctx->d_disp.ensure(dplane * n));
-        CU(ctx->d_bgr.ensure(cplane * n));
-        if (label_mode) { CU(ctx->d_labels.ensure(lplane * n)); CU(ctx->d_coef.ensure(std::max<size_t>(coef_total, 1) * 8)); }
-        if (kp_total) CU(ctx->d_kp.ensure(kp_total * 4));
+        std::vector<const void*> sig;
+        frames_signature(frames, n, sig);
+        // the OLDEST matching prefetch: a caller that recycles its host buffers issues the next cycle's prefetch
+        // (same pointers) before this call, and that copy is still in flight
+        for (int s = 0; s < 2; ++s) {
+            const o3r_ctx::Prefetch& pf = ctx->prefetch[s];
+            if (pf.valid && pf.n == n && pf.disp_type == disp_type && pf.sig == sig &&
+                (!prefetched || pf.seq < ctx->prefetch[set].seq)) {
+                prefetched = true; set = s;
+            }
+        }
+        if (prefetched) ctx->prefetch[set].valid = false;
+        if (!prefetched) set = ctx->free_stage_set();
     }
     if (blur) CU(ctx->d_blur.ensure((size_t)n * p.rows * blur_step));
     std::vector<FrameDev> fd(n);
     std::vector<BlurJob> jobs(blur ? n : 0);
     bool vec = (J == 1) && (ctx->nx % 4 == 0) && (P.x0 % 4 == 0) && !label_mode;
-    {
-        size_t kp_at = 0, coef_at = 0;
-        for (int i = 0; i < n; ++i) {
-            const o3r_frame& f = frames[i];
-            FrameDev& d = fd[i];
+    std::vector<FrameDev> fd_stage;   // where the H2D copies land (fd[i].disp is redirected to the blurred plane below)
+    if (host_inputs) {
+        int rc = stage_layout(ctx, frames, n, label_mode, J, G, set, fd);
+        if (rc) return rc;
+        if (!prefetched) fd_stage = fd;
+    }
+    for (int i = 0; i < n; ++i) {
+        const o3r_frame& f = frames[i];
+        FrameDev& d = fd[i];
+        if (!host_inputs) {
             const int nk = (J != 1 && f.kp_xy && f.n_kp > 0) ? f.n_kp : 0;
-            if (host_inputs) {
-                d.disp = label_mode ? nullptr : ctx->d_disp.as<uint8_t>() + dplane * i; d.disp_step = dstep;
-                d.bgr = ctx->d_bgr.as<uint8_t>() + cplane * i; d.bgr_step = cstep;
-                d.labels = label_mode ? ctx->d_labels.as<uint8_t>() + lplane * i : nullptr; d.labels_step = lstep;
-                d.plane_coef = label_mode ? ctx->d_coef.as<double>() + coef_at : nullptr;
-                d.kp_xy = nk ? ctx->d_kp.as<float>() + kp_at : nullptr;
-            } else {
-                d.disp = (const uint8_t*)f.disp; d.disp_step = f.disp_step;
-                d.bgr = f.bgr; d.bgr_step = f.bgr_step;
-                d.labels = label_mode ? f.labels : nullptr; d.labels_step = f.labels_step;
-                d.plane_coef = label_mode ? f.plane_coef : nullptr;
-                d.kp_xy = nk ? f.kp_xy : nullptr;
-            }
+            d.disp = (const uint8_t*)f.disp; d.disp_step = f.disp_step;
+            d.bgr = f.bgr; d.bgr_step = f.bgr_step;
+            d.labels = label_mode ? f.labels : nullptr; d.labels_step = f.labels_step;
+            d.plane_coef = label_mode ? f.plane_coef : nullptr;
+            d.kp_xy = nk ? f.kp_xy : nullptr;
             d.n_planes = label_mode ? std::max(f.n_planes, 0) : 0;
             d.n_kp = nk;
-            kp_at += (size_t)nk * 2; coef_at += (size_t)d.n_planes * 3;
-            for (int k = 0; k < 12; ++k) d.T[k] = f.T[k];
-            if (blur) {
-                jobs[i].src = d.disp; jobs[i].sstep = d.disp_step;
-                jobs[i].dst = ctx->d_blur.as<uint8_t>() + (size_t)i * p.rows * blur_step; jobs[i].dstep = blur_step;
-                d.disp = jobs[i].dst; d.disp_step = blur_step;
-            }
-            if (!label_mode) vec = vec && ((uintptr_t)d.disp % 16 == 0) && (d.disp_step % (4 * es) == 0);
-            vec = vec && ((uintptr_t)d.bgr % 4 == 0) && (d.bgr_step % 4 == 0);
         }
+        for (int k = 0; k < 12; ++k) d.T[k] = f.T[k];
+        if (blur) {
+            jobs[i].src = d.disp; jobs[i].sstep = d.disp_step;
+            jobs[i].dst = ctx->d_blur.as<uint8_t>() + (size_t)i * p.rows * blur_step; jobs[i].dstep = blur_step;
+            d.disp = jobs[i].dst; d.disp_step = blur_step;
+        }
+        if (!label_mode) vec = vec && ((uintptr_t)d.disp % 16 == 0) && (d.disp_step % (4 * es) == 0);
+        vec = vec && ((uintptr_t)d.bgr % 4 == 0) && (d.bgr_step % 4 == 0);
     }
     P.vec = vec;
     CU(ctx->d_frames.ensure((size_t)n * sizeof(FrameDev)));
-    CU(cudaMemcpyAsync(ctx->d_frames.p, fd.data(), (size_t)n * sizeof(FrameDev), cudaMemcpyHostToDevice, ctx->st));
+    { int rcu = upload_small(ctx, ctx->d_frames.p, fd.data(), (size_t)n * sizeof(FrameDev)); if (rcu) return rcu; }
     if (blur) {
         CU(ctx->d_blurjobs.ensure((size_t)n * sizeof(BlurJob)));
-        CU(cudaMemcpyAsync(ctx->d_blurjobs.p, jobs.data(), (size_t)n * sizeof(BlurJob), cudaMemcpyHostToDevice, ctx->st));
+        { int rcu = upload_small(ctx, ctx->d_blurjobs.p, jobs.data(), (size_t)n * sizeof(BlurJob)); if (rcu) return rcu; }
     }
 
     // ---- buffers: batch-wide outputs, chunk-sized scratch
     // host inputs: chunks let the copies overlap the kernels; device inputs: one launch sequence for the whole batch
-    const int chunk = std::max(1, std::min(n, host_inputs ? ctx->chunk_frames : ctx->chunk_frames_dev));
+    const int chunk = std::max(1, std::min(n, (host_inputs && !prefetched) ? ctx->chunk_frames : ctx->chunk_frames_dev));
+    if (prefetched && trace) {
+        const bool done = cudaEventQuery(ctx->prefetch[set].ev) == cudaSuccess;
+        cudaGetLastError();
+        fprintf(stderr, "[o3r trace] prefetched inputs %s at entry\n", done ? "ready" : "still in flight");
+    }
+    if (prefetched) CU(cudaStreamWaitEvent(ctx->st, ctx->prefetch[set].ev, 0));
     const size_t per_frame_cap = (size_t)P.npix + (size_t)max_kp;
     const size_t cap_batch = per_frame_cap * n, cap_chunk = per_frame_cap * chunk;
     if (cap_batch >= (1ull << 32)) return ctx->fail(O3R_ERR_INVALID, "batch exceeds 2^32 samples; use fewer frames");
@@ -560,28 +755,17 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
         } else {
             CU(ctx->pts.ensure(cap_batch * 16));
         }
-        CU(cudaMemsetAsync(cnt + CNT_BASE, 0, 4, ctx->st));
-        CU(cudaMemsetAsync(ctx->vox_off.p, 0, 4, ctx->st));
+        ZERO(cnt + CNT_BASE, 4);
+        ZERO(ctx->vox_off.p, 4);
     }
     ctx->last_is_vox = P.want_keys;
     uint32_t* goff = ctx->vox_off.as<uint32_t>();
 
     for (int f0 = 0; f0 < n; f0 += chunk) {
         const int nc = std::min(chunk, n - f0);
-        if (host_inputs) {  // H2D of this chunk on the copy stream; the compute stream waits for its event only
-            for (int i = f0; i < f0 + nc; ++i) {
-                const o3r_frame& f = frames[i];
-                const FrameDev& d = fd[i];
-                if (!label_mode) {
-                    uint8_t* dst = ctx->d_disp.as<uint8_t>() + dplane * i;
-                    CU(cudaMemcpy2DAsync(dst, dstep, f.disp, f.disp_step, (size_t)p.cols * es, p.rows, cudaMemcpyHostToDevice, ctx->st_copy));
-                } else {
-                    CU(cudaMemcpy2DAsync((void*)d.labels, lstep, f.labels, f.labels_step, (size_t)p.cols, p.rows, cudaMemcpyHostToDevice, ctx->st_copy));
-                    if (d.n_planes) CU(cudaMemcpyAsync((void*)d.plane_coef, f.plane_coef, (size_t)d.n_planes * 24, cudaMemcpyHostToDevice, ctx->st_copy));
-                }
-                CU(cudaMemcpy2DAsync((void*)d.bgr, cstep, f.bgr, f.bgr_step, (size_t)p.cols * 3, p.rows, cudaMemcpyHostToDevice, ctx->st_copy));
-                if (d.n_kp) CU(cudaMemcpyAsync((void*)d.kp_xy, f.kp_xy, (size_t)d.n_kp * 8, cudaMemcpyHostToDevice, ctx->st_copy));
-            }
+        if (host_inputs && !prefetched) {  // H2D of this chunk on the copy stream; the compute stream waits for its event only
+            int rc = stage_copy(ctx, frames, fd_stage, f0, nc, label_mode, G);
+            if (rc) return rc;
             cudaEvent_t ev = ctx->chunk_event(f0 / chunk);
             CU(cudaEventRecord(ev, ctx->st_copy));
             CU(cudaStreamWaitEvent(ctx->st, ev, 0));
@@ -633,7 +817,9 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
     ctx->last_has_cellbb = ctx->last_is_vox && !ctx->retain();
     if (ctx->last_has_cellbb)
         CU(cudaMemcpyAsync(ctx->h_counters + CNT_CELLBB, cnt + CNT_CELLBB, 24, cudaMemcpyDeviceToHost, ctx->st));
+    const double tr1 = now();
     CU(cudaStreamSynchronize(ctx->st));
+    const double tr2 = now();
     if (ctx->last_has_cellbb) memcpy(ctx->last_cellbb, ctx->h_counters + CNT_CELLBB, 24);
     ctx->last_off.assign(ctx->h_offs, ctx->h_offs + n + 1);
     ctx->last_n = n;
@@ -643,7 +829,9 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
     if (!opt.merge || ctx->defer_merge) return O3R_OK;
     const float4* outp = ctx->last_is_vox ? ctx->vox.as<float4>() : ctx->pts.as<float4>();
     if (ctx->retain()) return cloud_append_dev(ctx, outp, ctx->last_total);
-    return acc_merge_points(ctx, outp, ctx->last_total, ctx->last_has_cellbb ? ctx->last_cellbb : nullptr);
+    const int rcm = acc_merge_points(ctx, outp, ctx->last_total, ctx->last_has_cellbb ? ctx->last_cellbb : nullptr);
+    if (trace) fprintf(stderr, "[o3r trace] frames_cloud: enqueue %.3f ms, sync wait %.3f ms, merge enqueue %.3f ms\n", tr1 - tr0, tr2 - tr1, now() - tr2);
+    return rcm;
 }
 
 int copy_out(o3r_ctx* ctx, const float4* src, size_t n, o3r_point* out, size_t cap, size_t* n_out) {
@@ -711,6 +899,8 @@ int o3r_create(const o3r_params* params, o3r_ctx** out_ctx) {
     if (const char* cf = getenv("O3R_GATHER_IN_SORT")) ctx->gather_in_sort = atoi(cf) != 0;
     if (const char* cf = getenv("O3R_VG_SHORT")) ctx->vg_short = atoi(cf) != 0;
     if ((e = cudaMallocHost((void**)&ctx->h_counters, CNT_N * 4)) != cudaSuccess) return bail(e, "pinned");
+    if ((e = cudaMallocHost((void**)&ctx->h_nres, 4)) != cudaSuccess) return bail(e, "pinned");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_nres, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
     if ((e = ctx->counters.ensure(CNT_N * 4)) != cudaSuccess) return bail(e, "counters");
     if ((e = cudaMemsetAsync(ctx->counters.p, 0, CNT_N * 4, ctx->st)) != cudaSuccess) return bail(e, "memset");
     // 1/(q14*d+q15) and (float)(q11 * that) for u8 disparities
@@ -764,7 +954,10 @@ void o3r_destroy(o3r_ctx* ctx) {
     cudaSetDevice(ctx->p.device);
     if (ctx->st_copy) cudaStreamSynchronize(ctx->st_copy);
     if (ctx->st) cudaStreamSynchronize(ctx->st);
-    DevBuf* bufs[] = {&ctx->lut_r, &ctx->lut_z, &ctx->d_disp, &ctx->d_bgr, &ctx->d_labels, &ctx->d_coef, &ctx->d_kp,
+    for (auto& pf : ctx->prefetch) if (pf.ev) cudaEventDestroy(pf.ev);
+    DevBuf* bufs[] = {&ctx->lut_r, &ctx->lut_z, &ctx->d_disp, &ctx->stg[0].disp, &ctx->stg[0].bgr, &ctx->stg[0].labels,
+                      &ctx->stg[0].coef, &ctx->stg[0].kp, &ctx->stg[1].disp, &ctx->stg[1].bgr, &ctx->stg[1].labels,
+                      &ctx->stg[1].coef, &ctx->stg[1].kp,
                       &ctx->d_frames, &ctx->d_blur, &ctx->d_blurjobs, &ctx->tile_cnt, &ctx->tile_off, &ctx->bbox,
                       &ctx->frame_off, &ctx->grids, &ctx->counters, &ctx->pts, &ctx->sortbuf, &ctx->hist,
                       &ctx->plan_all, &ctx->plan_v2, &ctx->ghist, &ctx->head_cnt, &ctx->head_off, &ctx->vox,
@@ -775,6 +968,8 @@ void o3r_destroy(o3r_ctx* ctx) {
     for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_nres) cudaFreeHost(ctx->h_nres);
+    if (ctx->ev_nres) cudaEventDestroy(ctx->ev_nres);
     if (ctx->h_offs) cudaFreeHost(ctx->h_offs);
     for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
     if (ctx->st_copy) cudaStreamDestroy(ctx->st_copy);
@@ -854,6 +1049,32 @@ int o3r_frames_cloud(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_type
     return frames_cloud_impl(ctx, frames, n, disp_type, frame_counts, BatchOpts(), true);
 }
 
+int o3r_frames_prefetch(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_type) {
+    if (!ctx || n <= 0 || !frames) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    if (disp_type < 0 || disp_type > 3) return ctx->fail(O3R_ERR_INVALID, "bad disp_type");
+    const o3r_params& p = ctx->p;
+    const bool label_mode = p.use_segment_labels && frames[0].labels && frames[0].plane_coef;
+    for (int i = 0; i < n; ++i)
+        if (!frames[i].bgr || (!frames[i].disp && !label_mode) || (label_mode && (!frames[i].labels || !frames[i].plane_coef)))
+            return ctx->fail(O3R_ERR_INVALID, "frame without disparity/colour");
+    const StageGeom G = stage_geom(p, disp_type);
+    const int set = ctx->free_stage_set();
+    o3r_ctx::Prefetch& pf = ctx->prefetch[set];
+    pf.valid = false;
+    std::vector<FrameDev> fd(n);
+    int rc = stage_layout(ctx, frames, n, label_mode, p.jump_pixels, G, set, fd);
+    if (rc) return rc;
+    rc = stage_copy(ctx, frames, fd, 0, n, label_mode, G);
+    if (rc) return rc;
+    if (!pf.ev) CU(cudaEventCreateWithFlags(&pf.ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(pf.ev, ctx->st_copy));
+    frames_signature(frames, n, pf.sig);
+    pf.n = n; pf.disp_type = disp_type; pf.seq = ++ctx->prefetch_seq; pf.valid = true;
+    return O3R_OK;
+}
+
 int o3r_frame_cloud(o3r_ctx* ctx, const o3r_frame* frame, int disp_type, o3r_point* out, size_t cap, size_t* n_out) {
     if (!ctx || !frame) return O3R_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -902,7 +1123,7 @@ int o3r_cloud_transform(o3r_ctx* ctx, const float T[16]) {
                          "o3r_cloud_transform needs O3R_MERGE_RETAIN: accumulated cells cannot be re-binned");
     if (ctx->n_cloud == 0) return O3R_OK;
     CU(ctx->tmat.ensure(64));
-    CU(cudaMemcpyAsync(ctx->tmat.p, T, 48, cudaMemcpyHostToDevice, ctx->st));
+    { int rcu = upload_small(ctx, ctx->tmat.p, T, 48); if (rcu) return rcu; }
     const uint32_t g = std::min<uint32_t>(cdiv(ctx->n_cloud, kThreads), 148 * 16);
     LAUNCH(k_transform_pts, g, kThreads, 0, ctx->cloud.as<float4>(), ctx->n_cloud, ctx->tmat.as<float>());
     return O3R_OK;
@@ -928,14 +1149,20 @@ int o3r_cloud_append(o3r_ctx* ctx, const o3r_point* pts, size_t n) {
 int o3r_cloud_size(o3r_ctx* ctx, size_t* n) {
     if (!ctx || !n) return O3R_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    *n = ctx->retain() ? ctx->n_cloud : ctx->n_res;
+    if (ctx->retain()) { *n = ctx->n_cloud; return O3R_OK; }
+    int rc = refresh_nres(ctx, true);
+    if (rc) return rc;
+    *n = ctx->n_res_ub;
     return O3R_OK;
 }
 
 int o3r_cloud_clear(o3r_ctx* ctx) {
     if (!ctx) return O3R_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    ctx->n_cloud = 0; ctx->n_res = 0;
+    CU(cudaSetDevice(ctx->p.device));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->n_cloud = 0; ctx->n_res_ub = 0; ctx->n_res_exact = true;
+    ZERO(ctx->counters.as<uint32_t>() + CNT_NRES, 4);
     return O3R_OK;
 }
 
@@ -947,7 +1174,7 @@ static int voxel_grid_dev(o3r_ctx* ctx, const float4* pts, size_t n, float ix, f
     uint32_t* cnt = ctx->counters.as<uint32_t>();
     CU(ctx->seg2.ensure(16));
     const uint32_t seg_h[2] = {0u, (uint32_t)n};
-    CU(cudaMemcpyAsync(ctx->seg2.p, seg_h, 8, cudaMemcpyHostToDevice, ctx->st));
+    { int rcu = upload_small(ctx, ctx->seg2.p, seg_h, 8); if (rcu) return rcu; }
     const uint32_t* seg = ctx->seg2.as<uint32_t>();
     CU(ctx->bbox.ensure(6 * 4));
     CU(ctx->grids.ensure(sizeof(GridParams)));
@@ -991,16 +1218,21 @@ static int cloud_downsample_dev(o3r_ctx* ctx, const float4** res, size_t* m) {
         *res = ctx->ckey.as<float4>();
         return O3R_OK;
     }
-    if (ctx->n_res == 0) return O3R_OK;
+    {
+        int rc0 = refresh_nres(ctx, true);   // the exact resident count (waits for the last merge's read-back)
+        if (rc0) return rc0;
+    }
+    const uint32_t n_res = (uint32_t)ctx->n_res_ub;
+    if (n_res == 0) return O3R_OK;
     const int cur = ctx->res_cur;
-    const uint32_t tiles = cdiv(ctx->n_res, kTileV);
+    const uint32_t tiles = cdiv(n_res, kTileV);
     CU(ctx->new_cnt.ensure((size_t)tiles * 4));
     CU(ctx->new_off.ensure((size_t)tiles * 4));
-    CU(ctx->cacc.ensure((size_t)ctx->n_res * 16));
-    LAUNCH(k_acc_emit_cnt, tiles, kThreads, 0, ctx->n_res, ctx->res_acc[cur].as<float4>(), ctx->p.min_points_per_voxel,
+    CU(ctx->cacc.ensure((size_t)n_res * 16));
+    LAUNCH(k_acc_emit_cnt, tiles, kThreads, 0, n_res, ctx->res_acc[cur].as<float4>(), ctx->p.min_points_per_voxel,
            ctx->new_cnt.as<uint32_t>());
     LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->new_cnt.as<uint32_t>(), ctx->new_off.as<uint32_t>(), tiles, cnt + CNT_EMIT);
-    LAUNCH(k_acc_emit, tiles, kThreads, 0, ctx->n_res, ctx->res_acc[cur].as<float4>(), ctx->res_rgb[cur].as<uint4>(),
+    LAUNCH(k_acc_emit, tiles, kThreads, 0, n_res, ctx->res_acc[cur].as<float4>(), ctx->res_rgb[cur].as<uint4>(),
            ctx->p.min_points_per_voxel, ctx->new_off.as<uint32_t>(), ctx->cacc.as<float4>());
     int rc = read_counters(ctx);
     if (rc) return rc;
@@ -1101,6 +1333,9 @@ int o3r_exchange_pack(o3r_ctx* ctx, int world, o3r_cell* send_dev, size_t cap, u
     AccItemsPts items{ctx->vox.as<float4>(), nullptr, nullptr};
     int rc = acc_build_cycle(ctx, items, ctx->last_total, false, ctx->last_has_cellbb ? ctx->last_cellbb : nullptr);
     if (rc) return rc;
+    rc = read_counters(ctx);   // the exact number of partial cells sizes the exchange
+    if (rc) return rc;
+    ctx->n_cyc = ctx->h_counters[CNT_CYC];
     const uint32_t n = ctx->n_cyc;
     if (n == 0) return O3R_OK;
     if (cap < n) return ctx->fail(O3R_ERR_CAPACITY, "send buffer too small");
@@ -1114,10 +1349,10 @@ int o3r_exchange_pack(o3r_ctx* ctx, int world, o3r_cell* send_dev, size_t cap, u
     SortPlan pl;
     memset(&pl, 0, sizeof(pl));
     pl.active_mask = 1; pl.final_parity = 1; pl.n_active = 1; pl.n_passes = 1; pl.bits[0] = 8;
-    CU(cudaMemsetAsync(ocnt, 0, (size_t)kMaxPasses * kRsBins * 4, ctx->st));
-    CU(cudaMemcpyAsync(plan, &pl, sizeof(pl), cudaMemcpyHostToDevice, ctx->st));
+    ZERO(ocnt, (size_t)kMaxPasses * kRsBins * 4);
+    { int rcu = upload_small(ctx, plan, &pl, sizeof(pl)); if (rcu) return rcu; }
     const uint32_t seg_h[2] = {0u, n};
-    CU(cudaMemcpyAsync(ctx->seg2.p, seg_h, 8, cudaMemcpyHostToDevice, ctx->st));
+    { int rcu = upload_small(ctx, ctx->seg2.p, seg_h, 8); if (rcu) return rcu; }
     const uint32_t g = std::min<uint32_t>(cdiv(n, kThreads), 148 * 8);
     LAUNCH(k_owner, g, kThreads, 0, n, ctx->ckey.as<uint64_t>(), (uint32_t)world, sb.k0, sb.v0, ocnt);
     rc = sort_pairs<uint32_t>(ctx, sb.k0, sb.k1, sb.v0, sb.v1, ctx->seg2.as<uint32_t>(), 1, n, plan, 1, 0, ocnt);

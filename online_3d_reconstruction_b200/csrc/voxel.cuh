@@ -751,7 +751,8 @@ struct AccArgs {
     uint32_t tiles_ub;
     KeyCodec kc;
     // resident shard (sorted by absolute key)
-    const uint64_t* res_keys; float4* res_acc; uint4* res_rgb; uint32_t n_res;
+    const uint64_t* res_keys; float4* res_acc; uint4* res_rgb;
+    const uint32_t* n_res_ptr;    // resident cell count lives on the device (the merge never syncs with the host)
 };
 
 // Counts the run heads of each tile and — fully in parallel, one thread per head — looks every head's cell up in
@@ -775,12 +776,13 @@ __global__ void __launch_bounds__(kThreads) k_acc_heads(AccArgs<KeyT> A, uint32_
                 if (pos == 0 || ck != keys[pos - 1]) {
                     ++c;
                     const uint64_t k = A.kc.to_abs((uint64_t)ck);
-                    uint32_t lo = 0, hi = A.n_res;  // lower_bound in the resident keys
+                    const uint32_t n_res = *A.n_res_ptr;
+                    uint32_t lo = 0, hi = n_res;  // lower_bound in the resident keys
                     while (lo < hi) {
                         const uint32_t mid = (lo + hi) >> 1;
                         if (A.res_keys[mid] < k) lo = mid + 1; else hi = mid;
                     }
-                    const bool found = lo < A.n_res && A.res_keys[lo] == k;
+                    const bool found = lo < n_res && A.res_keys[lo] == k;
                     tags[pos] = found ? lo + 1 : 0u;
                     if (!found) ++fresh;
                 }
@@ -846,9 +848,11 @@ __global__ void __launch_bounds__(kThreads, 5) k_acc_reduce(AccArgs<KeyT> A, Ite
 }
 
 // found cells: write the continued sums back in place; new cells: flag for compaction
-__global__ void __launch_bounds__(kThreads) k_acc_update(uint32_t n_cyc, const float4* __restrict__ cacc,
+// (launched over an upper bound of the cycle's cell count; the exact count is read from the device)
+__global__ void __launch_bounds__(kThreads) k_acc_update(const uint32_t* __restrict__ n_cyc_ptr, const float4* __restrict__ cacc,
                                                          const uint4* __restrict__ crgb, float4* __restrict__ res_acc,
                                                          uint4* __restrict__ res_rgb, uint32_t* __restrict__ new_cnt) {
+    const uint32_t n_cyc = *n_cyc_ptr;
     const uint32_t t = blockIdx.x;
     uint32_t c = 0;
 #pragma unroll
@@ -874,14 +878,17 @@ __global__ void __launch_bounds__(kThreads) k_acc_update(uint32_t n_cyc, const f
 }
 
 // new cells go to their merged position: q-th new cell -> q + lower_bound(res_keys, key)
-__global__ void __launch_bounds__(kThreads) k_acc_place_new(uint32_t n_cyc, const uint64_t* __restrict__ ckey,
+__global__ void __launch_bounds__(kThreads) k_acc_place_new(const uint32_t* __restrict__ n_cyc_ptr, const uint64_t* __restrict__ ckey,
                                                             const float4* __restrict__ cacc, const uint4* __restrict__ crgb,
                                                             const uint32_t* __restrict__ new_off,
-                                                            const uint64_t* __restrict__ res_keys, uint32_t n_res,
+                                                            const uint64_t* __restrict__ res_keys,
+                                                            const uint32_t* __restrict__ n_res_ptr,
                                                             uint64_t* __restrict__ dst_keys, float4* __restrict__ dst_acc,
                                                             uint4* __restrict__ dst_rgb, uint64_t* __restrict__ new_keys) {
     __shared__ uint32_t s_scan[34];
+    const uint32_t n_cyc = *n_cyc_ptr, n_res = *n_res_ptr;
     const uint32_t t = blockIdx.x;
+    if (t * kTileV >= n_cyc) return;
     uint32_t flags = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -911,11 +918,14 @@ __global__ void __launch_bounds__(kThreads) k_acc_place_new(uint32_t n_cyc, cons
 }
 
 // resident cells shift right by the number of new cells with a smaller key
-__global__ void __launch_bounds__(kThreads) k_acc_place_old(uint32_t n_res, const uint64_t* __restrict__ res_keys,
+__global__ void __launch_bounds__(kThreads) k_acc_place_old(const uint32_t* __restrict__ n_res_ptr,
+                                                            const uint64_t* __restrict__ res_keys,
                                                             const float4* __restrict__ res_acc, const uint4* __restrict__ res_rgb,
-                                                            const uint64_t* __restrict__ new_keys, uint32_t n_new,
+                                                            const uint64_t* __restrict__ new_keys,
+                                                            const uint32_t* __restrict__ n_new_ptr,
                                                             uint64_t* __restrict__ dst_keys, float4* __restrict__ dst_acc,
                                                             uint4* __restrict__ dst_rgb) {
+    const uint32_t n_res = *n_res_ptr, n_new = *n_new_ptr;
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n_res; i += gridDim.x * kThreads) {
         const uint64_t k = res_keys[i];
         uint32_t lo = 0, hi = n_new;
@@ -928,6 +938,11 @@ __global__ void __launch_bounds__(kThreads) k_acc_place_old(uint32_t n_res, cons
         dst_acc[d] = res_acc[i];
         dst_rgb[d] = res_rgb[i];
     }
+}
+
+// the merged shard now holds n_res + n_new cells
+__global__ void k_acc_finish(uint32_t* n_res, const uint32_t* n_new) {
+    if (threadIdx.x == 0) *n_res += *n_new;
 }
 
 // downsamplePtCloud(cloud_big, true) on the accumulators: count >= min_points -> centroid, z -= 500

@@ -13,7 +13,7 @@ SO_PATH = os.path.join(_HERE, "libo3r.so")
 #: every symbol include/o3r.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "o3r_create", "o3r_destroy", "o3r_last_error", "o3r_version", "o3r_host_alloc", "o3r_host_free",
-    "o3r_frame_cloud", "o3r_frames_cloud", "o3r_frames_cloud_dev", "o3r_last_batch_points",
+    "o3r_frame_cloud", "o3r_frames_cloud", "o3r_frames_cloud_dev", "o3r_frames_prefetch", "o3r_last_batch_points",
     "o3r_cloud_transform", "o3r_cloud_append", "o3r_cloud_downsample", "o3r_cloud_downsample_dev", "o3r_cloud_size",
     "o3r_cloud_clear",
     "o3r_voxel_grid", "o3r_blur_u8", "o3r_frame_mask",
@@ -54,6 +54,7 @@ def load():
     L.o3r_frame_cloud.argtypes = [vp, F, C.c_int, vp, sz, szp]
     L.o3r_frames_cloud.argtypes = [vp, F, C.c_int, C.c_int, vp]
     L.o3r_frames_cloud_dev.argtypes = [vp, F, C.c_int, C.c_int, vp]
+    L.o3r_frames_prefetch.argtypes = [vp, F, C.c_int, C.c_int]
     L.o3r_last_batch_points.argtypes = [vp, vp, sz, szp]
     L.o3r_cloud_transform.argtypes = [vp, C.POINTER(C.c_float)]
     L.o3r_cloud_append.argtypes = [vp, vp, sz]

@@ -109,6 +109,13 @@ class Pose:
         self._check(fn(self._h, arr, n, disp_type, counts.ctypes.data))
         return counts[:n]
 
+    def prefetchCycle(self, frames, disp_type=abi.DISP_U8):
+        """Starts the host->device copies of the NEXT cycle's frames (pass the same array to createCycleClouds later)."""
+        n = len(frames)
+        arr = frames if isinstance(frames, C.Array) else (abi.Frame * n)(*frames)
+        self._check(self._L.o3r_frames_prefetch(self._h, arr, n, disp_type))
+        return arr
+
     def lastCyclePoints(self):
         n = C.c_size_t(0)
         self._check(self._L.o3r_last_batch_points(self._h, None, 0, C.byref(n)))

@@ -328,6 +328,26 @@ def test_retain_mode_icp_retro_transform():
         P.transformPtCloud(tf)  # accumulate mode cannot re-bin
 
 
+def test_prefetch_is_transparent():
+    """o3r_frames_prefetch only moves the H2D copies earlier (double-buffered staging): same results; a prefetch of
+    other frames is ignored; buffers may be reused for the cycle after next."""
+    keep = []
+    geom = SMALL4
+    p = abi.make_params(jump_pixels=3, voxel_size=0.05, **geom)
+    cycles = [_frames(90 + c, 3, geom["rows"], geom["cols"], keep=keep, n_kp=20, traj_start=3 * c) for c in range(4)]
+    with Pose(p) as A, Pose(p) as B:
+        for c in cycles:
+            A.createCycleClouds(c)
+        arrs = [(abi.Frame * len(c))(*c) for c in cycles]
+        B.prefetchCycle(arrs[0])
+        for i, arr in enumerate(arrs):
+            if i + 1 < len(arrs):
+                B.prefetchCycle(arrs[i + 1] if i != 1 else arrs[0])   # cycle 2's prefetch is a wrong guess: ignored
+            B.createCycleClouds(arr)
+            _eq(B.lastCyclePoints(), A.lastCyclePoints()) if i == len(arrs) - 1 else None
+        _eq(A.downsamplePtCloud(), B.downsamplePtCloud())
+
+
 def test_device_pointer_entry_point_matches_host_entry_point():
     torch = pytest.importorskip("torch")
     keep = []
