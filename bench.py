@@ -115,7 +115,7 @@ def make_data(wl, rank, world, n_steps_total):
     return disp, bgr, T
 
 
-def params_for(wl, device, merge_mode=abi.MERGE_ACCUMULATE):
+def params_for(wl, device, merge_mode=abi.MERGE_ACCUMULATE_TILED):
     rows, cols, dt, J, v, mp, nd, F, seed, qs = WORKLOADS[wl]
     return abi.make_params(rows=rows, cols=cols, jump_pixels=J, voxel_size=v, min_points_per_voxel=mp,
                            dont_downsample=nd, Q=synth.q_scaled(qs), device=device, max_batch_frames=F,

@@ -56,8 +56,14 @@ enum { O3R_BLUR_MEDIAN = 0, O3R_BLUR_BOX = 1 };
 enum {
     O3R_MERGE_ACCUMULATE = 0, /* per-cell accumulators keyed by the combined-grid key, merged every
                                  cycle; o3r_cloud_transform is unsupported                         */
-    O3R_MERGE_RETAIN     = 1  /* cloud_big kept as points (pose.cpp:434); o3r_cloud_transform
+    O3R_MERGE_RETAIN     = 1, /* cloud_big kept as points (pose.cpp:434); o3r_cloud_transform
                                  applies tf_icp in place (pose.cpp:353); one-shot voxelisation     */
+    O3R_MERGE_ACCUMULATE_TILED = 2 /* as ACCUMULATE, but every 1024 consecutive per-frame voxels are first
+                                 summed per cell inside the GPU's shared memory and only those partial
+                                 sums are sorted and merged (8x less traffic).  Cell keys, point counts and
+                                 colour sums are identical to ACCUMULATE; centroids differ by float
+                                 reassociation only (<= 1e-5 relative, north_star's tolerance) and are
+                                 reproducible from run to run                                       */
 };
 
 /* Read-only configuration: the `Pose` members the path reads (pose.h:93-98,108,118,126-128,149,168). */

@@ -13,6 +13,7 @@
 
 #include "blur.cuh"
 #include "common.cuh"
+#include "prereduce.cuh"
 #include "sort.cuh"
 #include "stage_a.cuh"
 #include "voxel.cuh"
@@ -54,7 +55,7 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-enum { CNT_PTS = 0, CNT_VOX = 1, CNT_CYC = 2, CNT_NEW = 3, CNT_EMIT = 4, CNT_NEWSCAN = 5, CNT_BASE = 6, CNT_NRES = 7, CNT_ZERO = 8,
+enum { CNT_PTS = 0, CNT_VOX = 1, CNT_CYC = 2, CNT_NEW = 3, CNT_EMIT = 4, CNT_NEWSCAN = 5, CNT_BASE = 6, CNT_NRES = 7, CNT_ZERO = 8, CNT_PART = 9, CNT_PARTCHUNK = 10,
        CNT_CELLBB = 16, CNT_N = 32 };
 
 }  // namespace
@@ -130,6 +131,9 @@ struct o3r_ctx {
     cudaEvent_t ev_nres = nullptr;
     size_t n_cyc_ub = 0;
     DevBuf ckey, cacc, crgb, new_cnt, new_off, new_keys, okeys;
+    DevBuf partials, pr_status;   // TILED mode: the batch's tile partials (o3r_cell) and the look-back words
+    size_t last_partials = 0;
+    bool last_has_partials = false;
     uint32_t n_cyc = 0;
     // ... or points (RETAIN / dont_downsample)
     DevBuf cloud;
@@ -146,6 +150,7 @@ struct o3r_ctx {
     }
 
     bool retain() const { return p.dont_downsample || p.merge_mode == O3R_MERGE_RETAIN; }
+    bool tiled() const { return !p.dont_downsample && p.merge_mode == O3R_MERGE_ACCUMULATE_TILED; }
     int fail(int code, const std::string& m) { err = m; return code; }
     int fail_cuda(cudaError_t e, const char* what, int line) {
         char buf[512];
@@ -493,6 +498,13 @@ int acc_merge_points(o3r_ctx* ctx, const float4* pts, size_t n, const int* bb) {
     return acc_apply_cycle(ctx);
 }
 
+int acc_merge_cells(o3r_ctx* ctx, const o3r_cell* cells, size_t n, const int* bb) {
+    AccItemsCells items{cells, nullptr, nullptr};
+    int rc = acc_build_cycle(ctx, items, n, true, bb);
+    if (rc) return rc;
+    return acc_apply_cycle(ctx);
+}
+
 int cloud_append_dev(o3r_ctx* ctx, const float4* pts, size_t n) {
     if (n == 0) return O3R_OK;
     CU(ctx->cloud.ensure((ctx->n_cloud + n) * 16, ctx->st, ctx->n_cloud * 16));
@@ -752,6 +764,11 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
             int rc = carve_sort_u32(ctx, cap_chunk, sb);
             if (rc) return rc;
             if (!ctx->retain()) LAUNCH(k_cellbb_init, 1, 32, 0, reinterpret_cast<int*>(cnt + CNT_CELLBB));
+            if (ctx->tiled()) {   // worst case one partial per item; never reached in practice (~1/8)
+                CU(ctx->partials.ensure(cap_batch * sizeof(o3r_cell)));
+                CU(ctx->pr_status.ensure(((size_t)cdiv(cap_chunk, kPrTile) + 16) * 4));
+                ZERO(cnt + CNT_PART, 8);
+            }
         } else {
             CU(ctx->pts.ensure(cap_batch * 16));
         }
@@ -801,6 +818,15 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
                                   ctx->grids.as<GridParams>(), ctx->inv_f, ctx->inv_f, ctx->inv_f, 0, 0,
                                   ctx->vox.as<float4>(), goff + f0, nullptr, nullptr, !ctx->retain(), cnt + CNT_BASE);
             if (rc) return rc;
+            if (ctx->tiled()) {   // group the chunk's voxel centroids by combined-grid cell, tile by tile
+                const uint32_t pt = cdiv(cap_chunk, kPrTile);
+                uint32_t* stw = ctx->pr_status.as<uint32_t>();
+                ZERO(stw, ((size_t)pt + 16) * 4);
+                ZERO(cnt + CNT_PARTCHUNK, 4);
+                LAUNCH(k_cell_prereduce, pt, kThreads, 0, ctx->vox.as<float4>(), cnt + CNT_BASE, cnt + CNT_VOX, ctx->inv_c,
+                       ctx->inv_cz, ctx->partials.as<o3r_cell>(), cnt + CNT_PART, cnt + CNT_PARTCHUNK, stw, stw + pt);
+                LAUNCH(k_add_u32, 1, 32, 0, cnt + CNT_PART, cnt + CNT_PARTCHUNK);
+            }
             LAUNCH(k_add_base, 1, 32, 0, cnt + CNT_BASE, cnt + CNT_VOX, goff + f0 + nc);
         } else {
             LAUNCH(k_add_base, 1, 32, 0, cnt + CNT_BASE, cnt + CNT_PTS, goff + f0 + nc);
@@ -817,8 +843,12 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
     ctx->last_has_cellbb = ctx->last_is_vox && !ctx->retain();
     if (ctx->last_has_cellbb)
         CU(cudaMemcpyAsync(ctx->h_counters + CNT_CELLBB, cnt + CNT_CELLBB, 24, cudaMemcpyDeviceToHost, ctx->st));
+    ctx->last_has_partials = ctx->last_is_vox && ctx->tiled();
+    if (ctx->last_has_partials)
+        CU(cudaMemcpyAsync(ctx->h_counters + CNT_PART, cnt + CNT_PART, 4, cudaMemcpyDeviceToHost, ctx->st));
     const double tr1 = now();
     CU(cudaStreamSynchronize(ctx->st));
+    ctx->last_partials = ctx->last_has_partials ? ctx->h_counters[CNT_PART] : 0;
     const double tr2 = now();
     if (ctx->last_has_cellbb) memcpy(ctx->last_cellbb, ctx->h_counters + CNT_CELLBB, 24);
     ctx->last_off.assign(ctx->h_offs, ctx->h_offs + n + 1);
@@ -829,7 +859,9 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
     if (!opt.merge || ctx->defer_merge) return O3R_OK;
     const float4* outp = ctx->last_is_vox ? ctx->vox.as<float4>() : ctx->pts.as<float4>();
     if (ctx->retain()) return cloud_append_dev(ctx, outp, ctx->last_total);
-    const int rcm = acc_merge_points(ctx, outp, ctx->last_total, ctx->last_has_cellbb ? ctx->last_cellbb : nullptr);
+    const int* bbp = ctx->last_has_cellbb ? ctx->last_cellbb : nullptr;
+    const int rcm = ctx->last_has_partials ? acc_merge_cells(ctx, ctx->partials.as<o3r_cell>(), ctx->last_partials, bbp)
+                                           : acc_merge_points(ctx, outp, ctx->last_total, bbp);
     if (trace) fprintf(stderr, "[o3r trace] frames_cloud: enqueue %.3f ms, sync wait %.3f ms, merge enqueue %.3f ms\n", tr1 - tr0, tr2 - tr1, now() - tr2);
     return rcm;
 }
@@ -963,7 +995,7 @@ void o3r_destroy(o3r_ctx* ctx) {
                       &ctx->plan_all, &ctx->plan_v2, &ctx->ghist, &ctx->head_cnt, &ctx->head_off, &ctx->vox,
                       &ctx->vox_off, &ctx->seg2, &ctx->tmat, &ctx->mask, &ctx->runwork, &ctx->spts, &ctx->res_keys[0], &ctx->res_keys[1],
                       &ctx->res_acc[0], &ctx->res_acc[1], &ctx->res_rgb[0], &ctx->res_rgb[1], &ctx->ckey, &ctx->cacc,
-                      &ctx->crgb, &ctx->new_cnt, &ctx->new_off, &ctx->new_keys, &ctx->okeys, &ctx->cloud};
+                      &ctx->crgb, &ctx->partials, &ctx->pr_status, &ctx->new_cnt, &ctx->new_off, &ctx->new_keys, &ctx->okeys, &ctx->cloud};
     for (DevBuf* b : bufs) b->release();
     for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -1143,6 +1175,7 @@ int o3r_cloud_append(o3r_ctx* ctx, const o3r_point* pts, size_t n) {
     CU(ctx->vox.ensure(n * 16));
     CU(cudaMemcpyAsync(ctx->vox.p, pts, n * 16, cudaMemcpyHostToDevice, ctx->st));
     ctx->last_n = 0; ctx->last_total = 0; ctx->last_has_cellbb = false;   // the batch buffer was overwritten
+    ctx->last_has_partials = false; ctx->last_partials = 0;
     return acc_merge_points(ctx, ctx->vox.as<float4>(), n, nullptr);
 }
 
@@ -1330,8 +1363,15 @@ int o3r_exchange_pack(o3r_ctx* ctx, int world, o3r_cell* send_dev, size_t cap, u
     if (ctx->retain()) return ctx->fail(O3R_ERR_UNSUPPORTED, "exchange needs O3R_MERGE_ACCUMULATE");
     std::fill(counts, counts + world, 0u);
     if (!ctx->last_is_vox || ctx->last_total == 0) { ctx->n_cyc = 0; return O3R_OK; }
-    AccItemsPts items{ctx->vox.as<float4>(), nullptr, nullptr};
-    int rc = acc_build_cycle(ctx, items, ctx->last_total, false, ctx->last_has_cellbb ? ctx->last_cellbb : nullptr);
+    int rc;
+    const int* bbp = ctx->last_has_cellbb ? ctx->last_cellbb : nullptr;
+    if (ctx->last_has_partials) {
+        AccItemsCells items{ctx->partials.as<o3r_cell>(), nullptr, nullptr};
+        rc = acc_build_cycle(ctx, items, ctx->last_partials, false, bbp);
+    } else {
+        AccItemsPts items{ctx->vox.as<float4>(), nullptr, nullptr};
+        rc = acc_build_cycle(ctx, items, ctx->last_total, false, bbp);
+    }
     if (rc) return rc;
     rc = read_counters(ctx);   // the exact number of partial cells sizes the exchange
     if (rc) return rc;

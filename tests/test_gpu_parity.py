@@ -276,6 +276,82 @@ def test_cycles_merge_equals_one_shot_reference(mode, min_pts):
     _eq(got, exp)
 
 
+def _close(got, exp, rel=1e-5):
+    """north_star tolerance for centroids: same records, order, colours (bit-exact) and |dxyz| <= rel * |value| measured
+    where the sums live (z + 500: pose_functions.cpp:1666 shifts z before the combined VoxelGrid)."""
+    assert got.shape == exp.shape, (got.shape, exp.shape)
+    assert np.array_equal(got["rgb"], exp["rgb"])
+    for f, shift in (("x", 0.0), ("y", 0.0), ("z", 500.0)):
+        a, b = got[f].astype(np.float64) + shift, exp[f].astype(np.float64) + shift
+        err = np.abs(a - b)
+        lim = rel * np.maximum(np.abs(b), 1e-3)
+        assert np.all(err <= lim), f"{f}: max rel err {np.max(err / np.maximum(np.abs(b), 1e-3)):.3g}"
+
+
+@pytest.mark.parametrize("min_pts", [1, 2, 5])
+@pytest.mark.parametrize("voxel", [0.05, 0.2])
+def test_tiled_merge_keys_counts_colours_exact_centroids_1e5(min_pts, voxel):
+    """O3R_MERGE_ACCUMULATE_TILED: tile partial sums are merged instead of single items.  The set of cells (keys), their
+    order, the per-cell point counts (probed through min_points_per_voxel = 1, 2, 5) and the colour sums must equal
+    the one-shot reference voxelisation exactly; centroids within 1e-5 relative (float reassociation)."""
+    keep = []
+    geom = SMALL4
+    p = abi.make_params(jump_pixels=1, voxel_size=voxel, min_points_per_voxel=min_pts,
+                        merge_mode=abi.MERGE_ACCUMULATE_TILED, **geom)
+    cycles = [_frames(140, 4, geom["rows"], geom["cols"], keep=keep, traj_start=0),
+              _frames(141, 3, geom["rows"], geom["cols"], keep=keep, traj_start=4),
+              _frames(142, 4, geom["rows"], geom["cols"], keep=keep, traj_start=5)]
+    big, counts = _oracle_cycles(p, cycles)
+    exp = ob.downsample_pt_cloud(p, big, True)
+    with Pose(p) as P:
+        at = 0
+        for frames, c in zip(cycles, counts):
+            assert np.array_equal(P.createCycleClouds(frames), c)
+            n = int(c.sum())
+            _eq(P.lastCyclePoints(), big[at:at + n])   # the per-frame clouds themselves stay bit-exact
+            at += n
+        got = P.downsamplePtCloud()
+    assert len(exp) > 50
+    _close(got, exp)
+    # cell keys of the outputs: identical sequence
+    inv = np.float32(1.0) / np.float32(voxel)
+    for f in ("x", "y"):
+        assert np.array_equal(np.floor(got[f] * inv), np.floor(exp[f] * inv))
+
+
+def test_tiled_merge_is_reproducible_and_matches_exact_mode_cells():
+    """Two runs of the tiled mode give identical bits (no atomics on floats, fixed fold order); the exact-order mode on
+    the same input has the same cells, counts and colours."""
+    keep = []
+    geom = SMALL4
+    frames = _frames(150, 5, geom["rows"], geom["cols"], keep=keep, n_kp=0)
+    outs = []
+    for mode in (abi.MERGE_ACCUMULATE_TILED, abi.MERGE_ACCUMULATE_TILED, abi.MERGE_ACCUMULATE):
+        p = abi.make_params(jump_pixels=1, voxel_size=0.05, merge_mode=mode, **geom)
+        with Pose(p) as P:
+            P.createCycleClouds(frames[:3])
+            P.createCycleClouds(frames[3:])
+            outs.append(P.downsamplePtCloud())
+    _eq(outs[0], outs[1])
+    _close(outs[0], outs[2])
+
+
+def test_tiled_merge_full_resolution_720p_against_exact_mode():
+    """Full-size property: at 1280x720 (748 000 points per frame, tiles that straddle frames and partial last tiles)
+    the tiled mode and the exact-order mode agree on cells, counts (min_points 3) and colours, centroids 1e-5."""
+    keep = []
+    frames = _frames(160, 3, 720, 1280, keep=keep)
+    outs = []
+    for mode in (abi.MERGE_ACCUMULATE_TILED, abi.MERGE_ACCUMULATE):
+        p = abi.make_params(jump_pixels=1, voxel_size=0.05, min_points_per_voxel=3, merge_mode=mode)
+        with Pose(p) as P:
+            P.createCycleClouds(frames[:2])
+            P.createCycleClouds(frames[2:])
+            outs.append(P.downsamplePtCloud())
+    assert len(outs[1]) > 10000
+    _close(outs[0], outs[1])
+
+
 def test_downsample_device_result_matches_host_result():
     torch = pytest.importorskip("torch")
     keep = []
@@ -407,14 +483,15 @@ def test_full_resolution_properties_720p():
 
 
 # -------------------------------------------------------------------------------------------- multi-GPU
-def test_exchange_two_ranks_equals_single_rank():
+@pytest.mark.parametrize("mode", [abi.MERGE_ACCUMULATE, abi.MERGE_ACCUMULATE_TILED])
+def test_exchange_two_ranks_equals_single_rank(mode):
     """SURVEY §8e on one device: two contexts act as two ranks (frames f mod 2), exchange hash-partitioned
     partial cells, and the union of their shards must equal the single-rank result: keys, counts and colours
     exactly, centroids within 1e-5 (cross-rank partial sums reassociate)."""
     torch = pytest.importorskip("torch")
     keep = []
     geom = SMALL4
-    p = abi.make_params(jump_pixels=1, voxel_size=0.05, min_points_per_voxel=1, **geom)
+    p = abi.make_params(jump_pixels=1, voxel_size=0.05, min_points_per_voxel=1, merge_mode=mode, **geom)
     cycles = [_frames(80, 6, geom["rows"], geom["cols"], keep=keep), _frames(81, 6, geom["rows"], geom["cols"], keep=keep, traj_start=6)]
     with Pose(p) as S:
         for frames in cycles:
