@@ -65,7 +65,8 @@ struct o3r_ctx {
     std::mutex mu;
     std::string err;
     uint64_t launches = 0;
-    cudaStream_t st = nullptr, st_copy = nullptr;
+    cudaStream_t st = nullptr, st_copy = nullptr, st_copy2 = nullptr;   // two copy streams: the per-copy set-up gaps of one hide behind the other
+    cudaEvent_t ev_copy2 = nullptr;
     std::vector<cudaEvent_t> chunk_ev;
     int chunk_frames = 10, chunk_frames_dev = 1 << 30;
     int gather_in_sort = 0;   // experiment: deliver points in sorted order from the last radix pass
@@ -96,9 +97,15 @@ struct o3r_ctx {
         cudaEvent_t ev = nullptr;
     } prefetch[2];
     uint64_t prefetch_seq = 0;
+    // A prefetch request is only RECORDED by o3r_frames_prefetch; its ~2 memcpy calls per frame are issued by the next
+    // frame-path call right after that call's kernels are queued (the GPU computes while the host issues copies)
+    // instead of in front of them with the GPU idle.
+    struct Deferred { bool pending = false; std::vector<o3r_frame> frames; int disp_type = 0; } deferred;
     // a staging set that holds no pending prefetch (inputs of finished calls are free: every frame-path call returns
     // only after its last input-reading kernel has completed)
+    int busy_set = -1;   // staging set the queued kernels of the running frame-path call still read
     int free_stage_set() {
+        if (busy_set >= 0) { prefetch[busy_set ^ 1].valid = false; return busy_set ^ 1; }
         if (!prefetch[0].valid) return 0;
         if (!prefetch[1].valid) return 1;
         const int s = prefetch[0].seq < prefetch[1].seq ? 0 : 1;
@@ -593,26 +600,68 @@ int stage_layout(o3r_ctx* ctx, const o3r_frame* frames, int n, bool label_mode, 
     return O3R_OK;
 }
 
-// issues the H2D copies of frames [f0, f0 + nc) on the copy stream
+// issues the H2D copies of frames [f0, f0 + nc): frames alternate between the two copy streams, and the first stream
+// then waits for the second, so an event recorded on st_copy after this call covers every copy
 int stage_copy(o3r_ctx* ctx, const o3r_frame* frames, const std::vector<FrameDev>& fd, int f0, int nc, bool label_mode,
                const StageGeom& G) {
     const o3r_params& p = ctx->p;
+    // Only the pixels the path can read cross PCIe: the scan ROI x in [x0, cols-bb), y in [bb, rows-bb)
+    // (pose_functions.cpp:1062,1094-1095; keypoints outside it are rejected too), widened by the blur window's reach for
+    // the disparity plane.  The device planes keep the full-image layout, so the kernels index as before.
+    const int halo = p.blur_kernel > 1 ? p.blur_kernel / 2 + 1 : 0;
+    const int cx0 = std::min(p.cols, std::max(0, p.cols_start_aft_cutout)), cx1 = std::max(cx0, p.cols - p.bounding_box);
+    const int cy0 = std::min(p.rows, std::max(0, p.bounding_box)), cy1 = std::max(cy0, p.rows - p.bounding_box);
+    const int dx0 = std::max(0, cx0 - halo), dx1 = std::min(p.cols, cx1 + halo);
+    const int dy0 = std::max(0, cy0 - halo), dy1 = std::min(p.rows, cy1 + halo);
+    if (cx1 <= cx0 || cy1 <= cy0) return O3R_OK;   // empty ROI: nothing is ever read
     for (int i = f0; i < f0 + nc; ++i) {
         const o3r_frame& f = frames[i];
         const FrameDev& d = fd[i];
+        cudaStream_t cs = (i & 1) ? ctx->st_copy2 : ctx->st_copy;
         if (!label_mode) {
-            CU(cudaMemcpy2DAsync((void*)d.disp, G.dstep, f.disp, f.disp_step, (size_t)p.cols * G.es, p.rows,
-                                 cudaMemcpyHostToDevice, ctx->st_copy));
+            CU(cudaMemcpy2DAsync((uint8_t*)d.disp + (size_t)dy0 * G.dstep + (size_t)dx0 * G.es, G.dstep,
+                                 (const uint8_t*)f.disp + (size_t)dy0 * f.disp_step + (size_t)dx0 * G.es, f.disp_step,
+                                 (size_t)(dx1 - dx0) * G.es, dy1 - dy0, cudaMemcpyHostToDevice, cs));
         } else {
-            CU(cudaMemcpy2DAsync((void*)d.labels, G.lstep, f.labels, f.labels_step, (size_t)p.cols, p.rows,
-                                 cudaMemcpyHostToDevice, ctx->st_copy));
+            CU(cudaMemcpy2DAsync((uint8_t*)d.labels + (size_t)cy0 * G.lstep + cx0, G.lstep,
+                                 f.labels + (size_t)cy0 * f.labels_step + cx0, f.labels_step, (size_t)(cx1 - cx0), cy1 - cy0,
+                                 cudaMemcpyHostToDevice, cs));
             if (d.n_planes)
-                CU(cudaMemcpyAsync((void*)d.plane_coef, f.plane_coef, (size_t)d.n_planes * 24, cudaMemcpyHostToDevice, ctx->st_copy));
+                CU(cudaMemcpyAsync((void*)d.plane_coef, f.plane_coef, (size_t)d.n_planes * 24, cudaMemcpyHostToDevice, cs));
         }
-        CU(cudaMemcpy2DAsync((void*)d.bgr, G.cstep, f.bgr, f.bgr_step, (size_t)p.cols * 3, p.rows, cudaMemcpyHostToDevice,
-                             ctx->st_copy));
-        if (d.n_kp) CU(cudaMemcpyAsync((void*)d.kp_xy, f.kp_xy, (size_t)d.n_kp * 8, cudaMemcpyHostToDevice, ctx->st_copy));
+        CU(cudaMemcpy2DAsync((uint8_t*)d.bgr + (size_t)cy0 * G.cstep + (size_t)cx0 * 3, G.cstep,
+                             f.bgr + (size_t)cy0 * f.bgr_step + (size_t)cx0 * 3, f.bgr_step, (size_t)(cx1 - cx0) * 3, cy1 - cy0,
+                             cudaMemcpyHostToDevice, cs));
+        if (d.n_kp) CU(cudaMemcpyAsync((void*)d.kp_xy, f.kp_xy, (size_t)d.n_kp * 8, cudaMemcpyHostToDevice, cs));
     }
+    if (nc > 1) {
+        CU(cudaEventRecord(ctx->ev_copy2, ctx->st_copy2));
+        CU(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_copy2, 0));
+    }
+    return O3R_OK;
+}
+
+// issues the copies of a recorded prefetch request into a free staging set
+int flush_deferred_prefetch(o3r_ctx* ctx) {
+    if (!ctx->deferred.pending) return O3R_OK;
+    ctx->deferred.pending = false;
+    const o3r_params& p = ctx->p;
+    const o3r_frame* frames = ctx->deferred.frames.data();
+    const int n = (int)ctx->deferred.frames.size(), disp_type = ctx->deferred.disp_type;
+    const bool label_mode = p.use_segment_labels && frames[0].labels && frames[0].plane_coef;
+    const StageGeom G = stage_geom(p, disp_type);
+    const int set = ctx->free_stage_set();
+    o3r_ctx::Prefetch& pf = ctx->prefetch[set];
+    pf.valid = false;
+    std::vector<FrameDev> fd(n);
+    int rc = stage_layout(ctx, frames, n, label_mode, p.jump_pixels, G, set, fd);
+    if (rc) return rc;
+    rc = stage_copy(ctx, frames, fd, 0, n, label_mode, G);
+    if (rc) return rc;
+    if (!pf.ev) CU(cudaEventCreateWithFlags(&pf.ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(pf.ev, ctx->st_copy));
+    frames_signature(frames, n, pf.sig);
+    pf.n = n; pf.disp_type = disp_type; pf.seq = ++ctx->prefetch_seq; pf.valid = true;
     return O3R_OK;
 }
 
@@ -622,6 +671,7 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
                       const BatchOpts& opt, bool host_inputs) {
     const o3r_params& p = ctx->p;
     static const bool trace = getenv("O3R_TRACE") != nullptr;
+    ctx->busy_set = -1;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double tr0 = now();
     if (n <= 0) { ctx->last_n = 0; ctx->last_total = 0; return O3R_OK; }
@@ -693,8 +743,20 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
                 prefetched = true; set = s;
             }
         }
+        if (!prefetched && ctx->deferred.pending && (int)ctx->deferred.frames.size() == n &&
+            ctx->deferred.disp_type == disp_type) {   // recorded but not issued yet (nothing ran in between): issue it now
+            std::vector<const void*> dsig;
+            frames_signature(ctx->deferred.frames.data(), n, dsig);
+            if (dsig == sig) {
+                int rcf = flush_deferred_prefetch(ctx);
+                if (rcf) return rcf;
+                for (int s = 0; s < 2; ++s)
+                    if (ctx->prefetch[s].valid && ctx->prefetch[s].seq == ctx->prefetch_seq) { prefetched = true; set = s; }
+            }
+        }
         if (prefetched) ctx->prefetch[set].valid = false;
         if (!prefetched) set = ctx->free_stage_set();
+        ctx->busy_set = set;
     }
     if (blur) CU(ctx->d_blur.ensure((size_t)n * p.rows * blur_step));
     std::vector<FrameDev> fd(n);
@@ -843,11 +905,18 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
     ctx->last_has_cellbb = ctx->last_is_vox && !ctx->retain();
     if (ctx->last_has_cellbb)
         CU(cudaMemcpyAsync(ctx->h_counters + CNT_CELLBB, cnt + CNT_CELLBB, 24, cudaMemcpyDeviceToHost, ctx->st));
+    // the kernels of this call are queued: now issue the copies of a recorded prefetch (next cycle's inputs).  The
+    // staging set they go to is not the one these kernels read.
+    if (ctx->deferred.pending && !opt.mask_only) {
+        int rcf = flush_deferred_prefetch(ctx);
+        if (rcf) return rcf;
+    }
     ctx->last_has_partials = ctx->last_is_vox && ctx->tiled();
     if (ctx->last_has_partials)
         CU(cudaMemcpyAsync(ctx->h_counters + CNT_PART, cnt + CNT_PART, 4, cudaMemcpyDeviceToHost, ctx->st));
     const double tr1 = now();
     CU(cudaStreamSynchronize(ctx->st));
+    ctx->busy_set = -1;
     ctx->last_partials = ctx->last_has_partials ? ctx->h_counters[CNT_PART] : 0;
     const double tr2 = now();
     if (ctx->last_has_cellbb) memcpy(ctx->last_cellbb, ctx->h_counters + CNT_CELLBB, 24);
@@ -926,6 +995,8 @@ int o3r_create(const o3r_params* params, o3r_ctx** out_ctx) {
     };
     if ((e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
     if ((e = cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+    if ((e = cudaStreamCreateWithFlags(&ctx->st_copy2, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_copy2, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
     if (const char* cf = getenv("O3R_CHUNK_FRAMES")) ctx->chunk_frames = std::max(1, atoi(cf));
     if (const char* cf = getenv("O3R_CHUNK_FRAMES_DEV")) ctx->chunk_frames_dev = std::max(1, atoi(cf));
     if (const char* cf = getenv("O3R_GATHER_IN_SORT")) ctx->gather_in_sort = atoi(cf) != 0;
@@ -984,6 +1055,7 @@ int o3r_create(const o3r_params* params, o3r_ctx** out_ctx) {
 void o3r_destroy(o3r_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->p.device);
+    if (ctx->st_copy2) cudaStreamSynchronize(ctx->st_copy2);
     if (ctx->st_copy) cudaStreamSynchronize(ctx->st_copy);
     if (ctx->st) cudaStreamSynchronize(ctx->st);
     for (auto& pf : ctx->prefetch) if (pf.ev) cudaEventDestroy(pf.ev);
@@ -1004,6 +1076,8 @@ void o3r_destroy(o3r_ctx* ctx) {
     if (ctx->ev_nres) cudaEventDestroy(ctx->ev_nres);
     if (ctx->h_offs) cudaFreeHost(ctx->h_offs);
     for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
+    if (ctx->ev_copy2) cudaEventDestroy(ctx->ev_copy2);
+    if (ctx->st_copy2) cudaStreamDestroy(ctx->st_copy2);
     if (ctx->st_copy) cudaStreamDestroy(ctx->st_copy);
     if (ctx->st) cudaStreamDestroy(ctx->st);
     delete ctx;
@@ -1091,19 +1165,11 @@ int o3r_frames_prefetch(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_t
     for (int i = 0; i < n; ++i)
         if (!frames[i].bgr || (!frames[i].disp && !label_mode) || (label_mode && (!frames[i].labels || !frames[i].plane_coef)))
             return ctx->fail(O3R_ERR_INVALID, "frame without disparity/colour");
-    const StageGeom G = stage_geom(p, disp_type);
-    const int set = ctx->free_stage_set();
-    o3r_ctx::Prefetch& pf = ctx->prefetch[set];
-    pf.valid = false;
-    std::vector<FrameDev> fd(n);
-    int rc = stage_layout(ctx, frames, n, label_mode, p.jump_pixels, G, set, fd);
+    int rc = flush_deferred_prefetch(ctx);   // at most one request waits; an older one goes out now
     if (rc) return rc;
-    rc = stage_copy(ctx, frames, fd, 0, n, label_mode, G);
-    if (rc) return rc;
-    if (!pf.ev) CU(cudaEventCreateWithFlags(&pf.ev, cudaEventDisableTiming));
-    CU(cudaEventRecord(pf.ev, ctx->st_copy));
-    frames_signature(frames, n, pf.sig);
-    pf.n = n; pf.disp_type = disp_type; pf.seq = ++ctx->prefetch_seq; pf.valid = true;
+    ctx->deferred.frames.assign(frames, frames + n);
+    ctx->deferred.disp_type = disp_type;
+    ctx->deferred.pending = true;
     return O3R_OK;
 }
 
@@ -1235,8 +1301,11 @@ static int voxel_grid_dev(o3r_ctx* ctx, const float4* pts, size_t n, float ix, f
 }
 
 // downsamplePtCloud(cloud_big, true) into a device buffer: *res = result, *m = records
-static int cloud_downsample_dev(o3r_ctx* ctx, const float4** res, size_t* m) {
+// When *exact_pending comes back true, *m is only an upper bound and the exact record count is still on the device
+// (cnt[CNT_EMIT]): the caller queues its read-back (and the output copy) behind the kernels and syncs ONCE.
+static int cloud_downsample_dev(o3r_ctx* ctx, const float4** res, size_t* m, bool* exact_pending) {
     *res = nullptr; *m = 0;
+    if (exact_pending) *exact_pending = false;
     if (ctx->p.dont_downsample) {  // pose.cpp:533-536: cloud_small = cloud_big
         *res = ctx->cloud.as<float4>(); *m = ctx->n_cloud;
         return O3R_OK;
@@ -1251,26 +1320,34 @@ static int cloud_downsample_dev(o3r_ctx* ctx, const float4** res, size_t* m) {
         *res = ctx->ckey.as<float4>();
         return O3R_OK;
     }
-    {
-        int rc0 = refresh_nres(ctx, true);   // the exact resident count (waits for the last merge's read-back)
-        if (rc0) return rc0;
-    }
-    const uint32_t n_res = (uint32_t)ctx->n_res_ub;
-    if (n_res == 0) return O3R_OK;
+    // device-driven: launches are sized by the host's upper bound of the resident count, the kernels read the exact one
+    { int rc0 = refresh_nres(ctx, false); if (rc0) return rc0; }
+    const size_t n_ub = ctx->n_res_ub;
+    if (n_ub == 0) return O3R_OK;
     const int cur = ctx->res_cur;
-    const uint32_t tiles = cdiv(n_res, kTileV);
+    const uint32_t tiles = cdiv(n_ub, kTileV);
     CU(ctx->new_cnt.ensure((size_t)tiles * 4));
     CU(ctx->new_off.ensure((size_t)tiles * 4));
-    CU(ctx->cacc.ensure((size_t)n_res * 16));
-    LAUNCH(k_acc_emit_cnt, tiles, kThreads, 0, n_res, ctx->res_acc[cur].as<float4>(), ctx->p.min_points_per_voxel,
+    CU(ctx->cacc.ensure(n_ub * 16));
+    LAUNCH(k_acc_emit_cnt, tiles, kThreads, 0, cnt + CNT_NRES, ctx->res_acc[cur].as<float4>(), ctx->p.min_points_per_voxel,
            ctx->new_cnt.as<uint32_t>());
     LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->new_cnt.as<uint32_t>(), ctx->new_off.as<uint32_t>(), tiles, cnt + CNT_EMIT);
-    LAUNCH(k_acc_emit, tiles, kThreads, 0, n_res, ctx->res_acc[cur].as<float4>(), ctx->res_rgb[cur].as<uint4>(),
+    LAUNCH(k_acc_emit, tiles, kThreads, 0, cnt + CNT_NRES, ctx->res_acc[cur].as<float4>(), ctx->res_rgb[cur].as<uint4>(),
            ctx->p.min_points_per_voxel, ctx->new_off.as<uint32_t>(), ctx->cacc.as<float4>());
-    int rc = read_counters(ctx);
-    if (rc) return rc;
-    *m = ctx->h_counters[CNT_EMIT];
     *res = ctx->cacc.as<float4>();
+    *m = n_ub;   // upper bound; the exact count is cnt[CNT_EMIT] once the stream has run (callers read it back)
+    if (exact_pending) *exact_pending = true;
+    return O3R_OK;
+}
+
+// one read-back of the exact output count (and of the resident count, which tightens the host's bound)
+static int downsample_finish(o3r_ctx* ctx, size_t* m) {
+    uint32_t* cnt = ctx->counters.as<uint32_t>();
+    CU(cudaMemcpyAsync(ctx->h_counters, cnt, CNT_N * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    *m = ctx->h_counters[CNT_EMIT];
+    ctx->n_res_ub = ctx->h_counters[CNT_NRES];
+    ctx->n_res_exact = true;
     return O3R_OK;
 }
 
@@ -1281,9 +1358,19 @@ int o3r_cloud_downsample(o3r_ctx* ctx, o3r_point* out, size_t cap, size_t* n_out
     if (n_out) *n_out = 0;
     const float4* res;
     size_t m;
-    int rc = cloud_downsample_dev(ctx, &res, &m);
+    bool pending;
+    int rc = cloud_downsample_dev(ctx, &res, &m, &pending);
     if (rc) return rc;
-    return copy_out(ctx, res, m, out, cap, n_out);
+    if (!pending) return copy_out(ctx, res, m, out, cap, n_out);
+    // accumulators: the copy of up to min(cap, bound) records is queued behind the emit kernels, one sync for everything
+    const size_t ncopy = (out && cap) ? std::min(cap, m) : 0;
+    if (ncopy) CU(cudaMemcpyAsync(out, res, ncopy * 16, cudaMemcpyDeviceToHost, ctx->st));
+    rc = downsample_finish(ctx, &m);
+    if (rc) return rc;
+    if (n_out) *n_out = m;
+    if (!out && cap == 0) return O3R_OK;
+    if (cap < m) return ctx->fail(O3R_ERR_CAPACITY, "output buffer too small");
+    return O3R_OK;
 }
 
 int o3r_cloud_downsample_dev(o3r_ctx* ctx, const o3r_point** dev_out, size_t* n_out) {
@@ -1291,9 +1378,11 @@ int o3r_cloud_downsample_dev(o3r_ctx* ctx, const o3r_point** dev_out, size_t* n_
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->p.device));
     const float4* res;
-    int rc = cloud_downsample_dev(ctx, &res, n_out);
+    bool pending;
+    int rc = cloud_downsample_dev(ctx, &res, n_out, &pending);
     if (rc) return rc;
-    CU(cudaStreamSynchronize(ctx->st));
+    if (pending) { rc = downsample_finish(ctx, n_out); if (rc) return rc; }
+    else CU(cudaStreamSynchronize(ctx->st));
     if (dev_out) *dev_out = reinterpret_cast<const o3r_point*>(res);
     return O3R_OK;
 }

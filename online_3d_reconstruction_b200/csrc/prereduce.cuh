@@ -34,7 +34,7 @@ struct PrSmem {
     uint16_t base[kPrTile + 1];      // bin b occupies items[base[b], base[b + 1])
     uint16_t tot[kPrTile];           // items per bin
     uint32_t scan[34];
-    uint32_t ticket, out0;
+    uint32_t ticket, out0, nb;
 };
 
 // in:  items [*in_base, *in_base + *in_count) of `vox` (per-frame voxel centroids of the chunk, {x, y, z, 0x00RRGGBB})
@@ -50,18 +50,20 @@ __global__ void __launch_bounds__(kThreads, 5) k_cell_prereduce(const float4* __
     __shared__ PrSmem S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    if (tid == 0) S.ticket = atomicAdd(ticket, 1u);
+    if (tid == 0) { S.ticket = atomicAdd(ticket, 1u); S.nb = 0; }
+    const uint32_t n = *in_count, ibase = *in_base, obase = *out_base;
+    // ---- clear the table (128-bit stores)
+    {
+        uint4* tz = reinterpret_cast<uint4*>(S.u.h.tab);
+#pragma unroll
+        for (int i = 0; i < kPrTab / 2 / kThreads; ++i) tz[i * kThreads + tid] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    }
     __syncthreads();
     const uint32_t t = S.ticket;
-    const uint32_t n = *in_count;
     if (t * kPrTile >= n) return;
     const uint32_t nt = (n + kPrTile - 1) / kPrTile;
     const uint32_t wn = min((uint32_t)kPrTile, n - t * kPrTile);
-    vox += *in_base + t * kPrTile;
-
-    // ---- clear the table
-#pragma unroll
-    for (int i = 0; i < kPrTab / kThreads; ++i) S.u.h.tab[i * kThreads + tid] = kPrEmpty;
+    vox += ibase + t * kPrTile;
     // ---- load: warp w owns items [w*128, w*128 + 128) as 4 rounds of 32 consecutive items
     float4 it[kPrItems];
     unsigned long long key[kPrItems];
@@ -76,8 +78,7 @@ __global__ void __launch_bounds__(kThreads, 5) k_cell_prereduce(const float4* __
             key[r] = abs_cell_key(it[r].x, it[r].y, it[r].z, icx, icx, icz);
         }
     }
-    __syncthreads();
-    // ---- one table slot per distinct cell
+    // ---- one table slot per distinct cell; whoever creates the slot numbers the bin
 #pragma unroll
     for (int r = 0; r < kPrItems; ++r) {
         slot[r] = 0;
@@ -87,25 +88,15 @@ __global__ void __launch_bounds__(kThreads, 5) k_cell_prereduce(const float4* __
             h >>= 32 - 11;   // kPrTab = 2048
             for (;;) {
                 const unsigned long long old = atomicCAS(&S.u.h.tab[h], kPrEmpty, k);
-                if (old == kPrEmpty || old == k) break;
+                if (old == kPrEmpty) { S.u.h.dense[h] = (uint16_t)atomicAdd(&S.nb, 1u); break; }
+                if (old == k) break;
                 h = (h + 1) & (kPrTab - 1);
             }
             slot[r] = h;
         }
     }
     __syncthreads();
-    // ---- dense bin ids in table order
-    uint32_t nb;
-    {
-        constexpr int E = kPrTab / kThreads;   // 8 entries per thread
-        uint32_t occ = 0;
-#pragma unroll
-        for (int j = 0; j < E; ++j) occ += S.u.h.tab[tid * E + j] != kPrEmpty;
-        uint32_t o = block_excl_scan(occ, S.scan, nb);
-#pragma unroll
-        for (int j = 0; j < E; ++j)
-            if (S.u.h.tab[tid * E + j] != kPrEmpty) S.u.h.dense[tid * E + j] = (uint16_t)o++;
-    }
+    const uint32_t nb = S.nb;
     // publish the tile's record count early: the successors' look-back rarely has to wait
     if (tid == 0) st_volatile_u32(status + t, (t == 0 ? kStGlobal : kStLocal) | nb);
     // the counters of the live bins (and of the stand-in bin of lanes without an item)
@@ -181,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 5) k_cell_prereduce(const float4* __
         }
     }
     __syncthreads();
-    out += *out_base + S.out0;
+    out += obase + S.out0;
     // ---- one thread per bin: left fold in tile order
     for (uint32_t b = tid; b < nb; b += kThreads) {
         const uint32_t a = S.base[b], e = S.base[b + 1];

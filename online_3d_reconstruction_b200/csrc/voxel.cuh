@@ -946,8 +946,10 @@ __global__ void k_acc_finish(uint32_t* n_res, const uint32_t* n_new) {
 }
 
 // downsamplePtCloud(cloud_big, true) on the accumulators: count >= min_points -> centroid, z -= 500
-__global__ void __launch_bounds__(kThreads) k_acc_emit_cnt(uint32_t n_res, const float4* __restrict__ res_acc,
+// (launched over an upper bound of the resident cell count; the exact count is read from the device)
+__global__ void __launch_bounds__(kThreads) k_acc_emit_cnt(const uint32_t* __restrict__ n_res_ptr, const float4* __restrict__ res_acc,
                                                            uint32_t min_points, uint32_t* __restrict__ cnt) {
+    const uint32_t n_res = *n_res_ptr;
     const uint32_t t = blockIdx.x;
     uint32_t c = 0;
 #pragma unroll
@@ -964,10 +966,11 @@ __global__ void __launch_bounds__(kThreads) k_acc_emit_cnt(uint32_t n_res, const
     if (threadIdx.x == 0) cnt[t] = s_c;
 }
 
-__global__ void __launch_bounds__(kThreads) k_acc_emit(uint32_t n_res, const float4* __restrict__ res_acc,
+__global__ void __launch_bounds__(kThreads) k_acc_emit(const uint32_t* __restrict__ n_res_ptr, const float4* __restrict__ res_acc,
                                                        const uint4* __restrict__ res_rgb, uint32_t min_points,
                                                        const uint32_t* __restrict__ off, float4* __restrict__ out) {
     __shared__ uint32_t s_scan[34];
+    const uint32_t n_res = *n_res_ptr;
     const uint32_t t = blockIdx.x;
     uint32_t flags = 0;
 #pragma unroll
