@@ -55,7 +55,7 @@ struct Pose {
            imageNumbersFile = "images/image_numbers.txt";
     string imagePrefix = "images/", disparityPrefix = "disparities/", segmentlblPrefix = "segmentlabels/";
     string folder = "output/", pose_corrections_file;
-    int blur_mode = O3R_BLUR_MEDIAN, device = 0;
+    int blur_mode = O3R_BLUR_BILATERAL, device = 0;   // the reference's live filter (pose_functions.cpp:1044)
     double Q[16] = {0};
     vector<RawImageData> rawImageDataVec;
     data_t pose_data, images_times_data;
@@ -84,7 +84,7 @@ void Pose::printUsage() {
             "      --only_MAVLink --dont_icp --preview --log 0/1 --downsample <file.ply>\n"
             "  path overrides (the reference hard-codes these, pose.h:129-137): --data_root DIR --image_prefix P\n"
             "      --disparity_prefix P --segmentlbl_prefix P --output DIR --calib FILE\n"
-            "  extensions: --blur_mode median|box --pose_corrections FILE --device N\n"
+            "  extensions: --blur_mode bilateral|median|box (default bilateral = the reference) --pose_corrections FILE --device N\n"
             "  not in this driver (host-side tools of the reference): --visualize --align_point_cloud --smooth_surface\n"
             "      --mesh_surface --segment_cloud --segment_cloud_only --displayUAVPositions\n";
 }
@@ -133,7 +133,7 @@ int Pose::parseCmdArgs(int argc, char** argv) {
         else if (a == "--calib") calib_file = need("file");
         else if (a == "--pose_corrections") pose_corrections_file = need("file");
         else if (a == "--device") device = atoi(need("n"));
-        else if (a == "--blur_mode") { const string m = need("mode"); blur_mode = (m == "box") ? O3R_BLUR_BOX : O3R_BLUR_MEDIAN; }
+        else if (a == "--blur_mode") { const string m = need("mode"); blur_mode = (m == "box") ? O3R_BLUR_BOX : (m == "median") ? O3R_BLUR_MEDIAN : O3R_BLUR_BILATERAL; }
         else {
             cout << atoi(argv[i]) << endl;
             if (first_img_num == -1) first_img_num = atoi(argv[i]); else last_img_num = atoi(argv[i]);

@@ -49,8 +49,9 @@ typedef struct o3r_point {
 enum { O3R_DISP_U8 = 0, O3R_DISP_U16 = 1, O3R_DISP_F32 = 2, O3R_DISP_F64 = 3 };
 
 /* blur applied when blur_kernel > 1 (pose_functions.cpp:1040-1047).  The reference's live filter is
- * cv::bilateralFilter (not built yet); north_star names median and box. */
-enum { O3R_BLUR_MEDIAN = 0, O3R_BLUR_BOX = 1 };
+ * cv::bilateralFilter(src, dst, k, 2k, k/2) (pose_functions.cpp:1044, integer k/2); north_star names median
+ * (the commented alternative at :1045) and box. */
+enum { O3R_BLUR_MEDIAN = 0, O3R_BLUR_BOX = 1, O3R_BLUR_BILATERAL = 2 };
 
 /* how the global cloud is kept */
 enum {

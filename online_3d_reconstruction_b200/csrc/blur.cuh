@@ -122,4 +122,65 @@ __global__ void __launch_bounds__(kBlurRows) k_blur(const BlurJob* __restrict__ 
     }
 }
 
+// ---- cv::bilateralFilter(u8, d = k, sigmaColor = 2k, sigmaSpace = k/2): the reference's LIVE blur (pose_functions.cpp:1044)
+// OpenCV 3.1 bilateralFilter_8u: BORDER_REFLECT_101 halo, circular tap mask of radius k/2 walked row-major, weight =
+// space_weight[tap] * color_weight[|v - v0|] (float LUTs computed on the host with std::exp, exactly like OpenCV
+// and the oracle do), two sequential float accumulations per pixel, round-half-even(sum / wsum).  No FMA: the products
+// and sums are rounded one by one in the tap order, so the result equals the CPU loop bit for bit.
+// One CTA = 32 x 8 outputs, one output per thread; the tile + halo, both LUTs and the per-row tap extents sit in
+// shared memory (the colour LUT is read at data-dependent indices: shared memory, not constant memory).
+constexpr int kBilTX = 32, kBilTY = 8;
+
+struct BilateralLut {       // device copies, built once per context
+    const float* color_w;   // [256]
+    const float* space_w;   // [maxk] in tap order
+    const int* jmax;        // [2 * radius + 1]: taps of row i are j in [-jmax, jmax]
+    int radius, maxk;
+};
+
+inline size_t bilateral_smem(int radius, int maxk) {
+    const int tw = kBilTX + 2 * radius, th = kBilTY + 2 * radius;
+    size_t s = ((size_t)tw * th + 15) & ~(size_t)15;
+    return s + (size_t)256 * 4 + (size_t)maxk * 4 + (size_t)(2 * radius + 1) * 4;
+}
+
+__global__ void __launch_bounds__(kBilTX * kBilTY) k_bilateral(const BlurJob* __restrict__ jobs, BilateralLut L, int rows,
+                                                               int cols, int rx0, int ry0, int rx1, int ry1) {
+    extern __shared__ __align__(16) unsigned char bsm[];
+    const BlurJob job = jobs[blockIdx.z];
+    const int r = L.radius, tw = kBilTX + 2 * r, th = kBilTY + 2 * r;
+    unsigned char* tin = bsm;
+    float* cw = reinterpret_cast<float*>(bsm + (((size_t)tw * th + 15) & ~(size_t)15));
+    float* sw = cw + 256;
+    int* jm = reinterpret_cast<int*>(sw + L.maxk);
+    const int tid = threadIdx.y * kBilTX + threadIdx.x, nthr = kBilTX * kBilTY;
+    const int bx = rx0 + blockIdx.x * kBilTX, by = ry0 + blockIdx.y * kBilTY;
+    for (int i = tid; i < tw * th; i += nthr) {
+        const int ly = i / tw, lx = i - ly * tw;
+        tin[i] = job.src[(size_t)dev_reflect101(by - r + ly, rows) * job.sstep + dev_reflect101(bx - r + lx, cols)];
+    }
+    for (int i = tid; i < 256; i += nthr) cw[i] = L.color_w[i];
+    for (int i = tid; i < L.maxk; i += nthr) sw[i] = L.space_w[i];
+    for (int i = tid; i < 2 * r + 1; i += nthr) jm[i] = L.jmax[i];
+    __syncthreads();
+    const int gx = bx + threadIdx.x, gy = by + threadIdx.y;
+    if (gx >= rx1 || gy >= ry1) return;
+    const unsigned char* c0 = tin + (threadIdx.y + r) * tw + threadIdx.x + r;
+    const int v0 = *c0;
+    float sum = 0.f, wsum = 0.f;
+    int k = 0;
+    for (int i = -r; i <= r; ++i) {
+        const int m = jm[i + r];
+        const unsigned char* row = c0 + i * tw;
+#pragma unroll 4
+        for (int j = -m; j <= m; ++j, ++k) {
+            const int v = row[j];
+            const float w = __fmul_rn(sw[k], cw[abs(v - v0)]);
+            sum = __fadd_rn(sum, __fmul_rn((float)v, w));
+            wsum = __fadd_rn(wsum, w);
+        }
+    }
+    job.dst[(size_t)gy * job.dstep + gx] = (unsigned char)__float2int_rn(__fdiv_rn(sum, wsum));
+}
+
 }  // namespace o3r

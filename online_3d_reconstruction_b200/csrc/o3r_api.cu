@@ -114,6 +114,8 @@ struct o3r_ctx {
     }
     DevBuf d_disp;   // scratch plane of o3r_blur_u8
     DevBuf d_frames, d_blur, d_blurjobs;
+    DevBuf bil_lut;            // bilateral LUTs (colour weights, space weights, per-row tap extents) of bil_kernel
+    int bil_kernel = -1, bil_radius = 0, bil_maxk = 0;
     // per-batch work buffers
     DevBuf tile_cnt, tile_off, bbox, frame_off, grids, counters, pts, sortbuf, hist, plan_all, plan_v2, ghist;
     DevBuf head_cnt, head_off, vox, vox_off, seg2, tmat, mask, runwork, spts;
@@ -236,6 +238,42 @@ inline size_t disp_elem(int t) { return t == O3R_DISP_U8 ? 1 : t == O3R_DISP_U16
 int read_counters(o3r_ctx* ctx) {
     CU(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
+    return O3R_OK;
+}
+
+// LUTs of cv::bilateralFilter(src, dst, d = k, sigmaColor = 2k, sigmaSpace = k/2) (pose_functions.cpp:1044), computed on the
+// host with std::exp exactly as OpenCV 3.1 bilateralFilter_8u (and the oracle) do, cached per kernel size.
+int bilateral_lut(o3r_ctx* ctx, int k, BilateralLut* out) {
+    if (ctx->bil_kernel != k) {
+        double sigma_color = (double)(k * 2), sigma_space = (double)(k / 2);
+        if (sigma_color <= 0) sigma_color = 1;
+        if (sigma_space <= 0) sigma_space = 1;
+        const double gc = -0.5 / (sigma_color * sigma_color), gs = -0.5 / (sigma_space * sigma_space);
+        const int radius = std::max(k <= 0 ? (int)std::lrint(sigma_space * 1.5) : k / 2, 1);
+        std::vector<float> buf(256);
+        for (int i = 0; i < 256; ++i) buf[i] = (float)std::exp(i * i * gc);
+        std::vector<int> jm(2 * radius + 1, -1);
+        for (int i = -radius; i <= radius; ++i)
+            for (int j = -radius; j <= radius; ++j) {
+                const double r = std::sqrt((double)i * i + (double)j * j);
+                if (r > radius) continue;
+                buf.push_back((float)std::exp(r * r * gs));
+                jm[i + radius] = std::max(jm[i + radius], j);   // the mask is symmetric in j
+            }
+        const int maxk = (int)buf.size() - 256;
+        const size_t bytes = buf.size() * 4 + jm.size() * 4;
+        std::vector<unsigned char> blob(bytes);
+        memcpy(blob.data(), buf.data(), buf.size() * 4);
+        memcpy(blob.data() + buf.size() * 4, jm.data(), jm.size() * 4);
+        CU(ctx->bil_lut.ensure(bytes));
+        { int rcu = upload_small(ctx, ctx->bil_lut.p, blob.data(), bytes); if (rcu) return rcu; }
+        ctx->bil_kernel = k; ctx->bil_radius = radius; ctx->bil_maxk = maxk;
+        CU(cudaFuncSetAttribute(k_bilateral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bilateral_smem(radius, maxk)));
+    }
+    out->color_w = ctx->bil_lut.as<float>();
+    out->space_w = out->color_w + 256;
+    out->jmax = reinterpret_cast<const int*>(out->space_w + ctx->bil_maxk);
+    out->radius = ctx->bil_radius; out->maxk = ctx->bil_maxk;
     return O3R_OK;
 }
 
@@ -686,7 +724,7 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
             return ctx->fail(O3R_ERR_INVALID, "blur_kernel > 1 requires u8 disparity (OpenCV rejects CV_64F)");
         if (p.blur_mode == O3R_BLUR_MEDIAN && (p.blur_kernel & 1) == 0)
             return ctx->fail(O3R_ERR_INVALID, "median blur needs an odd blur_kernel (cv::medianBlur asserts)");
-        if (p.blur_mode != O3R_BLUR_MEDIAN && p.blur_mode != O3R_BLUR_BOX)
+        if (p.blur_mode != O3R_BLUR_MEDIAN && p.blur_mode != O3R_BLUR_BOX && p.blur_mode != O3R_BLUR_BILATERAL)
             return ctx->fail(O3R_ERR_INVALID, "unknown blur_mode");
         if (p.blur_kernel > kBlurMaxK) return ctx->fail(O3R_ERR_INVALID, "blur_kernel too large (max 127)");
     }
@@ -856,7 +894,13 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
                 const dim3 g(cdiv(rx1 - rx0, kBlurStrip), cdiv(ry1 - ry0, kBlurRows), nc);
                 const size_t sm = blur_smem(p.blur_kernel, p.blur_mode);
                 const BlurJob* bj = ctx->d_blurjobs.as<BlurJob>() + f0;
-                if (p.blur_mode == O3R_BLUR_MEDIAN)
+                if (p.blur_mode == O3R_BLUR_BILATERAL) {
+                    BilateralLut L;
+                    int rcl = bilateral_lut(ctx, p.blur_kernel, &L);
+                    if (rcl) return rcl;
+                    const dim3 gb(cdiv(rx1 - rx0, kBilTX), cdiv(ry1 - ry0, kBilTY), nc);
+                    LAUNCH(k_bilateral, gb, dim3(kBilTX, kBilTY), bilateral_smem(L.radius, L.maxk), bj, L, p.rows, p.cols, rx0, ry0, rx1, ry1);
+                } else if (p.blur_mode == O3R_BLUR_MEDIAN)
                     LAUNCH_N("k_blur_median", (k_blur<O3R_BLUR_MEDIAN>), g, kBlurRows, sm, bj, p.rows, p.cols, p.blur_kernel, rx0, ry0, rx1, ry1);
                 else
                     LAUNCH_N("k_blur_box", (k_blur<O3R_BLUR_BOX>), g, kBlurRows, sm, bj, p.rows, p.cols, p.blur_kernel, rx0, ry0, rx1, ry1);
@@ -1062,7 +1106,7 @@ void o3r_destroy(o3r_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->lut_r, &ctx->lut_z, &ctx->d_disp, &ctx->stg[0].disp, &ctx->stg[0].bgr, &ctx->stg[0].labels,
                       &ctx->stg[0].coef, &ctx->stg[0].kp, &ctx->stg[1].disp, &ctx->stg[1].bgr, &ctx->stg[1].labels,
                       &ctx->stg[1].coef, &ctx->stg[1].kp,
-                      &ctx->d_frames, &ctx->d_blur, &ctx->d_blurjobs, &ctx->tile_cnt, &ctx->tile_off, &ctx->bbox,
+                      &ctx->d_frames, &ctx->d_blur, &ctx->d_blurjobs, &ctx->bil_lut, &ctx->tile_cnt, &ctx->tile_off, &ctx->bbox,
                       &ctx->frame_off, &ctx->grids, &ctx->counters, &ctx->pts, &ctx->sortbuf, &ctx->hist,
                       &ctx->plan_all, &ctx->plan_v2, &ctx->ghist, &ctx->head_cnt, &ctx->head_off, &ctx->vox,
                       &ctx->vox_off, &ctx->seg2, &ctx->tmat, &ctx->mask, &ctx->runwork, &ctx->spts, &ctx->res_keys[0], &ctx->res_keys[1],
@@ -1426,7 +1470,8 @@ int o3r_blur_u8(o3r_ctx* ctx, const uint8_t* src, size_t src_step, int rows, int
     if (kernel < 1 || kernel > kBlurMaxK) return ctx->fail(O3R_ERR_INVALID, "kernel must be in 1..127");
     if (mode == O3R_BLUR_MEDIAN && (kernel & 1) == 0)
         return ctx->fail(O3R_ERR_INVALID, "median blur needs an odd kernel (cv::medianBlur asserts)");
-    if (mode != O3R_BLUR_MEDIAN && mode != O3R_BLUR_BOX) return ctx->fail(O3R_ERR_INVALID, "unknown blur mode");
+    if (mode != O3R_BLUR_MEDIAN && mode != O3R_BLUR_BOX && mode != O3R_BLUR_BILATERAL)
+        return ctx->fail(O3R_ERR_INVALID, "unknown blur mode");
     const size_t step = ((size_t)cols + 15) & ~(size_t)15, plane = step * rows;
     CU(ctx->d_disp.ensure(plane));
     CU(ctx->d_blur.ensure(plane));
@@ -1436,7 +1481,13 @@ int o3r_blur_u8(o3r_ctx* ctx, const uint8_t* src, size_t src_step, int rows, int
     CU(cudaMemcpyAsync(ctx->d_blurjobs.p, &job, sizeof(job), cudaMemcpyHostToDevice, ctx->st));
     const dim3 g(cdiv(cols, kBlurStrip), cdiv(rows, kBlurRows), 1);
     const size_t sm = blur_smem(kernel, mode);
-    if (mode == O3R_BLUR_MEDIAN)
+    if (mode == O3R_BLUR_BILATERAL) {
+        BilateralLut L;
+        int rcl = bilateral_lut(ctx, kernel, &L);
+        if (rcl) return rcl;
+        const dim3 gb(cdiv(cols, kBilTX), cdiv(rows, kBilTY), 1);
+        LAUNCH(k_bilateral, gb, dim3(kBilTX, kBilTY), bilateral_smem(L.radius, L.maxk), ctx->d_blurjobs.as<BlurJob>(), L, rows, cols, 0, 0, cols, rows);
+    } else if (mode == O3R_BLUR_MEDIAN)
         LAUNCH_N("k_blur_median", (k_blur<O3R_BLUR_MEDIAN>), g, kBlurRows, sm, ctx->d_blurjobs.as<BlurJob>(), rows, cols, kernel, 0, 0, cols, rows);
     else
         LAUNCH_N("k_blur_box", (k_blur<O3R_BLUR_BOX>), g, kBlurRows, sm, ctx->d_blurjobs.as<BlurJob>(), rows, cols, kernel, 0, 0, cols, rows);

@@ -324,13 +324,26 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? 4 : 3) k_rs_ones
                 if ((uint32_t)(b0 + q) >= nb) continue;
                 uint32_t real = run[q];
                 if ((uint32_t)(b0 + q) == nb - 1u) real -= (kRsTile - ntile);
+                // The tiles of a segment start together, so most predecessors are still LOCAL when a tile looks back and
+                // the walk is long: kLb status words are loaded per step (independent loads, one L2 round trip).
+                constexpr int kLb = 8;
                 const uint32_t* pst = st + q - kRsBins;
                 uint32_t pf = 0;
-                for (uint32_t back = t; back > 0; --back, pst -= kRsBins) {
-                    uint32_t v;
-                    while (((v = ld_volatile_u32(pst)) >> 30) == 0u) __nanosleep(32);
-                    pf += v & kStMask;
-                    if ((v >> 30) == 2u) break;
+                bool done = false;
+                for (uint32_t back = t; back > 0 && !done;) {
+                    const uint32_t m = min(back, (uint32_t)kLb);
+                    uint32_t v[kLb];
+#pragma unroll
+                    for (int j = 0; j < kLb; ++j) v[j] = (uint32_t)j < m ? ld_volatile_u32(pst - (size_t)j * kRsBins) : kStGlobal;
+#pragma unroll
+                    for (int j = 0; j < kLb; ++j) {
+                        if (done) continue;
+                        while ((v[j] >> 30) == 0u) { __nanosleep(32); v[j] = ld_volatile_u32(pst - (size_t)j * kRsBins); }
+                        pf += v[j] & kStMask;
+                        if ((v[j] >> 30) == 2u) done = true;
+                    }
+                    back -= m;
+                    pst -= (size_t)m * kRsBins;
                 }
                 prefix[q] = pf;
                 st_volatile_u32(st + q, kStGlobal | (pf + real));

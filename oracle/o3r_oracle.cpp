@@ -82,6 +82,61 @@ void box_u8(const uint8_t* src, size_t sstep, int rows, int cols, int k, uint8_t
     }
 }
 
+/* cv::bilateralFilter(u8, d, sigmaColor, sigmaSpace), OpenCV 3.1.0 modules/imgproc/src/smooth.cpp bilateralFilter_8u
+ * (third-party, not under /root/reference; call site pose_functions.cpp:1044 with d = k, sigmaColor = 2k,
+ * sigmaSpace = k/2 in integer division).  BORDER_REFLECT_101 halo, circular tap mask in row-major (i, j) order,
+ * float LUTs (float)std::exp(.), per pixel two sequential float accumulations (the 3.1 SSE path vectorises across
+ * pixels, so each pixel still sums its taps in this order), cvRound(sum / wsum) = round-half-even.  cn = 1 or 3. */
+void bilateral_u8(const uint8_t* src, size_t sstep, int rows, int cols, int cn, int d, double sigma_color,
+                  double sigma_space, uint8_t* dst, size_t dstep) {
+    if (sigma_color <= 0) sigma_color = 1;
+    if (sigma_space <= 0) sigma_space = 1;
+    const double gauss_color_coeff = -0.5 / (sigma_color * sigma_color);
+    const double gauss_space_coeff = -0.5 / (sigma_space * sigma_space);
+    int radius = d <= 0 ? (int)std::lrint(sigma_space * 1.5) : d / 2;
+    radius = radius < 1 ? 1 : radius;
+    std::vector<float> color_weight((size_t)cn * 256);
+    for (int i = 0; i < 256 * cn; ++i) color_weight[i] = (float)std::exp(i * i * gauss_color_coeff);
+    std::vector<float> sw;
+    std::vector<int> oi, oj;
+    for (int i = -radius; i <= radius; ++i)
+        for (int j = -radius; j <= radius; ++j) {
+            const double r = std::sqrt((double)i * i + (double)j * j);
+            if (r > radius) continue;
+            sw.push_back((float)std::exp(r * r * gauss_space_coeff));
+            oi.push_back(i); oj.push_back(j);
+        }
+    const size_t maxk = sw.size();
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x) {
+            const uint8_t* c0 = src + (size_t)y * sstep + (size_t)x * cn;
+            if (cn == 1) {
+                float sum = 0.f, wsum = 0.f;
+                const int val0 = c0[0];
+                for (size_t k = 0; k < maxk; ++k) {
+                    const int val = src[(size_t)reflect101(y + oi[k], rows) * sstep + reflect101(x + oj[k], cols)];
+                    const float w = sw[k] * color_weight[std::abs(val - val0)];
+                    sum += val * w;
+                    wsum += w;
+                }
+                dst[(size_t)y * dstep + x] = (uint8_t)std::lrintf(sum / wsum);
+            } else {
+                float sb = 0.f, sg = 0.f, sr = 0.f, wsum = 0.f;
+                const int b0 = c0[0], g0 = c0[1], r0 = c0[2];
+                for (size_t k = 0; k < maxk; ++k) {
+                    const uint8_t* q = src + (size_t)reflect101(y + oi[k], rows) * sstep + (size_t)reflect101(x + oj[k], cols) * 3;
+                    const int b = q[0], g = q[1], r = q[2];
+                    const float w = sw[k] * color_weight[std::abs(b - b0) + std::abs(g - g0) + std::abs(r - r0)];
+                    sb += b * w; sg += g * w; sr += r * w;
+                    wsum += w;
+                }
+                wsum = 1.f / wsum;
+                uint8_t* o = dst + (size_t)y * dstep + (size_t)x * 3;
+                o[0] = (uint8_t)std::lrintf(sb * wsum); o[1] = (uint8_t)std::lrintf(sg * wsum); o[2] = (uint8_t)std::lrintf(sr * wsum);
+            }
+        }
+}
+
 struct DispReader {
     const o3r_params* p;
     const o3r_frame* f;
@@ -185,9 +240,18 @@ int orc_blur_u8(const uint8_t* src, size_t src_step, int rows, int cols, int ker
         median_u8(src, src_step, rows, cols, kernel, dst, dst_step);
     } else if (mode == O3R_BLUR_BOX) {
         box_u8(src, src_step, rows, cols, kernel, dst, dst_step);
+    } else if (mode == O3R_BLUR_BILATERAL) { /* pose_functions.cpp:1044: bilateralFilter(src, dst, k, k*2, k/2) */
+        bilateral_u8(src, src_step, rows, cols, 1, kernel, (double)(kernel * 2), (double)(kernel / 2), dst, dst_step);
     } else {
         return O3R_ERR_INVALID;
     }
+    return O3R_OK;
+}
+
+int orc_bilateral_u8(const uint8_t* src, size_t src_step, int rows, int cols, int cn, int d, double sigma_color,
+                     double sigma_space, uint8_t* dst, size_t dst_step) {
+    if (!src || !dst || rows <= 0 || cols <= 0 || (cn != 1 && cn != 3)) return O3R_ERR_INVALID;
+    bilateral_u8(src, src_step, rows, cols, cn, d, sigma_color, sigma_space, dst, dst_step);
     return O3R_OK;
 }
 

@@ -27,6 +27,11 @@ extern "C" {
 int orc_blur_u8(const uint8_t* src, size_t src_step, int rows, int cols, int kernel, int mode,
                 uint8_t* dst, size_t dst_step);
 
+/* cv::bilateralFilter on a u8 image with cn = 1 or 3 interleaved channels (OpenCV 3.1 bilateralFilter_8u);
+ * used to pin the model on the reference's own build/output/bilateralFiltered_15.png (cn = 3). */
+int orc_bilateral_u8(const uint8_t* src, size_t src_step, int rows, int cols, int cn, int d, double sigma_color,
+                     double sigma_space, uint8_t* dst, size_t dst_step);
+
 /* createSingleImgPtCloud  pose_functions.cpp:1030-1134.  Camera-frame points (before transform).
  * mask (optional) gets 1 byte per scanned grid sample, *n_scanned the number of samples. */
 int orc_create_single_img_pt_cloud(const o3r_params* p, const o3r_frame* f, int disp_type,

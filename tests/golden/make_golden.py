@@ -7,6 +7,7 @@ Sources (relative to /root/reference/build):
   disparities/{1248,1249,1251}.png, segmentlabels/{same}.png, images/1248.png  real 1280x720 frames
   output/log.txt:39-46,64          valid-pixel counts + variances the reference logged for them
   output/medianBlurred_{15,31}.png cv::medianBlur outputs of images/1248.png written by the reference
+  output/bilateralFiltered_{15,31}.png cv::bilateralFilter(img, k, 2k, k/2) outputs written by the reference
   cloud.ply                        a combined-grid VoxelGrid output of the reference (voxel_size 0.05)
 Decoding PNGs needs cv2 (present in the build container only).
 """
@@ -40,6 +41,17 @@ def main():
                         out15=m15[:160, :240, 1].copy(), out31=m31[:160, :240, 1].copy(),
                         src_br=img[-200:, -280:, 2].copy(),     # bottom-right corner, red channel
                         out15_br=m15[-160:, -240:, 2].copy(), out31_br=m31[-160:, -240:, 2].copy())
+    # --- bilateral filter: crops of the reference's own outputs (cv::bilateralFilter(img, k, 2k, k/2), 3 channels),
+    #     and a cn = 1 case (a real disparity crop) filtered by this container's cv2 (the reference call, pose_functions.cpp:1044)
+    b15 = cv2.imread(R + "output/bilateralFiltered_15.png")
+    b31 = cv2.imread(R + "output/bilateralFiltered_31.png")
+    d1248 = cv2.imread(R + "disparities/1248.png", cv2.IMREAD_GRAYSCALE)
+    dcrop = d1248[300:460, 500:740].copy()
+    np.savez_compressed(os.path.join(OUT, "bilateral_ref.npz"),
+                        src=img[:200, :280].copy(),             # BGR input crop (top-left corner: border + halo)
+                        out15=b15[:160, :240].copy(), out31=b31[:160, :240].copy(),
+                        disp=dcrop, disp_cv2_k5=cv2.bilateralFilter(dcrop, 5, 10, 2),
+                        disp_cv2_k30=cv2.bilateralFilter(dcrop, 30, 60, 15), cv2_version=np.array(cv2.__version__))
     # --- cloud.ply vertices ---
     raw = open(R + "cloud.ply", "rb").read()
     h = raw.index(b"end_header\n") + len(b"end_header\n")

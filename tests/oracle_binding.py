@@ -29,6 +29,7 @@ def lib():
         P, F = C.POINTER(abi.Params), C.POINTER(abi.Frame)
         vp, sz, szp = C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)
         L.orc_blur_u8.argtypes = [vp, sz, C.c_int, C.c_int, C.c_int, C.c_int, vp, sz]
+        L.orc_bilateral_u8.argtypes = [vp, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp, sz]
         L.orc_create_single_img_pt_cloud.argtypes = [P, F, C.c_int, vp, sz, szp, vp, sz, szp]
         L.orc_transform_pt_cloud.argtypes = [vp, sz, C.POINTER(C.c_float), vp]
         L.orc_transform_pt_cloud.restype = None
@@ -59,6 +60,16 @@ def blur_u8(src, kernel, mode):
     dst = np.empty_like(src)
     _check(lib().orc_blur_u8(src.ctypes.data, src.strides[0], src.shape[0], src.shape[1], kernel, mode,
                              dst.ctypes.data, dst.strides[0]), "blur")
+    return dst
+
+
+def bilateral_u8(src, d, sigma_color, sigma_space):
+    """cv::bilateralFilter on a (rows, cols) or (rows, cols, 3) u8 image."""
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    cn = 1 if src.ndim == 2 else src.shape[2]
+    dst = np.empty_like(src)
+    _check(lib().orc_bilateral_u8(src.ctypes.data, src.strides[0], src.shape[0], src.shape[1], cn, d, float(sigma_color),
+                                  float(sigma_space), dst.ctypes.data, dst.strides[0]), "bilateral")
     return dst
 
 

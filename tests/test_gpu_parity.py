@@ -201,7 +201,9 @@ def test_voxel_grid_reproduces_reference_cloud_ply(golden_dir):
 
 # ------------------------------------------------------------------------------------------------- blur
 @pytest.mark.parametrize("mode,k", [(abi.BLUR_MEDIAN, 3), (abi.BLUR_MEDIAN, 15), (abi.BLUR_MEDIAN, 31),
-                                    (abi.BLUR_BOX, 2), (abi.BLUR_BOX, 5), (abi.BLUR_BOX, 30), (abi.BLUR_BOX, 31)])
+                                    (abi.BLUR_BOX, 2), (abi.BLUR_BOX, 5), (abi.BLUR_BOX, 30), (abi.BLUR_BOX, 31),
+                                    (abi.BLUR_BILATERAL, 2), (abi.BLUR_BILATERAL, 5), (abi.BLUR_BILATERAL, 30),
+                                    (abi.BLUR_BILATERAL, 31), (abi.BLUR_BILATERAL, 101)])
 def test_blur_plane_bit_exact(mode, k):
     rng = np.random.default_rng(k)
     src = synth.make_frame_images(rng, 150, 210)[0]
@@ -219,7 +221,19 @@ def test_blur_matches_reference_median_outputs(golden_dir):
             assert np.array_equal(P.blur(g["src_br"], k, abi.BLUR_MEDIAN)[-160:, -240:], g[f"out{k}_br"])
 
 
-@pytest.mark.parametrize("mode,k,J", [(abi.BLUR_MEDIAN, 7, 1), (abi.BLUR_BOX, 6, 1), (abi.BLUR_MEDIAN, 5, 4)])
+def test_bilateral_on_real_disparity_matches_oracle_and_cv2(golden_dir):
+    """The reference's live filter (pose_functions.cpp:1044) on a real 8-bit disparity crop: bit-exact against the
+    oracle, and equal to cv2.bilateralFilter at the README's k = 30 (committed fixture)."""
+    g = np.load(os.path.join(golden_dir, "bilateral_ref.npz"))
+    with Pose(abi.make_params(**SMALL)) as P:
+        for k in (5, 30):
+            got = P.blur(g["disp"], k, abi.BLUR_BILATERAL)
+            assert np.array_equal(got, ob.blur_u8(g["disp"], k, abi.BLUR_BILATERAL))
+        assert np.array_equal(got, g["disp_cv2_k30"])   # (k = 5 ties break differently under OpenCV 4.x's FMA)
+
+
+@pytest.mark.parametrize("mode,k,J", [(abi.BLUR_MEDIAN, 7, 1), (abi.BLUR_BOX, 6, 1), (abi.BLUR_MEDIAN, 5, 4),
+                                      (abi.BLUR_BILATERAL, 30, 1), (abi.BLUR_BILATERAL, 9, 3)])
 def test_blurred_frame_cloud(mode, k, J):
     keep = []
     p = abi.make_params(jump_pixels=J, voxel_size=0.05, blur_kernel=k, blur_mode=mode, **SMALL4)
