@@ -195,6 +195,23 @@ int o3r_voxel_grid(o3r_ctx* ctx, const o3r_point* pts, size_t n, float lx, float
 int o3r_blur_u8(o3r_ctx* ctx, const uint8_t* src, size_t src_step, int rows, int cols,
                 int kernel, int mode, uint8_t* dst, size_t dst_step);
 
+/* ---- pre-pass: the per-frame reductions in front of the hot path --------------------------- */
+
+/* Replaces: double Pose::getVariance(Mat disp_img, false) (pose_functions.cpp:1007-1028, with getMean :987-1005):
+ * the bad-frame gate of the accept loop (pose.cpp:187-196 rejects a frame whose variance is > 5).  The reference's
+ * formula is kept as written: sums run over the VALID ROI samples (disp > min_disparity) but are divided by ALL ROI
+ * samples (minus one for the variance).  u8 disparity, host pointer. */
+int o3r_disp_variance(o3r_ctx* ctx, const uint8_t* disp, size_t disp_step, double* variance);
+
+/* Replaces: void Pose::createPlaneFittedDisparityImages(int) (pose_functions.cpp:900-985): for every segment label
+ * 1, 2, ... (until the first label that does not occur, :923) the least-squares plane d = a*x + b*y + c over the
+ * label's pixels strictly inside the ROI (:929), solved as inv_SVD(AtA) * At * b (:957-965).  coef receives
+ * [n_planes][3] doubles (coef_cap = planes it can hold, 255 suffices for 8-bit labels); a label without ROI pixels
+ * keeps (0, 0, 0) (:939-940).  The result is what o3r_frame.plane_coef takes.  If variance != NULL it receives
+ * getVariance(plane-fitted image, true) (:973); the reference throws when it exceeds 3 (:975-982). */
+int o3r_plane_fit(o3r_ctx* ctx, const uint8_t* labels, size_t labels_step, const uint8_t* disp, size_t disp_step,
+                  double* coef, int coef_cap, int* n_planes, double* variance);
+
 /* Per-pixel validity mask of the grid scan (1 byte per scanned pixel, row-major over the ROI
  * samples) for one frame — the bit-exact mask contract of north_star. Host pointers. */
 int o3r_frame_mask(o3r_ctx* ctx, const o3r_frame* frame, int disp_type,

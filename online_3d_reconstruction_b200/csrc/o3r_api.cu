@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -13,6 +14,7 @@
 
 #include "blur.cuh"
 #include "common.cuh"
+#include "prepass.cuh"
 #include "prereduce.cuh"
 #include "sort.cuh"
 #include "stage_a.cuh"
@@ -114,6 +116,7 @@ struct o3r_ctx {
     }
     DevBuf d_disp;   // scratch plane of o3r_blur_u8
     DevBuf d_frames, d_blur, d_blurjobs;
+    DevBuf pp_labels, pp_disp, pp_sums, pp_rows, pp_coef;   // pre-pass scratch (plane fit / variance gate)
     DevBuf bil_lut;            // bilateral LUTs (colour weights, space weights, per-row tap extents) of bil_kernel
     int bil_kernel = -1, bil_radius = 0, bil_maxk = 0;
     // per-batch work buffers
@@ -1106,7 +1109,8 @@ void o3r_destroy(o3r_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->lut_r, &ctx->lut_z, &ctx->d_disp, &ctx->stg[0].disp, &ctx->stg[0].bgr, &ctx->stg[0].labels,
                       &ctx->stg[0].coef, &ctx->stg[0].kp, &ctx->stg[1].disp, &ctx->stg[1].bgr, &ctx->stg[1].labels,
                       &ctx->stg[1].coef, &ctx->stg[1].kp,
-                      &ctx->d_frames, &ctx->d_blur, &ctx->d_blurjobs, &ctx->bil_lut, &ctx->tile_cnt, &ctx->tile_off, &ctx->bbox,
+                      &ctx->d_frames, &ctx->d_blur, &ctx->d_blurjobs, &ctx->bil_lut, &ctx->pp_labels, &ctx->pp_disp, &ctx->pp_sums,
+                      &ctx->pp_rows, &ctx->pp_coef, &ctx->tile_cnt, &ctx->tile_off, &ctx->bbox,
                       &ctx->frame_off, &ctx->grids, &ctx->counters, &ctx->pts, &ctx->sortbuf, &ctx->hist,
                       &ctx->plan_all, &ctx->plan_v2, &ctx->ghist, &ctx->head_cnt, &ctx->head_off, &ctx->vox,
                       &ctx->vox_off, &ctx->seg2, &ctx->tmat, &ctx->mask, &ctx->runwork, &ctx->spts, &ctx->res_keys[0], &ctx->res_keys[1],
@@ -1554,6 +1558,142 @@ int o3r_exchange_merge(o3r_ctx* ctx, const o3r_cell* recv_dev, size_t n) {
     int rc = acc_build_cycle(ctx, items, n, true, nullptr);
     if (rc) return rc;
     return acc_apply_cycle(ctx);
+}
+
+
+// ---- pre-pass ---------------------------------------------------------------------------------------------
+namespace {
+
+// symmetric 3x3 eigen-decomposition by cyclic Jacobi rotations: AtA = V diag(w) V^T (what cv::invert(AtA, DECOMP_SVD)
+// needs for a symmetric positive semi-definite matrix)
+void sym3_eigen(double A[3][3], double V[3][3], double w[3]) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) V[i][j] = (i == j);
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        const double off = std::fabs(A[0][1]) + std::fabs(A[0][2]) + std::fabs(A[1][2]);
+        if (off == 0.0) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (A[p][q] == 0.0) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 3; ++k) {
+                    const double akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - sn * akq;
+                    A[k][q] = sn * akp + c * akq;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - sn * aqk;
+                    A[q][k] = sn * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - sn * vkq;
+                    V[k][q] = sn * vkp + c * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < 3; ++i) w[i] = A[i][i];
+}
+
+// getMean + getVariance (pose_functions.cpp:987-1028) of the ROI; the sample source is already on the device
+int roi_variance(o3r_ctx* ctx, const uint8_t* d_disp, size_t dstep, const uint8_t* d_labels, size_t lstep,
+                 const double* d_coef, int n_planes, double* variance) {
+    const o3r_params& p = ctx->p;
+    const int nrow = p.rows - 2 * p.bounding_box, ncol = p.cols - p.bounding_box - p.cols_start_aft_cutout;
+    if (nrow <= 0 || ncol <= 0) return ctx->fail(O3R_ERR_INVALID, "empty ROI");
+    CU(ctx->pp_rows.ensure((size_t)nrow * 8));
+    std::vector<double> rows_h(nrow);
+    double mean = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+        LAUNCH(k_row_moment, nrow, kThreads, 0, d_disp, dstep, d_labels, lstep, d_coef, n_planes, p.cols,
+               p.cols_start_aft_cutout, p.bounding_box, p.min_disparity, pass, mean, ctx->pp_rows.as<double>());
+        CU(cudaMemcpyAsync(rows_h.data(), ctx->pp_rows.p, (size_t)nrow * 8, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        double s = 0.0;
+        for (int r = 0; r < nrow; ++r) s += rows_h[r];
+        if (pass == 0) mean = s / ((double)nrow * ncol);            // :1004 (divides by ALL ROI pixels)
+        else *variance = s / ((double)nrow * ncol - 1);             // :1026
+    }
+    return O3R_OK;
+}
+
+int stage_plane_u8(o3r_ctx* ctx, DevBuf& buf, const uint8_t* src, size_t src_step, size_t* step_out) {
+    const o3r_params& p = ctx->p;
+    const size_t step = ((size_t)p.cols + 15) & ~(size_t)15;
+    CU(buf.ensure(step * p.rows));
+    CU(cudaMemcpy2DAsync(buf.p, step, src, src_step, p.cols, p.rows, cudaMemcpyHostToDevice, ctx->st));
+    *step_out = step;
+    return O3R_OK;
+}
+
+}  // namespace
+
+int o3r_disp_variance(o3r_ctx* ctx, const uint8_t* disp, size_t disp_step, double* variance) {
+    if (!ctx || !disp || !variance) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    size_t step;
+    int rc = stage_plane_u8(ctx, ctx->pp_disp, disp, disp_step, &step);
+    if (rc) return rc;
+    return roi_variance(ctx, ctx->pp_disp.as<uint8_t>(), step, nullptr, 0, nullptr, 0, variance);
+}
+
+int o3r_plane_fit(o3r_ctx* ctx, const uint8_t* labels, size_t labels_step, const uint8_t* disp, size_t disp_step,
+                  double* coef, int coef_cap, int* n_planes, double* variance) {
+    if (!ctx || !labels || !disp || !coef || !n_planes) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    const o3r_params& p = ctx->p;
+    size_t lstep, dstep;
+    int rc = stage_plane_u8(ctx, ctx->pp_labels, labels, labels_step, &lstep);
+    if (rc) return rc;
+    rc = stage_plane_u8(ctx, ctx->pp_disp, disp, disp_step, &dstep);
+    if (rc) return rc;
+    const size_t sum_bytes = (size_t)256 * kLabSums * 8;
+    CU(ctx->pp_sums.ensure(sum_bytes));
+    ZERO(ctx->pp_sums.p, sum_bytes);
+    LAUNCH(k_label_sums, cdiv(p.rows, 8), kThreads, 0, ctx->pp_labels.as<uint8_t>(), lstep, ctx->pp_disp.as<uint8_t>(), dstep,
+           p.rows, p.cols, p.cols_start_aft_cutout, p.bounding_box, ctx->pp_sums.as<unsigned long long>());
+    std::vector<unsigned long long> S((size_t)256 * kLabSums);
+    CU(cudaMemcpyAsync(S.data(), ctx->pp_sums.p, sum_bytes, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    int np = 0;
+    for (int cluster = 1; cluster < 256; ++cluster) {   // :907 (labels are 8-bit); stops at the first absent label (:923)
+        const unsigned long long* s = &S[(size_t)cluster * kLabSums];
+        if (s[0] == 0) break;
+        if (cluster > coef_cap) return ctx->fail(O3R_ERR_CAPACITY, "coef buffer too small");
+        double* c = coef + 3 * (cluster - 1);
+        c[0] = c[1] = c[2] = 0.0;
+        np = cluster;
+        if (s[1] == 0) continue;   // :939-940: no pixel inside the ROI, the label keeps 0.0
+        // :957-965: x = inv_SVD(AtA) * At * b with AtA = [[Sxx Sxy Sx][Sxy Syy Sy][Sx Sy n]], At*b = [Sxd Syd Sd]
+        double A[3][3] = {{(double)s[4], (double)s[5], (double)s[2]}, {(double)s[5], (double)s[6], (double)s[3]},
+                          {(double)s[2], (double)s[3], (double)s[1]}};
+        double V[3][3], w[3];
+        sym3_eigen(A, V, w);
+        const double thr = DBL_EPSILON * 2 * (std::fabs(w[0]) + std::fabs(w[1]) + std::fabs(w[2]));
+        const double rhs[3] = {(double)s[7], (double)s[8], (double)s[9]};
+        for (int i = 0; i < 3; ++i) {
+            double acc = 0;
+            for (int j = 0; j < 3; ++j) {
+                double inv_ij = 0;
+                for (int e = 0; e < 3; ++e)
+                    if (std::fabs(w[e]) > thr) inv_ij += V[i][e] * V[j][e] / w[e];
+                acc += inv_ij * rhs[j];
+            }
+            c[i] = acc;
+        }
+    }
+    *n_planes = np;
+    if (variance) {   // getVariance(new_disp_img, true), :973; the caller applies the > 3 gate (:975-982)
+        CU(ctx->pp_coef.ensure(std::max(np, 1) * 24));
+        if (np) { int rcu = upload_small(ctx, ctx->pp_coef.p, coef, (size_t)np * 24); if (rcu) return rcu; }
+        return roi_variance(ctx, nullptr, 0, ctx->pp_labels.as<uint8_t>(), lstep, ctx->pp_coef.as<double>(), np, variance);
+    }
+    return O3R_OK;
 }
 
 }  // extern "C"

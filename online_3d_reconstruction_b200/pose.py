@@ -178,6 +178,24 @@ class Pose:
                                         mode, dst.ctypes.data, dst.strides[0]))
         return dst
 
+    # -- pre-pass ------------------------------------------------------------------------------------------
+    def getVariance(self, disp):
+        """pose_functions.cpp:1007-1028 getVariance(disp_img, false): the bad-frame gate's statistic (pose.cpp:187)."""
+        disp = np.ascontiguousarray(disp, dtype=np.uint8)
+        v = C.c_double(0)
+        self._check(self._L.o3r_disp_variance(self._h, disp.ctypes.data, disp.strides[0], C.byref(v)))
+        return v.value
+
+    def createPlaneFittedDisparityImages(self, labels, disp):
+        """pose_functions.cpp:900-985 -> (plane coefficients [n_planes, 3] f64, plane_fitted_disp_img_var)."""
+        labels = np.ascontiguousarray(labels, dtype=np.uint8)
+        disp = np.ascontiguousarray(disp, dtype=np.uint8)
+        coef = np.zeros((255, 3), dtype=np.float64)
+        n, v = C.c_int(0), C.c_double(0)
+        self._check(self._L.o3r_plane_fit(self._h, labels.ctypes.data, labels.strides[0], disp.ctypes.data, disp.strides[0],
+                                          coef.ctypes.data, 255, C.byref(n), C.byref(v)))
+        return coef[:n.value].copy(), v.value
+
     # -- multi-GPU exchange (device buffers are torch tensors owned by the caller) -----------------------------
     def setDeferMerge(self, defer):
         self._check(self._L.o3r_set_defer_merge(self._h, int(defer)))

@@ -75,6 +75,55 @@ def test_mask_counts_match_reference_log_720p(real):
             _eq(P.createAndTransformPtCloud(fr, abi.DISP_F64), exp)
 
 
+# ----------------------------------------------------------------------------------------------- pre-pass
+def test_plane_fit_and_variance_gate_on_real_frames(real):
+    """createPlaneFittedDisparityImages + getVariance on the GPU for the three shipped 720p frames: plane coefficients
+    bit-identical to the oracle (the normal-equation sums are exact integers), both variances within 1e-10 relative of
+    the oracle and equal to what the reference logged (build/output/log.txt:39-42) to its 6 printed digits."""
+    p = abi.make_params(jump_pixels=1, use_segment_labels=True)
+    with Pose(p) as P:
+        for i in range(3):
+            labels, disp = real["labels"][i], real["disp"][i]
+            coef, f64 = ob.plane_fit(p, labels, disp)
+            got_coef, got_var = P.createPlaneFittedDisparityImages(labels, disp)
+            assert np.array_equal(got_coef, coef)
+            exp_var = ob.get_variance(p, f64, True)
+            assert abs(got_var - exp_var) <= 1e-10 * exp_var
+            assert f"{got_var:.6g}" == f"{real['plane_fitted_disp_img_var'][i]:.6g}"
+            raw_var = P.getVariance(disp)
+            assert abs(raw_var - ob.get_variance(p, disp, False)) <= 1e-10 * raw_var
+            assert f"{raw_var:.6g}" == f"{real['disp_img_var'][i]:.6g}"
+
+
+def test_plane_fit_synthetic_labels_small():
+    """Ragged cases: a label with no ROI pixel keeps (0,0,0), numbering stops at the first absent label, label 0 is
+    never fitted; the coefficients feed straight into the label-mode frame path."""
+    rng = np.random.default_rng(5)
+    rows, cols = SMALL4["rows"], SMALL4["cols"]
+    p = abi.make_params(jump_pixels=1, use_segment_labels=True, **SMALL4)
+    labels = np.zeros((rows, cols), np.uint8)
+    labels[:, 40:120] = 1
+    labels[:60, 120:] = 2
+    labels[60:, 120:] = 3
+    labels[:10, :30] = 4          # entirely outside the ROI (x < x0, y < bb): fitted as (0, 0, 0)
+    labels[70:80, 130:140] = 6    # label 5 is absent: 6 is never reached (pose_functions.cpp:923)
+    yy, xx = np.mgrid[:rows, :cols]
+    disp = np.clip(90 + 0.05 * xx + 0.1 * yy + rng.normal(0, 1, (rows, cols)), 0, 255).astype(np.uint8)
+    coef, f64 = ob.plane_fit(p, labels, disp)
+    with Pose(p) as P:
+        got_coef, got_var = P.createPlaneFittedDisparityImages(labels, disp)
+        assert got_coef.shape == coef.shape == (4, 3)
+        assert np.array_equal(got_coef, coef) and not got_coef[3].any()
+        exp_var = ob.get_variance(p, f64, True)
+        assert abs(got_var - exp_var) <= 1e-10 * max(exp_var, 1e-300)
+        keep = []
+        bgr = synth.make_frame_images(rng, rows, cols)[1]
+        fr = abi.make_frame(None, bgr, np.eye(4), labels=labels, plane_coef=got_coef, keep=keep)
+        pts = P.createAndTransformPtCloud(fr, abi.DISP_F64)
+    fr64 = abi.make_frame(f64, bgr, np.eye(4), keep=keep)
+    _eq(pts, ob.create_and_transform_pt_cloud(p, fr64, abi.DISP_F64))
+
+
 # ------------------------------------------------------------------------------- points (no downsample)
 @pytest.mark.parametrize("J,n_kp", [(1, 0), (1, 50), (7, 300), (0, 1500), (15, 1500)])
 @pytest.mark.parametrize("geom", [SMALL, SMALL4])
