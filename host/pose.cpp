@@ -21,6 +21,7 @@
 #include <map>
 #include <sstream>
 #include <string>
+#include <deque>
 #include <vector>
 
 #include "o3r.h"
@@ -72,7 +73,6 @@ struct Pose {
     int binarySearchImageTime(int l, int r, int imageNumber);
     int binarySearchUsingTime(const vector<double>& seq, int l, int r, double time);
     void populateData();
-    double getVariance(const Image& disp);
     int run();
     int runDownsampleTool();
 };
@@ -274,23 +274,6 @@ void Pose::populateData() {   // :624-744 (the 7-thread loaders become a plain l
     cout << endl;
 }
 
-double Pose::getVariance(const Image& d) {   // :987-1028 (sum over valid pixels / ALL ROI pixels, as in the reference)
-    double sum = 0.0;
-    const long long npx = (long long)(rows - 2 * boundingBox) * (cols - boundingBox - cols_start_aft_cutout);
-    for (int y = boundingBox; y < rows - boundingBox; ++y)
-        for (int x = cols_start_aft_cutout; x < cols - boundingBox; ++x) {
-            const double v = d.data[(size_t)y * d.cols + x];
-            if (v > minDisparity) sum += v;
-        }
-    const double mean = sum / npx;
-    double temp = 0;
-    for (int y = boundingBox; y < rows - boundingBox; ++y)
-        for (int x = cols_start_aft_cutout; x < cols - boundingBox; ++x) {
-            const double v = d.data[(size_t)y * d.cols + x];
-            if (v > minDisparity) temp += (v - mean) * (v - mean);
-        }
-    return temp / (npx - 1);
-}
 
 static string currentDateTime() {   // pose_functions.cpp:331-345
     time_t now = time(0);
@@ -307,7 +290,7 @@ static o3r_ctx* make_ctx(Pose& P, int merge_mode, int max_batch) {
     for (int i = 0; i < 16; ++i) p.Q[i] = P.Q[i];
     p.jump_pixels = P.jump_pixels; p.blur_kernel = P.blur_kernel; p.blur_mode = P.blur_mode;
     p.voxel_size = P.voxel_size; p.min_points_per_voxel = P.min_points_per_voxel;
-    p.dont_downsample = P.dont_downsample; p.use_segment_labels = 0;
+    p.dont_downsample = P.dont_downsample; p.use_segment_labels = P.use_segment_labels ? 1 : 0;
     p.disp_divisor = 200.0; p.merge_mode = merge_mode; p.device = P.device; p.max_batch_frames = max(1, max_batch);
     o3r_ctx* ctx = nullptr;
     if (o3r_create(&p, &ctx) != O3R_OK) { cerr << "o3r_create: " << o3r_last_error(nullptr) << endl; return nullptr; }
@@ -352,7 +335,6 @@ int Pose::run() {
                 " (--only_MAVLink path) times --pose_corrections when given." << endl;
     populateData();
     if (rows == 0 || cols == 0 || cols_start_aft_cutout == 0) throw "Exception: some important values not set!";
-    if (use_segment_labels) throw "Exception: --use_segment_labels needs the host plane fit of the reference (pass plane coefficients through the ABI)";
     const double app_start_time = now_s();
     o3r_ctx* ctx = make_ctx(*this, O3R_MERGE_ACCUMULATE, seq_len);
     if (!ctx) return 1;
@@ -367,12 +349,15 @@ int Pose::run() {
         cout << "\nCycle " << cycle << endl;
         log_file << "\nCycle " << cycle << endl;
         vector<o3r_frame> batch;
+        std::deque<vector<double>> plane_coefs;   // per accepted frame, stable addresses for the batch
         int images_in_cycle = 0;
         while (images_in_cycle < seq_len && current_idx <= last_idx) {   // :162-255
             RawImageData& r = rawImageDataVec[current_idx];
             if (r.rgb_image.empty()) { cout << r.img_num << " could not read rgb image. \tRejected!" << endl; log_file << r.img_num << " could not read rgb image. \tRejected!" << endl; current_idx++; continue; }
             if (r.disparity_image.empty()) { cout << r.img_num << " could not read disparity image. \tRejected!" << endl; log_file << r.img_num << " could not read disparity image. \tRejected!" << endl; current_idx++; continue; }
-            const double disp_img_var = getVariance(r.disparity_image);
+            double disp_img_var = 0;   // getVariance (pose_functions.cpp:1007) on the GPU
+            if (o3r_disp_variance(ctx, r.disparity_image.data.data(), r.disparity_image.step(), &disp_img_var) != O3R_OK)
+                throw "Exception: o3r_disp_variance failed";
             cout << r.img_num << " " << flush;
             log_file << r.img_num << " disp_img_var " << disp_img_var << "\t";
             if (disp_img_var > 5) { cout << " disp_img_var = " << disp_img_var << " > 5.\tRejected!" << endl; log_file << " disp_img_var = " << disp_img_var << " > 5.\tRejected!" << endl; current_idx++; continue; }
@@ -380,6 +365,22 @@ int Pose::run() {
             auto c = corrections.find(r.img_num);
             if (c != corrections.end()) t = host::mat4_mul(c->second, t);               // :232
             o3r_frame f{};
+            if (use_segment_labels) {   // createPlaneFittedDisparityImages (pose_functions.cpp:900-985) on the GPU
+                if (r.segment_label.empty()) { cout << r.img_num << " could not read segment labels. \tRejected!" << endl; log_file << r.img_num << " could not read segment labels. \tRejected!" << endl; current_idx++; continue; }
+                plane_coefs.emplace_back(255 * 3, 0.0);
+                int n_planes = 0;
+                double pf_var = 0;
+                if (o3r_plane_fit(ctx, r.segment_label.data.data(), r.segment_label.step(), r.disparity_image.data.data(),
+                                  r.disparity_image.step(), plane_coefs.back().data(), 255, &n_planes, &pf_var) != O3R_OK)
+                    throw "Exception: o3r_plane_fit failed";
+                log_file << " plane_fitted_disp_img_var " << pf_var << "\t";
+                if (pf_var > 3) {   // :975-982
+                    cout << "Exception: plane_fitted_disp_img_var " << current_idx << " > 3. Unacceptable disparity image." << endl;
+                    throw "Error";
+                }
+                f.labels = r.segment_label.data.data(); f.labels_step = r.segment_label.step();
+                f.plane_coef = plane_coefs.back().data(); f.n_planes = n_planes;
+            }
             f.disp = r.disparity_image.data.data(); f.disp_step = r.disparity_image.step();
             f.bgr = r.rgb_image.data.data(); f.bgr_step = r.rgb_image.step();
             memcpy(f.T, t.m, sizeof(f.T));
@@ -406,7 +407,8 @@ int Pose::run() {
         log_file << "Adding Point Cloud number/points ";
         vector<uint32_t> counts(batch.size());
         if (!batch.empty()) {
-            const int rc = o3r_frames_cloud(ctx, batch.data(), (int)batch.size(), O3R_DISP_U8, counts.data());
+            const int rc = o3r_frames_cloud(ctx, batch.data(), (int)batch.size(), use_segment_labels ? O3R_DISP_F64 : O3R_DISP_U8,
+                                            counts.data());
             if (rc != O3R_OK) cout << "Exception caught in cycle " << cycle << ": " << o3r_last_error(ctx) << endl;   // pose.cpp:620-635
             for (size_t i = 0; i < batch.size(); ++i) {
                 cout << " " << accepted_nums[accepted + i] << flush;

@@ -74,9 +74,11 @@ def test_cli_usage_and_reference_error_messages(pose_bin):
     assert r.returncode == 1   # no such data set
 
 
-def _write_dataset(root, n, rows, cols, seed=77):
+def _write_dataset(root, n, rows, cols, seed=77, labels=None):
     os.makedirs(os.path.join(root, "data_files")); os.makedirs(os.path.join(root, "images"))
     os.makedirs(os.path.join(root, "disparities"))
+    if labels is not None:
+        os.makedirs(os.path.join(root, "segmentlabels"))
     rng = np.random.default_rng(seed)
     Q = abi.Q_CAM13
     with open(os.path.join(root, "data_files", "cam13calib.yml"), "w") as f:
@@ -96,6 +98,8 @@ def _write_dataset(root, n, rows, cols, seed=77):
     for i, (d, img, _) in enumerate(seq):
         num = 100 + i
         write_png(os.path.join(root, "disparities", f"{num}.png"), d)
+        if labels is not None:
+            write_png(os.path.join(root, "segmentlabels", f"{num}.png"), labels)
         write_png(os.path.join(root, "images", f"{num}.png"), img[:, :, ::-1])   # file is RGB, imread gives BGR
         t_ns = 1532043429586341888 + i * 227000000
         times.append((num, t_ns))
@@ -152,6 +156,44 @@ def test_driver_end_to_end_matches_python_path(pose_bin, tmp_path):
     assert np.array_equal(got, exp)
     uav, _, _ = read_ply(os.path.join(run_dir, "cloud_uavpos.ply"))
     assert len(uav) == 2 * (n - 1) and set(np.unique(uav["rgb"])) == {0x00FF00, 0xFF0000}
+
+
+@pytest.mark.gpu
+def test_driver_use_segment_labels_runs_plane_fit_on_gpu(pose_bin, tmp_path):
+    """--use_segment_labels: the driver fits the per-label planes (createPlaneFittedDisparityImages, pose_functions.cpp:
+    900-985) and gates frames through the GPU pre-pass, then scans the plane-fitted disparity.  cloud.ply must equal the
+    Python mirror fed with the same labels and the GPU-fitted coefficients."""
+    from online_3d_reconstruction_b200.pose import Pose
+    rows, cols, n = 128, 256, 4
+    labels = np.ones((rows, cols), np.uint8)
+    labels[:, 130:200] = 2
+    labels[:, 200:] = 3
+    labels[60:63, 100:104] = 0   # a few unlabelled pixels: 0.0 -> masked out by disp > 64 (more than ~1 % of them would
+                                 # trip the reference's plane_fitted_disp_img_var > 3 gate, whose mean divides by ALL pixels)
+    root = str(tmp_path / "data")
+    seq, poses = _write_dataset(root, n, rows, cols, seed=78, labels=labels)
+    out = str(tmp_path / "out")
+    r = subprocess.run([pose_bin, "100", "103", "--seq_len", "4", "--voxel_size", "0.05", "--jump_pixels", "1",
+                        "--min_points_per_voxel", "1", "--only_MAVLink", "--use_segment_labels", "--data_root", root,
+                        "--output", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    run_dir = os.path.join(out, sorted(os.listdir(out))[0])
+    got, _, _ = read_ply(os.path.join(run_dir, "cloud.ply"))
+    assert "plane_fitted_disp_img_var" in open(os.path.join(run_dir, "log.txt")).read()
+    p = abi.make_params(rows=rows, cols=cols, jump_pixels=1, voxel_size=0.05, min_points_per_voxel=1, use_segment_labels=True)
+    keep, frames = [], []
+    with Pose(p) as P:
+        for i, ((d, img, _), (t, *pp)) in enumerate(zip(seq, poses)):
+            if i == 2:
+                continue   # rejected by the variance gate
+            coef, var = P.createPlaneFittedDisparityImages(labels, d)
+            assert var <= 3
+            pv = [float(f"{v:.9f}") for v in pp]
+            frames.append(abi.make_frame(None, img, tmat.generate_tmat(*pv), labels=labels, plane_coef=coef, keep=keep))
+        P.createCycleClouds(frames, abi.DISP_F64)
+        exp = P.downsamplePtCloud()
+    assert len(exp) > 100
+    assert np.array_equal(got, exp)
 
 
 @pytest.mark.gpu
