@@ -85,6 +85,10 @@ typedef struct o3r_params {
     int      merge_mode;              /* O3R_MERGE_*                                                   */
     int      device;                  /* CUDA device ordinal                                           */
     int      max_batch_frames;        /* frames the context sizes its staging buffers for (>=1)       */
+    int      sor_mean_k;              /* pcl::StatisticalOutlierRemoval before the per-frame VoxelGrid
+                                         (pose_functions.cpp:1673-1686; the reference uses 50 whenever
+                                         jump_pixels > 0).  0 = filter off                             */
+    double   sor_stddev_mul;          /* setStddevMulThresh (1.0 in the reference)                     */
 } o3r_params;
 
 /* One frame of input: what createAndTransformPtCloud reads from acceptedImageDataVec[i]
@@ -125,7 +129,8 @@ void  o3r_host_free(void* p);
 
 /* Replaces: void Pose::createAndTransformPtCloud(int, PointCloud::Ptr&)  pose.cpp:596-636
  *   = createSingleImgPtCloud (pose_functions.cpp:1030-1134) + transformPtCloud (:1358-1362)
- *   + downsamplePtCloud(cloud,false) (:1654-1709, VoxelGrid leaf voxel_size/5; SOR not built yet).
+ *   + downsamplePtCloud(cloud,false) (:1654-1709: StatisticalOutlierRemoval when sor_mean_k > 0, then VoxelGrid leaf
+ *     voxel_size/5).
  * Host pointers in `frame`; `out` is a host buffer of `cap` records; *n_out = records produced
  * (also set on O3R_ERR_CAPACITY).  Output order is the reference's: keypoints then row-major grid
  * (dont_downsample) or ascending VoxelGrid index.  Thread-safe per ctx (internally serialised). */
@@ -190,6 +195,12 @@ int o3r_cloud_clear(o3r_ctx* ctx);
 int o3r_voxel_grid(o3r_ctx* ctx, const o3r_point* pts, size_t n, float lx, float ly, float lz,
                    unsigned min_points, o3r_point* out, size_t cap, size_t* n_out,
                    uint64_t* keys, uint32_t* counts, int* passthrough);
+
+/* pcl::StatisticalOutlierRemoval alone on a host cloud (pose_functions.cpp:1673-1686: setMeanK(50),
+ * setStddevMulThresh(1.0)): keep[i] = 0 for the points PCL removes; dist (optional, n floats) = every point's mean
+ * distance to its mean_k nearest neighbours; threshold (optional) = mean + mul * stddev of those. */
+int o3r_sor(o3r_ctx* ctx, const o3r_point* pts, size_t n, int mean_k, double stddev_mul,
+            uint8_t* keep, float* dist, double* threshold);
 
 /* The blur stage alone on a u8 plane (pose_functions.cpp:1040-1047 with blur_mode). Host pointers. */
 int o3r_blur_u8(o3r_ctx* ctx, const uint8_t* src, size_t src_step, int rows, int cols,

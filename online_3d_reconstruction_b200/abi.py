@@ -47,6 +47,8 @@ class Params(C.Structure):
         ("merge_mode", C.c_int),
         ("device", C.c_int),
         ("max_batch_frames", C.c_int),
+        ("sor_mean_k", C.c_int),
+        ("sor_stddev_mul", C.c_double),
     ]
 
 
@@ -72,7 +74,7 @@ Q_CAM13 = (1.0, 0.0, 0.0, -5.2425751876831055e+02,
 def make_params(rows=720, cols=1280, *, jump_pixels=10, voxel_size=0.1, min_points_per_voxel=1,
                 blur_kernel=1, blur_mode=BLUR_MEDIAN, dont_downsample=False, use_segment_labels=False,
                 Q=Q_CAM13, min_disparity=64.0, bounding_box=20, cutout_ratio=8, disp_divisor=200.0,
-                merge_mode=MERGE_ACCUMULATE, device=0, max_batch_frames=64):
+                merge_mode=MERGE_ACCUMULATE, device=0, max_batch_frames=64, sor_mean_k=0, sor_stddev_mul=1.0):
     """Defaults are the reference's (pose.h:93-98,108,118,126,149,168)."""
     p = Params()
     p.rows, p.cols = rows, cols
@@ -91,6 +93,8 @@ def make_params(rows=720, cols=1280, *, jump_pixels=10, voxel_size=0.1, min_poin
     p.merge_mode = merge_mode
     p.device = device
     p.max_batch_frames = max_batch_frames
+    p.sor_mean_k = sor_mean_k          # the reference: 50 whenever jump_pixels > 0 (pose_functions.cpp:1673-1686)
+    p.sor_stddev_mul = sor_stddev_mul
     return p
 
 

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "prepass.cuh"
 #include "prereduce.cuh"
+#include "sor.cuh"
 #include "sort.cuh"
 #include "stage_a.cuh"
 #include "voxel.cuh"
@@ -143,6 +144,7 @@ struct o3r_ctx {
     cudaEvent_t ev_nres = nullptr;
     size_t n_cyc_ub = 0;
     DevBuf ckey, cacc, crgb, new_cnt, new_off, new_keys, okeys;
+    DevBuf sor_pts, sor_off, sor_dist, sor_grids, sor_pgrids, sor_rows, sor_thr, sor_skeys, sor_svals, sor_cnt, sor_cntoff;   // SOR scratch
     DevBuf partials, pr_status;   // TILED mode: the batch's tile partials (o3r_cell) and the look-back words
     size_t last_partials = 0;
     bool last_has_partials = false;
@@ -312,11 +314,10 @@ int carve_sort_u32(o3r_ctx* ctx, size_t n, SortU32& s) {
     return O3R_OK;
 }
 
-// sorts + reduces; out/out_off sized by the caller.  CNT_VOX receives the total.
-int vg_sorted_reduce(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const uint32_t* seg_off, int n_seg,
-                     size_t per_seg_cap, const GridParams* grids, float ix, float iy, float iz, uint32_t min_points,
-                     int z_shift, float4* out, uint32_t* out_off, uint64_t* out_keys, uint32_t* out_counts,
-                     bool track_cells = false, const uint32_t* out_base = nullptr) {
+// digit layout, whole-segment histograms and pass plan of a segmented u32 sort whose keys sit in sb.k0
+// (grids[s].key_bits = live key bits of segment s); leaves the plan in ctx->plan_all, the histograms in ctx->ghist
+int sort_segments_plan(o3r_ctx* ctx, const SortU32& sb, const uint32_t* seg_off, int n_seg, size_t per_seg_cap,
+                       const GridParams* grids) {
     const size_t gh_bytes = (size_t)n_seg * kMaxPasses * kRsBins * 4;
     CU(ctx->ghist.ensure(gh_bytes));
     CU(ctx->plan_all.ensure((size_t)n_seg * sizeof(SortPlan)));
@@ -327,6 +328,17 @@ int vg_sorted_reduce(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const u
     LAUNCH_N("k_rs_ghist_u32", (k_rs_ghist<uint32_t, 4>), dim3(std::max(1u, cdiv(per_seg_cap, kRsTile)), n_seg),
              kThreads, 0, sb.k0, seg_off, plan, ctx->ghist.as<uint32_t>());
     LAUNCH(k_rs_plan, n_seg, kThreads, 0, ctx->ghist.as<uint32_t>(), seg_off, plan, grids);
+    return O3R_OK;
+}
+
+// sorts + reduces; out/out_off sized by the caller.  CNT_VOX receives the total.
+int vg_sorted_reduce(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const uint32_t* seg_off, int n_seg,
+                     size_t per_seg_cap, const GridParams* grids, float ix, float iy, float iz, uint32_t min_points,
+                     int z_shift, float4* out, uint32_t* out_off, uint64_t* out_keys, uint32_t* out_counts,
+                     bool track_cells = false, const uint32_t* out_base = nullptr) {
+    int rcs = sort_segments_plan(ctx, sb, seg_off, n_seg, per_seg_cap, grids);
+    if (rcs) return rcs;
+    SortPlan* plan = ctx->plan_all.as<SortPlan>();
     // the fast reduce streams the points in sorted order: the last radix pass gathers them into `spts`
     const bool fast = min_points <= 1 && !out_keys && !out_counts;
     float4* spts = nullptr;
@@ -558,6 +570,61 @@ int cloud_append_dev(o3r_ctx* ctx, const float4* pts, size_t n) {
     CU(ctx->cloud.ensure((ctx->n_cloud + n) * 16, ctx->st, ctx->n_cloud * 16));
     CU(cudaMemcpyAsync(ctx->cloud.as<float4>() + ctx->n_cloud, pts, n * 16, cudaMemcpyDeviceToDevice, ctx->st));
     ctx->n_cloud += n;
+    return O3R_OK;
+}
+
+// ---- pcl::StatisticalOutlierRemoval on the frames of a chunk (pose_functions.cpp:1673-1686) -----------------------------
+// in: pts with segment offsets seg_off[n_seg + 1] (device).  out: ctx->sor_pts / ctx->sor_off (same layout, kept points
+// in their original order).  Uses the sort buffers (free again afterwards) and ctx->bbox / ctx->spts as scratch.
+int sor_filter(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const uint32_t* seg_off, int n_seg, size_t per_seg_cap,
+               int mean_k, double stddev_mul) {
+    if (mean_k < 1) return ctx->fail(O3R_ERR_INVALID, "sor_mean_k must be positive");
+    if (mean_k + 1 > kSorMaxK) return ctx->fail(O3R_ERR_INVALID, "sor_mean_k too large (max 127)");
+    const size_t cap = per_seg_cap * n_seg;
+    const uint32_t tiles = std::max(1u, cdiv(per_seg_cap, kTileV));
+    CU(ctx->sor_pts.ensure(cap * 16));
+    CU(ctx->sor_off.ensure((size_t)(n_seg + 1) * 4));
+    CU(ctx->sor_dist.ensure(cap * 4));
+    CU(ctx->sor_skeys.ensure(cap * 4));
+    CU(ctx->sor_svals.ensure(cap * 4));
+    CU(ctx->spts.ensure(cap * 16));
+    CU(ctx->sor_grids.ensure((size_t)n_seg * sizeof(SorGrid)));
+    CU(ctx->sor_pgrids.ensure((size_t)n_seg * sizeof(GridParams)));
+    CU(ctx->sor_rows.ensure((size_t)n_seg * kSorRowsCap * 8));
+    CU(ctx->sor_thr.ensure((size_t)n_seg * 8));
+    CU(ctx->sor_cnt.ensure((size_t)tiles * n_seg * 4));
+    CU(ctx->sor_cntoff.ensure((size_t)tiles * n_seg * 4));
+    CU(ctx->bbox.ensure((size_t)n_seg * 6 * 4));
+    SorGrid* grids = ctx->sor_grids.as<SorGrid>();
+    GridParams* pgrids = ctx->sor_pgrids.as<GridParams>();
+    uint32_t* rowb = ctx->sor_rows.as<uint32_t>();
+    uint32_t* rowe = rowb + (size_t)n_seg * kSorRowsCap;
+    uint32_t* cnt = ctx->counters.as<uint32_t>();
+    const uint32_t gl = std::min<uint32_t>(std::max(1u, cdiv(per_seg_cap, kThreads)), 148 * 4);
+    LAUNCH(k_bbox_init, cdiv((size_t)n_seg * 6, kThreads), kThreads, 0, ctx->bbox.as<uint32_t>(), n_seg);
+    LAUNCH(k_bbox_pts, dim3(tiles, n_seg), kThreads, 0, pts, seg_off, 0, ctx->bbox.as<uint32_t>());
+    LAUNCH(k_sor_grid, cdiv(n_seg, 64), 64, 0, n_seg, ctx->bbox.as<uint32_t>(), seg_off, mean_k, grids, pgrids);
+    LAUNCH(k_sor_key, dim3(gl, n_seg), kThreads, 0, pts, seg_off, grids, sb.k0);
+    int rc = sort_segments_plan(ctx, sb, seg_off, n_seg, per_seg_cap, pgrids);
+    if (rc) return rc;
+    SortPlan* plan = ctx->plan_all.as<SortPlan>();
+    rc = sort_pairs<uint32_t>(ctx, sb.k0, sb.k1, sb.v0, sb.v1, seg_off, n_seg, per_seg_cap, plan, 4, 1, ctx->ghist.as<uint32_t>());
+    if (rc) return rc;
+    LAUNCH(k_sor_rows_clear, dim3(std::min<uint32_t>(cdiv(kSorRowsCap, kThreads), 256), n_seg), kThreads, 0, grids, rowb, rowe);
+    LAUNCH(k_sor_rows, dim3(gl, n_seg), kThreads, 0, sb.k0, sb.k1, sb.v0, sb.v1, plan, pts, seg_off, grids, rowb, rowe,
+           ctx->sor_skeys.as<uint32_t>(), ctx->sor_svals.as<uint32_t>(), ctx->spts.as<float4>());
+    const size_t heap_bytes = (size_t)(mean_k + 1) * kSorThreads * 4;
+    CU(cudaFuncSetAttribute(k_sor_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heap_bytes));
+    LAUNCH(k_sor_knn, dim3(std::max(1u, cdiv(per_seg_cap, kSorThreads)), n_seg), kSorThreads, heap_bytes, ctx->spts.as<float4>(),
+           ctx->sor_skeys.as<uint32_t>(), ctx->sor_svals.as<uint32_t>(), seg_off, grids, rowb, rowe, mean_k,
+           ctx->sor_dist.as<float>());
+    LAUNCH(k_sor_stats, n_seg, kThreads, 0, ctx->sor_dist.as<float>(), seg_off, stddev_mul, ctx->sor_thr.as<double>());
+    LAUNCH(k_sor_count, dim3(tiles, n_seg), kThreads, 0, ctx->sor_dist.as<float>(), seg_off, ctx->sor_thr.as<double>(), tiles,
+           ctx->sor_cnt.as<uint32_t>());
+    LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->sor_cnt.as<uint32_t>(), ctx->sor_cntoff.as<uint32_t>(), (uint32_t)((size_t)tiles * n_seg),
+           cnt + CNT_PTS);
+    LAUNCH(k_sor_compact, dim3(tiles, n_seg), kThreads, 0, pts, ctx->sor_dist.as<float>(), seg_off, ctx->sor_thr.as<double>(), tiles,
+           ctx->sor_cntoff.as<uint32_t>(), cnt + CNT_PTS, n_seg, ctx->sor_pts.as<float4>(), ctx->sor_off.as<uint32_t>());
     return O3R_OK;
 }
 
@@ -922,8 +989,25 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
         }
         if (rc) return rc;
         if (opt.mask_only) return O3R_OK;   // (single frame)
+        const float4* vg_pts = ctx->pts.as<float4>();
+        const uint32_t* vg_off = ctx->frame_off.as<uint32_t>();
+        if (P.want_keys && p.sor_mean_k > 0 && J > 0) {
+            // StatisticalOutlierRemoval first (pose_functions.cpp:1673-1686); the VoxelGrid then sees the filtered cloud, so
+            // its bbox, grid and leaf indices are recomputed from the kept points
+            rc = sor_filter(ctx, sb, vg_pts, vg_off, nc, per_frame_cap, p.sor_mean_k, p.sor_stddev_mul);
+            if (rc) return rc;
+            vg_pts = ctx->sor_pts.as<float4>();
+            vg_off = ctx->sor_off.as<uint32_t>();
+            const uint32_t tl = std::max(1u, cdiv(per_frame_cap, kTileV));
+            LAUNCH(k_bbox_init, cdiv((size_t)nc * 6, kThreads), kThreads, 0, ctx->bbox.as<uint32_t>(), nc);
+            LAUNCH(k_bbox_pts, dim3(tl, nc), kThreads, 0, vg_pts, vg_off, 0, ctx->bbox.as<uint32_t>());
+            LAUNCH(k_grid_params, cdiv(nc, 64), 64, 0, nc, ctx->bbox.as<uint32_t>(), ctx->inv_f, ctx->inv_f, ctx->inv_f,
+                   ctx->grids.as<GridParams>());
+            LAUNCH(k_vg_key, dim3(std::min<uint32_t>(std::max(1u, cdiv(per_frame_cap, kThreads)), 148 * 4), nc), kThreads, 0, vg_pts,
+                   vg_off, ctx->grids.as<GridParams>(), 0, sb.k0);
+        }
         if (P.want_keys) {  // per-frame VoxelGrid, leaf voxel_size / 5 (pose_functions.cpp:1698), appended at the base
-            rc = vg_sorted_reduce(ctx, sb, ctx->pts.as<float4>(), ctx->frame_off.as<uint32_t>(), nc, per_frame_cap,
+            rc = vg_sorted_reduce(ctx, sb, vg_pts, vg_off, nc, per_frame_cap,
                                   ctx->grids.as<GridParams>(), ctx->inv_f, ctx->inv_f, ctx->inv_f, 0, 0,
                                   ctx->vox.as<float4>(), goff + f0, nullptr, nullptr, !ctx->retain(), cnt + CNT_BASE);
             if (rc) return rc;
@@ -1115,7 +1199,8 @@ void o3r_destroy(o3r_ctx* ctx) {
                       &ctx->plan_all, &ctx->plan_v2, &ctx->ghist, &ctx->head_cnt, &ctx->head_off, &ctx->vox,
                       &ctx->vox_off, &ctx->seg2, &ctx->tmat, &ctx->mask, &ctx->runwork, &ctx->spts, &ctx->res_keys[0], &ctx->res_keys[1],
                       &ctx->res_acc[0], &ctx->res_acc[1], &ctx->res_rgb[0], &ctx->res_rgb[1], &ctx->ckey, &ctx->cacc,
-                      &ctx->crgb, &ctx->partials, &ctx->pr_status, &ctx->new_cnt, &ctx->new_off, &ctx->new_keys, &ctx->okeys, &ctx->cloud};
+                      &ctx->crgb, &ctx->partials, &ctx->pr_status, &ctx->sor_pts, &ctx->sor_off, &ctx->sor_dist, &ctx->sor_grids,
+                      &ctx->sor_pgrids, &ctx->sor_rows, &ctx->sor_thr, &ctx->sor_skeys, &ctx->sor_svals, &ctx->sor_cnt, &ctx->sor_cntoff, &ctx->new_cnt, &ctx->new_off, &ctx->new_keys, &ctx->okeys, &ctx->cloud};
     for (DevBuf* b : bufs) b->release();
     for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -1693,6 +1778,36 @@ int o3r_plane_fit(o3r_ctx* ctx, const uint8_t* labels, size_t labels_step, const
         if (np) { int rcu = upload_small(ctx, ctx->pp_coef.p, coef, (size_t)np * 24); if (rcu) return rcu; }
         return roi_variance(ctx, nullptr, 0, ctx->pp_labels.as<uint8_t>(), lstep, ctx->pp_coef.as<double>(), np, variance);
     }
+    return O3R_OK;
+}
+
+
+int o3r_sor(o3r_ctx* ctx, const o3r_point* pts, size_t n, int mean_k, double stddev_mul, uint8_t* keep, float* dist,
+            double* threshold) {
+    if (!ctx || (n && !pts) || !keep) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    if (n == 0) return O3R_OK;
+    if (n >= (1ull << 32)) return ctx->fail(O3R_ERR_INVALID, "cloud too large for 32-bit indices");
+    CU(ctx->pts.ensure(n * 16));
+    CU(ctx->seg2.ensure(16));
+    ctx->last_n = 0; ctx->last_total = 0; ctx->last_has_partials = false;
+    CU(cudaMemcpyAsync(ctx->pts.p, pts, n * 16, cudaMemcpyHostToDevice, ctx->st));
+    const uint32_t seg_h[2] = {0u, (uint32_t)n};
+    { int rcu = upload_small(ctx, ctx->seg2.p, seg_h, 8); if (rcu) return rcu; }
+    SortU32 sb;
+    int rc = carve_sort_u32(ctx, n, sb);
+    if (rc) return rc;
+    rc = sor_filter(ctx, sb, ctx->pts.as<float4>(), ctx->seg2.as<uint32_t>(), 1, n, mean_k, stddev_mul);
+    if (rc) return rc;
+    std::vector<float> d(n);
+    double thr = 0;
+    CU(cudaMemcpyAsync(d.data(), ctx->sor_dist.p, n * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(&thr, ctx->sor_thr.p, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    for (size_t i = 0; i < n; ++i) keep[i] = !((double)d[i] > thr);
+    if (dist) memcpy(dist, d.data(), n * 4);
+    if (threshold) *threshold = thr;
     return O3R_OK;
 }
 

@@ -1,0 +1,317 @@
+// sor.cuh — pcl::StatisticalOutlierRemoval (pose_functions.cpp:1673-1686: setMeanK(50), setStddevMulThresh(1.0)), the
+// filter the reference applies to every frame's cloud before the per-frame VoxelGrid whenever jump_pixels > 0.
+//
+// PCL: for every point the mean_k + 1 nearest neighbours by exact k-NN (KdTreeFLANN, flann::L2_Simple<float>:
+// d2 = ((dx*dx) + (dy*dy)) + (dz*dz) in float), dist_i = (float)(sum_{k=1..mean_k} sqrt((double)d2_k) / mean_k) with the
+// neighbours in ascending order (k = 0 is the query), then mean and stddev of dist over the cloud in double and
+// "remove iff dist_i > mean + mul * stddev".  An exact k-NN does not depend on how it is found; here:
+//   * a uniform grid per frame (cell = the radius that holds mean_k + 1 points of a surface of the frame's density),
+//     points radix-sorted by cell index (x minor), a begin/end table per (y, z) row of cells;
+//   * one thread per query, in cell order (a warp's queries share their candidate rows): the cube of (2s+1)^3 cells
+//     around the query is scanned into a per-thread max-heap of the mean_k + 1 smallest d2 (shared memory), s grows until
+//     the heap's top provably lies inside the cube (every unscanned point is farther than (s - 0.05) cells);
+//   * heapsort in place, sum in ascending order -> the same double additions as the CPU loop, bit for bit.
+// The cloud statistics are reduced in a fixed tree order (the reference adds sequentially: ~1e-13 relative on the
+// threshold, which only matters for a point whose distance equals the threshold to 13 digits).
+#pragma once
+#include "common.cuh"
+#include "sort.cuh"
+
+namespace o3r {
+
+constexpr int kSorThreads = 128;
+constexpr int kSorRowsCap = 1 << 18;   // (y, z) rows of cells per frame; the cell is enlarged until they fit
+constexpr int kSorMaxK = 128;          // mean_k + 1 <= 128
+
+struct SorGrid {
+    float mn[3];
+    float inv, c;
+    int nc[3];
+    int empty;
+};
+
+// per frame: cell size and table shape from the frame's bbox ({minx,miny,minz,maxx,maxy,maxz} as ordered uints) and count.
+// Also fills the GridParams fields the radix-sort planner reads (key_bits, passthrough, empty).
+__global__ void k_sor_grid(int n_seg, const uint32_t* __restrict__ bbox, const uint32_t* __restrict__ seg_off, int mean_k,
+                           SorGrid* __restrict__ grids, GridParams* __restrict__ plan_grids) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    const uint32_t n = seg_off[s + 1] - seg_off[s];
+    SorGrid G;
+    GridParams P;
+    memset(&P, 0, sizeof(P));
+    G.empty = (n == 0) || bbox[6 * s] == 0xffffffffu;
+    G.inv = 1.f; G.c = 1.f;
+    G.nc[0] = G.nc[1] = G.nc[2] = 1;
+    G.mn[0] = G.mn[1] = G.mn[2] = 0.f;
+    P.empty = G.empty;
+    P.key_bits = 1;
+    if (!G.empty) {
+        double ext[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            G.mn[a] = ord2f(bbox[6 * s + a]);
+            ext[a] = (double)ord2f(bbox[6 * s + 3 + a]) - (double)G.mn[a];
+        }
+        const double e_hi = fmax(ext[0], fmax(ext[1], ext[2])), e_lo = fmin(ext[0], fmin(ext[1], ext[2]));
+        const double e_mid = ext[0] + ext[1] + ext[2] - e_hi - e_lo;
+        const double area = fmax(e_hi * e_mid, 1e-12);
+        double c = sqrt((double)(mean_k + 1) * area / (3.141592653589793 * (double)n));
+        c = fmax(c, 1e-6);
+        long long nc[3];
+        for (;;) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) nc[a] = (long long)(ext[a] / c) + 2;
+            if (nc[0] * nc[1] * nc[2] <= (1ll << 31) && nc[1] * nc[2] <= (long long)kSorRowsCap) break;
+            c *= 1.26;
+        }
+        G.c = (float)c;
+        G.inv = (float)(1.0 / c);
+        G.nc[0] = (int)nc[0]; G.nc[1] = (int)nc[1]; G.nc[2] = (int)nc[2];
+        const long long cells = nc[0] * nc[1] * nc[2];
+        P.key_bits = cells > 1 ? 64 - __clzll(cells - 1) : 1;
+    }
+    grids[s] = G;
+    plan_grids[s] = P;
+}
+
+__device__ __forceinline__ uint32_t sor_cell(const SorGrid& G, float x, float y, float z) {
+    const int ix = min(G.nc[0] - 1, max(0, (int)floorf(__fmul_rn(__fsub_rn(x, G.mn[0]), G.inv))));
+    const int iy = min(G.nc[1] - 1, max(0, (int)floorf(__fmul_rn(__fsub_rn(y, G.mn[1]), G.inv))));
+    const int iz = min(G.nc[2] - 1, max(0, (int)floorf(__fmul_rn(__fsub_rn(z, G.mn[2]), G.inv))));
+    return (uint32_t)ix + (uint32_t)G.nc[0] * ((uint32_t)iy + (uint32_t)G.nc[1] * (uint32_t)iz);
+}
+
+__global__ void __launch_bounds__(kThreads) k_sor_key(const float4* __restrict__ pts, const uint32_t* __restrict__ seg_off,
+                                                      const SorGrid* __restrict__ grids, uint32_t* __restrict__ keys) {
+    const int s = blockIdx.y;
+    const uint32_t beg = seg_off[s], n = seg_off[s + 1] - beg;
+    const SorGrid G = grids[s];
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        const float4 p = pts[beg + i];
+        keys[beg + i] = sor_cell(G, p.x, p.y, p.z);
+    }
+}
+
+// rows of the frame's table that exist get begin = end = 0 (empty); rows past nc[1]*nc[2] are never read
+__global__ void __launch_bounds__(kThreads) k_sor_rows_clear(const SorGrid* __restrict__ grids, uint32_t* __restrict__ row_begin,
+                                                             uint32_t* __restrict__ row_end) {
+    const int s = blockIdx.y;
+    const uint32_t rows = (uint32_t)grids[s].nc[1] * (uint32_t)grids[s].nc[2];
+    for (uint32_t r = blockIdx.x * kThreads + threadIdx.x; r < rows; r += gridDim.x * kThreads) {
+        row_begin[(size_t)s * kSorRowsCap + r] = 0u;
+        row_end[(size_t)s * kSorRowsCap + r] = 0u;
+    }
+}
+
+// sorted keys -> [begin, end) of every (y, z) row, positions relative to the segment; also copies the sorted keys,
+// values and points out of the sort's ping-pong buffers (which side holds a segment's result is per segment)
+__global__ void __launch_bounds__(kThreads) k_sor_rows(const uint32_t* __restrict__ keys0, const uint32_t* __restrict__ keys1,
+                                                       const uint32_t* __restrict__ vals0, const uint32_t* __restrict__ vals1,
+                                                       const SortPlan* __restrict__ plan, const float4* __restrict__ pts,
+                                                       const uint32_t* __restrict__ seg_off, const SorGrid* __restrict__ grids,
+                                                       uint32_t* __restrict__ row_begin, uint32_t* __restrict__ row_end,
+                                                       uint32_t* __restrict__ skeys, uint32_t* __restrict__ svals,
+                                                       float4* __restrict__ spts) {
+    const int s = blockIdx.y;
+    const uint32_t beg = seg_off[s], n = seg_off[s + 1] - beg;
+    const uint32_t nx = (uint32_t)grids[s].nc[0];
+    const int par = plan[s].final_parity;
+    const bool ident = plan[s].n_active == 0;   // nothing was sorted: values were never written (identity)
+    const uint32_t* keys = (par ? keys1 : keys0) + beg;
+    const uint32_t* vals = (par ? vals1 : vals0) + beg;
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        const uint32_t k = keys[i], r = k / nx;
+        if (i == 0 || keys[i - 1] / nx != r) row_begin[(size_t)s * kSorRowsCap + r] = i;
+        if (i + 1 == n || keys[i + 1] / nx != r) row_end[(size_t)s * kSorRowsCap + r] = i + 1;
+        const uint32_t v = ident ? beg + i : vals[i];
+        skeys[beg + i] = k;
+        svals[beg + i] = v;
+        spts[beg + i] = pts[v];
+    }
+}
+
+// one thread per query (sorted position).  Dynamic shared memory: (mean_k + 1) * kSorThreads floats.
+__global__ void __launch_bounds__(kSorThreads) k_sor_knn(const float4* __restrict__ spts, const uint32_t* __restrict__ keys,
+                                                         const uint32_t* __restrict__ vals, const uint32_t* __restrict__ seg_off,
+                                                         const SorGrid* __restrict__ grids, const uint32_t* __restrict__ row_begin,
+                                                         const uint32_t* __restrict__ row_end, int mean_k,
+                                                         float* __restrict__ dist) {
+    extern __shared__ float sor_heap[];
+    const int s = blockIdx.y;
+    const uint32_t beg = seg_off[s], n = seg_off[s + 1] - beg;
+    const uint32_t j = blockIdx.x * kSorThreads + threadIdx.x;
+    if (j >= n) return;
+    const SorGrid G = grids[s];
+    const int K = mean_k + 1;
+    float* h = sor_heap + threadIdx.x;   // element k at h[k * kSorThreads]
+#define SOR_H(k) h[(k) * kSorThreads]
+    const float4 q = spts[beg + j];
+    const uint32_t key = keys[beg + j];
+    const int nx = G.nc[0], ny = G.nc[1], nz = G.nc[2];
+    const int ix = (int)(key % (uint32_t)nx), rr = (int)(key / (uint32_t)nx), iy = rr % ny, iz = rr / ny;
+    const uint32_t* kseg = keys + beg;
+    const float4* pseg = spts + beg;
+    const uint32_t* rb = row_begin + (size_t)s * kSorRowsCap;
+    const uint32_t* re = row_end + (size_t)s * kSorRowsCap;
+    int cnt = 0;
+    for (int sh = 2;; ++sh) {
+        cnt = 0;
+        for (int dz = -sh; dz <= sh; ++dz) {
+            const int z = iz + dz;
+            if (z < 0 || z >= nz) continue;
+            for (int dy = -sh; dy <= sh; ++dy) {
+                const int y = iy + dy;
+                if (y < 0 || y >= ny) continue;
+                const uint32_t row = (uint32_t)y + (uint32_t)ny * (uint32_t)z;
+                const uint32_t e = re[row];
+                uint32_t lo = rb[row];
+                if (lo >= e) continue;
+                const uint32_t k0 = (uint32_t)max(0, ix - sh) + (uint32_t)nx * row, k1 = (uint32_t)min(nx - 1, ix + sh) + (uint32_t)nx * row;
+                if (kseg[lo] < k0) {   // lower_bound of k0 in the row
+                    uint32_t hi = e;
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (kseg[mid] < k0) lo = mid + 1; else hi = mid;
+                    }
+                }
+                for (uint32_t t = lo; t < e && kseg[t] <= k1; ++t) {
+                    const float4 p = pseg[t];
+                    const float dx = __fsub_rn(q.x, p.x), dy2 = __fsub_rn(q.y, p.y), dz2 = __fsub_rn(q.z, p.z);
+                    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy2, dy2)), __fmul_rn(dz2, dz2));
+                    if (cnt < K) {   // sift up
+                        int c = cnt++;
+                        while (c > 0) {
+                            const int par = (c - 1) >> 1;
+                            const float pv = SOR_H(par);
+                            if (pv >= d2) break;
+                            SOR_H(c) = pv;
+                            c = par;
+                        }
+                        SOR_H(c) = d2;
+                    } else if (d2 < SOR_H(0)) {   // replace the largest, sift down
+                        int c = 0;
+                        for (;;) {
+                            int ch = 2 * c + 1;
+                            if (ch >= K) break;
+                            float cv = SOR_H(ch);
+                            if (ch + 1 < K) {
+                                const float cv2 = SOR_H(ch + 1);
+                                if (cv2 > cv) { cv = cv2; ++ch; }
+                            }
+                            if (cv <= d2) break;
+                            SOR_H(c) = cv;
+                            c = ch;
+                        }
+                        SOR_H(c) = d2;
+                    }
+                }
+            }
+        }
+        const bool all = ix - sh <= 0 && ix + sh >= nx - 1 && iy - sh <= 0 && iy + sh >= ny - 1 && iz - sh <= 0 && iz + sh >= nz - 1;
+        const float reach = __fmul_rn((float)sh - 0.05f, G.c);
+        if (all || (cnt == K && SOR_H(0) <= __fmul_rn(reach, reach))) break;
+    }
+    // heapsort in place -> ascending; element 0 is the query itself (0.0)
+    for (int m = cnt - 1; m > 0; --m) {
+        const float last = SOR_H(m);
+        SOR_H(m) = SOR_H(0);
+        int c = 0;
+        for (;;) {
+            int ch = 2 * c + 1;
+            if (ch >= m) break;
+            float cv = SOR_H(ch);
+            if (ch + 1 < m) {
+                const float cv2 = SOR_H(ch + 1);
+                if (cv2 > cv) { cv = cv2; ++ch; }
+            }
+            if (cv <= last) break;
+            SOR_H(c) = cv;
+            c = ch;
+        }
+        SOR_H(c) = last;
+    }
+    double sum = 0.0;
+    for (int k = 1; k < cnt; ++k) sum = __dadd_rn(sum, __dsqrt_rn((double)SOR_H(k)));
+    dist[vals[beg + j]] = __double2float_rn(__ddiv_rn(sum, (double)mean_k));
+#undef SOR_H
+}
+
+// per frame: mean / stddev of the distances -> removal threshold (double).  One CTA per frame, fixed-order tree.
+__global__ void __launch_bounds__(kThreads) k_sor_stats(const float* __restrict__ dist, const uint32_t* __restrict__ seg_off,
+                                                        double stddev_mul, double* __restrict__ threshold) {
+    __shared__ double s_sum[kThreads], s_sq[kThreads];
+    const int s = blockIdx.x;
+    const uint32_t beg = seg_off[s], n = seg_off[s + 1] - beg;
+    double sum = 0.0, sq = 0.0;
+    for (uint32_t i = threadIdx.x; i < n; i += kThreads) {
+        const float d = dist[beg + i];
+        sum = __dadd_rn(sum, (double)d);
+        sq = __dadd_rn(sq, (double)__fmul_rn(d, d));   // PCL: float product
+    }
+    s_sum[threadIdx.x] = sum; s_sq[threadIdx.x] = sq;
+    __syncthreads();
+    for (int o = kThreads / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            s_sum[threadIdx.x] = __dadd_rn(s_sum[threadIdx.x], s_sum[threadIdx.x + o]);
+            s_sq[threadIdx.x] = __dadd_rn(s_sq[threadIdx.x], s_sq[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double nn = (double)n;
+        const double mean = __ddiv_rn(s_sum[0], nn);
+        const double var = __ddiv_rn(__dsub_rn(s_sq[0], __ddiv_rn(__dmul_rn(s_sum[0], s_sum[0]), nn)), __dsub_rn(nn, 1.0));
+        threshold[s] = __dadd_rn(mean, __dmul_rn(stddev_mul, __dsqrt_rn(var)));
+    }
+}
+
+// stable compaction of the kept points, per frame: counts per tile, then (after a scan) the copy
+__global__ void __launch_bounds__(kThreads) k_sor_count(const float* __restrict__ dist, const uint32_t* __restrict__ seg_off,
+                                                        const double* __restrict__ threshold, uint32_t tiles_ub,
+                                                        uint32_t* __restrict__ tile_cnt) {
+    __shared__ uint32_t s_c;
+    const int s = blockIdx.y;
+    const uint32_t beg = seg_off[s], n = seg_off[s + 1] - beg;
+    if (threadIdx.x == 0) s_c = 0;
+    __syncthreads();
+    const double thr = threshold[s];
+    uint32_t c = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t i = blockIdx.x * (kThreads * 4) + threadIdx.x * 4 + r;
+        if (i < n && !((double)dist[beg + i] > thr)) ++c;
+    }
+    c = __reduce_add_sync(kFull, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_c, c);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_cnt[(size_t)s * tiles_ub + blockIdx.x] = s_c;
+}
+
+__global__ void __launch_bounds__(kThreads) k_sor_compact(const float4* __restrict__ pts, const float* __restrict__ dist,
+                                                          const uint32_t* __restrict__ seg_off, const double* __restrict__ threshold,
+                                                          uint32_t tiles_ub, const uint32_t* __restrict__ tile_off,
+                                                          const uint32_t* __restrict__ total, int n_seg,
+                                                          float4* __restrict__ out, uint32_t* __restrict__ out_off) {
+    __shared__ uint32_t s_scan[34];
+    const int s = blockIdx.y;
+    const uint32_t beg = seg_off[s], n = seg_off[s + 1] - beg;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        out_off[s] = tile_off[(size_t)s * tiles_ub];
+        if (s == n_seg - 1) out_off[n_seg] = *total;
+    }
+    const double thr = threshold[s];
+    uint32_t flags = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t i = blockIdx.x * (kThreads * 4) + threadIdx.x * 4 + r;
+        if (i < n && !((double)dist[beg + i] > thr)) flags |= 1u << r;
+    }
+    uint32_t tot;
+    uint32_t o = tile_off[(size_t)s * tiles_ub + blockIdx.x] + block_excl_scan((uint32_t)__popc(flags), s_scan, tot);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        if (flags & (1u << r)) out[o++] = pts[beg + blockIdx.x * (kThreads * 4) + threadIdx.x * 4 + r];
+}
+
+}  // namespace o3r

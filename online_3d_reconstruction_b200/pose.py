@@ -171,6 +171,16 @@ class Pose:
         k = m.value
         return out[:k].copy(), keys[:k].copy(), counts[:k].copy(), bool(pt.value)
 
+    def statisticalOutlierRemoval(self, pts, mean_k=50, stddev_mul=1.0):
+        """pcl::StatisticalOutlierRemoval on a host cloud -> (keep mask u8, mean neighbour distances f32, threshold)."""
+        pts = np.ascontiguousarray(pts, dtype=abi.POINT)
+        keep = np.zeros(max(1, pts.size), dtype=np.uint8)
+        dist = np.zeros(max(1, pts.size), dtype=np.float32)
+        thr = C.c_double(0)
+        self._check(self._L.o3r_sor(self._h, pts.ctypes.data, pts.size, mean_k, float(stddev_mul), keep.ctypes.data,
+                                    dist.ctypes.data, C.byref(thr)))
+        return keep[:pts.size], dist[:pts.size], thr.value
+
     def blur(self, src, kernel, mode):
         src = np.ascontiguousarray(src, dtype=np.uint8)
         dst = np.empty_like(src)

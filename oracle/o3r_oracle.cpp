@@ -137,6 +137,121 @@ void bilateral_u8(const uint8_t* src, size_t sstep, int rows, int cols, int cn, 
         }
 }
 
+
+/* ---- pcl::StatisticalOutlierRemoval<PointXYZRGB> (PCL 1.8 filters/impl/statistical_outlier_removal.hpp; third-party, not
+ * under /root/reference; call site pose_functions.cpp:1673-1686 with setMeanK(50), setStddevMulThresh(1.0)) -------------
+ * For every point: nearestKSearch(point, mean_k + 1) on a pcl::KdTreeFLANN (exact search, flann::L2_Simple<float>:
+ * d2 = ((dx*dx) + (dy*dy)) + (dz*dz) in float); dist_i = (float)(sum_{k=1..mean_k} sqrt((double)d2_k) / mean_k), k = 0 being
+ * the query itself; then mean / stddev of dist over all points in double (sum, sq_sum += dist*dist with a float product),
+ * variance = (sq_sum - sum*sum/n) / (n - 1), threshold = mean + mul * stddev; a point is REMOVED iff dist > threshold.
+ * Restated from memory of the PCL sources ("parity unpinned"): the unqualified sqrt() is taken as the double overload and
+ * a cloud with fewer than mean_k + 1 points (where PCL reads past the returned neighbours) sums what exists.
+ * The k-NN itself is exact, so how it is found does not matter: here a uniform grid whose cube around the query grows
+ * until the (mean_k+1)-th smallest distance is provably inside it; orc_sor(..., brute = 1) checks every pair instead. */
+struct SorHeap {   /* max-heap of the smallest `cap` squared distances seen */
+    std::vector<float> h; size_t cap;
+    explicit SorHeap(size_t c) : cap(c) { h.reserve(c); }
+    void clear() { h.clear(); }
+    void push(float d) {
+        if (h.size() < cap) { h.push_back(d); std::push_heap(h.begin(), h.end()); }
+        else if (d < h.front()) { std::pop_heap(h.begin(), h.end()); h.back() = d; std::push_heap(h.begin(), h.end()); }
+    }
+};
+inline float sor_d2(const o3r_point& a, const o3r_point& b) {
+    const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+    return ((dx * dx) + (dy * dy)) + (dz * dz);
+}
+inline float sor_mean_dist(SorHeap& H, int mean_k) {
+    std::sort(H.h.begin(), H.h.end());   /* ascending: k = 0 (the query, 0.0) first */
+    double sum = 0.0;
+    for (size_t k = 1; k < H.h.size(); ++k) sum += std::sqrt((double)H.h[k]);
+    return (float)(sum / mean_k);
+}
+
+void sor_distances(const o3r_point* pts, size_t n, int mean_k, int threads, bool brute, float* dist) {
+    const size_t K = (size_t)mean_k + 1;
+    if (n == 0) return;
+    if (brute || n <= K) {
+        auto work = [&](size_t lo, size_t hi) {
+            SorHeap H(K);
+            for (size_t i = lo; i < hi; ++i) {
+                H.clear();
+                for (size_t j = 0; j < n; ++j) H.push(sor_d2(pts[i], pts[j]));
+                dist[i] = sor_mean_dist(H, mean_k);
+            }
+        };
+        std::vector<std::thread> th;
+        const int T = std::max(1, threads);
+        for (int t = 0; t < T; ++t) th.emplace_back(work, n * t / T, n * (t + 1) / T);
+        for (auto& x : th) x.join();
+        return;
+    }
+    /* uniform grid: cell size from the density of a surface-like cloud, enlarged until the tables stay small */
+    float mn[3] = {pts[0].x, pts[0].y, pts[0].z}, mx[3] = {pts[0].x, pts[0].y, pts[0].z};
+    for (size_t i = 1; i < n; ++i) {
+        const float v[3] = {pts[i].x, pts[i].y, pts[i].z};
+        for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], v[a]); mx[a] = std::max(mx[a], v[a]); }
+    }
+    double ext[3] = {(double)mx[0] - mn[0], (double)mx[1] - mn[1], (double)mx[2] - mn[2]};
+    double e[3] = {ext[0], ext[1], ext[2]};
+    std::sort(e, e + 3);
+    const double area = std::max(e[2] * e[1], 1e-12);
+    double c = std::sqrt((double)K * area / (3.141592653589793 * (double)n));
+    c = std::max(c, 1e-6);
+    long long nc[3];
+    for (;;) {
+        for (int a = 0; a < 3; ++a) nc[a] = (long long)(ext[a] / c) + 2;
+        if (nc[0] * nc[1] * nc[2] <= (1ll << 31) && nc[1] * nc[2] <= (1ll << 22)) break;
+        c *= 1.26;
+    }
+    const double inv = 1.0 / c;
+    auto cell = [&](const o3r_point& p, long long ijk[3]) {
+        const float v[3] = {p.x, p.y, p.z};
+        for (int a = 0; a < 3; ++a) ijk[a] = std::min<long long>(nc[a] - 1, std::max<long long>(0, (long long)std::floor(((double)v[a] - mn[a]) * inv)));
+    };
+    std::vector<std::pair<long long, uint32_t>> order(n);
+    for (size_t i = 0; i < n; ++i) {
+        long long ijk[3];
+        cell(pts[i], ijk);
+        order[i] = {ijk[0] + nc[0] * (ijk[1] + nc[1] * ijk[2]), (uint32_t)i};
+    }
+    std::sort(order.begin(), order.end());
+    const size_t rows = (size_t)(nc[1] * nc[2]);
+    std::vector<uint32_t> rb(rows + 1, 0);
+    for (size_t i = 0; i < n; ++i) rb[(size_t)(order[i].first / nc[0]) + 1]++;
+    for (size_t r = 0; r < rows; ++r) rb[r + 1] += rb[r];
+    auto work = [&](size_t lo, size_t hi) {
+        SorHeap H(K);
+        for (size_t i = lo; i < hi; ++i) {
+            long long q[3];
+            cell(pts[i], q);
+            for (long long s = 1;; ++s) {
+                H.clear();
+                for (long long dz = -s; dz <= s; ++dz)
+                    for (long long dy = -s; dy <= s; ++dy) {
+                        const long long y = q[1] + dy, z = q[2] + dz;
+                        if (y < 0 || y >= nc[1] || z < 0 || z >= nc[2]) continue;
+                        const size_t r = (size_t)(y + nc[1] * z);
+                        const long long k0 = std::max<long long>(0, q[0] - s) + nc[0] * (long long)r,
+                                        k1 = std::min<long long>(nc[0] - 1, q[0] + s) + nc[0] * (long long)r;
+                        auto b = std::lower_bound(order.begin() + rb[r], order.begin() + rb[r + 1], std::make_pair(k0, 0u));
+                        for (; b != order.begin() + rb[r + 1] && b->first <= k1; ++b) H.push(sor_d2(pts[i], pts[b->second]));
+                    }
+                const bool all = q[0] - s <= 0 && q[0] + s >= nc[0] - 1 && q[1] - s <= 0 && q[1] + s >= nc[1] - 1 &&
+                                 q[2] - s <= 0 && q[2] + s >= nc[2] - 1;
+                /* every point outside the cube is farther than (s - 0.05) cells (the margin covers the cell rounding) */
+                const double reach = (s - 0.05) * c;
+                if (all || (H.h.size() == K && (double)H.h.front() <= reach * reach)) break;
+            }
+            dist[i] = sor_mean_dist(H, mean_k);
+        }
+    };
+    std::vector<std::thread> th;
+    const int T = std::max(1, threads);
+    for (int t = 0; t < T; ++t) th.emplace_back(work, n * t / T, n * (t + 1) / T);
+    for (auto& x : th) x.join();
+}
+
 struct DispReader {
     const o3r_params* p;
     const o3r_frame* f;
@@ -415,12 +530,40 @@ int orc_voxel_grid(const o3r_point* pts, size_t n, float lx, float ly, float lz,
     return rc;
 }
 
+int orc_sor(const o3r_point* pts, size_t n, int mean_k, double stddev_mul, int threads, int brute,
+            uint8_t* keep, float* dist_out) {
+    if ((n && !pts) || !keep || mean_k < 1) return O3R_ERR_INVALID;
+    std::vector<float> dist(n);
+    sor_distances(pts, n, mean_k, threads, brute != 0, dist.data());
+    double sum = 0, sq_sum = 0;
+    for (size_t i = 0; i < n; ++i) {
+        sum += dist[i];
+        sq_sum += dist[i] * dist[i];   /* float product, as in PCL */
+    }
+    const double mean = sum / (double)n;
+    const double variance = (sq_sum - sum * sum / (double)n) / ((double)n - 1);
+    const double stddev = std::sqrt(variance);
+    const double threshold = mean + stddev_mul * stddev;
+    for (size_t i = 0; i < n; ++i) keep[i] = !(dist[i] > threshold);
+    if (dist_out) std::memcpy(dist_out, dist.data(), n * sizeof(float));
+    return O3R_OK;
+}
+
 int orc_downsample_pt_cloud(const o3r_params* p, const o3r_point* pts, size_t n, int combined,
                             o3r_point* out, size_t cap, size_t* n_out) {
     std::vector<o3r_point> tmp(pts, pts + n); /* pose_functions.cpp:1660-1669 */
     if (combined)
         for (size_t i = 0; i < n; ++i) tmp[i].z += 500; /* :1666 */
-    /* :1673-1686 StatisticalOutlierRemoval(50, 1.0) when !combined && jump_pixels > 0: NOT RESTATED (§8f-1) */
+    if (!combined && p->jump_pixels > 0 && p->sor_mean_k > 0) { /* :1673-1686 */
+        std::vector<uint8_t> keep(n);
+        int rs = orc_sor(tmp.data(), n, p->sor_mean_k, p->sor_stddev_mul, 1, 0, keep.data(), nullptr);
+        if (rs) return rs;
+        size_t m = 0;
+        for (size_t i = 0; i < n; ++i)
+            if (keep[i]) tmp[m++] = tmp[i];
+        tmp.resize(m);
+        n = m;
+    }
     int rc;
     if (combined) { /* :1691-1695 */
         rc = orc_voxel_grid(tmp.data(), n, (float)p->voxel_size, (float)p->voxel_size, 1000.0f,

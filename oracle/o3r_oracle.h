@@ -49,6 +49,11 @@ int orc_voxel_grid(const o3r_point* pts, size_t n, float lx, float ly, float lz,
 
 /* downsamplePtCloud  pose_functions.cpp:1654-1709 (StatisticalOutlierRemoval :1673-1686 EXCLUDED,
  * SURVEY §8f-1). */
+/* pcl::StatisticalOutlierRemoval (pose_functions.cpp:1673-1686): keep[i] = 0 for removed points; dist_out (optional)
+ * receives every point's mean distance to its mean_k nearest neighbours.  brute = 1: all-pairs search (small clouds). */
+int orc_sor(const o3r_point* pts, size_t n, int mean_k, double stddev_mul, int threads, int brute,
+            uint8_t* keep, float* dist_out);
+
 int orc_downsample_pt_cloud(const o3r_params* p, const o3r_point* pts, size_t n, int combined,
                             o3r_point* out, size_t cap, size_t* n_out);
 

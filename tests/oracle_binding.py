@@ -29,6 +29,7 @@ def lib():
         P, F = C.POINTER(abi.Params), C.POINTER(abi.Frame)
         vp, sz, szp = C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)
         L.orc_blur_u8.argtypes = [vp, sz, C.c_int, C.c_int, C.c_int, C.c_int, vp, sz]
+        L.orc_sor.argtypes = [vp, sz, C.c_int, C.c_double, C.c_int, C.c_int, vp, vp]
         L.orc_bilateral_u8.argtypes = [vp, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp, sz]
         L.orc_create_single_img_pt_cloud.argtypes = [P, F, C.c_int, vp, sz, szp, vp, sz, szp]
         L.orc_transform_pt_cloud.argtypes = [vp, sz, C.POINTER(C.c_float), vp]
@@ -71,6 +72,16 @@ def bilateral_u8(src, d, sigma_color, sigma_space):
     _check(lib().orc_bilateral_u8(src.ctypes.data, src.strides[0], src.shape[0], src.shape[1], cn, d, float(sigma_color),
                                   float(sigma_space), dst.ctypes.data, dst.strides[0]), "bilateral")
     return dst
+
+
+def sor(pts, mean_k=50, stddev_mul=1.0, threads=4, brute=False):
+    """pcl::StatisticalOutlierRemoval -> (keep mask u8, mean neighbour distances f32)."""
+    pts = np.ascontiguousarray(pts, dtype=abi.POINT)
+    keep = np.zeros(max(1, pts.size), dtype=np.uint8)
+    dist = np.zeros(max(1, pts.size), dtype=np.float32)
+    _check(lib().orc_sor(pts.ctypes.data, pts.size, mean_k, float(stddev_mul), threads, int(brute), keep.ctypes.data,
+                         dist.ctypes.data), "sor")
+    return keep[:pts.size], dist[:pts.size]
 
 
 def max_points(p, n_kp=0):

@@ -302,6 +302,70 @@ def test_blur_rejections():
         P.createAndTransformPtCloud(fr)  # cv::medianBlur asserts on even ksize -> empty cloud in the reference
 
 
+# ------------------------------------------------------------------------------------------------- SOR
+def _frame_points(seed, geom, J=1, n_kp=0):
+    keep = []
+    p = abi.make_params(jump_pixels=J, dont_downsample=True, **geom)
+    fr = _frames(seed, 1, geom["rows"], geom["cols"], keep=keep, n_kp=n_kp)[0]
+    return ob.create_and_transform_pt_cloud(p, fr, abi.DISP_U8)
+
+
+@pytest.mark.parametrize("J,n_kp,mean_k", [(1, 0, 50), (3, 200, 50), (7, 400, 20), (15, 1500, 50)])
+def test_sor_distances_and_mask_bit_exact(J, n_kp, mean_k):
+    """pcl::StatisticalOutlierRemoval (pose_functions.cpp:1673-1686): every point's mean distance to its mean_k nearest
+    neighbours must equal the oracle's bit for bit (exact k-NN, float squared distances, ascending double sum), the
+    removal mask must be identical; the threshold (cloud statistics, reduced in tree order) within 1e-12 relative."""
+    pts = _frame_points(170 + J, SMALL4, J=J, n_kp=n_kp)
+    assert len(pts) > mean_k + 1
+    keep_o, dist_o = ob.sor(pts, mean_k, 1.0, brute=len(pts) < 6000)
+    with Pose(abi.make_params(**SMALL4)) as P:
+        keep, dist, thr = P.statisticalOutlierRemoval(pts, mean_k, 1.0)
+    assert np.array_equal(dist.view(np.uint32), dist_o.view(np.uint32))
+    assert np.array_equal(keep, keep_o)
+    d = dist_o.astype(np.float64)
+    sq = (dist_o * dist_o).astype(np.float64)
+    n = len(d)
+    exp_thr = d.sum() / n + np.sqrt((sq.sum() - d.sum() ** 2 / n) / (n - 1))
+    assert abs(thr - exp_thr) <= 1e-12 * exp_thr
+    assert 0.5 < keep.mean() < 1.0
+
+
+def test_sor_ragged_clouds():
+    """Fewer points than mean_k + 1, duplicates (zero distances), one far outlier, a single point."""
+    rng = np.random.default_rng(9)
+    base = _frame_points(180, SMALL)[:400].copy()
+    with Pose(abi.make_params(**SMALL)) as P:
+        for pts in (base[:30], base[:1], np.concatenate([base[:200], base[:200]]), base):
+            pts = pts.copy()
+            if len(pts) > 100:
+                pts["x"][7] += 50.0   # a far outlier: removed
+            keep_o, dist_o = ob.sor(pts, 50, 1.0, brute=True)
+            keep, dist, _ = P.statisticalOutlierRemoval(pts, 50, 1.0)
+            assert np.array_equal(dist.view(np.uint32), dist_o.view(np.uint32))
+            assert np.array_equal(keep, keep_o)
+            if len(pts) > 100:
+                assert keep[7] == 0
+
+
+@pytest.mark.parametrize("J,n_kp", [(1, 0), (4, 300)])
+def test_frame_cloud_with_sor_matches_reference_composition(J, n_kp):
+    """createAndTransformPtCloud with the reference's full per-frame downsample (pose_functions.cpp:1654-1709):
+    StatisticalOutlierRemoval(50, 1.0), then VoxelGrid(voxel_size / 5) on the filtered cloud."""
+    keep = []
+    p = abi.make_params(jump_pixels=J, voxel_size=0.05, sor_mean_k=50, **SMALL4)
+    frames = _frames(185, 3, SMALL4["rows"], SMALL4["cols"], keep=keep, n_kp=n_kp)
+    with Pose(p) as P:
+        for fr in frames[:2]:
+            _eq(P.createAndTransformPtCloud(fr), ob.create_and_transform_pt_cloud(p, fr, abi.DISP_U8))
+        cloud, n, counts = ob.run_cycle(p, frames, abi.DISP_U8, 4)
+        got_counts = P.createCycleClouds(frames)
+        assert np.array_equal(got_counts, counts)
+        _eq(P.lastCyclePoints(), cloud[:n])
+        _eq(P.downsamplePtCloud(), ob.downsample_pt_cloud(p, cloud[:n], True))
+    p0 = abi.make_params(jump_pixels=J, voxel_size=0.05, **SMALL4)
+    assert len(ob.create_and_transform_pt_cloud(p0, frames[0], abi.DISP_U8)) > len(ob.create_and_transform_pt_cloud(p, frames[0], abi.DISP_U8))
+
+
 # ---------------------------------------------------------------------------------- cycles + global cloud
 def _oracle_cycles(p, cycles):
     cloud, n = None, 0
