@@ -48,7 +48,11 @@ WORKLOADS = {
     "config4_sweep_720p_v002": (720, 1280, abi.DISP_U8, 1, 0.02, 1, False, 50, 1004, 1.0),
     "config5_4k_u16_v001": (2160, 3840, abi.DISP_U16, 1, 0.01, 1, False, 10, 1005, 3.0),
     "config1_sparse_720p": (720, 1280, abi.DISP_U8, 15, 0.05, 1, False, 50, 1001, 1.0),
+    # configs[1] with the reference's StatisticalOutlierRemoval(50, 1.0) in front of the per-frame VoxelGrid
+    # (pose_functions.cpp:1673-1686) — the full per-frame composition of the reference, SURVEY 8f-1
+    "config2_semidense_720p_sor": (720, 1280, abi.DISP_U8, 1, 0.05, 1, False, 50, 1002, 1.0),
 }
+SOR_MEAN_K = {"config2_semidense_720p_sor": 50}
 
 
 def peaks():
@@ -119,7 +123,7 @@ def params_for(wl, device, merge_mode=abi.MERGE_ACCUMULATE_TILED):
     rows, cols, dt, J, v, mp, nd, F, seed, qs = WORKLOADS[wl]
     return abi.make_params(rows=rows, cols=cols, jump_pixels=J, voxel_size=v, min_points_per_voxel=mp,
                            dont_downsample=nd, Q=synth.q_scaled(qs), device=device, max_batch_frames=F,
-                           merge_mode=merge_mode)
+                           merge_mode=merge_mode, sor_mean_k=SOR_MEAN_K.get(wl, 0))
 
 
 def frames_array(disp_ptrs, disp_step, bgr_ptrs, bgr_step, Ts):
@@ -326,7 +330,9 @@ def run_ours(args, rank, world, local_rank):
                    "valid_points_per_step_per_gpu": n_valid, "per_frame_voxels_per_step_per_gpu": stats["n_vox"],
                    "resident_cells_after_timed_region": cells_after_value,
                    "l2": f"inputs ({F * (rows * cols * bd + rows * cols * 3) / 1e6:.0f} MB/step) and intermediates exceed the 126 MB L2",
-                   "sor": "StatisticalOutlierRemoval excluded on GPU and CPU sides (not built)",
+                   "sor": ("StatisticalOutlierRemoval(50, 1.0) applied per frame on both the GPU and the CPU side" if wl in SOR_MEAN_K
+                           else "north_star path: StatisticalOutlierRemoval not applied on either side (sor_mean_k = 0); "
+                                "--workload config2_semidense_720p_sor runs the reference's full per-frame composition"),
                    "parallelism": f"frames f mod {world}; NCCL all-to-all of hash-partitioned cells" if world > 1 else "single GPU"},
         "clocks": clk, "wall_ms_per_step": wall / K,
         "e2e": {"value": frames_total / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e / K,
@@ -377,7 +383,7 @@ def run_reference(args, rank, world):
             "steps": K, "warmup": W, "ms_per_step": t / K * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8->f64->f32", "data": "synthetic",
             "config": {"workload": wl, "frames_per_step": sample_frames, "note": "CPU port of the reference path "
-                       "(oracle/, g++ -O2; the reference was built with no -O flag); SOR excluded"},
+                       "(oracle/, g++ -O2; the reference was built with no -O flag); " + ("with SOR" if wl in SOR_MEAN_K else "no SOR")},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                              "sample": f"{K} cycles of {sample_frames} frames + combined downsample each"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -422,7 +428,7 @@ def main():
         cpu_cycle(wl, disp[:4], bgr[:4], T[0][:4], threads)  # warm
         t = cpu_cycle(wl, disp[:n], bgr[:n], T[args.warmup][:n], threads)
         res["cpu_baseline"] = {"value": n / t, "unit": "frames/s", "cores": threads, "kind": "port",
-                               "sample": f"1 cycle of {n} frames + combined downsample, {t:.2f} s, SOR excluded"}
+                               "sample": f"1 cycle of {n} frames + combined downsample, {t:.2f} s, " + ("with SOR" if wl in SOR_MEAN_K else "no SOR")}
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

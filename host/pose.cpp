@@ -50,7 +50,7 @@ struct Pose {
     double dist_nearby = 2, voxel_size = 0.1;
     unsigned min_points_per_voxel = 1;
     bool downsample = false, only_MAVLink = false, dont_downsample = false, dont_icp = false, log_stuff = true,
-         preview = false, use_segment_labels = false, run3d_reconstruction = true;
+         preview = false, use_segment_labels = false, run3d_reconstruction = true, sor = true;
     string read_PLY_filename0, calib_file = "cam13calib.yml";
     string dataFilesPrefix = "data_files/", pose_file = "pose.txt", images_times_file = "images.txt",
            imageNumbersFile = "images/image_numbers.txt";
@@ -85,6 +85,7 @@ void Pose::printUsage() {
             "  path overrides (the reference hard-codes these, pose.h:129-137): --data_root DIR --image_prefix P\n"
             "      --disparity_prefix P --segmentlbl_prefix P --output DIR --calib FILE\n"
             "  extensions: --blur_mode bilateral|median|box (default bilateral = the reference) --pose_corrections FILE --device N\n"
+            "              --no_sor (skip the StatisticalOutlierRemoval the reference applies per frame when jump_pixels > 0)\n"
             "  not in this driver (host-side tools of the reference): --visualize --align_point_cloud --smooth_surface\n"
             "      --mesh_surface --segment_cloud --segment_cloud_only --displayUAVPositions\n";
 }
@@ -133,6 +134,7 @@ int Pose::parseCmdArgs(int argc, char** argv) {
         else if (a == "--calib") calib_file = need("file");
         else if (a == "--pose_corrections") pose_corrections_file = need("file");
         else if (a == "--device") device = atoi(need("n"));
+        else if (a == "--no_sor") sor = false;
         else if (a == "--blur_mode") { const string m = need("mode"); blur_mode = (m == "box") ? O3R_BLUR_BOX : (m == "median") ? O3R_BLUR_MEDIAN : O3R_BLUR_BILATERAL; }
         else {
             cout << atoi(argv[i]) << endl;
@@ -291,6 +293,7 @@ static o3r_ctx* make_ctx(Pose& P, int merge_mode, int max_batch) {
     p.jump_pixels = P.jump_pixels; p.blur_kernel = P.blur_kernel; p.blur_mode = P.blur_mode;
     p.voxel_size = P.voxel_size; p.min_points_per_voxel = P.min_points_per_voxel;
     p.dont_downsample = P.dont_downsample; p.use_segment_labels = P.use_segment_labels ? 1 : 0;
+    p.sor_mean_k = (P.sor && P.jump_pixels > 0) ? 50 : 0; p.sor_stddev_mul = 1.0;   // pose_functions.cpp:1673-1686
     p.disp_divisor = 200.0; p.merge_mode = merge_mode; p.device = P.device; p.max_batch_frames = max(1, max_batch);
     o3r_ctx* ctx = nullptr;
     if (o3r_create(&p, &ctx) != O3R_OK) { cerr << "o3r_create: " << o3r_last_error(nullptr) << endl; return nullptr; }

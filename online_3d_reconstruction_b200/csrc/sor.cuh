@@ -22,6 +22,10 @@ namespace o3r {
 constexpr int kSorThreads = 128;
 constexpr int kSorRowsCap = 1 << 18;   // (y, z) rows of cells per frame; the cell is enlarged until they fit
 constexpr int kSorMaxK = 128;          // mean_k + 1 <= 128
+#ifndef O3R_SOR_CALIB_RANK
+#define O3R_SOR_CALIB_RANK 115
+#endif
+constexpr int kSorCalibRank = O3R_SOR_CALIB_RANK;   // which of the 128 sorted sample radii sizes the cell (115 = 90th percentile; measured: the median makes the hard phase 3x longer)
 
 struct SorGrid {
     float mn[3];
@@ -131,88 +135,109 @@ __global__ void __launch_bounds__(kThreads) k_sor_rows(const uint32_t* __restric
     }
 }
 
-// one thread per query (sorted position).  Dynamic shared memory: (mean_k + 1) * kSorThreads floats.
-__global__ void __launch_bounds__(kSorThreads) k_sor_knn(const float4* __restrict__ spts, const uint32_t* __restrict__ keys,
-                                                         const uint32_t* __restrict__ vals, const uint32_t* __restrict__ seg_off,
-                                                         const SorGrid* __restrict__ grids, const uint32_t* __restrict__ row_begin,
-                                                         const uint32_t* __restrict__ row_end, int mean_k,
-                                                         float* __restrict__ dist) {
-    extern __shared__ float sor_heap[];
-    const int s = blockIdx.y;
-    const uint32_t beg = seg_off[s], n = seg_off[s + 1] - beg;
-    const uint32_t j = blockIdx.x * kSorThreads + threadIdx.x;
-    if (j >= n) return;
-    const SorGrid G = grids[s];
-    const int K = mean_k + 1;
-    float* h = sor_heap + threadIdx.x;   // element k at h[k * kSorThreads]
 #define SOR_H(k) h[(k) * kSorThreads]
-    const float4 q = spts[beg + j];
-    const uint32_t key = keys[beg + j];
+// One pass of the exact (mean_k + 1)-NN search of a query: scans the cube of (2*sh+1)^3 cells around it into the thread's
+// max-heap (element k at h[k * kSorThreads]).  Returns true when the result is proven: the heap holds K entries and its
+// top lies inside the cube (every unscanned point is farther than (sh - 0.05) cells), or the cube covers the whole grid.
+// cnt = heap entries, top = the heap's largest entry when cnt == K.
+__device__ __forceinline__ bool sor_pass(const SorGrid& G, const float4 q, const int ix, const int iy, const int iz,
+                                         const uint32_t* __restrict__ kseg, const float4* __restrict__ pseg,
+                                         const uint32_t* __restrict__ rb, const uint32_t* __restrict__ re, const int K,
+                                         float* __restrict__ h, const int sh, int& cnt, float& top) {
     const int nx = G.nc[0], ny = G.nc[1], nz = G.nc[2];
-    const int ix = (int)(key % (uint32_t)nx), rr = (int)(key / (uint32_t)nx), iy = rr % ny, iz = rr / ny;
-    const uint32_t* kseg = keys + beg;
-    const float4* pseg = spts + beg;
-    const uint32_t* rb = row_begin + (size_t)s * kSorRowsCap;
-    const uint32_t* re = row_end + (size_t)s * kSorRowsCap;
-    int cnt = 0;
-    for (int sh = 2;; ++sh) {
-        cnt = 0;
-        for (int dz = -sh; dz <= sh; ++dz) {
-            const int z = iz + dz;
-            if (z < 0 || z >= nz) continue;
-            for (int dy = -sh; dy <= sh; ++dy) {
-                const int y = iy + dy;
-                if (y < 0 || y >= ny) continue;
-                const uint32_t row = (uint32_t)y + (uint32_t)ny * (uint32_t)z;
-                const uint32_t e = re[row];
-                uint32_t lo = rb[row];
-                if (lo >= e) continue;
-                const uint32_t k0 = (uint32_t)max(0, ix - sh) + (uint32_t)nx * row, k1 = (uint32_t)min(nx - 1, ix + sh) + (uint32_t)nx * row;
-                if (kseg[lo] < k0) {   // lower_bound of k0 in the row
-                    uint32_t hi = e;
-                    while (lo < hi) {
-                        const uint32_t mid = (lo + hi) >> 1;
-                        if (kseg[mid] < k0) lo = mid + 1; else hi = mid;
-                    }
+    cnt = 0;
+    top = 0.f;
+    // rows are visited ring by ring around the query's own row, so the heap's top is close to final after the first
+    // few rows and later candidates rarely replace anything; once the heap is full, a row whose (y, z) interval is
+    // farther from the query than sqrt(top) is skipped without touching memory (2 % of a cell of slack for the float
+    // rounding of the cell assignment)
+    const float slack = __fmul_rn(0.02f, G.c);
+    for (int ring = 0; ring <= sh; ++ring)
+    for (int dz = -ring; dz <= ring; ++dz) {
+        const int z = iz + dz;
+        if (z < 0 || z >= nz) continue;
+        const float zlo = __fadd_rn(G.mn[2], __fmul_rn((float)z, G.c));
+        const float gz = fmaxf(0.f, __fsub_rn(fmaxf(__fsub_rn(zlo, q.z), __fsub_rn(q.z, __fadd_rn(zlo, G.c))), slack));
+        for (int dy = -ring; dy <= ring; ++dy) {
+            if (max(abs(dy), abs(dz)) != ring) continue;
+            const int y = iy + dy;
+            if (y < 0 || y >= ny) continue;
+            if (cnt == K) {
+                const float ylo = __fadd_rn(G.mn[1], __fmul_rn((float)y, G.c));
+                const float gy = fmaxf(0.f, __fsub_rn(fmaxf(__fsub_rn(ylo, q.y), __fsub_rn(q.y, __fadd_rn(ylo, G.c))), slack));
+                if (__fadd_rn(__fmul_rn(gy, gy), __fmul_rn(gz, gz)) > top) continue;
+            }
+            const uint32_t row = (uint32_t)y + (uint32_t)ny * (uint32_t)z;
+            const uint32_t e = re[row];
+            uint32_t lo = rb[row];
+            if (lo >= e) continue;
+            const uint32_t k0 = (uint32_t)max(0, ix - sh) + (uint32_t)nx * row, k1 = (uint32_t)min(nx - 1, ix + sh) + (uint32_t)nx * row;
+            if (kseg[lo] < k0) {   // lower_bound of k0 in the row
+                uint32_t hi = e;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (kseg[mid] < k0) lo = mid + 1; else hi = mid;
                 }
-                for (uint32_t t = lo; t < e && kseg[t] <= k1; ++t) {
-                    const float4 p = pseg[t];
-                    const float dx = __fsub_rn(q.x, p.x), dy2 = __fsub_rn(q.y, p.y), dz2 = __fsub_rn(q.z, p.z);
-                    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy2, dy2)), __fmul_rn(dz2, dz2));
-                    if (cnt < K) {   // sift up
-                        int c = cnt++;
-                        while (c > 0) {
-                            const int par = (c - 1) >> 1;
-                            const float pv = SOR_H(par);
-                            if (pv >= d2) break;
-                            SOR_H(c) = pv;
-                            c = par;
-                        }
-                        SOR_H(c) = d2;
-                    } else if (d2 < SOR_H(0)) {   // replace the largest, sift down
-                        int c = 0;
-                        for (;;) {
-                            int ch = 2 * c + 1;
-                            if (ch >= K) break;
-                            float cv = SOR_H(ch);
-                            if (ch + 1 < K) {
-                                const float cv2 = SOR_H(ch + 1);
-                                if (cv2 > cv) { cv = cv2; ++ch; }
-                            }
-                            if (cv <= d2) break;
-                            SOR_H(c) = cv;
-                            c = ch;
-                        }
-                        SOR_H(c) = d2;
+            }
+            for (uint32_t t = lo; t < e && kseg[t] <= k1; ++t) {
+                const float4 p = pseg[t];
+                const float dx = __fsub_rn(q.x, p.x), dy = __fsub_rn(q.y, p.y), dz = __fsub_rn(q.z, p.z);
+                const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                if (cnt < K) {   // sift up
+                    int c = cnt++;
+                    while (c > 0) {
+                        const int par = (c - 1) >> 1;
+                        const float pv = SOR_H(par);
+                        if (pv >= d2) break;
+                        SOR_H(c) = pv;
+                        c = par;
                     }
+                    SOR_H(c) = d2;
+                    if (cnt == K) top = SOR_H(0);
+                } else if (d2 < top) {   // replace the largest, sift down
+                    int c = 0;
+                    for (;;) {
+                        int ch = 2 * c + 1;
+                        if (ch >= K) break;
+                        float cv = SOR_H(ch);
+                        if (ch + 1 < K) {
+                            const float cv2 = SOR_H(ch + 1);
+                            if (cv2 > cv) { cv = cv2; ++ch; }
+                        }
+                        if (cv <= d2) break;
+                        SOR_H(c) = cv;
+                        c = ch;
+                    }
+                    SOR_H(c) = d2;
+                    top = SOR_H(0);
                 }
             }
         }
-        const bool all = ix - sh <= 0 && ix + sh >= nx - 1 && iy - sh <= 0 && iy + sh >= ny - 1 && iz - sh <= 0 && iz + sh >= nz - 1;
-        const float reach = __fmul_rn((float)sh - 0.05f, G.c);
-        if (all || (cnt == K && SOR_H(0) <= __fmul_rn(reach, reach))) break;
     }
-    // heapsort in place -> ascending; element 0 is the query itself (0.0)
+    const bool all = ix - sh <= 0 && ix + sh >= nx - 1 && iy - sh <= 0 && iy + sh >= ny - 1 && iz - sh <= 0 && iz + sh >= nz - 1;
+    const float reach = __fmul_rn((float)sh - 0.05f, G.c);
+    return all || (cnt == K && top <= __fmul_rn(reach, reach));
+}
+
+// the cube that is certain to prove the result after a pass that did not: the ball of radius sqrt(top) holds K points, so
+// the K-th neighbour is no farther; without a full heap the cube just doubles
+__device__ __forceinline__ int sor_next_sh(const SorGrid& G, int sh, int cnt, int K, float top) {
+    if (cnt == K) return max(sh + 1, (int)ceilf(__fadd_rn(__fmul_rn(sqrtf(top), G.inv), 0.06f)));
+    return sh * 2;
+}
+
+// full search: passes until proven
+__device__ __forceinline__ int sor_query(const SorGrid& G, const float4 q, const int ix, const int iy, const int iz,
+                                         const uint32_t* __restrict__ kseg, const float4* __restrict__ pseg,
+                                         const uint32_t* __restrict__ rb, const uint32_t* __restrict__ re, const int K,
+                                         float* __restrict__ h, int sh, float& top) {
+    int cnt;
+    while (!sor_pass(G, q, ix, iy, iz, kseg, pseg, rb, re, K, h, sh, cnt, top)) sh = sor_next_sh(G, sh, cnt, K, top);
+    return cnt;
+}
+
+// heapsort in place (ascending; element 0 is the query itself, 0.0), then PCL's sum over k = 1 .. in that order
+__device__ __forceinline__ float sor_mean_distance(float* __restrict__ h, int cnt, int mean_k) {
     for (int m = cnt - 1; m > 0; --m) {
         const float last = SOR_H(m);
         SOR_H(m) = SOR_H(0);
@@ -233,8 +258,126 @@ __global__ void __launch_bounds__(kSorThreads) k_sor_knn(const float4* __restric
     }
     double sum = 0.0;
     for (int k = 1; k < cnt; ++k) sum = __dadd_rn(sum, __dsqrt_rn((double)SOR_H(k)));
-    dist[vals[beg + j]] = __double2float_rn(__ddiv_rn(sum, (double)mean_k));
+    return __double2float_rn(__ddiv_rn(sum, (double)mean_k));
+}
 #undef SOR_H
+
+// Calibration: the exact (mean_k + 1)-NN radius of 128 evenly spaced sample queries per frame on the first grid (whose
+// cell comes from a surface-density guess), and from their 90th percentile the cell of the grid the full search runs on:
+// cell = r90 / 1.9, so that the first cube (2 cells each way) already proves the result for ~90 % of the queries while
+// holding ~2x the points of the exact ball.  Layered / noisy clouds are several times sparser than the guess assumes.
+__global__ void __launch_bounds__(kSorThreads) k_sor_calib(const float4* __restrict__ spts, const uint32_t* __restrict__ keys,
+                                                           const uint32_t* __restrict__ seg_off, SorGrid* __restrict__ grids,
+                                                           GridParams* __restrict__ plan_grids, const uint32_t* __restrict__ bbox,
+                                                           const uint32_t* __restrict__ row_begin,
+                                                           const uint32_t* __restrict__ row_end, int mean_k) {
+    extern __shared__ float sor_heap[];
+    __shared__ float s_r[kSorThreads];
+    __shared__ float s_r90;
+    const int s = blockIdx.x;
+    const uint32_t beg = seg_off[s], n = seg_off[s + 1] - beg;
+    const int K = mean_k + 1;
+    if (n <= (uint32_t)K) return;   // every query scans the whole cloud anyway
+    const SorGrid G = grids[s];
+    const uint32_t j = (uint32_t)(((unsigned long long)threadIdx.x * n) / kSorThreads);
+    const float4 q = spts[beg + j];
+    const uint32_t key = keys[beg + j];
+    const int ix = (int)(key % (uint32_t)G.nc[0]), rr = (int)(key / (uint32_t)G.nc[0]), iy = rr % G.nc[1], iz = rr / G.nc[1];
+    float* h = sor_heap + threadIdx.x;
+    // at most two passes per sample (the second over at most 13^3 cells): a sample that is still unproven is an outlier
+    // of the radius distribution and simply ranks last
+    float top;
+    int cnt;
+    const uint32_t* rb = row_begin + (size_t)s * kSorRowsCap;
+    const uint32_t* re = row_end + (size_t)s * kSorRowsCap;
+    bool ok = sor_pass(G, q, ix, iy, iz, keys + beg, spts + beg, rb, re, K, h, 2, cnt, top);
+    if (!ok) ok = sor_pass(G, q, ix, iy, iz, keys + beg, spts + beg, rb, re, K, h, min(sor_next_sh(G, 2, cnt, K, top), 6), cnt, top);
+    s_r[threadIdx.x] = (ok && cnt == K) ? sqrtf(top) : 3.0e38f;
+    if (threadIdx.x == 0) s_r90 = 0.f;
+    __syncthreads();
+    const float mine = s_r[threadIdx.x];
+    int rank = 0;
+    for (int t = 0; t < kSorThreads; ++t) rank += (s_r[t] < mine) || (s_r[t] == mine && t < (int)threadIdx.x);
+    if (rank == kSorCalibRank) s_r90 = mine;
+    __syncthreads();
+    if (threadIdx.x == 0 && s_r90 > 0.f && s_r90 < 1.0e38f) {
+        double ext[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) ext[a] = (double)ord2f(bbox[6 * s + 3 + a]) - (double)G.mn[a];
+        double c = fmax((double)s_r90 / 1.9, 1e-6);
+        long long nc[3];
+        for (;;) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) nc[a] = (long long)(ext[a] / c) + 2;
+            if (nc[0] * nc[1] * nc[2] <= (1ll << 31) && nc[1] * nc[2] <= (long long)kSorRowsCap) break;
+            c *= 1.26;
+        }
+        SorGrid N = G;
+        N.c = (float)c;
+        N.inv = (float)(1.0 / c);
+        N.nc[0] = (int)nc[0]; N.nc[1] = (int)nc[1]; N.nc[2] = (int)nc[2];
+        grids[s] = N;
+        const long long cells = nc[0] * nc[1] * nc[2];
+        plan_grids[s].key_bits = cells > 1 ? 64 - __clzll(cells - 1) : 1;
+    }
+}
+
+// Phase 1: one thread per query (sorted position), ONE pass over the 5^3 cube.  Proven queries (~90 %) are finished; the
+// others go to the hard list {position in the batch, frame << 16 | cube to scan next}, so that their long searches run in
+// warps of their own (phase 2) instead of stalling the 31 easy queries of their warp.
+// Dynamic shared memory of both kernels: (mean_k + 1) * kSorThreads floats.
+__global__ void __launch_bounds__(kSorThreads) k_sor_knn(const float4* __restrict__ spts, const uint32_t* __restrict__ keys,
+                                                         const uint32_t* __restrict__ vals, const uint32_t* __restrict__ seg_off,
+                                                         const SorGrid* __restrict__ grids, const uint32_t* __restrict__ row_begin,
+                                                         const uint32_t* __restrict__ row_end, int mean_k,
+                                                         float* __restrict__ dist, uint2* __restrict__ hard,
+                                                         uint32_t* __restrict__ n_hard) {
+    extern __shared__ float sor_heap[];
+    const int s = blockIdx.y;
+    const uint32_t beg = seg_off[s], n = seg_off[s + 1] - beg;
+    const uint32_t j = blockIdx.x * kSorThreads + threadIdx.x;
+    if (j >= n) return;
+    const SorGrid G = grids[s];
+    const int K = mean_k + 1;
+    float* h = sor_heap + threadIdx.x;
+    const float4 q = spts[beg + j];
+    const uint32_t key = keys[beg + j];
+    const int ix = (int)(key % (uint32_t)G.nc[0]), rr = (int)(key / (uint32_t)G.nc[0]), iy = rr % G.nc[1], iz = rr / G.nc[1];
+    int cnt;
+    float top;
+    if (sor_pass(G, q, ix, iy, iz, keys + beg, spts + beg, row_begin + (size_t)s * kSorRowsCap, row_end + (size_t)s * kSorRowsCap, K,
+                 h, 2, cnt, top)) {
+        dist[vals[beg + j]] = sor_mean_distance(h, cnt, mean_k);
+    } else {
+        const int sh = min(sor_next_sh(G, 2, cnt, K, top), 65535);
+        hard[atomicAdd(n_hard, 1u)] = make_uint2(beg + j, ((uint32_t)s << 16) | (uint32_t)sh);
+    }
+}
+
+// Phase 2: the hard queries, densely packed.  (Launched over an upper bound; the count is read from the device.)
+__global__ void __launch_bounds__(kSorThreads) k_sor_knn_hard(const float4* __restrict__ spts, const uint32_t* __restrict__ keys,
+                                                              const uint32_t* __restrict__ vals, const uint32_t* __restrict__ seg_off,
+                                                              const SorGrid* __restrict__ grids,
+                                                              const uint32_t* __restrict__ row_begin,
+                                                              const uint32_t* __restrict__ row_end, int mean_k,
+                                                              float* __restrict__ dist, const uint2* __restrict__ hard,
+                                                              const uint32_t* __restrict__ n_hard) {
+    extern __shared__ float sor_heap[];
+    const uint32_t i = blockIdx.x * kSorThreads + threadIdx.x;
+    if (i >= *n_hard) return;
+    const uint2 hq = hard[i];
+    const int s = (int)(hq.y >> 16);
+    const uint32_t beg = seg_off[s];
+    const SorGrid G = grids[s];
+    const int K = mean_k + 1;
+    float* h = sor_heap + threadIdx.x;
+    const float4 q = spts[hq.x];
+    const uint32_t key = keys[hq.x];
+    const int ix = (int)(key % (uint32_t)G.nc[0]), rr = (int)(key / (uint32_t)G.nc[0]), iy = rr % G.nc[1], iz = rr / G.nc[1];
+    float top;
+    const int cnt = sor_query(G, q, ix, iy, iz, keys + beg, spts + beg, row_begin + (size_t)s * kSorRowsCap,
+                              row_end + (size_t)s * kSorRowsCap, K, h, (int)(hq.y & 0xffffu), top);
+    dist[vals[hq.x]] = sor_mean_distance(h, cnt, mean_k);
 }
 
 // per frame: mean / stddev of the distances -> removal threshold (double).  One CTA per frame, fixed-order tree.

@@ -139,7 +139,7 @@ def test_driver_end_to_end_matches_python_path(pose_bin, tmp_path):
     for s in ("Cycle 0", "Cycle 1", "Point Cloud Creation time:", "Cycle time:", "disp_img_var", "Finished Pose Estimation"):
         assert s in log, s
     # the same frames through the Python mirror; poses as the driver parses them from pose.txt (9 decimals)
-    p = abi.make_params(rows=rows, cols=cols, jump_pixels=1, voxel_size=0.05, min_points_per_voxel=1)
+    p = abi.make_params(rows=rows, cols=cols, jump_pixels=1, voxel_size=0.05, min_points_per_voxel=1, sor_mean_k=50)
     keep = []
     frames = []
     for i, ((d, img, _), (t, *pp)) in enumerate(zip(seq, poses)):
@@ -180,7 +180,8 @@ def test_driver_use_segment_labels_runs_plane_fit_on_gpu(pose_bin, tmp_path):
     run_dir = os.path.join(out, sorted(os.listdir(out))[0])
     got, _, _ = read_ply(os.path.join(run_dir, "cloud.ply"))
     assert "plane_fitted_disp_img_var" in open(os.path.join(run_dir, "log.txt")).read()
-    p = abi.make_params(rows=rows, cols=cols, jump_pixels=1, voxel_size=0.05, min_points_per_voxel=1, use_segment_labels=True)
+    p = abi.make_params(rows=rows, cols=cols, jump_pixels=1, voxel_size=0.05, min_points_per_voxel=1, use_segment_labels=True,
+                        sor_mean_k=50)   # the driver applies the reference's per-frame SOR (jump_pixels > 0)
     keep, frames = [], []
     with Pose(p) as P:
         for i, ((d, img, _), (t, *pp)) in enumerate(zip(seq, poses)):
