@@ -287,7 +287,7 @@ int bilateral_lut(o3r_ctx* ctx, int k, BilateralLut* out) {
 template <typename KeyT>
 int sort_pairs(o3r_ctx* ctx, KeyT* k0, KeyT* k1, uint32_t* v0, uint32_t* v1, const uint32_t* seg_off, int n_seg,
                size_t per_seg_cap, const SortPlan* plan, int passes, int iota_first, const uint32_t* ghist,
-               const float4* gsrc = nullptr, float4* gdst = nullptr) {
+               const float4* gsrc = nullptr, float4* gdst = nullptr, int ghist_is_prefix = 1) {
     const uint32_t tiles_ub = std::max(1u, cdiv(per_seg_cap, kRsTile));
     const size_t st_words = (size_t)n_seg * tiles_ub * kRsBins;
     // status words for every pass + one ticket per pass, cleared with one memset
@@ -299,7 +299,7 @@ int sort_pairs(o3r_ctx* ctx, KeyT* k0, KeyT* k1, uint32_t* v0, uint32_t* v1, con
     for (int p = 0; p < passes; ++p)
         LAUNCH_N(sizeof(KeyT) == 4 ? "k_rs_onesweep_u32" : "k_rs_onesweep_u64", (k_rs_onesweep<KeyT>), grid, kThreads,
                  rs_scatter_smem<KeyT>(), k0, k1, v0, v1, seg_off, plan, p, tiles_ub, ghist,
-                 status + st_words * p, tickets + p, iota_first, gsrc, gdst);
+                 status + st_words * p, tickets + p, iota_first, gsrc, gdst, ghist_is_prefix);
     return O3R_OK;
 }
 
@@ -1640,7 +1640,8 @@ int o3r_exchange_pack(o3r_ctx* ctx, int world, o3r_cell* send_dev, size_t cap, u
     { int rcu = upload_small(ctx, ctx->seg2.p, seg_h, 8); if (rcu) return rcu; }
     const uint32_t g = std::min<uint32_t>(cdiv(n, kThreads), 148 * 8);
     LAUNCH(k_owner, g, kThreads, 0, n, ctx->ckey.as<uint64_t>(), (uint32_t)world, sb.k0, sb.v0, ocnt);
-    rc = sort_pairs<uint32_t>(ctx, sb.k0, sb.k1, sb.v0, sb.v1, ctx->seg2.as<uint32_t>(), 1, n, plan, 1, 0, ocnt);
+    rc = sort_pairs<uint32_t>(ctx, sb.k0, sb.k1, sb.v0, sb.v1, ctx->seg2.as<uint32_t>(), 1, n, plan, 1, 0, ocnt, nullptr, nullptr,
+                              0 /* raw owner counts: they are also the result read back below */);
     if (rc) return rc;
     LAUNCH(k_pack_cells, g, kThreads, 0, n, sb.v1, ctx->ckey.as<uint64_t>(), ctx->cacc.as<float4>(),
            ctx->crgb.as<uint4>(), send_dev);

@@ -18,11 +18,20 @@
 
 namespace o3r {
 
-constexpr int kRsItems = 16;
+#ifndef O3R_RS_ITEMS
+#define O3R_RS_ITEMS 16
+#endif
+#ifndef O3R_RS_MINB
+#define O3R_RS_MINB 4
+#endif
+constexpr int kRsItems = O3R_RS_ITEMS;
 constexpr int kRsTile = kThreads * kRsItems;  // 4096 pairs per CTA
 // Measured on B200 (r01): 10-bit digits save a pass (28-bit index: 3 instead of 4) but the per-tile bin work
 // (warps x bins counters to prefix, 4 look-backs per thread) makes each pass ~50 % slower; 8 bits wins.
-constexpr int kRsMaxBits = 8;
+#ifndef O3R_RS_BITS
+#define O3R_RS_BITS 8
+#endif
+constexpr int kRsMaxBits = O3R_RS_BITS;
 constexpr int kRsBins = 1 << kRsMaxBits;      // bins at most per pass
 constexpr int kRsBpt = kRsBins / kThreads;    // bins per thread
 constexpr int kMaxPasses = 8;
@@ -83,9 +92,12 @@ __global__ void k_rs_layout(int n_seg, const GridParams* __restrict__ grids, int
 
 // ---- which passes run: skip digits that are constant over the segment and segments that need no sorting ---------
 // ghist[S][kMaxPasses][kRsBins]
-__global__ void k_rs_plan(const uint32_t* __restrict__ ghist, const uint32_t* __restrict__ seg_off,
-                          SortPlan* __restrict__ plan, const GridParams* __restrict__ grids) {
+// Finally turns each pass's histogram into its exclusive prefix (where every digit's run starts in the segment), which
+// is what the radix pass needs: computed once here instead of once per tile.
+__global__ void __launch_bounds__(kThreads) k_rs_plan(uint32_t* __restrict__ ghist, const uint32_t* __restrict__ seg_off,
+                                                      SortPlan* __restrict__ plan, const GridParams* __restrict__ grids) {
     __shared__ int s_trivial[kMaxPasses];
+    __shared__ uint32_t s_scan[34];
     const int s = blockIdx.x;
     const uint32_t n = seg_off[s + 1] - seg_off[s];
     const int np = plan[s].n_passes;
@@ -107,6 +119,16 @@ __global__ void k_rs_plan(const uint32_t* __restrict__ ghist, const uint32_t* __
         plan[s].parity_mask = pm;
         plan[s].final_parity = par;
         plan[s].n_active = na;
+    }
+    for (int p = 0; p < np; ++p) {
+        uint32_t* gh = ghist + ((size_t)s * kMaxPasses + p) * kRsBins + threadIdx.x * kRsBpt;
+        uint32_t h[kRsBpt], sum = 0;
+#pragma unroll
+        for (int q = 0; q < kRsBpt; ++q) { h[q] = gh[q]; sum += h[q]; }
+        uint32_t tot;
+        uint32_t e = block_excl_scan(sum, s_scan, tot);
+#pragma unroll
+        for (int q = 0; q < kRsBpt; ++q) { gh[q] = e; e += h[q]; }
     }
 }
 
@@ -189,11 +211,11 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
 }
 
 template <typename KeyT>
-__global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? 4 : 3) k_rs_onesweep(
+__global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? O3R_RS_MINB : (O3R_RS_MINB > 3 ? 3 : O3R_RS_MINB)) k_rs_onesweep(
     KeyT* __restrict__ keys0, KeyT* __restrict__ keys1, uint32_t* __restrict__ vals0, uint32_t* __restrict__ vals1,
     const uint32_t* __restrict__ seg_off, const SortPlan* __restrict__ plan, int pass, uint32_t tiles_ub,
     const uint32_t* __restrict__ ghist, uint32_t* __restrict__ status, uint32_t* __restrict__ ticket, int iota_first,
-    const float4* __restrict__ gsrc, float4* __restrict__ gdst) {
+    const float4* __restrict__ gsrc, float4* __restrict__ gdst, int ghist_is_prefix) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
     RsPair<KeyT>* s_pairs = reinterpret_cast<RsPair<KeyT>*>(rs_smem);
     uint16_t* cnt = reinterpret_cast<uint16_t*>(rs_smem + (size_t)kRsTile * sizeof(RsPair<KeyT>));   // [kWarps][1024]
@@ -203,9 +225,14 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? 4 : 3) k_rs_ones
 
     if (threadIdx.x == 0) *s_ticket = atomicAdd(ticket, 1u);
     __syncthreads();
+    // Tickets go round-robin over the segments (tile 0 of every segment, then tile 1 of every segment, ...): the CTAs
+    // resident at any moment are then a few consecutive tiles of EACH segment, and a tile's look-back meets an inclusive
+    // prefix after a handful of predecessors.  Segment-major tickets put all ~180 tiles of a frame in flight together,
+    // every one of them still LOCAL, and each look-back walked back to tile 0 (O(tiles^2) status reads per segment).
     const uint32_t lin = *s_ticket;
-    const int s = lin / tiles_ub;
-    const uint32_t t = lin - (uint32_t)s * tiles_ub;
+    const uint32_t n_seg = gridDim.x / tiles_ub;
+    const int s = (int)(lin % n_seg);
+    const uint32_t t = lin / n_seg;
     const uint32_t amask = plan[s].active_mask;
     if (!((amask >> pass) & 1u)) return;
     const uint32_t beg = seg_off[s], n = seg_off[s + 1] - beg;
@@ -229,22 +256,28 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? 4 : 3) k_rs_ones
     const unsigned lt = (1u << lane) - 1u;
     const int b0 = threadIdx.x * kRsBpt;   // this thread's bin(s)
 
-    {   // zero the warp-private u16 counters
-        uint32_t* cz = reinterpret_cast<uint32_t*>(cnt);
+    {   // every warp zeroes ITS OWN u16 counters (no CTA barrier stands between this and the ranking loop)
+        uint32_t* cz = reinterpret_cast<uint32_t*>(cnt + warp * kRsBins);
 #pragma unroll
-        for (int i = 0; i < kWarps * kRsBins / 2 / kThreads; ++i) cz[i * kThreads + threadIdx.x] = 0u;
+        for (int i = 0; i < kRsBins / 2 / 32; ++i) cz[i * 32 + lane] = 0u;
+        __syncwarp();
     }
     // exclusive scan of the segment's digit histogram = where each digit's run starts in the segment
     uint32_t dbase[kRsBpt];
     {
         const uint32_t* gh = ghist + ((size_t)s * kMaxPasses + pass) * kRsBins + b0;
-        uint32_t h[kRsBpt], sum = 0;
+        if (ghist_is_prefix) {   // k_rs_plan already scanned it
 #pragma unroll
-        for (int q = 0; q < kRsBpt; ++q) { h[q] = gh[q]; sum += h[q]; }
-        uint32_t tot;
-        uint32_t e = block_excl_scan(sum, s_scan, tot);
+            for (int q = 0; q < kRsBpt; ++q) dbase[q] = gh[q];
+        } else {
+            uint32_t h[kRsBpt], sum = 0;
 #pragma unroll
-        for (int q = 0; q < kRsBpt; ++q) { dbase[q] = e; e += h[q]; }
+            for (int q = 0; q < kRsBpt; ++q) { h[q] = gh[q]; sum += h[q]; }
+            uint32_t tot;
+            uint32_t e = block_excl_scan(sum, s_scan, tot);
+#pragma unroll
+            for (int q = 0; q < kRsBpt; ++q) { dbase[q] = e; e += h[q]; }
+        }
     }
 
     KeyT key[kRsItems];
