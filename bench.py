@@ -36,9 +36,9 @@ from online_3d_reconstruction_b200 import abi, synth  # noqa: E402
 
 # (workload, kernel) -> DRAM bytes per launch from `ncu --set full` (see profiles/r01*_ncu_*.txt)
 NCU_TRAFFIC = {
-    # profiles/r01f_ncu_full.txt: 7 launches per cycle (4 per-frame-index passes: 391.6, 547.3, 547.7, 548.0 MB;
-    # 3 combined-key passes: 369.6, 370.1, 371.0 MB) -> mean per launch
-    ("config2_semidense_720p", "k_rs_onesweep_u32"): 449.3e6,
+    # profiles/r01j_ncu_full.txt: 7 launches per cycle (4 per-frame-index passes: 406.0, 555.3, 555.0, 552.6 MB;
+    # 3 passes over the tile partials: 26.0, 25.9, 25.9 MB) -> mean per launch
+    ("config2_semidense_720p", "k_rs_onesweep_u32"): 306.7e6,
 }
 
 WORKLOADS = {
@@ -139,22 +139,26 @@ def frames_array(disp_ptrs, disp_step, bgr_ptrs, bgr_step, Ts):
 # per-kernel algorithmic bytes of one step (what the kernel must read + write once), keyed by profile name.
 # n_valid = points after the mask, n_vox = per-frame voxels of the cycle, np1 / np2 = radix passes of the per-frame
 # index sort / the combined-grid key sort (7-8 bit digits: 28-bit index -> 4, 20-bit key -> 3).
-def algorithmic_bytes(wl, n_valid, n_vox, n_cells_cycle, bd, np1=4, np2=3):
+def algorithmic_bytes(wl, n_valid, n_vox, n_cells_cycle, bd, np1=4, np2=3, n_part=0):
+    """n_part = tile partial cells of the cycle (O3R_MERGE_ACCUMULATE_TILED): the merge then sorts and reduces those
+    40-byte records instead of the n_vox per-frame voxels."""
     rows, cols, dt, J, v, mp, nd, F, seed, qs = WORKLOADS[wl]
     p = params_for(wl, 0)
     ny, nx = abi.scan_dims(p)
     npix = ny * nx * F
+    m, item = (n_part, 40) if n_part else (n_vox, 16)   # records the merge works on, bytes per gathered record
     return {
         "k_pre": npix * bd,
         "k_emit": npix * bd + npix * 3 + n_valid * (16 + (0 if nd else 4)),
         "k_rs_ghist_u32": n_valid * 4,
         # first pass reads keys only (values are the element index), every pass writes key + value
-        "k_rs_onesweep_u32": n_valid * (4 + 8) + (np1 - 1) * n_valid * 16 + np2 * n_vox * 16,
+        "k_rs_onesweep_u32": n_valid * (4 + 8) + (np1 - 1) * n_valid * 16 + np2 * m * 16,
         "k_vg_heads": n_valid * 4,
         "k_vg_reduce_w": n_valid * (4 + 4 + 16) + n_vox * 16,
-        "k_acc_key": n_vox * (16 + 8),
-        "k_acc_heads": n_vox * 4,
-        "k_acc_reduce": n_vox * (4 + 4 + 16) + n_cells_cycle * 40,
+        "k_cell_prereduce": n_vox * 16 + n_part * 40,
+        "k_acc_key": m * (item + 8),
+        "k_acc_heads": m * 4,
+        "k_acc_reduce": m * (4 + 4 + item) + n_cells_cycle * 40,
     }
 
 
@@ -210,6 +214,7 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             exchange()
         stats["n_vox"] = int(counts.sum())
+        stats["n_part"] = P.lastCyclePartials()
         if nd:   # --dont_downsample: cloud_small = cloud_big, nothing to compute; it is saved once at exit
             stats["n_out"] = 0
             return
@@ -218,7 +223,7 @@ def run_ours(args, rank, world, local_rank):
                 out = P.downsamplePtCloud(out_pin.numpy().view(abi.POINT))
             except O3RError:   # the cloud outgrew the pinned result buffer: grow it and read again
                 need = P.cloudSize() * abi.POINT.itemsize
-                out_pin = torch.empty((int(need * 1.5) + 15) // 16 * 16, dtype=torch.uint8).pin_memory()
+                out_pin = torch.empty((int(need * 4) + 15) // 16 * 16, dtype=torch.uint8).pin_memory()
                 out = P.downsamplePtCloud(out_pin.numpy().view(abi.POINT))
             stats["n_out"] = len(out)
         else:
@@ -288,7 +293,7 @@ def run_ours(args, rank, world, local_rank):
 
     n_valid = int(sum(int((a[p.bounding_box:rows - p.bounding_box, p.cols_start_aft_cutout:cols - p.bounding_box][::J, ::J].astype(np.float64)
                            / (p.disp_divisor if dt == abi.DISP_U16 else 1.0) > p.min_disparity).sum()) for a in disp))
-    alg = algorithmic_bytes(wl, n_valid, stats["n_vox"], max(new_cells_per_step, 1), bd)
+    alg = algorithmic_bytes(wl, n_valid, stats["n_vox"], max(new_cells_per_step, 1), bd, n_part=stats.get("n_part", 0))
     peak, peak_src = peaks()
     kern = sorted(prof.items(), key=lambda kv: -kv[1][1])
     total_kernel_ms = sum(v[1] for v in prof.values())
@@ -328,6 +333,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": wl, "frames_per_step_per_gpu": F, "frame": f"{cols}x{rows}", "jump_pixels": J,
                    "voxel_size": v, "min_points_per_voxel": mp, "dont_downsample": nd, "seq_len": F,
                    "valid_points_per_step_per_gpu": n_valid, "per_frame_voxels_per_step_per_gpu": stats["n_vox"],
+                   "tile_partials_per_step_per_gpu": stats.get("n_part", 0), "merge_mode": "ACCUMULATE_TILED",
                    "resident_cells_after_timed_region": cells_after_value,
                    "l2": f"inputs ({F * (rows * cols * bd + rows * cols * 3) / 1e6:.0f} MB/step) and intermediates exceed the 126 MB L2",
                    "sor": ("StatisticalOutlierRemoval(50, 1.0) applied per frame on both the GPU and the CPU side" if wl in SOR_MEAN_K

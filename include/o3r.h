@@ -262,6 +262,9 @@ int o3r_profile_read(o3r_ctx* ctx, char* buf, size_t cap);
 
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */
 uint64_t o3r_launch_count(const o3r_ctx* ctx);
+/* Tile partial cells the last batch produced (O3R_MERGE_ACCUMULATE_TILED; 0 otherwise): the record count the
+ * merge's sort and reduce ran on, for traffic accounting. */
+size_t o3r_last_batch_partials(const o3r_ctx* ctx);
 /* The CUDA stream all work of the context is issued on (a cudaStream_t) — for event timing. */
 void* o3r_stream(o3r_ctx* ctx);
 /* Blocks until all work issued on the context's stream has completed. */

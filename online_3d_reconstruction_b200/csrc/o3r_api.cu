@@ -164,6 +164,9 @@ struct o3r_ctx {
     }
 
     bool retain() const { return p.dont_downsample || p.merge_mode == O3R_MERGE_RETAIN; }
+    // tile pre-reduction is skipped while it does not reduce (probed again every 16th batch)
+    unsigned tiled_poor = 0, tiled_batches = 0;
+    bool tiled_now = false;
     bool tiled() const { return !p.dont_downsample && p.merge_mode == O3R_MERGE_ACCUMULATE_TILED; }
     int fail(int code, const std::string& m) { err = m; return code; }
     int fail_cuda(cudaError_t e, const char* what, int line) {
@@ -361,7 +364,7 @@ int vg_sorted_reduce(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const u
     const dim3 grid(A.tiles_ub, n_seg);
     uint32_t* cnt = ctx->counters.as<uint32_t>();
     LAUNCH(k_vg_heads, grid, kThreads, 0, A, ctx->head_cnt.as<uint32_t>());
-    LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->head_cnt.as<uint32_t>(), ctx->head_off.as<uint32_t>(), (uint32_t)nt,
+    LAUNCH(k_scan_u32, 1, kScanThreads, 0, ctx->head_cnt.as<uint32_t>(), ctx->head_off.as<uint32_t>(), (uint32_t)nt,
            cnt + CNT_VOX);
     if (fast && ctx->vg_short && !spts && !z_shift) {   // (the combined grid has long runs: staged kernel)
         // short runs (per-frame grid): warp-level reduce, no shared-memory staging, no carry chain
@@ -445,7 +448,7 @@ int acc_build_cycle_t(o3r_ctx* ctx, Items items, size_t n, bool use_resident, co
     tr.mark("ensures");
     LAUNCH_N("k_acc_heads", (k_acc_heads<KeyT>), A.tiles_ub, kThreads, 0, A, v0, v1, ctx->head_cnt.as<uint32_t>(),
              cnt + CNT_NEW);
-    LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->head_cnt.as<uint32_t>(), ctx->head_off.as<uint32_t>(), A.tiles_ub,
+    LAUNCH(k_scan_u32, 1, kScanThreads, 0, ctx->head_cnt.as<uint32_t>(), ctx->head_off.as<uint32_t>(), A.tiles_ub,
            cnt + CNT_CYC);
     LAUNCH_N("k_acc_reduce", (k_acc_reduce<KeyT, Items>), A.tiles_ub, kThreads, 0, A, items, ctx->head_off.as<uint32_t>(),
              ctx->ckey.as<uint64_t>(), ctx->cacc.as<float4>(), ctx->crgb.as<uint4>(), ctx->runwork.as<uint32_t>(),
@@ -529,7 +532,7 @@ int acc_apply_cycle(o3r_ctx* ctx) {
     tr.mark("ensures");
     LAUNCH(k_acc_update, tiles, kThreads, 0, cnt + CNT_CYC, ctx->cacc.as<float4>(), ctx->crgb.as<uint4>(),
            ctx->res_acc[cur].as<float4>(), ctx->res_rgb[cur].as<uint4>(), ctx->new_cnt.as<uint32_t>());
-    LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->new_cnt.as<uint32_t>(), ctx->new_off.as<uint32_t>(), tiles,
+    LAUNCH(k_scan_u32, 1, kScanThreads, 0, ctx->new_cnt.as<uint32_t>(), ctx->new_off.as<uint32_t>(), tiles,
            cnt + CNT_NEWSCAN);
     LAUNCH(k_acc_place_new, tiles, kThreads, 0, cnt + CNT_CYC, ctx->ckey.as<uint64_t>(), ctx->cacc.as<float4>(),
            ctx->crgb.as<uint4>(), ctx->new_off.as<uint32_t>(), ctx->res_keys[cur].as<uint64_t>(), cnt + CNT_NRES,
@@ -637,7 +640,7 @@ int sor_filter(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const uint32_
     LAUNCH(k_sor_stats, n_seg, kThreads, 0, ctx->sor_dist.as<float>(), seg_off, stddev_mul, ctx->sor_thr.as<double>());
     LAUNCH(k_sor_count, dim3(tiles, n_seg), kThreads, 0, ctx->sor_dist.as<float>(), seg_off, ctx->sor_thr.as<double>(), tiles,
            ctx->sor_cnt.as<uint32_t>());
-    LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->sor_cnt.as<uint32_t>(), ctx->sor_cntoff.as<uint32_t>(), (uint32_t)((size_t)tiles * n_seg),
+    LAUNCH(k_scan_u32, 1, kScanThreads, 0, ctx->sor_cnt.as<uint32_t>(), ctx->sor_cntoff.as<uint32_t>(), (uint32_t)((size_t)tiles * n_seg),
            cnt + CNT_PTS);
     LAUNCH(k_sor_compact, dim3(tiles, n_seg), kThreads, 0, pts, ctx->sor_dist.as<float>(), seg_off, ctx->sor_thr.as<double>(), tiles,
            ctx->sor_cntoff.as<uint32_t>(), cnt + CNT_PTS, n_seg, ctx->sor_pts.as<float4>(), ctx->sor_off.as<uint32_t>());
@@ -662,7 +665,7 @@ int launch_stage_a(o3r_ctx* ctx, const AParams& P, const FrameDev* fr, int n, co
     LAUNCH_N("k_pre", (k_pre<DT>), grid, kThreads, 0, P, fr, ctx->tile_cnt.as<uint32_t>(), ctx->bbox.as<uint32_t>(),
              opt.mask_dev);
     if (opt.mask_only) return O3R_OK;
-    LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->tile_cnt.as<uint32_t>(), ctx->tile_off.as<uint32_t>(),
+    LAUNCH(k_scan_u32, 1, kScanThreads, 0, ctx->tile_cnt.as<uint32_t>(), ctx->tile_off.as<uint32_t>(),
            (uint32_t)((size_t)P.tiles_per_frame * n), cnt + CNT_PTS);
     LAUNCH(k_a_post, cdiv(n + 1, kThreads), kThreads, 0, n, P.tiles_per_frame, ctx->tile_off.as<uint32_t>(),
            cnt + CNT_PTS, ctx->bbox.as<uint32_t>(), ctx->inv_f, ctx->inv_f, ctx->inv_f, P.want_keys,
@@ -950,7 +953,9 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
             int rc = carve_sort_u32(ctx, cap_chunk, sb);
             if (rc) return rc;
             if (!ctx->retain()) LAUNCH(k_cellbb_init, 1, 32, 0, reinterpret_cast<int*>(cnt + CNT_CELLBB));
-            if (ctx->tiled()) {   // worst case one partial per item; never reached in practice (~1/8)
+            ctx->tiled_now = ctx->tiled() && !(ctx->tiled_poor && (ctx->tiled_batches % 16) != 0);
+            ++ctx->tiled_batches;
+            if (ctx->tiled_now) {   // worst case one partial per item; never reached in practice (~1/8)
                 CU(ctx->partials.ensure(cap_batch * sizeof(o3r_cell)));
                 CU(ctx->pr_status.ensure(((size_t)cdiv(cap_chunk, kPrTile) + 16) * 4));
                 ZERO(cnt + CNT_PART, 8);
@@ -1027,7 +1032,7 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
                                   ctx->grids.as<GridParams>(), ctx->inv_f, ctx->inv_f, ctx->inv_f, 0, 0,
                                   ctx->vox.as<float4>(), goff + f0, nullptr, nullptr, !ctx->retain(), cnt + CNT_BASE);
             if (rc) return rc;
-            if (ctx->tiled()) {   // group the chunk's voxel centroids by combined-grid cell, tile by tile
+            if (ctx->tiled_now) {   // group the chunk's voxel centroids by combined-grid cell, tile by tile
                 const uint32_t pt = cdiv(cap_chunk, kPrTile);
                 uint32_t* stw = ctx->pr_status.as<uint32_t>();
                 ZERO(stw, ((size_t)pt + 16) * 4);
@@ -1058,13 +1063,19 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
         int rcf = flush_deferred_prefetch(ctx);
         if (rcf) return rcf;
     }
-    ctx->last_has_partials = ctx->last_is_vox && ctx->tiled();
+    ctx->last_has_partials = ctx->last_is_vox && ctx->tiled() && ctx->tiled_now;
     if (ctx->last_has_partials)
         CU(cudaMemcpyAsync(ctx->h_counters + CNT_PART, cnt + CNT_PART, 4, cudaMemcpyDeviceToHost, ctx->st));
     const double tr1 = now();
     CU(cudaStreamSynchronize(ctx->st));
     ctx->busy_set = -1;
     ctx->last_partials = ctx->last_has_partials ? ctx->h_counters[CNT_PART] : 0;
+    // The tile pre-reduction pays only when it reduces: a 40-byte partial replaces a 16-byte voxel in the merge.  On grids
+    // finer than the point spacing (e.g. 4K at voxel_size 0.01) nearly every voxel is its own cell: merge the voxels then.
+    if (ctx->last_has_partials) {
+        ctx->tiled_poor = ctx->last_partials * 2 > ctx->h_offs[n];
+        if (ctx->tiled_poor) { ctx->last_has_partials = false; ctx->last_partials = 0; }
+    }
     const double tr2 = now();
     if (ctx->last_has_cellbb) memcpy(ctx->last_cellbb, ctx->h_counters + CNT_CELLBB, 24);
     ctx->last_off.assign(ctx->h_offs, ctx->h_offs + n + 1);
@@ -1233,6 +1244,7 @@ void o3r_destroy(o3r_ctx* ctx) {
 }
 
 uint64_t o3r_launch_count(const o3r_ctx* ctx) { return ctx ? ctx->launches : 0; }
+size_t o3r_last_batch_partials(const o3r_ctx* ctx) { return (ctx && ctx->last_has_partials) ? ctx->last_partials : 0; }
 void* o3r_stream(o3r_ctx* ctx) { return ctx ? (void*)ctx->st : nullptr; }
 
 int o3r_sync(o3r_ctx* ctx) {
@@ -1480,7 +1492,7 @@ static int cloud_downsample_dev(o3r_ctx* ctx, const float4** res, size_t* m, boo
     CU(ctx->cacc.ensure(n_ub * 16));
     LAUNCH(k_acc_emit_cnt, tiles, kThreads, 0, cnt + CNT_NRES, ctx->res_acc[cur].as<float4>(), ctx->p.min_points_per_voxel,
            ctx->new_cnt.as<uint32_t>());
-    LAUNCH(k_scan_u32, 1, kThreads, 0, ctx->new_cnt.as<uint32_t>(), ctx->new_off.as<uint32_t>(), tiles, cnt + CNT_EMIT);
+    LAUNCH(k_scan_u32, 1, kScanThreads, 0, ctx->new_cnt.as<uint32_t>(), ctx->new_off.as<uint32_t>(), tiles, cnt + CNT_EMIT);
     LAUNCH(k_acc_emit, tiles, kThreads, 0, cnt + CNT_NRES, ctx->res_acc[cur].as<float4>(), ctx->res_rgb[cur].as<uint4>(),
            ctx->p.min_points_per_voxel, ctx->new_off.as<uint32_t>(), ctx->cacc.as<float4>());
     *res = ctx->cacc.as<float4>();

@@ -46,18 +46,49 @@ struct SortPlan {
     uint8_t bits[kMaxPasses];
 };
 
-// ---- generic single-segment exclusive scan (one CTA, coalesced, carry across iterations) ----------------
-__global__ void __launch_bounds__(kThreads) k_scan_u32(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                                                       uint32_t n, uint32_t* __restrict__ total_out) {
-    __shared__ uint32_t sm[34];
+// ---- generic single-segment exclusive scan (one CTA of 1024 threads, 4 per thread and iteration, carry across iterations) ----
+// The inputs are per-tile counts (tens of thousands of words): one wide CTA finishes them in a handful of iterations.
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads) k_scan_u32(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                           uint32_t n, uint32_t* __restrict__ total_out) {
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_tot;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t carry = 0;
-    for (uint32_t base = 0; base < n; base += kThreads * 4) {
+    for (uint32_t base = 0; base < n; base += kScanThreads * 4) {
         const uint32_t i = base + threadIdx.x * 4;
         uint32_t v[4];
+        if (i + 3 < n && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+            const uint4 q = *reinterpret_cast<const uint4*>(in + i);
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = (i + j < n) ? in[i + j] : 0u;
-        uint32_t tot;
-        uint32_t off = block_excl_scan(v[0] + v[1] + v[2] + v[3], sm, tot) + carry;
+            for (int j = 0; j < 4; ++j) v[j] = (i + j < n) ? in[i + j] : 0u;
+        }
+        const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+        uint32_t inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = s_w[lane];
+            uint32_t winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(kFull, winc, o);
+                if (lane >= o) winc += t;
+            }
+            s_w[lane] = winc - w;
+            if (lane == 31) s_tot = winc;
+        }
+        __syncthreads();
+        uint32_t off = carry + s_w[warp] + inc - mine;
+        const uint32_t tot = s_tot;
+        __syncthreads();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (i + j < n) out[i + j] = off;

@@ -59,6 +59,9 @@ class Pose:
         ny, nx = abi.scan_dims(self.params)
         return ny * nx
 
+    def lastCyclePartials(self):
+        return int(self._L.o3r_last_batch_partials(self._h))
+
     def launch_count(self):
         return int(self._L.o3r_launch_count(self._h))
 
