@@ -198,13 +198,13 @@ def run_ours(args, rank, world, local_rank):
     out_pin = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()   # pinned result buffer of the e2e leg (grown if the cloud outgrows it)
     stats = {}
 
+    info = torch.zeros(world + 8, dtype=torch.int32, device=dev) if world > 1 else None
+
     def exchange():
-        # hash-partitioned partial cells -> owners: pack on the GPU, grouped ncclSend/ncclRecv, merge on the GPU
-        counts = P.exchangePack(world, send.data_ptr(), cell_cap)
-        recv, n_recv = xchg.exchange_cells(send[:int(counts.sum()) * abi.CELL.itemsize], counts)
-        torch.cuda.current_stream().synchronize()
-        P.exchangeMerge(recv.data_ptr(), n_recv)
-        stats["exchange_cells_sent"] = int(counts.sum())
+        # hash-partitioned partial cells -> owners: pack on the GPU, all-gather of the headers (one host read), grouped
+        # ncclSend/ncclRecv, merge on the GPU — all queued on the context's stream
+        with torch.cuda.stream(stream):
+            stats["exchange_cells_sent"] = xchg.exchange_cycle(P, send, info)
 
     def step(s, host):
         """One cycle (pose.cpp:361-434) + the combined downsample of the global cloud (pose.cpp:527-531 / :645).

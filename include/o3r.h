@@ -248,6 +248,16 @@ int o3r_exchange_pack(o3r_ctx* ctx, int world, o3r_cell* send_dev, size_t cap, u
 /* Merge `n` received partial cells (DEVICE buffer, any order) into the resident shard. */
 int o3r_exchange_merge(o3r_ctx* ctx, const o3r_cell* recv_dev, size_t n);
 
+/* The same exchange without host round trips.  o3r_exchange_pack_dev queues the pack on the context's stream and
+ * returns at once; `info_dev` (DEVICE, world + 8 u32) receives the cells per owner, then the cycle's combined-grid cell
+ * range {imin, jmin, kmin, imax, jmax, kmax} as int32 (min > max when the batch was empty), then the cell count and a
+ * pad word — the header the ranks all-gather (on the same stream) to size the payload exchange.  `cap` must be at least
+ * o3r_exchange_bound(ctx), the host-known bound of the cells the pack can emit.  o3r_exchange_merge_bb takes the union
+ * of the gathered cell ranges, so the merge does not have to reduce (and wait for) the range of the received cells. */
+size_t o3r_exchange_bound(o3r_ctx* ctx);
+int o3r_exchange_pack_dev(o3r_ctx* ctx, int world, o3r_cell* send_dev, size_t cap, uint32_t* info_dev);
+int o3r_exchange_merge_bb(o3r_ctx* ctx, const o3r_cell* recv_dev, size_t n, const int bb[6]);
+
 /* When set, o3r_frames_cloud* keeps the batch's per-frame clouds but does not merge them into the
  * resident cloud; the caller runs o3r_exchange_pack / o3r_exchange_merge instead. */
 int o3r_set_defer_merge(o3r_ctx* ctx, int defer);

@@ -1003,9 +1003,12 @@ __host__ __device__ __forceinline__ uint64_t hash64(uint64_t x) {  // splitmix64
 }
 
 // owner of each cycle cell + per-owner histogram; keys32 = owner, vals = cell index (then one sort pass)
-__global__ void __launch_bounds__(kThreads) k_owner(uint32_t n_cyc, const uint64_t* __restrict__ ckey, uint32_t world,
-                                                    uint32_t* __restrict__ okeys, uint32_t* __restrict__ ovals,
-                                                    uint32_t* __restrict__ counts) {
+// (the cell count is read from the device; seg receives {0, n_cyc} for the sort that follows)
+__global__ void __launch_bounds__(kThreads) k_owner(const uint32_t* __restrict__ n_cyc_ptr, const uint64_t* __restrict__ ckey,
+                                                    uint32_t world, uint32_t* __restrict__ okeys, uint32_t* __restrict__ ovals,
+                                                    uint32_t* __restrict__ counts, uint32_t* __restrict__ seg) {
+    const uint32_t n_cyc = *n_cyc_ptr;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { seg[0] = 0u; seg[1] = n_cyc; }
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n_cyc; i += gridDim.x * kThreads) {
         const uint32_t o = (uint32_t)(hash64(ckey[i]) % world);
         okeys[i] = o;
@@ -1014,9 +1017,21 @@ __global__ void __launch_bounds__(kThreads) k_owner(uint32_t n_cyc, const uint64
     }
 }
 
-__global__ void __launch_bounds__(kThreads) k_pack_cells(uint32_t n_cyc, const uint32_t* __restrict__ order,
+// also publishes the exchange header: counts per owner, then the cycle's cell range (6 int32), then 2 pad words
+__global__ void __launch_bounds__(kThreads) k_pack_cells(const uint32_t* __restrict__ n_cyc_ptr, const uint32_t* __restrict__ order,
                                                          const uint64_t* __restrict__ ckey, const float4* __restrict__ cacc,
-                                                         const uint4* __restrict__ crgb, o3r_cell* __restrict__ out) {
+                                                         const uint4* __restrict__ crgb, o3r_cell* __restrict__ out,
+                                                         const uint32_t* __restrict__ counts, uint32_t world, int b0, int b1,
+                                                         int b2, int b3, int b4, int b5, uint32_t* __restrict__ info) {
+    const uint32_t n_cyc = *n_cyc_ptr;
+    if (blockIdx.x == 0 && info) {
+        for (uint32_t r = threadIdx.x; r < world; r += kThreads) info[r] = counts[r];
+        if (threadIdx.x == 0) {
+            const int bb[6] = {b0, b1, b2, b3, b4, b5};
+            for (int a = 0; a < 6; ++a) info[world + a] = (uint32_t)bb[a];
+            info[world + 6] = n_cyc; info[world + 7] = 0u;
+        }
+    }
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n_cyc; i += gridDim.x * kThreads) {
         const uint32_t h = order[i];
         const float4 a = cacc[h];

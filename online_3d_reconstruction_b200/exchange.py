@@ -72,6 +72,51 @@ def exchange_cells(send, counts, group=None):
     return recv, n_recv
 
 
+def exchange_cycle(P, send, info, group=None):
+    """One cycle's exchange with a single host round trip: pack on the GPU (queued), all-gather of the headers,
+    ONE read of the gathered headers (split sizes + cell ranges), grouped send/recv, merge on the GPU (queued).
+
+    P:    the rank's Pose (defer-merge mode); call this with torch's current stream set to P's stream
+          (`with torch.cuda.stream(torch.cuda.ExternalStream(P.stream()))`) so that the library's kernels and the
+          collectives are ordered without extra synchronisation.
+    send: uint8 device tensor of at least P.exchangeBound() cells; info: int32 device tensor of world + 8 words.
+    Returns the number of cells this rank sent.
+    """
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    P.exchangePackDevice(world, send.data_ptr(), send.numel() // CELL_BYTES, info.data_ptr())
+    gathered = torch.empty(world * (world + 8), dtype=torch.int32, device=send.device)
+    dist.all_gather_into_tensor(gathered, info, group=group)
+    g = gathered.cpu().numpy().reshape(world, world + 8)          # the one host sync of the exchange
+    counts = [int(c) for c in g[rank, :world]]
+    recv_counts = [int(g[src, rank]) for src in range(world)]
+    bbs = g[:, world:world + 6]
+    valid = bbs[:, 0] <= bbs[:, 3]
+    bb = None
+    if valid.any():
+        bb = list(bbs[valid, :3].min(axis=0)) + list(bbs[valid, 3:].max(axis=0))
+    n_recv = sum(recv_counts)
+    recv = torch.empty(max(n_recv, 1) * CELL_BYTES, dtype=torch.uint8, device=send.device)
+    s_off = np.concatenate([[0], np.cumsum(counts)]) * CELL_BYTES
+    r_off = np.concatenate([[0], np.cumsum(recv_counts)]) * CELL_BYTES
+    ops = []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        if recv_counts[peer]:
+            ops.append(dist.P2POp(dist.irecv, recv[r_off[peer]:r_off[peer + 1]], peer, group))
+        if counts[peer]:
+            ops.append(dist.P2POp(dist.isend, send[s_off[peer]:s_off[peer + 1]], peer, group))
+    if counts[rank]:
+        recv[r_off[rank]:r_off[rank + 1]].copy_(send[s_off[rank]:s_off[rank + 1]])
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    if n_recv:
+        P.exchangeMerge(recv.data_ptr(), n_recv, bb)
+    P._exchange_keepalive = recv     # the merge kernels are only queued: keep the buffer until the next cycle
+    return sum(counts)
+
+
 def merge_cells_host(cells):
     """Reference merge of partial cells on the host (tests): sort by key, add partials in order."""
     cells = np.asarray(cells, dtype=abi.CELL)

@@ -218,5 +218,15 @@ class Pose:
         self._check(self._L.o3r_exchange_pack(self._h, world, send_ptr, cap, counts.ctypes.data))
         return counts
 
-    def exchangeMerge(self, recv_ptr, n):
-        self._check(self._L.o3r_exchange_merge(self._h, recv_ptr, n))
+    def exchangeMerge(self, recv_ptr, n, bb=None):
+        if bb is None:
+            self._check(self._L.o3r_exchange_merge(self._h, recv_ptr, n))
+        else:
+            self._check(self._L.o3r_exchange_merge_bb(self._h, recv_ptr, n, (C.c_int * 6)(*[int(b) for b in bb])))
+
+    def exchangeBound(self):
+        return int(self._L.o3r_exchange_bound(self._h))
+
+    def exchangePackDevice(self, world, send_ptr, cap, info_ptr):
+        """Queues the pack on the context's stream; info_ptr = device buffer of world + 8 u32 (see o3r.h)."""
+        self._check(self._L.o3r_exchange_pack_dev(self._h, world, send_ptr, cap, info_ptr))

@@ -610,8 +610,9 @@ def test_full_resolution_properties_720p():
 
 
 # -------------------------------------------------------------------------------------------- multi-GPU
+@pytest.mark.parametrize("api", ["sync", "dev"])
 @pytest.mark.parametrize("mode", [abi.MERGE_ACCUMULATE, abi.MERGE_ACCUMULATE_TILED])
-def test_exchange_two_ranks_equals_single_rank(mode):
+def test_exchange_two_ranks_equals_single_rank(mode, api):
     """SURVEY §8e on one device: two contexts act as two ranks (frames f mod 2), exchange hash-partitioned
     partial cells, and the union of their shards must equal the single-rank result: keys, counts and colours
     exactly, centroids within 1e-5 (cross-rank partial sums reassociate)."""
@@ -630,13 +631,26 @@ def test_exchange_two_ranks_equals_single_rank(mode):
         for r in ranks:
             r.setDeferMerge(True)
         for frames in cycles:
-            sends, counts = [], []
+            sends, counts, bbs = [], [], []
             for r, P in enumerate(ranks):
                 P.createCycleClouds(frames[r::W])
                 buf = torch.empty(len(frames) * P.max_points_per_frame * abi.CELL.itemsize // W + 64, dtype=torch.uint8, device="cuda")
-                c = P.exchangePack(W, buf.data_ptr(), buf.numel() // abi.CELL.itemsize)
+                if api == "sync":
+                    c = P.exchangePack(W, buf.data_ptr(), buf.numel() // abi.CELL.itemsize)
+                else:   # the round-trip-free entry points: header on the device, cell range passed to the merge
+                    assert 0 < P.exchangeBound() <= buf.numel() // abi.CELL.itemsize
+                    info = torch.zeros(W + 8, dtype=torch.int32, device="cuda")
+                    P.exchangePackDevice(W, buf.data_ptr(), buf.numel() // abi.CELL.itemsize, info.data_ptr())
+                    P.sync()
+                    h = info.cpu().numpy()
+                    c = h[:W].astype(np.uint32)
+                    assert int(h[W + 6]) == int(c.sum()) <= P.exchangeBound()
+                    bbs.append(h[W:W + 6])
                 sends.append(buf)
                 counts.append(c)
+            bb = None
+            if bbs:
+                bb = list(np.min([b[:3] for b in bbs], axis=0)) + list(np.max([b[3:] for b in bbs], axis=0))
             for s, buf in enumerate(sends):   # the device buckets by the same hash the host mirror computes
                 sent = buf[:int(counts[s].sum()) * abi.CELL.itemsize].cpu().numpy().view(abi.CELL)
                 own = exchange.owner_of(sent["key"], W)
@@ -648,7 +662,7 @@ def test_exchange_two_ranks_equals_single_rank(mode):
                     parts.append(sends[s][off:off + int(counts[s][r]) * abi.CELL.itemsize])
                 recv = torch.cat(parts)
                 torch.cuda.synchronize()
-                P.exchangeMerge(recv.data_ptr(), recv.numel() // abi.CELL.itemsize)
+                P.exchangeMerge(recv.data_ptr(), recv.numel() // abi.CELL.itemsize, bb)
         shards = [P.downsamplePtCloud() for P in ranks]
     finally:
         for r in ranks:
