@@ -136,6 +136,28 @@ __global__ void __launch_bounds__(kThreads) k_sor_rows(const uint32_t* __restric
 }
 
 #define SOR_H(k) h[(k) * kSorThreads]
+// The heap is 4-ary (children of c: 4c+1 .. 4c+4): 3 levels for 51 entries instead of 6, and the four child loads of a
+// level are independent, so a sift costs half the dependent shared-memory round trips of a binary heap.
+// Sinks value v from position c in a heap of m entries.
+__device__ __forceinline__ void sor_sift_down(float* __restrict__ h, int c, const int m, const float v) {
+    for (;;) {
+        const int ch0 = 4 * c + 1;
+        if (ch0 >= m) break;
+        float cv = SOR_H(ch0);
+        int ch = ch0;
+#pragma unroll
+        for (int u = 1; u < 4; ++u) {
+            if (ch0 + u < m) {
+                const float w = SOR_H(ch0 + u);
+                if (w > cv) { cv = w; ch = ch0 + u; }
+            }
+        }
+        if (cv <= v) break;
+        SOR_H(c) = cv;
+        c = ch;
+    }
+    SOR_H(c) = v;
+}
 // One pass of the exact (mean_k + 1)-NN search of a query: scans the cube of (2*sh+1)^3 cells around it into the thread's
 // max-heap (element k at h[k * kSorThreads]).  Returns true when the result is proven: the heap holds K entries and its
 // top lies inside the cube (every unscanned point is farther than (sh - 0.05) cells), or the cube covers the whole grid.
@@ -162,16 +184,23 @@ __device__ __forceinline__ bool sor_pass(const SorGrid& G, const float4 q, const
             if (max(abs(dy), abs(dz)) != ring) continue;
             const int y = iy + dy;
             if (y < 0 || y >= ny) continue;
+            int xlo = max(0, ix - sh), xhi = min(nx - 1, ix + sh);
             if (cnt == K) {
                 const float ylo = __fadd_rn(G.mn[1], __fmul_rn((float)y, G.c));
                 const float gy = fmaxf(0.f, __fsub_rn(fmaxf(__fsub_rn(ylo, q.y), __fsub_rn(q.y, __fadd_rn(ylo, G.c))), slack));
-                if (__fadd_rn(__fmul_rn(gy, gy), __fmul_rn(gz, gz)) > top) continue;
+                const float rem = __fsub_rn(top, __fadd_rn(__fmul_rn(gy, gy), __fmul_rn(gz, gz)));
+                if (rem < 0.f) continue;
+                // only the cells of the row within sqrt(rem) of the query in x can still hold a closer point
+                const float dxm = __fadd_rn(sqrtf(rem), slack);
+                xlo = max(xlo, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.x, dxm), G.mn[0]), G.inv)) - 0);
+                xhi = min(xhi, (int)floorf(__fmul_rn(__fsub_rn(__fadd_rn(q.x, dxm), G.mn[0]), G.inv)));
+                if (xlo > xhi) continue;
             }
             const uint32_t row = (uint32_t)y + (uint32_t)ny * (uint32_t)z;
             const uint32_t e = re[row];
             uint32_t lo = rb[row];
             if (lo >= e) continue;
-            const uint32_t k0 = (uint32_t)max(0, ix - sh) + (uint32_t)nx * row, k1 = (uint32_t)min(nx - 1, ix + sh) + (uint32_t)nx * row;
+            const uint32_t k0 = (uint32_t)xlo + (uint32_t)nx * row, k1 = (uint32_t)xhi + (uint32_t)nx * row;
             if (kseg[lo] < k0) {   // lower_bound of k0 in the row
                 uint32_t hi = e;
                 while (lo < hi) {
@@ -186,7 +215,7 @@ __device__ __forceinline__ bool sor_pass(const SorGrid& G, const float4 q, const
                 if (cnt < K) {   // sift up
                     int c = cnt++;
                     while (c > 0) {
-                        const int par = (c - 1) >> 1;
+                        const int par = (c - 1) >> 2;
                         const float pv = SOR_H(par);
                         if (pv >= d2) break;
                         SOR_H(c) = pv;
@@ -195,20 +224,7 @@ __device__ __forceinline__ bool sor_pass(const SorGrid& G, const float4 q, const
                     SOR_H(c) = d2;
                     if (cnt == K) top = SOR_H(0);
                 } else if (d2 < top) {   // replace the largest, sift down
-                    int c = 0;
-                    for (;;) {
-                        int ch = 2 * c + 1;
-                        if (ch >= K) break;
-                        float cv = SOR_H(ch);
-                        if (ch + 1 < K) {
-                            const float cv2 = SOR_H(ch + 1);
-                            if (cv2 > cv) { cv = cv2; ++ch; }
-                        }
-                        if (cv <= d2) break;
-                        SOR_H(c) = cv;
-                        c = ch;
-                    }
-                    SOR_H(c) = d2;
+                    sor_sift_down(h, 0, K, d2);
                     top = SOR_H(0);
                 }
             }
@@ -241,20 +257,7 @@ __device__ __forceinline__ float sor_mean_distance(float* __restrict__ h, int cn
     for (int m = cnt - 1; m > 0; --m) {
         const float last = SOR_H(m);
         SOR_H(m) = SOR_H(0);
-        int c = 0;
-        for (;;) {
-            int ch = 2 * c + 1;
-            if (ch >= m) break;
-            float cv = SOR_H(ch);
-            if (ch + 1 < m) {
-                const float cv2 = SOR_H(ch + 1);
-                if (cv2 > cv) { cv = cv2; ++ch; }
-            }
-            if (cv <= last) break;
-            SOR_H(c) = cv;
-            c = ch;
-        }
-        SOR_H(c) = last;
+        sor_sift_down(h, 0, m, last);
     }
     double sum = 0.0;
     for (int k = 1; k < cnt; ++k) sum = __dadd_rn(sum, __dsqrt_rn((double)SOR_H(k)));
