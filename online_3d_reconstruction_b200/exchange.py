@@ -72,28 +72,27 @@ def exchange_cells(send, counts, group=None):
     return recv, n_recv
 
 
-def exchange_cycle(P, send, info, group=None):
-    """One cycle's exchange with a single host round trip: pack on the GPU (queued), all-gather of the headers,
-    ONE read of the gathered headers (split sizes + cell ranges), grouped send/recv, merge on the GPU (queued).
+def exchange_by_header(send, info, group=None):
+    """The transport half of a cycle's exchange: all-gather of the ranks' headers, ONE host read of the gathered
+    headers, grouped send/recv of the buckets.
 
-    P:    the rank's Pose (defer-merge mode); call this with torch's current stream set to P's stream
-          (`with torch.cuda.stream(torch.cuda.ExternalStream(P.stream()))`) so that the library's kernels and the
-          collectives are ordered without extra synchronisation.
-    send: uint8 device tensor of at least P.exchangeBound() cells; info: int32 device tensor of world + 8 words.
-    Returns the number of cells this rank sent.
+    send: uint8 tensor with this rank's cells bucketed by destination rank (as o3r_exchange_pack_dev leaves them).
+    info: int32 tensor of world + 8 words on the same device (o3r.h): cells per destination rank, the rank's
+          combined-grid cell range {imin, jmin, kmin, imax, jmax, kmax} (min > max when it sent nothing), cell count, pad.
+    Returns (recv uint8 tensor, n_recv, bb, n_sent): the cells this rank owns grouped by source rank, and the union of
+    the ranks' cell ranges (None when nobody sent anything).
     """
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    P.exchangePackDevice(world, send.data_ptr(), send.numel() // CELL_BYTES, info.data_ptr())
-    gathered = torch.empty(world * (world + 8), dtype=torch.int32, device=send.device)
-    dist.all_gather_into_tensor(gathered, info, group=group)
-    g = gathered.cpu().numpy().reshape(world, world + 8)          # the one host sync of the exchange
+    gathered = [torch.empty_like(info) for _ in range(world)]
+    dist.all_gather(gathered, info, group=group)
+    g = torch.stack(gathered).cpu().numpy().reshape(world, world + 8)   # the one host sync of the exchange
     counts = [int(c) for c in g[rank, :world]]
     recv_counts = [int(g[src, rank]) for src in range(world)]
     bbs = g[:, world:world + 6]
     valid = bbs[:, 0] <= bbs[:, 3]
     bb = None
     if valid.any():
-        bb = list(bbs[valid, :3].min(axis=0)) + list(bbs[valid, 3:].max(axis=0))
+        bb = [int(v) for v in bbs[valid, :3].min(axis=0)] + [int(v) for v in bbs[valid, 3:].max(axis=0)]
     n_recv = sum(recv_counts)
     recv = torch.empty(max(n_recv, 1) * CELL_BYTES, dtype=torch.uint8, device=send.device)
     s_off = np.concatenate([[0], np.cumsum(counts)]) * CELL_BYTES
@@ -111,10 +110,26 @@ def exchange_cycle(P, send, info, group=None):
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
+    return recv, n_recv, bb, sum(counts)
+
+
+def exchange_cycle(P, send, info, group=None):
+    """One cycle's exchange with a single host round trip: pack on the GPU (queued), exchange_by_header, merge on the
+    GPU (queued).
+
+    P:    the rank's Pose (defer-merge mode); call this with torch's current stream set to P's stream
+          (`with torch.cuda.stream(torch.cuda.ExternalStream(P.stream()))`) so that the library's kernels and the
+          collectives are ordered without extra synchronisation.
+    send: uint8 device tensor of at least P.exchangeBound() cells; info: int32 device tensor of world + 8 words.
+    Returns the number of cells this rank sent.
+    """
+    world = dist.get_world_size(group)
+    P.exchangePackDevice(world, send.data_ptr(), send.numel() // CELL_BYTES, info.data_ptr())
+    recv, n_recv, bb, n_sent = exchange_by_header(send, info, group)
     if n_recv:
         P.exchangeMerge(recv.data_ptr(), n_recv, bb)
     P._exchange_keepalive = recv     # the merge kernels are only queued: keep the buffer until the next cycle
-    return sum(counts)
+    return n_sent
 
 
 def merge_cells_host(cells):

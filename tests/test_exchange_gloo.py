@@ -52,6 +52,50 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
+def _header_worker(rank, world, port, out_dir):
+    """exchange_by_header: the header (counts + cell range) travels as the device would publish it; rank 1 sends nothing."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cells = _make_cells(rank, 0 if rank == 1 else 3000 + 700 * rank, seed=5)
+        own = exchange.owner_of(cells["key"], world)
+        order = np.argsort(own, kind="stable")
+        info = np.zeros(world + 8, dtype=np.int32)
+        info[:world] = np.bincount(own, minlength=world)
+        if len(cells):
+            i = (cells["key"] & np.uint64(0x1fffff)).astype(np.int64) - (1 << 20)
+            j = ((cells["key"] >> np.uint64(21)) & np.uint64(0x1fffff)).astype(np.int64) - (1 << 20)
+            info[world:world + 6] = [i.min(), j.min(), 0, i.max(), j.max(), 0]
+        else:
+            info[world:world + 6] = [0x7fffffff] * 3 + [-0x80000000] * 3
+        info[world + 6] = len(cells)
+        send = torch.from_numpy(cells[order].view(np.uint8).copy())
+        recv, n, bb, n_sent = exchange.exchange_by_header(send, torch.from_numpy(info))
+        assert n_sent == len(cells)
+        np.save(os.path.join(out_dir, f"hrecv{rank}.npy"), recv[:n * exchange.CELL_BYTES].numpy().view(abi.CELL))
+        np.save(os.path.join(out_dir, f"hbb{rank}.npy"), np.array(bb))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_header_driven_exchange_one_round_trip(world, tmp_path):
+    """The exchange the multi-GPU bench uses (exchange.exchange_cycle minus the GPU pack / merge): sizes come from the
+    all-gathered headers, every rank learns the union of the cell ranges, an empty sender is handled."""
+    port = _free_port()
+    mp.spawn(_header_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    sent = [_make_cells(r, 0 if r == 1 else 3000 + 700 * r, seed=5) for r in range(world)]
+    allc = np.concatenate(sent)
+    i = (allc["key"] & np.uint64(0x1fffff)).astype(np.int64) - (1 << 20)
+    j = ((allc["key"] >> np.uint64(21)) & np.uint64(0x1fffff)).astype(np.int64) - (1 << 20)
+    for r in range(world):
+        got = np.load(tmp_path / f"hrecv{r}.npy")
+        exp = np.concatenate([s[exchange.owner_of(s["key"], world) == r] for s in sent])
+        assert np.array_equal(got, exp)
+        assert np.load(tmp_path / f"hbb{r}.npy").tolist() == [i.min(), j.min(), 0, i.max(), j.max(), 0]
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_all_to_all_v_delivers_every_cell_to_its_owner(world, tmp_path):
     port = _free_port()

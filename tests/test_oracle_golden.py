@@ -202,3 +202,73 @@ def test_generate_tmat_structure():
                 s = np.float32(s + np.float32(a[i, k] * b[k, j]))
             exp[i, j] = s
     assert np.array_equal(m, exp)
+
+
+# ------------------------------------------------------------------------------ StatisticalOutlierRemoval
+def _sor_numpy(pts, mean_k, mul):
+    """Independent restatement in numpy (all pairs): float squared distances, double sqrt, ascending sum."""
+    xyz = np.stack([pts["x"], pts["y"], pts["z"]], 1).astype(np.float32)
+    n = len(xyz)
+    dist = np.zeros(n, np.float32)
+    for i in range(n):
+        d = xyz[i] - xyz                                      # float32
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        nn = np.sort(d2)[:mean_k + 1]
+        s = 0.0
+        for v in nn[1:]:
+            s += np.sqrt(np.float64(v))
+        dist[i] = np.float32(s / mean_k)
+    s, sq = 0.0, 0.0
+    for v in dist:
+        s += float(v)
+        sq += float(np.float32(v * v))
+    mean = s / n
+    thr = mean + mul * np.sqrt((sq - s * s / n) / (n - 1))
+    return (~(dist.astype(np.float64) > thr)).astype(np.uint8), dist
+
+
+def test_sor_known_answer_line_of_points():
+    """Points on a line at unit spacing plus one far point: with mean_k = 2 the inner points' mean neighbour distance
+    is 1, the ends' 1.5, the outlier's is large and it alone is removed."""
+    pts = np.zeros(8, dtype=abi.POINT)
+    pts["x"][:7] = np.arange(7)
+    pts["x"][7] = 100.0
+    keep, dist = ob.sor(pts, 2, 1.0, brute=True)
+    assert dist[:7].tolist() == [1.5, 1.0, 1.0, 1.0, 1.0, 1.0, 1.5]
+    assert dist[7] == np.float32((94.0 + 95.0) / 2)
+    assert keep.tolist() == [1] * 7 + [0]
+
+
+def test_sor_grid_search_equals_all_pairs_and_numpy():
+    """The oracle's grid k-NN is exact: identical to its own all-pairs search and to an independent numpy restatement
+    (surface-like cloud with outliers, duplicates and a cloud smaller than mean_k + 1)."""
+    rng = np.random.default_rng(11)
+    n = 1500
+    pts = np.zeros(n, dtype=abi.POINT)
+    pts["x"], pts["y"] = rng.uniform(0, 3, n).astype(np.float32), rng.uniform(0, 2, n).astype(np.float32)
+    pts["z"] = (0.05 * np.round(rng.normal(0, 1, n)) + 0.01 * pts["x"]).astype(np.float32)   # layered, tilted
+    pts["z"][:20] += rng.uniform(1, 5, 20).astype(np.float32)                                  # outliers
+    pts[100:120] = pts[200:220]                                                                # duplicates
+    for cloud, k in ((pts, 50), (pts, 7), (pts[:40], 50), (pts[:1], 50)):
+        kb, db = ob.sor(cloud, k, 1.0, brute=True)
+        kg, dg = ob.sor(cloud, k, 1.0, brute=False, threads=3)
+        assert np.array_equal(db.view(np.uint32), dg.view(np.uint32)) and np.array_equal(kb, kg)
+    kn, dn = _sor_numpy(pts[:400], 10, 1.0)
+    ko, do = ob.sor(pts[:400], 10, 1.0, brute=False)
+    assert np.array_equal(dn.view(np.uint32), do.view(np.uint32)) and np.array_equal(kn, ko)
+    assert ko[:20].sum() < 5   # the lifted points are (mostly) removed
+
+
+def test_downsample_applies_sor_only_per_frame_and_only_for_jump_pixels():
+    """pose_functions.cpp:1673: SOR runs iff !combinedPtCloud && jump_pixels > 0."""
+    rng = np.random.default_rng(12)
+    n = 3000
+    pts = np.zeros(n, dtype=abi.POINT)
+    pts["x"], pts["y"] = rng.uniform(0, 1, n).astype(np.float32), rng.uniform(0, 1, n).astype(np.float32)
+    pts["z"][:30] = 3.0
+    on = abi.make_params(jump_pixels=1, voxel_size=0.05, sor_mean_k=50, rows=64, cols=64)
+    off = abi.make_params(jump_pixels=1, voxel_size=0.05, sor_mean_k=0, rows=64, cols=64)
+    kp_only = abi.make_params(jump_pixels=0, voxel_size=0.05, sor_mean_k=50, rows=64, cols=64)
+    a, b, c = (ob.downsample_pt_cloud(p, pts, False) for p in (on, off, kp_only))
+    assert len(a) < len(b) and np.array_equal(b, c)
+    assert np.array_equal(ob.downsample_pt_cloud(on, pts, True), ob.downsample_pt_cloud(off, pts, True))
