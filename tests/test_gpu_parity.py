@@ -186,6 +186,35 @@ def test_empty_frame_and_empty_batch():
         assert len(P.downsamplePtCloud()) == 0
 
 
+@pytest.mark.parametrize("sor", [0, 50])
+@pytest.mark.parametrize("mode", [abi.MERGE_ACCUMULATE, abi.MERGE_ACCUMULATE_TILED, abi.MERGE_RETAIN])
+def test_cycle_with_empty_and_tiny_frames(sor, mode):
+    """Ragged cycle: an all-invalid frame, a frame with fewer valid pixels than mean_k + 1, and normal frames — in every
+    merge mode, with and without StatisticalOutlierRemoval."""
+    keep = []
+    geom = SMALL4
+    rows, cols = geom["rows"], geom["cols"]
+    p = abi.make_params(jump_pixels=1, voxel_size=0.05, sor_mean_k=sor, merge_mode=mode, **geom)
+    frames = _frames(190, 4, rows, cols, keep=keep)
+    seq = synth.sequence(190, 4, rows, cols)
+    empty = abi.make_frame(np.zeros((rows, cols), np.uint8), seq[1][1], seq[1][2], keep=keep)
+    tiny_d = np.zeros((rows, cols), np.uint8)
+    tiny_d[40:44, 100:107] = 110          # 28 valid pixels
+    tiny = abi.make_frame(tiny_d, seq[2][1], seq[2][2], keep=keep)
+    cycle = [frames[0], empty, tiny, frames[3]]
+    cloud, n, counts = ob.run_cycle(p, cycle, abi.DISP_U8, 2)
+    exp = ob.downsample_pt_cloud(p, cloud[:n], True)
+    with Pose(p) as P:
+        got_counts = P.createCycleClouds(cycle)
+        assert np.array_equal(got_counts, counts) and counts[1] == 0 and 0 < counts[2] <= 28
+        _eq(P.lastCyclePoints(), cloud[:n])
+        got = P.downsamplePtCloud()
+    if mode == abi.MERGE_ACCUMULATE_TILED:
+        _close(got, exp)
+    else:
+        _eq(got, exp)
+
+
 # ------------------------------------------------------------------------------------- per-frame VoxelGrid
 @pytest.mark.parametrize("voxel_size", [0.05, 0.1, 0.5])
 @pytest.mark.parametrize("geom", [SMALL, SMALL4])
