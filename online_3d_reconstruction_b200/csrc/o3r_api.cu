@@ -72,9 +72,6 @@ struct o3r_ctx {
     cudaEvent_t ev_copy2 = nullptr;
     std::vector<cudaEvent_t> chunk_ev;
     int chunk_frames = 10, chunk_frames_dev = 1 << 30;
-    int gather_in_sort = 0;   // experiment: deliver points in sorted order from the last radix pass
-    int vg_short = 0;         // per-frame grid reduce: 1 = warp-level short-run kernel (instruction bound, 0.60 ms),
-                              // 0 = shared-memory staged kernel (L1 bound, 0.56 ms) — measured r01, config 2
     cudaEvent_t chunk_event(size_t i) {
         while (chunk_ev.size() <= i) {
             cudaEvent_t e;
@@ -290,7 +287,7 @@ int bilateral_lut(o3r_ctx* ctx, int k, BilateralLut* out) {
 template <typename KeyT>
 int sort_pairs(o3r_ctx* ctx, KeyT* k0, KeyT* k1, uint32_t* v0, uint32_t* v1, const uint32_t* seg_off, int n_seg,
                size_t per_seg_cap, const SortPlan* plan, int passes, int iota_first, const uint32_t* ghist,
-               const float4* gsrc = nullptr, float4* gdst = nullptr, int ghist_is_prefix = 1) {
+               int ghist_is_prefix = 1) {
     const uint32_t tiles_ub = std::max(1u, cdiv(per_seg_cap, kRsTile));
     const size_t st_words = (size_t)n_seg * tiles_ub * kRsBins;
     // status words for every pass + one ticket per pass, cleared with one memset
@@ -302,7 +299,7 @@ int sort_pairs(o3r_ctx* ctx, KeyT* k0, KeyT* k1, uint32_t* v0, uint32_t* v1, con
     for (int p = 0; p < passes; ++p)
         LAUNCH_N(sizeof(KeyT) == 4 ? "k_rs_onesweep_u32" : "k_rs_onesweep_u64", (k_rs_onesweep<KeyT>), grid, kThreads,
                  rs_scatter_smem<KeyT>(), k0, k1, v0, v1, seg_off, plan, p, tiles_ub, ghist,
-                 status + st_words * p, tickets + p, iota_first, gsrc, gdst, ghist_is_prefix);
+                 status + st_words * p, tickets + p, iota_first, ghist_is_prefix);
     return O3R_OK;
 }
 
@@ -342,15 +339,9 @@ int vg_sorted_reduce(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const u
     int rcs = sort_segments_plan(ctx, sb, seg_off, n_seg, per_seg_cap, grids);
     if (rcs) return rcs;
     SortPlan* plan = ctx->plan_all.as<SortPlan>();
-    // the fast reduce streams the points in sorted order: the last radix pass gathers them into `spts`
     const bool fast = min_points <= 1 && !out_keys && !out_counts;
-    float4* spts = nullptr;
-    if (fast && ctx->gather_in_sort) {
-        CU(ctx->spts.ensure((size_t)per_seg_cap * n_seg * 16));
-        spts = ctx->spts.as<float4>();
-    }
     int rc = sort_pairs<uint32_t>(ctx, sb.k0, sb.k1, sb.v0, sb.v1, seg_off, n_seg, per_seg_cap, plan, 4, 1,
-                                  ctx->ghist.as<uint32_t>(), pts, spts);
+                                  ctx->ghist.as<uint32_t>());
     if (rc) return rc;
     VgArgs A;
     A.keys0 = sb.k0; A.keys1 = sb.k1; A.vals0 = sb.v0; A.vals1 = sb.v1;
@@ -366,18 +357,13 @@ int vg_sorted_reduce(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const u
     LAUNCH(k_vg_heads, grid, kThreads, 0, A, ctx->head_cnt.as<uint32_t>());
     LAUNCH(k_scan_u32, 1, kScanThreads, 0, ctx->head_cnt.as<uint32_t>(), ctx->head_off.as<uint32_t>(), (uint32_t)nt,
            cnt + CNT_VOX);
-    if (fast && ctx->vg_short && !spts && !z_shift) {   // (the combined grid has long runs: staged kernel)
-        // short runs (per-frame grid): warp-level reduce, no shared-memory staging, no carry chain
-        LAUNCH(k_vg_reduce_s, grid, kThreads, 0, A, ctx->head_off.as<uint32_t>(), out, out_off, track_cells ? 1 : 0,
-               ctx->inv_c, ctx->inv_cz, reinterpret_cast<int*>(cnt + CNT_CELLBB), out_base);
-        if (!out_base) LAUNCH(k_set_total, 1, 32, 0, out_off + n_seg, cnt + CNT_VOX);
-    } else if (fast) {
+    if (fast) {
         const size_t wbytes = 64 + (nt + 1) * sizeof(RunCarry);
         CU(ctx->runwork.ensure(wbytes));
         ZERO(ctx->runwork.p, wbytes);
         LAUNCH(k_vg_reduce_w, (uint32_t)nt, kThreads, 0, A, ctx->head_off.as<uint32_t>(), cnt + CNT_VOX, out, out_off,
                n_seg, ctx->runwork.as<uint32_t>(), reinterpret_cast<RunCarry*>(ctx->runwork.as<char>() + 64),
-               track_cells ? 1 : 0, ctx->inv_c, ctx->inv_cz, reinterpret_cast<int*>(cnt + CNT_CELLBB), out_base, spts);
+               track_cells ? 1 : 0, ctx->inv_c, ctx->inv_cz, reinterpret_cast<int*>(cnt + CNT_CELLBB), out_base);
     } else
         LAUNCH(k_vg_reduce, grid, kThreads, 0, A, ctx->head_off.as<uint32_t>(), cnt + CNT_VOX, out, out_off, n_seg,
                out_keys, out_counts);
@@ -414,15 +400,7 @@ int acc_build_cycle_t(o3r_ctx* ctx, Items items, size_t n, bool use_resident, co
              k0, v0, ctx->ghist.as<uint32_t>());
     LAUNCH(k_rs_plan, 1, kThreads, 0, ctx->ghist.as<uint32_t>(), seg, plan, (const GridParams*)nullptr);
     tr.mark("key+plan");
-    float4* spts = nullptr;
-    const float4* gsrc = nullptr;
-    if constexpr (Items::kGather) if (ctx->gather_in_sort) {   // the last radix pass delivers the points in sorted order
-        CU(ctx->spts.ensure(n * 16));
-        spts = ctx->spts.as<float4>();
-        items.spts = spts;
-        gsrc = items.pts;
-    }
-    int rc = sort_pairs<KeyT>(ctx, k0, k1, v0, v1, seg, 1, n, plan, passes, 0, ctx->ghist.as<uint32_t>(), gsrc, spts);
+    int rc = sort_pairs<KeyT>(ctx, k0, k1, v0, v1, seg, 1, n, plan, passes, 0, ctx->ghist.as<uint32_t>());
     if (rc) return rc;
     tr.mark("sort_pairs");
     AccArgs<KeyT> A;
@@ -626,7 +604,6 @@ int sor_filter(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const uint32_
             LAUNCH(k_sor_calib, n_seg, kSorThreads, heap_bytes, ctx->spts.as<float4>(), ctx->sor_skeys.as<uint32_t>(), seg_off, grids,
                    pgrids, ctx->bbox.as<uint32_t>(), rowb, rowe, mean_k);
     }
-    int rc = O3R_OK;
     CU(ctx->sor_hard.ensure(cap * 8 + 64));
     uint32_t* n_hard = reinterpret_cast<uint32_t*>(ctx->sor_hard.as<char>() + cap * 8);
     ZERO(n_hard, 4);
@@ -1157,8 +1134,6 @@ int o3r_create(const o3r_params* params, o3r_ctx** out_ctx) {
     if ((e = cudaEventCreateWithFlags(&ctx->ev_copy2, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
     if (const char* cf = getenv("O3R_CHUNK_FRAMES")) ctx->chunk_frames = std::max(1, atoi(cf));
     if (const char* cf = getenv("O3R_CHUNK_FRAMES_DEV")) ctx->chunk_frames_dev = std::max(1, atoi(cf));
-    if (const char* cf = getenv("O3R_GATHER_IN_SORT")) ctx->gather_in_sort = atoi(cf) != 0;
-    if (const char* cf = getenv("O3R_VG_SHORT")) ctx->vg_short = atoi(cf) != 0;
     if ((e = cudaMallocHost((void**)&ctx->h_counters, CNT_N * 4)) != cudaSuccess) return bail(e, "pinned");
     if ((e = cudaMallocHost((void**)&ctx->h_nres, 4)) != cudaSuccess) return bail(e, "pinned");
     if ((e = cudaEventCreateWithFlags(&ctx->ev_nres, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
@@ -1657,7 +1632,7 @@ static int exchange_pack_impl(o3r_ctx* ctx, int world, o3r_cell* send_dev, size_
     const uint32_t g = std::min<uint32_t>(std::max(1u, cdiv(nub, kThreads)), 148 * 8);
     LAUNCH(k_owner, g, kThreads, 0, cnt + CNT_CYC, ctx->ckey.as<uint64_t>(), (uint32_t)world, sb.k0, sb.v0, ocnt, ctx->seg2.as<uint32_t>());
     rc = sort_pairs<uint32_t>(ctx, sb.k0, sb.k1, sb.v0, sb.v1, ctx->seg2.as<uint32_t>(), 1, std::max<size_t>(nub, 1), plan, 1, 0, ocnt,
-                              nullptr, nullptr, 0 /* raw owner counts: they are also the exchange header */);
+                              0 /* raw owner counts: they are also the exchange header */);
     if (rc) return rc;
     const int* bb = bbp ? bbp : none;
     LAUNCH(k_pack_cells, g, kThreads, 0, cnt + CNT_CYC, sb.v1, ctx->ckey.as<uint64_t>(), ctx->cacc.as<float4>(), ctx->crgb.as<uint4>(),

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? O3R_RS_MINB : (O
     KeyT* __restrict__ keys0, KeyT* __restrict__ keys1, uint32_t* __restrict__ vals0, uint32_t* __restrict__ vals1,
     const uint32_t* __restrict__ seg_off, const SortPlan* __restrict__ plan, int pass, uint32_t tiles_ub,
     const uint32_t* __restrict__ ghist, uint32_t* __restrict__ status, uint32_t* __restrict__ ticket, int iota_first,
-    const float4* __restrict__ gsrc, float4* __restrict__ gdst, int ghist_is_prefix) {
+    int ghist_is_prefix) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
     RsPair<KeyT>* s_pairs = reinterpret_cast<RsPair<KeyT>*>(rs_smem);
     uint16_t* cnt = reinterpret_cast<uint16_t*>(rs_smem + (size_t)kRsTile * sizeof(RsPair<KeyT>));   // [kWarps][1024]
@@ -278,11 +278,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? O3R_RS_MINB : (O
     KeyT* kout = (par ? keys0 : keys1) + beg;
     uint32_t* vout = (par ? vals0 : vals1) + beg;
     const bool first = (amask & ((1u << pass) - 1u)) == 0u;   // no active pass before this one
-    const bool last = (amask >> (pass + 1)) == 0u;            // none after it
     const bool iota = iota_first && first;   // values are the global element index, not read from memory
-    // in the last active pass the 16-byte records the values point at can be delivered in sorted order
-    // (gdst[beg + rank] = gsrc[value]) instead of the values
-    const bool gather = last && gdst != nullptr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const int b0 = threadIdx.x * kRsBpt;   // this thread's bin(s)
@@ -439,16 +435,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? O3R_RS_MINB : (O
         s_pairs[pos] = pr;
     }
     __syncthreads();
-    if (gather) {
-        float4* go = gdst + beg;
-#pragma unroll 4
-        for (uint32_t i = threadIdx.x; i < ntile; i += kThreads) {
-            const RsPair<KeyT> pr = s_pairs[i];
-            const uint32_t g = gbase[rs_digit(pr.k, shift, dmask)] + i;
-            kout[g] = pr.k;
-            go[g] = gsrc[pr.v];
-        }
-    } else if (full) {
+    if (full) {
 #pragma unroll
         for (int r = 0; r < kRsItems; ++r) {
             const uint32_t i = r * kThreads + threadIdx.x;

@@ -382,7 +382,7 @@ __device__ __forceinline__ void run_reduce_tile(const KeyT* __restrict__ keys, u
 struct VgPol {
     static constexpr bool kNeedsKey = false;
     static constexpr bool kPacked = true;
-    const float4* spts;   // the segment's points in sorted order (null: gather pts[vals[pos]])
+    const float4* spts;   // the segment's points when they are already in sorted order (null: gather pts[vals[pos]])
     const float4* pts; const uint32_t* vals;
     float4* out; int z_shift; bool verbatim;
     int want_cells; float icx, icz;
@@ -425,8 +425,7 @@ __global__ void __launch_bounds__(kThreads, 5) k_vg_reduce_w(VgArgs A, const uin
                                                           int n_seg, uint32_t* __restrict__ ticket,
                                                           RunCarry* __restrict__ carries, int want_cells, float icx,
                                                           float icz, int* __restrict__ cellbb,
-                                                          const uint32_t* __restrict__ out_base,
-                                                          const float4* __restrict__ sorted_pts) {
+                                                          const uint32_t* __restrict__ out_base) {
     __shared__ RunSmem<uint32_t, true> S;
     __shared__ int s_bb[6];
     if (threadIdx.x == 0) S.ticket = atomicAdd(ticket, 1u);
@@ -444,8 +443,8 @@ __global__ void __launch_bounds__(kThreads, 5) k_vg_reduce_w(VgArgs A, const uin
     if (t * kTileV >= n) return;
     const SortPlan pl = A.plan[s];
     const int par = pl.final_parity;
-    // the last radix pass delivered the points in sorted order; a segment that needed no pass is already sorted
-    const float4* sp = pl.n_active ? (sorted_pts ? sorted_pts + beg : nullptr) : A.pts + beg;
+    // a segment that needed no radix pass is already in order: its points are read sequentially, not gathered
+    const float4* sp = pl.n_active ? nullptr : A.pts + beg;
     VgPol pol{sp, A.pts, (par ? A.vals1 : A.vals0) + beg, out + obase, A.z_shift, A.grids && A.grids[s].passthrough,
               want_cells, icx, icz,
               {0x7fffffff, 0x7fffffff, 0x7fffffff}, {(int)0x80000000, (int)0x80000000, (int)0x80000000}};
@@ -456,169 +455,6 @@ __global__ void __launch_bounds__(kThreads, 5) k_vg_reduce_w(VgArgs A, const uin
         for (int a = 0; a < 3; ++a) {
             const int lo = __reduce_min_sync(kFull, pol.mn[a]), hi = __reduce_max_sync(kFull, pol.mx[a]);
             if ((threadIdx.x & 31) == 0) { atomicMin(&s_bb[a], lo); atomicMax(&s_bb[3 + a], hi); }
-        }
-        __syncthreads();
-        if (threadIdx.x < 3) atomicMin(&cellbb[threadIdx.x], s_bb[threadIdx.x]);
-        else if (threadIdx.x < 6) atomicMax(&cellbb[threadIdx.x], s_bb[threadIdx.x]);
-    }
-}
-
-// ---- engine 1, short-run variant (per-frame grid: ~1.4 points per voxel) ----------------------------------------------
-// No shared-memory staging: lane = element (coalesced key / value loads, one gather per lane, all four chunks of
-// the warp in flight at once), the in-order sum of a run travels lane to lane with one shuffle step per element of
-// the LONGEST run in the 32-element chunk (3-4 steps here instead of a fixed 31), and a warp follows its last
-// run past its range end.  Sums are added in exactly the sorted order, so results stay bit-identical.
-__global__ void __launch_bounds__(kThreads) k_vg_reduce_s(VgArgs A, const uint32_t* __restrict__ head_off,
-                                                          float4* __restrict__ out, uint32_t* __restrict__ seg_out_off,
-                                                          int want_cells, float icx, float icz, int* __restrict__ cellbb,
-                                                          const uint32_t* __restrict__ out_base) {
-    constexpr int CH = kTileV / kWarps / 32;   // 4 chunks of 32 per warp
-    __shared__ uint32_t s_w[kWarps];
-    __shared__ int s_bb[6];
-    const int s = blockIdx.y;
-    const uint32_t t = blockIdx.x;
-    const uint32_t obase = out_base ? *out_base : 0u;
-    if (t == 0 && threadIdx.x == 0) seg_out_off[s] = obase + head_off[(size_t)s * A.tiles_ub];
-    const uint32_t beg = A.seg_off[s], n = A.seg_off[s + 1] - beg;
-    if (t * kTileV >= n) return;
-    const SortPlan& pl = A.plan[s];
-    const int par = pl.final_parity;
-    const bool ident = pl.n_active == 0;            // nothing was sorted: values are the identity
-    const bool verbatim = A.grids && A.grids[s].passthrough;
-    const uint32_t* keys = (par ? A.keys1 : A.keys0) + beg;
-    const uint32_t* vals = (par ? A.vals1 : A.vals0) + beg;
-    const float4* pts = A.pts;
-    out += obase;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt = (1u << lane) - 1u;
-    if (threadIdx.x < 6) s_bb[threadIdx.x] = threadIdx.x < 3 ? 0x7fffffff : (int)0x80000000;
-    const uint32_t w0 = t * kTileV + warp * (CH * 32);
-
-    // all loads of the warp's own range up front
-    uint32_t k[CH];
-    float4 p[CH];
-    unsigned hm[CH];
-    uint32_t nheads = 0;
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-        const uint32_t pos = w0 + 32 * c + lane;
-        k[c] = pos < n ? keys[pos] : 0u;
-    }
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-        const uint32_t pos = w0 + 32 * c + lane;
-        p[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (pos < n) p[c] = pts[ident ? beg + pos : vals[pos]];
-    }
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-        const uint32_t pos = w0 + 32 * c + lane;
-        const bool valid = pos < n;
-        uint32_t prev = __shfl_up_sync(kFull, k[c], 1);
-        const uint32_t prev_chunk_last = __shfl_sync(kFull, k[c > 0 ? c - 1 : 0], 31);
-        if (lane == 0) prev = (c > 0) ? prev_chunk_last : ((valid && pos > 0) ? keys[pos - 1] : 0u);
-        const bool head = valid && (pos == 0 || k[c] != prev);
-        hm[c] = __ballot_sync(kFull, head);
-        nheads += __popc(hm[c]);
-    }
-    if (lane == 0) s_w[warp] = nheads;
-    __syncthreads();
-    uint32_t slot_w = head_off[(size_t)s * A.tiles_ub + t];
-    for (int w = 0; w < warp; ++w) slot_w += s_w[w];
-
-    int mn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, mx[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
-    bool open = false;          // an owned run continues from the previous chunk (warp-uniform)
-    float cx = 0.f, cy = 0.f, cz = 0.f;
-    uint32_t cn = 0, cr = 0, cg = 0, cb = 0, cslot = 0;
-    uint32_t seen = 0;
-    auto chunk = [&](const uint32_t base, const bool own, const uint32_t key, const float4 pt, const unsigned m) {
-        const uint32_t pos = base + lane;
-        const bool valid = pos < n;
-        const unsigned vmask = __ballot_sync(kFull, valid);
-        const int first = m ? (__ffs(m) - 1) : 32;
-        const unsigned before_first = first >= 32 ? 0xffffffffu : ((1u << first) - 1u);
-        const unsigned live_mask = own ? (vmask & (open ? 0xffffffffu : ~before_first)) : (vmask & before_first);
-        const bool live = (live_mask >> lane) & 1u;
-        const bool head = own && ((m >> lane) & 1u);
-        uint32_t nk = __shfl_down_sync(kFull, key, 1);
-        const bool has_next = pos + 1 < n;
-        if (lane == 31 && has_next) nk = keys[pos + 1];
-        const bool is_last = live && (!has_next || nk != key);
-        // own values
-        const uint32_t c = __float_as_uint(pt.w);
-        const float ix = pt.x, iy = pt.y, iz = A.z_shift ? __fadd_rn(pt.z, 500.0f) : pt.z;
-        const uint32_t ir = (c >> 16) & 255u, ig = (c >> 8) & 255u, ib = c & 255u;
-        // distance from the run's first element inside this chunk (carried run: distance from "lane -1")
-        const unsigned below = own ? (m & (lt | (1u << lane))) : 0u;
-        const int hl = below ? (31 - __clz(below)) : -1;
-        const int dist = live ? (hl >= 0 ? lane - hl : lane + 1) : 0;
-        float ax = ix, ay = iy, az = iz;
-        uint32_t an = 1, ar = ir, ag = ig, ab = ib;
-        if (head) { ax = __fadd_rn(0.f, ix); ay = __fadd_rn(0.f, iy); az = __fadd_rn(0.f, iz); }   // sums start at +0
-        const int maxd = __reduce_max_sync(kFull, dist);
-        for (int j = 1; j <= maxd; ++j) {
-            float px = __shfl_up_sync(kFull, ax, 1), py = __shfl_up_sync(kFull, ay, 1), pz = __shfl_up_sync(kFull, az, 1);
-            uint32_t pn = __shfl_up_sync(kFull, an, 1), pr = __shfl_up_sync(kFull, ar, 1), pg = __shfl_up_sync(kFull, ag, 1),
-                     pb = __shfl_up_sync(kFull, ab, 1);
-            if (lane == 0) { px = cx; py = cy; pz = cz; pn = cn; pr = cr; pg = cg; pb = cb; }
-            if (dist == j) {
-                ax = __fadd_rn(px, ix); ay = __fadd_rn(py, iy); az = __fadd_rn(pz, iz);
-                an = pn + 1; ar = pr + ir; ag = pg + ig; ab = pb + ib;
-            }
-        }
-        const uint32_t run_slot = hl >= 0 ? slot_w + seen + __popc(m & ((1u << hl) - 1u)) : cslot;
-        if (is_last) {
-            float4 o;
-            if (verbatim) {
-                o = pt;
-            } else {
-                const float fn = (float)an;
-                float oz = __fdiv_rn(az, fn);
-                if (A.z_shift) oz = __fsub_rn(oz, 500.0f);
-                const uint32_t rgb = ((uint32_t)__fdiv_rn((float)ar, fn) << 16) | ((uint32_t)__fdiv_rn((float)ag, fn) << 8) |
-                                     (uint32_t)__fdiv_rn((float)ab, fn);
-                o = make_float4(__fdiv_rn(ax, fn), __fdiv_rn(ay, fn), oz, __uint_as_float(rgb));
-            }
-            out[run_slot] = o;
-            if (want_cells) {
-                const int ci = (int)floorf(__fmul_rn(o.x, icx)), cj = (int)floorf(__fmul_rn(o.y, icx)),
-                          ck = (int)floorf(__fmul_rn(__fadd_rn(o.z, 500.0f), icz));
-                mn[0] = min(mn[0], ci); mx[0] = max(mx[0], ci);
-                mn[1] = min(mn[1], cj); mx[1] = max(mx[1], cj);
-                mn[2] = min(mn[2], ck); mx[2] = max(mx[2], ck);
-            }
-        }
-        const bool cont = live && !is_last;
-        open = __shfl_sync(kFull, (int)cont, 31) != 0;
-        if (open) {
-            cx = __shfl_sync(kFull, ax, 31); cy = __shfl_sync(kFull, ay, 31); cz = __shfl_sync(kFull, az, 31);
-            cn = __shfl_sync(kFull, an, 31); cr = __shfl_sync(kFull, ar, 31); cg = __shfl_sync(kFull, ag, 31);
-            cb = __shfl_sync(kFull, ab, 31); cslot = __shfl_sync(kFull, run_slot, 31);
-        }
-        if (own) seen += __popc(m);
-    };
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-        const uint32_t base = w0 + 32u * c;
-        if (base < n) chunk(base, true, k[c], p[c], hm[c]);
-    }
-    for (uint32_t base = w0 + 32u * CH; open && base < n; base += 32u) {   // follow the last run past the range end
-        const uint32_t pos = base + lane;
-        const bool valid = pos < n;
-        const uint32_t key = valid ? keys[pos] : 0u;
-        uint32_t prev = __shfl_up_sync(kFull, key, 1);
-        if (lane == 0 && valid) prev = keys[pos - 1];
-        const unsigned m = __ballot_sync(kFull, valid && key != prev);
-        const int first = m ? (__ffs(m) - 1) : 32;
-        float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid && lane < first) pt = pts[ident ? beg + pos : vals[pos]];
-        chunk(base, false, key, pt, m);
-    }
-    if (want_cells) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const int lo = __reduce_min_sync(kFull, mn[a]), hi = __reduce_max_sync(kFull, mx[a]);
-            if (lane == 0) { atomicMin(&s_bb[a], lo); atomicMax(&s_bb[3 + a], hi); }
         }
         __syncthreads();
         if (threadIdx.x < 3) atomicMin(&cellbb[threadIdx.x], s_bb[threadIdx.x]);
@@ -649,7 +485,7 @@ struct KeyCodec {
 
 struct AccItemsPts {   // items are points of weight 1 (z gets +500)
     const float4* pts;
-    const float4* spts;    // the same points in sorted order when the last radix pass gathered them, else null
+    const float4* spts;    // the points themselves when nothing had to be sorted (already in order), else null
     const uint32_t* vals;  // sorted order -> point index (when spts is null)
     static constexpr bool kGather = true;
     static constexpr bool kPacked = true;
