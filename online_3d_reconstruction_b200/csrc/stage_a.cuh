@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kThreads) k_emit(AParams P, const FrameDev* __
     __shared__ double rl[256];
     __shared__ float zl[256];
     __shared__ uint32_t s_scan[34];
-    __shared__ float4 s_pts[kTileA];
+    __shared__ __align__(128) float4 s_pts[kTileA];
     __shared__ uint32_t s_keys[kTileA];
     const int tile = blockIdx.x, f = blockIdx.y;
     const FrameDev& F = frames[f];
@@ -319,15 +319,25 @@ __global__ void __launch_bounds__(kThreads) k_emit(AParams P, const FrameDev* __
                 ++o;
             }
     }
+    // The tile's points leave as ONE bulk copy (TMA, shared -> global, issued by one thread): the 16-byte records are
+    // contiguous in shared memory and in the output, so no thread has to issue store instructions for them.  The writers'
+    // generic-proxy stores are fenced into the async proxy before the barrier.
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     const uint32_t base = tile_off[(size_t)f * P.tiles_per_frame + tile];
     const bool pass = P.want_keys && grids[f].passthrough;
     const uint32_t fbase = frame_off[f];
     if (out_base) pts += *out_base;   // batch-wide output position of this chunk
-    for (uint32_t i = threadIdx.x; i < total; i += kThreads) {
-        pts[base + i] = s_pts[i];
-        if (P.want_keys) keys[base + i] = pass ? (base + i - fbase) : s_keys[i];  // passthrough: identity order
+    if (threadIdx.x == 0) {
+        const uint32_t src = (uint32_t)__cvta_generic_to_shared(s_pts);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(pts + base), "r"(src), "r"(total * 16u)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
+    if (P.want_keys)
+        for (uint32_t i = threadIdx.x; i < total; i += kThreads)
+            keys[base + i] = pass ? (base + i - fbase) : s_keys[i];  // passthrough: identity order
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem is read before the CTA retires
 }
 
 }  // namespace o3r
