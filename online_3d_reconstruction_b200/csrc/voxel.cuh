@@ -419,7 +419,10 @@ struct VgPol {
 
 // fast path of engine 1: every run is emitted (min_points <= 1), no key / count outputs.
 // Linear grid of tiles_ub * n_seg CTAs; work[0] is the ticket, carries follow.
-__global__ void __launch_bounds__(kThreads, 5) k_vg_reduce_w(VgArgs A, const uint32_t* __restrict__ head_off,
+#ifndef O3R_VG_MINB
+#define O3R_VG_MINB 5
+#endif
+__global__ void __launch_bounds__(kThreads, O3R_VG_MINB) k_vg_reduce_w(VgArgs A, const uint32_t* __restrict__ head_off,
                                                           const uint32_t* __restrict__ head_total,
                                                           float4* __restrict__ out, uint32_t* __restrict__ seg_out_off,
                                                           int n_seg, uint32_t* __restrict__ ticket,
