@@ -433,7 +433,10 @@ def main():
         threads = os.cpu_count() or 1
         cpu_cycle(wl, disp[:4], bgr[:4], T[0][:4], threads)  # warm
         t = cpu_cycle(wl, disp[:n], bgr[:n], T[args.warmup][:n], threads)
+        n7 = min(n, 14)   # the reference's own fan-out is 7 boost::threads per batch (pose.cpp:392-413): two batches of 7
+        t7 = cpu_cycle(wl, disp[:n7], bgr[:n7], T[args.warmup][:n7], 7) if wl not in SOR_MEAN_K else None
         res["cpu_baseline"] = {"value": n / t, "unit": "frames/s", "cores": threads, "kind": "port",
+                               "value_7_threads": (n7 / t7) if t7 else None,
                                "sample": f"1 cycle of {n} frames + combined downsample, {t:.2f} s, " + ("with SOR" if wl in SOR_MEAN_K else "no SOR")}
     if world > 1:
         import torch.distributed as dist
