@@ -64,7 +64,9 @@ enum {
                                  sums are sorted and merged (8x less traffic).  Cell keys, point counts and
                                  colour sums are identical to ACCUMULATE; centroids differ by float
                                  reassociation only (<= 1e-5 relative, north_star's tolerance) and are
-                                 reproducible from run to run                                       */
+                                 reproducible from run to run.  While the pre-reduction does not reduce
+                                 (more than one partial per two voxels: grids finer than the point spacing)
+                                 it is skipped and the voxels are merged directly, as in ACCUMULATE    */
 };
 
 /* Read-only configuration: the `Pose` members the path reads (pose.h:93-98,108,118,126-128,149,168). */
