@@ -23,15 +23,14 @@ int sor_filter(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const uint32_
     CU(ctx->spts.ensure(cap * 16));
     CU(ctx->sor_grids.ensure((size_t)n_seg * sizeof(SorGrid)));
     CU(ctx->sor_pgrids.ensure((size_t)n_seg * sizeof(GridParams)));
-    CU(ctx->sor_rows.ensure((size_t)n_seg * kSorRowsCap * 8));
+    CU(ctx->sor_rows.ensure((size_t)n_seg * (kSorCellsCap + 1) * 4));
     CU(ctx->sor_thr.ensure((size_t)n_seg * 8));
     CU(ctx->sor_cnt.ensure((size_t)tiles * n_seg * 4));
     CU(ctx->sor_cntoff.ensure((size_t)tiles * n_seg * 4));
     CU(ctx->bbox.ensure((size_t)n_seg * 6 * 4));
     SorGrid* grids = ctx->sor_grids.as<SorGrid>();
     GridParams* pgrids = ctx->sor_pgrids.as<GridParams>();
-    uint32_t* rowb = ctx->sor_rows.as<uint32_t>();
-    uint32_t* rowe = rowb + (size_t)n_seg * kSorRowsCap;
+    uint32_t* cell_start = ctx->sor_rows.as<uint32_t>();   // [n_seg][kSorCellsCap + 1]
     uint32_t* cnt = ctx->counters.as<uint32_t>();
     const uint32_t gl = std::min<uint32_t>(std::max(1u, cdiv(per_seg_cap, kThreads)), 148 * 4);
     LAUNCH(k_bbox_init, cdiv((size_t)n_seg * 6, kThreads), kThreads, 0, ctx->bbox.as<uint32_t>(), n_seg);
@@ -49,22 +48,21 @@ int sor_filter(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const uint32_
         plan = ctx->plan_all.as<SortPlan>();
         rc = sort_pairs<uint32_t>(ctx, sb.k0, sb.k1, sb.v0, sb.v1, seg_off, n_seg, per_seg_cap, plan, 4, 1, ctx->ghist.as<uint32_t>());
         if (rc) return rc;
-        LAUNCH(k_sor_rows_clear, dim3(std::min<uint32_t>(cdiv(kSorRowsCap, kThreads), 256), n_seg), kThreads, 0, grids, rowb, rowe);
-        LAUNCH(k_sor_rows, dim3(gl, n_seg), kThreads, 0, sb.k0, sb.k1, sb.v0, sb.v1, plan, pts, seg_off, grids, rowb, rowe,
+        LAUNCH(k_sor_cells, dim3(gl, n_seg), kThreads, 0, sb.k0, sb.k1, sb.v0, sb.v1, plan, pts, seg_off, grids, cell_start,
                ctx->sor_skeys.as<uint32_t>(), ctx->sor_svals.as<uint32_t>(), ctx->spts.as<float4>());
         if (round == 0)
             LAUNCH(k_sor_calib, n_seg, kSorThreads, heap_bytes, ctx->spts.as<float4>(), ctx->sor_skeys.as<uint32_t>(), seg_off, grids,
-                   pgrids, ctx->bbox.as<uint32_t>(), rowb, rowe, mean_k);
+                   pgrids, ctx->bbox.as<uint32_t>(), cell_start, mean_k);
     }
     CU(ctx->sor_hard.ensure(cap * 8 + 64));
     uint32_t* n_hard = reinterpret_cast<uint32_t*>(ctx->sor_hard.as<char>() + cap * 8);
     ZERO(n_hard, 4);
     CU(cudaFuncSetAttribute(k_sor_knn_hard, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heap_bytes));
     LAUNCH(k_sor_knn, dim3(std::max(1u, cdiv(per_seg_cap, kSorThreads)), n_seg), kSorThreads, heap_bytes, ctx->spts.as<float4>(),
-           ctx->sor_skeys.as<uint32_t>(), ctx->sor_svals.as<uint32_t>(), seg_off, grids, rowb, rowe, mean_k,
+           ctx->sor_skeys.as<uint32_t>(), ctx->sor_svals.as<uint32_t>(), seg_off, grids, cell_start, mean_k,
            ctx->sor_dist.as<float>(), ctx->sor_hard.as<uint2>(), n_hard);
     LAUNCH(k_sor_knn_hard, std::max(1u, cdiv(cap, kSorThreads)), kSorThreads, heap_bytes, ctx->spts.as<float4>(),
-           ctx->sor_skeys.as<uint32_t>(), ctx->sor_svals.as<uint32_t>(), seg_off, grids, rowb, rowe, mean_k,
+           ctx->sor_skeys.as<uint32_t>(), ctx->sor_svals.as<uint32_t>(), seg_off, grids, cell_start, mean_k,
            ctx->sor_dist.as<float>(), ctx->sor_hard.as<uint2>(), n_hard);
     LAUNCH(k_sor_stats, n_seg, kThreads, 0, ctx->sor_dist.as<float>(), seg_off, stddev_mul, ctx->sor_thr.as<double>());
     LAUNCH(k_sor_count, dim3(tiles, n_seg), kThreads, 0, ctx->sor_dist.as<float>(), seg_off, ctx->sor_thr.as<double>(), tiles,

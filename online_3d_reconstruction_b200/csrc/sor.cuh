@@ -5,8 +5,11 @@
 // d2 = ((dx*dx) + (dy*dy)) + (dz*dz) in float), dist_i = (float)(sum_{k=1..mean_k} sqrt((double)d2_k) / mean_k) with the
 // neighbours in ascending order (k = 0 is the query), then mean and stddev of dist over the cloud in double and
 // "remove iff dist_i > mean + mul * stddev".  An exact k-NN does not depend on how it is found; here:
-//   * a uniform grid per frame (cell = the radius that holds mean_k + 1 points of a surface of the frame's density),
-//     points radix-sorted by cell index (x minor), a begin/end table per (y, z) row of cells;
+//   * a uniform grid per frame, points radix-sorted by cell index (x minor) and a start offset per CELL (the classic
+//     uniform-grid layout): "all points in cells [a, b] of a (y, z) row" is one contiguous range found with two
+//     independent loads — no per-row search, no key compares in the candidate loop (a per-row table with a binary
+//     search was the first version: each of the ~30 rows a query visits cost a chain of 6-8 dependent loads, which
+//     is what bounded the kernel);
 //   * one thread per query, in cell order (a warp's queries share their candidate rows): the cube of (2s+1)^3 cells
 //     around the query is scanned into a per-thread max-heap of the mean_k + 1 smallest d2 (shared memory), s grows until
 //     the heap's top provably lies inside the cube (every unscanned point is farther than (s - 0.05) cells);
@@ -20,7 +23,7 @@
 namespace o3r {
 
 constexpr int kSorThreads = 128;
-constexpr int kSorRowsCap = 1 << 18;   // (y, z) rows of cells per frame; the cell is enlarged until they fit
+constexpr int kSorCellsCap = 1 << 22;  // cells per frame (4 M start offsets = 16 MB); the cell is enlarged until they fit
 constexpr int kSorMaxK = 128;          // mean_k + 1 <= 128
 #ifndef O3R_SOR_CALIB_RANK
 #define O3R_SOR_CALIB_RANK 115
@@ -66,7 +69,7 @@ __global__ void k_sor_grid(int n_seg, const uint32_t* __restrict__ bbox, const u
         for (;;) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) nc[a] = (long long)(ext[a] / c) + 2;
-            if (nc[0] * nc[1] * nc[2] <= (1ll << 31) && nc[1] * nc[2] <= (long long)kSorRowsCap) break;
+            if (nc[0] * nc[1] * nc[2] <= (long long)kSorCellsCap) break;
             c *= 1.26;
         }
         G.c = (float)c;
@@ -97,37 +100,33 @@ __global__ void __launch_bounds__(kThreads) k_sor_key(const float4* __restrict__
     }
 }
 
-// rows of the frame's table that exist get begin = end = 0 (empty); rows past nc[1]*nc[2] are never read
-__global__ void __launch_bounds__(kThreads) k_sor_rows_clear(const SorGrid* __restrict__ grids, uint32_t* __restrict__ row_begin,
-                                                             uint32_t* __restrict__ row_end) {
-    const int s = blockIdx.y;
-    const uint32_t rows = (uint32_t)grids[s].nc[1] * (uint32_t)grids[s].nc[2];
-    for (uint32_t r = blockIdx.x * kThreads + threadIdx.x; r < rows; r += gridDim.x * kThreads) {
-        row_begin[(size_t)s * kSorRowsCap + r] = 0u;
-        row_end[(size_t)s * kSorRowsCap + r] = 0u;
-    }
-}
-
-// sorted keys -> [begin, end) of every (y, z) row, positions relative to the segment; also copies the sorted keys,
-// values and points out of the sort's ping-pong buffers (which side holds a segment's result is per segment)
-__global__ void __launch_bounds__(kThreads) k_sor_rows(const uint32_t* __restrict__ keys0, const uint32_t* __restrict__ keys1,
-                                                       const uint32_t* __restrict__ vals0, const uint32_t* __restrict__ vals1,
-                                                       const SortPlan* __restrict__ plan, const float4* __restrict__ pts,
-                                                       const uint32_t* __restrict__ seg_off, const SorGrid* __restrict__ grids,
-                                                       uint32_t* __restrict__ row_begin, uint32_t* __restrict__ row_end,
-                                                       uint32_t* __restrict__ skeys, uint32_t* __restrict__ svals,
-                                                       float4* __restrict__ spts) {
+// sorted keys -> start offset of every cell (cell_start[c] = first sorted position whose key is >= c, cell_start[cells] = n;
+// positions relative to the segment); also copies the sorted keys, values and points out of the sort's ping-pong
+// buffers (which side holds a segment's result is per segment).  Thread i fills the cells between key[i-1] and key[i].
+__global__ void __launch_bounds__(kThreads) k_sor_cells(const uint32_t* __restrict__ keys0, const uint32_t* __restrict__ keys1,
+                                                        const uint32_t* __restrict__ vals0, const uint32_t* __restrict__ vals1,
+                                                        const SortPlan* __restrict__ plan, const float4* __restrict__ pts,
+                                                        const uint32_t* __restrict__ seg_off, const SorGrid* __restrict__ grids,
+                                                        uint32_t* __restrict__ cell_start, uint32_t* __restrict__ skeys,
+                                                        uint32_t* __restrict__ svals, float4* __restrict__ spts) {
     const int s = blockIdx.y;
     const uint32_t beg = seg_off[s], n = seg_off[s + 1] - beg;
-    const uint32_t nx = (uint32_t)grids[s].nc[0];
+    const uint32_t cells = (uint32_t)grids[s].nc[0] * (uint32_t)grids[s].nc[1] * (uint32_t)grids[s].nc[2];
+    uint32_t* cs = cell_start + (size_t)s * (kSorCellsCap + 1);
     const int par = plan[s].final_parity;
     const bool ident = plan[s].n_active == 0;   // nothing was sorted: values were never written (identity)
     const uint32_t* keys = (par ? keys1 : keys0) + beg;
     const uint32_t* vals = (par ? vals1 : vals0) + beg;
+    if (n == 0) {
+        for (uint32_t c = blockIdx.x * kThreads + threadIdx.x; c <= cells; c += gridDim.x * kThreads) cs[c] = 0u;
+        return;
+    }
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
-        const uint32_t k = keys[i], r = k / nx;
-        if (i == 0 || keys[i - 1] / nx != r) row_begin[(size_t)s * kSorRowsCap + r] = i;
-        if (i + 1 == n || keys[i + 1] / nx != r) row_end[(size_t)s * kSorRowsCap + r] = i + 1;
+        const uint32_t k = keys[i];
+        const uint32_t first = i == 0 ? 0u : keys[i - 1] + 1u;
+        for (uint32_t c = first; c <= k; ++c) cs[c] = i;          // (empty when key[i] == key[i-1])
+        if (i + 1 == n)
+            for (uint32_t c = k + 1; c <= cells; ++c) cs[c] = n;
         const uint32_t v = ident ? beg + i : vals[i];
         skeys[beg + i] = k;
         svals[beg + i] = v;
@@ -163,8 +162,7 @@ __device__ __forceinline__ void sor_sift_down(float* __restrict__ h, int c, cons
 // top lies inside the cube (every unscanned point is farther than (sh - 0.05) cells), or the cube covers the whole grid.
 // cnt = heap entries, top = the heap's largest entry when cnt == K.
 __device__ __forceinline__ bool sor_pass(const SorGrid& G, const float4 q, const int ix, const int iy, const int iz,
-                                         const uint32_t* __restrict__ kseg, const float4* __restrict__ pseg,
-                                         const uint32_t* __restrict__ rb, const uint32_t* __restrict__ re, const int K,
+                                         const float4* __restrict__ pseg, const uint32_t* __restrict__ cs, const int K,
                                          float* __restrict__ h, const int sh, int& cnt, float& top) {
     const int nx = G.nc[0], ny = G.nc[1], nz = G.nc[2];
     cnt = 0;
@@ -196,19 +194,9 @@ __device__ __forceinline__ bool sor_pass(const SorGrid& G, const float4 q, const
                 xhi = min(xhi, (int)floorf(__fmul_rn(__fsub_rn(__fadd_rn(q.x, dxm), G.mn[0]), G.inv)));
                 if (xlo > xhi) continue;
             }
-            const uint32_t row = (uint32_t)y + (uint32_t)ny * (uint32_t)z;
-            const uint32_t e = re[row];
-            uint32_t lo = rb[row];
-            if (lo >= e) continue;
-            const uint32_t k0 = (uint32_t)xlo + (uint32_t)nx * row, k1 = (uint32_t)xhi + (uint32_t)nx * row;
-            if (kseg[lo] < k0) {   // lower_bound of k0 in the row
-                uint32_t hi = e;
-                while (lo < hi) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (kseg[mid] < k0) lo = mid + 1; else hi = mid;
-                }
-            }
-            for (uint32_t t = lo; t < e && kseg[t] <= k1; ++t) {
+            const uint32_t c0 = (uint32_t)nx * ((uint32_t)y + (uint32_t)ny * (uint32_t)z);
+            const uint32_t lo = cs[c0 + (uint32_t)xlo], e = cs[c0 + (uint32_t)xhi + 1u];
+            for (uint32_t t = lo; t < e; ++t) {
                 const float4 p = pseg[t];
                 const float dx = __fsub_rn(q.x, p.x), dy = __fsub_rn(q.y, p.y), dz = __fsub_rn(q.z, p.z);
                 const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
@@ -244,11 +232,10 @@ __device__ __forceinline__ int sor_next_sh(const SorGrid& G, int sh, int cnt, in
 
 // full search: passes until proven
 __device__ __forceinline__ int sor_query(const SorGrid& G, const float4 q, const int ix, const int iy, const int iz,
-                                         const uint32_t* __restrict__ kseg, const float4* __restrict__ pseg,
-                                         const uint32_t* __restrict__ rb, const uint32_t* __restrict__ re, const int K,
+                                         const float4* __restrict__ pseg, const uint32_t* __restrict__ cs, const int K,
                                          float* __restrict__ h, int sh, float& top) {
     int cnt;
-    while (!sor_pass(G, q, ix, iy, iz, kseg, pseg, rb, re, K, h, sh, cnt, top)) sh = sor_next_sh(G, sh, cnt, K, top);
+    while (!sor_pass(G, q, ix, iy, iz, pseg, cs, K, h, sh, cnt, top)) sh = sor_next_sh(G, sh, cnt, K, top);
     return cnt;
 }
 
@@ -272,8 +259,7 @@ __device__ __forceinline__ float sor_mean_distance(float* __restrict__ h, int cn
 __global__ void __launch_bounds__(kSorThreads) k_sor_calib(const float4* __restrict__ spts, const uint32_t* __restrict__ keys,
                                                            const uint32_t* __restrict__ seg_off, SorGrid* __restrict__ grids,
                                                            GridParams* __restrict__ plan_grids, const uint32_t* __restrict__ bbox,
-                                                           const uint32_t* __restrict__ row_begin,
-                                                           const uint32_t* __restrict__ row_end, int mean_k) {
+                                                           const uint32_t* __restrict__ cell_start, int mean_k) {
     extern __shared__ float sor_heap[];
     __shared__ float s_r[kSorThreads];
     __shared__ float s_r90;
@@ -291,10 +277,9 @@ __global__ void __launch_bounds__(kSorThreads) k_sor_calib(const float4* __restr
     // of the radius distribution and simply ranks last
     float top;
     int cnt;
-    const uint32_t* rb = row_begin + (size_t)s * kSorRowsCap;
-    const uint32_t* re = row_end + (size_t)s * kSorRowsCap;
-    bool ok = sor_pass(G, q, ix, iy, iz, keys + beg, spts + beg, rb, re, K, h, 2, cnt, top);
-    if (!ok) ok = sor_pass(G, q, ix, iy, iz, keys + beg, spts + beg, rb, re, K, h, min(sor_next_sh(G, 2, cnt, K, top), 6), cnt, top);
+    const uint32_t* cs = cell_start + (size_t)s * (kSorCellsCap + 1);
+    bool ok = sor_pass(G, q, ix, iy, iz, spts + beg, cs, K, h, 2, cnt, top);
+    if (!ok) ok = sor_pass(G, q, ix, iy, iz, spts + beg, cs, K, h, min(sor_next_sh(G, 2, cnt, K, top), 6), cnt, top);
     s_r[threadIdx.x] = (ok && cnt == K) ? sqrtf(top) : 3.0e38f;
     if (threadIdx.x == 0) s_r90 = 0.f;
     __syncthreads();
@@ -312,7 +297,7 @@ __global__ void __launch_bounds__(kSorThreads) k_sor_calib(const float4* __restr
         for (;;) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) nc[a] = (long long)(ext[a] / c) + 2;
-            if (nc[0] * nc[1] * nc[2] <= (1ll << 31) && nc[1] * nc[2] <= (long long)kSorRowsCap) break;
+            if (nc[0] * nc[1] * nc[2] <= (long long)kSorCellsCap) break;
             c *= 1.26;
         }
         SorGrid N = G;
@@ -331,8 +316,7 @@ __global__ void __launch_bounds__(kSorThreads) k_sor_calib(const float4* __restr
 // Dynamic shared memory of both kernels: (mean_k + 1) * kSorThreads floats.
 __global__ void __launch_bounds__(kSorThreads) k_sor_knn(const float4* __restrict__ spts, const uint32_t* __restrict__ keys,
                                                          const uint32_t* __restrict__ vals, const uint32_t* __restrict__ seg_off,
-                                                         const SorGrid* __restrict__ grids, const uint32_t* __restrict__ row_begin,
-                                                         const uint32_t* __restrict__ row_end, int mean_k,
+                                                         const SorGrid* __restrict__ grids, const uint32_t* __restrict__ cell_start, int mean_k,
                                                          float* __restrict__ dist, uint2* __restrict__ hard,
                                                          uint32_t* __restrict__ n_hard) {
     extern __shared__ float sor_heap[];
@@ -348,8 +332,7 @@ __global__ void __launch_bounds__(kSorThreads) k_sor_knn(const float4* __restric
     const int ix = (int)(key % (uint32_t)G.nc[0]), rr = (int)(key / (uint32_t)G.nc[0]), iy = rr % G.nc[1], iz = rr / G.nc[1];
     int cnt;
     float top;
-    if (sor_pass(G, q, ix, iy, iz, keys + beg, spts + beg, row_begin + (size_t)s * kSorRowsCap, row_end + (size_t)s * kSorRowsCap, K,
-                 h, 2, cnt, top)) {
+    if (sor_pass(G, q, ix, iy, iz, spts + beg, cell_start + (size_t)s * (kSorCellsCap + 1), K, h, 2, cnt, top)) {
         dist[vals[beg + j]] = sor_mean_distance(h, cnt, mean_k);
     } else {
         const int sh = min(sor_next_sh(G, 2, cnt, K, top), 65535);
@@ -361,8 +344,7 @@ __global__ void __launch_bounds__(kSorThreads) k_sor_knn(const float4* __restric
 __global__ void __launch_bounds__(kSorThreads) k_sor_knn_hard(const float4* __restrict__ spts, const uint32_t* __restrict__ keys,
                                                               const uint32_t* __restrict__ vals, const uint32_t* __restrict__ seg_off,
                                                               const SorGrid* __restrict__ grids,
-                                                              const uint32_t* __restrict__ row_begin,
-                                                              const uint32_t* __restrict__ row_end, int mean_k,
+                                                              const uint32_t* __restrict__ cell_start, int mean_k,
                                                               float* __restrict__ dist, const uint2* __restrict__ hard,
                                                               const uint32_t* __restrict__ n_hard) {
     extern __shared__ float sor_heap[];
@@ -378,8 +360,8 @@ __global__ void __launch_bounds__(kSorThreads) k_sor_knn_hard(const float4* __re
     const uint32_t key = keys[hq.x];
     const int ix = (int)(key % (uint32_t)G.nc[0]), rr = (int)(key / (uint32_t)G.nc[0]), iy = rr % G.nc[1], iz = rr / G.nc[1];
     float top;
-    const int cnt = sor_query(G, q, ix, iy, iz, keys + beg, spts + beg, row_begin + (size_t)s * kSorRowsCap,
-                              row_end + (size_t)s * kSorRowsCap, K, h, (int)(hq.y & 0xffffu), top);
+    const int cnt = sor_query(G, q, ix, iy, iz, spts + beg, cell_start + (size_t)s * (kSorCellsCap + 1), K, h, (int)(hq.y & 0xffffu),
+                              top);
     dist[vals[hq.x]] = sor_mean_distance(h, cnt, mean_k);
 }
 
