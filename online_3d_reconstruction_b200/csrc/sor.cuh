@@ -102,7 +102,9 @@ __global__ void __launch_bounds__(kThreads) k_sor_key(const float4* __restrict__
 
 // sorted keys -> start offset of every cell (cell_start[c] = first sorted position whose key is >= c, cell_start[cells] = n;
 // positions relative to the segment); also copies the sorted keys, values and points out of the sort's ping-pong
-// buffers (which side holds a segment's result is per segment).  Thread i fills the cells between key[i-1] and key[i].
+// buffers (which side holds a segment's result is per segment).  Position i owns the cells (key[i-1], key[i]]; most cells of
+// a surface's bounding box are empty, so those gaps are long (whole rows of cells): gaps of more than 4 cells are filled by
+// the whole warp with coalesced stores, and the cells behind the last key by the whole grid.
 __global__ void __launch_bounds__(kThreads) k_sor_cells(const uint32_t* __restrict__ keys0, const uint32_t* __restrict__ keys1,
                                                         const uint32_t* __restrict__ vals0, const uint32_t* __restrict__ vals1,
                                                         const SortPlan* __restrict__ plan, const float4* __restrict__ pts,
@@ -117,20 +119,31 @@ __global__ void __launch_bounds__(kThreads) k_sor_cells(const uint32_t* __restri
     const bool ident = plan[s].n_active == 0;   // nothing was sorted: values were never written (identity)
     const uint32_t* keys = (par ? keys1 : keys0) + beg;
     const uint32_t* vals = (par ? vals1 : vals0) + beg;
-    if (n == 0) {
-        for (uint32_t c = blockIdx.x * kThreads + threadIdx.x; c <= cells; c += gridDim.x * kThreads) cs[c] = 0u;
-        return;
-    }
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
-        const uint32_t k = keys[i];
-        const uint32_t first = i == 0 ? 0u : keys[i - 1] + 1u;
-        for (uint32_t c = first; c <= k; ++c) cs[c] = i;          // (empty when key[i] == key[i-1])
-        if (i + 1 == n)
-            for (uint32_t c = k + 1; c <= cells; ++c) cs[c] = n;
-        const uint32_t v = ident ? beg + i : vals[i];
-        skeys[beg + i] = k;
-        svals[beg + i] = v;
-        spts[beg + i] = pts[v];
+    const uint32_t gtid = blockIdx.x * kThreads + threadIdx.x, gstride = gridDim.x * kThreads;
+    const uint32_t tail = n ? keys[n - 1] + 1u : 0u;
+    for (uint32_t c = tail + gtid; c <= cells; c += gstride) cs[c] = n;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t base = gtid - lane; base < n; base += gstride) {   // warp-uniform trip count
+        const uint32_t i = base + lane;
+        uint32_t first = 0u, len = 0u;
+        if (i < n) {
+            const uint32_t k = keys[i];
+            first = i == 0 ? 0u : keys[i - 1] + 1u;
+            len = k + 1u - first;                                    // 0 when key[i] == key[i-1]
+            if (len <= 4u)
+                for (uint32_t c = 0; c < len; ++c) cs[first + c] = i;
+            const uint32_t v = ident ? beg + i : vals[i];
+            skeys[beg + i] = k;
+            svals[beg + i] = v;
+            spts[beg + i] = pts[v];
+        }
+        uint32_t m = __ballot_sync(kFull, len > 4u);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1u;
+            const uint32_t f = __shfl_sync(kFull, first, src), l = __shfl_sync(kFull, len, src);
+            for (uint32_t c = lane; c < l; c += 32u) cs[f + c] = base + (uint32_t)src;
+        }
     }
 }
 
