@@ -162,6 +162,39 @@ def algorithmic_bytes(wl, n_valid, n_vox, n_cells_cycle, bd, np1=4, np2=3, n_par
     }
 
 
+def _cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-rank runs: keep the rank's host thread — and with it, by first touch, the pinned staging buffers it is about to
+    allocate — on the NUMA node the rank's GPU hangs off, so that N ranks' H2D copies read N different memory controllers
+    instead of crossing the socket link.  Returns a short description for the JSON line (None when nothing was bound:
+    no sysfs entry, a single node, or the node's CPUs are outside this process's allowed set)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _cpulist(f.read()) & os.sched_getaffinity(0)
+        if not cpus or cpus == os.sched_getaffinity(0):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"node {node}, {len(cpus)} cpus"
+    except Exception:   # binding is an optimisation, never a requirement
+        return None
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -426,7 +459,11 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    allowed = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     res, (disp, bgr, T) = run_ours(args, rank, world, local_rank)
+    os.sched_setaffinity(0, allowed)
+    res["config"]["host_numa_binding"] = numa
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         wl = args.workload
         n = min(len(disp), args.cpu_baseline_frames)
