@@ -24,6 +24,10 @@ namespace o3r {
 #ifndef O3R_RS_MINB
 #define O3R_RS_MINB 4
 #endif
+// In-warp peer search of the ranking loop: 0 = match.any, 1 = shared-memory atomicOr on a per-warp mask per digit.
+#ifndef O3R_RS_RANK
+#define O3R_RS_RANK 1
+#endif
 constexpr int kRsItems = O3R_RS_ITEMS;
 constexpr int kRsTile = kThreads * kRsItems;  // 4096 pairs per CTA
 // Measured on B200 (r01): 10-bit digits save a pass (28-bit index: 3 instead of 4) but the per-tile bin work
@@ -226,7 +230,8 @@ struct __align__(8) RsPair<uint32_t> { uint32_t k; uint32_t v; };
 
 template <typename KeyT>
 constexpr size_t rs_scatter_smem() {
-    return (size_t)kRsTile * sizeof(RsPair<KeyT>) + (size_t)kWarps * kRsBins * 2 + (size_t)kRsBins * 4 + 36 * 4;
+    return (size_t)kRsTile * sizeof(RsPair<KeyT>) + (size_t)kWarps * kRsBins * 2 + (size_t)kRsBins * 4 + 36 * 4 +
+           (O3R_RS_RANK == 1 && sizeof(KeyT) == 4 ? (size_t)kWarps * kRsBins * 4 : 0);
 }
 
 constexpr uint32_t kStLocal = 1u << 30, kStGlobal = 2u << 30, kStMask = (1u << 30) - 1u;
@@ -253,6 +258,9 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? O3R_RS_MINB : (O
     uint32_t* gbase = reinterpret_cast<uint32_t*>(cnt + kWarps * kRsBins);   // [1024] destination of local position i: gbase[d] + i
     uint32_t* s_scan = gbase + kRsBins;                                      // [34]
     uint32_t* s_ticket = s_scan + 34;
+    // 32-bit keys only: with 16-byte pairs the extra 8 KB would cost the third resident CTA
+    constexpr bool kOrMask = O3R_RS_RANK == 1 && sizeof(KeyT) == 4;
+    uint32_t* wmask = s_ticket + 2;                                          // [kWarps][kRsBins] lanes holding digit d (kOrMask)
 
     if (threadIdx.x == 0) *s_ticket = atomicAdd(ticket, 1u);
     __syncthreads();
@@ -287,6 +295,10 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? O3R_RS_MINB : (O
         uint32_t* cz = reinterpret_cast<uint32_t*>(cnt + warp * kRsBins);
 #pragma unroll
         for (int i = 0; i < kRsBins / 2 / 32; ++i) cz[i * 32 + lane] = 0u;
+        if constexpr (kOrMask) {
+#pragma unroll
+            for (int i = 0; i < kRsBins / 32; ++i) wmask[warp * kRsBins + i * 32 + lane] = 0u;
+        }
         __syncwarp();
     }
     // exclusive scan of the segment's digit histogram = where each digit's run starts in the segment
@@ -323,16 +335,35 @@ __global__ void __launch_bounds__(kThreads, sizeof(KeyT) == 4 ? O3R_RS_MINB : (O
         }
     }
     uint16_t* wc = cnt + warp * kRsBins;
+    uint32_t* wm = wmask + warp * kRsBins;
 #pragma unroll
     for (int r = 0; r < kRsItems; ++r) {
         // padding items carry the highest digit and sit at the very end of the tile order, so they never
         // precede a real item inside any digit run
         const uint32_t d = rs_digit(key[r], shift, dmask);
-        const unsigned peers = __match_any_sync(kFull, d);
-        const uint32_t old = wc[d];                   // every peer reads the counter (broadcast) ...
-        __syncwarp();
-        if ((peers & lt) == 0u) wc[d] = (uint16_t)(old + __popc(peers));   // ... then the lowest peer bumps it
-        __syncwarp();
+        unsigned peers;
+        uint32_t old;
+        if constexpr (kOrMask) {
+            // MATCH.ANY costs one step per DISTINCT value in the warp (ncu: the ADU pipe at 78 % on the passes over evenly
+            // spread digits, which ran 1.7x longer than the pass over the clustered top digit).  The lanes OR their bit
+            // into the digit's mask word instead: one shared-memory atomic whatever the digits are.
+            atomicOr(&wm[d], 1u << lane);
+            __syncwarp();
+            peers = wm[d];
+            old = wc[d];                                  // every peer reads mask and counter (broadcast) ...
+            __syncwarp();
+            if ((peers & lt) == 0u) {                     // ... then the lowest peer bumps the counter and clears the mask
+                wc[d] = (uint16_t)(old + __popc(peers));
+                wm[d] = 0u;
+            }
+            __syncwarp();
+        } else {
+            peers = __match_any_sync(kFull, d);
+            old = wc[d];                                  // every peer reads the counter (broadcast) ...
+            __syncwarp();
+            if ((peers & lt) == 0u) wc[d] = (uint16_t)(old + __popc(peers));   // ... then the lowest peer bumps it
+            __syncwarp();
+        }
         const uint32_t rnk = old + __popc(peers & lt);
         if (r & 1) rk[r >> 1] |= rnk << 16; else rk[r >> 1] = rnk;
     }
