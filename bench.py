@@ -36,9 +36,9 @@ from online_3d_reconstruction_b200 import abi, synth  # noqa: E402
 
 # (workload, kernel) -> DRAM bytes per launch from `ncu --set full` (see profiles/r01*_ncu_*.txt)
 NCU_TRAFFIC = {
-    # profiles/r01k_ncu_full.txt: 7 launches per cycle (4 per-frame-index passes: 405.1, 557.9, 555.6, 552.2 MB;
-    # 3 passes over the tile partials: 26.0, 26.3, 25.9 MB) -> mean per launch
-    ("config2_semidense_720p", "k_rs_onesweep_u32"): 307.0e6,
+    # profiles/r01n_ncu_full.txt: 7 launches per cycle (4 per-frame-index passes: 403.8, 554.8, 554.7, 551.9 MB;
+    # 3 passes over the tile partials: 25.7 MB each) -> mean per launch
+    ("config2_semidense_720p", "k_rs_onesweep_u32"): 306.0e6,
 }
 
 WORKLOADS = {
