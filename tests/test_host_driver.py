@@ -55,19 +55,20 @@ def read_ply(path):
     return pts, raw[:h], raw[h + 15 * n:]
 
 
-def test_cli_usage_and_reference_error_messages(pose_bin):
-    r = subprocess.run([pose_bin], capture_output=True, text=True)
+def test_cli_usage_and_reference_error_messages(pose_bin, tmp_path):
+    # (the driver creates output/<timestamp>/ under its working directory, like the reference: keep that out of the repo)
+    r = subprocess.run([pose_bin], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 0 and "--seq_len" in r.stdout and "--dont_downsample" in r.stdout
-    r = subprocess.run([pose_bin, "1", "2", "--seq_len", "0"], capture_output=True, text=True)
+    r = subprocess.run([pose_bin, "1", "2", "--seq_len", "0"], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 1 and "Exception: invalid seq_len value!" in r.stdout       # pose_functions.cpp:199-200
-    r = subprocess.run([pose_bin, "1", "2", "--voxel_size", "0.05"], capture_output=True, text=True)
+    r = subprocess.run([pose_bin, "1", "2", "--voxel_size", "0.05"], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 1 and "seq_len" in r.stdout                                   # pose.h:97
-    r = subprocess.run([pose_bin, "--visualize", "x.ply"], capture_output=True, text=True)
+    r = subprocess.run([pose_bin, "--visualize", "x.ply"], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 2 and "host-side tool" in r.stdout
     # every flag north_star lists is parsed and echoed the way the reference echoes it
     r = subprocess.run([pose_bin, "5", "6", "--seq_len", "50", "--voxel_size", "0.05", "--jump_pixels", "15",
                         "--range_width", "30", "--dist_nearby", "2", "--min_points_per_voxel", "1", "--blur_kernel", "1",
-                        "--dont_downsample", "--data_root", "/nonexistent"], capture_output=True, text=True)
+                        "--dont_downsample", "--data_root", "/nonexistent"], capture_output=True, text=True, cwd=tmp_path)
     for s in ("seq_len 50", "voxel_size 0.05", "jump_pixels 15", "range_width 30", "dist_nearby 2",
               "min_points_per_voxel 1", "blur_kernel 1", "dont_downsample"):
         assert s in r.stdout, s
