@@ -119,8 +119,14 @@ def make_data(wl, rank, world, n_steps_total):
     return disp, bgr, T
 
 
-def params_for(wl, device, merge_mode=abi.MERGE_ACCUMULATE_TILED):
+MERGE_MODES = {"fused": abi.MERGE_ACCUMULATE_FUSED, "tiled": abi.MERGE_ACCUMULATE_TILED, "accumulate": abi.MERGE_ACCUMULATE}
+MERGE_MODE = "fused"   # set from --merge-mode
+
+
+def params_for(wl, device, merge_mode=None):
     rows, cols, dt, J, v, mp, nd, F, seed, qs = WORKLOADS[wl]
+    if merge_mode is None:
+        merge_mode = MERGE_MODES[MERGE_MODE]
     return abi.make_params(rows=rows, cols=cols, jump_pixels=J, voxel_size=v, min_points_per_voxel=mp,
                            dont_downsample=nd, Q=synth.q_scaled(qs), device=device, max_batch_frames=F,
                            merge_mode=merge_mode, sor_mean_k=SOR_MEAN_K.get(wl, 0))
@@ -156,6 +162,11 @@ def algorithmic_bytes(wl, n_valid, n_vox, n_cells_cycle, bd, np1=4, np2=3, n_par
         "k_vg_heads": n_valid * 4,
         "k_vg_reduce_w": n_valid * (4 + 4 + 16) + n_vox * 16,
         "k_cell_prereduce": n_vox * 16 + n_part * 40,
+        # the fused bucket engine (csrc/bucket.cuh): histogram reads the disparity, the scatter reads disparity + colour and
+        # writes 16 B point + 4 B scan position, the reduce reads those and writes the partial cells
+        "k_bk_hist": npix * bd,
+        "k_bk_scatter": npix * bd + npix * 3 + n_valid * 20,
+        "k_bk_reduce": n_valid * 20 + n_part * 40,
         "k_acc_key": m * (item + 8),
         "k_acc_heads": m * 4,
         "k_acc_reduce": m * (4 + 4 + item) + n_cells_cycle * 40,
@@ -248,6 +259,7 @@ def run_ours(args, rank, world, local_rank):
             exchange()
         stats["n_vox"] = int(counts.sum())
         stats["n_part"] = P.lastCyclePartials()
+        stats["engine"] = P.lastCycleEngine()
         if nd:   # --dont_downsample: cloud_small = cloud_big, nothing to compute; it is saved once at exit
             stats["n_out"] = 0
             return
@@ -366,7 +378,8 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": wl, "frames_per_step_per_gpu": F, "frame": f"{cols}x{rows}", "jump_pixels": J,
                    "voxel_size": v, "min_points_per_voxel": mp, "dont_downsample": nd, "seq_len": F,
                    "valid_points_per_step_per_gpu": n_valid, "per_frame_voxels_per_step_per_gpu": stats["n_vox"],
-                   "tile_partials_per_step_per_gpu": stats.get("n_part", 0), "merge_mode": "ACCUMULATE_TILED",
+                   "tile_partials_per_step_per_gpu": stats.get("n_part", 0), "merge_mode": "ACCUMULATE_" + MERGE_MODE.upper() if MERGE_MODE != "accumulate" else "ACCUMULATE",
+                   "engine": "bucket" if stats.get("engine") else "sort",
                    "resident_cells_after_timed_region": cells_after_value,
                    "l2": f"inputs ({F * (rows * cols * bd + rows * cols * 3) / 1e6:.0f} MB/step) and intermediates exceed the 126 MB L2",
                    "sor": ("StatisticalOutlierRemoval(50, 1.0) applied per frame on both the GPU and the CPU side" if wl in SOR_MEAN_K
@@ -445,7 +458,10 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=50, help="frames per CPU-reference step (bounded sample)")
     ap.add_argument("--cpu-baseline-frames", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--merge-mode", default="fused", choices=sorted(MERGE_MODES))
     args = ap.parse_args()
+    global MERGE_MODE
+    MERGE_MODE = args.merge_mode
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

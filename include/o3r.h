@@ -59,7 +59,7 @@ enum {
                                  cycle; o3r_cloud_transform is unsupported                         */
     O3R_MERGE_RETAIN     = 1, /* cloud_big kept as points (pose.cpp:434); o3r_cloud_transform
                                  applies tf_icp in place (pose.cpp:353); one-shot voxelisation     */
-    O3R_MERGE_ACCUMULATE_TILED = 2 /* as ACCUMULATE, but every 1024 consecutive per-frame voxels are first
+    O3R_MERGE_ACCUMULATE_TILED = 2, /* as ACCUMULATE, but every 1024 consecutive per-frame voxels are first
                                  summed per cell inside the GPU's shared memory and only those partial
                                  sums are sorted and merged (8x less traffic).  Cell keys, point counts and
                                  colour sums are identical to ACCUMULATE; centroids differ by float
@@ -67,6 +67,15 @@ enum {
                                  reproducible from run to run.  While the pre-reduction does not reduce
                                  (more than one partial per two voxels: grids finer than the point spacing)
                                  it is skipped and the voxels are merged directly, as in ACCUMULATE    */
+    O3R_MERGE_ACCUMULATE_FUSED = 3 /* the fused disparity -> cloud -> voxel pipeline: a cycle's points are binned once into
+                                 buckets of 5 x 5 per-frame leaf columns (= one combined cell) and every bucket is finished
+                                 in shared memory: per-frame VoxelGrid centroids (bit-identical to ACCUMULATE's, each leaf
+                                 summed in scan order) are folded straight into one partial sum per combined cell; the
+                                 per-frame clouds are never written to memory, so o3r_last_batch_points is unsupported
+                                 (frame_counts are still reported).  Same result contract as ACCUMULATE_TILED: keys, counts,
+                                 colour sums exact, centroids within float reassociation (<= 1e-5 relative), reproducible.
+                                 Batches the engine cannot take (StatisticalOutlierRemoval on, a Q without the rectified-
+                                 stereo sparsity, more than 256 points in one bucket) run as ACCUMULATE_TILED             */
 };
 
 /* Read-only configuration: the `Pose` members the path reads (pose.h:93-98,108,118,126-128,149,168). */
@@ -147,13 +156,22 @@ int o3r_frame_cloud(o3r_ctx* ctx, const o3r_frame* frame, int disp_type,
 int o3r_frames_cloud(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_type,
                      uint32_t* frame_counts);
 
-/* Starts the host->device copies of a coming o3r_frames_cloud call (same frame pointers, same n) on the context's copy
- * stream and returns at once; the copies overlap whatever the context is computing (input staging is double-buffered:
- * one prefetch may be pending while the call before it is issued, e.g. prefetch(k+1); frames_cloud(k); ...).
+/* Announces the frames of a coming o3r_frames_cloud call (same frame pointers, same n) so that their host->device copies
+ * overlap whatever the context is computing (input staging is double-buffered: one prefetch may be pending while the call
+ * before it is issued, e.g. prefetch(k+1); frames_cloud(k); ...).  The request is only recorded here; the copies are issued
+ * on the context's copy streams by the next frame-path call (right after its kernels are queued) or the next prefetch.
  * The reference loads every image into host RAM up front (populateData, pose_functions.cpp:624-744); this is the
- * device-side equivalent for the next cycle.  The host buffers must stay valid and unchanged until that
- * o3r_frames_cloud call returns.  A following o3r_frames_cloud with different frames simply ignores the prefetch. */
+ * device-side equivalent for the next cycle.
+ * LIFETIME: from this call on the library may read the frames' host buffers at any time, until either the matching
+ * o3r_frames_cloud call (same buffer pointers, n and disp_type) has returned or o3r_frames_prefetch_cancel has returned;
+ * they must stay allocated and unchanged for that long.  A prefetch is matched by its buffer POINTERS, so buffers that are
+ * recycled with new contents before then would be served stale.  A prefetch that is never consumed only costs the copy —
+ * but its buffers stay bound by the rule above until it is cancelled or overwritten by two later prefetches. */
 int o3r_frames_prefetch(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_type);
+
+/* Abandons every announced prefetch: a recorded request is dropped, copies already in flight are waited for, staged inputs
+ * are forgotten.  When it returns the library holds no reference to any prefetched host buffer. */
+int o3r_frames_prefetch_cancel(o3r_ctx* ctx);
 
 /* Same as o3r_frames_cloud but every pointer inside `frames` is DEVICE memory on ctx's device and
  * nothing is copied (the inputs-resident-in-HBM measurement).  T is still read from host. */
@@ -260,6 +278,10 @@ size_t o3r_exchange_bound(o3r_ctx* ctx);
 int o3r_exchange_pack_dev(o3r_ctx* ctx, int world, o3r_cell* send_dev, size_t cap, uint32_t* info_dev);
 int o3r_exchange_merge_bb(o3r_ctx* ctx, const o3r_cell* recv_dev, size_t n, const int bb[6]);
 
+/* Parity probe for O3R_MERGE_ACCUMULATE_FUSED: when set, the fused engine also stores every per-frame voxel centroid of
+ * the batch, in no particular order, and o3r_last_batch_points returns that multiset. */
+int o3r_set_keep_frame_voxels(o3r_ctx* ctx, int keep);
+
 /* When set, o3r_frames_cloud* keeps the batch's per-frame clouds but does not merge them into the
  * resident cloud; the caller runs o3r_exchange_pack / o3r_exchange_merge instead. */
 int o3r_set_defer_merge(o3r_ctx* ctx, int defer);
@@ -277,6 +299,9 @@ uint64_t o3r_launch_count(const o3r_ctx* ctx);
 /* Tile partial cells the last batch produced (O3R_MERGE_ACCUMULATE_TILED; 0 otherwise): the record count the
  * merge's sort and reduce ran on, for traffic accounting. */
 size_t o3r_last_batch_partials(const o3r_ctx* ctx);
+/* Engine the last batch ran through: 1 = the fused bucket engine (O3R_MERGE_ACCUMULATE_FUSED), 0 = the sort engine
+ * (every other mode, and FUSED batches the bucket engine could not take). */
+int o3r_last_batch_engine(const o3r_ctx* ctx);
 /* The CUDA stream all work of the context is issued on (a cudaStream_t) — for event timing. */
 void* o3r_stream(o3r_ctx* ctx);
 /* Blocks until all work issued on the context's stream has completed. */

@@ -16,7 +16,7 @@ O3R_ERR_NOMEM = -5
 
 DISP_U8, DISP_U16, DISP_F32, DISP_F64 = 0, 1, 2, 3
 BLUR_MEDIAN, BLUR_BOX, BLUR_BILATERAL = 0, 1, 2
-MERGE_ACCUMULATE, MERGE_RETAIN, MERGE_ACCUMULATE_TILED = 0, 1, 2
+MERGE_ACCUMULATE, MERGE_RETAIN, MERGE_ACCUMULATE_TILED, MERGE_ACCUMULATE_FUSED = 0, 1, 2, 3
 
 DISP_NP = {DISP_U8: np.uint8, DISP_U16: np.uint16, DISP_F32: np.float32, DISP_F64: np.float64}
 

@@ -132,7 +132,9 @@ __device__ __forceinline__ GridParams make_grid(const uint32_t* bb, float ix, fl
     G.mul1 = div[0];
     G.mul2 = div[0] * div[1];
     const long long cells = (long long)div[0] * div[1] * div[2];
-    G.key_bits = cells > 1 ? 64 - __clzll(cells - 1) : 1;
+    // PCL's index is a 32-bit int: when div0*div1*div2 exceeds it (the guard above uses the slightly smaller d = (int64)((max - min) * inv) + 1)
+    // the index wraps, here exactly as in PCL, and all 32 bits are live
+    G.key_bits = cells > 1 ? min(32, 64 - __clzll(cells - 1)) : 1;
     return G;
 }
 

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "blur.cuh"
+#include "bucket.cuh"
 #include "common.cuh"
 #include "prepass.cuh"
 #include "prereduce.cuh"
@@ -48,8 +49,8 @@ struct DevBuf {
         if (e != cudaSuccess) return e;
         if (p && preserve) {
             e = cudaMemcpyAsync(np, p, preserve, cudaMemcpyDeviceToDevice, st);
-            if (e != cudaSuccess) return e;
-            cudaStreamSynchronize(st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { cudaFree(np); return e; }
         }
         if (p) cudaFree(p);
         p = np;
@@ -144,6 +145,13 @@ struct o3r_ctx {
     DevBuf ckey, cacc, crgb, new_cnt, new_off, new_keys, okeys;
     DevBuf sor_hard, sor_pts, sor_off, sor_dist, sor_grids, sor_pgrids, sor_rows, sor_thr, sor_skeys, sor_svals, sor_cnt, sor_cntoff;   // SOR scratch
     DevBuf partials, pr_status;   // TILED mode: the batch's tile partials (o3r_cell) and the look-back words
+    // FUSED mode (bucket.cuh): per-frame bucket grids, bucket counters / cursors, non-empty bucket list, binned points + scan
+    // positions, look-back words, flags / totals / tickets / per-frame counts
+    DevBuf bk_frames, bk_counts, bk_nl, bk_pts, bk_pos, bk_status, bk_misc, bk_stray;
+    int bk_reduce_ctas = 148 * 4;
+    bool bucket_off = false;          // a batch overflowed the engine's limits: the sort engine serves this context from then on
+    bool last_bucketed = false;       // the last batch ran through the bucket engine (no per-frame clouds were materialised)
+    bool keep_frame_voxels = false;   // parity probe: the bucket engine also writes every per-frame voxel centroid (any order)
     size_t last_partials = 0;
     bool last_has_partials = false;
     uint32_t n_cyc = 0;
@@ -165,7 +173,8 @@ struct o3r_ctx {
     // tile pre-reduction is skipped while it does not reduce (probed again every 16th batch)
     unsigned tiled_poor = 0, tiled_batches = 0;
     bool tiled_now = false;
-    bool tiled() const { return !p.dont_downsample && p.merge_mode == O3R_MERGE_ACCUMULATE_TILED; }
+    bool tiled() const { return !p.dont_downsample && (p.merge_mode == O3R_MERGE_ACCUMULATE_TILED || p.merge_mode == O3R_MERGE_ACCUMULATE_FUSED); }
+    bool fused() const { return !p.dont_downsample && p.merge_mode == O3R_MERGE_ACCUMULATE_FUSED; }
     int fail(int code, const std::string& m) { err = m; return code; }
     int fail_cuda(cudaError_t e, const char* what, const char* file, int line) {
         const char* base = strrchr(file, '/');

@@ -4,6 +4,7 @@
 
 #include "host_merge.cuh"
 #include "host_sor.cuh"
+#include "host_bucket.cuh"
 
 namespace {
 
@@ -298,145 +299,196 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
     const size_t cap_batch = per_frame_cap * n, cap_chunk = per_frame_cap * chunk;
     if (cap_batch >= (1ull << 32)) return ctx->fail(O3R_ERR_INVALID, "batch exceeds 2^32 samples; use fewer frames");
     const size_t n_tiles = (size_t)P.tiles_per_frame * chunk;
-    CU(ctx->tile_cnt.ensure(n_tiles * 4));
-    CU(ctx->tile_off.ensure(n_tiles * 4));
-    CU(ctx->bbox.ensure((size_t)chunk * 6 * 4));
-    CU(ctx->frame_off.ensure((size_t)(chunk + 1) * 4));
-    CU(ctx->grids.ensure((size_t)chunk * sizeof(GridParams)));
-    SortU32 sb{nullptr, nullptr, nullptr, nullptr};
     uint32_t* cnt = ctx->counters.as<uint32_t>();
-    if (!opt.mask_only) {
-        CU(ctx->vox_off.ensure((size_t)(n + 1) * 4));
-        if (P.want_keys) {
-            CU(ctx->pts.ensure(cap_chunk * 16));
-            CU(ctx->vox.ensure(cap_batch * 16));
-            int rc = carve_sort_u32(ctx, cap_chunk, sb);
-            if (rc) return rc;
-            if (!ctx->retain()) LAUNCH(k_cellbb_init, 1, 32, 0, reinterpret_cast<int*>(cnt + CNT_CELLBB));
-            ctx->tiled_now = ctx->tiled() && !(ctx->tiled_poor && (ctx->tiled_batches % 16) != 0);
-            ++ctx->tiled_batches;
-            if (ctx->tiled_now) {   // worst case one partial per item; never reached in practice (~1/8)
-                CU(ctx->partials.ensure(cap_batch * sizeof(o3r_cell)));
-                CU(ctx->pr_status.ensure(((size_t)cdiv(cap_chunk, kPrTile) + 16) * 4));
+    // The fused bucket engine (bucket.cuh) serves the merged path of O3R_MERGE_ACCUMULATE_FUSED; everything that needs the
+    // per-frame clouds themselves (single-frame calls, masks, StatisticalOutlierRemoval) or that it cannot bound runs
+    // through the sort engine, as does a batch on which the device raised one of its overflow flags (second attempt).
+    BkPlan bkp;
+    bool use_bucket = ctx->fused() && P.want_keys && opt.merge && !opt.mask_only && !ctx->bucket_off &&
+                      !(p.sor_mean_k > 0 && J > 0) && bk_plan(ctx, frames, n, chunk, disp_type, label_mode, bkp);
+    if (trace && ctx->fused()) fprintf(stderr, "[o3r trace] fused: bucket engine %s (want_keys %d merge %d off %d canon %d)\n", use_bucket ? "on" : "off", P.want_keys, (int)opt.merge, (int)ctx->bucket_off, ctx->canon);
+    bool inputs_resident = false;   // second attempt: the staging buffers already hold every frame
+    double tr1 = 0, tr2 = 0;
+    for (;;) {
+        CU(ctx->tile_cnt.ensure(n_tiles * 4));
+        CU(ctx->tile_off.ensure(n_tiles * 4));
+        CU(ctx->bbox.ensure((size_t)chunk * 6 * 4));
+        CU(ctx->frame_off.ensure((size_t)(chunk + 1) * 4));
+        CU(ctx->grids.ensure((size_t)chunk * sizeof(GridParams)));
+        SortU32 sb{nullptr, nullptr, nullptr, nullptr};
+        if (!opt.mask_only) {
+            CU(ctx->vox_off.ensure((size_t)(n + 1) * 4));
+            if (use_bucket) {
+                int rc = bk_prepare(ctx, bkp, n, cap_batch, cap_chunk);
+                if (rc) return rc;
+                if (ctx->keep_frame_voxels) CU(ctx->vox.ensure(cap_batch * 16));
+                const BkMisc M = bk_misc(ctx, n);
+                ZERO(M.flags, 8);
+                ZERO(M.dbg_cnt, 4);
+                LAUNCH(k_cellbb_init, 1, 32, 0, reinterpret_cast<int*>(cnt + CNT_CELLBB));
                 ZERO(cnt + CNT_PART, 8);
+                ctx->tiled_now = false;
+            } else if (P.want_keys) {
+                CU(ctx->pts.ensure(cap_chunk * 16));
+                CU(ctx->vox.ensure(cap_batch * 16));
+                int rc = carve_sort_u32(ctx, cap_chunk, sb);
+                if (rc) return rc;
+                if (!ctx->retain()) LAUNCH(k_cellbb_init, 1, 32, 0, reinterpret_cast<int*>(cnt + CNT_CELLBB));
+                ctx->tiled_now = ctx->tiled() && !(ctx->tiled_poor && (ctx->tiled_batches % 16) != 0);
+                ++ctx->tiled_batches;
+                if (ctx->tiled_now) {   // worst case one partial per item; never reached in practice (~1/8)
+                    CU(ctx->partials.ensure(cap_batch * sizeof(o3r_cell)));
+                    CU(ctx->pr_status.ensure(((size_t)cdiv(cap_chunk, kPrTile) + 16) * 4));
+                    ZERO(cnt + CNT_PART, 8);
+                }
+            } else {
+                CU(ctx->pts.ensure(cap_batch * 16));
             }
-        } else {
-            CU(ctx->pts.ensure(cap_batch * 16));
+            ZERO(cnt + CNT_BASE, 4);
+            ZERO(ctx->vox_off.p, 4);
         }
-        ZERO(cnt + CNT_BASE, 4);
-        ZERO(ctx->vox_off.p, 4);
-    }
-    ctx->last_is_vox = P.want_keys;
-    uint32_t* goff = ctx->vox_off.as<uint32_t>();
+        if (!opt.mask_only) ctx->last_is_vox = P.want_keys;
+        uint32_t* goff = ctx->vox_off.as<uint32_t>();
 
-    for (int f0 = 0; f0 < n; f0 += chunk) {
-        const int nc = std::min(chunk, n - f0);
-        if (host_inputs && !prefetched) {  // H2D of this chunk on the copy stream; the compute stream waits for its event only
-            int rc = stage_copy(ctx, frames, fd_stage, f0, nc, label_mode, G);
+        for (int f0 = 0; f0 < n; f0 += chunk) {
+            const int nc = std::min(chunk, n - f0);
+            if (host_inputs && !prefetched && !inputs_resident) {  // H2D of this chunk on the copy stream; the compute stream waits for its event only
+                int rc = stage_copy(ctx, frames, fd_stage, f0, nc, label_mode, G);
+                if (rc) return rc;
+                cudaEvent_t ev = ctx->chunk_event(f0 / chunk);
+                CU(cudaEventRecord(ev, ctx->st_copy));
+                CU(cudaStreamWaitEvent(ctx->st, ev, 0));
+            }
+            const FrameDev* fr = ctx->d_frames.as<FrameDev>() + f0;
+            if (blur) {
+                const int rx0 = P.x0, rx1 = p.cols - p.bounding_box, ry0 = p.bounding_box, ry1 = p.rows - p.bounding_box;
+                if (rx1 > rx0 && ry1 > ry0) {
+                    const dim3 g(cdiv(rx1 - rx0, kBlurStrip), cdiv(ry1 - ry0, kBlurRows), nc);
+                    const size_t sm = blur_smem(p.blur_kernel, p.blur_mode);
+                    const BlurJob* bj = ctx->d_blurjobs.as<BlurJob>() + f0;
+                    if (p.blur_mode == O3R_BLUR_BILATERAL) {
+                        BilateralLut L;
+                        int rcl = bilateral_lut(ctx, p.blur_kernel, &L);
+                        if (rcl) return rcl;
+                        const dim3 gb(cdiv(rx1 - rx0, kBilTX), cdiv(ry1 - ry0, kBilTY), nc);
+                        LAUNCH(k_bilateral, gb, dim3(kBilTX, kBilTY), bilateral_smem(L.radius, L.maxk), bj, L, p.rows, p.cols, rx0, ry0, rx1, ry1);
+                    } else if (p.blur_mode == O3R_BLUR_MEDIAN)
+                        LAUNCH_N("k_blur_median", (k_blur<O3R_BLUR_MEDIAN>), g, kBlurRows, sm, bj, p.rows, p.cols, p.blur_kernel, rx0, ry0, rx1, ry1);
+                    else
+                        LAUNCH_N("k_blur_box", (k_blur<O3R_BLUR_BOX>), g, kBlurRows, sm, bj, p.rows, p.cols, p.blur_kernel, rx0, ry0, rx1, ry1);
+                }
+            }
+            int rc;
+            if (use_bucket) {   // hist -> scan -> scatter -> reduce: partial cells of the chunk, per-frame voxel counts
+                const int ci = f0 / chunk;
+                switch (disp_type) {
+                    case O3R_DISP_U8: rc = bk_run_chunk<O3R_DISP_U8>(ctx, P, bkp, ci, f0, nc, n, cap_chunk); break;
+                    case O3R_DISP_U16: rc = bk_run_chunk<O3R_DISP_U16>(ctx, P, bkp, ci, f0, nc, n, cap_chunk); break;
+                    case O3R_DISP_F32: rc = bk_run_chunk<O3R_DISP_F32>(ctx, P, bkp, ci, f0, nc, n, cap_chunk); break;
+                    default: rc = bk_run_chunk<O3R_DISP_F64>(ctx, P, bkp, ci, f0, nc, n, cap_chunk); break;
+                }
+                if (rc) return rc;
+                continue;
+            }
+            // stage A: V1 mode writes the chunk scratch; dont_downsample mode writes the batch buffer at the running base
+            float4* pts_out = ctx->pts.as<float4>();
+            const uint32_t* base_a = P.want_keys ? nullptr : cnt + CNT_BASE;
+            uint32_t* goff_a = P.want_keys ? nullptr : goff + f0;
+            switch (disp_type) {
+                case O3R_DISP_U8: rc = launch_stage_a<O3R_DISP_U8>(ctx, P, fr, nc, opt, pts_out, sb.k0, base_a, goff_a); break;
+                case O3R_DISP_U16: rc = launch_stage_a<O3R_DISP_U16>(ctx, P, fr, nc, opt, pts_out, sb.k0, base_a, goff_a); break;
+                case O3R_DISP_F32: rc = launch_stage_a<O3R_DISP_F32>(ctx, P, fr, nc, opt, pts_out, sb.k0, base_a, goff_a); break;
+                default: rc = launch_stage_a<O3R_DISP_F64>(ctx, P, fr, nc, opt, pts_out, sb.k0, base_a, goff_a); break;
+            }
             if (rc) return rc;
-            cudaEvent_t ev = ctx->chunk_event(f0 / chunk);
-            CU(cudaEventRecord(ev, ctx->st_copy));
-            CU(cudaStreamWaitEvent(ctx->st, ev, 0));
-        }
-        const FrameDev* fr = ctx->d_frames.as<FrameDev>() + f0;
-        if (blur) {
-            const int rx0 = P.x0, rx1 = p.cols - p.bounding_box, ry0 = p.bounding_box, ry1 = p.rows - p.bounding_box;
-            if (rx1 > rx0 && ry1 > ry0) {
-                const dim3 g(cdiv(rx1 - rx0, kBlurStrip), cdiv(ry1 - ry0, kBlurRows), nc);
-                const size_t sm = blur_smem(p.blur_kernel, p.blur_mode);
-                const BlurJob* bj = ctx->d_blurjobs.as<BlurJob>() + f0;
-                if (p.blur_mode == O3R_BLUR_BILATERAL) {
-                    BilateralLut L;
-                    int rcl = bilateral_lut(ctx, p.blur_kernel, &L);
-                    if (rcl) return rcl;
-                    const dim3 gb(cdiv(rx1 - rx0, kBilTX), cdiv(ry1 - ry0, kBilTY), nc);
-                    LAUNCH(k_bilateral, gb, dim3(kBilTX, kBilTY), bilateral_smem(L.radius, L.maxk), bj, L, p.rows, p.cols, rx0, ry0, rx1, ry1);
-                } else if (p.blur_mode == O3R_BLUR_MEDIAN)
-                    LAUNCH_N("k_blur_median", (k_blur<O3R_BLUR_MEDIAN>), g, kBlurRows, sm, bj, p.rows, p.cols, p.blur_kernel, rx0, ry0, rx1, ry1);
-                else
-                    LAUNCH_N("k_blur_box", (k_blur<O3R_BLUR_BOX>), g, kBlurRows, sm, bj, p.rows, p.cols, p.blur_kernel, rx0, ry0, rx1, ry1);
+            if (opt.mask_only) { ctx->busy_set = -1; return O3R_OK; }   // (single frame; the last batch's state is untouched)
+            const float4* vg_pts = ctx->pts.as<float4>();
+            const uint32_t* vg_off = ctx->frame_off.as<uint32_t>();
+            if (P.want_keys && p.sor_mean_k > 0 && J > 0) {
+                // StatisticalOutlierRemoval first (pose_functions.cpp:1673-1686); the VoxelGrid then sees the filtered cloud, so
+                // its bbox, grid and leaf indices are recomputed from the kept points
+                rc = sor_filter(ctx, sb, vg_pts, vg_off, nc, per_frame_cap, p.sor_mean_k, p.sor_stddev_mul);
+                if (rc) return rc;
+                vg_pts = ctx->sor_pts.as<float4>();
+                vg_off = ctx->sor_off.as<uint32_t>();
+                const uint32_t tl = std::max(1u, cdiv(per_frame_cap, kTileV));
+                LAUNCH(k_bbox_init, cdiv((size_t)nc * 6, kThreads), kThreads, 0, ctx->bbox.as<uint32_t>(), nc);
+                LAUNCH(k_bbox_pts, dim3(tl, nc), kThreads, 0, vg_pts, vg_off, 0, ctx->bbox.as<uint32_t>());
+                LAUNCH(k_grid_params, cdiv(nc, 64), 64, 0, nc, ctx->bbox.as<uint32_t>(), ctx->inv_f, ctx->inv_f, ctx->inv_f,
+                       ctx->grids.as<GridParams>());
+                LAUNCH(k_vg_key, dim3(std::min<uint32_t>(std::max(1u, cdiv(per_frame_cap, kThreads)), 148 * 4), nc), kThreads, 0, vg_pts,
+                       vg_off, ctx->grids.as<GridParams>(), 0, sb.k0);
+            }
+            if (P.want_keys) {  // per-frame VoxelGrid, leaf voxel_size / 5 (pose_functions.cpp:1698), appended at the base
+                rc = vg_sorted_reduce(ctx, sb, vg_pts, vg_off, nc, per_frame_cap,
+                                      ctx->grids.as<GridParams>(), ctx->inv_f, ctx->inv_f, ctx->inv_f, 0, 0,
+                                      ctx->vox.as<float4>(), goff + f0, nullptr, nullptr, !ctx->retain(), cnt + CNT_BASE);
+                if (rc) return rc;
+                if (ctx->tiled_now) {   // group the chunk's voxel centroids by combined-grid cell, tile by tile
+                    const uint32_t pt = cdiv(cap_chunk, kPrTile);
+                    uint32_t* stw = ctx->pr_status.as<uint32_t>();
+                    ZERO(stw, ((size_t)pt + 16) * 4);
+                    ZERO(cnt + CNT_PARTCHUNK, 4);
+                    LAUNCH(k_cell_prereduce, pt, kThreads, 0, ctx->vox.as<float4>(), cnt + CNT_BASE, cnt + CNT_VOX, ctx->inv_c,
+                           ctx->inv_cz, ctx->partials.as<o3r_cell>(), cnt + CNT_PART, cnt + CNT_PARTCHUNK, stw, stw + pt);
+                    LAUNCH(k_add_u32, 1, 32, 0, cnt + CNT_PART, cnt + CNT_PARTCHUNK);
+                }
+                LAUNCH(k_add_base, 1, 32, 0, cnt + CNT_BASE, cnt + CNT_VOX, goff + f0 + nc);
+            } else {
+                LAUNCH(k_add_base, 1, 32, 0, cnt + CNT_BASE, cnt + CNT_PTS, goff + f0 + nc);
             }
         }
-        // stage A: V1 mode writes the chunk scratch; dont_downsample mode writes the batch buffer at the running base
-        float4* pts_out = ctx->pts.as<float4>();
-        const uint32_t* base_a = P.want_keys ? nullptr : cnt + CNT_BASE;
-        uint32_t* goff_a = P.want_keys ? nullptr : goff + f0;
-        int rc;
-        switch (disp_type) {
-            case O3R_DISP_U8: rc = launch_stage_a<O3R_DISP_U8>(ctx, P, fr, nc, opt, pts_out, sb.k0, base_a, goff_a); break;
-            case O3R_DISP_U16: rc = launch_stage_a<O3R_DISP_U16>(ctx, P, fr, nc, opt, pts_out, sb.k0, base_a, goff_a); break;
-            case O3R_DISP_F32: rc = launch_stage_a<O3R_DISP_F32>(ctx, P, fr, nc, opt, pts_out, sb.k0, base_a, goff_a); break;
-            default: rc = launch_stage_a<O3R_DISP_F64>(ctx, P, fr, nc, opt, pts_out, sb.k0, base_a, goff_a); break;
-        }
-        if (rc) return rc;
-        if (opt.mask_only) return O3R_OK;   // (single frame)
-        const float4* vg_pts = ctx->pts.as<float4>();
-        const uint32_t* vg_off = ctx->frame_off.as<uint32_t>();
-        if (P.want_keys && p.sor_mean_k > 0 && J > 0) {
-            // StatisticalOutlierRemoval first (pose_functions.cpp:1673-1686); the VoxelGrid then sees the filtered cloud, so
-            // its bbox, grid and leaf indices are recomputed from the kept points
-            rc = sor_filter(ctx, sb, vg_pts, vg_off, nc, per_frame_cap, p.sor_mean_k, p.sor_stddev_mul);
-            if (rc) return rc;
-            vg_pts = ctx->sor_pts.as<float4>();
-            vg_off = ctx->sor_off.as<uint32_t>();
-            const uint32_t tl = std::max(1u, cdiv(per_frame_cap, kTileV));
-            LAUNCH(k_bbox_init, cdiv((size_t)nc * 6, kThreads), kThreads, 0, ctx->bbox.as<uint32_t>(), nc);
-            LAUNCH(k_bbox_pts, dim3(tl, nc), kThreads, 0, vg_pts, vg_off, 0, ctx->bbox.as<uint32_t>());
-            LAUNCH(k_grid_params, cdiv(nc, 64), 64, 0, nc, ctx->bbox.as<uint32_t>(), ctx->inv_f, ctx->inv_f, ctx->inv_f,
-                   ctx->grids.as<GridParams>());
-            LAUNCH(k_vg_key, dim3(std::min<uint32_t>(std::max(1u, cdiv(per_frame_cap, kThreads)), 148 * 4), nc), kThreads, 0, vg_pts,
-                   vg_off, ctx->grids.as<GridParams>(), 0, sb.k0);
-        }
-        if (P.want_keys) {  // per-frame VoxelGrid, leaf voxel_size / 5 (pose_functions.cpp:1698), appended at the base
-            rc = vg_sorted_reduce(ctx, sb, vg_pts, vg_off, nc, per_frame_cap,
-                                  ctx->grids.as<GridParams>(), ctx->inv_f, ctx->inv_f, ctx->inv_f, 0, 0,
-                                  ctx->vox.as<float4>(), goff + f0, nullptr, nullptr, !ctx->retain(), cnt + CNT_BASE);
-            if (rc) return rc;
-            if (ctx->tiled_now) {   // group the chunk's voxel centroids by combined-grid cell, tile by tile
-                const uint32_t pt = cdiv(cap_chunk, kPrTile);
-                uint32_t* stw = ctx->pr_status.as<uint32_t>();
-                ZERO(stw, ((size_t)pt + 16) * 4);
-                ZERO(cnt + CNT_PARTCHUNK, 4);
-                LAUNCH(k_cell_prereduce, pt, kThreads, 0, ctx->vox.as<float4>(), cnt + CNT_BASE, cnt + CNT_VOX, ctx->inv_c,
-                       ctx->inv_cz, ctx->partials.as<o3r_cell>(), cnt + CNT_PART, cnt + CNT_PARTCHUNK, stw, stw + pt);
-                LAUNCH(k_add_u32, 1, 32, 0, cnt + CNT_PART, cnt + CNT_PARTCHUNK);
-            }
-            LAUNCH(k_add_base, 1, 32, 0, cnt + CNT_BASE, cnt + CNT_VOX, goff + f0 + nc);
-        } else {
-            LAUNCH(k_add_base, 1, 32, 0, cnt + CNT_BASE, cnt + CNT_PTS, goff + f0 + nc);
-        }
-    }
 
-    // ---- per-frame output offsets (+ the combined-grid cell range) back to the host: the one sync of the frame path
-    if (ctx->h_offs_cap < (size_t)n + 1) {
-        if (ctx->h_offs) cudaFreeHost(ctx->h_offs);
-        ctx->h_offs_cap = std::max<size_t>(n + 1, 256);
-        CU(cudaMallocHost((void**)&ctx->h_offs, ctx->h_offs_cap * 4));
+        // ---- per-frame output offsets (+ the combined-grid cell range) back to the host: the one sync of the frame path
+        if (ctx->h_offs_cap < (size_t)n + 3) {
+            if (ctx->h_offs) cudaFreeHost(ctx->h_offs);
+            ctx->h_offs_cap = std::max<size_t>(n + 3, 256);
+            CU(cudaMallocHost((void**)&ctx->h_offs, ctx->h_offs_cap * 4));
+        }
+        if (use_bucket) {   // per-frame voxel COUNTS (h_offs[1..n]) and the two overflow flag words (h_offs[n+1..n+2])
+            const BkMisc M = bk_misc(ctx, n);
+            CU(cudaMemcpyAsync(ctx->h_offs + 1, M.fvox, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->st));
+            CU(cudaMemcpyAsync(ctx->h_offs + n + 1, M.flags, 8, cudaMemcpyDeviceToHost, ctx->st));
+        } else {
+            CU(cudaMemcpyAsync(ctx->h_offs, goff, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, ctx->st));
+        }
+        ctx->last_has_cellbb = ctx->last_is_vox && !ctx->retain();
+        if (ctx->last_has_cellbb)
+            CU(cudaMemcpyAsync(ctx->h_counters + CNT_CELLBB, cnt + CNT_CELLBB, 24, cudaMemcpyDeviceToHost, ctx->st));
+        // the kernels of this call are queued: now issue the copies of a recorded prefetch (next cycle's inputs).  The
+        // staging set they go to is not the one these kernels read.
+        if (ctx->deferred.pending && !opt.mask_only) {
+            int rcf = flush_deferred_prefetch(ctx);
+            if (rcf) return rcf;
+        }
+        ctx->last_has_partials = ctx->last_is_vox && ((ctx->tiled() && ctx->tiled_now) || use_bucket);
+        if (ctx->last_has_partials)
+            CU(cudaMemcpyAsync(ctx->h_counters + CNT_PART, cnt + CNT_PART, 4, cudaMemcpyDeviceToHost, ctx->st));
+        tr1 = now();
+        CU(cudaStreamSynchronize(ctx->st));
+        tr2 = now();
+        if (use_bucket) {
+            if (ctx->h_offs[n + 1] | ctx->h_offs[n + 2]) {   // a bucket too full / a point outside the grid bound: sort engine from now on
+                if (trace) fprintf(stderr, "[o3r trace] bucket engine overflow flags %u %u: falling back to the sort engine\n", ctx->h_offs[n + 1], ctx->h_offs[n + 2]);
+                ctx->bucket_off = true;
+                use_bucket = false;
+                inputs_resident = true;
+                continue;
+            }
+            ctx->h_offs[0] = 0;
+            for (int i = 0; i < n; ++i) ctx->h_offs[i + 1] += ctx->h_offs[i];
+        }
+        break;
     }
-    CU(cudaMemcpyAsync(ctx->h_offs, goff, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, ctx->st));
-    ctx->last_has_cellbb = ctx->last_is_vox && !ctx->retain();
-    if (ctx->last_has_cellbb)
-        CU(cudaMemcpyAsync(ctx->h_counters + CNT_CELLBB, cnt + CNT_CELLBB, 24, cudaMemcpyDeviceToHost, ctx->st));
-    // the kernels of this call are queued: now issue the copies of a recorded prefetch (next cycle's inputs).  The
-    // staging set they go to is not the one these kernels read.
-    if (ctx->deferred.pending && !opt.mask_only) {
-        int rcf = flush_deferred_prefetch(ctx);
-        if (rcf) return rcf;
-    }
-    ctx->last_has_partials = ctx->last_is_vox && ctx->tiled() && ctx->tiled_now;
-    if (ctx->last_has_partials)
-        CU(cudaMemcpyAsync(ctx->h_counters + CNT_PART, cnt + CNT_PART, 4, cudaMemcpyDeviceToHost, ctx->st));
-    const double tr1 = now();
-    CU(cudaStreamSynchronize(ctx->st));
+    ctx->last_bucketed = use_bucket;
     ctx->busy_set = -1;
     ctx->last_partials = ctx->last_has_partials ? ctx->h_counters[CNT_PART] : 0;
     // The tile pre-reduction pays only when it reduces: a 40-byte partial replaces a 16-byte voxel in the merge.  On grids
     // finer than the point spacing (e.g. 4K at voxel_size 0.01) nearly every voxel is its own cell: merge the voxels then.
-    if (ctx->last_has_partials) {
+    if (ctx->last_has_partials && !use_bucket) {
         ctx->tiled_poor = ctx->last_partials * 2 > ctx->h_offs[n];
         if (ctx->tiled_poor) { ctx->last_has_partials = false; ctx->last_partials = 0; }
     }
-    const double tr2 = now();
     if (ctx->last_has_cellbb) memcpy(ctx->last_cellbb, ctx->h_counters + CNT_CELLBB, 24);
     ctx->last_off.assign(ctx->h_offs, ctx->h_offs + n + 1);
     ctx->last_n = n;
@@ -447,6 +499,7 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
     const float4* outp = ctx->last_is_vox ? ctx->vox.as<float4>() : ctx->pts.as<float4>();
     if (ctx->retain()) return cloud_append_dev(ctx, outp, ctx->last_total);
     const int* bbp = ctx->last_has_cellbb ? ctx->last_cellbb : nullptr;
+    if (use_bucket && ctx->last_partials == 0) return O3R_OK;   // nothing valid in the whole batch
     const int rcm = ctx->last_has_partials ? acc_merge_cells(ctx, ctx->partials.as<o3r_cell>(), ctx->last_partials, bbp)
                                            : acc_merge_points(ctx, outp, ctx->last_total, bbp);
     if (trace) fprintf(stderr, "[o3r trace] frames_cloud: enqueue %.3f ms, sync wait %.3f ms, merge enqueue %.3f ms\n", tr1 - tr0, tr2 - tr1, now() - tr2);

@@ -102,6 +102,9 @@ int o3r_create(const o3r_params* params, o3r_ctx** out_ctx) {
             cudaFuncSetAttribute(k_emit<O3R_DISP_F64>, cudaFuncAttributePreferredSharedMemoryCarveout, cv_emit);
         }
     }
+    e = cudaFuncSetAttribute(k_bk_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_reduce_smem());
+    if (e != cudaSuccess) return bail(e, "smem attr");
+    if (const char* v = getenv("O3R_BK_CTAS")) ctx->bk_reduce_ctas = std::max(1, atoi(v));
     const int bs = (int)blur_smem(kBlurMaxK, O3R_BLUR_MEDIAN);
     cudaFuncSetAttribute(k_blur<O3R_BLUR_MEDIAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs);
     cudaFuncSetAttribute(k_blur<O3R_BLUR_BOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs);
@@ -125,7 +128,8 @@ void o3r_destroy(o3r_ctx* ctx) {
                       &ctx->plan_all, &ctx->plan_v2, &ctx->ghist, &ctx->head_cnt, &ctx->head_off, &ctx->vox,
                       &ctx->vox_off, &ctx->seg2, &ctx->tmat, &ctx->mask, &ctx->runwork, &ctx->spts, &ctx->res_keys[0], &ctx->res_keys[1],
                       &ctx->res_acc[0], &ctx->res_acc[1], &ctx->res_rgb[0], &ctx->res_rgb[1], &ctx->ckey, &ctx->cacc,
-                      &ctx->crgb, &ctx->partials, &ctx->pr_status, &ctx->sor_hard, &ctx->sor_pts, &ctx->sor_off, &ctx->sor_dist, &ctx->sor_grids,
+                      &ctx->crgb, &ctx->partials, &ctx->pr_status, &ctx->bk_frames, &ctx->bk_counts, &ctx->bk_nl, &ctx->bk_pts, &ctx->bk_pos,
+                      &ctx->bk_status, &ctx->bk_misc, &ctx->bk_stray, &ctx->sor_hard, &ctx->sor_pts, &ctx->sor_off, &ctx->sor_dist, &ctx->sor_grids,
                       &ctx->sor_pgrids, &ctx->sor_rows, &ctx->sor_thr, &ctx->sor_skeys, &ctx->sor_svals, &ctx->sor_cnt, &ctx->sor_cntoff, &ctx->new_cnt, &ctx->new_off, &ctx->new_keys, &ctx->okeys, &ctx->cloud};
     for (DevBuf* b : bufs) b->release();
     for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -144,6 +148,7 @@ void o3r_destroy(o3r_ctx* ctx) {
 
 uint64_t o3r_launch_count(const o3r_ctx* ctx) { return ctx ? ctx->launches : 0; }
 size_t o3r_last_batch_partials(const o3r_ctx* ctx) { return (ctx && ctx->last_has_partials) ? ctx->last_partials : 0; }
+int o3r_last_batch_engine(const o3r_ctx* ctx) { return (ctx && ctx->last_bucketed) ? 1 : 0; }
 void* o3r_stream(o3r_ctx* ctx) { return ctx ? (void*)ctx->st : nullptr; }
 
 int o3r_sync(o3r_ctx* ctx) {
@@ -185,6 +190,12 @@ int o3r_profile_read(o3r_ctx* ctx, char* buf, size_t cap) {
     }
     if (out.size() + 1 > cap) return ctx->fail(O3R_ERR_CAPACITY, "profile buffer too small");
     memcpy(buf, out.c_str(), out.size() + 1);
+    return O3R_OK;
+}
+
+int o3r_set_keep_frame_voxels(o3r_ctx* ctx, int keep) {
+    if (!ctx) return O3R_ERR_INVALID;
+    ctx->keep_frame_voxels = keep != 0;
     return O3R_OK;
 }
 
@@ -233,6 +244,18 @@ int o3r_frames_prefetch(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_t
     return O3R_OK;
 }
 
+int o3r_frames_prefetch_cancel(o3r_ctx* ctx) {
+    if (!ctx) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    ctx->deferred.pending = false;           // recorded but not issued: nothing will ever read those buffers
+    ctx->deferred.frames.clear();
+    CU(cudaStreamSynchronize(ctx->st_copy2));   // copies already in flight finish reading the host buffers here
+    CU(cudaStreamSynchronize(ctx->st_copy));
+    for (auto& pf : ctx->prefetch) pf.valid = false;
+    return O3R_OK;
+}
+
 int o3r_frame_cloud(o3r_ctx* ctx, const o3r_frame* frame, int disp_type, o3r_point* out, size_t cap, size_t* n_out) {
     if (!ctx || !frame) return O3R_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -268,6 +291,8 @@ int o3r_last_batch_points(o3r_ctx* ctx, o3r_point* out, size_t cap, size_t* n_ou
     if (!ctx) return O3R_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->p.device));
+    if (ctx->last_bucketed && !ctx->keep_frame_voxels)
+        return ctx->fail(O3R_ERR_UNSUPPORTED, "O3R_MERGE_ACCUMULATE_FUSED does not materialise the per-frame clouds (see o3r_set_keep_frame_voxels)");
     const float4* src = ctx->last_is_vox ? ctx->vox.as<float4>() : ctx->pts.as<float4>();
     return copy_out(ctx, src, ctx->last_total, out, cap, n_out);
 }
@@ -295,13 +320,14 @@ int o3r_cloud_append(o3r_ctx* ctx, const o3r_point* pts, size_t n) {
     if (ctx->retain()) {
         CU(ctx->cloud.ensure((ctx->n_cloud + n) * 16, ctx->st, ctx->n_cloud * 16));
         CU(cudaMemcpyAsync(ctx->cloud.as<float4>() + ctx->n_cloud, pts, n * 16, cudaMemcpyHostToDevice, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));   // the caller may reuse or free `pts` as soon as this returns
         ctx->n_cloud += n;
         return O3R_OK;
     }
     CU(ctx->vox.ensure(n * 16));
     CU(cudaMemcpyAsync(ctx->vox.p, pts, n * 16, cudaMemcpyHostToDevice, ctx->st));
     ctx->last_n = 0; ctx->last_total = 0; ctx->last_has_cellbb = false;   // the batch buffer was overwritten
-    ctx->last_has_partials = false; ctx->last_partials = 0;
+    ctx->last_has_partials = false; ctx->last_partials = 0; ctx->last_bucketed = false;
     return acc_merge_points(ctx, ctx->vox.as<float4>(), n, nullptr);
 }
 

@@ -13,11 +13,11 @@ SO_PATH = os.path.join(_HERE, "libo3r.so")
 #: every symbol include/o3r.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "o3r_create", "o3r_destroy", "o3r_last_error", "o3r_version", "o3r_host_alloc", "o3r_host_free",
-    "o3r_frame_cloud", "o3r_frames_cloud", "o3r_frames_cloud_dev", "o3r_frames_prefetch", "o3r_last_batch_points",
+    "o3r_frame_cloud", "o3r_frames_cloud", "o3r_frames_cloud_dev", "o3r_frames_prefetch", "o3r_frames_prefetch_cancel", "o3r_last_batch_points",
     "o3r_cloud_transform", "o3r_cloud_append", "o3r_cloud_downsample", "o3r_cloud_downsample_dev", "o3r_cloud_size",
     "o3r_cloud_clear",
     "o3r_voxel_grid", "o3r_blur_u8", "o3r_frame_mask", "o3r_disp_variance", "o3r_plane_fit", "o3r_sor", "o3r_last_batch_partials", "o3r_exchange_bound", "o3r_exchange_pack_dev", "o3r_exchange_merge_bb",
-    "o3r_exchange_pack", "o3r_exchange_merge", "o3r_set_defer_merge",
+    "o3r_exchange_pack", "o3r_exchange_merge", "o3r_set_defer_merge", "o3r_set_keep_frame_voxels", "o3r_last_batch_engine",
     "o3r_launch_count", "o3r_stream", "o3r_sync", "o3r_profile", "o3r_profile_read",
 ]
 
@@ -55,6 +55,7 @@ def load():
     L.o3r_frames_cloud.argtypes = [vp, F, C.c_int, C.c_int, vp]
     L.o3r_frames_cloud_dev.argtypes = [vp, F, C.c_int, C.c_int, vp]
     L.o3r_frames_prefetch.argtypes = [vp, F, C.c_int, C.c_int]
+    L.o3r_frames_prefetch_cancel.argtypes = [vp]
     L.o3r_last_batch_points.argtypes = [vp, vp, sz, szp]
     L.o3r_cloud_transform.argtypes = [vp, C.POINTER(C.c_float)]
     L.o3r_cloud_append.argtypes = [vp, vp, sz]
@@ -78,6 +79,8 @@ def load():
     L.o3r_exchange_pack_dev.argtypes = [vp, C.c_int, vp, sz, vp]
     L.o3r_exchange_merge_bb.argtypes = [vp, vp, sz, C.POINTER(C.c_int)]
     L.o3r_set_defer_merge.argtypes = [vp, C.c_int]
+    L.o3r_set_keep_frame_voxels.argtypes = [vp, C.c_int]
+    L.o3r_last_batch_engine.argtypes = [vp]
     L.o3r_launch_count.argtypes = [vp]
     L.o3r_launch_count.restype = C.c_uint64
     L.o3r_stream.argtypes = [vp]

@@ -119,12 +119,25 @@ class Pose:
         self._check(self._L.o3r_frames_prefetch(self._h, arr, n, disp_type))
         return arr
 
+    def cancelPrefetch(self):
+        """Drops announced prefetches; afterwards the library no longer references their host buffers."""
+        self._check(self._L.o3r_frames_prefetch_cancel(self._h))
+
     def lastCyclePoints(self):
         n = C.c_size_t(0)
         self._check(self._L.o3r_last_batch_points(self._h, None, 0, C.byref(n)))
         out = np.empty(max(1, n.value), dtype=abi.POINT)
         self._check(self._L.o3r_last_batch_points(self._h, out.ctypes.data, out.size, C.byref(n)))
         return out[:n.value]
+
+    def lastCycleEngine(self):
+        """1 when the last cycle ran through the fused bucket engine, 0 for the sort engine."""
+        return int(self._L.o3r_last_batch_engine(self._h))
+
+    def setKeepFrameVoxels(self, keep):
+        """Parity probe of MERGE_ACCUMULATE_FUSED: lastCyclePoints() then returns the per-frame voxel centroids of the
+        cycle as a multiset (no particular order)."""
+        self._check(self._L.o3r_set_keep_frame_voxels(self._h, int(keep)))
 
     # -- global cloud ------------------------------------------------------------------------------------
     def transformPtCloud(self, T):
