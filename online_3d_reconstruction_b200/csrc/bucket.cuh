@@ -40,7 +40,7 @@ namespace o3r {
 
 constexpr int kBkB = 5;                            // bucket edge in leaf cells (= voxel_size / leaf)
 constexpr int kBkSub = kBkB * kBkB;                // leaf columns per bucket (<= 32: one lane per column in the scan)
-constexpr int kBkCap = 256;                        // points per bucket the reduce ranks in shared memory (fast path)
+constexpr int kBkCap = 128;                        // points the reduce ranks in shared memory at once (a bucket, or one leaf column of a big one)
 constexpr int kBkCapSlow = 65535;                  // larger buckets (parallax overlaps) are ranked one leaf column at a time; a column holds <= kBkCap
 constexpr int kBkRounds = kBkCap / 32;
 constexpr int kBkPerWarp = 4;                      // buckets a warp takes per ticket
@@ -48,7 +48,7 @@ constexpr int kBkMaxPart = 8;                      // partial cells per bucket
 constexpr int kBkScanItems = 8;
 constexpr int kBkScanTile = kThreads * kBkScanItems;
 #ifndef O3R_BK_MINB
-#define O3R_BK_MINB 3
+#define O3R_BK_MINB 4
 #endif
 constexpr int kBkKBits = 26;                       // (z cell - k0) must fit: (2^26 * 25) < 2^32
 
@@ -159,10 +159,12 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
 }
 constexpr unsigned long long kBk64Local = 1ull << 62, kBk64Global = 2ull << 62, kBk64Mask = (1ull << 62) - 1ull;
 
-// counts[g] becomes the bucket's first slot (the scatter's cursor); nl[r] = {first slot, points | frame << 16} of the
-// r-th non-empty bucket; totals = {points, non-empty buckets}
+// counts[g] becomes the bucket's first slot (the scatter's cursor); nl[r] = {first slot, points | frame << 16 | pass-through
+// << 31, I, J} of the r-th non-empty bucket ((I, J) = the bucket's position in units of kBkB leaf cells = its nominal cell on
+// the combined grid); totals = {points, non-empty buckets}
 __global__ void __launch_bounds__(kThreads) k_bk_scan(uint32_t* __restrict__ counts, uint32_t nb_total,
-                                                      const BkFrame* __restrict__ bk, int n_frames, uint2* __restrict__ nl,
+                                                      const BkFrame* __restrict__ bk, const uint8_t* __restrict__ frame_pass,
+                                                      int n_frames, uint4* __restrict__ nl,
                                                       unsigned long long* __restrict__ status, uint32_t* __restrict__ ticket,
                                                       uint32_t* __restrict__ totals, uint32_t* __restrict__ flags) {
     __shared__ unsigned long long s_w[kWarps + 2];
@@ -256,7 +258,11 @@ __global__ void __launch_bounds__(kThreads) k_bk_scan(uint32_t* __restrict__ cou
         o[q] = start;
         if (g < nb_total && c[q]) {
             while (g >= next_base) { ++f; next_base = (f + 1 < n_frames) ? bk[f + 1].base : 0xffffffffu; }
-            nl[rank++] = make_uint2(start, min(c[q], 0xffffu) | ((uint32_t)f << 16));
+            const BkFrame Bf = bk[f];
+            const uint32_t lg = g - Bf.base;
+            const int nI = Bf.i0c / kBkB + (int)(lg % (uint32_t)Bf.ni), nJ = Bf.j0c / kBkB + (int)(lg / (uint32_t)Bf.ni);
+            nl[rank++] = make_uint4(start, min(c[q], 0xffffu) | ((uint32_t)f << 16) | (frame_pass[f] ? 0x80000000u : 0u),
+                                    (uint32_t)nI, (uint32_t)nJ);
             start += c[q];
         }
     }
@@ -270,52 +276,68 @@ __global__ void __launch_bounds__(kThreads) k_bk_scan(uint32_t* __restrict__ cou
     }
 }
 
-// Exclusive MAX scan of one value per thread over the CTA (identity 0).  `sm` is kWarps + 1 words; ends with a barrier.
-__device__ __forceinline__ uint32_t block_excl_max_scan(uint32_t v, uint32_t* sm) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(kFull, inc, o);
-        if (lane >= o) inc = max(inc, t);
-    }
-    if (lane == 31) sm[warp] = inc;
-    __syncthreads();
-    uint32_t before = 0;   // max over the warps in front of this one
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w)
-        if (w < warp) before = max(before, sm[w]);
-    uint32_t prev = __shfl_up_sync(kFull, inc, 1);
-    if (lane == 0) prev = 0;
-    __syncthreads();
-    return max(before, prev);
+// ordering key of a point inside its bucket: leaf (z cell, column) — or the column alone in a pass-through frame, where
+// every point is its own voxel — then the scan position.  (i, j, k) = the point's leaf cell.
+__device__ __forceinline__ unsigned long long bk_key64(const BkFrame& B, bool pass, int ci, int cj, int ck, uint32_t ps,
+                                                       uint32_t& col) {
+    const int bi = ci - B.i0c, bj = cj - B.j0c;
+    col = (uint32_t)(bi - (bi / kBkB) * kBkB) + (uint32_t)(bj - (bj / kBkB) * kBkB) * kBkB;
+    const uint32_t k32 = pass ? col : (uint32_t)(ck - B.k0) * kBkSub + col;
+    return ((unsigned long long)k32 << 32) | ps;
+}
+__device__ __forceinline__ uint32_t bk_key_col(unsigned long long key, bool pass) {
+    const uint32_t k32 = (uint32_t)(key >> 32);
+    return pass ? k32 : k32 % (uint32_t)kBkSub;
 }
 
+// Shared-memory staging of a warp's 128 samples: a lane writes its (up to) four consecutive records, later lane t reads
+// record 32 k + t.  Position p of an array of 16- / 8- / 4-byte records lives at p ^ swizzle(p), which spreads the
+// writers' 64- / 32- / 16-byte strides over all banks and keeps the readers' consecutive positions conflict-free.
+__device__ __forceinline__ uint32_t swz16(uint32_t p) { return p ^ ((p >> 3) & 3u); }
+__device__ __forceinline__ uint32_t swz8(uint32_t p) { return p ^ ((p >> 4) & 3u); }
+__device__ __forceinline__ uint32_t swz4(uint32_t p) { return p ^ ((p >> 5) & 3u); }
+
 // ---- pass 2: evaluate again, colour, bin into the buckets ---------------------------------------------------------------
-// pos_out = the point's position in the frame's scan order (keypoints, then the row-major grid): the order PCL's stable
-// grouping (the oracle's) adds the points of a leaf in.
+// Every warp works on its 128 consecutive samples alone (no CTA barrier after the table load): compaction by warp prefix,
+// staging in the warp's slice of shared memory, one atomic per run of consecutive points of one bucket (issued by the run's
+// last point), coalesced copy-out of {x, y, z, rgb} (16 B) + ordering key (8 B: leaf key | scan position).
+// The scan position (keypoints, then the row-major grid) is the order PCL's stable grouping (the oracle's) adds the points
+// of a leaf in.
+constexpr int kBkWarpItems = 128;
+struct BkScatterWarp {
+    float4 pts[kBkWarpItems];
+    unsigned long long key[kBkWarpItems];
+    uint32_t bkt[kBkWarpItems];    // bucket of the staged point, then its destination slot
+    uint32_t base[kBkWarpItems];   // by run head position: first slot of the run
+};
 template <int DT>
 __global__ void __launch_bounds__(kThreads) k_bk_scatter(AParams P, const FrameDev* __restrict__ frames,
-                                                         const BkFrame* __restrict__ bk, float inv_f,
-                                                         uint32_t* __restrict__ cursor, float4* __restrict__ pts,
-                                                         uint32_t* __restrict__ pos_out, const uint32_t* __restrict__ flags) {
+                                                         const BkFrame* __restrict__ bk, const uint8_t* __restrict__ frame_pass,
+                                                         float inv_f, uint32_t* __restrict__ cursor, float4* __restrict__ pts,
+                                                         unsigned long long* __restrict__ keys_out,
+                                                         const uint32_t* __restrict__ flags) {
     __shared__ double rl[256];
     __shared__ float zl[256];
-    __shared__ uint32_t s_scan[34];
-    __shared__ __align__(16) float4 s_pts[kTileA];
-    __shared__ uint32_t s_pos[kTileA];
-    __shared__ __align__(16) uint32_t s_bkt[kTileA + 4];   // bucket of the staged point, then its destination slot
-    __shared__ uint32_t s_base[kTileA];                    // by run head position: first slot of the run
+    __shared__ __align__(16) BkScatterWarp s_w[kWarps];
     if (*flags) return;   // the histogram already overflowed: the host reruns the batch through the sort engine
-    const int tile = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    const int tile = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const unsigned lt = (1u << lane) - 1u;
     const FrameDev& F = frames[f];
     const BkFrame B = bk[f];
+    const bool pass = frame_pass[f] != 0;
+    BkScatterWarp& W = s_w[tid >> 5];
     load_lut(P, rl, zl);
     Samp S;
     eval4<DT>(P, F, rl, zl, tile, S);
-    uint32_t total;
-    const uint32_t off = block_excl_scan((uint32_t)__popc(S.mask), s_scan, total);
-    if (total == 0) return;
+    const uint32_t nv = (uint32_t)__popc(S.mask);
+    uint32_t inc = nv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += t;
+    }
+    const uint32_t total = __shfl_sync(kFull, inc, 31);
+    if (total == 0) return;   // (warp-uniform)
     if (S.mask) {
         uint32_t rgb[4];
         if (S.vec_row) {
@@ -336,7 +358,7 @@ __global__ void __launch_bounds__(kThreads) k_bk_scatter(AParams P, const FrameD
         // scan position: keypoint index, or n_kp + grid sample index
         const uint32_t p0 = tile < P.kp_tiles ? (uint32_t)tile * kTileA + tid * 4
                                               : (uint32_t)F.n_kp + (uint32_t)(tile - P.kp_tiles) * kTileA + tid * 4;
-        uint32_t o = off;
+        uint32_t o = inc - nv;
         bool bad = false;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -345,26 +367,34 @@ __global__ void __launch_bounds__(kThreads) k_bk_scatter(AParams P, const FrameD
                 xform(F.T, S.x[j], S.y[j], S.z[j], tx, ty, tz);
                 int ci, cj, ck;
                 bk_cell(tx, ty, tz, inv_f, ci, cj, ck);
-                s_pts[o] = make_float4(tx, ty, tz, __uint_as_float(rgb[j]));
-                s_pos[o] = p0 + j;
-                s_bkt[o] = bk_index(B, ci, cj, ck, bad);
+                uint32_t col;
+                W.pts[swz16(o)] = make_float4(tx, ty, tz, __uint_as_float(rgb[j]));
+                W.key[swz8(o)] = bk_key64(B, pass, ci, cj, ck, p0 + j, col);
+                W.bkt[swz4(o)] = bk_index(B, ci, cj, ck, bad);
                 ++o;
             }
     }
-    __syncthreads();
+    __syncwarp();
     // ---- runs of consecutive staged points of one bucket: the run's last point reserves the slots
-    const uint32_t e0 = tid * 4;
+    const uint32_t e0 = lane * 4;
     uint32_t b[6];   // b[1 + j] = bucket of staged point e0 + j; b[0] / b[5] = the neighbours
 #pragma unroll
     for (int j = -1; j <= 4; ++j) {
-        const uint32_t e = e0 + j;   // (wraps for e0 == 0, j == -1: caught by e < total being false for 0xffffffff)
-        b[j + 1] = e < total ? s_bkt[e] : 0xffffffffu;
+        const uint32_t e = e0 + j;   // (wraps for e0 == 0, j == -1: e < total is then false)
+        b[j + 1] = e < total ? W.bkt[swz4(e)] : 0xffffffffu;
     }
     uint32_t lh = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
         if (e0 + j < total && b[j + 1] != b[j]) lh = e0 + j;
-    uint32_t L = block_excl_max_scan(lh, s_scan);   // head of the run that is open when this thread's points begin
+    uint32_t L = lh;   // head of the run that is open when this lane's points begin: exclusive max scan over the lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, L, o);
+        if (lane >= o) L = max(L, t);
+    }
+    L = __shfl_up_sync(kFull, L, 1);
+    if (lane == 0) L = 0;
     uint32_t hp[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -373,352 +403,99 @@ __global__ void __launch_bounds__(kThreads) k_bk_scatter(AParams P, const FrameD
         if (e < total) {
             if (b[j + 1] != b[j]) L = e;
             hp[j] = L;
-            if (b[j + 2] != b[j + 1]) s_base[L] = atomicAdd(&cursor[b[j + 1]], e - L + 1u);
+            if (b[j + 2] != b[j + 1]) W.base[L] = atomicAdd(&cursor[b[j + 1]], e - L + 1u);
         }
     }
-    __syncthreads();
+    __syncwarp();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const uint32_t e = e0 + j;
-        if (e < total) s_bkt[e] = s_base[hp[j]] + (e - hp[j]);
+        if (e < total) W.bkt[swz4(e)] = W.base[hp[j]] + (e - hp[j]);
     }
-    __syncthreads();
-    for (uint32_t i = tid; i < total; i += kThreads) {
-        const uint32_t g = s_bkt[i];
-        pts[g] = s_pts[i];
-        pos_out[g] = s_pos[i];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t t = k * 32 + lane;
+        if (t < total) {
+            const uint32_t g = W.bkt[swz4(t)];
+            pts[g] = W.pts[swz16(t)];
+            keys_out[g] = W.key[swz8(t)];
+        }
     }
+    (void)lt;
 }
 
-// ---- pass 3: one warp per bucket ---------------------------------------------------------------------------------------
-// Warps are independent (no CTA barrier, no ordering between buckets): the r-th non-empty bucket writes its main partial cell
-// to slot r of the chunk's partial list; the rare stray centroids (see below) are appended behind the main slots by an
-// atomic counter and put into a canonical order afterwards (k_bk_strays), so the list is reproducible.
-struct BkWarp {
-    float4 pts[kBkCap];                       // the points being ranked, load order
-    union {
-        unsigned long long bkeys[kBkCap];     // (leaf key << 32 | scan position) in column order
-        struct { uint32_t key[kBkCap]; uint8_t idx[kBkCap]; } s;   // the same in final order: leaf key, index into pts
-        uint32_t ppos[kBkCap];                // big buckets: scan positions of the staged column (dead once the keys are formed)
-    } u;
-    o3r_cell stray[kBkMaxPart];               // centroids that fell into a neighbour of the nominal combined cell
-    uint16_t bin[36];                         // per column: count, then first position
+// ---- pass 3: buckets -> per-frame voxel centroids -> one partial sum per combined-grid cell ------------------------------
+// A CTA takes kRdG consecutive non-empty buckets (~1000 points) per ticket and works on all of them at once, one THREAD per
+// point in every phase:
+//   load      point + ordering key into shared memory; bin = (bucket, leaf column); one shared-memory atomic per point numbers
+//             it inside its bin (the arrival order is arbitrary: the rank below orders)
+//   scan      first position of every bin
+//   rank      each point counts the keys of its bin (3 points on average) that precede its own (leaf key, scan position):
+//             final position = PCL's order (column, z cell, scan position) inside the bucket
+//   fold      each run head left-folds its leaf in scan order (bit-identical centroid: the oracle's stable order), cells the
+//             centroid on the combined grid and leaves it in shared memory
+//   sum       one warp per bucket adds the centroids that fell into the bucket's nominal combined cell — lanes in position
+//             order, then an xor butterfly: a fixed tree — and writes the partial cell to slot r of the chunk's list
+// Centroids that land in a neighbour of the nominal cell (they sit on its border to the last float bit: a couple per frame) are
+// "strays": single-centroid records appended behind the main slots through an atomic counter and put into a canonical order
+// afterwards (k_bk_strays), so the partial list is reproducible.
+constexpr int kRdG = 12;                          // buckets per ticket
+constexpr int kRdItems = 5;                       // points per thread
+constexpr int kRdCap = kThreads * kRdItems;       // points a CTA holds at once
+constexpr int kRdBins = kRdG * kBkSub;
+constexpr int kRdStray = 4;                       // strays per bucket kept in shared memory
+
+struct RdSmem {
+    float4 pts[kRdCap];                    // load order; a run head's slot is overwritten by its centroid (z + 500)
+    unsigned long long skey[kRdCap];       // bin order: (leaf key << 32 | scan position)
+    uint32_t fkey[kRdCap];                 // final order: leaf key
+    uint16_t sidx[kRdCap];                 // bin order: load index
+    uint16_t fidx[kRdCap];                 // final order: load index | 0x8000 head in the nominal cell | 0x4000 stray head
+    uint32_t bin[kRdBins + 4];             // per bin: count, then first position ([n_bins] = total)
+    uint32_t startbits[kRdCap / 32 + 1];   // bit p: position p starts a bin
+    uint4 ent[kRdG];
+    uint32_t bstart[kRdG + 1];             // first point of each bucket, relative to the sub-batch
+    int kz[kRdG];                          // z cell of the nominal combined cell
+    o3r_cell stray[kRdG][kRdStray];
+    uint32_t nstray[kRdG];
+    uint32_t scan[34];
+    uint32_t ticket;
+    int bb[6];
 };
-constexpr size_t bk_reduce_smem() { return sizeof(BkWarp) * kWarps; }
+constexpr size_t bk_reduce_smem() { return sizeof(RdSmem); }
 
-// ordering key of a point inside its bucket: leaf (z cell, column) — or the column alone in a pass-through frame, where
-// every point is its own voxel — then the scan position
-__device__ __forceinline__ unsigned long long bk_key64(const BkFrame& B, bool pass, float inv_f, const float4& p, uint32_t ps,
-                                                       uint32_t& col) {
-    int ci, cj, ck;
-    bk_cell(p.x, p.y, p.z, inv_f, ci, cj, ck);
-    const int bi = ci - B.i0c, bj = cj - B.j0c;
-    col = (uint32_t)(bi - (bi / kBkB) * kBkB) + (uint32_t)(bj - (bj / kBkB) * kBkB) * kBkB;
-    const uint32_t k32 = pass ? col : (uint32_t)(ck - B.k0) * kBkSub + col;
-    return ((unsigned long long)k32 << 32) | ps;
+// x / n for a small positive integer n, bit-identical to IEEE division (what pcl::CentroidPoint's `/ n` compiles to): with
+// r = RN(1 / n), q = RN(x r), the residual x - n q is exact in an FMA and one correction step lands on RN(x / n) (Markstein);
+// the guard sends anything near the ends of the exponent range, and large n, to the generic division.
+__device__ __forceinline__ float bk_div_small(float x, float fn, float r) {
+    const float q = __fmul_rn(x, r);
+    const float e = __fmaf_rn(-fn, q, x);
+    return __fmaf_rn(e, r, q);
 }
-
-// V1 centroid of pcl::CentroidPoint<PointXYZRGB> (float sums / (float)n; colour uint32(sum / n))
+// pcl::CentroidPoint<PointXYZRGB>: float sums / (float)n; colour uint32(float sum / n) = integer division for these ranges
 __device__ __forceinline__ float4 bk_centroid(float sx, float sy, float sz, uint32_t n, uint32_t r, uint32_t g, uint32_t b) {
     const float fn = (float)n;
-    const uint32_t rgb = ((uint32_t)__fdiv_rn((float)r, fn) << 16) | ((uint32_t)__fdiv_rn((float)g, fn) << 8) |
-                         (uint32_t)__fdiv_rn((float)b, fn);
-    return make_float4(__fdiv_rn(sx, fn), __fdiv_rn(sy, fn), __fdiv_rn(sz, fn), __uint_as_float(rgb));
+    float cx, cy, cz;
+    uint32_t rgb;
+    const float lim_lo = 1e-30f, lim_hi = 1e30f;
+    const float ax = fabsf(sx), ay = fabsf(sy), az = fabsf(sz);
+    const bool fast = n <= 1024u && (ax == 0.f || (ax > lim_lo && ax < lim_hi)) && (ay == 0.f || (ay > lim_lo && ay < lim_hi)) &&
+                      (az == 0.f || (az > lim_lo && az < lim_hi));
+    if (fast) {
+        const float rc = __frcp_rn(fn);
+        cx = bk_div_small(sx, fn, rc); cy = bk_div_small(sy, fn, rc); cz = bk_div_small(sz, fn, rc);
+        // channel sums s <= 255 n are integers: uint32((float)s / fn) == floor(s / n), and s * rc + rc / 2 lies within 1e-4 of
+        // s / n + 1 / (2 n), whose floor is the same integer (n <= 1024)
+        const float h = __fmul_rn(0.5f, rc);
+        rgb = ((uint32_t)__fmaf_rn((float)r, rc, h) << 16) | ((uint32_t)__fmaf_rn((float)g, rc, h) << 8) | (uint32_t)__fmaf_rn((float)b, rc, h);
+    } else {
+        cx = __fdiv_rn(sx, fn); cy = __fdiv_rn(sy, fn); cz = __fdiv_rn(sz, fn);
+        rgb = ((uint32_t)__fdiv_rn((float)r, fn) << 16) | ((uint32_t)__fdiv_rn((float)g, fn) << 8) | (uint32_t)__fdiv_rn((float)b, fn);
+    }
+    return make_float4(cx, cy, cz, __uint_as_float(rgb));
 }
 
-// running state of one bucket across the passes of bk_pass
-struct BkAcc {
-    unsigned long long K0;    // nominal combined cell (x, y fields) + the first centroid's z cell
-    float ax, ay, az;         // per lane: the lane's centroids of cell K0, added in leaf order
-    uint32_t an, ar, ag, ab;
-    uint32_t nvox, nstray;    // warp-uniform
-    int have_k0;
-};
-
-// Ranks the m (<= kBkCap) points src_pts[0..m) / src_pos[0..m) — a whole bucket, or one leaf column of a big bucket —
-// into PCL's order (column, z cell, scan position), left-folds every leaf in scan order, cells each centroid on the
-// combined grid and adds it to the bucket's partial sums.  STAGED: the points already sit in W.pts (src_pts == W.pts).
-template <bool STAGED>
-__device__ __forceinline__ void bk_pass(BkWarp& W, const float4* __restrict__ src_pts, const uint32_t* __restrict__ src_pos,
-                                        uint32_t m, const BkFrame& B, bool pass, float inv_f, float icx, float icz, BkAcc& A,
-                                        int* cmn, int* cmx, float4* __restrict__ dbg_vox, uint32_t* __restrict__ dbg_cnt) {
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    const int R = (int)((m + 31u) >> 5);
-    W.bin[lane] = 0;
-    if (lane < 4) W.bin[32 + lane] = 0;
-    __syncwarp();
-    // ---- load; counting sort by leaf column (stable in load order, which is arbitrary — the rank below orders)
-    unsigned long long key64[kBkRounds];
-    uint32_t sb[kBkRounds];   // column | slot inside the column << 8, later the final position
-#pragma unroll
-    for (int rr = 0; rr < kBkRounds; ++rr) {
-        if (rr >= R) break;
-        const uint32_t e = rr * 32 + lane;
-        const bool valid = e < m;
-        const unsigned vm = __ballot_sync(kFull, valid);
-        if (valid) {
-            float4 p;
-            uint32_t ps;
-            if (STAGED) { p = W.pts[e]; ps = W.u.ppos[e]; }
-            else { p = __ldcs(src_pts + e); ps = __ldcs(src_pos + e); W.pts[e] = p; }
-            uint32_t s;
-            key64[rr] = bk_key64(B, pass, inv_f, p, ps, s);
-            const unsigned peers = __match_any_sync(vm, s);
-            const uint32_t old = W.bin[s];
-            __syncwarp(vm);
-            if ((peers & lt) == 0u) W.bin[s] = (uint16_t)(old + __popc(peers));
-            __syncwarp(vm);
-            sb[rr] = s | ((old + __popc(peers & lt)) << 8);
-        }
-    }
-    __syncwarp();
-    {   // first position of every column
-        const uint32_t cv = W.bin[lane];
-        uint32_t inc = cv;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(kFull, inc, o);
-            if (lane >= o) inc += v;
-        }
-        __syncwarp();
-        W.bin[lane] = (uint16_t)(inc - cv);
-        if (lane == 31) W.bin[32] = (uint16_t)inc;
-    }
-    __syncwarp();   // (STAGED: every lane has read its scan positions, which the keys now overwrite)
-#pragma unroll
-    for (int rr = 0; rr < kBkRounds; ++rr) {
-        if (rr >= R) break;
-        if ((uint32_t)(rr * 32 + lane) < m) W.u.bkeys[(uint32_t)W.bin[sb[rr] & 255u] + (sb[rr] >> 8)] = key64[rr];
-    }
-    __syncwarp();
-    // ---- rank inside the column by (leaf key, scan position): final position = PCL's order inside the bucket
-#pragma unroll
-    for (int rr = 0; rr < kBkRounds; ++rr) {
-        if (rr >= R) break;
-        if ((uint32_t)(rr * 32 + lane) < m) {
-            const uint32_t s = sb[rr] & 255u;
-            const uint32_t a = W.bin[s], e = W.bin[s + 1];
-            uint32_t rk = 0;
-            for (uint32_t i = a; i < e; ++i) rk += W.u.bkeys[i] < key64[rr] ? 1u : 0u;
-            sb[rr] = a + rk;
-        }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int rr = 0; rr < kBkRounds; ++rr) {
-        if (rr >= R) break;
-        if ((uint32_t)(rr * 32 + lane) < m) {
-            W.u.s.key[sb[rr]] = (uint32_t)(key64[rr] >> 32);
-            W.u.s.idx[sb[rr]] = (uint8_t)(rr * 32 + lane);
-        }
-    }
-    __syncwarp();
-    // ---- leaves: left fold in scan order; combined-grid cell of every centroid; the bucket's partial sums
-#pragma unroll 1
-    for (int rr = 0; rr < R; ++rr) {
-        const uint32_t fp = rr * 32 + lane;
-        bool head = false;
-        uint32_t k32 = 0;
-        if (fp < m) {
-            k32 = W.u.s.key[fp];
-            head = pass || fp == 0 || W.u.s.key[fp - 1] != k32;
-        }
-        float4 cen = make_float4(0.f, 0.f, 0.f, 0.f);
-        unsigned long long vk = 0;
-        if (head) {
-            float4 p = W.pts[W.u.s.idx[fp]];
-            if (pass) {
-                cen = p;   // PCL: output = *input_
-            } else {
-                float sx = 0.f, sy = 0.f, sz = 0.f;
-                uint32_t n = 0, cr = 0, cg = 0, cb = 0;
-                uint32_t q = fp;
-                for (;;) {
-                    sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z);
-                    const uint32_t w = __float_as_uint(p.w);
-                    cr += (w >> 16) & 255u; cg += (w >> 8) & 255u; cb += w & 255u;
-                    ++n; ++q;
-                    if (q >= m || W.u.s.key[q] != k32) break;
-                    p = W.pts[W.u.s.idx[q]];
-                }
-                cen = bk_centroid(sx, sy, sz, n, cr, cg, cb);
-            }
-            if (dbg_vox) dbg_vox[atomicAdd(dbg_cnt, 1u)] = cen;
-            cen.z = __fadd_rn(cen.z, 500.0f);   // pose_functions.cpp:1666
-            const int vi = (int)floorf(__fmul_rn(cen.x, icx)), vj = (int)floorf(__fmul_rn(cen.y, icx)),
-                      vkz = (int)floorf(__fmul_rn(cen.z, icz));
-            cmn[0] = min(cmn[0], vi); cmx[0] = max(cmx[0], vi);
-            cmn[1] = min(cmn[1], vj); cmx[1] = max(cmx[1], vj);
-            cmn[2] = min(cmn[2], vkz); cmx[2] = max(cmx[2], vkz);
-            const long long Bi = 1 << 20;
-            vk = ((unsigned long long)(vkz + Bi) << 42) | ((unsigned long long)(vj + Bi) << 21) | (unsigned long long)(vi + Bi);
-        }
-        if (!A.have_k0) {   // (warp-uniform) the first centroid of the bucket fixes the z cell of the nominal key
-            const unsigned long long first = __shfl_sync(kFull, vk, 0);   // position 0 is always a head
-            A.K0 = (first & ~((1ull << 42) - 1ull)) | A.K0;
-            A.have_k0 = 1;
-        }
-        const unsigned hm = __ballot_sync(kFull, head);
-        A.nvox += __popc(hm);
-        const bool other = head && vk != A.K0;
-        if (head && !other) {
-            const uint32_t w = __float_as_uint(cen.w);
-            A.ax = __fadd_rn(A.ax, cen.x); A.ay = __fadd_rn(A.ay, cen.y); A.az = __fadd_rn(A.az, cen.z);
-            ++A.an; A.ar += (w >> 16) & 255u; A.ag += (w >> 8) & 255u; A.ab += w & 255u;
-        }
-        const unsigned om = __ballot_sync(kFull, other);
-        if (om) {   // a centroid on the border of the nominal cell to the last float bit: its own record
-            if (other) {
-                const uint32_t sl = A.nstray + __popc(om & lt);
-                if (sl < (uint32_t)kBkMaxPart) {
-                    const uint32_t w = __float_as_uint(cen.w);
-                    o3r_cell pc;
-                    pc.key = vk; pc.sx = cen.x; pc.sy = cen.y; pc.sz = cen.z; pc.n = 1u;
-                    pc.sr = (w >> 16) & 255u; pc.sg = (w >> 8) & 255u; pc.sb = w & 255u; pc.pad = 0u;
-                    W.stray[sl] = pc;
-                }
-            }
-            A.nstray += __popc(om);
-        }
-    }
-    __syncwarp();
-}
-
-// out[*out_base + r]            main partial of the r-th non-empty bucket (r < totals[1])
-// out[*out_base + totals[1] + ...]  strays, appended through *stray_cnt (at most stray_cap)
-__global__ void __launch_bounds__(kThreads, O3R_BK_MINB) k_bk_reduce(
-    const float4* __restrict__ pts, const uint32_t* __restrict__ pos, const uint2* __restrict__ nl,
-    const uint32_t* __restrict__ totals, const BkFrame* __restrict__ bk, const uint8_t* __restrict__ frame_pass, float inv_f,
-    float icx, float icz, o3r_cell* __restrict__ out, const uint32_t* __restrict__ out_base, uint32_t* __restrict__ stray_cnt,
-    uint32_t stray_cap, uint32_t* __restrict__ ticket, uint32_t* __restrict__ frame_vox, int* __restrict__ cellbb,
-    uint32_t* __restrict__ flags, float4* __restrict__ dbg_vox, uint32_t* __restrict__ dbg_cnt) {
-    extern __shared__ __align__(16) unsigned char bk_smem_raw[];
-    __shared__ int s_bb[6];
-    if (flags[0]) return;   // raised by the histogram / scan (complete before this kernel starts): uniform exit
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    BkWarp& W = reinterpret_cast<BkWarp*>(bk_smem_raw)[warp];
-    const uint32_t NR = totals[1];
-    o3r_cell* const out0 = out + *out_base;
-    if (tid < 6) s_bb[tid] = tid < 3 ? 0x7fffffff : (int)0x80000000;
-    int cmn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, cmx[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
-    for (;;) {
-        uint32_t r0 = 0;
-        if (lane == 0) r0 = atomicAdd(ticket, (uint32_t)kBkPerWarp);
-        r0 = __shfl_sync(kFull, r0, 0);
-        if (r0 >= NR) break;
-#pragma unroll 1
-        for (uint32_t r = r0; r < min(r0 + (uint32_t)kBkPerWarp, NR); ++r) {
-            const uint2 ent = nl[r];
-            const uint32_t start = ent.x, cnt = ent.y & 0xffffu;
-            const int f = (int)(ent.y >> 16);
-            const BkFrame B = bk[f];
-            const bool pass = frame_pass[f] != 0;
-            const float4* gp = pts + start;
-            const uint32_t* gpos = pos + start;
-            BkAcc A;
-            A.ax = A.ay = A.az = 0.f;
-            A.an = A.ar = A.ag = A.ab = 0u;
-            A.nvox = A.nstray = 0u;
-            A.have_k0 = 0;
-            {   // the bucket's NOMINAL combined cell: its leaf columns are [5I, 5I + 5) x [5J, 5J + 5), i.e. cell (I, J) — a
-                // centroid lands in a neighbour only when it sits on the cell border to the last float bit
-                const float4 p = gp[0];
-                int ci, cj, ck;
-                bk_cell(p.x, p.y, p.z, inv_f, ci, cj, ck);
-                const long long Bi = 1 << 20;
-                const long long nI = ci >= 0 ? ci / kBkB : -((-ci + kBkB - 1) / kBkB), nJ = cj >= 0 ? cj / kBkB : -((-cj + kBkB - 1) / kBkB);
-                A.K0 = ((unsigned long long)(nJ + Bi) << 21) | (unsigned long long)(nI + Bi);
-            }
-            if (cnt <= (uint32_t)kBkCap) {
-                bk_pass<false>(W, gp, gpos, cnt, B, pass, inv_f, icx, icz, A, cmn, cmx, dbg_vox, dbg_cnt);
-            } else {
-                // ---- rare (overlapping surfaces pile up in one cell): one leaf column at a time.  PCL's order is
-                // (column, z cell, scan position), so the columns can be ranked and folded one after the other.
-                for (uint32_t col = 0; col < (uint32_t)kBkSub; ++col) {
-                    uint32_t m = 0;
-                    for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {
-                        const uint32_t e = e0 + lane;
-                        bool mine = false;
-                        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-                        uint32_t ps = 0;
-                        if (e < cnt) {
-                            p = gp[e]; ps = gpos[e];
-                            uint32_t c;
-                            bk_key64(B, pass, inv_f, p, ps, c);
-                            mine = c == col;
-                        }
-                        const unsigned mm = __ballot_sync(kFull, mine);
-                        if (mine) {
-                            const uint32_t at = m + __popc(mm & ((1u << lane) - 1u));
-                            if (at < (uint32_t)kBkCap) { W.pts[at] = p; W.u.ppos[at] = ps; }
-                        }
-                        m += __popc(mm);
-                    }
-                    __syncwarp();
-                    if (m > (uint32_t)kBkCap) {   // more than 256 points in ONE leaf column: give up (host falls back)
-                        if (lane == 0) atomicOr(flags + 1, BK_FLAG_BUCKET);
-                        m = kBkCap;
-                    }
-                    if (m) bk_pass<true>(W, W.pts, W.u.ppos, m, B, pass, inv_f, icx, icz, A, cmn, cmx, dbg_vox, dbg_cnt);
-                }
-            }
-            // the main partial: lanes already folded their leaves in order; fixed xor butterfly across the lanes
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                A.ax = __fadd_rn(A.ax, __shfl_xor_sync(kFull, A.ax, o));
-                A.ay = __fadd_rn(A.ay, __shfl_xor_sync(kFull, A.ay, o));
-                A.az = __fadd_rn(A.az, __shfl_xor_sync(kFull, A.az, o));
-            }
-            const uint32_t an = __reduce_add_sync(kFull, A.an), ar = __reduce_add_sync(kFull, A.ar),
-                           ag = __reduce_add_sync(kFull, A.ag), ab = __reduce_add_sync(kFull, A.ab);
-            uint32_t ns = A.nstray;
-            if (ns > (uint32_t)kBkMaxPart) {
-                if (lane == 0) atomicOr(flags + 1, BK_FLAG_PART);
-                ns = kBkMaxPart;
-            }
-            o3r_cell mainc;
-            mainc.key = A.K0; mainc.sx = A.ax; mainc.sy = A.ay; mainc.sz = A.az; mainc.n = an;
-            mainc.sr = ar; mainc.sg = ag; mainc.sb = ab; mainc.pad = 0u;
-            if (an == 0u) mainc = W.stray[--ns];   // every centroid strayed: no empty record, the last stray takes the main slot
-            if (lane == 0) {
-                out0[r] = mainc;
-                atomicAdd(&frame_vox[f], A.nvox);
-            }
-            if (ns) {
-                uint32_t at = 0;
-                if (lane == 0) at = atomicAdd(stray_cnt, ns);
-                at = __shfl_sync(kFull, at, 0);
-                if (at + ns > stray_cap) {
-                    if (lane == 0) atomicOr(flags + 1, BK_FLAG_PART);
-                } else {
-                    uint32_t* dst = reinterpret_cast<uint32_t*>(out0 + NR + at);
-                    const uint32_t* src = reinterpret_cast<const uint32_t*>(&W.stray[0]);
-                    for (uint32_t i = lane; i < ns * (uint32_t)(sizeof(o3r_cell) / 4); i += 32) dst[i] = src[i];
-                }
-            }
-            __syncwarp();
-        }
-    }
-    // ---- range of combined-grid cells touched (the merge packs its sort keys into it)
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const int lo = __reduce_min_sync(kFull, cmn[a]), hi = __reduce_max_sync(kFull, cmx[a]);
-        cmn[a] = lo; cmx[a] = hi;
-    }
-    __syncthreads();
-    if (lane == 0) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) { atomicMin(&s_bb[a], cmn[a]); atomicMax(&s_bb[3 + a], cmx[a]); }
-    }
-    __syncthreads();
-    if (tid < 3) { if (s_bb[tid] != 0x7fffffff) atomicMin(&cellbb[tid], s_bb[tid]); }
-    else if (tid < 6) { if (s_bb[tid] != (int)0x80000000) atomicMax(&cellbb[tid], s_bb[tid]); }
-}
-
-// Canonical order of the chunk's stray records (they were appended in atomic order): rank by the whole record.  Two records
-// that compare equal are identical, so their mutual order does not matter.  One CTA; n is tiny (a couple per frame).
-// Also publishes the chunk's record count: main slots + strays.
 __device__ __forceinline__ bool bk_cell_less(const o3r_cell& a, const o3r_cell& b) {
     if (a.key != b.key) return a.key < b.key;
     const uint32_t av[7] = {__float_as_uint(a.sx), __float_as_uint(a.sy), __float_as_uint(a.sz), a.n, a.sr, a.sg, a.sb};
@@ -728,6 +505,248 @@ __device__ __forceinline__ bool bk_cell_less(const o3r_cell& a, const o3r_cell& 
         if (av[i] != bv[i]) return av[i] < bv[i];
     return false;
 }
+
+// out[*out_base + r]            main partial of the r-th non-empty bucket (r < totals[1])
+// out[*out_base + totals[1] + ...]  strays, appended through *stray_cnt (at most stray_cap)
+__global__ void __launch_bounds__(kThreads, O3R_BK_MINB) k_bk_reduce(
+    const float4* __restrict__ pts, const unsigned long long* __restrict__ keys, const uint4* __restrict__ nl,
+    const uint32_t* __restrict__ totals, float icx, float icz, o3r_cell* __restrict__ out,
+    const uint32_t* __restrict__ out_base, uint32_t* __restrict__ stray_cnt, uint32_t stray_cap, uint32_t* __restrict__ ticket,
+    uint32_t* __restrict__ frame_vox, int* __restrict__ cellbb, uint32_t* __restrict__ flags, float4* __restrict__ dbg_vox,
+    uint32_t* __restrict__ dbg_cnt) {
+    extern __shared__ __align__(16) unsigned char bk_smem_raw[];
+    RdSmem& S = *reinterpret_cast<RdSmem*>(bk_smem_raw);
+    if (flags[0]) return;   // raised by the histogram / scan (complete before this kernel starts): uniform exit
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t NR = totals[1];
+    o3r_cell* const out0 = out + *out_base;
+    if (tid < 6) S.bb[tid] = tid < 3 ? 0x7fffffff : (int)0x80000000;
+    // range of combined-grid cells touched (the merge packs its sort keys into it)
+    int cmn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, cmx[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+    const int Bi = 1 << 20;
+    for (;;) {
+        __syncthreads();   // (the previous ticket's shared memory is free)
+        if (tid == 0) S.ticket = atomicAdd(ticket, (uint32_t)kRdG);
+        __syncthreads();
+        const uint32_t r0 = S.ticket;
+        if (r0 >= NR) break;
+        const int nb = (int)min((uint32_t)kRdG, NR - r0);
+        if (tid < nb) S.ent[tid] = nl[r0 + tid];
+        __syncthreads();
+        for (int b0 = 0; b0 < nb;) {
+            // ---- sub-batch: as many of the ticket's buckets as fit (normally all of them)
+            const uint32_t base = S.ent[b0].x;
+            int b1 = b0;
+            uint32_t n = 0;
+            while (b1 < nb) {
+                const uint32_t c = S.ent[b1].y & 0xffffu;
+                if (n + c > (uint32_t)kRdCap) break;
+                n += c; ++b1;
+            }
+            if (b1 == b0) {   // a single bucket larger than a CTA can hold: give up (the host falls back to the sort engine)
+                if (tid == 0) atomicOr(flags + 1, BK_FLAG_BUCKET);
+                ++b0;
+                continue;
+            }
+            const int nbb = b1 - b0, nbins = nbb * kBkSub;
+            __syncthreads();   // (the previous sub-batch is done with shared memory)
+            for (int i = tid; i <= nbins; i += kThreads) S.bin[i] = 0u;
+            for (int i = tid; i < kRdCap / 32 + 1; i += kThreads) S.startbits[i] = 0u;
+            if (tid <= nbb) S.bstart[tid] = tid < nbb ? S.ent[b0 + tid].x - base : n;
+            if (tid < nbb) S.nstray[tid] = 0u;
+            __syncthreads();
+            // ---- load; number every point inside its (bucket, column) bin
+            unsigned long long key[kRdItems];
+            uint32_t bs[kRdItems];   // bin | slot << 16
+#pragma unroll
+            for (int k = 0; k < kRdItems; ++k) {
+                const uint32_t i = k * kThreads + tid;
+                if (i < n) {
+                    key[k] = __ldcs(keys + base + i);
+                    S.pts[i] = __ldcs(pts + base + i);
+                    int bl = 0;
+#pragma unroll
+                    for (int st = 8; st > 0; st >>= 1)
+                        if (bl + st < nbb && S.bstart[bl + st] <= i) bl += st;
+                    const bool pass = (S.ent[b0 + bl].y >> 31) != 0u;
+                    const uint32_t bin = (uint32_t)bl * kBkSub + bk_key_col(key[k], pass);
+                    bs[k] = bin | (atomicAdd(&S.bin[bin], 1u) << 16);
+                }
+            }
+            __syncthreads();
+            {   // first position of every bin; mark where bins start
+                const int i0 = tid * 2;
+                const uint32_t c0 = i0 < nbins ? S.bin[i0] : 0u, c1 = i0 + 1 < nbins ? S.bin[i0 + 1] : 0u;
+                uint32_t tot;
+                const uint32_t ex = block_excl_scan(c0 + c1, S.scan, tot);
+                if (i0 < nbins) { S.bin[i0] = ex; if (c0) atomicOr(&S.startbits[ex >> 5], 1u << (ex & 31u)); }
+                if (i0 + 1 < nbins) { S.bin[i0 + 1] = ex + c0; if (c1) atomicOr(&S.startbits[(ex + c0) >> 5], 1u << ((ex + c0) & 31u)); }
+                if (tid == 0) S.bin[nbins] = n;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < kRdItems; ++k) {
+                const uint32_t i = k * kThreads + tid;
+                if (i < n) {
+                    const uint32_t at = S.bin[bs[k] & 0xffffu] + (bs[k] >> 16);
+                    S.skey[at] = key[k];
+                    S.sidx[at] = (uint16_t)i;
+                }
+            }
+            __syncthreads();
+            // ---- rank inside the bin by (leaf key, scan position)
+#pragma unroll
+            for (int k = 0; k < kRdItems; ++k) {
+                const uint32_t i = k * kThreads + tid;
+                if (i < n) {
+                    const uint32_t bin = bs[k] & 0xffffu;
+                    const uint32_t a = S.bin[bin], e = S.bin[bin + 1];
+                    uint32_t rk = a;
+                    for (uint32_t j = a; j < e; ++j) rk += S.skey[j] < key[k] ? 1u : 0u;
+                    S.fkey[rk] = (uint32_t)(key[k] >> 32);
+                    S.fidx[rk] = (uint16_t)i;
+                }
+            }
+            __syncthreads();
+            // z cell of each bucket's nominal combined cell: that of its first point in final order
+            if (tid < nbb) {
+                const float4 p = S.pts[S.fidx[S.bstart[tid]]];
+                S.kz[tid] = (int)floorf(__fmul_rn(__fadd_rn(p.z, 500.0f), icz));
+            }
+            __syncthreads();
+            // ---- leaves: left fold in scan order; combined-grid cell of every centroid
+#pragma unroll 1
+            for (int k = 0; k < kRdItems; ++k) {
+                const uint32_t pos = k * kThreads + tid;
+                if (pos >= n) break;
+                int bl = 0;
+#pragma unroll
+                for (int st = 8; st > 0; st >>= 1)
+                    if (bl + st < nbb && S.bstart[bl + st] <= pos) bl += st;
+                const uint4 ent = S.ent[b0 + bl];
+                const bool pass = (ent.y >> 31) != 0u;
+                const uint32_t k32 = S.fkey[pos];
+                const bool head = pass || ((S.startbits[pos >> 5] >> (pos & 31u)) & 1u) || S.fkey[pos - 1] != k32;
+                if (!head) continue;
+                const uint32_t me = S.fidx[pos];
+                float4 p = S.pts[me];
+                float4 cen;
+                if (pass) {
+                    cen = p;   // PCL: output = *input_
+                } else {
+                    float sx = 0.f, sy = 0.f, sz = 0.f;
+                    uint32_t cn = 0, cr = 0, cg = 0, cb = 0;
+                    uint32_t q = pos;
+                    for (;;) {
+                        sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z);
+                        const uint32_t w = __float_as_uint(p.w);
+                        cr += (w >> 16) & 255u; cg += (w >> 8) & 255u; cb += w & 255u;
+                        ++cn; ++q;
+                        if (q >= n || ((S.startbits[q >> 5] >> (q & 31u)) & 1u) || S.fkey[q] != k32) break;
+                        p = S.pts[S.fidx[q]];
+                    }
+                    cen = bk_centroid(sx, sy, sz, cn, cr, cg, cb);
+                }
+                if (dbg_vox) dbg_vox[atomicAdd(dbg_cnt, 1u)] = cen;
+                cen.z = __fadd_rn(cen.z, 500.0f);   // pose_functions.cpp:1666
+                const int vi = (int)floorf(__fmul_rn(cen.x, icx)), vj = (int)floorf(__fmul_rn(cen.y, icx)),
+                          vk = (int)floorf(__fmul_rn(cen.z, icz));
+                if (vi == (int)ent.z && vj == (int)ent.w && vk == S.kz[bl]) {
+                    S.pts[me] = cen;
+                    S.fidx[pos] = (uint16_t)(me | 0x8000u);
+                } else {   // on the border of the nominal cell to the last float bit: its own record
+                    S.fidx[pos] = (uint16_t)(me | 0x4000u);
+                    cmn[0] = min(cmn[0], vi); cmx[0] = max(cmx[0], vi);
+                    cmn[1] = min(cmn[1], vj); cmx[1] = max(cmx[1], vj);
+                    cmn[2] = min(cmn[2], vk); cmx[2] = max(cmx[2], vk);
+                    const uint32_t sl = atomicAdd(&S.nstray[bl], 1u);
+                    if (sl < (uint32_t)kRdStray) {
+                        const uint32_t w = __float_as_uint(cen.w);
+                        o3r_cell pc;
+                        pc.key = ((unsigned long long)(uint32_t)(vk + Bi) << 42) | ((unsigned long long)(uint32_t)(vj + Bi) << 21) |
+                                 (unsigned long long)(uint32_t)(vi + Bi);
+                        pc.sx = cen.x; pc.sy = cen.y; pc.sz = cen.z; pc.n = 1u;
+                        pc.sr = (w >> 16) & 255u; pc.sg = (w >> 8) & 255u; pc.sb = w & 255u; pc.pad = 0u;
+                        S.stray[bl][sl] = pc;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- one warp per bucket: the partial sum of the nominal cell (lanes in position order, then an xor butterfly)
+            for (int bl = warp; bl < nbb; bl += kWarps) {
+                const uint4 ent = S.ent[b0 + bl];
+                const uint32_t a = S.bstart[bl], e = S.bstart[bl + 1];
+                float ax = 0.f, ay = 0.f, az = 0.f;
+                uint32_t an = 0, ar = 0, ag = 0, ab = 0, nh = 0;
+                for (uint32_t pos = a + lane; pos < e; pos += 32) {
+                    const uint32_t fi = S.fidx[pos];
+                    if (fi & 0x8000u) {
+                        const float4 c = S.pts[fi & 0x3fffu];
+                        const uint32_t w = __float_as_uint(c.w);
+                        ax = __fadd_rn(ax, c.x); ay = __fadd_rn(ay, c.y); az = __fadd_rn(az, c.z);
+                        ++an; ar += (w >> 16) & 255u; ag += (w >> 8) & 255u; ab += w & 255u;
+                    }
+                    nh += (fi & 0xc000u) ? 1u : 0u;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    ax = __fadd_rn(ax, __shfl_xor_sync(kFull, ax, o));
+                    ay = __fadd_rn(ay, __shfl_xor_sync(kFull, ay, o));
+                    az = __fadd_rn(az, __shfl_xor_sync(kFull, az, o));
+                }
+                an = __reduce_add_sync(kFull, an); ar = __reduce_add_sync(kFull, ar);
+                ag = __reduce_add_sync(kFull, ag); ab = __reduce_add_sync(kFull, ab);
+                nh = __reduce_add_sync(kFull, nh);
+                if (lane == 0) {
+                    uint32_t ns = S.nstray[bl];
+                    if (ns > (uint32_t)kRdStray) { atomicOr(flags + 1, BK_FLAG_PART); ns = kRdStray; }
+                    o3r_cell mainc;
+                    const int nI = (int)ent.z, nJ = (int)ent.w, kz = S.kz[bl];
+                    mainc.key = ((unsigned long long)(uint32_t)(kz + Bi) << 42) | ((unsigned long long)(uint32_t)(nJ + Bi) << 21) |
+                                (unsigned long long)(uint32_t)(nI + Bi);
+                    mainc.sx = ax; mainc.sy = ay; mainc.sz = az; mainc.n = an; mainc.sr = ar; mainc.sg = ag; mainc.sb = ab; mainc.pad = 0u;
+                    if (an == 0u) {   // every centroid strayed: no empty record — the smallest stray takes the main slot
+                        uint32_t best = 0;
+                        for (uint32_t i = 1; i < ns; ++i)
+                            if (bk_cell_less(S.stray[bl][i], S.stray[bl][best])) best = i;
+                        mainc = S.stray[bl][best];
+                        S.stray[bl][best] = S.stray[bl][ns - 1];
+                        --ns;
+                    } else {
+                        cmn[0] = min(cmn[0], nI); cmx[0] = max(cmx[0], nI);
+                        cmn[1] = min(cmn[1], nJ); cmx[1] = max(cmx[1], nJ);
+                        cmn[2] = min(cmn[2], kz); cmx[2] = max(cmx[2], kz);
+                    }
+                    out0[r0 + b0 + bl] = mainc;
+                    atomicAdd(&frame_vox[(ent.y >> 16) & 0x7fffu], nh);
+                    if (ns) {
+                        const uint32_t at = atomicAdd(stray_cnt, ns);
+                        if (at + ns > stray_cap) atomicOr(flags + 1, BK_FLAG_PART);
+                        else
+                            for (uint32_t i = 0; i < ns; ++i) out0[NR + at + i] = S.stray[bl][i];
+                    }
+                }
+            }
+            b0 = b1;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int lo = __reduce_min_sync(kFull, cmn[a]), hi = __reduce_max_sync(kFull, cmx[a]);
+        cmn[a] = lo; cmx[a] = hi;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { atomicMin(&S.bb[a], cmn[a]); atomicMax(&S.bb[3 + a], cmx[a]); }
+    }
+    __syncthreads();
+    if (tid < 3) { if (S.bb[tid] != 0x7fffffff) atomicMin(&cellbb[tid], S.bb[tid]); }
+    else if (tid < 6) { if (S.bb[tid] != (int)0x80000000) atomicMax(&cellbb[tid], S.bb[tid]); }
+}
+
+// Canonical order of the chunk's stray records (they were appended in atomic order): rank by the whole record.  Two records
+// that compare equal are identical, so their mutual order does not matter.  One CTA; n is tiny (a couple per frame).
+// Also publishes the chunk's record count: main slots + strays.
 __global__ void __launch_bounds__(1024) k_bk_strays(o3r_cell* __restrict__ out, const uint32_t* __restrict__ out_base,
                                                     const uint32_t* __restrict__ totals, const uint32_t* __restrict__ stray_cnt,
                                                     uint32_t stray_cap, o3r_cell* __restrict__ tmp, uint32_t* __restrict__ chunk_total,

@@ -97,9 +97,9 @@ int bk_prepare(o3r_ctx* ctx, const BkPlan& pl, int n, size_t cap_batch, size_t c
     { int rcu = upload_small(ctx, ctx->bk_frames.p, pl.fr.data(), (size_t)n * sizeof(BkFrame)); if (rcu) return rcu; }
     CU(ctx->bk_counts.ensure(pl.max_chunk_nb * 4 + 64));
     const size_t nl_ub = std::min(pl.max_chunk_nb, cap_chunk);
-    CU(ctx->bk_nl.ensure(nl_ub * 8 + 64));
+    CU(ctx->bk_nl.ensure(nl_ub * 16 + 64));
     CU(ctx->bk_pts.ensure(cap_chunk * 16));
-    CU(ctx->bk_pos.ensure(cap_chunk * 4));
+    CU(ctx->bk_pos.ensure(cap_chunk * 8));   // ordering keys (leaf key | scan position)
     CU(ctx->bk_status.ensure(((size_t)cdiv(pl.max_chunk_nb, kBkScanTile) + 1) * 8 + 64));
     CU(ctx->bk_stray.ensure((size_t)kBkStrayCap * sizeof(o3r_cell)));
     CU(ctx->bk_misc.ensure(256 + (size_t)n * 4 + (size_t)n));
@@ -143,14 +143,14 @@ int bk_run_chunk(o3r_ctx* ctx, const AParams& P, const BkPlan& pl, int ci, int f
     LAUNCH(k_bbox_init, cdiv((size_t)nc * 6, kThreads), kThreads, 0, bbox, nc);
     LAUNCH_N("k_bk_hist", (k_bk_hist<DT>), grid, kThreads, 0, P, fr, bk, ctx->inv_f, ctx->bk_counts.as<uint32_t>(), bbox, M.flags);
     LAUNCH(k_bk_frames, cdiv(nc, 64), 64, 0, nc, bbox, ctx->inv_f, M.pass + f0, M.fvox + f0);
-    LAUNCH(k_bk_scan, scan_tiles, kThreads, 0, ctx->bk_counts.as<uint32_t>(), (uint32_t)nb, bk, nc, ctx->bk_nl.as<uint2>(),
-           st_scan, M.t_scan, M.totals, M.flags);
-    LAUNCH_N("k_bk_scatter", (k_bk_scatter<DT>), grid, kThreads, 0, P, fr, bk, ctx->inv_f, ctx->bk_counts.as<uint32_t>(),
-             ctx->bk_pts.as<float4>(), ctx->bk_pos.as<uint32_t>(), M.flags);
-    const uint32_t rgrid = std::max(1u, std::min<uint32_t>(cdiv(nl_ub, kWarps * kBkPerWarp), (uint32_t)ctx->bk_reduce_ctas));
+    LAUNCH(k_bk_scan, scan_tiles, kThreads, 0, ctx->bk_counts.as<uint32_t>(), (uint32_t)nb, bk, M.pass + f0, nc,
+           ctx->bk_nl.as<uint4>(), st_scan, M.t_scan, M.totals, M.flags);
+    LAUNCH_N("k_bk_scatter", (k_bk_scatter<DT>), grid, kThreads, 0, P, fr, bk, M.pass + f0, ctx->inv_f,
+             ctx->bk_counts.as<uint32_t>(), ctx->bk_pts.as<float4>(), ctx->bk_pos.as<unsigned long long>(), M.flags);
+    const uint32_t rgrid = std::max(1u, std::min<uint32_t>(cdiv(nl_ub, kRdG), (uint32_t)ctx->bk_reduce_ctas));
     float4* dbg = ctx->keep_frame_voxels ? ctx->vox.as<float4>() : nullptr;
-    LAUNCH(k_bk_reduce, rgrid, kThreads, bk_reduce_smem(), ctx->bk_pts.as<float4>(), ctx->bk_pos.as<uint32_t>(),
-           ctx->bk_nl.as<uint2>(), M.totals, bk, M.pass + f0, ctx->inv_f, ctx->inv_c, ctx->inv_cz, ctx->partials.as<o3r_cell>(),
+    LAUNCH(k_bk_reduce, rgrid, kThreads, bk_reduce_smem(), ctx->bk_pts.as<float4>(), ctx->bk_pos.as<unsigned long long>(),
+           ctx->bk_nl.as<uint4>(), M.totals, ctx->inv_c, ctx->inv_cz, ctx->partials.as<o3r_cell>(),
            cnt + CNT_PART, M.stray_cnt, (uint32_t)kBkStrayCap, M.t_reduce, M.fvox + f0, reinterpret_cast<int*>(cnt + CNT_CELLBB),
            M.flags, dbg, M.dbg_cnt);
     LAUNCH(k_bk_strays, 1, 1024, 0, ctx->partials.as<o3r_cell>(), cnt + CNT_PART, M.totals, M.stray_cnt, (uint32_t)kBkStrayCap,

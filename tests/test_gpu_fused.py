@@ -130,9 +130,9 @@ def test_fused_passthrough_frames():
     _close(got, exp)
 
 
-@pytest.mark.parametrize("voxel", [0.08, 0.2])
+@pytest.mark.parametrize("voxel", [0.08, 0.12])
 def test_fused_big_buckets_are_ranked_column_by_column(voxel):
-    """voxel_size 0.08 / 0.2 put ~210 / ~1300 points into one 5x5-leaf bucket: above 256 the warp ranks one leaf column at a
+    """voxel_size 0.08 / 0.12 put ~210 / ~470 points into one 5x5-leaf bucket: above 128 the warp ranks one leaf column at a
     time (PCL's order is column-major inside a bucket), same bit-exact per-frame centroids."""
     keep = []
     geom = SMALL4
@@ -144,7 +144,7 @@ def test_fused_big_buckets_are_ranked_column_by_column(voxel):
 
 
 def test_fused_falls_back_to_the_sort_engine_when_a_leaf_column_overflows():
-    """voxel_size 0.5 puts ~330 points into ONE leaf column (> 256): the device raises the overflow flag, the batch is rerun
+    """voxel_size 0.5 puts ~330 points into ONE leaf column (> 128): the device raises the overflow flag, the batch is rerun
     through the sort engine (TILED contract) and the context stays there."""
     keep = []
     geom = SMALL4
