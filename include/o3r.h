@@ -282,6 +282,27 @@ int o3r_exchange_merge_bb(o3r_ctx* ctx, const o3r_cell* recv_dev, size_t n, cons
  * the batch, in no particular order, and o3r_last_batch_points returns that multiset. */
 int o3r_set_keep_frame_voxels(o3r_ctx* ctx, int keep);
 
+/* ---- the exchange inside the library -------------------------------------------------------------------------------------
+ * One process per GPU; rank r reconstructs the cycle's frames f with f mod world == r (the reference's 7-thread fan-out,
+ * pose.cpp:383-424, spread over GPUs) and owns the combined-grid cells whose hash64(key) mod world == r.  After each
+ * o3r_frames_cloud* call every rank calls o3r_exchange_cycle: the batch's partial cells are bucketed by owner and exchanged
+ * with grouped ncclSend / ncclRecv on the context's stream, and what arrives is folded into the rank's shard.  Each (source,
+ * destination) pair moves ONE fixed-size slot of slot_cells cells per cycle with the valid count in its first record, so
+ * nothing about a cycle's exchange crosses the host and the call returns without waiting for the GPU.  slot_cells must be
+ * the same on all ranks; size it at twice the cells one rank sends to one owner in a cycle (a rank's partial cells per cycle
+ * / world).  An overflowing slot drops cells: the next o3r_cloud_downsample then fails with O3R_ERR_CAPACITY.
+ * The union of the ranks' o3r_cloud_downsample outputs, ordered by cell key, is the single-GPU cloud: keys, counts and
+ * colours exactly, centroids within float reassociation (1e-5 relative).
+ * NCCL is loaded at run time (libnccl.so.2); o3r_comm_unique_id + o3r_comm_init create a communicator of the library's own
+ * (the id travels by whatever channel the host has: MPI, a file, torch.distributed), o3r_comm_attach adopts an existing
+ * ncclComm_t.  Both switch the context to deferred merging (o3r_set_defer_merge). */
+#define O3R_COMM_ID_BYTES 128
+int o3r_comm_unique_id(void* id_out /* O3R_COMM_ID_BYTES, rank 0 */);
+int o3r_comm_init(o3r_ctx* ctx, int world, int rank, const void* id, size_t slot_cells);   /* collective */
+int o3r_comm_attach(o3r_ctx* ctx, void* nccl_comm, int world, int rank, size_t slot_cells);
+int o3r_comm_destroy(o3r_ctx* ctx);
+int o3r_exchange_cycle(o3r_ctx* ctx);                                                     /* collective, asynchronous */
+
 /* When set, o3r_frames_cloud* keeps the batch's per-frame clouds but does not merge them into the
  * resident cloud; the caller runs o3r_exchange_pack / o3r_exchange_merge instead. */
 int o3r_set_defer_merge(o3r_ctx* ctx, int defer);

@@ -311,7 +311,7 @@ struct BkScatterWarp {
     uint32_t base[kBkWarpItems];   // by run head position: first slot of the run
 };
 template <int DT>
-__global__ void __launch_bounds__(kThreads) k_bk_scatter(AParams P, const FrameDev* __restrict__ frames,
+__global__ void __launch_bounds__(kThreads, 5) k_bk_scatter(AParams P, const FrameDev* __restrict__ frames,
                                                          const BkFrame* __restrict__ bk, const uint8_t* __restrict__ frame_pass,
                                                          float inv_f, uint32_t* __restrict__ cursor, float4* __restrict__ pts,
                                                          unsigned long long* __restrict__ keys_out,
@@ -456,6 +456,8 @@ struct RdSmem {
     uint32_t startbits[kRdCap / 32 + 1];   // bit p: position p starts a bin
     uint4 ent[kRdG];
     uint32_t bstart[kRdG + 1];             // first point of each bucket, relative to the sub-batch
+    uint8_t cb[kRdCap / 32 + 4];           // bucket that holds position 32 c (the lookup walks on from there)
+    uint32_t sub_b1, sub_n;                // the sub-batch: buckets [b0, sub_b1), sub_n points
     int kz[kRdG];                          // z cell of the nominal combined cell
     o3r_cell stray[kRdG][kRdStray];
     uint32_t nstray[kRdG];
@@ -536,24 +538,39 @@ __global__ void __launch_bounds__(kThreads, O3R_BK_MINB) k_bk_reduce(
         for (int b0 = 0; b0 < nb;) {
             // ---- sub-batch: as many of the ticket's buckets as fit (normally all of them)
             const uint32_t base = S.ent[b0].x;
-            int b1 = b0;
-            uint32_t n = 0;
-            while (b1 < nb) {
-                const uint32_t c = S.ent[b1].y & 0xffffu;
-                if (n + c > (uint32_t)kRdCap) break;
-                n += c; ++b1;
+            __syncthreads();   // (the previous sub-batch is done with shared memory)
+            if (tid == 0) {
+                int e1 = b0;
+                uint32_t m = 0;
+                while (e1 < nb) {
+                    const uint32_t c = S.ent[e1].y & 0xffffu;
+                    if (m + c > (uint32_t)kRdCap) break;
+                    m += c; ++e1;
+                }
+                S.sub_b1 = (uint32_t)e1; S.sub_n = m;
             }
+            __syncthreads();
+            const int b1 = (int)S.sub_b1;
+            const uint32_t n = S.sub_n;
             if (b1 == b0) {   // a single bucket larger than a CTA can hold: give up (the host falls back to the sort engine)
                 if (tid == 0) atomicOr(flags + 1, BK_FLAG_BUCKET);
                 ++b0;
                 continue;
             }
             const int nbb = b1 - b0, nbins = nbb * kBkSub;
-            __syncthreads();   // (the previous sub-batch is done with shared memory)
             for (int i = tid; i <= nbins; i += kThreads) S.bin[i] = 0u;
             for (int i = tid; i < kRdCap / 32 + 1; i += kThreads) S.startbits[i] = 0u;
             if (tid <= nbb) S.bstart[tid] = tid < nbb ? S.ent[b0 + tid].x - base : n;
             if (tid < nbb) S.nstray[tid] = 0u;
+            __syncthreads();
+            if (tid * 32u < n + 32u) {   // coarse position -> bucket table
+                const uint32_t i = tid * 32u;
+                int bl = 0;
+#pragma unroll
+                for (int st = 8; st > 0; st >>= 1)
+                    if (bl + st < nbb && S.bstart[bl + st] <= i) bl += st;
+                S.cb[tid] = (uint8_t)bl;
+            }
             __syncthreads();
             // ---- load; number every point inside its (bucket, column) bin
             unsigned long long key[kRdItems];
@@ -564,10 +581,8 @@ __global__ void __launch_bounds__(kThreads, O3R_BK_MINB) k_bk_reduce(
                 if (i < n) {
                     key[k] = __ldcs(keys + base + i);
                     S.pts[i] = __ldcs(pts + base + i);
-                    int bl = 0;
-#pragma unroll
-                    for (int st = 8; st > 0; st >>= 1)
-                        if (bl + st < nbb && S.bstart[bl + st] <= i) bl += st;
+                    int bl = S.cb[i >> 5];
+                    while (bl + 1 < nbb && S.bstart[bl + 1] <= i) ++bl;
                     const bool pass = (S.ent[b0 + bl].y >> 31) != 0u;
                     const uint32_t bin = (uint32_t)bl * kBkSub + bk_key_col(key[k], pass);
                     bs[k] = bin | (atomicAdd(&S.bin[bin], 1u) << 16);
@@ -602,6 +617,7 @@ __global__ void __launch_bounds__(kThreads, O3R_BK_MINB) k_bk_reduce(
                     const uint32_t bin = bs[k] & 0xffffu;
                     const uint32_t a = S.bin[bin], e = S.bin[bin + 1];
                     uint32_t rk = a;
+#pragma unroll 2
                     for (uint32_t j = a; j < e; ++j) rk += S.skey[j] < key[k] ? 1u : 0u;
                     S.fkey[rk] = (uint32_t)(key[k] >> 32);
                     S.fidx[rk] = (uint16_t)i;
@@ -619,10 +635,8 @@ __global__ void __launch_bounds__(kThreads, O3R_BK_MINB) k_bk_reduce(
             for (int k = 0; k < kRdItems; ++k) {
                 const uint32_t pos = k * kThreads + tid;
                 if (pos >= n) break;
-                int bl = 0;
-#pragma unroll
-                for (int st = 8; st > 0; st >>= 1)
-                    if (bl + st < nbb && S.bstart[bl + st] <= pos) bl += st;
+                int bl = S.cb[pos >> 5];
+                while (bl + 1 < nbb && S.bstart[bl + 1] <= pos) ++bl;
                 const uint4 ent = S.ent[b0 + bl];
                 const bool pass = (ent.y >> 31) != 0u;
                 const uint32_t k32 = S.fkey[pos];

@@ -111,14 +111,14 @@ int bk_prepare(o3r_ctx* ctx, const BkPlan& pl, int n, size_t cap_batch, size_t c
 }
 
 // misc layout: [0..1] flags (upstream, reduce), [2..3] totals {points, non-empty buckets}, [4] scan ticket, [5] reduce ticket,
-// [6] debug voxel count, [7] stray count, [64..64+n) per-frame voxel counts, then n bytes of per-frame pass-through flags
+// [6] stray count, [7] debug voxel count (batch-wide), [64..64+n) per-frame voxel counts, then n bytes of per-frame pass-through flags
 struct BkMisc {
     uint32_t *flags, *totals, *t_scan, *t_reduce, *dbg_cnt, *stray_cnt, *fvox;
     uint8_t* pass;
 };
 BkMisc bk_misc(o3r_ctx* ctx, int n) {
     uint32_t* m = ctx->bk_misc.as<uint32_t>();
-    return BkMisc{m, m + 2, m + 4, m + 5, m + 6, m + 7, m + 64, reinterpret_cast<uint8_t*>(m + 64 + n)};
+    return BkMisc{m, m + 2, m + 4, m + 5, m + 7, m + 6, m + 64, reinterpret_cast<uint8_t*>(m + 64 + n)};
 }
 
 // one chunk of frames [f0, f0 + nc) through hist -> scan -> scatter -> reduce; partial cells are appended to ctx->partials at
@@ -133,11 +133,15 @@ int bk_run_chunk(o3r_ctx* ctx, const AParams& P, const BkPlan& pl, int ci, int f
     const uint32_t scan_tiles = cdiv(nb, kBkScanTile);
     const size_t nl_ub = std::min(nb, cap_chunk);
     unsigned long long* st_scan = ctx->bk_status.as<unsigned long long>();
-    ZERO(ctx->bk_counts.p, nb * 4);
-    ZERO(ctx->bk_status.p, ((size_t)scan_tiles + 1) * 8);
-    ZERO(M.totals, 16);   // totals + both tickets
-    ZERO(M.stray_cnt, 4);
-    ZERO(cnt + CNT_PARTCHUNK, 4);
+    {
+        ZeroBatch Z;
+        Z.add(ctx->bk_counts.p, nb * 4);
+        Z.add(ctx->bk_status.p, ((size_t)scan_tiles + 1) * 8);
+        Z.add(M.totals, 20);   // totals, both tickets, stray count
+        Z.add(cnt + CNT_PARTCHUNK, 4);
+        int rcz = zero_batch(ctx, Z);
+        if (rcz) return rcz;
+    }
     const dim3 grid(P.tiles_per_frame, nc);
     uint32_t* bbox = ctx->bbox.as<uint32_t>() + (size_t)f0 * 6;
     LAUNCH(k_bbox_init, cdiv((size_t)nc * 6, kThreads), kThreads, 0, bbox, nc);

@@ -61,6 +61,7 @@ struct DevBuf {
 };
 
 enum { CNT_PTS = 0, CNT_VOX = 1, CNT_CYC = 2, CNT_NEW = 3, CNT_EMIT = 4, CNT_NEWSCAN = 5, CNT_BASE = 6, CNT_NRES = 7, CNT_ZERO = 8, CNT_PART = 9, CNT_PARTCHUNK = 10,
+       CNT_XFLAG = 11, CNT_XRECV = 12,
        CNT_CELLBB = 16, CNT_N = 32 };
 
 }  // namespace
@@ -151,6 +152,13 @@ struct o3r_ctx {
     int bk_reduce_ctas = 148 * 4;
     bool bucket_off = false;          // a batch overflowed the engine's limits: the sort engine serves this context from then on
     bool last_bucketed = false;       // the last batch ran through the bucket engine (no per-frame clouds were materialised)
+    // multi-GPU exchange inside the library (host_comm.cuh)
+    void* comm = nullptr;             // ncclComm_t
+    bool comm_owned = false;
+    int world = 1, rank = 0;
+    uint32_t slot_cap = 0;            // cells per (source, destination) slot
+    DevBuf x_send, x_recv, x_list;
+    bool x_pending_check = false;
     bool keep_frame_voxels = false;   // parity probe: the bucket engine also writes every per-frame voxel centroid (any order)
     size_t last_partials = 0;
     bool last_has_partials = false;
@@ -249,6 +257,35 @@ int zero_fill(o3r_ctx* ctx, void* dst, size_t bytes) {
     return O3R_OK;
 }
 #define ZERO(ptr, bytes) do { int rcz_ = zero_fill(ctx, (ptr), (bytes)); if (rcz_) return rcz_; } while (0)
+// several regions in ONE launch (every launch costs a few microseconds of an otherwise idle GPU)
+struct ZeroList { uint32_t* p[8]; unsigned long long words[8]; int n; };
+__global__ void __launch_bounds__(kThreads) k_zero_list(ZeroList L) {
+    for (int r = 0; r < L.n; ++r) {
+        uint32_t* dst = L.p[r];
+        const size_t n_words = L.words[r], stride = (size_t)gridDim.x * kThreads;
+        const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+        const size_t n4 = ((uintptr_t)dst % 16 == 0) ? n_words / 4 : 0;
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        for (size_t j = i; j < n4; j += stride) d4[j] = make_uint4(0u, 0u, 0u, 0u);
+        for (size_t j = n4 * 4 + i; j < n_words; j += stride) dst[j] = 0u;
+    }
+}
+struct ZeroBatch {
+    ZeroList L{};
+    size_t max_words = 0;
+    void add(void* p, size_t bytes) {
+        if (!bytes) return;
+        L.p[L.n] = reinterpret_cast<uint32_t*>(p); L.words[L.n] = (bytes + 3) / 4;
+        max_words = std::max<size_t>(max_words, L.words[L.n]);
+        ++L.n;
+    }
+};
+int zero_batch(o3r_ctx* ctx, const ZeroBatch& B) {
+    if (!B.L.n) return O3R_OK;
+    const uint32_t g = (uint32_t)std::min<size_t>((B.max_words / 4 + kThreads - 1) / kThreads + 1, 148 * 8);
+    LAUNCH(k_zero_list, g, kThreads, 0, B.L);
+    return O3R_OK;
+}
 inline size_t disp_elem(int t) { return t == O3R_DISP_U8 ? 1 : t == O3R_DISP_U16 ? 2 : t == O3R_DISP_F32 ? 4 : 8; }
 
 int read_counters(o3r_ctx* ctx) {

@@ -10,7 +10,8 @@ namespace {
 inline int bits_for(long long range) { int b = 0; while ((1ll << b) <= range) ++b; return b; }
 
 template <typename KeyT, typename Items>
-int acc_build_cycle_t(o3r_ctx* ctx, Items items, size_t n, bool use_resident, const KeyCodec& kc, int total_bits) {
+int acc_build_cycle_t(o3r_ctx* ctx, Items items, size_t n, bool use_resident, const KeyCodec& kc, int total_bits,
+                      const uint32_t* n_dev = nullptr) {
     const int passes = std::max(1, (total_bits + kRsMaxBits - 1) / kRsMaxBits);
     uint32_t* cnt = ctx->counters.as<uint32_t>();
     const size_t n4 = (n + 63) & ~(size_t)63;
@@ -24,8 +25,11 @@ int acc_build_cycle_t(o3r_ctx* ctx, Items items, size_t n, bool use_resident, co
     CU(ctx->seg2.ensure(16));
     CU(ctx->ghist.ensure(kMaxPasses * kRsBins * 4));
     CU(ctx->plan_v2.ensure(sizeof(SortPlan)));
-    const uint32_t seg_h[2] = {0u, (uint32_t)n};
-    { int rcu = upload_small(ctx, ctx->seg2.p, seg_h, 8); if (rcu) return rcu; }
+    if (!n_dev) {
+        const uint32_t seg_h[2] = {0u, (uint32_t)n};
+        int rcu = upload_small(ctx, ctx->seg2.p, seg_h, 8);
+        if (rcu) return rcu;
+    }   // (else k_acc_key writes the segment from the device-side count)
     ZERO(ctx->ghist.p, kMaxPasses * kRsBins * 4);
     ZERO(cnt + CNT_NEW, 4);
     const uint32_t* seg = ctx->seg2.as<uint32_t>();
@@ -33,7 +37,7 @@ int acc_build_cycle_t(o3r_ctx* ctx, Items items, size_t n, bool use_resident, co
     SortPlan* plan = ctx->plan_v2.as<SortPlan>();
     LAUNCH(k_rs_layout, 1, 32, 0, 1, (const GridParams*)nullptr, total_bits, plan);
     LAUNCH_N("k_acc_key", (k_acc_key<KeyT, Items>), gk, kThreads, 0, items, (uint32_t)n, ctx->inv_c, ctx->inv_cz, kc, plan,
-             k0, v0, ctx->ghist.as<uint32_t>());
+             k0, v0, ctx->ghist.as<uint32_t>(), n_dev, ctx->seg2.as<uint32_t>());
     LAUNCH(k_rs_plan, 1, kThreads, 0, ctx->ghist.as<uint32_t>(), seg, plan, (const GridParams*)nullptr);
     tr.mark("key+plan");
     int rc = sort_pairs<KeyT>(ctx, k0, k1, v0, v1, seg, 1, n, plan, passes, 0, ctx->ghist.as<uint32_t>());
@@ -117,6 +121,23 @@ int acc_build_cycle(o3r_ctx* ctx, const Items& items, size_t n, bool use_residen
     ctx->n_cyc_ub = (size_t)std::min((double)n, range_cells);
     if (total <= 32) return acc_build_cycle_t<uint32_t, Items>(ctx, items, n, use_resident, kc, total);
     return acc_build_cycle_t<uint64_t, Items>(ctx, items, n, use_resident, kc, total);
+}
+
+// The same with ABSOLUTE 63-bit cell keys: no cell range has to be known (nothing is read back), and the item count may live
+// on the device (n = the host's bound).  The radix plan skips the digits that are constant over the batch.
+template <typename Items>
+int acc_build_cycle_abs(o3r_ctx* ctx, const Items& items, size_t n, bool use_resident, const uint32_t* n_dev) {
+    ctx->n_cyc = 0;
+    ctx->n_cyc_ub = 0;
+    ctx->h_counters[CNT_CYC] = ctx->h_counters[CNT_NEW] = 0;
+    if (n == 0) return O3R_OK;
+    { int rc = refresh_nres(ctx, false); if (rc) return rc; }
+    if (n >= (1ull << 32)) return ctx->fail(O3R_ERR_INVALID, "batch too large for 32-bit indices");
+    KeyCodec kc;
+    kc.imin = kc.jmin = kc.kmin = -(1 << 20);
+    kc.wi = kc.wj = 21;
+    ctx->n_cyc_ub = n;
+    return acc_build_cycle_t<uint64_t, Items>(ctx, items, n, use_resident, kc, 63, n_dev);
 }
 
 // Applies the cycle's cell list to the resident shard: in-place update of found cells, sorted insert of new ones.

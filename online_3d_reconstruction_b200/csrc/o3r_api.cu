@@ -5,6 +5,7 @@
 #include "host_merge.cuh"
 #include "host_sor.cuh"
 #include "host_frames.cuh"
+#include "host_comm.cuh"
 
 
 // =====================================================================================================================
@@ -104,6 +105,12 @@ int o3r_create(const o3r_params* params, o3r_ctx** out_ctx) {
     }
     e = cudaFuncSetAttribute(k_bk_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_reduce_smem());
     if (e != cudaSuccess) return bail(e, "smem attr");
+    // the bucket kernels stage through shared memory and want their 4-5 CTAs per SM: largest carve-out
+    cudaFuncSetAttribute(k_bk_reduce, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_bk_scatter<O3R_DISP_U8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_bk_scatter<O3R_DISP_U16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_bk_scatter<O3R_DISP_F32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_bk_scatter<O3R_DISP_F64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (const char* v = getenv("O3R_BK_CTAS")) ctx->bk_reduce_ctas = std::max(1, atoi(v));
     const int bs = (int)blur_smem(kBlurMaxK, O3R_BLUR_MEDIAN);
     cudaFuncSetAttribute(k_blur<O3R_BLUR_MEDIAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bs);
@@ -118,6 +125,8 @@ void o3r_destroy(o3r_ctx* ctx) {
     if (ctx->st_copy2) cudaStreamSynchronize(ctx->st_copy2);
     if (ctx->st_copy) cudaStreamSynchronize(ctx->st_copy);
     if (ctx->st) cudaStreamSynchronize(ctx->st);
+    if (ctx->comm && ctx->comm_owned && nccl_api()->CommDestroy) nccl_api()->CommDestroy((ncclComm_t)ctx->comm);
+    ctx->comm = nullptr;
     for (auto& pf : ctx->prefetch) if (pf.ev) cudaEventDestroy(pf.ev);
     DevBuf* bufs[] = {&ctx->lut_r, &ctx->lut_z, &ctx->d_disp, &ctx->stg[0].disp, &ctx->stg[0].bgr, &ctx->stg[0].labels,
                       &ctx->stg[0].coef, &ctx->stg[0].kp, &ctx->stg[1].disp, &ctx->stg[1].bgr, &ctx->stg[1].labels,
@@ -129,7 +138,7 @@ void o3r_destroy(o3r_ctx* ctx) {
                       &ctx->vox_off, &ctx->seg2, &ctx->tmat, &ctx->mask, &ctx->runwork, &ctx->spts, &ctx->res_keys[0], &ctx->res_keys[1],
                       &ctx->res_acc[0], &ctx->res_acc[1], &ctx->res_rgb[0], &ctx->res_rgb[1], &ctx->ckey, &ctx->cacc,
                       &ctx->crgb, &ctx->partials, &ctx->pr_status, &ctx->bk_frames, &ctx->bk_counts, &ctx->bk_nl, &ctx->bk_pts, &ctx->bk_pos,
-                      &ctx->bk_status, &ctx->bk_misc, &ctx->bk_stray, &ctx->sor_hard, &ctx->sor_pts, &ctx->sor_off, &ctx->sor_dist, &ctx->sor_grids,
+                      &ctx->bk_status, &ctx->bk_misc, &ctx->bk_stray, &ctx->x_send, &ctx->x_recv, &ctx->x_list, &ctx->sor_hard, &ctx->sor_pts, &ctx->sor_off, &ctx->sor_dist, &ctx->sor_grids,
                       &ctx->sor_pgrids, &ctx->sor_rows, &ctx->sor_thr, &ctx->sor_skeys, &ctx->sor_svals, &ctx->sor_cnt, &ctx->sor_cntoff, &ctx->new_cnt, &ctx->new_off, &ctx->new_keys, &ctx->okeys, &ctx->cloud};
     for (DevBuf* b : bufs) b->release();
     for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -434,6 +443,11 @@ static int downsample_finish(o3r_ctx* ctx, size_t* m) {
     *m = ctx->h_counters[CNT_EMIT];
     ctx->n_res_ub = ctx->h_counters[CNT_NRES];
     ctx->n_res_exact = true;
+    if (ctx->x_pending_check) {   // the exchanges since the last read-back: did a slot overflow?
+        ctx->x_pending_check = false;
+        if (ctx->h_counters[CNT_XFLAG])
+            return ctx->fail(O3R_ERR_CAPACITY, "exchange slot overflow: cells were dropped; create the communicator with more slot_cells");
+    }
     return O3R_OK;
 }
 
@@ -648,6 +662,67 @@ int o3r_exchange_merge_bb(o3r_ctx* ctx, const o3r_cell* recv_dev, size_t n, cons
     return exchange_merge_impl(ctx, recv_dev, n, bb);
 }
 
+
+// ---- the exchange inside the library: communicator + one call per cycle --------------------------------------
+int o3r_comm_unique_id(void* id_out) {
+    if (!id_out) return O3R_ERR_INVALID;
+    NcclApi* N = nccl_api();
+    if (!N->err.empty()) { g_create_err = N->err; return O3R_ERR_CUDA; }
+    ncclUniqueId id;
+    if (N->GetUniqueId(&id) != ncclSuccess) { g_create_err = "ncclGetUniqueId failed"; return O3R_ERR_CUDA; }
+    memcpy(id_out, &id, sizeof(id));
+    return O3R_OK;
+}
+
+int o3r_comm_init(o3r_ctx* ctx, int world, int rank, const void* id, size_t slot_cells) {
+    if (!ctx || !id) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    NcclApi* N = nccl_api();
+    if (!N->err.empty()) return ctx->fail(O3R_ERR_CUDA, N->err);
+    if (ctx->comm) return ctx->fail(O3R_ERR_INVALID, "the context already has a communicator");
+    int rc = comm_setup(ctx, world, rank, slot_cells);
+    if (rc) return rc;
+    ZERO(ctx->counters.as<uint32_t>() + CNT_XFLAG, 8);
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    ncclComm_t c = nullptr;
+    NC(N->CommInitRank(&c, world, uid, rank));
+    ctx->comm = c; ctx->comm_owned = true;
+    return O3R_OK;
+}
+
+int o3r_comm_attach(o3r_ctx* ctx, void* nccl_comm, int world, int rank, size_t slot_cells) {
+    if (!ctx || !nccl_comm) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    NcclApi* N = nccl_api();
+    if (!N->err.empty()) return ctx->fail(O3R_ERR_CUDA, N->err);
+    if (ctx->comm) return ctx->fail(O3R_ERR_INVALID, "the context already has a communicator");
+    int rc = comm_setup(ctx, world, rank, slot_cells);
+    if (rc) return rc;
+    ZERO(ctx->counters.as<uint32_t>() + CNT_XFLAG, 8);
+    ctx->comm = nccl_comm; ctx->comm_owned = false;
+    return O3R_OK;
+}
+
+int o3r_comm_destroy(o3r_ctx* ctx) {
+    if (!ctx) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    CU(cudaStreamSynchronize(ctx->st));
+    NcclApi* N = nccl_api();
+    if (ctx->comm && ctx->comm_owned) NC(N->CommDestroy((ncclComm_t)ctx->comm));
+    ctx->comm = nullptr; ctx->comm_owned = false; ctx->world = 1; ctx->rank = 0;
+    return O3R_OK;
+}
+
+int o3r_exchange_cycle(o3r_ctx* ctx) {
+    if (!ctx) return O3R_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->p.device));
+    return exchange_cycle_impl(ctx);
+}
 
 // ---- pre-pass ---------------------------------------------------------------------------------------------
 namespace {

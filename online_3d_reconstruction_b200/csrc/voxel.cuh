@@ -554,8 +554,13 @@ __global__ void k_cellbb_init(int* cellbb) {
 template <typename KeyT, typename Items>
 __global__ void __launch_bounds__(kThreads) k_acc_key(Items items, uint32_t n, float ix, float iz, KeyCodec kc,
                                                       const SortPlan* __restrict__ plan, KeyT* __restrict__ keys,
-                                                      uint32_t* __restrict__ vals, uint32_t* __restrict__ ghist) {
+                                                      uint32_t* __restrict__ vals, uint32_t* __restrict__ ghist,
+                                                      const uint32_t* __restrict__ n_dev, uint32_t* __restrict__ seg_out) {
     __shared__ uint32_t sh[kMaxPasses * kRsBins];
+    if (n_dev) {   // the item count lives on the device (n is the host's bound); publish the segment for the sort
+        n = min(n, *n_dev);
+        if (blockIdx.x == 0 && threadIdx.x == 0) { seg_out[0] = 0u; seg_out[1] = n; }
+    }
     const int np = plan[0].n_passes;
     for (int i = threadIdx.x; i < np * kRsBins; i += kThreads) sh[i] = 0;
     __syncthreads();

@@ -18,6 +18,7 @@ SYMBOLS = [
     "o3r_cloud_clear",
     "o3r_voxel_grid", "o3r_blur_u8", "o3r_frame_mask", "o3r_disp_variance", "o3r_plane_fit", "o3r_sor", "o3r_last_batch_partials", "o3r_exchange_bound", "o3r_exchange_pack_dev", "o3r_exchange_merge_bb",
     "o3r_exchange_pack", "o3r_exchange_merge", "o3r_set_defer_merge", "o3r_set_keep_frame_voxels", "o3r_last_batch_engine",
+    "o3r_comm_unique_id", "o3r_comm_init", "o3r_comm_attach", "o3r_comm_destroy", "o3r_exchange_cycle",
     "o3r_launch_count", "o3r_stream", "o3r_sync", "o3r_profile", "o3r_profile_read",
 ]
 
@@ -81,6 +82,11 @@ def load():
     L.o3r_set_defer_merge.argtypes = [vp, C.c_int]
     L.o3r_set_keep_frame_voxels.argtypes = [vp, C.c_int]
     L.o3r_last_batch_engine.argtypes = [vp]
+    L.o3r_comm_unique_id.argtypes = [vp]
+    L.o3r_comm_init.argtypes = [vp, C.c_int, C.c_int, vp, sz]
+    L.o3r_comm_attach.argtypes = [vp, vp, C.c_int, C.c_int, sz]
+    L.o3r_comm_destroy.argtypes = [vp]
+    L.o3r_exchange_cycle.argtypes = [vp]
     L.o3r_launch_count.argtypes = [vp]
     L.o3r_launch_count.restype = C.c_uint64
     L.o3r_stream.argtypes = [vp]

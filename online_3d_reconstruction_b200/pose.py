@@ -237,6 +237,26 @@ class Pose:
         else:
             self._check(self._L.o3r_exchange_merge_bb(self._h, recv_ptr, n, (C.c_int * 6)(*[int(b) for b in bb])))
 
+    # the exchange inside the library (NCCL bound at run time): see include/o3r.h
+    @staticmethod
+    def commUniqueId():
+        """rank 0: the 128-byte NCCL id every rank passes to commInit (send it over any host channel)."""
+        buf = C.create_string_buffer(128)
+        rc = lib.load().o3r_comm_unique_id(buf)
+        if rc != 0:
+            raise lib.O3RError(rc, lib.load().o3r_last_error(None).decode())
+        return buf.raw
+
+    def commInit(self, world, rank, uid, slot_cells):
+        self._check(self._L.o3r_comm_init(self._h, world, rank, C.c_char_p(uid), slot_cells))
+
+    def commDestroy(self):
+        self._check(self._L.o3r_comm_destroy(self._h))
+
+    def exchangeCycle(self):
+        """Collective, asynchronous: partial cells of the last cycle -> owners (grouped ncclSend/ncclRecv) -> merge."""
+        self._check(self._L.o3r_exchange_cycle(self._h))
+
     def exchangeBound(self):
         return int(self._L.o3r_exchange_bound(self._h))
 
