@@ -34,12 +34,14 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 
 from online_3d_reconstruction_b200 import abi, synth  # noqa: E402
 
-# (workload, kernel) -> DRAM bytes per launch from `ncu --set full` (see profiles/r01*_ncu_*.txt)
+# (workload, kernel) -> dram__bytes_read.sum + dram__bytes_write.sum per launch, from the COMMITTED `ncu --set full` capture of
+# the same command (profiles/r02_ncu_full.txt) — a constant of that capture, not a property of this run (roofline.traffic_source)
 NCU_TRAFFIC = {
-    # profiles/r01n_ncu_full.txt: 7 launches per cycle (4 per-frame-index passes: 403.8, 554.8, 554.7, 551.9 MB;
-    # 3 passes over the tile partials: 25.7 MB each) -> mean per launch
-    ("config2_semidense_720p", "k_rs_onesweep_u32"): 306.0e6,
+    ("config2_semidense_720p", "k_bk_reduce"): 899.2e6,
+    ("config2_semidense_720p", "k_bk_scatter"): 1000.8e6,
+    ("config2_semidense_720p", "k_bk_hist"): 41.7e6,
 }
+NCU_TRAFFIC_SOURCE = "profiles/r02_ncu_full.txt (ncu --set full --clock-control none, cold caches, one launch each)"
 
 WORKLOADS = {
     # name: (rows, cols, disp_type, J, voxel_size, min_pts, dont_downsample, frames/step, seed, Q scale)
@@ -53,6 +55,11 @@ WORKLOADS = {
     "config2_semidense_720p_sor": (720, 1280, abi.DISP_U8, 1, 0.05, 1, False, 50, 1002, 1.0),
 }
 SOR_MEAN_K = {"config2_semidense_720p_sor": 50}
+# configs[1] with the reference's live blur (cv::bilateralFilter(k, 2k, k/2), README's --blur_kernel 30) / the median
+# north_star names (odd kernel) in front of the scan: row F of SURVEY 8a on the books
+WORKLOADS["config2_semidense_720p_blur30"] = WORKLOADS["config2_semidense_720p"]
+WORKLOADS["config2_semidense_720p_median31"] = WORKLOADS["config2_semidense_720p"]
+BLUR = {"config2_semidense_720p_blur30": (30, abi.BLUR_BILATERAL), "config2_semidense_720p_median31": (31, abi.BLUR_MEDIAN)}
 
 
 def peaks():
@@ -121,15 +128,31 @@ def make_data(wl, rank, world, n_steps_total):
 
 MERGE_MODES = {"fused": abi.MERGE_ACCUMULATE_FUSED, "tiled": abi.MERGE_ACCUMULATE_TILED, "accumulate": abi.MERGE_ACCUMULATE}
 MERGE_MODE = "fused"   # set from --merge-mode
+ENGINE_NAMES = {0: "sort", 1: "bucket", 2: "tile"}
 
 
 def params_for(wl, device, merge_mode=None):
     rows, cols, dt, J, v, mp, nd, F, seed, qs = WORKLOADS[wl]
     if merge_mode is None:
         merge_mode = MERGE_MODES[MERGE_MODE]
+    bk, bm = BLUR.get(wl, (1, abi.BLUR_MEDIAN))
     return abi.make_params(rows=rows, cols=cols, jump_pixels=J, voxel_size=v, min_points_per_voxel=mp,
                            dont_downsample=nd, Q=synth.q_scaled(qs), device=device, max_batch_frames=F,
-                           merge_mode=merge_mode, sor_mean_k=SOR_MEAN_K.get(wl, 0))
+                           merge_mode=merge_mode, sor_mean_k=SOR_MEAN_K.get(wl, 0), blur_kernel=bk, blur_mode=bm)
+
+
+def static_config(wl, world):
+    """The workload description both arms print (the driver compares the two config objects)."""
+    rows, cols, dt, J, v, mp, nd, F, seed, qs = WORKLOADS[wl]
+    bk, bm = BLUR.get(wl, (1, abi.BLUR_MEDIAN))
+    return {"workload": wl, "frames_per_step": F, "frames_per_step_is": "per GPU (weak scaling)", "frame": f"{cols}x{rows}",
+            "jump_pixels": J, "voxel_size": v, "min_points_per_voxel": mp, "dont_downsample": nd, "seq_len": F,
+            "blur_kernel": bk, "blur": {abi.BLUR_BILATERAL: "bilateral", abi.BLUR_MEDIAN: "median", abi.BLUR_BOX: "box"}[bm] if bk > 1 else "off",
+            "synthetic_seed": seed,
+            "l2": "inputs and intermediates of a step exceed the 126 MB L2 (184 MB of input planes per 50-frame 720p step)",
+            "sor": ("StatisticalOutlierRemoval(50, 1.0) applied per frame on both the GPU and the CPU side" if wl in SOR_MEAN_K
+                    else "north_star path: StatisticalOutlierRemoval not applied on either side (sor_mean_k = 0); "
+                         "--workload config2_semidense_720p_sor runs the reference's full per-frame composition")}
 
 
 def frames_array(disp_ptrs, disp_step, bgr_ptrs, bgr_step, Ts):
@@ -146,8 +169,10 @@ def frames_array(disp_ptrs, disp_step, bgr_ptrs, bgr_step, Ts):
 # n_valid = points after the mask, n_vox = per-frame voxels of the cycle, np1 / np2 = radix passes of the per-frame
 # index sort / the combined-grid key sort (7-8 bit digits: 28-bit index -> 4, 20-bit key -> 3).
 def algorithmic_bytes(wl, n_valid, n_vox, n_cells_cycle, bd, np1=4, np2=3, n_part=0):
-    """n_part = tile partial cells of the cycle (O3R_MERGE_ACCUMULATE_TILED): the merge then sorts and reduces those
-    40-byte records instead of the n_vox per-frame voxels."""
+    """n_part = tile partial cells of the cycle (O3R_MERGE_ACCUMULATE_TILED / _FUSED): the merge then sorts and reduces those
+    40-byte records instead of the n_vox per-frame voxels.  np1 = radix passes of the per-frame leaf-index sort that actually
+    ran (0 when the frame path is the bucket / tile engine or every frame is a PCL pass-through), np2 = passes of the
+    combined-grid key sort; the caller derives both from the launches the library counted, not from constants."""
     rows, cols, dt, J, v, mp, nd, F, seed, qs = WORKLOADS[wl]
     p = params_for(wl, 0)
     ny, nx = abi.scan_dims(p)
@@ -222,8 +247,6 @@ def run_ours(args, rank, world, local_rank):
     bd = disp[0].dtype.itemsize
     p = params_for(wl, local_rank)
     P = Pose(p)
-    if world > 1:
-        P.setDeferMerge(True)
     # inputs resident in HBM
     d_disp = [torch.from_numpy(a).to(dev) for a in disp]
     d_bgr = [torch.from_numpy(a).to(dev) for a in bgr]
@@ -238,17 +261,25 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.ExternalStream(P.stream(), device=dev)
     ny, nx = abi.scan_dims(p)
     cell_cap = F * ny * nx
-    send = torch.empty(cell_cap * abi.CELL.itemsize, dtype=torch.uint8, device=dev) if world > 1 else None
     out_pin = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()   # pinned result buffer of the e2e leg (grown if the cloud outgrows it)
     stats = {}
 
-    info = torch.zeros(world + 8, dtype=torch.int32, device=dev) if world > 1 else None
+    if world > 1:
+        # the library's own exchange (o3r_exchange_cycle: grouped ncclSend/ncclRecv of fixed-size slots inside libo3r.so).
+        # Slot size: twice what one rank sends to one owner in a cycle, from a probe cycle (the same on all ranks).
+        P.createCycleClouds(fr_dev[0], dt, device_pointers=True)
+        probe = max(P.lastCyclePartials(), 1) if P.lastCycleEngine() or P.lastCyclePartials() else int(F * ny * nx)
+        t = torch.tensor([probe], device=dev, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        slot_cells = int(2 * int(t.item()) // world + 4096)
+        P.clearCloud()
+        box = [Pose.commUniqueId() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, device=dev)
+        P.commInit(world, rank, box[0], slot_cells)
+        stats["exchange_slot_cells"] = slot_cells
 
     def exchange():
-        # hash-partitioned partial cells -> owners: pack on the GPU, all-gather of the headers (one host read), grouped
-        # ncclSend/ncclRecv, merge on the GPU — all queued on the context's stream
-        with torch.cuda.stream(stream):
-            stats["exchange_cells_sent"] = xchg.exchange_cycle(P, send, info)
+        P.exchangeCycle()
 
     def step(s, host):
         """One cycle (pose.cpp:361-434) + the combined downsample of the global cloud (pose.cpp:527-531 / :645).
@@ -338,7 +369,19 @@ def run_ours(args, rank, world, local_rank):
 
     n_valid = int(sum(int((a[p.bounding_box:rows - p.bounding_box, p.cols_start_aft_cutout:cols - p.bounding_box][::J, ::J].astype(np.float64)
                            / (p.disp_divisor if dt == abi.DISP_U16 else 1.0) > p.min_disparity).sum()) for a in disp))
-    alg = algorithmic_bytes(wl, n_valid, stats["n_vox"], max(new_cells_per_step, 1), bd, n_part=stats.get("n_part", 0))
+    # radix passes from the launches the library counted (a planned-out pass still launches and exits at once, so these are
+    # upper bounds of the passes that moved data): the per-frame leaf-index sort only exists in the sort engine
+    sort_launches = prof.get("k_rs_onesweep_u32", (0, 0.0))[0] / K
+    engine = stats.get("engine", 0)
+    np1 = 0 if engine else min(4, int(round(sort_launches)))
+    np2 = max(0, int(round(sort_launches)) - np1)
+    # sort engine: whether a launched pass moved data is decided on the device (k_rs_plan); only configs[1]'s plan is known
+    # here (28-bit leaf index -> 4 passes, 20-bit compact cell key -> 3), so the radix kernel gets a figure on that workload only
+    passes_known = bool(engine) or (v == 0.05 and rows == 720 and dt == abi.DISP_U8 and J == 1)
+    alg = algorithmic_bytes(wl, n_valid, stats["n_vox"], max(new_cells_per_step, 1), bd, np1=np1, np2=np2,
+                            n_part=stats.get("n_part", 0))
+    if not passes_known:
+        alg.pop("k_rs_onesweep_u32", None)
     peak, peak_src = peaks()
     kern = sorted(prof.items(), key=lambda kv: -kv[1][1])
     total_kernel_ms = sum(v[1] for v in prof.values())
@@ -360,6 +403,8 @@ def run_ours(args, rank, world, local_rank):
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
     # capture of this workload (profiles/), when one exists for this kernel
     roof["traffic"] = NCU_TRAFFIC.get((wl, top_name))
+    roof["traffic_source"] = NCU_TRAFFIC_SOURCE if roof["traffic"] is not None else None
+    roof["radix_passes_counted"] = {"per_frame_index_sort": np1, "combined_key_sort": np2}
     # whole-step view: compulsory bytes of the fused pipeline / step time
     ny, nx = abi.scan_dims(p)
     step_alg = F * (rows * cols * bd + 3 * ny * nx) + (16 * n_valid if nd else 20 * stats["n_vox"] + 2 * 32 * new_cells_per_step)
@@ -375,17 +420,13 @@ def run_ours(args, rank, world, local_rank):
         "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": {abi.DISP_U8: "u8", abi.DISP_U16: "u16", abi.DISP_F32: "f32"}[dt] + "->f64->f32",
         "data": "synthetic", "mpoints_per_sec": world * n_valid * K / (ms * 1e-3) / 1e6,
-        "config": {"workload": wl, "frames_per_step_per_gpu": F, "frame": f"{cols}x{rows}", "jump_pixels": J,
-                   "voxel_size": v, "min_points_per_voxel": mp, "dont_downsample": nd, "seq_len": F,
-                   "valid_points_per_step_per_gpu": n_valid, "per_frame_voxels_per_step_per_gpu": stats["n_vox"],
-                   "tile_partials_per_step_per_gpu": stats.get("n_part", 0), "merge_mode": "ACCUMULATE_" + MERGE_MODE.upper() if MERGE_MODE != "accumulate" else "ACCUMULATE",
-                   "engine": "bucket" if stats.get("engine") else "sort",
-                   "resident_cells_after_timed_region": cells_after_value,
-                   "l2": f"inputs ({F * (rows * cols * bd + rows * cols * 3) / 1e6:.0f} MB/step) and intermediates exceed the 126 MB L2",
-                   "sor": ("StatisticalOutlierRemoval(50, 1.0) applied per frame on both the GPU and the CPU side" if wl in SOR_MEAN_K
-                           else "north_star path: StatisticalOutlierRemoval not applied on either side (sor_mean_k = 0); "
-                                "--workload config2_semidense_720p_sor runs the reference's full per-frame composition"),
-                   "parallelism": f"frames f mod {world}; NCCL all-to-all of hash-partitioned cells" if world > 1 else "single GPU"},
+        "config": static_config(wl, world),
+        "run": {"valid_points_per_step_per_gpu": n_valid, "per_frame_voxels_per_step_per_gpu": stats["n_vox"],
+                "partial_cells_per_step_per_gpu": stats.get("n_part", 0),
+                "merge_mode": "ACCUMULATE_" + MERGE_MODE.upper() if MERGE_MODE != "accumulate" else "ACCUMULATE",
+                "engine": ENGINE_NAMES.get(stats.get("engine"), str(stats.get("engine"))),
+                "resident_cells_after_timed_region": cells_after_value,
+                "parallelism": f"frames f mod {world}; grouped ncclSend/ncclRecv of hash-partitioned cells inside libo3r.so" if world > 1 else "single GPU"},
         "clocks": clk, "wall_ms_per_step": wall / K,
         "e2e": {"value": frames_total / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": int(F * roi_px * (bd + 3)), "d2h_bytes_per_step": int(d2h),
@@ -395,9 +436,59 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches), "roofline": roof,
     }
     if world > 1:
-        res["config"]["exchange_cells_sent_last_step"] = stats.get("exchange_cells_sent")
+        res["run"]["exchange_slot_cells"] = stats.get("exchange_slot_cells")
     P.close()
+    if world == 1 and args.parity_steps > 0:
+        res["parity"] = parity_leg(wl, local_rank, fr_dev, disp, bgr, T, args.parity_steps)
     return res, (disp, bgr, T)
+
+
+def parity_leg(wl, device, fr_dev, disp, bgr, T, n_cycles):
+    """After the timed regions: the first n_cycles cycles of the SAME workload through a fresh context (device-resident inputs,
+    the mode that was timed) and through the CPU oracle (tests/oracle_binding.py, the checker), compared the way
+    tests/test_gpu_fused.py does: per-frame voxel counts, the combined cloud's cells / order / colours exactly, centroids
+    relative to where the sums live (z + 500)."""
+    import oracle_binding as ob
+    from online_3d_reconstruction_b200.pose import Pose
+    rows, cols, dt, J, v, mp, nd, F, seed, qs = WORKLOADS[wl]
+    p = params_for(wl, device)
+    threads = os.cpu_count() or 1
+    keep, cloud, n, counts_equal = [], None, 0, True
+    t0 = time.perf_counter()
+    with Pose(p) as P:
+        at = 0
+        for s in range(n_cycles):
+            frames = [abi.make_frame(disp[i], bgr[i], T[s][i], keep=keep) for i in range(F)]
+            at = n
+            cloud, n, counts = ob.run_cycle(p, frames, dt, threads, cloud, n)
+            got_counts = P.createCycleClouds(fr_dev[s], dt, device_pointers=True)
+            counts_equal = counts_equal and bool(np.array_equal(got_counts, counts))
+        if nd:   # --dont_downsample: the cloud itself, bit for bit
+            got = P.lastCyclePoints()
+            exp = cloud[at:n]
+        else:
+            got = P.downsamplePtCloud()
+            exp = ob.downsample_pt_cloud(p, cloud[:n], True)
+    out = {"checked_steps": n_cycles, "frames_checked": n_cycles * F, "against": "CPU oracle (oracle/o3r_oracle.cpp), same frames",
+           "per_frame_counts_equal": counts_equal, "records": int(len(got)), "records_equal": bool(len(got) == len(exp))}
+    if len(got) == len(exp):
+        inv = np.float32(1.0) / np.float32(v)
+        out["keys_equal"] = bool(nd or all(np.array_equal(np.floor(got[f] * inv), np.floor(exp[f] * inv)) for f in ("x", "y")))
+        out["colours_equal"] = bool(np.array_equal(got["rgb"], exp["rgb"]))
+        rel = 0.0
+        for f, shift in (("x", 0.0), ("y", 0.0), ("z", 500.0)):
+            a, b = got[f].astype(np.float64) + shift, exp[f].astype(np.float64) + shift
+            if len(a):
+                rel = max(rel, float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-3))))
+        out["max_centroid_rel"] = rel
+        out["bitwise_equal"] = bool(np.array_equal(got, exp))
+    # per-cell point counts are probed by tests/ through min_points_per_voxel = 1, 2, 5 (not visible in a cloud at min 1)
+    out["counts_equal"] = counts_equal and out.get("colours_equal", False)
+    out["seconds"] = round(time.perf_counter() - t0, 1)
+    return out
+
+
+CPU_PHASES = {}   # split of the last cpu_cycle call
 
 
 def cpu_cycle(wl, disp, bgr, Ts, threads):
@@ -409,9 +500,12 @@ def cpu_cycle(wl, disp, bgr, Ts, threads):
     frames = [abi.make_frame(disp[i], bgr[i], Ts[i], keep=keep) for i in range(len(Ts))]
     t0 = time.perf_counter()
     cloud, n, counts = ob.run_cycle(p, frames, dt, threads)
+    t1 = time.perf_counter()
     if not nd:
         ob.downsample_pt_cloud(p, cloud[:n], True)
-    return time.perf_counter() - t0
+    t2 = time.perf_counter()
+    CPU_PHASES["per_frame_path_s"], CPU_PHASES["combined_downsample_s"] = t1 - t0, t2 - t1
+    return t2 - t0
 
 
 def run_reference(args, rank, world):
@@ -434,8 +528,9 @@ def run_reference(args, rank, world):
     return {"impl": "reference", "metric": "frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": t / K * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8->f64->f32", "data": "synthetic",
-            "config": {"workload": wl, "frames_per_step": sample_frames, "note": "CPU port of the reference path "
-                       "(oracle/, g++ -O2; the reference was built with no -O flag); " + ("with SOR" if wl in SOR_MEAN_K else "no SOR")},
+            "config": static_config(wl, world),
+            "run": {"frames_per_cpu_step": sample_frames, "note": "CPU port of the reference path (oracle/, g++ -O2; the reference "
+                    "was built with no -O flag); " + ("with SOR" if wl in SOR_MEAN_K else "no SOR")},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                              "sample": f"{K} cycles of {sample_frames} frames + combined downsample each"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -459,9 +554,13 @@ def main():
     ap.add_argument("--cpu-baseline-frames", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--merge-mode", default="fused", choices=sorted(MERGE_MODES))
+    ap.add_argument("--parity-steps", type=int, default=-1,
+                    help="cycles compared with the CPU oracle after the timed regions (default 2; 1 at 4K; 0 = off)")
     args = ap.parse_args()
     global MERGE_MODE
     MERGE_MODE = args.merge_mode
+    if args.parity_steps < 0:
+        args.parity_steps = 1 if WORKLOADS[args.workload][0] > 1000 else 2
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -479,17 +578,20 @@ def main():
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     res, (disp, bgr, T) = run_ours(args, rank, world, local_rank)
     os.sched_setaffinity(0, allowed)
-    res["config"]["host_numa_binding"] = numa
+    res["run"]["host_numa_binding"] = numa
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         wl = args.workload
         n = min(len(disp), args.cpu_baseline_frames)
         threads = os.cpu_count() or 1
         cpu_cycle(wl, disp[:4], bgr[:4], T[0][:4], threads)  # warm
         t = cpu_cycle(wl, disp[:n], bgr[:n], T[args.warmup][:n], threads)
+        phases = {k: round(x, 3) for k, x in CPU_PHASES.items()}
+        phases["note"] = (f"per-frame path (pose.cpp:356-429) on {threads} threads; the combined downsample (pose.cpp:527-531) is one "
+                          "thread, as in the reference (a single pcl::VoxelGrid call)")
         n7 = min(n, 14)   # the reference's own fan-out is 7 boost::threads per batch (pose.cpp:392-413): two batches of 7
         t7 = cpu_cycle(wl, disp[:n7], bgr[:n7], T[args.warmup][:n7], 7) if wl not in SOR_MEAN_K else None
         res["cpu_baseline"] = {"value": n / t, "unit": "frames/s", "cores": threads, "kind": "port",
-                               "value_7_threads": (n7 / t7) if t7 else None,
+                               "value_7_threads": (n7 / t7) if t7 else None, "phases": phases,
                                "sample": f"1 cycle of {n} frames + combined downsample, {t:.2f} s, " + ("with SOR" if wl in SOR_MEAN_K else "no SOR")}
     if world > 1:
         import torch.distributed as dist
