@@ -151,7 +151,14 @@ struct o3r_ctx {
     DevBuf bk_frames, bk_counts, bk_nl, bk_pts, bk_pos, bk_status, bk_misc, bk_stray;
     int bk_reduce_ctas = 148 * 4;
     bool bucket_off = false;          // a batch overflowed the engine's limits: the sort engine serves this context from then on
-    bool last_bucketed = false;       // the last batch ran through the bucket engine (no per-frame clouds were materialised)
+    bool last_bucketed = false;       // the last batch ran through the bucket / tile engine (no per-frame clouds were materialised)
+    int last_engine = 0;              // 0 sort, 1 bucket, 2 tile
+    // FUSED mode, tile engine (tile.cuh): look-back words; flags / ticket / per-frame counts / pass-through guesses
+    DevBuf tv_status, tv_misc;
+    bool tv_off = false;              // a batch exceeded the engine's limits: the bucket / sort engine serve this context from then on
+    int tv_R = -1;                    // window radius in use (-1: not chosen yet)
+    int tv_guess = -1;                // PCL's overflow guard on the last frame seen (-1: none yet) = the guess for the next batch
+    uint32_t tv_attr = 0;             // k_tv instantiations whose shared-memory attribute is set
     // multi-GPU exchange inside the library (host_comm.cuh)
     void* comm = nullptr;             // ncclComm_t
     bool comm_owned = false;

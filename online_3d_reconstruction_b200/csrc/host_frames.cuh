@@ -5,6 +5,7 @@
 #include "host_merge.cuh"
 #include "host_sor.cuh"
 #include "host_bucket.cuh"
+#include "host_tile.cuh"
 
 namespace {
 
@@ -303,10 +304,25 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
     // The fused bucket engine (bucket.cuh) serves the merged path of O3R_MERGE_ACCUMULATE_FUSED; everything that needs the
     // per-frame clouds themselves (single-frame calls, masks, StatisticalOutlierRemoval) or that it cannot bound runs
     // through the sort engine, as does a batch on which the device raised one of its overflow flags (second attempt).
+    // Engines of the merged path, best first: the tile engine (tile.cuh: one kernel from the planes to the partial cells; dense
+    // scans of a rectified-stereo Q), the bucket engine (bucket.cuh: strided scans, keypoints), the sort engine (everything).
     BkPlan bkp;
-    bool use_bucket = ctx->fused() && P.want_keys && opt.merge && !opt.mask_only && !ctx->bucket_off &&
-                      !(p.sor_mean_k > 0 && J > 0) && bk_plan(ctx, frames, n, chunk, disp_type, label_mode, bkp);
-    if (trace && ctx->fused()) fprintf(stderr, "[o3r trace] fused: bucket engine %s (want_keys %d merge %d off %d canon %d)\n", use_bucket ? "on" : "off", P.want_keys, (int)opt.merge, (int)ctx->bucket_off, ctx->canon);
+    TvPlan tvp;
+    const bool fused_ok = ctx->fused() && P.want_keys && opt.merge && !opt.mask_only && !(p.sor_mean_k > 0 && J > 0);
+    bool use_tile = fused_ok && !ctx->tv_off && tv_plan(ctx, P, frames, n, tvp);
+    bool use_bucket = !use_tile && fused_ok && !ctx->bucket_off && bk_plan(ctx, frames, n, chunk, disp_type, label_mode, bkp);
+    std::vector<uint8_t> tv_guess;   // per frame: PCL's overflow guard as the tile kernel will assume it
+    int tv_R = 0;
+    if (use_tile) {
+        tv_guess.assign(n, (uint8_t)(ctx->tv_guess >= 0 ? ctx->tv_guess : (tvp.guess_pass ? 1 : 0)));
+        if (ctx->tv_R < 0) {   // smallest window that covers the nominal depth range (disparities up to 2 min_disparity)
+            const double w_need = std::fabs(p.Q[14] * 2.0 * p.min_disparity + p.Q[15]);
+            ctx->tv_R = kTvMaxR;
+            for (int r = 1; r <= kTvMaxR; ++r)
+                if (tvp.wlim(r) >= w_need) { ctx->tv_R = r; break; }
+        }
+    }
+    if (trace && ctx->fused()) fprintf(stderr, "[o3r trace] fused: engine %s (want_keys %d merge %d tile_off %d bucket_off %d canon %d vec %d R %d)\n", use_tile ? "tile" : use_bucket ? "bucket" : "sort", P.want_keys, (int)opt.merge, (int)ctx->tv_off, (int)ctx->bucket_off, ctx->canon, P.vec, ctx->tv_R);
     bool inputs_resident = false;   // second attempt: the staging buffers already hold every frame
     double tr1 = 0, tr2 = 0;
     for (;;) {
@@ -318,7 +334,17 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
         SortU32 sb{nullptr, nullptr, nullptr, nullptr};
         if (!opt.mask_only) {
             CU(ctx->vox_off.ensure((size_t)(n + 1) * 4));
-            if (use_bucket) {
+            if (use_tile) {
+                bool all_pass = true;
+                for (uint8_t g : tv_guess) all_pass = all_pass && g;
+                tv_R = all_pass ? 0 : ctx->tv_R;
+                int rc = tv_prepare(ctx, tvp, n, chunk, cap_batch, tv_guess);
+                if (rc) return rc;
+                if (ctx->keep_frame_voxels) CU(ctx->vox.ensure(cap_batch * 16));
+                LAUNCH(k_cellbb_init, 1, 32, 0, reinterpret_cast<int*>(cnt + CNT_CELLBB));
+                ZERO(cnt + CNT_PART, 8);
+                ctx->tiled_now = false;
+            } else if (use_bucket) {
                 int rc = bk_prepare(ctx, bkp, n, cap_batch, cap_chunk);
                 if (rc) return rc;
                 if (ctx->keep_frame_voxels) CU(ctx->vox.ensure(cap_batch * 16));
@@ -379,6 +405,16 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
                 }
             }
             int rc;
+            if (use_tile) {   // planes -> partial cells of the chunk, per-frame voxel counts, exact bboxes
+                switch (disp_type) {
+                    case O3R_DISP_U8: rc = tv_run_chunk<O3R_DISP_U8>(ctx, P, tvp, tv_R, f0, nc, n); break;
+                    case O3R_DISP_U16: rc = tv_run_chunk<O3R_DISP_U16>(ctx, P, tvp, tv_R, f0, nc, n); break;
+                    case O3R_DISP_F32: rc = tv_run_chunk<O3R_DISP_F32>(ctx, P, tvp, tv_R, f0, nc, n); break;
+                    default: rc = tv_run_chunk<O3R_DISP_F64>(ctx, P, tvp, tv_R, f0, nc, n); break;
+                }
+                if (rc) return rc;
+                continue;
+            }
             if (use_bucket) {   // hist -> scan -> scatter -> reduce: partial cells of the chunk, per-frame voxel counts
                 const int ci = f0 / chunk;
                 switch (disp_type) {
@@ -440,12 +476,18 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
         }
 
         // ---- per-frame output offsets (+ the combined-grid cell range) back to the host: the one sync of the frame path
-        if (ctx->h_offs_cap < (size_t)n + 3) {
+        const size_t offs_words = (size_t)n + 3 + ((size_t)n + 3) / 4 + 1;   // offsets / counts, two flag words, n flag bytes
+        if (ctx->h_offs_cap < offs_words) {
             if (ctx->h_offs) cudaFreeHost(ctx->h_offs);
-            ctx->h_offs_cap = std::max<size_t>(n + 3, 256);
+            ctx->h_offs_cap = std::max<size_t>(offs_words, 256);
             CU(cudaMallocHost((void**)&ctx->h_offs, ctx->h_offs_cap * 4));
         }
-        if (use_bucket) {   // per-frame voxel COUNTS (h_offs[1..n]) and the two overflow flag words (h_offs[n+1..n+2])
+        if (use_tile) {   // per-frame voxel COUNTS (h_offs[1..n]), the flag word (h_offs[n+1]), the guard's actual verdicts
+            const TvMisc M = tv_misc(ctx, n);
+            CU(cudaMemcpyAsync(ctx->h_offs + 1, M.fvox, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->st));
+            CU(cudaMemcpyAsync(ctx->h_offs + n + 1, M.flags, 4, cudaMemcpyDeviceToHost, ctx->st));
+            CU(cudaMemcpyAsync(ctx->h_offs + n + 3, M.actual, (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
+        } else if (use_bucket) {   // per-frame voxel COUNTS (h_offs[1..n]) and the two overflow flag words (h_offs[n+1..n+2])
             const BkMisc M = bk_misc(ctx, n);
             CU(cudaMemcpyAsync(ctx->h_offs + 1, M.fvox, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->st));
             CU(cudaMemcpyAsync(ctx->h_offs + n + 1, M.flags, 8, cudaMemcpyDeviceToHost, ctx->st));
@@ -461,12 +503,34 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
             int rcf = flush_deferred_prefetch(ctx);
             if (rcf) return rcf;
         }
-        ctx->last_has_partials = ctx->last_is_vox && ((ctx->tiled() && ctx->tiled_now) || use_bucket);
+        ctx->last_has_partials = ctx->last_is_vox && ((ctx->tiled() && ctx->tiled_now) || use_bucket || use_tile);
         if (ctx->last_has_partials)
             CU(cudaMemcpyAsync(ctx->h_counters + CNT_PART, cnt + CNT_PART, 4, cudaMemcpyDeviceToHost, ctx->st));
         tr1 = now();
         CU(cudaStreamSynchronize(ctx->st));
         tr2 = now();
+        if (use_tile) {
+            const uint32_t fl = ctx->h_offs[n + 1];
+            const uint8_t* actual = reinterpret_cast<const uint8_t*>(ctx->h_offs + n + 3);
+            if (fl) {
+                if (trace) fprintf(stderr, "[o3r trace] tile engine flags %u (R %d)\n", fl, tv_R);
+                inputs_resident = true;
+                bool retry = true;
+                if (fl & TV_FLAG_PASS) tv_guess.assign(actual, actual + n);   // the bboxes are exact: so is this
+                else if (fl & TV_FLAG_RANGE) {   // a disparity beyond the window's reach: widen it
+                    if (tv_R < kTvMaxR) ctx->tv_R = tv_R + 1; else retry = false;
+                }
+                if (!retry) {   // no window is wide enough: next engine
+                    ctx->tv_off = true;
+                    use_tile = false;
+                    use_bucket = !ctx->bucket_off && bk_plan(ctx, frames, n, chunk, disp_type, label_mode, bkp);
+                }
+                continue;
+            }
+            ctx->tv_guess = actual[n - 1];
+            ctx->h_offs[0] = 0;
+            for (int i = 0; i < n; ++i) ctx->h_offs[i + 1] += ctx->h_offs[i];
+        }
         if (use_bucket) {
             if (ctx->h_offs[n + 1] | ctx->h_offs[n + 2]) {   // a bucket too full / a point outside the grid bound: sort engine from now on
                 if (trace) fprintf(stderr, "[o3r trace] bucket engine overflow flags %u %u: falling back to the sort engine\n", ctx->h_offs[n + 1], ctx->h_offs[n + 2]);
@@ -480,12 +544,13 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
         }
         break;
     }
-    ctx->last_bucketed = use_bucket;
+    ctx->last_bucketed = use_bucket || use_tile;
+    ctx->last_engine = use_tile ? 2 : use_bucket ? 1 : 0;
     ctx->busy_set = -1;
     ctx->last_partials = ctx->last_has_partials ? ctx->h_counters[CNT_PART] : 0;
     // The tile pre-reduction pays only when it reduces: a 40-byte partial replaces a 16-byte voxel in the merge.  On grids
     // finer than the point spacing (e.g. 4K at voxel_size 0.01) nearly every voxel is its own cell: merge the voxels then.
-    if (ctx->last_has_partials && !use_bucket) {
+    if (ctx->last_has_partials && !use_bucket && !use_tile) {
         ctx->tiled_poor = ctx->last_partials * 2 > ctx->h_offs[n];
         if (ctx->tiled_poor) { ctx->last_has_partials = false; ctx->last_partials = 0; }
     }
@@ -499,7 +564,7 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
     const float4* outp = ctx->last_is_vox ? ctx->vox.as<float4>() : ctx->pts.as<float4>();
     if (ctx->retain()) return cloud_append_dev(ctx, outp, ctx->last_total);
     const int* bbp = ctx->last_has_cellbb ? ctx->last_cellbb : nullptr;
-    if (use_bucket && ctx->last_partials == 0) return O3R_OK;   // nothing valid in the whole batch
+    if ((use_bucket || use_tile) && ctx->last_partials == 0) return O3R_OK;   // nothing valid in the whole batch
     const int rcm = ctx->last_has_partials ? acc_merge_cells(ctx, ctx->partials.as<o3r_cell>(), ctx->last_partials, bbp)
                                            : acc_merge_points(ctx, outp, ctx->last_total, bbp);
     if (trace) fprintf(stderr, "[o3r trace] frames_cloud: enqueue %.3f ms, sync wait %.3f ms, merge enqueue %.3f ms\n", tr1 - tr0, tr2 - tr1, now() - tr2);

@@ -1,0 +1,150 @@
+// host_tile.cuh — host side of the fused tile engine (tile.cuh): the window bound, the pass-through guess, buffer sizing and
+// the launch sequence of one chunk of frames
+// (host side of libo3r.so; included by o3r_api.cu, one translation unit)
+#pragma once
+
+#include "host_bucket.cuh"
+#include "tile.cuh"
+
+namespace {
+
+struct TvPlan {
+    int ntx = 0, nty = 0;
+    size_t tiles_per_frame = 0;
+    double D = 0, S = 0;             // leaf diagonal (with float slop), worst sqrt(1 + t^2) / |q| of the scan region
+    bool guess_pass = false;         // the guard's verdict on a nominal frame (first batch of a context)
+    double wlim(int R) const { return (double)(R + 1) / (D * S); }
+};
+
+// Geometry of the tiling and of the window bound (tile.cuh, header).  false = the engine does not apply.
+bool tv_plan(const o3r_ctx* ctx, const AParams& P, const o3r_frame* frames, int n, TvPlan& pl) {
+    const o3r_params& p = ctx->p;
+    if (!ctx->canon || !P.vec || P.kp_tiles != 0 || P.J != 1 || P.nx <= 0 || P.ny <= 0) return false;
+    const double* Q = p.Q;
+    if (Q[0] == 0.0 || Q[5] == 0.0 || Q[11] == 0.0) return false;
+    pl.ntx = (P.nx + kTvW - 1) / kTvW;
+    pl.nty = (P.ny + kTvH - 1) / kTvH;
+    pl.tiles_per_frame = (size_t)pl.ntx * pl.nty;
+    const int xlo = P.x0, xhi = P.x0 + P.nx - 1, ylo = P.bb, yhi = P.bb + P.ny - 1;
+    const double tx = std::max(std::fabs(Q[0] * xlo + Q[3]), std::fabs(Q[0] * xhi + Q[3])) / std::fabs(Q[11]);
+    const double ty = std::max(std::fabs(Q[5] * ylo + Q[7]), std::fabs(Q[5] * yhi + Q[7])) / std::fabs(Q[11]);
+    pl.S = std::max(std::sqrt(1.0 + tx * tx) / std::fabs(Q[0]), std::sqrt(1.0 + ty * ty) / std::fabs(Q[5]));
+    // nominal depth range: disparities in (min_disparity, 2 min_disparity]
+    const double w_a = Q[14] * p.min_disparity + Q[15], w_b = Q[14] * 2.0 * p.min_disparity + Q[15];
+    if (!(w_a != 0.0) || !std::isfinite(w_a) || !std::isfinite(w_b) || (w_a > 0) != (w_b > 0)) return false;
+    const double s_a = 1.0 / w_a, s_b = 1.0 / w_b;
+    const double range = std::fabs(Q[11] * s_a) * std::sqrt(1.0 + tx * tx + ty * ty);
+    double tmax = 0;
+    for (int i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) tmax = std::max(tmax, (double)std::fabs(frames[i].T[4 * a + 3]));
+    if (!std::isfinite(tmax) || !std::isfinite(range)) return false;
+    // two points of one leaf are at most its diagonal apart; the float rounding of the transformed coordinates adds a few ulps
+    pl.D = std::sqrt(3.0) * (double)ctx->leaf_f * 1.001 + 16.0 * FLT_EPSILON * (tmax + range);
+    // the guard on a nominal frame: extents of the frustum slab, rotated by the first frame's matrix
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    const float* T = frames[0].T;
+    for (int c = 0; c < 8; ++c) {
+        const double s = (c & 1) ? s_a : s_b;
+        const double cam[3] = {(Q[0] * ((c & 2) ? xhi : xlo) + Q[3]) * s, (Q[5] * ((c & 4) ? yhi : ylo) + Q[7]) * s, Q[11] * s};
+        for (int a = 0; a < 3; ++a) {
+            const double w = (double)T[4 * a] * cam[0] + (double)T[4 * a + 1] * cam[1] + (double)T[4 * a + 2] * cam[2];
+            mn[a] = std::min(mn[a], w); mx[a] = std::max(mx[a], w);
+        }
+    }
+    double cells = 1;
+    for (int a = 0; a < 3; ++a) cells *= std::floor((mx[a] - mn[a]) * (double)ctx->inv_f) + 1.0;
+    pl.guess_pass = cells > 2147483647.0;
+    return true;
+}
+
+// misc layout (u32 words): [0] flags, [1] ticket, [2] debug voxel count, [3] spare, [16 .. 16 + n) per-frame voxel counts,
+// then n bytes of guessed and n bytes of actual pass-through flags
+struct TvMisc {
+    uint32_t *flags, *ticket, *dbg_cnt, *fvox;
+    uint8_t *guess, *actual;
+};
+TvMisc tv_misc(o3r_ctx* ctx, int n) {
+    uint32_t* m = ctx->tv_misc.as<uint32_t>();
+    uint8_t* b = reinterpret_cast<uint8_t*>(m + 16 + n);
+    return TvMisc{m, m + 1, m + 2, m + 16, b, b + n};
+}
+
+int tv_prepare(o3r_ctx* ctx, const TvPlan& pl, int n, int chunk, size_t cap_batch, const std::vector<uint8_t>& guess) {
+    const size_t tiles_chunk = pl.tiles_per_frame * (size_t)chunk, tiles_batch = pl.tiles_per_frame * (size_t)n;
+    CU(ctx->tv_status.ensure((tiles_chunk + 1) * 4));
+    CU(ctx->tv_misc.ensure((16 + (size_t)n) * 4 + 2 * (size_t)n + 16));
+    CU(ctx->bbox.ensure((size_t)n * 6 * 4));
+    // a tile emits at most one record per centroid (<= kTvItems), the batch at most one per sample
+    CU(ctx->partials.ensure(std::max<size_t>(std::min(tiles_batch * (size_t)kTvItems, cap_batch), 1) * sizeof(o3r_cell)));
+    const TvMisc M = tv_misc(ctx, n);
+    ZERO(M.flags, (16 + (size_t)n) * 4);
+    return upload_small(ctx, M.guess, guess.data(), (size_t)n);
+}
+
+template <int DT, int R>
+int tv_launch(o3r_ctx* ctx, const AParams& P, const TvArgs& A, uint32_t n_tiles) {
+    const uint32_t bit = 1u << (DT * (kTvMaxR + 1) + R);
+    if (!(ctx->tv_attr & bit)) {   // (the attribute is per function and device)
+        CU(cudaFuncSetAttribute(k_tv<DT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tv_smem<R>()));
+        cudaFuncSetAttribute(k_tv<DT, R>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        ctx->tv_attr |= bit;
+    }
+    LAUNCH_N("k_tv", (k_tv<DT, R>), n_tiles, kThreads, tv_smem<R>(), P, A);
+    return O3R_OK;
+}
+
+// one chunk of frames [f0, f0 + nc): the fused kernel + the guard check; partial cells are appended to ctx->partials at the
+// device-side base cnt[CNT_PART] (advanced here)
+template <int DT>
+int tv_run_chunk(o3r_ctx* ctx, const AParams& P, const TvPlan& pl, int R, int f0, int nc, int n) {
+    uint32_t* cnt = ctx->counters.as<uint32_t>();
+    const TvMisc M = tv_misc(ctx, n);
+    const uint32_t n_tiles = (uint32_t)(pl.tiles_per_frame * (size_t)nc);
+    {
+        ZeroBatch Z;
+        Z.add(ctx->tv_status.p, ((size_t)n_tiles + 1) * 4);
+        Z.add(M.ticket, 4);
+        Z.add(cnt + CNT_PARTCHUNK, 4);
+        int rcz = zero_batch(ctx, Z);
+        if (rcz) return rcz;
+    }
+    uint32_t* bbox = ctx->bbox.as<uint32_t>() + (size_t)f0 * 6;
+    LAUNCH(k_bbox_init, cdiv((size_t)nc * 6, kThreads), kThreads, 0, bbox, nc);
+    TvArgs A;
+    A.frames = ctx->d_frames.as<FrameDev>() + f0;
+    A.frame_pass = M.guess + f0;
+    A.ntx = pl.ntx; A.nty = pl.nty; A.n_frames = nc;
+    A.inv_f = ctx->inv_f; A.icx = ctx->inv_c; A.icz = ctx->inv_cz;
+    A.wlim = R > 0 ? pl.wlim(R) : INFINITY;
+    {   // the largest u8 disparity that keeps |q14 d + q15| below the bound
+        int dl = -1;
+        for (int d = 0; d < 256; ++d)
+            if (std::fabs(ctx->p.Q[14] * d + ctx->p.Q[15]) < A.wlim) dl = d; else if (dl >= 0) break;
+        A.dlim_i = dl;
+    }
+    A.out = ctx->partials.as<o3r_cell>();
+    A.out_base = cnt + CNT_PART;
+    A.chunk_total = cnt + CNT_PARTCHUNK;
+    A.status = ctx->tv_status.as<uint32_t>();
+    A.ticket = M.ticket;
+    A.frame_vox = M.fvox + f0;
+    A.bbox = bbox;
+    A.cellbb = reinterpret_cast<int*>(cnt + CNT_CELLBB);
+    A.flags = M.flags;
+    A.dbg_vox = ctx->keep_frame_voxels ? ctx->vox.as<float4>() : nullptr;
+    A.dbg_cnt = M.dbg_cnt;
+    int rc;
+    switch (R) {
+        case 0: rc = tv_launch<DT, 0>(ctx, P, A, n_tiles); break;
+        case 1: rc = tv_launch<DT, 1>(ctx, P, A, n_tiles); break;
+        case 2: rc = tv_launch<DT, 2>(ctx, P, A, n_tiles); break;
+        case 3: rc = tv_launch<DT, 3>(ctx, P, A, n_tiles); break;
+        default: rc = tv_launch<DT, 4>(ctx, P, A, n_tiles); break;
+    }
+    if (rc) return rc;
+    LAUNCH(k_tv_check, cdiv(nc, 64), 64, 0, nc, bbox, ctx->inv_f, M.guess + f0, M.actual + f0, M.flags);
+    LAUNCH(k_add_u32, 1, 32, 0, cnt + CNT_PART, cnt + CNT_PARTCHUNK);
+    return O3R_OK;
+}
+
+}  // namespace

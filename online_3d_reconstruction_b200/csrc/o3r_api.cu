@@ -138,7 +138,7 @@ void o3r_destroy(o3r_ctx* ctx) {
                       &ctx->vox_off, &ctx->seg2, &ctx->tmat, &ctx->mask, &ctx->runwork, &ctx->spts, &ctx->res_keys[0], &ctx->res_keys[1],
                       &ctx->res_acc[0], &ctx->res_acc[1], &ctx->res_rgb[0], &ctx->res_rgb[1], &ctx->ckey, &ctx->cacc,
                       &ctx->crgb, &ctx->partials, &ctx->pr_status, &ctx->bk_frames, &ctx->bk_counts, &ctx->bk_nl, &ctx->bk_pts, &ctx->bk_pos,
-                      &ctx->bk_status, &ctx->bk_misc, &ctx->bk_stray, &ctx->x_send, &ctx->x_recv, &ctx->x_list, &ctx->sor_hard, &ctx->sor_pts, &ctx->sor_off, &ctx->sor_dist, &ctx->sor_grids,
+                      &ctx->bk_status, &ctx->bk_misc, &ctx->bk_stray, &ctx->tv_status, &ctx->tv_misc, &ctx->x_send, &ctx->x_recv, &ctx->x_list, &ctx->sor_hard, &ctx->sor_pts, &ctx->sor_off, &ctx->sor_dist, &ctx->sor_grids,
                       &ctx->sor_pgrids, &ctx->sor_rows, &ctx->sor_thr, &ctx->sor_skeys, &ctx->sor_svals, &ctx->sor_cnt, &ctx->sor_cntoff, &ctx->new_cnt, &ctx->new_off, &ctx->new_keys, &ctx->okeys, &ctx->cloud};
     for (DevBuf* b : bufs) b->release();
     for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -157,7 +157,7 @@ void o3r_destroy(o3r_ctx* ctx) {
 
 uint64_t o3r_launch_count(const o3r_ctx* ctx) { return ctx ? ctx->launches : 0; }
 size_t o3r_last_batch_partials(const o3r_ctx* ctx) { return (ctx && ctx->last_has_partials) ? ctx->last_partials : 0; }
-int o3r_last_batch_engine(const o3r_ctx* ctx) { return (ctx && ctx->last_bucketed) ? 1 : 0; }
+int o3r_last_batch_engine(const o3r_ctx* ctx) { return ctx ? ctx->last_engine : 0; }
 void* o3r_stream(o3r_ctx* ctx) { return ctx ? (void*)ctx->st : nullptr; }
 
 int o3r_sync(o3r_ctx* ctx) {
@@ -336,7 +336,7 @@ int o3r_cloud_append(o3r_ctx* ctx, const o3r_point* pts, size_t n) {
     CU(ctx->vox.ensure(n * 16));
     CU(cudaMemcpyAsync(ctx->vox.p, pts, n * 16, cudaMemcpyHostToDevice, ctx->st));
     ctx->last_n = 0; ctx->last_total = 0; ctx->last_has_cellbb = false;   // the batch buffer was overwritten
-    ctx->last_has_partials = false; ctx->last_partials = 0; ctx->last_bucketed = false;
+    ctx->last_has_partials = false; ctx->last_partials = 0; ctx->last_bucketed = false; ctx->last_engine = 0;
     return acc_merge_points(ctx, ctx->vox.as<float4>(), n, nullptr);
 }
 

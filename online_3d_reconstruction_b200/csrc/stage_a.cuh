@@ -61,7 +61,8 @@ __device__ __forceinline__ double disp_scalar(const AParams& P, const FrameDev& 
 // cv::Mat_<double> 4x4 * 4x1 sums each row left to right; `/= w` multiplies by 1.0/w.  With the
 // rectified-stereo sparsity (q1=q2=q4=q6=q8=q9=q10=q12=q13=0) the zero products drop out exactly:
 //   v0 = q0*x + q3, v1 = q5*y + q7, v2 = q11, v3 = q14*d + q15.
-__device__ __forceinline__ void reproject(const AParams& P, int x, int y, double d, float& X, float& Y, float& Z) {
+// `w` receives the homogeneous coordinate v3 (its magnitude bounds the pixel footprint of a distance at that depth: tile.cuh)
+__device__ __forceinline__ void reproject_w(const AParams& P, int x, int y, double d, float& X, float& Y, float& Z, double& w) {
     const double dx = (double)x, dy = (double)y;
     double v0, v1, v2, v3;
     if (P.canon) {
@@ -79,6 +80,11 @@ __device__ __forceinline__ void reproject(const AParams& P, int x, int y, double
     X = __double2float_rn(__dmul_rn(v0, s));
     Y = __double2float_rn(__dmul_rn(v1, s));
     Z = __double2float_rn(__dmul_rn(v2, s));
+    w = v3;
+}
+__device__ __forceinline__ void reproject(const AParams& P, int x, int y, double d, float& X, float& Y, float& Z) {
+    double w;
+    reproject_w(P, x, y, d, X, Y, Z, w);
 }
 
 struct Samp {

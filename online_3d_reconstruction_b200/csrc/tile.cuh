@@ -1,0 +1,562 @@
+// tile.cuh — the fused tile engine of O3R_MERGE_ACCUMULATE_FUSED: ONE kernel from the disparity / colour planes to the
+// partial sums of the combined grid.
+//
+// What it replaces: createSingleImgPtCloud (pose_functions.cpp:1030-1134) + transformPtCloud (:1358-1362) +
+// downsamplePtCloud(cloud, false) (:1654-1709, pcl::VoxelGrid with leaf voxel_size / 5) + the append to cloud_big
+// (pose.cpp:434) of a whole cycle, up to the per-cell partial sums that the incremental merge (voxel.cuh engine 2) folds
+// into the resident shard — the dense scan (jump_pixels == 1, no keypoints) of a rectified-stereo Q.
+//
+// Why no sort and no binning pass: inside ONE frame all points come from one projection centre, so the points of a leaf
+// (a cube of edge voxel_size / 5) lie on rays that pass through that cube: they are pixels within a few columns and rows of
+// each other.  For two points with |P1 - P2| <= D (D = the leaf diagonal, rigid transforms keep distances) and
+// homogeneous coordinate w = q14 d + q15 (depth Z = q11 / w):
+//     |x1 - x2| = |q11 / q0| |X1/Z1 - X2/Z2| = |q11 / q0| |dX - t2 dZ| / |Z1| <= D |w1| sqrt(1 + t2^2) / |q0|,   t2 = X2 / Z2,
+// and the same in y.  With R = the largest integer below D |w| S (S = the worst sqrt(1 + t^2) / |q| of the scan region) every
+// leaf-mate of a pixel lies in its (2R+1) x (2R+1) pixel window.  The host picks R from that bound, and the kernel checks the
+// bound for every valid pixel it evaluates (|w| < wlim): a violation raises TV_FLAG_RANGE and the host reruns the batch
+// with a larger window, or through the bucket engine (bucket.cuh).
+//
+// One CTA per tile of 64 x 32 pixels (ticket order = frame, tile row, tile column):
+//   A  evaluate the tile plus a halo of R rows / 4 columns (validity, Q reprojection, rigid transform, colour, leaf cell):
+//      planes {cell hash, x, y, z, rgb} in shared memory; the exact PCL bbox of the frame (atomicMin / Max) on the side
+//   B  every core pixel compares the hashes of its window: an equal hash EARLIER in scan order (verified on the cell itself)
+//      means the pixel is not its leaf's first point; a first point left-folds its later window mates in scan order — the
+//      oracle's stable order, so the per-frame VoxelGrid centroid is bit-identical — and divides (pcl::CentroidPoint).
+//      A leaf belongs to the tile that holds its first point, and the halo shows that tile every mate.
+//   C  the centroids are celled on the combined grid (voxel_size, voxel_size, 1000 after z += 500); the tile's cells index
+//      a dense table (no hash), the centroids are counting-sorted by cell (warp match + warp-private counters: no atomics)
+//      and every cell is summed by four lanes in a fixed tree: one 40-byte partial cell per (tile, cell), written in cell
+//      order at an offset from a decoupled look-back over the tiles, so the partial list is reproducible bit for bit.
+//      (A tile whose cells span more than the table — a depth discontinuity, a grid finer than the pixels — writes every
+//      centroid as its own single-point record instead.)
+//
+// PCL's int32 overflow guard (output = input for a frame whose leaf grid has more than 2^31 cells) depends on the frame's
+// exact bbox, which only exists once every pixel has been evaluated: the kernel runs on the host's per-frame guess, computes
+// the bbox anyway, and k_tv_check compares the guard's verdict with the guess (TV_FLAG_PASS + the actual flags -> rerun).
+//
+// Contract = O3R_MERGE_ACCUMULATE_TILED's: per-frame centroids bit-exact, cells / counts / colour sums exact, combined
+// centroids equal to the oracle's single left fold within float reassociation (<= 1e-5 relative).
+#pragma once
+#include "bucket.cuh"
+#include "common.cuh"
+#include "sort.cuh"
+#include "stage_a.cuh"
+
+namespace o3r {
+
+constexpr int kTvW = 64, kTvH = 32;                    // core pixels of a tile
+constexpr int kTvGroupsRow = kTvW / 4;                 // 4-pixel groups per core row
+constexpr int kTvCoreGroups = kTvGroupsRow * kTvH;     // 512: two per thread
+constexpr int kTvQ = kTvCoreGroups / kThreads;         // core groups per thread
+constexpr int kTvItems = kTvW * kTvH;                  // centroids a tile can emit
+constexpr int kTvBins = 1024;                          // combined-grid cells a tile may touch (dense table)
+constexpr int kTvMaxR = 4;
+constexpr uint32_t kTvNoHash = 0xffffffffu;            // invalid pixel (valid hashes keep bit 31 clear)
+static_assert(kTvQ * kThreads == kTvCoreGroups, "core groups must divide evenly");
+
+enum { TV_FLAG_RANGE = 1u, TV_FLAG_PASS = 4u };
+
+template <int R>
+struct TvGeom {
+    static constexpr int HX = R ? 4 : 0, HY = R;       // halo columns stay a multiple of 4: aligned 4-pixel groups
+    static constexpr int NC = kTvW + 2 * HX, NR = kTvH + 2 * HY, N = NC * NR, NG = N / 4;
+    static constexpr int W = 2 * R + 1, S = R * W + R; // window width, index of the pixel itself
+    static constexpr size_t plane_bytes = (size_t)5 * N * 4 > (size_t)kTvItems * 16 ? (size_t)5 * N * 4 : (size_t)kTvItems * 16;
+};
+
+struct TvTail {
+    union {
+        uint16_t cnt[kWarps][kTvBins + 2];   // phase C: per warp and cell: count, then exclusive prefix over the warps
+        struct { double rl[256]; float zl[256]; } lut;   // phase A
+    } u;
+    uint32_t bd[kTvBins + 1];                // per cell: first item | rank among the non-empty cells << 16
+    uint32_t scan[34];
+    uint32_t ticket, out0, nb, nitems;
+    int cmin[3], cmax[3];
+    uint32_t bb[6];
+    uint32_t any_valid, bad;
+};
+template <int R>
+constexpr size_t tv_smem() { return TvGeom<R>::plane_bytes + sizeof(TvTail); }
+
+struct TvArgs {
+    const FrameDev* frames;
+    const uint8_t* frame_pass;     // the host's guess of PCL's overflow guard per frame
+    int ntx, nty, n_frames;
+    float inv_f, icx, icz;
+    double wlim;                   // |q14 d + q15| must stay below this for the window to hold every leaf-mate
+    int dlim_i;                    // the same bound as a u8 disparity (LUT path)
+    o3r_cell* out;
+    const uint32_t* out_base;
+    uint32_t* chunk_total;
+    uint32_t* status;
+    uint32_t* ticket;
+    uint32_t* frame_vox;
+    uint32_t* bbox;
+    int* cellbb;
+    uint32_t* flags;
+    float4* dbg_vox;
+    uint32_t* dbg_cnt;
+};
+
+__device__ __forceinline__ uint32_t tv_hash(int i, int j, int k) {
+    uint32_t h = (uint32_t)i * 0x9e3779b1u + (uint32_t)j * 0x85ebca77u + (uint32_t)k * 0xc2b2ae3du;
+    h ^= h >> 15;
+    return h & 0x7fffffffu;
+}
+
+// The thread's 4 consecutive pixels (xb .. xb + 3, y) of the dense scan: validity + camera-frame point, exactly the
+// arithmetic of eval4's vector branch (stage_a.cuh).  `over` is raised when a valid pixel breaks the window bound.
+template <int DT>
+__device__ __forceinline__ uint32_t tv_eval4(const AParams& P, const FrameDev& F, const double* rl, const float* zl, int xb, int y,
+                                             const TvArgs& A, float (&X)[4], float (&Y)[4], float (&Z)[4], bool& over) {
+    uint32_t mask = 0;
+    const uint8_t* row = F.disp + (size_t)y * F.disp_step;
+    if (DT == O3R_DISP_U8) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(row + xb);
+        if (P.use_lut) {
+            const double vy = __dadd_rn(__dmul_rn(P.q[5], (double)y), P.q[7]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int d = (w >> (8 * j)) & 255;
+                if (d > P.thr_i) {
+                    mask |= 1u << j;
+                    over = over || d > A.dlim_i;
+                    const double s = rl[d];
+                    const double v0 = __dadd_rn(__dmul_rn(P.q[0], (double)(xb + j)), P.q[3]);
+                    X[j] = __double2float_rn(__dmul_rn(v0, s));
+                    Y[j] = __double2float_rn(__dmul_rn(vy, s));
+                    Z[j] = zl[d];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int d = (w >> (8 * j)) & 255;
+                if (d > P.thr_i) {
+                    mask |= 1u << j;
+                    double hw;
+                    reproject_w(P, xb + j, y, (double)d, X[j], Y[j], Z[j], hw);
+                    over = over || !(fabs(hw) < A.wlim);
+                }
+            }
+        }
+    } else {
+        double dv[4];
+        if (DT == O3R_DISP_U16) {
+            const uint2 w = *reinterpret_cast<const uint2*>(row + 2 * (size_t)xb);
+            dv[0] = __ddiv_rn((double)(w.x & 0xffffu), P.div); dv[1] = __ddiv_rn((double)(w.x >> 16), P.div);
+            dv[2] = __ddiv_rn((double)(w.y & 0xffffu), P.div); dv[3] = __ddiv_rn((double)(w.y >> 16), P.div);
+        } else if (DT == O3R_DISP_F32) {
+            const float4 w = *reinterpret_cast<const float4*>(row + 4 * (size_t)xb);
+            dv[0] = (double)w.x; dv[1] = (double)w.y; dv[2] = (double)w.z; dv[3] = (double)w.w;
+        } else {
+            const double2 a = *reinterpret_cast<const double2*>(row + 8 * (size_t)xb);
+            const double2 b = *reinterpret_cast<const double2*>(row + 8 * (size_t)xb + 16);
+            dv[0] = a.x; dv[1] = a.y; dv[2] = b.x; dv[3] = b.y;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (dv[j] > P.min_disp) {
+                mask |= 1u << j;
+                double hw;
+                reproject_w(P, xb + j, y, dv[j], X[j], Y[j], Z[j], hw);
+                over = over || !(fabs(hw) < A.wlim);
+            }
+    }
+    return mask;
+}
+
+template <int R>
+struct TvMask { typedef uint32_t type; };
+template <>
+struct TvMask<4> { typedef unsigned long long type; };
+__device__ __forceinline__ int tv_ffs(uint32_t m) { return __ffs((int)m) - 1; }
+__device__ __forceinline__ int tv_ffs(unsigned long long m) { return __ffsll((long long)m) - 1; }
+
+// Where the tile's `nb` records go: decoupled look-back over the predecessors' counts, 32 tiles per step (warp 0; the caller
+// synchronises the CTA afterwards and reads *out0).  Every tile — also one without records — publishes its count.
+__device__ __forceinline__ uint32_t tv_lookback(const TvArgs& A, uint32_t t, uint32_t nt, uint32_t nb, uint32_t* out0, int warp,
+                                                int lane) {
+    uint32_t pf = 0;
+    if (warp == 0) {
+        if (lane == 0) st_volatile_u32(A.status + t, (t == 0 ? kStGlobal : kStLocal) | nb);
+        for (int32_t back = (int32_t)t - 1; back >= 0; back -= 32) {
+            const int32_t idx = back - lane;
+            uint32_t v = kStGlobal;
+            if (idx >= 0)
+                while (((v = ld_volatile_u32(A.status + idx)) >> 30) == 0u) __nanosleep(32);
+            const unsigned gm = __ballot_sync(kFull, (v >> 30) == 2u);
+            const int first = gm ? __ffs(gm) - 1 : 31;
+            pf += __reduce_add_sync(kFull, lane <= first ? (v & kStMask) : 0u);
+            if (gm) break;
+        }
+        if (lane == 0) {
+            if (t > 0) st_volatile_u32(A.status + t, kStGlobal | (pf + nb));
+            *out0 = pf;
+            if (t == nt - 1) *A.chunk_total = pf + nb;
+        }
+    }
+    return pf;
+}
+// range of combined-grid cells touched (the merge packs its sort keys into it)
+__device__ __forceinline__ void tv_cellbb(const TvArgs& A, const int* cmin, const int* cmax, int tid) {
+    if (tid < 6) {
+        int* gb = A.cellbb + tid;
+        const int v = tid < 3 ? cmin[tid] : cmax[tid - 3];
+        if (tid < 3) { if (v < *reinterpret_cast<volatile int*>(gb)) atomicMin(gb, v); }
+        else { if (v > *reinterpret_cast<volatile int*>(gb)) atomicMax(gb, v); }
+    }
+}
+
+template <int DT, int R>
+__global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvArgs A) {
+    typedef TvGeom<R> G;
+    typedef typename TvMask<R>::type M;
+    extern __shared__ __align__(16) unsigned char tv_smem_raw[];
+    uint32_t* const SH = reinterpret_cast<uint32_t*>(tv_smem_raw);       // planes: hash, x, y, z, rgb
+    float* const SX = reinterpret_cast<float*>(SH + G::N);
+    float* const SY = SX + G::N;
+    float* const SZ = SY + G::N;
+    uint32_t* const SC = reinterpret_cast<uint32_t*>(SZ + G::N);
+    float4* const items = reinterpret_cast<float4*>(tv_smem_raw);      // phase C: the tile's centroids in cell order (aliases the planes)
+    TvTail& S = *reinterpret_cast<TvTail*>(tv_smem_raw + G::plane_bytes);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+
+    if (tid == 0) { S.ticket = atomicAdd(A.ticket, 1u); S.any_valid = 0u; S.bad = 0u; }
+    if (tid < 3) { S.cmin[tid] = 0x7fffffff; S.cmax[tid] = (int)0x80000000; S.bb[tid] = 0xffffffffu; S.bb[3 + tid] = 0u; }
+    if (P.use_lut) { S.u.lut.rl[tid] = P.lut_r[tid]; S.u.lut.zl[tid] = P.lut_z[tid]; }
+    __syncthreads();
+    const uint32_t t = S.ticket;
+    const uint32_t per_frame = (uint32_t)(A.ntx * A.nty), nt = per_frame * (uint32_t)A.n_frames;
+    if (t >= nt) return;   // (uniform; the grid is exactly nt CTAs)
+    const int f = (int)(t / per_frame);
+    const int rem = (int)(t - (uint32_t)f * per_frame);
+    const int tyi = rem / A.ntx, txi = rem - tyi * A.ntx;
+    const FrameDev& F = A.frames[f];
+    const bool pass = A.frame_pass[f] != 0;
+    const int y_org = P.bb + tyi * kTvH - G::HY, x_org = P.x0 + txi * kTvW - G::HX;
+
+    // ---- A: evaluate core + halo into the planes -------------------------------------------------------------------------
+    {
+        uint32_t mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
+        bool over = false, anyv = false;
+        for (int g = tid; g < G::NG; g += kThreads) {
+            const int lr = g / (G::NC / 4), lc = (g - lr * (G::NC / 4)) * 4;
+            const int y = y_org + lr, xb = x_org + lc;
+            uint4 hh = make_uint4(kTvNoHash, kTvNoHash, kTvNoHash, kTvNoHash);
+            float px[4] = {0.f, 0.f, 0.f, 0.f}, py[4] = {0.f, 0.f, 0.f, 0.f}, pz[4] = {0.f, 0.f, 0.f, 0.f};
+            uint32_t rgb[4] = {0u, 0u, 0u, 0u};
+            if (y >= P.bb && y < P.bb + P.ny && xb >= P.x0 && xb < P.x0 + P.nx) {   // nx % 4 == 0: a group is inside or outside
+                float X[4], Y[4], Z[4];
+                const uint32_t mask = tv_eval4<DT>(P, F, S.u.lut.rl, S.u.lut.zl, xb, y, A, X, Y, Z, over);
+                if (mask) {
+                    const uint32_t* c = reinterpret_cast<const uint32_t*>(F.bgr + (size_t)y * F.bgr_step + 3 * (size_t)xb);
+                    const uint32_t w0 = __ldg(c), w1 = __ldg(c + 1), w2 = __ldg(c + 2);
+                    rgb[0] = w0 & 0x00ffffffu;
+                    rgb[1] = (w0 >> 24) | ((w1 & 0xffffu) << 8);
+                    rgb[2] = (w1 >> 16) | ((w2 & 0xffu) << 16);
+                    rgb[3] = w2 >> 8;
+                    const bool core = lr >= G::HY && lr < G::HY + kTvH && lc >= G::HX && lc < G::HX + kTvW;
+                    uint32_t h[4] = {kTvNoHash, kTvNoHash, kTvNoHash, kTvNoHash};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (mask & (1u << j)) {
+                            xform(F.T, X[j], Y[j], Z[j], px[j], py[j], pz[j]);
+                            int ci, cj, ck;
+                            bk_cell(px[j], py[j], pz[j], A.inv_f, ci, cj, ck);
+                            h[j] = tv_hash(ci, cj, ck);
+                            if (core) {
+                                const uint32_t ox = f2ord(px[j]), oy = f2ord(py[j]), oz = f2ord(pz[j]);
+                                mn[0] = min(mn[0], ox); mx[0] = max(mx[0], ox);
+                                mn[1] = min(mn[1], oy); mx[1] = max(mx[1], oy);
+                                mn[2] = min(mn[2], oz); mx[2] = max(mx[2], oz);
+                                anyv = true;
+                            }
+                        }
+                    hh = make_uint4(h[0], h[1], h[2], h[3]);
+                }
+            }
+            const int o = lr * G::NC + lc;
+            *reinterpret_cast<uint4*>(SH + o) = hh;
+            *reinterpret_cast<float4*>(SX + o) = make_float4(px[0], px[1], px[2], px[3]);
+            *reinterpret_cast<float4*>(SY + o) = make_float4(py[0], py[1], py[2], py[3]);
+            *reinterpret_cast<float4*>(SZ + o) = make_float4(pz[0], pz[1], pz[2], pz[3]);
+            *reinterpret_cast<uint4*>(SC + o) = make_uint4(rgb[0], rgb[1], rgb[2], rgb[3]);
+        }
+        // the frame's exact bbox (PCL getMinMax3D) from the core pixels: every pixel is core in exactly one tile
+        const unsigned anyw = __ballot_sync(kFull, anyv);
+        if (anyw) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                mn[a] = __reduce_min_sync(kFull, mn[a]);
+                mx[a] = __reduce_max_sync(kFull, mx[a]);
+            }
+            if (lane == 0) {
+                S.any_valid = 1u;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { atomicMin(&S.bb[a], mn[a]); atomicMax(&S.bb[3 + a], mx[a]); }
+            }
+        }
+        if (over && !pass) S.bad = 1u;   // (a pass-through frame has no window to break)
+    }
+    __syncthreads();
+    if (S.any_valid && tid < 6) {
+        uint32_t* gb = A.bbox + (size_t)f * 6 + tid;
+        const uint32_t v = S.bb[tid];
+        if (tid < 3) { if (v < *reinterpret_cast<volatile uint32_t*>(gb)) atomicMin(gb, v); }
+        else { if (v > *reinterpret_cast<volatile uint32_t*>(gb)) atomicMax(gb, v); }
+    }
+    if (tid == 0 && S.bad) atomicOr(A.flags, TV_FLAG_RANGE);
+
+    // ---- B: first points of the leaves fold their window mates in scan order -----------------------------------------------
+    float4 cen[kTvQ * 4];
+    uint32_t cvalid = 0;
+    int cmn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, cmx[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+#pragma unroll
+    for (int q = 0; q < kTvQ; ++q) {
+        const int g = tid + q * kThreads;
+        const int cr = g / kTvGroupsRow, cg = g - cr * kTvGroupsRow;
+        const int lr = cr + G::HY, lc = cg * 4 + G::HX;
+        const int o = lr * G::NC + lc;
+        const uint4 h4 = *reinterpret_cast<const uint4*>(SH + o);
+        const uint32_t h[4] = {h4.x, h4.y, h4.z, h4.w};
+        M me[4] = {0, 0, 0, 0}, ml[4] = {0, 0, 0, 0};
+        if (R > 0 && !pass && (h4.x & h4.y & h4.z & h4.w) != kTvNoHash) {
+#pragma unroll
+            for (int dr = -R; dr <= R; ++dr) {
+                const uint32_t* hr = SH + (lr + dr) * G::NC + lc - 4;
+                const uint4 a = *reinterpret_cast<const uint4*>(hr), b = *reinterpret_cast<const uint4*>(hr + 4),
+                            c = *reinterpret_cast<const uint4*>(hr + 8);
+                const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int dc = -R; dc <= R; ++dc) {
+                        const int idx = (dr + R) * G::W + (dc + R);
+                        if (idx == G::S) continue;
+                        if (w[4 + j + dc] == h[j]) {
+                            if (idx < G::S) me[j] |= (M)1 << idx;
+                            else ml[j] |= (M)1 << (idx - G::S - 1);
+                        }
+                    }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (h[j] == kTvNoHash) continue;
+            const int oc = o + j;
+            float4 p = make_float4(SX[oc], SY[oc], SZ[oc], __uint_as_float(SC[oc]));
+            float4 c = p;
+            if (R > 0 && !pass) {
+                int ci, cj, ck;
+                bk_cell(p.x, p.y, p.z, A.inv_f, ci, cj, ck);
+                bool head = true;
+                M e = me[j];
+                while (e) {   // an equal hash earlier in scan order: the leaf's first point lies there if the cell really is the same
+                    const int idx = tv_ffs(e);
+                    e &= e - 1;
+                    const int dr = idx / G::W - R, dc = idx - (idx / G::W) * G::W - R;
+                    const int on = oc + dr * G::NC + dc;
+                    int ni, nj, nk;
+                    bk_cell(SX[on], SY[on], SZ[on], A.inv_f, ni, nj, nk);
+                    if (ni == ci && nj == cj && nk == ck) { head = false; break; }
+                }
+                if (!head) continue;
+                M l = ml[j];
+                if (l) {
+                    float sx = __fadd_rn(0.f, p.x), sy = __fadd_rn(0.f, p.y), sz = __fadd_rn(0.f, p.z);   // (the oracle's sums start at +0)
+                    uint32_t w = __float_as_uint(p.w);
+                    uint32_t cn = 1, r = (w >> 16) & 255u, gg = (w >> 8) & 255u, bb = w & 255u;
+                    while (l) {
+                        const int idx = tv_ffs(l) + G::S + 1;
+                        l &= l - 1;
+                        const int dr = idx / G::W - R, dc = idx - (idx / G::W) * G::W - R;
+                        const int on = oc + dr * G::NC + dc;
+                        const float nx = SX[on], ny = SY[on], nz = SZ[on];
+                        int ni, nj, nk;
+                        bk_cell(nx, ny, nz, A.inv_f, ni, nj, nk);
+                        if (ni == ci && nj == cj && nk == ck) {
+                            sx = __fadd_rn(sx, nx); sy = __fadd_rn(sy, ny); sz = __fadd_rn(sz, nz);
+                            w = SC[on];
+                            r += (w >> 16) & 255u; gg += (w >> 8) & 255u; bb += w & 255u;
+                            ++cn;
+                        }
+                    }
+                    c = bk_centroid(sx, sy, sz, cn, r, gg, bb);
+                } else {
+                    const uint32_t w = __float_as_uint(p.w);
+                    c = bk_centroid(p.x, p.y, p.z, 1u, (w >> 16) & 255u, (w >> 8) & 255u, w & 255u);
+                }
+            }
+            if (A.dbg_vox) A.dbg_vox[atomicAdd(A.dbg_cnt, 1u)] = c;
+            c.z = __fadd_rn(c.z, 500.0f);   // pose_functions.cpp:1666
+            const int vi = (int)floorf(__fmul_rn(c.x, A.icx)), vj = (int)floorf(__fmul_rn(c.y, A.icx)),
+                      vk = (int)floorf(__fmul_rn(c.z, A.icz));
+            cmn[0] = min(cmn[0], vi); cmx[0] = max(cmx[0], vi);
+            cmn[1] = min(cmn[1], vj); cmx[1] = max(cmx[1], vj);
+            cmn[2] = min(cmn[2], vk); cmx[2] = max(cmx[2], vk);
+            cen[q * 4 + j] = c;
+            cvalid |= 1u << (q * 4 + j);
+        }
+    }
+    // ---- C: the tile's cells -------------------------------------------------------------------------------------------
+    {
+        const unsigned anyc = __ballot_sync(kFull, cvalid != 0u);
+        if (anyc) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                cmn[a] = __reduce_min_sync(kFull, cmn[a]);
+                cmx[a] = __reduce_max_sync(kFull, cmx[a]);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { atomicMin(&S.cmin[a], cmn[a]); atomicMax(&S.cmax[a], cmx[a]); }
+            }
+        }
+    }
+    __syncthreads();   // (the planes are dead from here on; the LUT as well)
+    const bool have = S.cmin[0] != 0x7fffffff;
+    const int c0i = S.cmin[0], c0j = S.cmin[1], c0k = S.cmin[2];
+    const long long ei = have ? (long long)S.cmax[0] - c0i + 1 : 0, ej = have ? (long long)S.cmax[1] - c0j + 1 : 0,
+                    ek = have ? (long long)S.cmax[2] - c0k + 1 : 0;
+    const bool fits = ei * ej * ek <= (long long)kTvBins && ei <= kTvBins && ej <= kTvBins && ek <= kTvBins;
+    const int nbins = fits ? (int)(ei * ej * ek) : 0;
+    const int Bi = 1 << 20;
+    if (!fits) {
+        // The tile's cells span more than the dense table holds (a depth discontinuity inside the tile, or a combined grid
+        // finer than the pixel footprint): every centroid leaves as its own single-point record, in tile order (thread, slot).
+        uint32_t tot;
+        uint32_t pos = block_excl_scan((uint32_t)__popc(cvalid), S.scan, tot);
+        const uint32_t pf = tv_lookback(A, t, nt, tot, &S.out0, warp, lane);
+        (void)pf;
+        __syncthreads();
+        if (tot == 0) return;
+        if (tid == 0) atomicAdd(A.frame_vox + f, tot);
+        tv_cellbb(A, S.cmin, S.cmax, tid);
+        o3r_cell* const out = A.out + *A.out_base + S.out0;
+#pragma unroll
+        for (int r = 0; r < kTvQ * 4; ++r)
+            if ((cvalid >> r) & 1u) {
+                const float4 p = cen[r];
+                const int vi = (int)floorf(__fmul_rn(p.x, A.icx)), vj = (int)floorf(__fmul_rn(p.y, A.icx)),
+                          vk = (int)floorf(__fmul_rn(p.z, A.icz));
+                const uint32_t w = __float_as_uint(p.w);
+                o3r_cell c;
+                c.key = ((unsigned long long)(uint32_t)(vk + Bi) << 42) | ((unsigned long long)(uint32_t)(vj + Bi) << 21) |
+                        (unsigned long long)(uint32_t)(vi + Bi);
+                c.sx = p.x; c.sy = p.y; c.sz = p.z; c.n = 1u;
+                c.sr = (w >> 16) & 255u; c.sg = (w >> 8) & 255u; c.sb = w & 255u; c.pad = 0u;
+                out[pos++] = c;
+            }
+        return;
+    }
+    for (int b = tid; b < (nbins + 2) * kWarps; b += kThreads) {
+        const int w = b / (nbins + 2), i = b - w * (nbins + 2);
+        S.u.cnt[w][i == nbins + 1 ? kTvBins + 1 : i] = 0;
+    }
+    __syncthreads();
+    // stable rank of every centroid inside its cell (tile order = warp, slot, lane); lanes without a centroid share the
+    // stand-in cell kTvBins + 1
+    uint32_t bin[kTvQ * 4], rk[kTvQ * 4];
+    uint16_t* wc = &S.u.cnt[warp][0];
+#pragma unroll
+    for (int r = 0; r < kTvQ * 4; ++r) {
+        const bool valid = (cvalid >> r) & 1u;
+        bin[r] = (uint32_t)(kTvBins + 1);
+        if (valid) {
+            const int vi = (int)floorf(__fmul_rn(cen[r].x, A.icx)), vj = (int)floorf(__fmul_rn(cen[r].y, A.icx)),
+                      vk = (int)floorf(__fmul_rn(cen[r].z, A.icz));
+            bin[r] = (uint32_t)(((vk - c0k) * (int)ej + (vj - c0j)) * (int)ei + (vi - c0i));
+        }
+        const unsigned peers = __match_any_sync(kFull, bin[r]);
+        const uint32_t old = wc[bin[r]];
+        __syncwarp();
+        if ((peers & lt) == 0u) wc[bin[r]] = (uint16_t)(old + __popc(peers));
+        __syncwarp();
+        rk[r] = old + __popc(peers & lt);
+    }
+    __syncthreads();
+    // per cell: exclusive prefix over the warps; then first item / rank among the non-empty cells (packed scan)
+    {
+        uint32_t run[4], psum = 0;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+            const int b = tid * 4 + qq;
+            uint32_t acc = 0;
+            if (b < nbins) {
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) { const uint32_t c = S.u.cnt[w][b]; S.u.cnt[w][b] = (uint16_t)acc; acc += c; }
+            }
+            run[qq] = acc | (acc ? 1u << 16 : 0u);
+            psum += run[qq];
+        }
+        uint32_t tot;
+        uint32_t ds = block_excl_scan(psum, S.scan, tot);
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+            const int b = tid * 4 + qq;
+            if (b < nbins) S.bd[b] = ds;
+            ds += run[qq];
+        }
+        if (tid == 0) { S.bd[nbins] = tot; S.nitems = tot & 0xffffu; S.nb = tot >> 16; }
+    }
+    __syncthreads();
+    const uint32_t nb = S.nb;
+#pragma unroll
+    for (int r = 0; r < kTvQ * 4; ++r)
+        if ((cvalid >> r) & 1u) items[(S.bd[bin[r]] & 0xffffu) + (uint32_t)wc[bin[r]] + rk[r]] = cen[r];
+    tv_lookback(A, t, nt, nb, &S.out0, warp, lane);
+    __syncthreads();
+    if (nb == 0) return;
+    if (tid == 0) atomicAdd(A.frame_vox + f, S.nitems);
+    tv_cellbb(A, S.cmin, S.cmax, tid);
+    o3r_cell* const out = A.out + *A.out_base + S.out0;
+    // four lanes per cell: lane s left-folds items s, s + 4, ... of the cell, then (s0 + s1) + (s2 + s3): a fixed tree
+    for (int b0 = warp * 8; b0 < nbins; b0 += kWarps * 8) {
+        const int b = b0 + (lane >> 2), sub = lane & 3;
+        uint32_t a = 0, e = 0, dense = 0;
+        if (b < nbins) {
+            const uint32_t v0 = S.bd[b], v1 = S.bd[b + 1];
+            a = v0 & 0xffffu; e = v1 & 0xffffu; dense = v0 >> 16;
+        }
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        uint32_t cr = 0, cg = 0, cb = 0;
+        for (uint32_t i = a + sub; i < e; i += 4) {
+            const float4 p = items[i];
+            sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z);
+            const uint32_t w = __float_as_uint(p.w);
+            cr += (w >> 16) & 255u; cg += (w >> 8) & 255u; cb += w & 255u;
+        }
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            sx = __fadd_rn(sx, __shfl_xor_sync(kFull, sx, o));
+            sy = __fadd_rn(sy, __shfl_xor_sync(kFull, sy, o));
+            sz = __fadd_rn(sz, __shfl_xor_sync(kFull, sz, o));
+            cr += __shfl_xor_sync(kFull, cr, o); cg += __shfl_xor_sync(kFull, cg, o); cb += __shfl_xor_sync(kFull, cb, o);
+        }
+        if (sub == 0 && e > a) {
+            const int vi = c0i + b % (int)ei, vj = c0j + (b / (int)ei) % (int)ej, vk = c0k + b / (int)(ei * ej);
+            o3r_cell c;
+            c.key = ((unsigned long long)(uint32_t)(vk + Bi) << 42) | ((unsigned long long)(uint32_t)(vj + Bi) << 21) |
+                    (unsigned long long)(uint32_t)(vi + Bi);
+            c.sx = sx; c.sy = sy; c.sz = sz; c.n = e - a;
+            c.sr = cr; c.sg = cg; c.sb = cb; c.pad = 0u;
+            out[dense] = c;
+        }
+    }
+}
+
+// per frame: PCL's int32 overflow guard on the exact bbox against the guess the kernel ran on
+__global__ void k_tv_check(int n_frames, const uint32_t* __restrict__ bbox, float inv_f, const uint8_t* __restrict__ guess,
+                           uint8_t* __restrict__ actual, uint32_t* __restrict__ flags) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    const GridParams G = make_grid(bbox + 6 * f, inv_f, inv_f, inv_f);
+    const uint8_t a = (uint8_t)(G.passthrough ? 1 : 0);
+    actual[f] = G.empty ? guess[f] : a;   // a frame without points has nothing to get wrong
+    if (!G.empty && a != guess[f]) atomicOr(flags, TV_FLAG_PASS);
+}
+
+}  // namespace o3r

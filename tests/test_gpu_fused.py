@@ -1,5 +1,7 @@
-"""GPU parity of O3R_MERGE_ACCUMULATE_FUSED (csrc/bucket.cuh, the mode bench.py times) against the CPU oracle, through
-the C-ABI, from small ragged cases up to BASELINE.json's configs at full size.
+"""GPU parity of O3R_MERGE_ACCUMULATE_FUSED (the mode bench.py times) against the CPU oracle, through the C-ABI, from small
+ragged cases up to BASELINE.json's configs at full size.  Three engines serve the mode (o3r_last_batch_engine): the tile
+engine (csrc/tile.cuh: dense scans of a rectified-stereo Q), the bucket engine (csrc/bucket.cuh: strided scans, keypoints,
+geometries without aligned rows, leaves wider than the tile engine's pixel window) and the sort engine (everything else).
 
 Contract (include/o3r.h): per-frame VoxelGrid centroids bit-identical to the oracle's (checked as a multiset through the
 keep-frame-voxels probe, because the fused engine never materialises the per-frame clouds in order), per-frame voxel
@@ -17,6 +19,7 @@ from test_gpu_parity import SMALL, SMALL4, _close, _eq, _frames
 pytestmark = pytest.mark.gpu
 
 FUSED = abi.MERGE_ACCUMULATE_FUSED
+SORT, BUCKET, TILE = 0, 1, 2
 
 
 def _multiset(a):
@@ -25,7 +28,7 @@ def _multiset(a):
     return v[np.lexsort((v[:, 3], v[:, 2], v[:, 1], v[:, 0]))]
 
 
-def _run_cycles(p, cycles, disp_type=abi.DISP_U8, expect_engine=1, probe=True, threads=4):
+def _run_cycles(p, cycles, disp_type=abi.DISP_U8, expect_engine=TILE, probe=True, threads=4):
     """Oracle and GPU over the same cycles -> (got combined cloud, expected combined cloud)."""
     cloud, n = None, 0
     with Pose(p) as P:
@@ -58,7 +61,7 @@ def test_fused_three_cycles_small(min_pts, geom):
     cycles = [_frames(240, 4, geom["rows"], geom["cols"], keep=keep, traj_start=0),
               _frames(241, 3, geom["rows"], geom["cols"], keep=keep, traj_start=4),
               _frames(242, 4, geom["rows"], geom["cols"], keep=keep, traj_start=5)]
-    got, exp = _run_cycles(p, cycles)
+    got, exp = _run_cycles(p, cycles, expect_engine=TILE if geom is SMALL4 else BUCKET)   # SMALL: rows not 4-aligned
     assert len(exp) > 50
     _close(got, exp)
     _same_cells(got, exp, 0.05)
@@ -70,7 +73,7 @@ def test_fused_unsupported_last_cycle_points_without_probe():
     p = abi.make_params(jump_pixels=1, voxel_size=0.05, merge_mode=FUSED, **SMALL4)
     with Pose(p) as P:
         P.createCycleClouds(_frames(243, 2, SMALL4["rows"], SMALL4["cols"], keep=keep))
-        assert P.lastCycleEngine() == 1
+        assert P.lastCycleEngine() == TILE
         with pytest.raises(O3RError):
             P.lastCyclePoints()
         # a single-frame call always runs the sort engine and returns the ordered per-frame cloud
@@ -85,7 +88,7 @@ def test_fused_strided_scan_and_keypoints(J, n_kp):
     geom = SMALL4
     p = abi.make_params(jump_pixels=J, voxel_size=0.05, merge_mode=FUSED, **geom)
     cycles = [_frames(250 + J, 5, geom["rows"], geom["cols"], keep=keep, n_kp=n_kp)]
-    got, exp = _run_cycles(p, cycles)
+    got, exp = _run_cycles(p, cycles, expect_engine=BUCKET)
     assert len(exp) > 20
     _close(got, exp)
 
@@ -130,15 +133,67 @@ def test_fused_passthrough_frames():
     _close(got, exp)
 
 
+def test_fused_tile_engine_mixed_passthrough_and_grouped_frames():
+    """One batch holds frames on both sides of PCL's int32 guard (a full frame at leaf 0.0004 trips it, a frame with a
+    4 x 7 pixel patch does not): the tile kernel runs on the host's guess, the exact bboxes contradict it, and the batch is
+    rerun with the guard's actual verdicts — per-frame clouds still bit-exact."""
+    keep = []
+    geom = SMALL4
+    rows, cols = geom["rows"], geom["cols"]
+    p = abi.make_params(jump_pixels=1, voxel_size=0.002, merge_mode=FUSED, **geom)
+    frames = _frames(282, 3, rows, cols, keep=keep)
+    seq = synth.sequence(282, 3, rows, cols)
+    tiny_d = np.zeros((rows, cols), np.uint8)
+    tiny_d[40:44, 100:107] = 110
+    tiny_d[41, 101:104] = 111
+    tiny = abi.make_frame(tiny_d, seq[1][1], seq[1][2], keep=keep)
+    got, exp = _run_cycles(p, [[frames[0], tiny, frames[2]], [tiny, tiny], [frames[1]]])
+    _close(got, exp)
+
+
+@pytest.mark.parametrize("voxel,engine", [(0.03, TILE), (0.06, TILE), (0.07, BUCKET)])
+def test_fused_tile_engine_window_follows_the_leaf_size(voxel, engine):
+    """The pixel window that holds a leaf's points grows with the leaf (tile.cuh): voxel_size 0.03 needs 2 pixels at these
+    depths, 0.06 needs the widest window (4), at 0.07 the device reports disparities beyond even that window's reach and the
+    context moves to the bucket engine.  Same bit-exact per-frame centroids everywhere."""
+    keep = []
+    geom = SMALL4
+    p = abi.make_params(jump_pixels=1, voxel_size=voxel, merge_mode=FUSED, **geom)
+    cycles = [_frames(285, 3, geom["rows"], geom["cols"], keep=keep), _frames(286, 3, geom["rows"], geom["cols"], keep=keep, traj_start=3)]
+    got, exp = _run_cycles(p, cycles, expect_engine=engine)
+    _close(got, exp)
+    _same_cells(got, exp, voxel)
+
+
+def test_fused_tile_engine_widens_its_window_when_a_disparity_is_out_of_reach():
+    """voxel_size 0.05 starts with a 3-pixel window (good for disparities below ~135); a patch at disparity 140 makes the
+    device raise the range flag, the batch is rerun with 4 pixels and the context keeps that window."""
+    keep = []
+    geom = SMALL4
+    rows, cols = geom["rows"], geom["cols"]
+    p = abi.make_params(jump_pixels=1, voxel_size=0.05, merge_mode=FUSED, **geom)
+    seq = synth.sequence(287, 4, rows, cols)
+    near = seq[1][0].copy()
+    near[30:60, 80:150] = 140
+    near[33:40, 90:100] = 141
+    cycles = [[abi.make_frame(seq[0][0], seq[0][1], seq[0][2], keep=keep)],
+              [abi.make_frame(near, seq[1][1], seq[1][2], keep=keep), abi.make_frame(seq[2][0], seq[2][1], seq[2][2], keep=keep)],
+              [abi.make_frame(seq[3][0], seq[3][1], seq[3][2], keep=keep)]]
+    got, exp = _run_cycles(p, cycles)
+    _close(got, exp)
+
+
 @pytest.mark.parametrize("voxel", [0.08, 0.12])
 def test_fused_big_buckets_are_ranked_column_by_column(voxel):
-    """voxel_size 0.08 / 0.12 put ~210 / ~470 points into one 5x5-leaf bucket: above 128 the warp ranks one leaf column at a
-    time (PCL's order is column-major inside a bucket), same bit-exact per-frame centroids."""
+    """voxel_size 0.08 / 0.12: a leaf spans more pixels than the tile engine's widest window (the device raises the range flag
+    on the first batch and the context moves to the bucket engine), and ~210 / ~470 points fall into one 5x5-leaf bucket: above
+    128 the warp ranks one leaf column at a time (PCL's order is column-major inside a bucket), same bit-exact per-frame
+    centroids."""
     keep = []
     geom = SMALL4
     p = abi.make_params(jump_pixels=1, voxel_size=voxel, merge_mode=FUSED, **geom)
     cycles = [_frames(290, 3, geom["rows"], geom["cols"], keep=keep), _frames(291, 3, geom["rows"], geom["cols"], keep=keep, traj_start=3)]
-    got, exp = _run_cycles(p, cycles)
+    got, exp = _run_cycles(p, cycles, expect_engine=BUCKET)
     _close(got, exp)
     _same_cells(got, exp, voxel)
 
@@ -150,7 +205,7 @@ def test_fused_falls_back_to_the_sort_engine_when_a_leaf_column_overflows():
     geom = SMALL4
     p = abi.make_params(jump_pixels=1, voxel_size=0.5, merge_mode=FUSED, **geom)
     cycles = [_frames(292, 3, geom["rows"], geom["cols"], keep=keep), _frames(293, 3, geom["rows"], geom["cols"], keep=keep, traj_start=3)]
-    got, exp = _run_cycles(p, cycles, expect_engine=0, probe=False)
+    got, exp = _run_cycles(p, cycles, expect_engine=SORT, probe=False)
     _close(got, exp)
     _same_cells(got, exp, 0.5)
 
@@ -161,7 +216,7 @@ def test_fused_generic_q_runs_the_sort_engine():
     q = list(abi.Q_CAM13)
     q[1] = 1e-3   # not the rectified-stereo sparsity: no frustum bound, the bucket engine does not apply
     p = abi.make_params(jump_pixels=1, voxel_size=0.05, merge_mode=FUSED, Q=tuple(q), **geom)
-    got, exp = _run_cycles(p, [_frames(295, 3, geom["rows"], geom["cols"], keep=keep)], expect_engine=0, probe=False)
+    got, exp = _run_cycles(p, [_frames(295, 3, geom["rows"], geom["cols"], keep=keep)], expect_engine=SORT, probe=False)
     _close(got, exp)
 
 
@@ -200,10 +255,10 @@ def test_fused_prefetch_and_chunked_host_inputs_agree_with_device_inputs():
         cb = B.createCycleClouds(dev, device_pointers=True)  # one launch sequence
         arr = Cx.prefetchCycle(host)
         cc = Cx.createCycleClouds(arr)                       # prefetched
-        assert A.lastCycleEngine() == B.lastCycleEngine() == Cx.lastCycleEngine() == 1
+        assert A.lastCycleEngine() == B.lastCycleEngine() == Cx.lastCycleEngine() == TILE
         assert np.array_equal(ca, cb) and np.array_equal(ca, cc)
         a, b, c = A.downsamplePtCloud(), B.downsamplePtCloud(), Cx.downsamplePtCloud()
-    # chunking changes which frames share a launch, not any sum: partial cells are per bucket and per frame
+    # chunking changes which frames share a launch, not any sum: partial cells are per tile and per frame
     _eq(a, b)
     _eq(a, c)
 
