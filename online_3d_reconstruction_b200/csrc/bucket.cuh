@@ -64,9 +64,9 @@ struct BkFrame {
 enum { BK_FLAG_RANGE = 1u, BK_FLAG_BUCKET = 2u, BK_FLAG_PART = 4u };
 
 __device__ __forceinline__ void bk_cell(float x, float y, float z, float inv, int& i, int& j, int& k) {
-    i = (int)floorf(__fmul_rn(x, inv));
-    j = (int)floorf(__fmul_rn(y, inv));
-    k = (int)floorf(__fmul_rn(z, inv));
+    i = __float2int_rd(__fmul_rn(x, inv));   // == (int)floorf(.) for every value an int holds, one conversion instead of two
+    j = __float2int_rd(__fmul_rn(y, inv));
+    k = __float2int_rd(__fmul_rn(z, inv));
 }
 
 // bucket of leaf column (i, j); `bad` is raised when the column lies outside the frame's grid (the index is then clamped:

@@ -154,7 +154,8 @@ struct o3r_ctx {
     bool last_bucketed = false;       // the last batch ran through the bucket / tile engine (no per-frame clouds were materialised)
     int last_engine = 0;              // 0 sort, 1 bucket, 2 tile
     // FUSED mode, tile engine (tile.cuh): look-back words; flags / ticket / per-frame counts / pass-through guesses
-    DevBuf tv_status, tv_misc;
+    DevBuf tv_tiles, tv_misc, tv_scratch;   // per-tile {count, scratch position, offset}; flags / counters; records in arrival order
+    size_t tv_scratch_cap = 0, tv_part_cap = 0;   // records the scratch list / the batch's partial list hold (grown on overflow)
     bool tv_off = false;              // a batch exceeded the engine's limits: the bucket / sort engine serve this context from then on
     int tv_R = -1;                    // window radius in use (-1: not chosen yet)
     int tv_guess = -1;                // PCL's overflow guard on the last frame seen (-1: none yet) = the guess for the next batch

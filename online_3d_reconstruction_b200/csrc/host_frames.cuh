@@ -486,6 +486,7 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
             const TvMisc M = tv_misc(ctx, n);
             CU(cudaMemcpyAsync(ctx->h_offs + 1, M.fvox, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->st));
             CU(cudaMemcpyAsync(ctx->h_offs + n + 1, M.flags, 4, cudaMemcpyDeviceToHost, ctx->st));
+            CU(cudaMemcpyAsync(ctx->h_offs + n + 2, M.max_cursor, 4, cudaMemcpyDeviceToHost, ctx->st));
             CU(cudaMemcpyAsync(ctx->h_offs + n + 3, M.actual, (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
         } else if (use_bucket) {   // per-frame voxel COUNTS (h_offs[1..n]) and the two overflow flag words (h_offs[n+1..n+2])
             const BkMisc M = bk_misc(ctx, n);
@@ -516,6 +517,10 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
                 if (trace) fprintf(stderr, "[o3r trace] tile engine flags %u (R %d)\n", fl, tv_R);
                 inputs_resident = true;
                 bool retry = true;
+                if (fl & TV_FLAG_SPACE) {   // a record list was too short: what the batch needs is known now (+ 25 %)
+                    ctx->tv_scratch_cap = std::max(ctx->tv_scratch_cap, (size_t)ctx->h_offs[n + 2] + ctx->h_offs[n + 2] / 4 + 1024);
+                    ctx->tv_part_cap = std::max(ctx->tv_part_cap, (size_t)ctx->h_counters[CNT_PART] + ctx->h_counters[CNT_PART] / 4 + 1024);
+                }
                 if (fl & TV_FLAG_PASS) tv_guess.assign(actual, actual + n);   // the bboxes are exact: so is this
                 else if (fl & TV_FLAG_RANGE) {   // a disparity beyond the window's reach: widen it
                     if (tv_R < kTvMaxR) ctx->tv_R = tv_R + 1; else retry = false;

@@ -57,25 +57,32 @@ bool tv_plan(const o3r_ctx* ctx, const AParams& P, const o3r_frame* frames, int 
     return true;
 }
 
-// misc layout (u32 words): [0] flags, [1] ticket, [2] debug voxel count, [3] spare, [16 .. 16 + n) per-frame voxel counts,
-// then n bytes of guessed and n bytes of actual pass-through flags
+// misc layout (u32 words): [0] flags, [1] ticket, [2] debug voxel count, [3] scratch cursor, [4] largest cursor of the batch,
+// [16 .. 16 + n) per-frame voxel counts, then n bytes of guessed and n bytes of actual pass-through flags
 struct TvMisc {
-    uint32_t *flags, *ticket, *dbg_cnt, *fvox;
+    uint32_t *flags, *ticket, *dbg_cnt, *cursor, *max_cursor, *fvox;
     uint8_t *guess, *actual;
 };
 TvMisc tv_misc(o3r_ctx* ctx, int n) {
     uint32_t* m = ctx->tv_misc.as<uint32_t>();
     uint8_t* b = reinterpret_cast<uint8_t*>(m + 16 + n);
-    return TvMisc{m, m + 1, m + 2, m + 16, b, b + n};
+    return TvMisc{m, m + 1, m + 2, m + 3, m + 4, m + 16, b, b + n};
 }
 
+// The record lists are sized from what the previous batches needed (the device reports overflow, the host grows and reruns):
+// a tile can emit up to kTvItems records, a typical one a few dozen.
 int tv_prepare(o3r_ctx* ctx, const TvPlan& pl, int n, int chunk, size_t cap_batch, const std::vector<uint8_t>& guess) {
     const size_t tiles_chunk = pl.tiles_per_frame * (size_t)chunk, tiles_batch = pl.tiles_per_frame * (size_t)n;
-    CU(ctx->tv_status.ensure((tiles_chunk + 1) * 4));
+    CU(ctx->tv_tiles.ensure(3 * (tiles_chunk + 4) * 4));
     CU(ctx->tv_misc.ensure((16 + (size_t)n) * 4 + 2 * (size_t)n + 16));
     CU(ctx->bbox.ensure((size_t)n * 6 * 4));
-    // a tile emits at most one record per centroid (<= kTvItems), the batch at most one per sample
-    CU(ctx->partials.ensure(std::max<size_t>(std::min(tiles_batch * (size_t)kTvItems, cap_batch), 1) * sizeof(o3r_cell)));
+    const size_t hard_chunk = std::min(tiles_chunk * (size_t)kTvItems, pl.tiles_per_frame ? cap_batch / n * chunk : 0);
+    const size_t hard_batch = std::min(tiles_batch * (size_t)kTvItems, cap_batch);
+    ctx->tv_scratch_cap = std::min(std::max(ctx->tv_scratch_cap, tiles_chunk * 256), std::max<size_t>(hard_chunk, 1));
+    ctx->tv_part_cap = std::min(std::max(ctx->tv_part_cap, tiles_batch * 256), std::max<size_t>(hard_batch, 1));
+    if (ctx->tv_scratch_cap >= (1ull << 32) || ctx->tv_part_cap >= (1ull << 32)) return ctx->fail(O3R_ERR_INVALID, "batch too large for the tile engine");
+    CU(ctx->tv_scratch.ensure(ctx->tv_scratch_cap * sizeof(o3r_cell)));
+    CU(ctx->partials.ensure(ctx->tv_part_cap * sizeof(o3r_cell)));
     const TvMisc M = tv_misc(ctx, n);
     ZERO(M.flags, (16 + (size_t)n) * 4);
     return upload_small(ctx, M.guess, guess.data(), (size_t)n);
@@ -100,10 +107,13 @@ int tv_run_chunk(o3r_ctx* ctx, const AParams& P, const TvPlan& pl, int R, int f0
     uint32_t* cnt = ctx->counters.as<uint32_t>();
     const TvMisc M = tv_misc(ctx, n);
     const uint32_t n_tiles = (uint32_t)(pl.tiles_per_frame * (size_t)nc);
+    uint32_t* tile_cnt = ctx->tv_tiles.as<uint32_t>();
+    uint32_t* tile_at = tile_cnt + (pl.tiles_per_frame * (size_t)nc + 4);
+    uint32_t* tile_off = tile_at + (pl.tiles_per_frame * (size_t)nc + 4);
     {
         ZeroBatch Z;
-        Z.add(ctx->tv_status.p, ((size_t)n_tiles + 1) * 4);
         Z.add(M.ticket, 4);
+        Z.add(M.cursor, 4);
         Z.add(cnt + CNT_PARTCHUNK, 4);
         int rcz = zero_batch(ctx, Z);
         if (rcz) return rcz;
@@ -122,10 +132,11 @@ int tv_run_chunk(o3r_ctx* ctx, const AParams& P, const TvPlan& pl, int R, int f0
             if (std::fabs(ctx->p.Q[14] * d + ctx->p.Q[15]) < A.wlim) dl = d; else if (dl >= 0) break;
         A.dlim_i = dl;
     }
-    A.out = ctx->partials.as<o3r_cell>();
-    A.out_base = cnt + CNT_PART;
-    A.chunk_total = cnt + CNT_PARTCHUNK;
-    A.status = ctx->tv_status.as<uint32_t>();
+    A.scratch = ctx->tv_scratch.as<o3r_cell>();
+    A.scratch_cap = (uint32_t)ctx->tv_scratch_cap;
+    A.cursor = M.cursor;
+    A.tile_cnt = tile_cnt;
+    A.tile_at = tile_at;
     A.ticket = M.ticket;
     A.frame_vox = M.fvox + f0;
     A.bbox = bbox;
@@ -142,6 +153,11 @@ int tv_run_chunk(o3r_ctx* ctx, const AParams& P, const TvPlan& pl, int R, int f0
         default: rc = tv_launch<DT, 4>(ctx, P, A, n_tiles); break;
     }
     if (rc) return rc;
+    // tile order: offsets = scan of the per-tile counts, then one warp per tile copies its records behind the batch's list
+    LAUNCH(k_scan_u32, 1, kScanThreads, 0, tile_cnt, tile_off, n_tiles, cnt + CNT_PARTCHUNK);
+    LAUNCH(k_tv_compact, cdiv(n_tiles, kWarps), kThreads, 0, ctx->tv_scratch.as<o3r_cell>(), tile_cnt, tile_at, tile_off, n_tiles,
+           ctx->partials.as<o3r_cell>(), cnt + CNT_PART, cnt + CNT_PARTCHUNK, (uint32_t)ctx->tv_part_cap, M.cursor, M.max_cursor,
+           M.flags);
     LAUNCH(k_tv_check, cdiv(nc, 64), 64, 0, nc, bbox, ctx->inv_f, M.guess + f0, M.actual + f0, M.flags);
     LAUNCH(k_add_u32, 1, 32, 0, cnt + CNT_PART, cnt + CNT_PARTCHUNK);
     return O3R_OK;

@@ -25,10 +25,13 @@
 //      A leaf belongs to the tile that holds its first point, and the halo shows that tile every mate.
 //   C  the centroids are celled on the combined grid (voxel_size, voxel_size, 1000 after z += 500); the tile's cells index
 //      a dense table (no hash), the centroids are counting-sorted by cell (warp match + warp-private counters: no atomics)
-//      and every cell is summed by four lanes in a fixed tree: one 40-byte partial cell per (tile, cell), written in cell
-//      order at an offset from a decoupled look-back over the tiles, so the partial list is reproducible bit for bit.
+//      and every cell is summed by four lanes in a fixed tree: one 40-byte partial cell per (tile, cell), in cell order.
 //      (A tile whose cells span more than the table — a depth discontinuity, a grid finer than the pixels — writes every
 //      centroid as its own single-point record instead.)
+//   The records of a tile go to a scratch list at a position taken from an atomic cursor — no tile ever waits for another —
+//   and k_tv_compact then copies them into the partial list in TILE order (a scan over the per-tile counts), so the list the
+//   merge sees, and with it every float sum, is reproducible bit for bit.  (A decoupled look-back inside the kernel was
+//   measured first: 14 % of the issued instructions were the spin on slower predecessors, plus the CTA-wide wait behind it.)
 //
 // PCL's int32 overflow guard (output = input for a frame whose leaf grid has more than 2^31 cells) depends on the frame's
 // exact bbox, which only exists once every pixel has been evaluated: the kernel runs on the host's per-frame guess, computes
@@ -54,7 +57,7 @@ constexpr int kTvMaxR = 4;
 constexpr uint32_t kTvNoHash = 0xffffffffu;            // invalid pixel (valid hashes keep bit 31 clear)
 static_assert(kTvQ * kThreads == kTvCoreGroups, "core groups must divide evenly");
 
-enum { TV_FLAG_RANGE = 1u, TV_FLAG_PASS = 4u };
+enum { TV_FLAG_RANGE = 1u, TV_FLAG_SPACE = 2u, TV_FLAG_PASS = 4u };
 
 template <int R>
 struct TvGeom {
@@ -86,10 +89,11 @@ struct TvArgs {
     float inv_f, icx, icz;
     double wlim;                   // |q14 d + q15| must stay below this for the window to hold every leaf-mate
     int dlim_i;                    // the same bound as a u8 disparity (LUT path)
-    o3r_cell* out;
-    const uint32_t* out_base;
-    uint32_t* chunk_total;
-    uint32_t* status;
+    o3r_cell* scratch;             // the chunk's records in arrival order
+    uint32_t scratch_cap;
+    uint32_t* cursor;              // next free scratch record
+    uint32_t* tile_cnt;            // per tile (ticket order): records,
+    uint32_t* tile_at;             // first scratch record
     uint32_t* ticket;
     uint32_t* frame_vox;
     uint32_t* bbox;
@@ -174,30 +178,18 @@ struct TvMask<4> { typedef unsigned long long type; };
 __device__ __forceinline__ int tv_ffs(uint32_t m) { return __ffs((int)m) - 1; }
 __device__ __forceinline__ int tv_ffs(unsigned long long m) { return __ffsll((long long)m) - 1; }
 
-// Where the tile's `nb` records go: decoupled look-back over the predecessors' counts, 32 tiles per step (warp 0; the caller
-// synchronises the CTA afterwards and reads *out0).  Every tile — also one without records — publishes its count.
-__device__ __forceinline__ uint32_t tv_lookback(const TvArgs& A, uint32_t t, uint32_t nt, uint32_t nb, uint32_t* out0, int warp,
-                                                int lane) {
-    uint32_t pf = 0;
-    if (warp == 0) {
-        if (lane == 0) st_volatile_u32(A.status + t, (t == 0 ? kStGlobal : kStLocal) | nb);
-        for (int32_t back = (int32_t)t - 1; back >= 0; back -= 32) {
-            const int32_t idx = back - lane;
-            uint32_t v = kStGlobal;
-            if (idx >= 0)
-                while (((v = ld_volatile_u32(A.status + idx)) >> 30) == 0u) __nanosleep(32);
-            const unsigned gm = __ballot_sync(kFull, (v >> 30) == 2u);
-            const int first = gm ? __ffs(gm) - 1 : 31;
-            pf += __reduce_add_sync(kFull, lane <= first ? (v & kStMask) : 0u);
-            if (gm) break;
-        }
-        if (lane == 0) {
-            if (t > 0) st_volatile_u32(A.status + t, kStGlobal | (pf + nb));
-            *out0 = pf;
-            if (t == nt - 1) *A.chunk_total = pf + nb;
-        }
+// Scratch position of the tile's `nb` records (thread 0; the caller synchronises the CTA afterwards and reads *out0:
+// 0xffffffff = the scratch list is full, the host grows it and reruns the batch).  Every tile records its count.
+__device__ __forceinline__ void tv_place(const TvArgs& A, uint32_t t, uint32_t nb, uint32_t* out0) {
+    const uint32_t at = nb ? atomicAdd(A.cursor, nb) : 0u;
+    A.tile_cnt[t] = nb;
+    A.tile_at[t] = at;
+    if (at + nb > A.scratch_cap) {
+        atomicOr(A.flags, TV_FLAG_SPACE);
+        *out0 = 0xffffffffu;
+    } else {
+        *out0 = at;
     }
-    return pf;
 }
 // range of combined-grid cells touched (the merge packs its sort keys into it)
 __device__ __forceinline__ void tv_cellbb(const TvArgs& A, const int* cmin, const int* cmax, int tid) {
@@ -240,7 +232,7 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
 
     // ---- A: evaluate core + halo into the planes -------------------------------------------------------------------------
     {
-        uint32_t mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
+        float fmn[3] = {INFINITY, INFINITY, INFINITY}, fmx[3] = {-INFINITY, -INFINITY, -INFINITY};
         bool over = false, anyv = false;
         for (int g = tid; g < G::NG; g += kThreads) {
             const int lr = g / (G::NC / 4), lc = (g - lr * (G::NC / 4)) * 4;
@@ -268,10 +260,9 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
                             bk_cell(px[j], py[j], pz[j], A.inv_f, ci, cj, ck);
                             h[j] = tv_hash(ci, cj, ck);
                             if (core) {
-                                const uint32_t ox = f2ord(px[j]), oy = f2ord(py[j]), oz = f2ord(pz[j]);
-                                mn[0] = min(mn[0], ox); mx[0] = max(mx[0], ox);
-                                mn[1] = min(mn[1], oy); mx[1] = max(mx[1], oy);
-                                mn[2] = min(mn[2], oz); mx[2] = max(mx[2], oz);
+                                fmn[0] = fminf(fmn[0], px[j]); fmx[0] = fmaxf(fmx[0], px[j]);
+                                fmn[1] = fminf(fmn[1], py[j]); fmx[1] = fmaxf(fmx[1], py[j]);
+                                fmn[2] = fminf(fmn[2], pz[j]); fmx[2] = fmaxf(fmx[2], pz[j]);
                                 anyv = true;
                             }
                         }
@@ -288,10 +279,11 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
         // the frame's exact bbox (PCL getMinMax3D) from the core pixels: every pixel is core in exactly one tile
         const unsigned anyw = __ballot_sync(kFull, anyv);
         if (anyw) {
+            uint32_t mn[3], mx[3];   // (order-preserving uint images: -0 < +0 as in the other engines' integer reductions)
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                mn[a] = __reduce_min_sync(kFull, mn[a]);
-                mx[a] = __reduce_max_sync(kFull, mx[a]);
+                mn[a] = __reduce_min_sync(kFull, anyv ? f2ord(fmn[a]) : 0xffffffffu);
+                mx[a] = __reduce_max_sync(kFull, anyv ? f2ord(fmx[a]) : 0u);
             }
             if (lane == 0) {
                 S.any_valid = 1u;
@@ -385,15 +377,14 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
                         }
                     }
                     c = bk_centroid(sx, sy, sz, cn, r, gg, bb);
-                } else {
-                    const uint32_t w = __float_as_uint(p.w);
-                    c = bk_centroid(p.x, p.y, p.z, 1u, (w >> 16) & 255u, (w >> 8) & 255u, w & 255u);
+                } else {   // a leaf of one point: (0 + x) / 1 (only -0 changes, to +0), colour as it is
+                    c.x = __fadd_rn(0.f, p.x); c.y = __fadd_rn(0.f, p.y); c.z = __fadd_rn(0.f, p.z);
                 }
             }
             if (A.dbg_vox) A.dbg_vox[atomicAdd(A.dbg_cnt, 1u)] = c;
             c.z = __fadd_rn(c.z, 500.0f);   // pose_functions.cpp:1666
-            const int vi = (int)floorf(__fmul_rn(c.x, A.icx)), vj = (int)floorf(__fmul_rn(c.y, A.icx)),
-                      vk = (int)floorf(__fmul_rn(c.z, A.icz));
+            const int vi = __float2int_rd(__fmul_rn(c.x, A.icx)), vj = __float2int_rd(__fmul_rn(c.y, A.icx)),
+                      vk = __float2int_rd(__fmul_rn(c.z, A.icz));
             cmn[0] = min(cmn[0], vi); cmx[0] = max(cmx[0], vi);
             cmn[1] = min(cmn[1], vj); cmx[1] = max(cmx[1], vj);
             cmn[2] = min(cmn[2], vk); cmx[2] = max(cmx[2], vk);
@@ -429,19 +420,19 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
         // finer than the pixel footprint): every centroid leaves as its own single-point record, in tile order (thread, slot).
         uint32_t tot;
         uint32_t pos = block_excl_scan((uint32_t)__popc(cvalid), S.scan, tot);
-        const uint32_t pf = tv_lookback(A, t, nt, tot, &S.out0, warp, lane);
-        (void)pf;
+        if (tid == 0) tv_place(A, t, tot, &S.out0);
         __syncthreads();
         if (tot == 0) return;
         if (tid == 0) atomicAdd(A.frame_vox + f, tot);
         tv_cellbb(A, S.cmin, S.cmax, tid);
-        o3r_cell* const out = A.out + *A.out_base + S.out0;
+        if (S.out0 == 0xffffffffu) return;
+        o3r_cell* const out = A.scratch + S.out0;
 #pragma unroll
         for (int r = 0; r < kTvQ * 4; ++r)
             if ((cvalid >> r) & 1u) {
                 const float4 p = cen[r];
-                const int vi = (int)floorf(__fmul_rn(p.x, A.icx)), vj = (int)floorf(__fmul_rn(p.y, A.icx)),
-                          vk = (int)floorf(__fmul_rn(p.z, A.icz));
+                const int vi = __float2int_rd(__fmul_rn(p.x, A.icx)), vj = __float2int_rd(__fmul_rn(p.y, A.icx)),
+                          vk = __float2int_rd(__fmul_rn(p.z, A.icz));
                 const uint32_t w = __float_as_uint(p.w);
                 o3r_cell c;
                 c.key = ((unsigned long long)(uint32_t)(vk + Bi) << 42) | ((unsigned long long)(uint32_t)(vj + Bi) << 21) |
@@ -466,8 +457,8 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
         const bool valid = (cvalid >> r) & 1u;
         bin[r] = (uint32_t)(kTvBins + 1);
         if (valid) {
-            const int vi = (int)floorf(__fmul_rn(cen[r].x, A.icx)), vj = (int)floorf(__fmul_rn(cen[r].y, A.icx)),
-                      vk = (int)floorf(__fmul_rn(cen[r].z, A.icz));
+            const int vi = __float2int_rd(__fmul_rn(cen[r].x, A.icx)), vj = __float2int_rd(__fmul_rn(cen[r].y, A.icx)),
+                      vk = __float2int_rd(__fmul_rn(cen[r].z, A.icz));
             bin[r] = (uint32_t)(((vk - c0k) * (int)ej + (vj - c0j)) * (int)ei + (vi - c0i));
         }
         const unsigned peers = __match_any_sync(kFull, bin[r]);
@@ -507,12 +498,13 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
 #pragma unroll
     for (int r = 0; r < kTvQ * 4; ++r)
         if ((cvalid >> r) & 1u) items[(S.bd[bin[r]] & 0xffffu) + (uint32_t)wc[bin[r]] + rk[r]] = cen[r];
-    tv_lookback(A, t, nt, nb, &S.out0, warp, lane);
+    if (tid == 0) tv_place(A, t, nb, &S.out0);
     __syncthreads();
     if (nb == 0) return;
     if (tid == 0) atomicAdd(A.frame_vox + f, S.nitems);
     tv_cellbb(A, S.cmin, S.cmax, tid);
-    o3r_cell* const out = A.out + *A.out_base + S.out0;
+    if (S.out0 == 0xffffffffu) return;
+    o3r_cell* const out = A.scratch + S.out0;
     // four lanes per cell: lane s left-folds items s, s + 4, ... of the cell, then (s0 + s1) + (s2 + s3): a fixed tree
     for (int b0 = warp * 8; b0 < nbins; b0 += kWarps * 8) {
         const int b = b0 + (lane >> 2), sub = lane & 3;
@@ -546,6 +538,28 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
             out[dense] = c;
         }
     }
+}
+
+// The chunk's records in tile order: one warp per tile copies its records from the scratch list to
+// out[*out_base + tile_off[t] ...) (tile_off = exclusive scan of tile_cnt, *chunk_total its total).  40-byte records move as
+// five 8-byte words.  The list is skipped (TV_FLAG_SPACE) when the scratch list overflowed or the output would.
+__global__ void __launch_bounds__(kThreads) k_tv_compact(const o3r_cell* __restrict__ scratch, const uint32_t* __restrict__ tile_cnt,
+                                                         const uint32_t* __restrict__ tile_at, const uint32_t* __restrict__ tile_off,
+                                                         uint32_t n_tiles, o3r_cell* __restrict__ out,
+                                                         const uint32_t* __restrict__ out_base, const uint32_t* __restrict__ chunk_total,
+                                                         uint32_t out_cap, const uint32_t* __restrict__ cursor,
+                                                         uint32_t* __restrict__ max_cursor, uint32_t* __restrict__ flags) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(max_cursor, *cursor);
+    const bool room = (unsigned long long)*out_base + *chunk_total <= (unsigned long long)out_cap;
+    if (!room && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(flags, TV_FLAG_SPACE);
+    if (!room || (*flags & TV_FLAG_SPACE)) return;
+    const uint32_t t = blockIdx.x * kWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (t >= n_tiles) return;
+    const uint32_t n = tile_cnt[t];
+    if (n == 0) return;
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(scratch + tile_at[t]);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(out + *out_base + tile_off[t]);
+    for (uint32_t i = lane; i < n * 5u; i += 32) dst[i] = __ldcs(src + i);
 }
 
 // per frame: PCL's int32 overflow guard on the exact bbox against the guess the kernel ran on
