@@ -52,7 +52,11 @@ constexpr int kTvGroupsRow = kTvW / 4;                 // 4-pixel groups per cor
 constexpr int kTvCoreGroups = kTvGroupsRow * kTvH;     // 512: two per thread
 constexpr int kTvQ = kTvCoreGroups / kThreads;         // core groups per thread
 constexpr int kTvItems = kTvW * kTvH;                  // centroids a tile can emit
-constexpr int kTvBins = 1024;                          // combined-grid cells a tile may touch (dense table)
+constexpr int kTvBinsN = 1024;                         // distinct combined-grid cells a tile can sum (more: one record per centroid)
+template <int R>
+struct TvBins { static constexpr int value = kTvBinsN; };
+constexpr int kTvHash = 2 * kTvItems;                  // hash slots of the sparse cell table (load <= 0.5)
+static_assert(kTvHash == 4096, "the hash shift below assumes 4096 slots");
 constexpr int kTvMaxR = 4;
 constexpr uint32_t kTvNoHash = 0xffffffffu;            // invalid pixel (valid hashes keep bit 31 clear)
 static_assert(kTvQ * kThreads == kTvCoreGroups, "core groups must divide evenly");
@@ -64,23 +68,26 @@ struct TvGeom {
     static constexpr int HX = R ? 4 : 0, HY = R;       // halo columns stay a multiple of 4: aligned 4-pixel groups
     static constexpr int NC = kTvW + 2 * HX, NR = kTvH + 2 * HY, N = NC * NR, NG = N / 4;
     static constexpr int W = 2 * R + 1, S = R * W + R; // window width, index of the pixel itself
-    static constexpr size_t plane_bytes = (size_t)5 * N * 4 > (size_t)kTvItems * 16 ? (size_t)5 * N * 4 : (size_t)kTvItems * 16;
+    // the planes (R > 0), later the sparse cell table (8-byte keys + 2-byte cell numbers), later the centroids in cell order
+    static constexpr size_t alias_bytes = (size_t)kTvHash * 10 > (size_t)kTvItems * 16 ? (size_t)kTvHash * 10 : (size_t)kTvItems * 16;
+    static constexpr size_t plane_bytes = (R && (size_t)5 * N * 4 > alias_bytes) ? (size_t)5 * N * 4 : alias_bytes;
 };
 
+template <int NB>
 struct TvTail {
     union {
-        uint16_t cnt[kWarps][kTvBins + 2];   // phase C: per warp and cell: count, then exclusive prefix over the warps
+        uint16_t cnt[kWarps][NB + 2];        // phase C: per warp and cell: count, then exclusive prefix over the warps
         struct { double rl[256]; float zl[256]; } lut;   // phase A
     } u;
-    uint32_t bd[kTvBins + 1];                // per cell: first item | rank among the non-empty cells << 16
+    uint32_t bd[NB + 1];                     // per cell: first item | rank among the non-empty cells << 16
     uint32_t scan[34];
-    uint32_t ticket, out0, nb, nitems;
+    uint32_t ticket, out0, nb, nitems, nbh;
     int cmin[3], cmax[3];
     uint32_t bb[6];
     uint32_t any_valid, bad;
 };
 template <int R>
-constexpr size_t tv_smem() { return TvGeom<R>::plane_bytes + sizeof(TvTail); }
+constexpr size_t tv_smem() { return TvGeom<R>::plane_bytes + sizeof(TvTail<TvBins<R>::value>); }
 
 struct TvArgs {
     const FrameDev* frames;
@@ -212,7 +219,8 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
     float* const SZ = SY + G::N;
     uint32_t* const SC = reinterpret_cast<uint32_t*>(SZ + G::N);
     float4* const items = reinterpret_cast<float4*>(tv_smem_raw);      // phase C: the tile's centroids in cell order (aliases the planes)
-    TvTail& S = *reinterpret_cast<TvTail*>(tv_smem_raw + G::plane_bytes);
+    constexpr int NB = TvBins<R>::value;
+    TvTail<NB>& S = *reinterpret_cast<TvTail<NB>*>(tv_smem_raw + G::plane_bytes);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
 
@@ -230,10 +238,52 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
     const bool pass = A.frame_pass[f] != 0;
     const int y_org = P.bb + tyi * kTvH - G::HY, x_org = P.x0 + txi * kTvW - G::HX;
 
-    // ---- A: evaluate core + halo into the planes -------------------------------------------------------------------------
+    float4 cen[kTvQ * 4];
+    uint32_t cvalid = 0;
+    int cmn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, cmx[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+    // ---- A: evaluate core + halo into the planes (R == 0, every frame a PCL pass-through: no window, no planes — the thread's
+    //      own eight pixels stay in registers as the per-frame "voxels" they are)
     {
         float fmn[3] = {INFINITY, INFINITY, INFINITY}, fmx[3] = {-INFINITY, -INFINITY, -INFINITY};
         bool over = false, anyv = false;
+        if (R == 0) {
+#pragma unroll
+            for (int q = 0; q < kTvQ; ++q) {
+                const int g = tid + q * kThreads;
+                const int cr = g / kTvGroupsRow, cg = g - cr * kTvGroupsRow;
+                const int y = y_org + cr, xb = x_org + cg * 4;
+                if (y < P.bb + P.ny && xb < P.x0 + P.nx) {
+                    float X[4], Y[4], Z[4];
+                    const uint32_t mask = tv_eval4<DT>(P, F, S.u.lut.rl, S.u.lut.zl, xb, y, A, X, Y, Z, over);
+                    if (mask) {
+                        const uint32_t* c = reinterpret_cast<const uint32_t*>(F.bgr + (size_t)y * F.bgr_step + 3 * (size_t)xb);
+                        const uint32_t w0 = __ldg(c), w1 = __ldg(c + 1), w2 = __ldg(c + 2);
+                        const uint32_t rgb[4] = {w0 & 0x00ffffffu, (w0 >> 24) | ((w1 & 0xffffu) << 8), (w1 >> 16) | ((w2 & 0xffu) << 16),
+                                                 w2 >> 8};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (mask & (1u << j)) {
+                                float4 p;
+                                xform(F.T, X[j], Y[j], Z[j], p.x, p.y, p.z);
+                                p.w = __uint_as_float(rgb[j]);
+                                fmn[0] = fminf(fmn[0], p.x); fmx[0] = fmaxf(fmx[0], p.x);
+                                fmn[1] = fminf(fmn[1], p.y); fmx[1] = fmaxf(fmx[1], p.y);
+                                fmn[2] = fminf(fmn[2], p.z); fmx[2] = fmaxf(fmx[2], p.z);
+                                anyv = true;
+                                if (A.dbg_vox) A.dbg_vox[atomicAdd(A.dbg_cnt, 1u)] = p;   // PCL: output = *input_
+                                p.z = __fadd_rn(p.z, 500.0f);   // pose_functions.cpp:1666
+                                const int vi = __float2int_rd(__fmul_rn(p.x, A.icx)), vj = __float2int_rd(__fmul_rn(p.y, A.icx)),
+                                          vk = __float2int_rd(__fmul_rn(p.z, A.icz));
+                                cmn[0] = min(cmn[0], vi); cmx[0] = max(cmx[0], vi);
+                                cmn[1] = min(cmn[1], vj); cmx[1] = max(cmx[1], vj);
+                                cmn[2] = min(cmn[2], vk); cmx[2] = max(cmx[2], vk);
+                                cen[q * 4 + j] = p;
+                                cvalid |= 1u << (q * 4 + j);
+                            }
+                    }
+                }
+            }
+        } else
         for (int g = tid; g < G::NG; g += kThreads) {
             const int lr = g / (G::NC / 4), lc = (g - lr * (G::NC / 4)) * 4;
             const int y = y_org + lr, xb = x_org + lc;
@@ -303,9 +353,7 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
     if (tid == 0 && S.bad) atomicOr(A.flags, TV_FLAG_RANGE);
 
     // ---- B: first points of the leaves fold their window mates in scan order -----------------------------------------------
-    float4 cen[kTvQ * 4];
-    uint32_t cvalid = 0;
-    int cmn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, cmx[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+    if (R > 0) {
 #pragma unroll
     for (int q = 0; q < kTvQ; ++q) {
         const int g = tid + q * kThreads;
@@ -392,6 +440,7 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
             cvalid |= 1u << (q * 4 + j);
         }
     }
+    }
     // ---- C: the tile's cells -------------------------------------------------------------------------------------------
     {
         const unsigned anyc = __ballot_sync(kFull, cvalid != 0u);
@@ -412,12 +461,62 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
     const int c0i = S.cmin[0], c0j = S.cmin[1], c0k = S.cmin[2];
     const long long ei = have ? (long long)S.cmax[0] - c0i + 1 : 0, ej = have ? (long long)S.cmax[1] - c0j + 1 : 0,
                     ek = have ? (long long)S.cmax[2] - c0k + 1 : 0;
-    const bool fits = ei * ej * ek <= (long long)kTvBins && ei <= kTvBins && ej <= kTvBins && ek <= kTvBins;
-    const int nbins = fits ? (int)(ei * ej * ek) : 0;
+    const bool fits = ei * ej * ek <= (long long)NB && ei <= NB && ej <= NB && ek <= NB;
+    int nbins = fits ? (int)(ei * ej * ek) : 0;
     const int Bi = 1 << 20;
-    if (!fits) {
-        // The tile's cells span more than the dense table holds (a depth discontinuity inside the tile, or a combined grid
-        // finer than the pixel footprint): every centroid leaves as its own single-point record, in tile order (thread, slot).
+    uint32_t bin[kTvQ * 4], rk[kTvQ * 4];   // cell number of the thread's centroids (NB + 1: none), rank inside the cell
+#pragma unroll
+    for (int r = 0; r < kTvQ * 4; ++r) bin[r] = (uint32_t)(NB + 1);
+    bool loose = false;
+    if (fits) {   // the box of the tile's cells indexes the table directly
+#pragma unroll
+        for (int r = 0; r < kTvQ * 4; ++r)
+            if ((cvalid >> r) & 1u) {
+                const int vi = __float2int_rd(__fmul_rn(cen[r].x, A.icx)), vj = __float2int_rd(__fmul_rn(cen[r].y, A.icx)),
+                          vk = __float2int_rd(__fmul_rn(cen[r].z, A.icz));
+                bin[r] = (uint32_t)(((vk - c0k) * (int)ej + (vj - c0j)) * (int)ei + (vi - c0i));
+            }
+    } else {
+        // The cells span more than the table (a depth discontinuity inside the tile, a combined grid that is fine against the
+        // sideways scatter of noisy depths): number the cells that are actually occupied through an open-addressing hash of the
+        // 64-bit cell key.  Which number a cell gets depends on a race, i.e. only the order of DIFFERENT cells' records does.
+        unsigned long long* const tab = reinterpret_cast<unsigned long long*>(tv_smem_raw);
+        uint16_t* const dense = reinterpret_cast<uint16_t*>(tv_smem_raw + (size_t)kTvHash * 8);
+        {
+            uint4* tz = reinterpret_cast<uint4*>(tab);
+            for (int i = tid; i < kTvHash / 2; i += kThreads) tz[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+            if (tid == 0) S.nbh = 0u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kTvQ * 4; ++r)
+            if ((cvalid >> r) & 1u) {
+                const int vi = __float2int_rd(__fmul_rn(cen[r].x, A.icx)), vj = __float2int_rd(__fmul_rn(cen[r].y, A.icx)),
+                          vk = __float2int_rd(__fmul_rn(cen[r].z, A.icz));
+                const unsigned long long k = ((unsigned long long)(uint32_t)(vk + Bi) << 42) | ((unsigned long long)(uint32_t)(vj + Bi) << 21) |
+                                             (unsigned long long)(uint32_t)(vi + Bi);
+                uint32_t h = ((uint32_t)(k ^ (k >> 21) ^ (k >> 42)) * 0x9e3779b1u) >> 20;   // kTvHash = 4096 slots
+                for (;;) {
+                    const unsigned long long old = atomicCAS(&tab[h], ~0ull, k);
+                    if (old == ~0ull) { dense[h] = (uint16_t)atomicAdd(&S.nbh, 1u); break; }
+                    if (old == k) break;
+                    h = (h + 1) & (kTvHash - 1);
+                }
+                bin[r] = h;
+            }
+        __syncthreads();
+        nbins = (int)S.nbh;
+        loose = nbins > NB;
+        if (!loose) {
+#pragma unroll
+            for (int r = 0; r < kTvQ * 4; ++r)
+                if ((cvalid >> r) & 1u) bin[r] = dense[bin[r]];
+        }
+        __syncthreads();   // (the table is dead: the centroids in cell order take its place)
+    }
+    if (loose) {
+        // more occupied cells than the table numbers (at least every second centroid alone in its cell): every centroid leaves
+        // as its own single-point record, in tile order (thread, slot)
         uint32_t tot;
         uint32_t pos = block_excl_scan((uint32_t)__popc(cvalid), S.scan, tot);
         if (tid == 0) tv_place(A, t, tot, &S.out0);
@@ -445,22 +544,14 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
     }
     for (int b = tid; b < (nbins + 2) * kWarps; b += kThreads) {
         const int w = b / (nbins + 2), i = b - w * (nbins + 2);
-        S.u.cnt[w][i == nbins + 1 ? kTvBins + 1 : i] = 0;
+        S.u.cnt[w][i == nbins + 1 ? NB + 1 : i] = 0;
     }
     __syncthreads();
     // stable rank of every centroid inside its cell (tile order = warp, slot, lane); lanes without a centroid share the
-    // stand-in cell kTvBins + 1
-    uint32_t bin[kTvQ * 4], rk[kTvQ * 4];
+    // stand-in cell NB + 1
     uint16_t* wc = &S.u.cnt[warp][0];
 #pragma unroll
     for (int r = 0; r < kTvQ * 4; ++r) {
-        const bool valid = (cvalid >> r) & 1u;
-        bin[r] = (uint32_t)(kTvBins + 1);
-        if (valid) {
-            const int vi = __float2int_rd(__fmul_rn(cen[r].x, A.icx)), vj = __float2int_rd(__fmul_rn(cen[r].y, A.icx)),
-                      vk = __float2int_rd(__fmul_rn(cen[r].z, A.icz));
-            bin[r] = (uint32_t)(((vk - c0k) * (int)ej + (vj - c0j)) * (int)ei + (vi - c0i));
-        }
         const unsigned peers = __match_any_sync(kFull, bin[r]);
         const uint32_t old = wc[bin[r]];
         __syncwarp();
@@ -471,10 +562,11 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
     __syncthreads();
     // per cell: exclusive prefix over the warps; then first item / rank among the non-empty cells (packed scan)
     {
-        uint32_t run[4], psum = 0;
+        constexpr int BPT = NB / kThreads;   // cells per thread
+        uint32_t run[BPT], psum = 0;
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-            const int b = tid * 4 + qq;
+        for (int qq = 0; qq < BPT; ++qq) {
+            const int b = tid * BPT + qq;
             uint32_t acc = 0;
             if (b < nbins) {
 #pragma unroll
@@ -486,8 +578,8 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
         uint32_t tot;
         uint32_t ds = block_excl_scan(psum, S.scan, tot);
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-            const int b = tid * 4 + qq;
+        for (int qq = 0; qq < BPT; ++qq) {
+            const int b = tid * BPT + qq;
             if (b < nbins) S.bd[b] = ds;
             ds += run[qq];
         }
@@ -529,7 +621,9 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
             cr += __shfl_xor_sync(kFull, cr, o); cg += __shfl_xor_sync(kFull, cg, o); cb += __shfl_xor_sync(kFull, cb, o);
         }
         if (sub == 0 && e > a) {
-            const int vi = c0i + b % (int)ei, vj = c0j + (b / (int)ei) % (int)ej, vk = c0k + b / (int)(ei * ej);
+            const float4 p0 = items[a];
+            const int vi = __float2int_rd(__fmul_rn(p0.x, A.icx)), vj = __float2int_rd(__fmul_rn(p0.y, A.icx)),
+                      vk = __float2int_rd(__fmul_rn(p0.z, A.icz));
             o3r_cell c;
             c.key = ((unsigned long long)(uint32_t)(vk + Bi) << 42) | ((unsigned long long)(uint32_t)(vj + Bi) << 21) |
                     (unsigned long long)(uint32_t)(vi + Bi);
@@ -559,7 +653,13 @@ __global__ void __launch_bounds__(kThreads) k_tv_compact(const o3r_cell* __restr
     if (n == 0) return;
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(scratch + tile_at[t]);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(out + *out_base + tile_off[t]);
-    for (uint32_t i = lane; i < n * 5u; i += 32) dst[i] = __ldcs(src + i);
+    const uint32_t nw = n * 5u;
+    uint32_t i = lane;
+    for (; i + 96u < nw; i += 128u) {   // four independent loads in flight per lane
+        const unsigned long long a = __ldcs(src + i), b = __ldcs(src + i + 32), c = __ldcs(src + i + 64), d = __ldcs(src + i + 96);
+        dst[i] = a; dst[i + 32] = b; dst[i + 64] = c; dst[i + 96] = d;
+    }
+    for (; i < nw; i += 32u) dst[i] = __ldcs(src + i);
 }
 
 // per frame: PCL's int32 overflow guard on the exact bbox against the guess the kernel ran on
