@@ -265,10 +265,11 @@ def run_ours(args, rank, world, local_rank):
     stats = {}
 
     if world > 1:
-        # the library's own exchange (o3r_exchange_cycle: grouped ncclSend/ncclRecv of fixed-size slots inside libo3r.so).
-        # Slot size: twice what one rank sends to one owner in a cycle, from a probe cycle (the same on all ranks).
+        # the library's own exchange (o3r_exchange_cycle: the cycle is pre-reduced on the combined grid, then grouped
+        # ncclSend/ncclRecv of fixed-size slots inside libo3r.so).  Slot size: twice what one rank sends to one owner in a
+        # cycle = the distinct cells of a probe cycle / world (the largest over the ranks).
         P.createCycleClouds(fr_dev[0], dt, device_pointers=True)
-        probe = max(P.lastCyclePartials(), 1) if P.lastCycleEngine() or P.lastCyclePartials() else int(F * ny * nx)
+        probe = max(P.cloudSize(), 1)
         t = torch.tensor([probe], device=dev, dtype=torch.int64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         slot_cells = int(2 * int(t.item()) // world + 4096)

@@ -15,25 +15,16 @@
 
 namespace o3r {
 
-// owner of each cell + per-owner histogram; keys32 = owner, vals = cell index (then one stable sort pass)
-__global__ void __launch_bounds__(kThreads) k_owner_cells(const o3r_cell* __restrict__ cells, uint32_t n, uint32_t world,
-                                                          uint32_t* __restrict__ okeys, uint32_t* __restrict__ ovals,
-                                                          uint32_t* __restrict__ counts, uint32_t* __restrict__ seg) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) { seg[0] = 0u; seg[1] = n; }
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
-        const uint32_t o = (uint32_t)(hash64(cells[i].key) % world);
-        okeys[i] = o;
-        ovals[i] = i;
-        atomicAdd(&counts[o], 1u);
-    }
-}
-
-// cells in owner order -> fixed-size slots: slot d = [header | slot_cap cells]; header.key = valid cells.
-// counts[d] = cells owned by d (raw histogram); a slot that would overflow raises *xflag and is truncated.
-__global__ void __launch_bounds__(kThreads) k_pack_slots(const o3r_cell* __restrict__ cells, const uint32_t* __restrict__ order,
-                                                         uint32_t n, const uint32_t* __restrict__ counts, uint32_t world,
-                                                         uint32_t slot_cap, o3r_cell* __restrict__ slots, uint32_t* __restrict__ xflag) {
+// the pre-reduced cycle list (ckey / cacc / crgb, in owner order through `order`; the cell count lives on the device) ->
+// fixed-size slots: slot d = [header | slot_cap cells]; header.key = valid cells.  counts[d] = cells owned by d (raw
+// histogram); a slot that would overflow raises *xflag and is truncated.
+__global__ void __launch_bounds__(kThreads) k_pack_slots_cyc(const uint32_t* __restrict__ n_cyc_ptr, const uint32_t* __restrict__ order,
+                                                             const uint64_t* __restrict__ ckey, const float4* __restrict__ cacc,
+                                                             const uint4* __restrict__ crgb, const uint32_t* __restrict__ counts,
+                                                             uint32_t world, uint32_t slot_cap, o3r_cell* __restrict__ slots,
+                                                             uint32_t* __restrict__ xflag) {
     __shared__ uint32_t s_start[257];
+    const uint32_t n = *n_cyc_ptr;
     if (threadIdx.x == 0) {
         uint32_t a = 0;
         for (uint32_t d = 0; d < world; ++d) { s_start[d] = a; a += counts[d]; }
@@ -51,7 +42,16 @@ __global__ void __launch_bounds__(kThreads) k_pack_slots(const o3r_cell* __restr
         uint32_t d = 0;   // owner of position i of the owner-sorted list
         while (d + 1 < world && s_start[d + 1] <= i) ++d;
         const uint32_t at = i - s_start[d];
-        if (at < slot_cap) slots[(size_t)d * (slot_cap + 1) + 1 + at] = cells[order[i]];
+        if (at < slot_cap) {
+            const uint32_t h = order[i];
+            const float4 a = cacc[h];
+            const uint4 c = crgb[h];
+            o3r_cell r;
+            r.key = ckey[h];
+            r.sx = a.x; r.sy = a.y; r.sz = a.z; r.n = __float_as_uint(a.w);
+            r.sr = c.x; r.sg = c.y; r.sb = c.z; r.pad = 0u;
+            slots[(size_t)d * (slot_cap + 1) + 1 + at] = r;
+        }
     }
 }
 
@@ -71,21 +71,6 @@ __global__ void __launch_bounds__(kThreads) k_unpack_slots(const o3r_cell* __res
         uint32_t s = 0;
         while (s + 1 < world && s_start[s + 1] <= i) ++s;
         out[i] = slots[(size_t)s * (slot_cap + 1) + 1 + (i - s_start[s])];
-    }
-}
-
-// voxel points of weight 1 -> partial-cell records (exact-order modes, whose batches are point lists)
-__global__ void __launch_bounds__(kThreads) k_points_to_cells(const float4* __restrict__ pts, uint32_t n, float icx, float icz,
-                                                              o3r_cell* __restrict__ out) {
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
-        const float4 p = pts[i];
-        const float z = __fadd_rn(p.z, 500.0f);
-        const uint32_t w = __float_as_uint(p.w);
-        o3r_cell c;
-        c.key = abs_cell_key(p.x, p.y, z, icx, icx, icz);
-        c.sx = p.x; c.sy = p.y; c.sz = z; c.n = 1u;
-        c.sr = (w >> 16) & 255u; c.sg = (w >> 8) & 255u; c.sb = w & 255u; c.pad = 0u;
-        out[i] = c;
     }
 }
 
@@ -155,40 +140,45 @@ int exchange_cycle_impl(o3r_ctx* ctx) {
     if (!ctx->comm) return ctx->fail(O3R_ERR_INVALID, "no communicator: call o3r_comm_init / o3r_comm_attach first");
     const uint32_t world = (uint32_t)ctx->world, cap = ctx->slot_cap;
     uint32_t* cnt = ctx->counters.as<uint32_t>();
-    // ---- this rank's cells of the cycle
-    const o3r_cell* cells = nullptr;
-    size_t n = 0;
+    // ---- this rank's cycle, pre-reduced on the combined grid (sort by compact cell key + in-order partial sums against an empty
+    //      resident: voxel.cuh engine 2): the cycle's frames overlap, so ~8x fewer records cross NVLink and reach the owners' merge
+    size_t nub = 0;
     if (ctx->last_is_vox && ctx->last_total) {
-        if (ctx->last_has_partials) { cells = ctx->partials.as<o3r_cell>(); n = ctx->last_partials; }
-        else {   // exact-order modes keep the batch as voxel points: one record per point
-            n = ctx->last_total;
-            CU(ctx->partials.ensure(n * sizeof(o3r_cell)));
-            LAUNCH(k_points_to_cells, std::min<uint32_t>(cdiv(n, kThreads), 148 * 8), kThreads, 0, ctx->vox.as<float4>(), (uint32_t)n,
-                   ctx->inv_c, ctx->inv_cz, ctx->partials.as<o3r_cell>());
-            cells = ctx->partials.as<o3r_cell>();
+        const int* bbp = ctx->last_has_cellbb ? ctx->last_cellbb : nullptr;
+        int rc;
+        if (ctx->last_has_partials) {
+            AccItemsCells items{ctx->partials.as<o3r_cell>(), nullptr, nullptr};
+            rc = acc_build_cycle(ctx, items, ctx->last_partials, false, bbp);
+        } else {   // exact-order modes keep the batch as voxel points
+            AccItemsPts items{ctx->vox.as<float4>(), nullptr, nullptr};
+            rc = acc_build_cycle(ctx, items, ctx->last_total, false, bbp);
         }
+        if (rc) return rc;
+        nub = ctx->n_cyc_ub;
+    } else {
+        ZERO(cnt + CNT_CYC, 4);
     }
-    if (n >= (1ull << 32)) return ctx->fail(O3R_ERR_INVALID, "batch too large");
-    // ---- bucket by owner: one stable radix pass on the owner id (the order of a rank's cells inside a slot is fixed)
+    // ---- bucket by owner: one stable radix pass on the owner id (a rank's cells stay in key order inside a slot)
     CU(ctx->okeys.ensure((size_t)kMaxPasses * kRsBins * 4 + sizeof(SortPlan)));
     uint32_t* ocnt = ctx->okeys.as<uint32_t>();
     ZERO(ocnt, (size_t)kMaxPasses * kRsBins * 4);
     SortU32 sb{nullptr, nullptr, nullptr, nullptr};
     CU(ctx->seg2.ensure(16));
-    const uint32_t g = std::min<uint32_t>(std::max(1u, cdiv(n, kThreads)), 148 * 8);
-    if (n) {
-        int rc = carve_sort_u32(ctx, n, sb);
+    const uint32_t g = std::min<uint32_t>(std::max(1u, cdiv(nub, kThreads)), 148 * 8);
+    if (nub) {
+        int rc = carve_sort_u32(ctx, nub, sb);
         if (rc) return rc;
         SortPlan* plan = reinterpret_cast<SortPlan*>(ocnt + kMaxPasses * kRsBins);
         SortPlan pl;
         memset(&pl, 0, sizeof(pl));
         pl.active_mask = 1; pl.final_parity = 1; pl.n_active = 1; pl.n_passes = 1; pl.bits[0] = 8;
         { int rcu = upload_small(ctx, plan, &pl, sizeof(pl)); if (rcu) return rcu; }
-        LAUNCH(k_owner_cells, g, kThreads, 0, cells, (uint32_t)n, world, sb.k0, sb.v0, ocnt, ctx->seg2.as<uint32_t>());
-        rc = sort_pairs<uint32_t>(ctx, sb.k0, sb.k1, sb.v0, sb.v1, ctx->seg2.as<uint32_t>(), 1, n, plan, 1, 0, ocnt, 0);
+        LAUNCH(k_owner, g, kThreads, 0, cnt + CNT_CYC, ctx->ckey.as<uint64_t>(), world, sb.k0, sb.v0, ocnt, ctx->seg2.as<uint32_t>());
+        rc = sort_pairs<uint32_t>(ctx, sb.k0, sb.k1, sb.v0, sb.v1, ctx->seg2.as<uint32_t>(), 1, nub, plan, 1, 0, ocnt, 0);
         if (rc) return rc;
     }
-    LAUNCH(k_pack_slots, g, kThreads, 0, cells, sb.v1, (uint32_t)n, ocnt, world, cap, ctx->x_send.as<o3r_cell>(), cnt + CNT_XFLAG);
+    LAUNCH(k_pack_slots_cyc, g, kThreads, 0, cnt + CNT_CYC, sb.v1, ctx->ckey.as<uint64_t>(), ctx->cacc.as<float4>(), ctx->crgb.as<uint4>(),
+           ocnt, world, cap, ctx->x_send.as<o3r_cell>(), cnt + CNT_XFLAG);
     // ---- all-to-all of the slots
     const size_t slot_bytes = (size_t)(cap + 1) * sizeof(o3r_cell);
     char* snd = ctx->x_send.as<char>();

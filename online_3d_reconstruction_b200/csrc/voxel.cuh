@@ -851,14 +851,25 @@ __host__ __device__ __forceinline__ uint64_t hash64(uint64_t x) {  // splitmix64
 __global__ void __launch_bounds__(kThreads) k_owner(const uint32_t* __restrict__ n_cyc_ptr, const uint64_t* __restrict__ ckey,
                                                     uint32_t world, uint32_t* __restrict__ okeys, uint32_t* __restrict__ ovals,
                                                     uint32_t* __restrict__ counts, uint32_t* __restrict__ seg) {
+    __shared__ uint32_t s_cnt[256];   // (world <= 256) the CTA's histogram: one global atomic per owner and CTA, not per cell
     const uint32_t n_cyc = *n_cyc_ptr;
     if (blockIdx.x == 0 && threadIdx.x == 0) { seg[0] = 0u; seg[1] = n_cyc; }
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n_cyc; i += gridDim.x * kThreads) {
-        const uint32_t o = (uint32_t)(hash64(ckey[i]) % world);
-        okeys[i] = o;
-        ovals[i] = i;
-        atomicAdd(&counts[o], 1u);
+    for (uint32_t r = threadIdx.x; r < world; r += kThreads) s_cnt[r] = 0u;
+    __syncthreads();
+    const uint32_t n_round = (n_cyc + 31u) & ~31u;   // whole warps take every trip (match_any below)
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n_round; i += gridDim.x * kThreads) {
+        uint32_t o = 0xffffffffu;
+        if (i < n_cyc) {
+            o = (uint32_t)(hash64(ckey[i]) % world);
+            okeys[i] = o;
+            ovals[i] = i;
+        }
+        const unsigned peers = __match_any_sync(kFull, o);
+        if (o != 0xffffffffu && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0u) atomicAdd(&s_cnt[o], (uint32_t)__popc(peers));
     }
+    __syncthreads();
+    for (uint32_t r = threadIdx.x; r < world; r += kThreads)
+        if (s_cnt[r]) atomicAdd(&counts[r], s_cnt[r]);
 }
 
 // also publishes the exchange header: counts per owner, then the cycle's cell range (6 int32), then 2 pad words
