@@ -37,11 +37,9 @@ from online_3d_reconstruction_b200 import abi, synth  # noqa: E402
 # (workload, kernel) -> dram__bytes_read.sum + dram__bytes_write.sum per launch, from the COMMITTED `ncu --set full` capture of
 # the same command (profiles/r02_ncu_full.txt) — a constant of that capture, not a property of this run (roofline.traffic_source)
 NCU_TRAFFIC = {
-    ("config2_semidense_720p", "k_bk_reduce"): 899.2e6,
-    ("config2_semidense_720p", "k_bk_scatter"): 1000.8e6,
-    ("config2_semidense_720p", "k_bk_hist"): 41.7e6,
+    ("config2_semidense_720p", "k_tv"): 181.9e6,
 }
-NCU_TRAFFIC_SOURCE = "profiles/r02_ncu_full.txt (ncu --set full --clock-control none, cold caches, one launch each)"
+NCU_TRAFFIC_SOURCE = "profiles/r02_ncu_full.txt (ncu --set full --clock-control none, cold caches, one launch)"
 
 WORKLOADS = {
     # name: (rows, cols, disp_type, J, voxel_size, min_pts, dont_downsample, frames/step, seed, Q scale)
@@ -192,6 +190,10 @@ def algorithmic_bytes(wl, n_valid, n_vox, n_cells_cycle, bd, np1=4, np2=3, n_par
         "k_bk_hist": npix * bd,
         "k_bk_scatter": npix * bd + npix * 3 + n_valid * 20,
         "k_bk_reduce": n_valid * 20 + n_part * 40,
+        # the fused tile engine (csrc/tile.cuh): SURVEY 8d's fused A+B figure — every input plane read once, 20 B per per-frame
+        # voxel (which this kernel never materialises: they live and die in shared memory) — the compaction copies the records
+        "k_tv": F * (rows * cols * bd + 3 * ny * nx) + 20 * n_vox,
+        "k_tv_compact": 2 * 40 * n_part,
         "k_acc_key": m * (item + 8),
         "k_acc_heads": m * 4,
         "k_acc_reduce": m * (4 + 4 + item) + n_cells_cycle * 40,

@@ -11,10 +11,25 @@ namespace {
 struct TvPlan {
     int ntx = 0, nty = 0;
     size_t tiles_per_frame = 0;
-    double D = 0, S = 0;             // leaf diagonal (with float slop), worst sqrt(1 + t^2) / |q| of the scan region
+    double L = 0;                    // pixels per unit of |q14 d + q15| that two points of one leaf can lie apart (tile.cuh, header)
     bool guess_pass = false;         // the guard's verdict on a nominal frame (first batch of a context)
-    double wlim(int R) const { return (double)(R + 1) / (D * S); }
+    double wlim(int R) const { return (double)(R + 1) / L; }
 };
+
+// inverse of the 3x3 part of a row-major 3x4 float matrix, in double; false when it is (numerically) singular
+inline bool tv_inv3(const float* T, double inv[9]) {
+    const double a = T[0], b = T[1], c = T[2], d = T[4], e = T[5], f = T[6], g = T[8], h = T[9], i = T[10];
+    const double A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+    const double det = a * A + b * B + c * C;
+    const double scale = std::fabs(a) + std::fabs(b) + std::fabs(c) + std::fabs(d) + std::fabs(e) + std::fabs(f) + std::fabs(g) +
+                         std::fabs(h) + std::fabs(i);
+    if (!std::isfinite(det) || !(std::fabs(det) > 1e-9 * scale * scale * scale)) return false;
+    const double r = 1.0 / det;
+    inv[0] = A * r; inv[1] = -(b * i - c * h) * r; inv[2] = (b * f - c * e) * r;
+    inv[3] = B * r; inv[4] = (a * i - c * g) * r;  inv[5] = -(a * f - c * d) * r;
+    inv[6] = C * r; inv[7] = -(a * h - b * g) * r; inv[8] = (a * e - b * d) * r;
+    return true;
+}
 
 // Geometry of the tiling and of the window bound (tile.cuh, header).  false = the engine does not apply.
 bool tv_plan(const o3r_ctx* ctx, const AParams& P, const o3r_frame* frames, int n, TvPlan& pl) {
@@ -28,7 +43,6 @@ bool tv_plan(const o3r_ctx* ctx, const AParams& P, const o3r_frame* frames, int 
     const int xlo = P.x0, xhi = P.x0 + P.nx - 1, ylo = P.bb, yhi = P.bb + P.ny - 1;
     const double tx = std::max(std::fabs(Q[0] * xlo + Q[3]), std::fabs(Q[0] * xhi + Q[3])) / std::fabs(Q[11]);
     const double ty = std::max(std::fabs(Q[5] * ylo + Q[7]), std::fabs(Q[5] * yhi + Q[7])) / std::fabs(Q[11]);
-    pl.S = std::max(std::sqrt(1.0 + tx * tx) / std::fabs(Q[0]), std::sqrt(1.0 + ty * ty) / std::fabs(Q[5]));
     // nominal depth range: disparities in (min_disparity, 2 min_disparity]
     const double w_a = Q[14] * p.min_disparity + Q[15], w_b = Q[14] * 2.0 * p.min_disparity + Q[15];
     if (!(w_a != 0.0) || !std::isfinite(w_a) || !std::isfinite(w_b) || (w_a > 0) != (w_b > 0)) return false;
@@ -38,8 +52,20 @@ bool tv_plan(const o3r_ctx* ctx, const AParams& P, const o3r_frame* frames, int 
     for (int i = 0; i < n; ++i)
         for (int a = 0; a < 3; ++a) tmax = std::max(tmax, (double)std::fabs(frames[i].T[4 * a + 3]));
     if (!std::isfinite(tmax) || !std::isfinite(range)) return false;
-    // two points of one leaf are at most its diagonal apart; the float rounding of the transformed coordinates adds a few ulps
-    pl.D = std::sqrt(3.0) * (double)ctx->leaf_f * 1.001 + 16.0 * FLT_EPSILON * (tmax + range);
+    // Two points of one leaf differ by less than the leaf edge on every WORLD axis (plus the float rounding of the transformed
+    // coordinates and of the cell function: a few ulps of the largest coordinate).  Back in the camera frame, dC = M^-1 dP:
+    // |dX| <= edge * sum_a |M^-1[0][a]| and so on, and |x1 - x2| <= (|dX| + |t2| |dZ|) |w1| / |q0| (header of tile.cuh).
+    const double edge = (double)ctx->leaf_f * 1.001 + 16.0 * FLT_EPSILON * (tmax + range);
+    pl.L = 0;
+    for (int i = 0; i < n; ++i) {
+        double inv[9];
+        if (!tv_inv3(frames[i].T, inv)) return false;
+        const double sx = std::fabs(inv[0]) + std::fabs(inv[1]) + std::fabs(inv[2]);
+        const double sy = std::fabs(inv[3]) + std::fabs(inv[4]) + std::fabs(inv[5]);
+        const double sz = std::fabs(inv[6]) + std::fabs(inv[7]) + std::fabs(inv[8]);
+        pl.L = std::max(pl.L, std::max((sx + tx * sz) / std::fabs(Q[0]), (sy + ty * sz) / std::fabs(Q[5])) * edge);
+    }
+    if (!std::isfinite(pl.L) || !(pl.L > 0)) return false;
     // the guard on a nominal frame: extents of the frustum slab, rotated by the first frame's matrix
     double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     const float* T = frames[0].T;

@@ -8,13 +8,14 @@
 //
 // Why no sort and no binning pass: inside ONE frame all points come from one projection centre, so the points of a leaf
 // (a cube of edge voxel_size / 5) lie on rays that pass through that cube: they are pixels within a few columns and rows of
-// each other.  For two points with |P1 - P2| <= D (D = the leaf diagonal, rigid transforms keep distances) and
-// homogeneous coordinate w = q14 d + q15 (depth Z = q11 / w):
-//     |x1 - x2| = |q11 / q0| |X1/Z1 - X2/Z2| = |q11 / q0| |dX - t2 dZ| / |Z1| <= D |w1| sqrt(1 + t2^2) / |q0|,   t2 = X2 / Z2,
-// and the same in y.  With R = the largest integer below D |w| S (S = the worst sqrt(1 + t^2) / |q| of the scan region) every
-// leaf-mate of a pixel lies in its (2R+1) x (2R+1) pixel window.  The host picks R from that bound, and the kernel checks the
-// bound for every valid pixel it evaluates (|w| < wlim): a violation raises TV_FLAG_RANGE and the host reruns the batch
-// with a larger window, or through the bucket engine (bucket.cuh).
+// each other.  Two points of one leaf differ by less than the leaf edge e on every world axis; in the camera frame
+// dC = M^-1 dP (M = the frame's matrix), so |dX| <= e s_x, |dZ| <= e s_z with s = the absolute row sums of M^-1.  With the
+// homogeneous coordinate w = q14 d + q15 (depth Z = q11 / w) and t2 = X2 / Z2:
+//     |x1 - x2| = |q11 / q0| |X1/Z1 - X2/Z2| = |q11 / q0| |dX - t2 dZ| / |Z1| <= e (s_x + |t2| s_z) |w1| / |q0|,
+// and the same in y.  With L = the worst e (s + t s_z) / |q| over the batch's matrices and the scan region, every leaf-mate
+// of a pixel with |w| < (R + 1) / L lies in its (2R+1) x (2R+1) pixel window.  The host picks R from that bound, and the kernel
+// checks it for every valid pixel it evaluates: a violation raises TV_FLAG_RANGE and the host reruns the batch with a larger
+// window, or through the bucket engine (bucket.cuh).
 //
 // One CTA per tile of 64 x 32 pixels (ticket order = frame, tile row, tile column):
 //   A  evaluate the tile plus a halo of R rows / 4 columns (validity, Q reprojection, rigid transform, colour, leaf cell):

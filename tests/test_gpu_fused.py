@@ -154,11 +154,11 @@ def test_fused_tile_engine_mixed_passthrough_and_grouped_frames():
     _close(got, exp)
 
 
-@pytest.mark.parametrize("voxel,engine", [(0.03, TILE), (0.06, TILE), (0.07, BUCKET)])
+@pytest.mark.parametrize("voxel,engine", [(0.03, TILE), (0.07, TILE), (0.12, BUCKET)])
 def test_fused_tile_engine_window_follows_the_leaf_size(voxel, engine):
-    """The pixel window that holds a leaf's points grows with the leaf (tile.cuh): voxel_size 0.03 needs 2 pixels at these
-    depths, 0.06 needs the widest window (4), at 0.07 the device reports disparities beyond even that window's reach and the
-    context moves to the bucket engine.  Same bit-exact per-frame centroids everywhere."""
+    """The pixel window that holds a leaf's points grows with the leaf (tile.cuh): voxel_size 0.03 needs 1 pixel at these
+    depths, 0.07 needs 3, at 0.12 the device reports disparities beyond even the widest window's reach (4) and the context
+    moves to the bucket engine.  Same bit-exact per-frame centroids everywhere."""
     keep = []
     geom = SMALL4
     p = abi.make_params(jump_pixels=1, voxel_size=voxel, merge_mode=FUSED, **geom)
@@ -169,16 +169,16 @@ def test_fused_tile_engine_window_follows_the_leaf_size(voxel, engine):
 
 
 def test_fused_tile_engine_widens_its_window_when_a_disparity_is_out_of_reach():
-    """voxel_size 0.05 starts with a 3-pixel window (good for disparities below ~135); a patch at disparity 140 makes the
-    device raise the range flag, the batch is rerun with 4 pixels and the context keeps that window."""
+    """voxel_size 0.05 starts with a 2-pixel window (good for disparities below ~150 in this geometry); a patch at disparity
+    170 makes the device raise the range flag, the batch is rerun with 3 pixels and the context keeps that window."""
     keep = []
     geom = SMALL4
     rows, cols = geom["rows"], geom["cols"]
     p = abi.make_params(jump_pixels=1, voxel_size=0.05, merge_mode=FUSED, **geom)
     seq = synth.sequence(287, 4, rows, cols)
     near = seq[1][0].copy()
-    near[30:60, 80:150] = 140
-    near[33:40, 90:100] = 141
+    near[30:60, 80:150] = 170
+    near[33:40, 90:100] = 171
     cycles = [[abi.make_frame(seq[0][0], seq[0][1], seq[0][2], keep=keep)],
               [abi.make_frame(near, seq[1][1], seq[1][2], keep=keep), abi.make_frame(seq[2][0], seq[2][1], seq[2][2], keep=keep)],
               [abi.make_frame(seq[3][0], seq[3][1], seq[3][2], keep=keep)]]
@@ -186,11 +186,11 @@ def test_fused_tile_engine_widens_its_window_when_a_disparity_is_out_of_reach():
     _close(got, exp)
 
 
-@pytest.mark.parametrize("voxel", [0.08, 0.12])
+@pytest.mark.parametrize("voxel", [0.12, 0.14])
 def test_fused_big_buckets_are_ranked_column_by_column(voxel):
-    """voxel_size 0.08 / 0.12: a leaf spans more pixels than the tile engine's widest window (the device raises the range flag
-    on the first batch and the context moves to the bucket engine), and ~210 / ~470 points fall into one 5x5-leaf bucket: above
-    128 the warp ranks one leaf column at a time (PCL's order is column-major inside a bucket), same bit-exact per-frame
+    """voxel_size 0.12 / 0.14: a leaf spans more pixels than the tile engine's widest window (the device raises the range flag
+    on the first batch and the context moves to the bucket engine), and several hundred points fall into one 5x5-leaf bucket:
+    above 128 the warp ranks one leaf column at a time (PCL's order is column-major inside a bucket), same bit-exact per-frame
     centroids."""
     keep = []
     geom = SMALL4
