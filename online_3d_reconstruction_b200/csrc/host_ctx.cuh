@@ -60,6 +60,23 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// Small device fills (zeroed counters and tables, bbox / cell-range initial values) are not launched one by one: they queue up
+// in the context and leave as ONE kernel in front of the next stream operation (every launch and CUDA call of the library goes
+// through LAUNCH / CU / NC, which flush the queue first), so stream order is what it would have been with separate kernels.
+struct FillList { uint32_t* p[8]; unsigned long long words[8]; int kind[8]; int n; };
+enum { FILL_ZERO = 0, FILL_BBOX = 1, FILL_CELLBB = 2 };   // bbox: {~0, ~0, ~0, 0, 0, 0} per 6 words; cell range: {INT_MAX x3, INT_MIN x3}
+struct FillQueue {
+    FillList L{};
+    size_t max_words = 0;
+    void add(void* p, size_t bytes, int kind) {
+        if (!bytes) return;
+        L.p[L.n] = reinterpret_cast<uint32_t*>(p); L.words[L.n] = (bytes + 3) / 4; L.kind[L.n] = kind;
+        max_words = std::max<size_t>(max_words, L.words[L.n]);
+        ++L.n;
+    }
+    void clear() { L.n = 0; max_words = 0; }
+};
+
 enum { CNT_PTS = 0, CNT_VOX = 1, CNT_CYC = 2, CNT_NEW = 3, CNT_EMIT = 4, CNT_NEWSCAN = 5, CNT_BASE = 6, CNT_NRES = 7, CNT_ZERO = 8, CNT_PART = 9, CNT_PARTCHUNK = 10,
        CNT_XFLAG = 11, CNT_XRECV = 12,
        CNT_CELLBB = 16, CNT_N = 32 };
@@ -71,6 +88,7 @@ struct o3r_ctx {
     std::mutex mu;
     std::string err;
     uint64_t launches = 0;
+    FillQueue fq;   // pending device fills (see FillList)
     cudaStream_t st = nullptr, st_copy = nullptr, st_copy2 = nullptr;   // two copy streams: the per-copy set-up gaps of one hide behind the other
     cudaEvent_t ev_copy2 = nullptr;
     std::vector<cudaEvent_t> chunk_ev;
@@ -201,14 +219,18 @@ struct o3r_ctx {
     }
 };
 
+int fill_flush(o3r_ctx* ctx);
+
 #define CU(call)                                                              \
     do {                                                                      \
+        if (ctx->fq.L.n) { int rcf_ = fill_flush(ctx); if (rcf_) return rcf_; } \
         cudaError_t e_ = (call);                                              \
         if (e_ != cudaSuccess) return ctx->fail_cuda(e_, #call, __FILE__, __LINE__);    \
     } while (0)
 
 #define LAUNCH_N(name, kernel, grid, block, smem, ...)                        \
     do {                                                                      \
+        if (ctx->fq.L.n) { int rcf_ = fill_flush(ctx); if (rcf_) return rcf_; } \
         cudaEvent_t pa_ = nullptr, pb_ = nullptr;                             \
         if (ctx->profiling) {                                                 \
             pa_ = ctx->ev_get(); pb_ = ctx->ev_get();                         \
@@ -247,51 +269,51 @@ int upload_small(o3r_ctx* ctx, void* dst, const void* src, size_t bytes) {
     }
     return O3R_OK;
 }
-// Zero fills run as kernels on the compute stream for the same reason: cudaMemsetAsync may be served by a copy engine
-// and then queues behind an input prefetch.  `bytes` and `dst` are multiples of 4 (all callers clear u32 tables).
-__global__ void __launch_bounds__(kThreads) k_zero(uint32_t* __restrict__ dst, size_t n_words) {
-    const size_t stride = (size_t)gridDim.x * kThreads;
-    size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
-    const size_t n4 = ((uintptr_t)dst % 16 == 0) ? n_words / 4 : 0;
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
-    for (size_t j = i; j < n4; j += stride) d4[j] = make_uint4(0u, 0u, 0u, 0u);
-    for (size_t j = n4 * 4 + i; j < n_words; j += stride) dst[j] = 0u;
-}
-int zero_fill(o3r_ctx* ctx, void* dst, size_t bytes) {
-    if (bytes == 0) return O3R_OK;
-    const size_t words = (bytes + 3) / 4;
-    const uint32_t g = (uint32_t)std::min<size_t>((words / 4 + kThreads - 1) / kThreads + 1, 148 * 8);
-    LAUNCH(k_zero, g, kThreads, 0, reinterpret_cast<uint32_t*>(dst), words);
-    return O3R_OK;
-}
-#define ZERO(ptr, bytes) do { int rcz_ = zero_fill(ctx, (ptr), (bytes)); if (rcz_) return rcz_; } while (0)
-// several regions in ONE launch (every launch costs a few microseconds of an otherwise idle GPU)
-struct ZeroList { uint32_t* p[8]; unsigned long long words[8]; int n; };
-__global__ void __launch_bounds__(kThreads) k_zero_list(ZeroList L) {
+// Fills run as kernels on the compute stream for the same reason: cudaMemsetAsync may be served by a copy engine and then
+// queues behind an input prefetch.  `bytes` and `dst` are multiples of 4 (all callers fill u32 tables).
+__global__ void __launch_bounds__(kThreads) k_fill_list(FillList L) {
     for (int r = 0; r < L.n; ++r) {
         uint32_t* dst = L.p[r];
         const size_t n_words = L.words[r], stride = (size_t)gridDim.x * kThreads;
         const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
-        const size_t n4 = ((uintptr_t)dst % 16 == 0) ? n_words / 4 : 0;
-        uint4* d4 = reinterpret_cast<uint4*>(dst);
-        for (size_t j = i; j < n4; j += stride) d4[j] = make_uint4(0u, 0u, 0u, 0u);
-        for (size_t j = n4 * 4 + i; j < n_words; j += stride) dst[j] = 0u;
+        if (L.kind[r] == FILL_ZERO) {
+            const size_t n4 = ((uintptr_t)dst % 16 == 0) ? n_words / 4 : 0;
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            for (size_t j = i; j < n4; j += stride) d4[j] = make_uint4(0u, 0u, 0u, 0u);
+            for (size_t j = n4 * 4 + i; j < n_words; j += stride) dst[j] = 0u;
+        } else if (L.kind[r] == FILL_BBOX) {
+            for (size_t j = i; j < n_words; j += stride) dst[j] = (j % 6 < 3) ? 0xffffffffu : 0u;
+        } else {
+            for (size_t j = i; j < n_words; j += stride) dst[j] = (j % 6 < 3) ? 0x7fffffffu : 0x80000000u;
+        }
     }
 }
+}  // namespace
+int fill_flush(o3r_ctx* ctx) {
+    if (!ctx->fq.L.n) return O3R_OK;
+    const FillList L = ctx->fq.L;
+    const uint32_t g = (uint32_t)std::min<size_t>((ctx->fq.max_words / 4 + kThreads - 1) / kThreads + 1, 148 * 8);
+    ctx->fq.clear();   // (before the launch macro: it flushes a non-empty queue)
+    LAUNCH_N("k_fill", k_fill_list, g, kThreads, 0, L);
+    return O3R_OK;
+}
+namespace {
+int fill_queue(o3r_ctx* ctx, void* dst, size_t bytes, int kind) {
+    if (bytes == 0) return O3R_OK;
+    if (ctx->fq.L.n == 8) { int rc = fill_flush(ctx); if (rc) return rc; }
+    ctx->fq.add(dst, bytes, kind);
+    return O3R_OK;
+}
+#define ZERO(ptr, bytes) do { int rcz_ = fill_queue(ctx, (ptr), (bytes), FILL_ZERO); if (rcz_) return rcz_; } while (0)
+#define FILL(ptr, bytes, kind) do { int rcz_ = fill_queue(ctx, (ptr), (bytes), (kind)); if (rcz_) return rcz_; } while (0)
+// (kept for the call sites that collect several regions themselves)
 struct ZeroBatch {
-    ZeroList L{};
-    size_t max_words = 0;
-    void add(void* p, size_t bytes) {
-        if (!bytes) return;
-        L.p[L.n] = reinterpret_cast<uint32_t*>(p); L.words[L.n] = (bytes + 3) / 4;
-        max_words = std::max<size_t>(max_words, L.words[L.n]);
-        ++L.n;
-    }
+    struct R { void* p; size_t bytes; } r[8];
+    int n = 0;
+    void add(void* p, size_t bytes) { if (bytes) { r[n].p = p; r[n].bytes = bytes; ++n; } }
 };
 int zero_batch(o3r_ctx* ctx, const ZeroBatch& B) {
-    if (!B.L.n) return O3R_OK;
-    const uint32_t g = (uint32_t)std::min<size_t>((B.max_words / 4 + kThreads - 1) / kThreads + 1, 148 * 8);
-    LAUNCH(k_zero_list, g, kThreads, 0, B.L);
+    for (int i = 0; i < B.n; ++i) { int rc = fill_queue(ctx, B.r[i].p, B.r[i].bytes, FILL_ZERO); if (rc) return rc; }
     return O3R_OK;
 }
 inline size_t disp_elem(int t) { return t == O3R_DISP_U8 ? 1 : t == O3R_DISP_U16 ? 2 : t == O3R_DISP_F32 ? 4 : 8; }

@@ -23,7 +23,7 @@ int launch_stage_a(o3r_ctx* ctx, const AParams& P, const FrameDev* fr, int n, co
                    uint32_t* keys_out, const uint32_t* out_base, uint32_t* goff) {
     const dim3 grid(P.tiles_per_frame, n);
     uint32_t* cnt = ctx->counters.as<uint32_t>();
-    LAUNCH(k_bbox_init, cdiv((size_t)n * 6, kThreads), kThreads, 0, ctx->bbox.as<uint32_t>(), n);
+    FILL(ctx->bbox.as<uint32_t>(), (size_t)(n) * 24, FILL_BBOX);
     LAUNCH_N("k_pre", (k_pre<DT>), grid, kThreads, 0, P, fr, ctx->tile_cnt.as<uint32_t>(), ctx->bbox.as<uint32_t>(),
              opt.mask_dev);
     if (opt.mask_only) return O3R_OK;
@@ -341,7 +341,7 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
                 int rc = tv_prepare(ctx, tvp, n, chunk, cap_batch, tv_guess);
                 if (rc) return rc;
                 if (ctx->keep_frame_voxels) CU(ctx->vox.ensure(cap_batch * 16));
-                LAUNCH(k_cellbb_init, 1, 32, 0, reinterpret_cast<int*>(cnt + CNT_CELLBB));
+                FILL(cnt + CNT_CELLBB, 24, FILL_CELLBB);
                 ZERO(cnt + CNT_PART, 8);
                 ctx->tiled_now = false;
             } else if (use_bucket) {
@@ -351,7 +351,7 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
                 const BkMisc M = bk_misc(ctx, n);
                 ZERO(M.flags, 8);
                 ZERO(M.dbg_cnt, 4);
-                LAUNCH(k_cellbb_init, 1, 32, 0, reinterpret_cast<int*>(cnt + CNT_CELLBB));
+                FILL(cnt + CNT_CELLBB, 24, FILL_CELLBB);
                 ZERO(cnt + CNT_PART, 8);
                 ctx->tiled_now = false;
             } else if (P.want_keys) {
@@ -359,7 +359,7 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
                 CU(ctx->vox.ensure(cap_batch * 16));
                 int rc = carve_sort_u32(ctx, cap_chunk, sb);
                 if (rc) return rc;
-                if (!ctx->retain()) LAUNCH(k_cellbb_init, 1, 32, 0, reinterpret_cast<int*>(cnt + CNT_CELLBB));
+                if (!ctx->retain()) FILL(cnt + CNT_CELLBB, 24, FILL_CELLBB);
                 ctx->tiled_now = ctx->tiled() && !(ctx->tiled_poor && (ctx->tiled_batches % 16) != 0);
                 ++ctx->tiled_batches;
                 if (ctx->tiled_now) {   // worst case one partial per item; never reached in practice (~1/8)
@@ -448,7 +448,7 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
                 vg_pts = ctx->sor_pts.as<float4>();
                 vg_off = ctx->sor_off.as<uint32_t>();
                 const uint32_t tl = std::max(1u, cdiv(per_frame_cap, kTileV));
-                LAUNCH(k_bbox_init, cdiv((size_t)nc * 6, kThreads), kThreads, 0, ctx->bbox.as<uint32_t>(), nc);
+                FILL(ctx->bbox.as<uint32_t>(), (size_t)(nc) * 24, FILL_BBOX);
                 LAUNCH(k_bbox_pts, dim3(tl, nc), kThreads, 0, vg_pts, vg_off, 0, ctx->bbox.as<uint32_t>());
                 LAUNCH(k_grid_params, cdiv(nc, 64), 64, 0, nc, ctx->bbox.as<uint32_t>(), ctx->inv_f, ctx->inv_f, ctx->inv_f,
                        ctx->grids.as<GridParams>());

@@ -99,7 +99,7 @@ int acc_build_cycle(o3r_ctx* ctx, const Items& items, size_t n, bool use_residen
     if (n >= (1ull << 32)) return ctx->fail(O3R_ERR_INVALID, "batch too large for 32-bit indices");
     int hb[6];
     if (!bb) {
-        LAUNCH(k_cellbb_init, 1, 32, 0, reinterpret_cast<int*>(cnt + CNT_CELLBB));
+        FILL(cnt + CNT_CELLBB, 24, FILL_CELLBB);
         LAUNCH_N("k_acc_cellbb", (k_acc_cellbb<Items>), std::min<uint32_t>(cdiv(n, kThreads), 148 * 8), kThreads, 0, items,
                  (uint32_t)n, ctx->inv_c, ctx->inv_cz, reinterpret_cast<int*>(cnt + CNT_CELLBB));
         int rc = read_counters(ctx);

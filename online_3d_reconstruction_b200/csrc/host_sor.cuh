@@ -33,7 +33,7 @@ int sor_filter(o3r_ctx* ctx, const SortU32& sb, const float4* pts, const uint32_
     uint32_t* cell_start = ctx->sor_rows.as<uint32_t>();   // [n_seg][kSorCellsCap + 1]
     uint32_t* cnt = ctx->counters.as<uint32_t>();
     const uint32_t gl = std::min<uint32_t>(std::max(1u, cdiv(per_seg_cap, kThreads)), 148 * 4);
-    LAUNCH(k_bbox_init, cdiv((size_t)n_seg * 6, kThreads), kThreads, 0, ctx->bbox.as<uint32_t>(), n_seg);
+    FILL(ctx->bbox.as<uint32_t>(), (size_t)(n_seg) * 24, FILL_BBOX);
     LAUNCH(k_bbox_pts, dim3(tiles, n_seg), kThreads, 0, pts, seg_off, 0, ctx->bbox.as<uint32_t>());
     LAUNCH(k_sor_grid, cdiv(n_seg, 64), 64, 0, n_seg, ctx->bbox.as<uint32_t>(), seg_off, mean_k, grids, pgrids);
     const size_t heap_bytes = (size_t)(mean_k + 1) * kSorThreads * 4;

@@ -145,7 +145,7 @@ int tv_run_chunk(o3r_ctx* ctx, const AParams& P, const TvPlan& pl, int R, int f0
         if (rcz) return rcz;
     }
     uint32_t* bbox = ctx->bbox.as<uint32_t>() + (size_t)f0 * 6;
-    LAUNCH(k_bbox_init, cdiv((size_t)nc * 6, kThreads), kThreads, 0, bbox, nc);
+    FILL(bbox, (size_t)(nc) * 24, FILL_BBOX);
     TvArgs A;
     A.frames = ctx->d_frames.as<FrameDev>() + f0;
     A.frame_pass = M.guess + f0;
@@ -183,8 +183,7 @@ int tv_run_chunk(o3r_ctx* ctx, const AParams& P, const TvPlan& pl, int R, int f0
     LAUNCH(k_scan_u32, 1, kScanThreads, 0, tile_cnt, tile_off, n_tiles, cnt + CNT_PARTCHUNK);
     LAUNCH(k_tv_compact, cdiv(n_tiles, kWarps), kThreads, 0, ctx->tv_scratch.as<o3r_cell>(), tile_cnt, tile_at, tile_off, n_tiles,
            ctx->partials.as<o3r_cell>(), cnt + CNT_PART, cnt + CNT_PARTCHUNK, (uint32_t)ctx->tv_part_cap, M.cursor, M.max_cursor,
-           M.flags);
-    LAUNCH(k_tv_check, cdiv(nc, 64), 64, 0, nc, bbox, ctx->inv_f, M.guess + f0, M.actual + f0, M.flags);
+           M.flags, nc, bbox, ctx->inv_f, M.guess + f0, M.actual + f0);
     LAUNCH(k_add_u32, 1, 32, 0, cnt + CNT_PART, cnt + CNT_PARTCHUNK);
     return O3R_OK;
 }

@@ -377,7 +377,7 @@ static int voxel_grid_dev(o3r_ctx* ctx, const float4* pts, size_t n, float ix, f
     int rc = carve_sort_u32(ctx, n, sb);
     if (rc) return rc;
     const uint32_t tiles = cdiv(n, kTileV);
-    LAUNCH(k_bbox_init, 1, kThreads, 0, ctx->bbox.as<uint32_t>(), 1);
+    FILL(ctx->bbox.as<uint32_t>(), (size_t)(1) * 24, FILL_BBOX);
     LAUNCH(k_bbox_pts, dim3(tiles, 1), kThreads, 0, pts, seg, z_shift, ctx->bbox.as<uint32_t>());
     LAUNCH(k_grid_params, 1, 32, 0, 1, ctx->bbox.as<uint32_t>(), ix, iy, iz, ctx->grids.as<GridParams>());
     LAUNCH(k_vg_key, dim3(std::min<uint32_t>(cdiv(n, kThreads), 148 * 16), 1), kThreads, 0, pts, seg,

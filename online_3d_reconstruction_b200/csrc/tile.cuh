@@ -643,8 +643,18 @@ __global__ void __launch_bounds__(kThreads) k_tv_compact(const o3r_cell* __restr
                                                          uint32_t n_tiles, o3r_cell* __restrict__ out,
                                                          const uint32_t* __restrict__ out_base, const uint32_t* __restrict__ chunk_total,
                                                          uint32_t out_cap, const uint32_t* __restrict__ cursor,
-                                                         uint32_t* __restrict__ max_cursor, uint32_t* __restrict__ flags) {
+                                                         uint32_t* __restrict__ max_cursor, uint32_t* __restrict__ flags, int n_frames,
+                                                         const uint32_t* __restrict__ bbox, float inv_f,
+                                                         const uint8_t* __restrict__ guess, uint8_t* __restrict__ actual) {
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(max_cursor, *cursor);
+    // per frame: PCL's int32 overflow guard on the exact bbox against the guess the tile kernel ran on
+    if (blockIdx.x == gridDim.x - 1)
+        for (int f = threadIdx.x; f < n_frames; f += kThreads) {
+            const GridParams G = make_grid(bbox + 6 * f, inv_f, inv_f, inv_f);
+            const uint8_t a = (uint8_t)(G.passthrough ? 1 : 0);
+            actual[f] = G.empty ? guess[f] : a;   // a frame without points has nothing to get wrong
+            if (!G.empty && a != guess[f]) atomicOr(flags, TV_FLAG_PASS);
+        }
     const bool room = (unsigned long long)*out_base + *chunk_total <= (unsigned long long)out_cap;
     if (!room && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(flags, TV_FLAG_SPACE);
     if (!room || (*flags & TV_FLAG_SPACE)) return;
@@ -661,17 +671,6 @@ __global__ void __launch_bounds__(kThreads) k_tv_compact(const o3r_cell* __restr
         dst[i] = a; dst[i + 32] = b; dst[i + 64] = c; dst[i + 96] = d;
     }
     for (; i < nw; i += 32u) dst[i] = __ldcs(src + i);
-}
-
-// per frame: PCL's int32 overflow guard on the exact bbox against the guess the kernel ran on
-__global__ void k_tv_check(int n_frames, const uint32_t* __restrict__ bbox, float inv_f, const uint8_t* __restrict__ guess,
-                           uint8_t* __restrict__ actual, uint32_t* __restrict__ flags) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= n_frames) return;
-    const GridParams G = make_grid(bbox + 6 * f, inv_f, inv_f, inv_f);
-    const uint8_t a = (uint8_t)(G.passthrough ? 1 : 0);
-    actual[f] = G.empty ? guess[f] : a;   // a frame without points has nothing to get wrong
-    if (!G.empty && a != guess[f]) atomicOr(flags, TV_FLAG_PASS);
 }
 
 }  // namespace o3r

@@ -18,11 +18,7 @@ namespace o3r {
 constexpr int kTileV = kThreads * 4;  // 1024 sorted elements per CTA in the run kernels
 
 // ---- bbox of arbitrary point segments (PCL getMinMax3D), z optionally shifted by +500 ------------------------
-__global__ void __launch_bounds__(kThreads) k_bbox_init(uint32_t* bbox, int n_seg) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_seg * 6) bbox[i] = (i % 6 < 3) ? 0xffffffffu : 0u;
-}
-
+// (bbox arrays start as {~0, ~0, ~0, 0, 0, 0} per segment: FILL_BBOX of the host's fill queue)
 __global__ void __launch_bounds__(kThreads) k_bbox_pts(const float4* __restrict__ pts, const uint32_t* __restrict__ seg_off,
                                                        int z_shift, uint32_t* __restrict__ bbox) {
     __shared__ uint32_t s_red[6];
@@ -544,10 +540,6 @@ __global__ void k_add_base(uint32_t* base, const uint32_t* total, uint32_t* goff
 
 __global__ void k_set_total(uint32_t* dst, const uint32_t* total) {
     if (threadIdx.x == 0) *dst = *total;
-}
-
-__global__ void k_cellbb_init(int* cellbb) {
-    if (threadIdx.x < 6) cellbb[threadIdx.x] = threadIdx.x < 3 ? 0x7fffffff : (int)0x80000000;
 }
 
 // compact keys of the cycle's items + whole-array digit histograms for the plan's digit layout
