@@ -345,6 +345,25 @@ def run_ours(args, rank, world, local_rank):
             ms, wall = t.tolist()
         return ms, wall, P.launch_count() - l0
 
+    def h2d_ceiling():
+        """Plain pinned -> device copies of one step's input volume, all ranks at once: what the host link gives each GPU."""
+        nbytes = int(F * (rows - 2 * p.bounding_box) * (cols - p.bounding_box - p.cols_start_aft_cutout) * (bd + 3))
+        src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        dst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        dst.copy_(src, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            dst.copy_(src, non_blocking=True)
+        barrier()
+        dt_s = (time.perf_counter() - t0) / 4
+        if world > 1:
+            t = torch.tensor([dt_s], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_s = float(t.item())
+        return nbytes / dt_s / 1e9, dt_s * 1e3
+
+    h2d_gbs, h2d_ms = h2d_ceiling()
     timed(host=False)  # untimed pass: every buffer reaches its steady-state size
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -434,6 +453,8 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": frames_total / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": int(F * roi_px * (bd + 3)), "d2h_bytes_per_step": int(d2h),
                 "h2d_note": "only the scan ROI of each frame crosses PCIe (x in [cols/8, cols-20), y in [20, rows-20))",
+                "h2d_ceiling_gbs_per_gpu": round(h2d_gbs, 2), "h2d_floor_ms_per_step": round(h2d_ms, 3),
+                "h2d_ceiling_note": f"one contiguous pinned->device copy of a step's input bytes, {world} rank(s) at once, slowest rank",
                 "compute_stream_ms_per_step": ms_e2e_ev / K, "timing": "wall clock around K steps incl. final sync",
                 "api": "o3r_frames_prefetch(next cycle) + o3r_frames_cloud(host pinned) + o3r_cloud_downsample(host pinned)"},
         "gpu_launches": int(launches), "roofline": roof,
