@@ -67,15 +67,23 @@ enum {
                                  reproducible from run to run.  While the pre-reduction does not reduce
                                  (more than one partial per two voxels: grids finer than the point spacing)
                                  it is skipped and the voxels are merged directly, as in ACCUMULATE    */
-    O3R_MERGE_ACCUMULATE_FUSED = 3 /* the fused disparity -> cloud -> voxel pipeline: a cycle's points are binned once into
-                                 buckets of 5 x 5 per-frame leaf columns (= one combined cell) and every bucket is finished
-                                 in shared memory: per-frame VoxelGrid centroids (bit-identical to ACCUMULATE's, each leaf
-                                 summed in scan order) are folded straight into one partial sum per combined cell; the
-                                 per-frame clouds are never written to memory, so o3r_last_batch_points is unsupported
-                                 (frame_counts are still reported).  Same result contract as ACCUMULATE_TILED: keys, counts,
-                                 colour sums exact, centroids within float reassociation (<= 1e-5 relative), reproducible.
-                                 Batches the engine cannot take (StatisticalOutlierRemoval on, a Q without the rectified-
-                                 stereo sparsity, more than 256 points in one bucket) run as ACCUMULATE_TILED             */
+    O3R_MERGE_ACCUMULATE_FUSED = 3 /* the fused disparity -> cloud -> voxel pipeline: the per-frame clouds are never written to
+                                 memory.  Three engines serve it, best first (o3r_last_batch_engine):
+                                 2 tile   — dense scans (jump_pixels 1, no keypoints) of a rectified-stereo Q: ONE kernel from
+                                            the disparity / colour planes to per-cell partial sums; a tile of 64 x 32 pixels and
+                                            its halo are evaluated into shared memory, the points of a per-frame leaf are found
+                                            in a small pixel window around the leaf's first point and summed in scan order
+                                            (per-frame VoxelGrid centroids bit-identical to ACCUMULATE's), and the centroids
+                                            are summed per combined cell inside the tile;
+                                 1 bucket — strided scans, keypoints, rows that are not 4-aligned, leaves wider than the
+                                            widest pixel window: points are binned once into buckets of 5 x 5 leaf columns
+                                            and every bucket is finished in shared memory;
+                                 0 sort   — everything else (StatisticalOutlierRemoval on, a Q without the rectified-stereo
+                                            sparsity, device-side limits of the other two exceeded, a combined grid so fine
+                                            that nothing reduces): runs as ACCUMULATE_TILED.
+                                 o3r_last_batch_points is unsupported while engines 1 / 2 serve the batch (frame_counts are
+                                 still reported).  Same result contract as ACCUMULATE_TILED: keys, counts, colour sums exact,
+                                 centroids within float reassociation (<= 1e-5 relative), reproducible bit for bit           */
 };
 
 /* Read-only configuration: the `Pose` members the path reads (pose.h:93-98,108,118,126-128,149,168). */
@@ -285,12 +293,13 @@ int o3r_set_keep_frame_voxels(o3r_ctx* ctx, int keep);
 /* ---- the exchange inside the library -------------------------------------------------------------------------------------
  * One process per GPU; rank r reconstructs the cycle's frames f with f mod world == r (the reference's 7-thread fan-out,
  * pose.cpp:383-424, spread over GPUs) and owns the combined-grid cells whose hash64(key) mod world == r.  After each
- * o3r_frames_cloud* call every rank calls o3r_exchange_cycle: the batch's partial cells are bucketed by owner and exchanged
- * with grouped ncclSend / ncclRecv on the context's stream, and what arrives is folded into the rank's shard.  Each (source,
- * destination) pair moves ONE fixed-size slot of slot_cells cells per cycle with the valid count in its first record, so
- * nothing about a cycle's exchange crosses the host and the call returns without waiting for the GPU.  slot_cells must be
- * the same on all ranks; size it at twice the cells one rank sends to one owner in a cycle (a rank's partial cells per cycle
- * / world).  An overflowing slot drops cells: the next o3r_cloud_downsample then fails with O3R_ERR_CAPACITY.
+ * o3r_frames_cloud* call every rank calls o3r_exchange_cycle: the batch is pre-reduced on the combined grid (one record per
+ * distinct cell of the cycle), the cells are bucketed by owner and exchanged with grouped ncclSend / ncclRecv on the context's
+ * stream, and what arrives is folded into the rank's shard.  Each (source, destination) pair moves ONE fixed-size slot of
+ * slot_cells cells per cycle with the valid count in its first record, so nothing about a cycle's exchange crosses the host
+ * and the call returns without waiting for the GPU.  slot_cells must be the same on all ranks; size it at twice the cells one
+ * rank sends to one owner in a cycle (the distinct combined-grid cells of a rank's cycle / world — o3r_cloud_size after one
+ * probe cycle).  An overflowing slot drops cells: the next o3r_cloud_downsample then fails with O3R_ERR_CAPACITY.
  * The union of the ranks' o3r_cloud_downsample outputs, ordered by cell key, is the single-GPU cloud: keys, counts and
  * colours exactly, centroids within float reassociation (1e-5 relative).
  * NCCL is loaded at run time (libnccl.so.2); o3r_comm_unique_id + o3r_comm_init create a communicator of the library's own
@@ -317,11 +326,11 @@ int o3r_profile_read(o3r_ctx* ctx, char* buf, size_t cap);
 
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */
 uint64_t o3r_launch_count(const o3r_ctx* ctx);
-/* Tile partial cells the last batch produced (O3R_MERGE_ACCUMULATE_TILED; 0 otherwise): the record count the
+/* Partial cells the last batch produced (O3R_MERGE_ACCUMULATE_TILED / _FUSED; 0 otherwise): the record count the
  * merge's sort and reduce ran on, for traffic accounting. */
 size_t o3r_last_batch_partials(const o3r_ctx* ctx);
-/* Engine the last batch ran through: 1 = the fused bucket engine (O3R_MERGE_ACCUMULATE_FUSED), 0 = the sort engine
- * (every other mode, and FUSED batches the bucket engine could not take). */
+/* Engine the last batch ran through: 2 = the tile engine, 1 = the bucket engine (both O3R_MERGE_ACCUMULATE_FUSED only),
+ * 0 = the sort engine (every other mode, and FUSED batches the other two could not take). */
 int o3r_last_batch_engine(const o3r_ctx* ctx);
 /* The CUDA stream all work of the context is issued on (a cudaStream_t) — for event timing. */
 void* o3r_stream(o3r_ctx* ctx);

@@ -533,11 +533,11 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
                 continue;
             }
             ctx->tv_guess = actual[n - 1];
-            {   // A combined grid finer than the pixel footprint leaves (nearly) one record per point: a 40-byte record per
+            {   // A combined grid fine against the sideways scatter of the points leaves one record per 1-3 points: a 40-byte record per
                 // 16-byte point is then a loss, and the sort engine's direct merge of the points serves the context from here on.
                 size_t total_vox = 0;
                 for (int i = 0; i < n; ++i) total_vox += ctx->h_offs[i + 1];
-                if ((size_t)ctx->h_counters[CNT_PART] * 2 > total_vox && total_vox > 0) ctx->tv_off = ctx->bucket_off = true;
+                if ((size_t)ctx->h_counters[CNT_PART] * 4 > total_vox && total_vox > 0) ctx->tv_off = ctx->bucket_off = true;
             }
             ctx->h_offs[0] = 0;
             for (int i = 0; i < n; ++i) ctx->h_offs[i + 1] += ctx->h_offs[i];

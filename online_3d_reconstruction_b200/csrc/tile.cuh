@@ -179,8 +179,33 @@ __device__ __forceinline__ uint32_t tv_eval4(const AParams& P, const FrameDev& F
     return mask;
 }
 
+// The window positions LATER than a pixel in scan order, numbered in scan order: (0, 1..R), then rows 1..R with columns -R..R.
+template <int R>
+struct TvLater {
+    static constexpr int W = 2 * R + 1, N = R + R * W;
+    __device__ static __forceinline__ constexpr int bit(int dr, int dc) { return dr == 0 ? dc - 1 : R + (dr - 1) * W + (dc + R); }
+    __device__ static __forceinline__ int offset(int k, int nc) {   // plane offset of position k
+        if (k < R) return k + 1;
+        const int q = k - R, dr = q / W;
+        return (dr + 1) * nc + (q - dr * W) - R;
+    }
+};
 template <int R>
 struct TvMask { typedef uint32_t type; };
+// four consecutive masks as 16-byte shared-memory accesses (a lane's stride is 16 / 32 bytes: scalar accesses would conflict 4-way)
+__device__ __forceinline__ void tv_st4(uint32_t* m, const uint32_t (&v)[4]) { *reinterpret_cast<uint4*>(m) = make_uint4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void tv_st4(unsigned long long* m, const unsigned long long (&v)[4]) {
+    *reinterpret_cast<ulonglong2*>(m) = make_ulonglong2(v[0], v[1]);
+    *reinterpret_cast<ulonglong2*>(m + 2) = make_ulonglong2(v[2], v[3]);
+}
+__device__ __forceinline__ void tv_ld4(const uint32_t* m, uint32_t (&v)[4]) {
+    const uint4 a = *reinterpret_cast<const uint4*>(m);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void tv_ld4(const unsigned long long* m, unsigned long long (&v)[4]) {
+    const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(m), b = *reinterpret_cast<const ulonglong2*>(m + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
 template <>
 struct TvMask<4> { typedef unsigned long long type; };
 __device__ __forceinline__ int tv_ffs(uint32_t m) { return __ffs((int)m) - 1; }
@@ -353,82 +378,122 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
     }
     if (tid == 0 && S.bad) atomicOr(A.flags, TV_FLAG_RANGE);
 
-    // ---- B: first points of the leaves fold their window mates in scan order -----------------------------------------------
-    if (R > 0) {
+    // ---- B: the leaves.  A pixel's leaf-mates lie in its window; it is its leaf's FIRST point iff no earlier pixel marks it.
+    if (R > 0 && !pass) {
+        typedef TvLater<R> LW;
+        M* const mlS = reinterpret_cast<M*>(&S.u);   // (the LUT is dead, the cell counters not yet alive) per core pixel: its verified later mates
+        // B1  every pixel of the core and of the halo rows above / columns beside it compares the hashes of the window positions
+        //     LATER in scan order (half of the window: every pair is looked at once), verifies an equal hash on the cell itself,
+        //     and marks the mate "not first" (bit 31 of its colour word: all writers write the same value).  Core pixels keep
+        //     the mask of their verified mates.
+        for (int g = tid; g < (G::HY + kTvH) * (G::NC / 4); g += kThreads) {
+            const int lr = g / (G::NC / 4), lc = (g - lr * (G::NC / 4)) * 4;
+            const int o = lr * G::NC + lc;
+            const uint4 h4 = *reinterpret_cast<const uint4*>(SH + o);
+            if ((h4.x & h4.y & h4.z & h4.w) == kTvNoHash) {   // nothing valid here (masks of a core group: none)
+                if (lr >= G::HY && lc >= G::HX && lc < G::HX + kTvW) {
+                    const M zero[4] = {0, 0, 0, 0};
+                    tv_st4(mlS + ((lr - G::HY) * kTvW + (lc - G::HX)), zero);
+                }
+                continue;
+            }
+            const uint32_t h[4] = {h4.x, h4.y, h4.z, h4.w};
+            M ml[4] = {0, 0, 0, 0};
+            const uint4 none = make_uint4(kTvNoHash, kTvNoHash, kTvNoHash, kTvNoHash);
 #pragma unroll
-    for (int q = 0; q < kTvQ; ++q) {
-        const int g = tid + q * kThreads;
-        const int cr = g / kTvGroupsRow, cg = g - cr * kTvGroupsRow;
-        const int lr = cr + G::HY, lc = cg * 4 + G::HX;
-        const int o = lr * G::NC + lc;
-        const uint4 h4 = *reinterpret_cast<const uint4*>(SH + o);
-        const uint32_t h[4] = {h4.x, h4.y, h4.z, h4.w};
-        M me[4] = {0, 0, 0, 0}, ml[4] = {0, 0, 0, 0};
-        if (R > 0 && !pass && (h4.x & h4.y & h4.z & h4.w) != kTvNoHash) {
-#pragma unroll
-            for (int dr = -R; dr <= R; ++dr) {
+            for (int dr = 0; dr <= R; ++dr) {
                 const uint32_t* hr = SH + (lr + dr) * G::NC + lc - 4;
-                const uint4 a = *reinterpret_cast<const uint4*>(hr), b = *reinterpret_cast<const uint4*>(hr + 4),
-                            c = *reinterpret_cast<const uint4*>(hr + 8);
+                const uint4 a = (lc >= 4 && dr > 0) ? *reinterpret_cast<const uint4*>(hr) : none;
+                const uint4 b = *reinterpret_cast<const uint4*>(hr + 4);
+                const uint4 c = (lc + 8 <= G::NC) ? *reinterpret_cast<const uint4*>(hr + 8) : none;
                 const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
 #pragma unroll
-                    for (int dc = -R; dc <= R; ++dc) {
-                        const int idx = (dr + R) * G::W + (dc + R);
-                        if (idx == G::S) continue;
-                        if (w[4 + j + dc] == h[j]) {
-                            if (idx < G::S) me[j] |= (M)1 << idx;
-                            else ml[j] |= (M)1 << (idx - G::S - 1);
-                        }
-                    }
+                    for (int dc = (dr == 0 ? 1 : -R); dc <= R; ++dc)
+                        if (w[4 + j + dc] == h[j]) ml[j] |= (M)1 << LW::bit(dr, dc);
             }
-        }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (h[j] == kTvNoHash) continue;
-            const int oc = o + j;
-            float4 p = make_float4(SX[oc], SY[oc], SZ[oc], __uint_as_float(SC[oc]));
-            float4 c = p;
-            if (R > 0 && !pass) {
-                int ci, cj, ck;
-                bk_cell(p.x, p.y, p.z, A.inv_f, ci, cj, ck);
-                bool head = true;
-                M e = me[j];
-                while (e) {   // an equal hash earlier in scan order: the leaf's first point lies there if the cell really is the same
-                    const int idx = tv_ffs(e);
-                    e &= e - 1;
-                    const int dr = idx / G::W - R, dc = idx - (idx / G::W) * G::W - R;
-                    const int on = oc + dr * G::NC + dc;
-                    int ni, nj, nk;
-                    bk_cell(SX[on], SY[on], SZ[on], A.inv_f, ni, nj, nk);
-                    if (ni == ci && nj == cj && nk == ck) { head = false; break; }
-                }
-                if (!head) continue;
-                M l = ml[j];
+            for (int j = 0; j < 4; ++j) {
+                M l = h[j] == kTvNoHash ? (M)0 : ml[j], keep = 0;
                 if (l) {
-                    float sx = __fadd_rn(0.f, p.x), sy = __fadd_rn(0.f, p.y), sz = __fadd_rn(0.f, p.z);   // (the oracle's sums start at +0)
-                    uint32_t w = __float_as_uint(p.w);
-                    uint32_t cn = 1, r = (w >> 16) & 255u, gg = (w >> 8) & 255u, bb = w & 255u;
+                    const int oc = o + j;
+                    int ci, cj, ck;
+                    bk_cell(SX[oc], SY[oc], SZ[oc], A.inv_f, ci, cj, ck);
                     while (l) {
-                        const int idx = tv_ffs(l) + G::S + 1;
+                        const int k = tv_ffs(l);
                         l &= l - 1;
-                        const int dr = idx / G::W - R, dc = idx - (idx / G::W) * G::W - R;
-                        const int on = oc + dr * G::NC + dc;
-                        const float nx = SX[on], ny = SY[on], nz = SZ[on];
+                        const int on = oc + LW::offset(k, G::NC);
                         int ni, nj, nk;
-                        bk_cell(nx, ny, nz, A.inv_f, ni, nj, nk);
+                        bk_cell(SX[on], SY[on], SZ[on], A.inv_f, ni, nj, nk);
                         if (ni == ci && nj == cj && nk == ck) {
-                            sx = __fadd_rn(sx, nx); sy = __fadd_rn(sy, ny); sz = __fadd_rn(sz, nz);
-                            w = SC[on];
-                            r += (w >> 16) & 255u; gg += (w >> 8) & 255u; bb += w & 255u;
-                            ++cn;
+                            keep |= (M)1 << k;
+                            SC[on] |= 0x80000000u;
                         }
                     }
-                    c = bk_centroid(sx, sy, sz, cn, r, gg, bb);
-                } else {   // a leaf of one point: (0 + x) / 1 (only -0 changes, to +0), colour as it is
-                    c.x = __fadd_rn(0.f, p.x); c.y = __fadd_rn(0.f, p.y); c.z = __fadd_rn(0.f, p.z);
                 }
+                ml[j] = keep;
+            }
+            if (lr >= G::HY && lc >= G::HX && lc < G::HX + kTvW) tv_st4(mlS + ((lr - G::HY) * kTvW + (lc - G::HX)), ml);
+        }
+        __syncthreads();
+        // B2  a first point with mates left-folds them in scan order — the oracle's stable order, so the per-frame VoxelGrid
+        //     centroid is bit-identical — divides (pcl::CentroidPoint) and leaves the centroid in its own plane slot (nobody else
+        //     reads a first point any more).  Each lane walks its own pending pixels back to back.
+        uint32_t todo = 0;
+#pragma unroll
+        for (int q = 0; q < kTvQ; ++q) {
+            const int g = tid + q * kThreads;
+            const int o = (g / kTvGroupsRow + G::HY) * G::NC + (g % kTvGroupsRow) * 4 + G::HX;
+            const uint4 h4 = *reinterpret_cast<const uint4*>(SH + o), c4 = *reinterpret_cast<const uint4*>(SC + o);
+            const uint32_t hv[4] = {h4.x, h4.y, h4.z, h4.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w};
+            M mv[4];
+            tv_ld4(mlS + g * 4, mv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (hv[j] != kTvNoHash && !(cv[j] & 0x80000000u) && mv[j] != 0) todo |= 1u << (q * 4 + j);
+        }
+        while (todo) {
+            const int r = __ffs((int)todo) - 1;
+            todo &= todo - 1;
+            const int g = tid + (r >> 2) * kThreads;
+            const int oc = (g / kTvGroupsRow + G::HY) * G::NC + (g % kTvGroupsRow) * 4 + G::HX + (r & 3);
+            M l = mlS[g * 4 + (r & 3)];
+            float sx = __fadd_rn(0.f, SX[oc]), sy = __fadd_rn(0.f, SY[oc]), sz = __fadd_rn(0.f, SZ[oc]);   // (the oracle's sums start at +0)
+            uint32_t w = SC[oc];
+            uint32_t cn = 1, cr = (w >> 16) & 255u, cg = (w >> 8) & 255u, cb = w & 255u;
+            while (l) {
+                const int k = tv_ffs(l);
+                l &= l - 1;
+                const int on = oc + LW::offset(k, G::NC);
+                sx = __fadd_rn(sx, SX[on]); sy = __fadd_rn(sy, SY[on]); sz = __fadd_rn(sz, SZ[on]);
+                w = SC[on];
+                cr += (w >> 16) & 255u; cg += (w >> 8) & 255u; cb += w & 255u;
+                ++cn;
+            }
+            const float4 c = bk_centroid(sx, sy, sz, cn, cr, cg, cb);
+            SX[oc] = c.x; SY[oc] = c.y; SZ[oc] = c.z; SC[oc] = __float_as_uint(c.w);
+        }
+        __syncthreads();
+    }
+    if (R > 0) {   // the thread's own core pixels: the unmarked ones are the per-frame voxels
+#pragma unroll
+        for (int r = 0; r < kTvQ * 4; ++r) {
+            const int g = tid + (r >> 2) * kThreads;
+            const int o = (g / kTvGroupsRow + G::HY) * G::NC + (g % kTvGroupsRow) * 4 + G::HX;
+            // (16-byte loads of the group's four pixels; the compiler keeps one copy per group)
+            const uint4 h4 = *reinterpret_cast<const uint4*>(SH + o), c4 = *reinterpret_cast<const uint4*>(SC + o);
+            const float4 x4 = *reinterpret_cast<const float4*>(SX + o), y4 = *reinterpret_cast<const float4*>(SY + o),
+                         z4 = *reinterpret_cast<const float4*>(SZ + o);
+            const int j = r & 3;
+            const uint32_t hq = j == 0 ? h4.x : j == 1 ? h4.y : j == 2 ? h4.z : h4.w;
+            const uint32_t w = j == 0 ? c4.x : j == 1 ? c4.y : j == 2 ? c4.z : c4.w;
+            if (hq == kTvNoHash || (w & 0x80000000u)) continue;
+            float4 c = make_float4(j == 0 ? x4.x : j == 1 ? x4.y : j == 2 ? x4.z : x4.w, j == 0 ? y4.x : j == 1 ? y4.y : j == 2 ? y4.z : y4.w,
+                                   j == 0 ? z4.x : j == 1 ? z4.y : j == 2 ? z4.z : z4.w, __uint_as_float(w));
+            if (!pass) {   // a leaf of one point: (0 + x) / 1 — only -0 changes, to +0 (a folded centroid is never -0); PCL's
+                           // pass-through keeps the point as it is
+                c.x = __fadd_rn(0.f, c.x); c.y = __fadd_rn(0.f, c.y); c.z = __fadd_rn(0.f, c.z);
             }
             if (A.dbg_vox) A.dbg_vox[atomicAdd(A.dbg_cnt, 1u)] = c;
             c.z = __fadd_rn(c.z, 500.0f);   // pose_functions.cpp:1666
@@ -437,10 +502,9 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
             cmn[0] = min(cmn[0], vi); cmx[0] = max(cmx[0], vi);
             cmn[1] = min(cmn[1], vj); cmx[1] = max(cmx[1], vj);
             cmn[2] = min(cmn[2], vk); cmx[2] = max(cmx[2], vk);
-            cen[q * 4 + j] = c;
-            cvalid |= 1u << (q * 4 + j);
+            cen[r] = c;
+            cvalid |= 1u << r;
         }
-    }
     }
     // ---- C: the tile's cells -------------------------------------------------------------------------------------------
     {
