@@ -37,7 +37,7 @@ from online_3d_reconstruction_b200 import abi, synth  # noqa: E402
 # (workload, kernel) -> dram__bytes_read.sum + dram__bytes_write.sum per launch, from the COMMITTED `ncu --set full` capture of
 # the same command (profiles/r02_ncu_full.txt) — a constant of that capture, not a property of this run (roofline.traffic_source)
 NCU_TRAFFIC = {
-    ("config2_semidense_720p", "k_tv"): 181.9e6,
+    ("config2_semidense_720p", "k_tv"): 180.4e6,
 }
 NCU_TRAFFIC_SOURCE = "profiles/r02_ncu_full.txt (ncu --set full --clock-control none, cold caches, one launch)"
 
@@ -181,7 +181,7 @@ def algorithmic_bytes(wl, n_valid, n_vox, n_cells_cycle, bd, np1=4, np2=3, n_par
         "k_emit": npix * bd + npix * 3 + n_valid * (16 + (0 if nd else 4)),
         "k_rs_ghist_u32": n_valid * 4,
         # first pass reads keys only (values are the element index), every pass writes key + value
-        "k_rs_onesweep_u32": n_valid * (4 + 8) + (np1 - 1) * n_valid * 16 + np2 * m * 16,
+        "k_rs_onesweep_u32": (n_valid * (4 + 8) + (np1 - 1) * n_valid * 16 if np1 > 0 else 0) + np2 * m * 16,
         "k_vg_heads": n_valid * 4,
         "k_vg_reduce_w": n_valid * (4 + 4 + 16) + n_vox * 16,
         "k_cell_prereduce": n_vox * 16 + n_part * 40,
