@@ -117,12 +117,13 @@ int tv_prepare(o3r_ctx* ctx, const TvPlan& pl, int n, int chunk, size_t cap_batc
 template <int DT, int R>
 int tv_launch(o3r_ctx* ctx, const AParams& P, const TvArgs& A, uint32_t n_tiles) {
     const uint32_t bit = 1u << (DT * (kTvMaxR + 1) + R);
+    static const size_t extra = getenv("O3R_TV_EXTRA_SMEM") ? (size_t)atoi(getenv("O3R_TV_EXTRA_SMEM")) : 0;   // occupancy experiments
     if (!(ctx->tv_attr & bit)) {   // (the attribute is per function and device)
-        CU(cudaFuncSetAttribute(k_tv<DT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tv_smem<R>()));
+        CU(cudaFuncSetAttribute(k_tv<DT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tv_smem<R>() + extra)));
         cudaFuncSetAttribute(k_tv<DT, R>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         ctx->tv_attr |= bit;
     }
-    LAUNCH_N("k_tv", (k_tv<DT, R>), n_tiles, kThreads, tv_smem<R>(), P, A);
+    LAUNCH_N("k_tv", (k_tv<DT, R>), n_tiles, kTvThreads, tv_smem<R>() + extra, P, A);
     return O3R_OK;
 }
 

@@ -48,19 +48,32 @@
 
 namespace o3r {
 
-constexpr int kTvW = 64, kTvH = 32;                    // core pixels of a tile
+#ifndef O3R_TV_H
+#define O3R_TV_H 32
+#endif
+#ifndef O3R_TV_BINS
+#define O3R_TV_BINS 512
+#endif
+#ifndef O3R_TV_THREADS
+#define O3R_TV_THREADS 256
+#endif
+constexpr int kTvThreads = O3R_TV_THREADS;             // threads of a tile's CTA: the kernel is latency-bound, T ~ 0.27 + 2.24 / (resident
+constexpr int kTvWarps = kTvThreads / 32;              // CTAs of 8 warps) ms on configs[1] — more warps per SM is what buys time
+constexpr int kTvW = 64, kTvH = O3R_TV_H;              // core pixels of a tile
 constexpr int kTvGroupsRow = kTvW / 4;                 // 4-pixel groups per core row
 constexpr int kTvCoreGroups = kTvGroupsRow * kTvH;     // 512: two per thread
-constexpr int kTvQ = kTvCoreGroups / kThreads;         // core groups per thread
+constexpr int kTvQ = kTvCoreGroups / kTvThreads;         // core groups per thread
 constexpr int kTvItems = kTvW * kTvH;                  // centroids a tile can emit
-constexpr int kTvBinsN = 1024;                         // distinct combined-grid cells a tile can sum (more: one record per centroid)
+constexpr int kTvBinsN = O3R_TV_BINS;                       // distinct combined-grid cells a tile can sum (more: one record per centroid)
 template <int R>
 struct TvBins { static constexpr int value = kTvBinsN; };
 constexpr int kTvHash = 2 * kTvItems;                  // hash slots of the sparse cell table (load <= 0.5)
-static_assert(kTvHash == 4096, "the hash shift below assumes 4096 slots");
+static_assert((kTvHash & (kTvHash - 1)) == 0 && kTvHash <= 65536, "hash slots: a power of two that a 16-bit cell number covers");
+constexpr int tv_log2(int v) { return v <= 1 ? 0 : 1 + tv_log2(v >> 1); }
+constexpr int kTvHashShift = 32 - tv_log2(kTvHash);
 constexpr int kTvMaxR = 4;
-constexpr uint32_t kTvNoHash = 0xffffffffu;            // invalid pixel (valid hashes keep bit 31 clear)
-static_assert(kTvQ * kThreads == kTvCoreGroups, "core groups must divide evenly");
+constexpr uint32_t kTvNoHash = 0xffffu;                // invalid pixel (valid hashes keep 15 bits; the plane holds 16-bit words)
+static_assert(kTvQ * kTvThreads == kTvCoreGroups, "core groups must divide evenly");
 
 enum { TV_FLAG_RANGE = 1u, TV_FLAG_SPACE = 2u, TV_FLAG_PASS = 4u };
 
@@ -71,14 +84,22 @@ struct TvGeom {
     static constexpr int W = 2 * R + 1, S = R * W + R; // window width, index of the pixel itself
     // the planes (R > 0), later the sparse cell table (8-byte keys + 2-byte cell numbers), later the centroids in cell order
     static constexpr size_t alias_bytes = (size_t)kTvHash * 10 > (size_t)kTvItems * 16 ? (size_t)kTvHash * 10 : (size_t)kTvItems * 16;
-    static constexpr size_t plane_bytes = (R && (size_t)5 * N * 4 > alias_bytes) ? (size_t)5 * N * 4 : alias_bytes;
+    static constexpr size_t plane_bytes = (R && (size_t)N * 18 > alias_bytes) ? (size_t)N * 18 : alias_bytes;   // 2-byte hash + x, y, z, rgb
 };
 
-template <int NB>
+// mask of a pixel's later window positions: R (2R + 2) bits
+template <int R>
+struct TvMask { typedef uint32_t type; };
+template <>
+struct TvMask<4> { typedef unsigned long long type; };
+
+template <int NB, int MB>
 struct TvTail {
+    static_assert(NB % kTvThreads == 0, "cells per thread");
     union {
-        uint16_t cnt[kWarps][NB + 2];        // phase C: per warp and cell: count, then exclusive prefix over the warps
+        uint16_t cnt[kTvWarps][NB + 2];        // phase C: per warp and cell: count, then exclusive prefix over the warps
         struct { double rl[256]; float zl[256]; } lut;   // phase A
+        unsigned long long ml[kTvItems * MB / 8];   // phase B: per core pixel the mask of its verified later mates (MB bytes each)
     } u;
     uint32_t bd[NB + 1];                     // per cell: first item | rank among the non-empty cells << 16
     uint32_t scan[34];
@@ -88,7 +109,14 @@ struct TvTail {
     uint32_t any_valid, bad;
 };
 template <int R>
-constexpr size_t tv_smem() { return TvGeom<R>::plane_bytes + sizeof(TvTail<TvBins<R>::value>); }
+constexpr size_t tv_smem() { return TvGeom<R>::plane_bytes + sizeof(TvTail<TvBins<R>::value, (int)sizeof(typename TvMask<R>::type)>); }
+
+// CTAs of this instantiation that fit an SM's 228 KB (1 KB reserved per CTA): the register budget follows from it
+template <int R>
+constexpr int tv_ctas_per_sm() {
+    return (int)((size_t)233472 / (tv_smem<R>() + 1024)) < 1 ? 1 : (int)((size_t)233472 / (tv_smem<R>() + 1024)) > 4 ? 4
+                                                                   : (int)((size_t)233472 / (tv_smem<R>() + 1024));
+}
 
 struct TvArgs {
     const FrameDev* frames;
@@ -114,7 +142,7 @@ struct TvArgs {
 __device__ __forceinline__ uint32_t tv_hash(int i, int j, int k) {
     uint32_t h = (uint32_t)i * 0x9e3779b1u + (uint32_t)j * 0x85ebca77u + (uint32_t)k * 0xc2b2ae3du;
     h ^= h >> 15;
-    return h & 0x7fffffffu;
+    return (h ^ (h >> 17)) & 0x7fffu;
 }
 
 // The thread's 4 consecutive pixels (xb .. xb + 3, y) of the dense scan: validity + camera-frame point, exactly the
@@ -190,8 +218,7 @@ struct TvLater {
         return (dr + 1) * nc + (q - dr * W) - R;
     }
 };
-template <int R>
-struct TvMask { typedef uint32_t type; };
+
 // four consecutive masks as 16-byte shared-memory accesses (a lane's stride is 16 / 32 bytes: scalar accesses would conflict 4-way)
 __device__ __forceinline__ void tv_st4(uint32_t* m, const uint32_t (&v)[4]) { *reinterpret_cast<uint4*>(m) = make_uint4(v[0], v[1], v[2], v[3]); }
 __device__ __forceinline__ void tv_st4(unsigned long long* m, const unsigned long long (&v)[4]) {
@@ -206,8 +233,6 @@ __device__ __forceinline__ void tv_ld4(const unsigned long long* m, unsigned lon
     const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(m), b = *reinterpret_cast<const ulonglong2*>(m + 2);
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
-template <>
-struct TvMask<4> { typedef unsigned long long type; };
 __device__ __forceinline__ int tv_ffs(uint32_t m) { return __ffs((int)m) - 1; }
 __device__ __forceinline__ int tv_ffs(unsigned long long m) { return __ffsll((long long)m) - 1; }
 
@@ -234,25 +259,55 @@ __device__ __forceinline__ void tv_cellbb(const TvArgs& A, const int* cmin, cons
     }
 }
 
+// Exclusive scan of one value per thread over the tile's CTA (kTvThreads threads).  `sm` is 34 words of shared memory.  Ends with a
+// barrier so `sm` may be reused immediately.
+__device__ __forceinline__ uint32_t tv_block_excl_scan(uint32_t v, uint32_t* sm, uint32_t& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) sm[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < kTvWarps ? sm[lane] : 0u, winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(kFull, winc, o);
+            if (lane >= o) winc += t;
+        }
+        if (lane < kTvWarps) sm[lane] = winc - w;
+        if (lane == kTvWarps - 1) sm[33] = winc;
+    }
+    __syncthreads();
+    total = sm[33];
+    const uint32_t r = sm[warp] + inc - v;
+    __syncthreads();
+    return r;
+}
+
 template <int DT, int R>
-__global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvArgs A) {
+__global__ void __launch_bounds__(kTvThreads, tv_ctas_per_sm<R>()) k_tv(AParams P, TvArgs A) {
     typedef TvGeom<R> G;
     typedef typename TvMask<R>::type M;
     extern __shared__ __align__(16) unsigned char tv_smem_raw[];
-    uint32_t* const SH = reinterpret_cast<uint32_t*>(tv_smem_raw);       // planes: hash, x, y, z, rgb
-    float* const SX = reinterpret_cast<float*>(SH + G::N);
+    uint16_t* const SH = reinterpret_cast<uint16_t*>(tv_smem_raw);       // planes: hash (16-bit), x, y, z, rgb
+    float* const SX = reinterpret_cast<float*>(tv_smem_raw + (size_t)G::N * 2);
     float* const SY = SX + G::N;
     float* const SZ = SY + G::N;
     uint32_t* const SC = reinterpret_cast<uint32_t*>(SZ + G::N);
     float4* const items = reinterpret_cast<float4*>(tv_smem_raw);      // phase C: the tile's centroids in cell order (aliases the planes)
     constexpr int NB = TvBins<R>::value;
-    TvTail<NB>& S = *reinterpret_cast<TvTail<NB>*>(tv_smem_raw + G::plane_bytes);
+    typedef TvTail<NB, (int)sizeof(M)> Tail;
+    Tail& S = *reinterpret_cast<Tail*>(tv_smem_raw + G::plane_bytes);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
 
     if (tid == 0) { S.ticket = atomicAdd(A.ticket, 1u); S.any_valid = 0u; S.bad = 0u; }
     if (tid < 3) { S.cmin[tid] = 0x7fffffff; S.cmax[tid] = (int)0x80000000; S.bb[tid] = 0xffffffffu; S.bb[3 + tid] = 0u; }
-    if (P.use_lut) { S.u.lut.rl[tid] = P.lut_r[tid]; S.u.lut.zl[tid] = P.lut_z[tid]; }
+    if (P.use_lut && tid < 256) { S.u.lut.rl[tid] = P.lut_r[tid]; S.u.lut.zl[tid] = P.lut_z[tid]; }
     __syncthreads();
     const uint32_t t = S.ticket;
     const uint32_t per_frame = (uint32_t)(A.ntx * A.nty), nt = per_frame * (uint32_t)A.n_frames;
@@ -275,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
         if (R == 0) {
 #pragma unroll
             for (int q = 0; q < kTvQ; ++q) {
-                const int g = tid + q * kThreads;
+                const int g = tid + q * kTvThreads;
                 const int cr = g / kTvGroupsRow, cg = g - cr * kTvGroupsRow;
                 const int y = y_org + cr, xb = x_org + cg * 4;
                 if (y < P.bb + P.ny && xb < P.x0 + P.nx) {
@@ -309,19 +364,26 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
                     }
                 }
             }
-        } else
-        for (int g = tid; g < G::NG; g += kThreads) {
+        } else {
+        // (the colour words are loaded whether or not a pixel turns out valid: they are in flight together with the disparity
+        //  word instead of behind it — a tile's latency, not its throughput, is what costs.  Unrolling the rounds, or keeping the
+        //  frame descriptor in registers, measured no better / worse: spills)
+        constexpr int kRounds = (G::NG + kTvThreads - 1) / kTvThreads;
+#pragma unroll 1
+        for (int it = 0; it < kRounds; ++it) {
+            const int g = tid + it * kTvThreads;
+            if (g >= G::NG) break;
             const int lr = g / (G::NC / 4), lc = (g - lr * (G::NC / 4)) * 4;
             const int y = y_org + lr, xb = x_org + lc;
-            uint4 hh = make_uint4(kTvNoHash, kTvNoHash, kTvNoHash, kTvNoHash);
+            uint2 hh = make_uint2(0xffffffffu, 0xffffffffu);
             float px[4] = {0.f, 0.f, 0.f, 0.f}, py[4] = {0.f, 0.f, 0.f, 0.f}, pz[4] = {0.f, 0.f, 0.f, 0.f};
             uint32_t rgb[4] = {0u, 0u, 0u, 0u};
             if (y >= P.bb && y < P.bb + P.ny && xb >= P.x0 && xb < P.x0 + P.nx) {   // nx % 4 == 0: a group is inside or outside
                 float X[4], Y[4], Z[4];
+                const uint32_t* c = reinterpret_cast<const uint32_t*>(F.bgr + (size_t)y * F.bgr_step + 3 * (size_t)xb);
+                const uint32_t w0 = __ldg(c), w1 = __ldg(c + 1), w2 = __ldg(c + 2);
                 const uint32_t mask = tv_eval4<DT>(P, F, S.u.lut.rl, S.u.lut.zl, xb, y, A, X, Y, Z, over);
                 if (mask) {
-                    const uint32_t* c = reinterpret_cast<const uint32_t*>(F.bgr + (size_t)y * F.bgr_step + 3 * (size_t)xb);
-                    const uint32_t w0 = __ldg(c), w1 = __ldg(c + 1), w2 = __ldg(c + 2);
                     rgb[0] = w0 & 0x00ffffffu;
                     rgb[1] = (w0 >> 24) | ((w1 & 0xffffu) << 8);
                     rgb[2] = (w1 >> 16) | ((w2 & 0xffu) << 16);
@@ -342,15 +404,16 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
                                 anyv = true;
                             }
                         }
-                    hh = make_uint4(h[0], h[1], h[2], h[3]);
+                    hh = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
                 }
             }
             const int o = lr * G::NC + lc;
-            *reinterpret_cast<uint4*>(SH + o) = hh;
+            *reinterpret_cast<uint2*>(SH + o) = hh;
             *reinterpret_cast<float4*>(SX + o) = make_float4(px[0], px[1], px[2], px[3]);
             *reinterpret_cast<float4*>(SY + o) = make_float4(py[0], py[1], py[2], py[3]);
             *reinterpret_cast<float4*>(SZ + o) = make_float4(pz[0], pz[1], pz[2], pz[3]);
             *reinterpret_cast<uint4*>(SC + o) = make_uint4(rgb[0], rgb[1], rgb[2], rgb[3]);
+        }
         }
         // the frame's exact bbox (PCL getMinMax3D) from the core pixels: every pixel is core in exactly one tile
         const unsigned anyw = __ballot_sync(kFull, anyv);
@@ -386,27 +449,28 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
         //     LATER in scan order (half of the window: every pair is looked at once), verifies an equal hash on the cell itself,
         //     and marks the mate "not first" (bit 31 of its colour word: all writers write the same value).  Core pixels keep
         //     the mask of their verified mates.
-        for (int g = tid; g < (G::HY + kTvH) * (G::NC / 4); g += kThreads) {
+        for (int g = tid; g < (G::HY + kTvH) * (G::NC / 4); g += kTvThreads) {
             const int lr = g / (G::NC / 4), lc = (g - lr * (G::NC / 4)) * 4;
             const int o = lr * G::NC + lc;
-            const uint4 h4 = *reinterpret_cast<const uint4*>(SH + o);
-            if ((h4.x & h4.y & h4.z & h4.w) == kTvNoHash) {   // nothing valid here (masks of a core group: none)
+            const uint2 h2 = *reinterpret_cast<const uint2*>(SH + o);
+            if ((h2.x & h2.y) == 0xffffffffu) {   // nothing valid here (masks of a core group: none)
                 if (lr >= G::HY && lc >= G::HX && lc < G::HX + kTvW) {
                     const M zero[4] = {0, 0, 0, 0};
                     tv_st4(mlS + ((lr - G::HY) * kTvW + (lc - G::HX)), zero);
                 }
                 continue;
             }
-            const uint32_t h[4] = {h4.x, h4.y, h4.z, h4.w};
+            const uint32_t h[4] = {h2.x & 0xffffu, h2.x >> 16, h2.y & 0xffffu, h2.y >> 16};
             M ml[4] = {0, 0, 0, 0};
-            const uint4 none = make_uint4(kTvNoHash, kTvNoHash, kTvNoHash, kTvNoHash);
+            const uint2 none = make_uint2(0xffffffffu, 0xffffffffu);
 #pragma unroll
             for (int dr = 0; dr <= R; ++dr) {
-                const uint32_t* hr = SH + (lr + dr) * G::NC + lc - 4;
-                const uint4 a = (lc >= 4 && dr > 0) ? *reinterpret_cast<const uint4*>(hr) : none;
-                const uint4 b = *reinterpret_cast<const uint4*>(hr + 4);
-                const uint4 c = (lc + 8 <= G::NC) ? *reinterpret_cast<const uint4*>(hr + 8) : none;
-                const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+                const uint16_t* hr = SH + (lr + dr) * G::NC + lc - 4;
+                const uint2 a = (lc >= 4 && dr > 0) ? *reinterpret_cast<const uint2*>(hr) : none;
+                const uint2 b = *reinterpret_cast<const uint2*>(hr + 4);
+                const uint2 c = (lc + 8 <= G::NC) ? *reinterpret_cast<const uint2*>(hr + 8) : none;
+                const uint32_t w[12] = {a.x & 0xffffu, a.x >> 16, a.y & 0xffffu, a.y >> 16, b.x & 0xffffu, b.x >> 16,
+                                        b.y & 0xffffu, b.y >> 16, c.x & 0xffffu, c.x >> 16, c.y & 0xffffu, c.y >> 16};
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -443,10 +507,11 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
         uint32_t todo = 0;
 #pragma unroll
         for (int q = 0; q < kTvQ; ++q) {
-            const int g = tid + q * kThreads;
+            const int g = tid + q * kTvThreads;
             const int o = (g / kTvGroupsRow + G::HY) * G::NC + (g % kTvGroupsRow) * 4 + G::HX;
-            const uint4 h4 = *reinterpret_cast<const uint4*>(SH + o), c4 = *reinterpret_cast<const uint4*>(SC + o);
-            const uint32_t hv[4] = {h4.x, h4.y, h4.z, h4.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w};
+            const uint2 h2 = *reinterpret_cast<const uint2*>(SH + o);
+            const uint4 c4 = *reinterpret_cast<const uint4*>(SC + o);
+            const uint32_t hv[4] = {h2.x & 0xffffu, h2.x >> 16, h2.y & 0xffffu, h2.y >> 16}, cv[4] = {c4.x, c4.y, c4.z, c4.w};
             M mv[4];
             tv_ld4(mlS + g * 4, mv);
 #pragma unroll
@@ -456,7 +521,7 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
         while (todo) {
             const int r = __ffs((int)todo) - 1;
             todo &= todo - 1;
-            const int g = tid + (r >> 2) * kThreads;
+            const int g = tid + (r >> 2) * kTvThreads;
             const int oc = (g / kTvGroupsRow + G::HY) * G::NC + (g % kTvGroupsRow) * 4 + G::HX + (r & 3);
             M l = mlS[g * 4 + (r & 3)];
             float sx = __fadd_rn(0.f, SX[oc]), sy = __fadd_rn(0.f, SY[oc]), sz = __fadd_rn(0.f, SZ[oc]);   // (the oracle's sums start at +0)
@@ -479,14 +544,15 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
     if (R > 0) {   // the thread's own core pixels: the unmarked ones are the per-frame voxels
 #pragma unroll
         for (int r = 0; r < kTvQ * 4; ++r) {
-            const int g = tid + (r >> 2) * kThreads;
+            const int g = tid + (r >> 2) * kTvThreads;
             const int o = (g / kTvGroupsRow + G::HY) * G::NC + (g % kTvGroupsRow) * 4 + G::HX;
             // (16-byte loads of the group's four pixels; the compiler keeps one copy per group)
-            const uint4 h4 = *reinterpret_cast<const uint4*>(SH + o), c4 = *reinterpret_cast<const uint4*>(SC + o);
+            const uint2 h2 = *reinterpret_cast<const uint2*>(SH + o);
+            const uint4 c4 = *reinterpret_cast<const uint4*>(SC + o);
             const float4 x4 = *reinterpret_cast<const float4*>(SX + o), y4 = *reinterpret_cast<const float4*>(SY + o),
                          z4 = *reinterpret_cast<const float4*>(SZ + o);
             const int j = r & 3;
-            const uint32_t hq = j == 0 ? h4.x : j == 1 ? h4.y : j == 2 ? h4.z : h4.w;
+            const uint32_t hq = j == 0 ? (h2.x & 0xffffu) : j == 1 ? (h2.x >> 16) : j == 2 ? (h2.y & 0xffffu) : (h2.y >> 16);
             const uint32_t w = j == 0 ? c4.x : j == 1 ? c4.y : j == 2 ? c4.z : c4.w;
             if (hq == kTvNoHash || (w & 0x80000000u)) continue;
             float4 c = make_float4(j == 0 ? x4.x : j == 1 ? x4.y : j == 2 ? x4.z : x4.w, j == 0 ? y4.x : j == 1 ? y4.y : j == 2 ? y4.z : y4.w,
@@ -549,7 +615,7 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
         uint16_t* const dense = reinterpret_cast<uint16_t*>(tv_smem_raw + (size_t)kTvHash * 8);
         {
             uint4* tz = reinterpret_cast<uint4*>(tab);
-            for (int i = tid; i < kTvHash / 2; i += kThreads) tz[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+            for (int i = tid; i < kTvHash / 2; i += kTvThreads) tz[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
             if (tid == 0) S.nbh = 0u;
         }
         __syncthreads();
@@ -560,7 +626,7 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
                           vk = __float2int_rd(__fmul_rn(cen[r].z, A.icz));
                 const unsigned long long k = ((unsigned long long)(uint32_t)(vk + Bi) << 42) | ((unsigned long long)(uint32_t)(vj + Bi) << 21) |
                                              (unsigned long long)(uint32_t)(vi + Bi);
-                uint32_t h = ((uint32_t)(k ^ (k >> 21) ^ (k >> 42)) * 0x9e3779b1u) >> 20;   // kTvHash = 4096 slots
+                uint32_t h = ((uint32_t)(k ^ (k >> 21) ^ (k >> 42)) * 0x9e3779b1u) >> kTvHashShift;
                 for (;;) {
                     const unsigned long long old = atomicCAS(&tab[h], ~0ull, k);
                     if (old == ~0ull) { dense[h] = (uint16_t)atomicAdd(&S.nbh, 1u); break; }
@@ -583,7 +649,7 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
         // more occupied cells than the table numbers (at least every second centroid alone in its cell): every centroid leaves
         // as its own single-point record, in tile order (thread, slot)
         uint32_t tot;
-        uint32_t pos = block_excl_scan((uint32_t)__popc(cvalid), S.scan, tot);
+        uint32_t pos = tv_block_excl_scan((uint32_t)__popc(cvalid), S.scan, tot);
         if (tid == 0) tv_place(A, t, tot, &S.out0);
         __syncthreads();
         if (tot == 0) return;
@@ -607,7 +673,7 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
             }
         return;
     }
-    for (int b = tid; b < (nbins + 2) * kWarps; b += kThreads) {
+    for (int b = tid; b < (nbins + 2) * kTvWarps; b += kTvThreads) {
         const int w = b / (nbins + 2), i = b - w * (nbins + 2);
         S.u.cnt[w][i == nbins + 1 ? NB + 1 : i] = 0;
     }
@@ -627,7 +693,7 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
     __syncthreads();
     // per cell: exclusive prefix over the warps; then first item / rank among the non-empty cells (packed scan)
     {
-        constexpr int BPT = NB / kThreads;   // cells per thread
+        constexpr int BPT = NB / kTvThreads;   // cells per thread
         uint32_t run[BPT], psum = 0;
 #pragma unroll
         for (int qq = 0; qq < BPT; ++qq) {
@@ -635,13 +701,13 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
             uint32_t acc = 0;
             if (b < nbins) {
 #pragma unroll
-                for (int w = 0; w < kWarps; ++w) { const uint32_t c = S.u.cnt[w][b]; S.u.cnt[w][b] = (uint16_t)acc; acc += c; }
+                for (int w = 0; w < kTvWarps; ++w) { const uint32_t c = S.u.cnt[w][b]; S.u.cnt[w][b] = (uint16_t)acc; acc += c; }
             }
             run[qq] = acc | (acc ? 1u << 16 : 0u);
             psum += run[qq];
         }
         uint32_t tot;
-        uint32_t ds = block_excl_scan(psum, S.scan, tot);
+        uint32_t ds = tv_block_excl_scan(psum, S.scan, tot);
 #pragma unroll
         for (int qq = 0; qq < BPT; ++qq) {
             const int b = tid * BPT + qq;
@@ -663,7 +729,7 @@ __global__ void __launch_bounds__(kThreads, R <= 3 ? 3 : 2) k_tv(AParams P, TvAr
     if (S.out0 == 0xffffffffu) return;
     o3r_cell* const out = A.scratch + S.out0;
     // four lanes per cell: lane s left-folds items s, s + 4, ... of the cell, then (s0 + s1) + (s2 + s3): a fixed tree
-    for (int b0 = warp * 8; b0 < nbins; b0 += kWarps * 8) {
+    for (int b0 = warp * 8; b0 < nbins; b0 += kTvWarps * 8) {
         const int b = b0 + (lane >> 2), sub = lane & 3;
         uint32_t a = 0, e = 0, dense = 0;
         if (b < nbins) {
