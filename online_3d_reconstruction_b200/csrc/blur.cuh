@@ -4,7 +4,7 @@
 //
 // One CTA produces a 128-row x 64-column block of outputs.  The input block with its halo is staged in
 // shared memory once (the border rule is applied while staging), then each thread walks one row:
-// it keeps a private 256-bin histogram (median; plus 16 coarse bins so the rank search is 32 probes)
+// it keeps a private 256-bin histogram in shared memory and tracks the median through it (median)
 // or a running sum (box) and slides it one column per step (k entries in, k out).  Outputs leave through
 // a shared-memory tile so the global stores are row-coalesced.
 #pragma once
@@ -30,7 +30,7 @@ __host__ __device__ inline int blur_pitch(int k) {
 inline size_t blur_smem(int k, int mode) {
     size_t s = (size_t)(kBlurRows + k - 1) * blur_pitch(k) + (size_t)kBlurRows * kBlurStrip;
     s = (s + 15) & ~(size_t)15;
-    if (mode == O3R_BLUR_MEDIAN) s += (size_t)(256 + 16) * kBlurRows * 2;
+    if (mode == O3R_BLUR_MEDIAN) s += (size_t)128 * kBlurRows * 4;   // 256 16-bit counters per thread
     return s;
 }
 
@@ -67,37 +67,49 @@ __global__ void __launch_bounds__(kBlurRows) k_blur(const BlurJob* __restrict__ 
     __syncthreads();
     const unsigned char* myrow = tin + tid * pitch;   // window rows are myrow + dy*pitch, dy in [0,k)
     if (MODE == O3R_BLUR_MEDIAN) {
-        uint16_t* hist = reinterpret_cast<uint16_t*>(bsm + (((size_t)th * pitch + (size_t)kBlurRows * kBlurStrip + 15) & ~(size_t)15));
-        uint16_t* coarse = hist + 256 * kBlurRows;
-        for (int b = 0; b < 256; ++b) hist[b * kBlurRows + tid] = 0;
-        for (int b = 0; b < 16; ++b) coarse[b * kBlurRows + tid] = 0;
-        for (int dy = 0; dy < k; ++dy)
+        // Huang's sliding median with the histogram in shared memory: 256 16-bit counters per thread, two to a word, laid out
+        // [word][thread] (a warp's 32 rows hit 32 banks).  Counters move by shared-memory atomics WITHOUT a result — the
+        // thread never waits for them, and k in + k out per step are independent instructions instead of a chain of dependent
+        // read-modify-writes (the first version: ~365 cycles per window row).  The median is tracked, not searched: `lt` counts
+        // the window's values below `med` (register arithmetic per update), and `med` walks to the bin where
+        // lt <= k*k/2 < lt + count(med) — a step or two per pixel on real disparities.  16-bit halves never carry: a counter
+        // is decremented only for a value that was counted, and k*k <= 127^2 < 65536.
+        uint32_t* hist = reinterpret_cast<uint32_t*>(bsm + (((size_t)th * pitch + (size_t)kBlurRows * kBlurStrip + 15) & ~(size_t)15)) + tid;
+        for (int b = 0; b < 128; ++b) hist[b * kBlurRows] = 0u;
+        for (int dy = 0; dy < k; ++dy) {
+            const unsigned char* r = myrow + dy * pitch;
+#pragma unroll 4
             for (int dx = 0; dx < k; ++dx) {
-                const int v = myrow[dy * pitch + dx];
-                hist[v * kBlurRows + tid]++;
-                coarse[(v >> 4) * kBlurRows + tid]++;
+                const int v = r[dx];
+                atomicAdd(&hist[(v >> 1) * kBlurRows], 1u << ((v & 1) << 4));
             }
+        }
         const int half = (k * k) / 2;
+        int med = 0, lt = 0;
         for (int x = 0; x < kBlurStrip; ++x) {
             if (x > 0) {
+                const unsigned char* r = myrow + x - 1;
+#pragma unroll 4
                 for (int dy = 0; dy < k; ++dy) {
-                    const int vo = myrow[dy * pitch + x - 1], vn = myrow[dy * pitch + x + k - 1];
-                    hist[vo * kBlurRows + tid]--; coarse[(vo >> 4) * kBlurRows + tid]--;
-                    hist[vn * kBlurRows + tid]++; coarse[(vn >> 4) * kBlurRows + tid]++;
+                    const int vo = r[dy * pitch], vn = r[dy * pitch + k];
+                    if (vo != vn) {
+                        atomicSub(&hist[(vo >> 1) * kBlurRows], 1u << ((vo & 1) << 4));
+                        atomicAdd(&hist[(vn >> 1) * kBlurRows], 1u << ((vn & 1) << 4));
+                        lt += (vn < med ? 1 : 0) - (vo < med ? 1 : 0);
+                    }
                 }
             }
-            int acc = 0, c = 0;
-            for (; c < 16; ++c) {
-                const int h = coarse[c * kBlurRows + tid];
-                if (acc + h > half) break;
-                acc += h;
+            while (lt > half) {
+                --med;
+                lt -= (int)((hist[(med >> 1) * kBlurRows] >> ((med & 1) << 4)) & 0xffffu);
             }
-            int v = c * 16;
-            for (;; ++v) {
-                acc += hist[v * kBlurRows + tid];
-                if (acc > half) break;
+            for (;;) {
+                const int c = (int)((hist[(med >> 1) * kBlurRows] >> ((med & 1) << 4)) & 0xffffu);
+                if (lt + c > half) break;
+                lt += c;
+                ++med;
             }
-            tout[tid * kBlurStrip + x] = (unsigned char)v;
+            tout[tid * kBlurStrip + x] = (unsigned char)med;
         }
     } else {
         const int kk = k * k;
@@ -127,9 +139,15 @@ __global__ void __launch_bounds__(kBlurRows) k_blur(const BlurJob* __restrict__ 
 // space_weight[tap] * color_weight[|v - v0|] (float LUTs computed on the host with std::exp, exactly like OpenCV
 // and the oracle do), two sequential float accumulations per pixel, round-half-even(sum / wsum).  No FMA: the products
 // and sums are rounded one by one in the tap order, so the result equals the CPU loop bit for bit.
-// One CTA = 32 x 8 outputs, one output per thread; the tile + halo, both LUTs and the per-row tap extents sit in
-// shared memory (the colour LUT is read at data-dependent indices: shared memory, not constant memory).
-constexpr int kBilTX = 32, kBilTY = 8;
+// One CTA = 32 x 8 threads, each producing kBilPX horizontally adjacent outputs; the tile + halo, both LUTs and the per-row
+// tap extents sit in shared memory (the colour LUT is read at data-dependent indices: shared memory, not constant memory).
+// The kernel lives on the shared-memory pipe and on instruction issue together (709 taps per pixel at k = 30), so a thread
+// shares what its two pixels have in common: the byte at column x + t of a window row is tap j = t of pixel x and tap j = t - 1
+// of pixel x + 1, and its space weight for the second pixel is the one loaded a step earlier.  Per step: ONE byte load, ONE
+// byte -> float conversion and ONE space-weight load serve both pixels; each pixel adds its colour-weight load (LUT mirrored
+// around entry 255: cw[255 + v - v0], one scaled add away from the byte), two products and two sums — in exactly the tap
+// order of the scalar loop, pixel by pixel.
+constexpr int kBilTX = 32, kBilTY = 8, kBilPX = 2, kBilW = kBilTX * kBilPX;
 
 struct BilateralLut {       // device copies, built once per context
     const float* color_w;   // [256]
@@ -139,48 +157,78 @@ struct BilateralLut {       // device copies, built once per context
 };
 
 inline size_t bilateral_smem(int radius, int maxk) {
-    const int tw = kBilTX + 2 * radius, th = kBilTY + 2 * radius;
+    const int tw = kBilW + 2 * radius, th = kBilTY + 2 * radius;
     size_t s = ((size_t)tw * th + 15) & ~(size_t)15;
-    return s + (size_t)256 * 4 + (size_t)maxk * 4 + (size_t)(2 * radius + 1) * 4;
+    return s + (size_t)512 * 4 + (size_t)maxk * 4 + (size_t)(2 * radius + 1) * 4;
 }
 
 __global__ void __launch_bounds__(kBilTX * kBilTY) k_bilateral(const BlurJob* __restrict__ jobs, BilateralLut L, int rows,
                                                                int cols, int rx0, int ry0, int rx1, int ry1) {
     extern __shared__ __align__(16) unsigned char bsm[];
     const BlurJob job = jobs[blockIdx.z];
-    const int r = L.radius, tw = kBilTX + 2 * r, th = kBilTY + 2 * r;
+    const int r = L.radius, tw = kBilW + 2 * r, th = kBilTY + 2 * r;
     unsigned char* tin = bsm;
     float* cw = reinterpret_cast<float*>(bsm + (((size_t)tw * th + 15) & ~(size_t)15));
-    float* sw = cw + 256;
+    float* sw = cw + 512;
     int* jm = reinterpret_cast<int*>(sw + L.maxk);
     const int tid = threadIdx.y * kBilTX + threadIdx.x, nthr = kBilTX * kBilTY;
-    const int bx = rx0 + blockIdx.x * kBilTX, by = ry0 + blockIdx.y * kBilTY;
+    const int bx = rx0 + blockIdx.x * kBilW, by = ry0 + blockIdx.y * kBilTY;
     for (int i = tid; i < tw * th; i += nthr) {
         const int ly = i / tw, lx = i - ly * tw;
         tin[i] = job.src[(size_t)dev_reflect101(by - r + ly, rows) * job.sstep + dev_reflect101(bx - r + lx, cols)];
     }
-    for (int i = tid; i < 256; i += nthr) cw[i] = L.color_w[i];
+    for (int i = tid; i < 511; i += nthr) cw[i] = L.color_w[abs(i - 255)];
     for (int i = tid; i < L.maxk; i += nthr) sw[i] = L.space_w[i];
     for (int i = tid; i < 2 * r + 1; i += nthr) jm[i] = L.jmax[i];
     __syncthreads();
-    const int gx = bx + threadIdx.x, gy = by + threadIdx.y;
+    const int gx = bx + threadIdx.x * kBilPX, gy = by + threadIdx.y;
     if (gx >= rx1 || gy >= ry1) return;
-    const unsigned char* c0 = tin + (threadIdx.y + r) * tw + threadIdx.x + r;
-    const int v0 = *c0;
-    float sum = 0.f, wsum = 0.f;
+    const unsigned char* c0 = tin + (threadIdx.y + r) * tw + threadIdx.x * kBilPX + r;   // centre of the thread's first pixel
+    const uint32_t cw_s = (uint32_t)__cvta_generic_to_shared(cw);
+    uint32_t cw0 = cw_s + (uint32_t)(255 - (int)c0[0]) * 4u, cw1 = cw_s + (uint32_t)(255 - (int)c0[1]) * 4u;   // &cw[255 - v0]
+    asm volatile("" : "+r"(cw0), "+r"(cw1));   // opaque: keeps the per-tap address ONE scaled add (base + 4 v) instead of two
+    auto cwv = [](uint32_t base, int v) {
+        float w;
+        asm("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(base + (uint32_t)v * 4u));
+        return w;
+    };
+    float sum0 = 0.f, wsum0 = 0.f, sum1 = 0.f, wsum1 = 0.f;
     int k = 0;
     for (int i = -r; i <= r; ++i) {
         const int m = jm[i + r];
         const unsigned char* row = c0 + i * tw;
-#pragma unroll 4
-        for (int j = -m; j <= m; ++j, ++k) {
-            const int v = row[j];
-            const float w = __fmul_rn(sw[k], cw[abs(v - v0)]);
-            sum = __fadd_rn(sum, __fmul_rn((float)v, w));
-            wsum = __fadd_rn(wsum, w);
+        const float* swr = sw + k + m;   // space weight of tap (i, j): swr[j]
+        // the byte at column t is tap j = t of the first pixel and tap j = t - 1 of the second
+        int v = row[-m];
+        float sp = swr[-m];
+        {   // t = -m: the first pixel's first tap
+            const float w = __fmul_rn(sp, cwv(cw0, v));
+            sum0 = __fadd_rn(sum0, __fmul_rn((float)v, w));
+            wsum0 = __fadd_rn(wsum0, w);
         }
+#pragma unroll 4
+        for (int t = -m + 1; t <= m; ++t) {
+            v = row[t];
+            const float f = (float)v, s = swr[t];
+            const float wa = __fmul_rn(s, cwv(cw0, v));
+            sum0 = __fadd_rn(sum0, __fmul_rn(f, wa));
+            wsum0 = __fadd_rn(wsum0, wa);
+            const float wb = __fmul_rn(sp, cwv(cw1, v));
+            sum1 = __fadd_rn(sum1, __fmul_rn(f, wb));
+            wsum1 = __fadd_rn(wsum1, wb);
+            sp = s;
+        }
+        {   // t = m + 1: the second pixel's last tap
+            v = row[m + 1];
+            const float w = __fmul_rn(sp, cwv(cw1, v));
+            sum1 = __fadd_rn(sum1, __fmul_rn((float)v, w));
+            wsum1 = __fadd_rn(wsum1, w);
+        }
+        k += 2 * m + 1;
     }
-    job.dst[(size_t)gy * job.dstep + gx] = (unsigned char)__float2int_rn(__fdiv_rn(sum, wsum));
+    uint8_t* out = job.dst + (size_t)gy * job.dstep + gx;
+    out[0] = (unsigned char)__float2int_rn(__fdiv_rn(sum0, wsum0));
+    if (gx + 1 < rx1) out[1] = (unsigned char)__float2int_rn(__fdiv_rn(sum1, wsum1));
 }
 
 }  // namespace o3r

@@ -396,7 +396,7 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
                         BilateralLut L;
                         int rcl = bilateral_lut(ctx, p.blur_kernel, &L);
                         if (rcl) return rcl;
-                        const dim3 gb(cdiv(rx1 - rx0, kBilTX), cdiv(ry1 - ry0, kBilTY), nc);
+                        const dim3 gb(cdiv(rx1 - rx0, kBilW), cdiv(ry1 - ry0, kBilTY), nc);
                         LAUNCH(k_bilateral, gb, dim3(kBilTX, kBilTY), bilateral_smem(L.radius, L.maxk), bj, L, p.rows, p.cols, rx0, ry0, rx1, ry1);
                     } else if (p.blur_mode == O3R_BLUR_MEDIAN)
                         LAUNCH_N("k_blur_median", (k_blur<O3R_BLUR_MEDIAN>), g, kBlurRows, sm, bj, p.rows, p.cols, p.blur_kernel, rx0, ry0, rx1, ry1);

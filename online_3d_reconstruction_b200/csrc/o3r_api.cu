@@ -541,7 +541,7 @@ int o3r_blur_u8(o3r_ctx* ctx, const uint8_t* src, size_t src_step, int rows, int
         BilateralLut L;
         int rcl = bilateral_lut(ctx, kernel, &L);
         if (rcl) return rcl;
-        const dim3 gb(cdiv(cols, kBilTX), cdiv(rows, kBilTY), 1);
+        const dim3 gb(cdiv(cols, kBilW), cdiv(rows, kBilTY), 1);
         LAUNCH(k_bilateral, gb, dim3(kBilTX, kBilTY), bilateral_smem(L.radius, L.maxk), ctx->d_blurjobs.as<BlurJob>(), L, rows, cols, 0, 0, cols, rows);
     } else if (mode == O3R_BLUR_MEDIAN)
         LAUNCH_N("k_blur_median", (k_blur<O3R_BLUR_MEDIAN>), g, kBlurRows, sm, ctx->d_blurjobs.as<BlurJob>(), rows, cols, kernel, 0, 0, cols, rows);

@@ -291,6 +291,23 @@ def test_blur_plane_bit_exact(mode, k):
     assert np.array_equal(got, exp), int((got != exp).sum())
 
 
+@pytest.mark.parametrize("mode,k", [(abi.BLUR_MEDIAN, 5), (abi.BLUR_MEDIAN, 41), (abi.BLUR_BOX, 7), (abi.BLUR_BILATERAL, 6),
+                                    (abi.BLUR_BILATERAL, 30)])
+def test_blur_plane_full_range_flat_areas_and_odd_width(mode, k):
+    """Planes the synthetic disparities do not reach: every 8-bit value incl. 0 and 255 next to large constant areas (the
+    sliding median's unchanged-column shortcut, its tracked median jumping across the whole histogram), and an odd width
+    (the bilateral kernel's threads own two columns each: the last thread of a row owns one)."""
+    rng = np.random.default_rng(1000 + k)
+    src = rng.integers(0, 256, (97, 211), dtype=np.uint8)
+    src[10:60, 20:120] = 255
+    src[30:90, 100:200] = 0
+    src[5:25, 150:205] = 77
+    exp = ob.blur_u8(src, k, mode)
+    with Pose(abi.make_params(**SMALL)) as P:
+        got = P.blur(src, k, mode)
+    assert np.array_equal(got, exp), int((got != exp).sum())
+
+
 def test_blur_matches_reference_median_outputs(golden_dir):
     g = np.load(os.path.join(golden_dir, "median_ref.npz"))
     with Pose(abi.make_params(**SMALL)) as P:
