@@ -253,8 +253,12 @@ def run_ours(args, rank, world, local_rank):
     d_disp = [torch.from_numpy(a).to(dev) for a in disp]
     d_bgr = [torch.from_numpy(a).to(dev) for a in bgr]
     # pinned host copies for the end-to-end leg
-    h_disp = [torch.from_numpy(a).pin_memory() for a in disp]
-    h_bgr = [torch.from_numpy(a).pin_memory() for a in bgr]
+    # (the cycle's frames sit back to back in ONE pinned arena per plane type — a ring buffer of page-locked image slots, what
+    #  o3r_host_alloc is for — so the library can move groups of adjacent planes with one 2-D copy each)
+    h_disp_all = torch.from_numpy(np.stack(disp)).pin_memory()
+    h_bgr_all = torch.from_numpy(np.stack(bgr)).pin_memory()
+    h_disp = [h_disp_all[i] for i in range(len(disp))]
+    h_bgr = [h_bgr_all[i] for i in range(len(bgr))]
     torch.cuda.synchronize()
     fr_dev = [frames_array([t.data_ptr() for t in d_disp], disp[0].strides[0], [t.data_ptr() for t in d_bgr],
                            bgr[0].strides[0], T[s]) for s in range(W + K + 1)]
@@ -280,6 +284,11 @@ def run_ours(args, rank, world, local_rank):
         dist.broadcast_object_list(box, src=0, device=dev)
         P.commInit(world, rank, box[0], slot_cells)
         stats["exchange_slot_cells"] = slot_cells
+
+    # bytes the library's copies move per step: groups of up to 16 adjacent frames, each group one pitched image per plane type
+    roi_w, roi_h = cols - p.bounding_box - p.cols_start_aft_cutout, rows - 2 * p.bounding_box
+    h2d_rows = sum((min(16, F - a) - 1) * rows + roi_h for a in range(0, F, 16))
+    h2d_bytes = h2d_rows * roi_w * (bd + 3)
 
     def exchange():
         P.exchangeCycle()
@@ -347,16 +356,17 @@ def run_ours(args, rank, world, local_rank):
 
     def h2d_ceiling():
         """Plain pinned -> device copies of one step's input volume, all ranks at once: what the host link gives each GPU."""
-        nbytes = int(F * (rows - 2 * p.bounding_box) * (cols - p.bounding_box - p.cols_start_aft_cutout) * (bd + 3))
+        nbytes = int(h2d_bytes)
         src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
         dst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         dst.copy_(src, non_blocking=True)
         barrier()
-        t0 = time.perf_counter()
-        for _ in range(4):
+        dt_s = float("inf")   # best of 6 (the first copies after the allocation run slow on some hosts)
+        for _ in range(6):
+            t0 = time.perf_counter()
             dst.copy_(src, non_blocking=True)
-        barrier()
-        dt_s = (time.perf_counter() - t0) / 4
+            barrier()
+            dt_s = min(dt_s, time.perf_counter() - t0)
         if world > 1:
             t = torch.tensor([dt_s], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -436,7 +446,6 @@ def run_ours(args, rank, world, local_rank):
     roof["profiled_step_ms"] = ms_prof / K
 
     frames_total = world * F * K
-    roi_px = (rows - 2 * p.bounding_box) * (cols - p.bounding_box - p.cols_start_aft_cutout)
     res = {
         "metric": "frames_per_sec", "value": frames_total / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
@@ -451,8 +460,10 @@ def run_ours(args, rank, world, local_rank):
                 "parallelism": f"frames f mod {world}; grouped ncclSend/ncclRecv of hash-partitioned cells inside libo3r.so" if world > 1 else "single GPU"},
         "clocks": clk, "wall_ms_per_step": wall / K,
         "e2e": {"value": frames_total / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e / K,
-                "h2d_bytes_per_step": int(F * roi_px * (bd + 3)), "d2h_bytes_per_step": int(d2h),
-                "h2d_note": "only the scan ROI of each frame crosses PCIe (x in [cols/8, cols-20), y in [20, rows-20))",
+                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h),
+                "h2d_note": ("only the scan ROI columns of each frame cross PCIe (x in [cols/8, cols-20)); the frames of a cycle sit back to "
+                             "back in one pinned arena, so up to 16 adjacent planes move as one 2-D copy (the 2 x 20 margin rows between "
+                             "two ROIs ride along and are counted here)"),
                 "h2d_ceiling_gbs_per_gpu": round(h2d_gbs, 2), "h2d_floor_ms_per_step": round(h2d_ms, 3),
                 "h2d_ceiling_note": f"one contiguous pinned->device copy of a step's input bytes, {world} rank(s) at once, slowest rank",
                 "compute_stream_ms_per_step": ms_e2e_ev / K, "timing": "wall clock around K steps incl. final sync",

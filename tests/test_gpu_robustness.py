@@ -152,3 +152,32 @@ def test_fused_tile_engine_takes_a_scaled_and_sheared_matrix():
         assert np.array_equal(_multiset(P.lastCyclePoints()), _multiset(cloud[:n]))
         got = P.downsamplePtCloud()
     _close(got, ob.downsample_pt_cloud(p, cloud[:n], True))
+
+
+@pytest.mark.parametrize("disp_type,blur", [(abi.DISP_U8, 1), (abi.DISP_U16, 1), (abi.DISP_U8, 5)])
+def test_adjacent_host_planes_move_as_grouped_copies(disp_type, blur):
+    """Frames held back to back in one host arena are staged with ONE 2-D copy per plane type and group of <= 16 frames
+    (host_frames.cuh::stage_copy; the margin rows between two ROIs ride along) — the staged ROI, and with it every result, must
+    equal the per-plane copies of separately allocated frames: 21 frames = groups of 16 + 5 when prefetched, 10 + 10 + 1 when
+    chunked; frame 7 lives in its own buffer and splits its group."""
+    keep = []
+    rows, cols = SMALL4["rows"], SMALL4["cols"]
+    p = abi.make_params(jump_pixels=1, voxel_size=0.05, max_batch_frames=32, blur_kernel=blur, **SMALL4)
+    seq = synth.sequence(520, 21, rows, cols, disp_type=disp_type)
+    d_all = np.stack([d for d, _, _ in seq])
+    c_all = np.stack([c for _, c, _ in seq])
+    lone_d, lone_c = d_all[7].copy(), c_all[7].copy()
+    arena = [abi.make_frame(lone_d if i == 7 else d_all[i], lone_c if i == 7 else c_all[i], T, keep=keep)
+             for i, (_, _, T) in enumerate(seq)]
+    assert arena[1].disp == arena[0].disp + rows * arena[0].disp_step and arena[8].disp != arena[7].disp + rows * arena[7].disp_step
+    apart = [abi.make_frame(d.copy(), c.copy(), T, keep=keep) for d, c, T in seq]
+    cloud, n, counts = ob.run_cycle(p, apart, disp_type, 4)
+    exp = ob.downsample_pt_cloud(p, cloud[:n], True)
+    for prefetch in (False, True):
+        for frames in (arena, apart):
+            with Pose(p) as P:
+                arr = P.prefetchCycle(frames, disp_type) if prefetch else frames
+                got_counts = P.createCycleClouds(arr, disp_type)
+                assert np.array_equal(got_counts, counts)
+                _eq(P.lastCyclePoints(), cloud[:n])
+                _eq(P.downsamplePtCloud(), exp)
