@@ -355,18 +355,31 @@ def run_ours(args, rank, world, local_rank):
         return ms, wall, P.launch_count() - l0
 
     def h2d_ceiling():
-        """Plain pinned -> device copies of one step's input volume, all ranks at once: what the host link gives each GPU."""
+        """Plain pinned -> device copies of one step's input volume, as two halves on two streams (the library stages on two copy
+        streams as well), all ranks at once: what the host link gives each GPU.  Best of 6 on one GPU, median of 6 when several
+        ranks share the link."""
         nbytes = int(h2d_bytes)
+        half = nbytes // 2
         src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        src.zero_()
         dst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        dst.copy_(src, non_blocking=True)
+        sa, sb = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+        def once():
+            with torch.cuda.stream(sa):
+                dst[:half].copy_(src[:half], non_blocking=True)
+            with torch.cuda.stream(sb):
+                dst[half:].copy_(src[half:], non_blocking=True)
+            torch.cuda.synchronize()
+
+        once()
         barrier()
-        dt_s = float("inf")   # best of 6 (the first copies after the allocation run slow on some hosts)
+        times = []
         for _ in range(6):
             t0 = time.perf_counter()
-            dst.copy_(src, non_blocking=True)
-            barrier()
-            dt_s = min(dt_s, time.perf_counter() - t0)
+            once()
+            times.append(time.perf_counter() - t0)
+        dt_s = min(times) if world == 1 else sorted(times)[3]
         if world > 1:
             t = torch.tensor([dt_s], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -465,7 +478,7 @@ def run_ours(args, rank, world, local_rank):
                              "back in one pinned arena, so up to 16 adjacent planes move as one 2-D copy (the 2 x 20 margin rows between "
                              "two ROIs ride along and are counted here)"),
                 "h2d_ceiling_gbs_per_gpu": round(h2d_gbs, 2), "h2d_floor_ms_per_step": round(h2d_ms, 3),
-                "h2d_ceiling_note": f"one contiguous pinned->device copy of a step's input bytes, {world} rank(s) at once, slowest rank",
+                "h2d_ceiling_note": f"a step's input bytes as two contiguous pinned->device copies on two streams, {world} rank(s) at once, slowest rank",
                 "compute_stream_ms_per_step": ms_e2e_ev / K, "timing": "wall clock around K steps incl. final sync",
                 "api": "o3r_frames_prefetch(next cycle) + o3r_frames_cloud(host pinned) + o3r_cloud_downsample(host pinned)"},
         "gpu_launches": int(launches), "roofline": roof,

@@ -104,6 +104,8 @@ struct TvTail {
     uint32_t bd[NB + 1];                     // per cell: first item | rank among the non-empty cells << 16
     uint32_t scan[34];
     uint32_t ticket, out0, nb, nitems, nbh;
+    uint16_t off[40];                        // plane offset of the window's later position k (TvLater::offset, tabulated: the
+                                             // division by the window width cost ~8 instructions per verified / folded mate)
     int cmin[3], cmax[3];
     uint32_t bb[6];
     uint32_t any_valid, bad;
@@ -308,6 +310,7 @@ __global__ void __launch_bounds__(kTvThreads, tv_ctas_per_sm<R>()) k_tv(AParams 
     if (tid == 0) { S.ticket = atomicAdd(A.ticket, 1u); S.any_valid = 0u; S.bad = 0u; }
     if (tid < 3) { S.cmin[tid] = 0x7fffffff; S.cmax[tid] = (int)0x80000000; S.bb[tid] = 0xffffffffu; S.bb[3 + tid] = 0u; }
     if (P.use_lut && tid < 256) { S.u.lut.rl[tid] = P.lut_r[tid]; S.u.lut.zl[tid] = P.lut_z[tid]; }
+    if (R > 0 && tid < TvLater<R ? R : 1>::N) S.off[tid] = (uint16_t)TvLater<R ? R : 1>::offset(tid, G::NC);
     __syncthreads();
     const uint32_t t = S.ticket;
     const uint32_t per_frame = (uint32_t)(A.ntx * A.nty), nt = per_frame * (uint32_t)A.n_frames;
@@ -487,7 +490,7 @@ __global__ void __launch_bounds__(kTvThreads, tv_ctas_per_sm<R>()) k_tv(AParams 
                     while (l) {
                         const int k = tv_ffs(l);
                         l &= l - 1;
-                        const int on = oc + LW::offset(k, G::NC);
+                        const int on = oc + (int)S.off[k];
                         int ni, nj, nk;
                         bk_cell(SX[on], SY[on], SZ[on], A.inv_f, ni, nj, nk);
                         if (ni == ci && nj == cj && nk == ck) {
@@ -530,7 +533,7 @@ __global__ void __launch_bounds__(kTvThreads, tv_ctas_per_sm<R>()) k_tv(AParams 
             while (l) {
                 const int k = tv_ffs(l);
                 l &= l - 1;
-                const int on = oc + LW::offset(k, G::NC);
+                const int on = oc + (int)S.off[k];
                 sx = __fadd_rn(sx, SX[on]); sy = __fadd_rn(sy, SY[on]); sz = __fadd_rn(sz, SZ[on]);
                 w = SC[on];
                 cr += (w >> 16) & 255u; cg += (w >> 8) & 255u; cb += w & 255u;
