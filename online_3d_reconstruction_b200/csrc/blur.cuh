@@ -2,25 +2,28 @@
 // with the two filters north_star names: exact k x k median (cv::medianBlur: BORDER_REPLICATE, odd k)
 // and normalised box (cv::blur: anchor k/2, BORDER_REFLECT_101, round-half-even(S / k^2)).
 //
-// One CTA produces a 128-row x 64-column block of outputs.  The input block with its halo is staged in
-// shared memory once (the border rule is applied while staging), then each thread walks one row:
-// it keeps a private 256-bin histogram in shared memory and tracks the median through it (median)
-// or a running sum (box) and slides it one column per step (k entries in, k out).  Outputs leave through
-// a shared-memory tile so the global stores are row-coalesced.
+// One CTA produces a block of 64 output columns x 128 rows (box) or 32 rows (median).  The input block with its halo is
+// staged in shared memory once (the border rule is applied while staging); a thread (box) or a group of four lanes (median)
+// walks one output row: a running sum, or a 256-bin histogram in shared memory through which the median is tracked, slid
+// one column per step (k entries in, k out).  Outputs leave through a shared-memory tile so the global stores are row-coalesced.
 #pragma once
 #include "common.cuh"
 
 namespace o3r {
 
-constexpr int kBlurRows = 128;   // threads per CTA == output rows per CTA
+constexpr int kBlurRows = 128;   // threads per CTA; output rows per CTA of the box filter (one thread per row)
 constexpr int kBlurStrip = 64;   // output columns per CTA
 constexpr int kBlurMaxK = 127;
+constexpr int kMedLanes = 4;                        // median: lanes that share one output row's histogram
+constexpr int kMedRows = kBlurRows / kMedLanes;     // median: output rows per CTA
+constexpr int kMedStride = kMedRows + 1;            // histogram words of one bin pair, padded: a row's lanes hit different banks
 
 struct BlurJob {
     const uint8_t* src; unsigned long long sstep;
     uint8_t* dst; unsigned long long dstep;
 };
 
+__host__ __device__ inline int blur_rows(int mode) { return mode == O3R_BLUR_MEDIAN ? kMedRows : kBlurRows; }
 __host__ __device__ inline int blur_pitch(int k) {
     int w = kBlurStrip + k - 1;
     int p = (w + 3) / 4;
@@ -28,9 +31,10 @@ __host__ __device__ inline int blur_pitch(int k) {
     return p * 4;
 }
 inline size_t blur_smem(int k, int mode) {
-    size_t s = (size_t)(kBlurRows + k - 1) * blur_pitch(k) + (size_t)kBlurRows * kBlurStrip;
+    const int rows = blur_rows(mode);
+    size_t s = (size_t)(rows + k - 1) * blur_pitch(k) + (size_t)rows * kBlurStrip;
     s = (s + 15) & ~(size_t)15;
-    if (mode == O3R_BLUR_MEDIAN) s += (size_t)128 * kBlurRows * 4;   // 256 16-bit counters per thread
+    if (mode == O3R_BLUR_MEDIAN) s += (size_t)128 * kMedStride * 4;   // 256 16-bit counters per output row, two to a word
     return s;
 }
 
@@ -44,10 +48,11 @@ template <int MODE>
 __global__ void __launch_bounds__(kBlurRows) k_blur(const BlurJob* __restrict__ jobs, int rows, int cols, int k,
                                                     int rx0, int ry0, int rx1, int ry1) {
     extern __shared__ __align__(16) unsigned char bsm[];
+    constexpr int ROWS = MODE == O3R_BLUR_MEDIAN ? kMedRows : kBlurRows;
     const BlurJob job = jobs[blockIdx.z];
     const int a = k / 2, pitch = blur_pitch(k);
-    const int bx = rx0 + blockIdx.x * kBlurStrip, by = ry0 + blockIdx.y * kBlurRows;
-    const int tw = kBlurStrip + k - 1, th = kBlurRows + k - 1;
+    const int bx = rx0 + blockIdx.x * kBlurStrip, by = ry0 + blockIdx.y * ROWS;
+    const int tw = kBlurStrip + k - 1, th = ROWS + k - 1;
     unsigned char* tin = bsm;
     unsigned char* tout = bsm + (size_t)th * pitch;
     const int tid = threadIdx.x;
@@ -64,54 +69,68 @@ __global__ void __launch_bounds__(kBlurRows) k_blur(const BlurJob* __restrict__ 
         }
         tin[ly * pitch + lx] = job.src[(size_t)gy * job.sstep + gx];
     }
-    __syncthreads();
-    const unsigned char* myrow = tin + tid * pitch;   // window rows are myrow + dy*pitch, dy in [0,k)
     if (MODE == O3R_BLUR_MEDIAN) {
-        // Huang's sliding median with the histogram in shared memory: 256 16-bit counters per thread, two to a word, laid out
-        // [word][thread] (a warp's 32 rows hit 32 banks).  Counters move by shared-memory atomics WITHOUT a result — the
-        // thread never waits for them, and k in + k out per step are independent instructions instead of a chain of dependent
-        // read-modify-writes (the first version: ~365 cycles per window row).  The median is tracked, not searched: `lt` counts
-        // the window's values below `med` (register arithmetic per update), and `med` walks to the bin where
-        // lt <= k*k/2 < lt + count(med) — a step or two per pixel on real disparities.  16-bit halves never carry: a counter
-        // is decremented only for a value that was counted, and k*k <= 127^2 < 65536.
-        uint32_t* hist = reinterpret_cast<uint32_t*>(bsm + (((size_t)th * pitch + (size_t)kBlurRows * kBlurStrip + 15) & ~(size_t)15)) + tid;
-        for (int b = 0; b < 128; ++b) hist[b * kBlurRows] = 0u;
-        for (int dy = 0; dy < k; ++dy) {
+        // Huang's sliding median, one histogram per output row in shared memory: 256 16-bit counters, two to a word, laid out
+        // [word][row] with a padded stride.  FOUR lanes share a row: each takes every fourth window row of the k values that
+        // enter and the k that leave per step, so a step's dependent chain is a quarter as long, and the 16 KB of histograms
+        // per CTA (instead of 64 KB with one thread per row) let 36 warps live on an SM instead of 8 — the first version of
+        // this kernel sat at 12 % occupancy waiting for its own shared-memory round trips.  Counters move by shared-memory
+        // atomics WITHOUT a result (nobody waits for them; lanes of one row may hit the same counter), unchanged columns are
+        // skipped, and the median is tracked, not searched: `lt` counts the window's values below `med` (register
+        // arithmetic per update, summed over the four lanes by two shuffles), and `med` walks to the bin where
+        // lt <= k*k/2 < lt + count(med) — a step or two per pixel on real disparities; the four lanes do that walk redundantly
+        // on the same counters.  16-bit halves never carry: a counter is decremented only for a value that was counted, and
+        // k*k <= 127^2 < 65536.
+        uint32_t* hist_all = reinterpret_cast<uint32_t*>(bsm + (((size_t)th * pitch + (size_t)ROWS * kBlurStrip + 15) & ~(size_t)15));
+        for (int i = tid; i < 128 * kMedStride; i += kBlurRows) hist_all[i] = 0u;
+        __syncthreads();
+        const int row = tid / kMedLanes, sub = tid % kMedLanes;
+        uint32_t* hist = hist_all + row;
+        const unsigned char* myrow = tin + row * pitch;   // window rows are myrow + dy*pitch, dy in [0,k)
+        for (int dy = sub; dy < k; dy += kMedLanes) {
             const unsigned char* r = myrow + dy * pitch;
 #pragma unroll 4
             for (int dx = 0; dx < k; ++dx) {
                 const int v = r[dx];
-                atomicAdd(&hist[(v >> 1) * kBlurRows], 1u << ((v & 1) << 4));
+                atomicAdd(&hist[(v >> 1) * kMedStride], 1u << ((v & 1) << 4));
             }
         }
         const int half = (k * k) / 2;
         int med = 0, lt = 0;
         for (int x = 0; x < kBlurStrip; ++x) {
+            int d = 0;
             if (x > 0) {
                 const unsigned char* r = myrow + x - 1;
 #pragma unroll 4
-                for (int dy = 0; dy < k; ++dy) {
+                for (int dy = sub; dy < k; dy += kMedLanes) {
                     const int vo = r[dy * pitch], vn = r[dy * pitch + k];
                     if (vo != vn) {
-                        atomicSub(&hist[(vo >> 1) * kBlurRows], 1u << ((vo & 1) << 4));
-                        atomicAdd(&hist[(vn >> 1) * kBlurRows], 1u << ((vn & 1) << 4));
-                        lt += (vn < med ? 1 : 0) - (vo < med ? 1 : 0);
+                        atomicSub(&hist[(vo >> 1) * kMedStride], 1u << ((vo & 1) << 4));
+                        atomicAdd(&hist[(vn >> 1) * kMedStride], 1u << ((vn & 1) << 4));
+                        d += (vn < med ? 1 : 0) - (vo < med ? 1 : 0);
                     }
                 }
             }
+            d += __shfl_xor_sync(kFull, d, 1);
+            d += __shfl_xor_sync(kFull, d, 2);
+            lt += d;
+            __syncwarp();   // the row's counters are final for this step
             while (lt > half) {
                 --med;
-                lt -= (int)((hist[(med >> 1) * kBlurRows] >> ((med & 1) << 4)) & 0xffffu);
+                lt -= (int)((hist[(med >> 1) * kMedStride] >> ((med & 1) << 4)) & 0xffffu);
             }
             for (;;) {
-                const int c = (int)((hist[(med >> 1) * kBlurRows] >> ((med & 1) << 4)) & 0xffffu);
+                const int c = (int)((hist[(med >> 1) * kMedStride] >> ((med & 1) << 4)) & 0xffffu);
                 if (lt + c > half) break;
                 lt += c;
                 ++med;
             }
-            tout[tid * kBlurStrip + x] = (unsigned char)med;
+            if (sub == 0) tout[row * kBlurStrip + x] = (unsigned char)med;
+            __syncwarp();   // every lane has read the counters before the next step moves them
         }
     } else {
+        __syncthreads();
+        const unsigned char* myrow = tin + tid * pitch;   // window rows are myrow + dy*pitch, dy in [0,k)
         const int kk = k * k;
         int S = 0;
         for (int dy = 0; dy < k; ++dy)
@@ -127,7 +146,7 @@ __global__ void __launch_bounds__(kBlurRows) k_blur(const BlurJob* __restrict__ 
         }
     }
     __syncthreads();
-    for (int i = tid; i < kBlurRows * kBlurStrip; i += kBlurRows) {
+    for (int i = tid; i < ROWS * kBlurStrip; i += kBlurRows) {
         const int ly = i / kBlurStrip, lx = i - ly * kBlurStrip;
         const int gy = by + ly, gx = bx + lx;
         if (gy < ry1 && gx < rx1) job.dst[(size_t)gy * job.dstep + gx] = tout[i];

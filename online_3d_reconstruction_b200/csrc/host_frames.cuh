@@ -406,7 +406,7 @@ int frames_cloud_impl(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_typ
             if (blur) {
                 const int rx0 = P.x0, rx1 = p.cols - p.bounding_box, ry0 = p.bounding_box, ry1 = p.rows - p.bounding_box;
                 if (rx1 > rx0 && ry1 > ry0) {
-                    const dim3 g(cdiv(rx1 - rx0, kBlurStrip), cdiv(ry1 - ry0, kBlurRows), nc);
+                    const dim3 g(cdiv(rx1 - rx0, kBlurStrip), cdiv(ry1 - ry0, blur_rows(p.blur_mode)), nc);
                     const size_t sm = blur_smem(p.blur_kernel, p.blur_mode);
                     const BlurJob* bj = ctx->d_blurjobs.as<BlurJob>() + f0;
                     if (p.blur_mode == O3R_BLUR_BILATERAL) {

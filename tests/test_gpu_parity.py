@@ -291,8 +291,8 @@ def test_blur_plane_bit_exact(mode, k):
     assert np.array_equal(got, exp), int((got != exp).sum())
 
 
-@pytest.mark.parametrize("mode,k", [(abi.BLUR_MEDIAN, 5), (abi.BLUR_MEDIAN, 41), (abi.BLUR_BOX, 7), (abi.BLUR_BILATERAL, 6),
-                                    (abi.BLUR_BILATERAL, 30)])
+@pytest.mark.parametrize("mode,k", [(abi.BLUR_MEDIAN, 5), (abi.BLUR_MEDIAN, 41), (abi.BLUR_MEDIAN, 127), (abi.BLUR_BOX, 7),
+                                    (abi.BLUR_BOX, 127), (abi.BLUR_BILATERAL, 6), (abi.BLUR_BILATERAL, 30)])
 def test_blur_plane_full_range_flat_areas_and_odd_width(mode, k):
     """Planes the synthetic disparities do not reach: every 8-bit value incl. 0 and 255 next to large constant areas (the
     sliding median's unchanged-column shortcut, its tracked median jumping across the whole histogram), and an odd width
