@@ -37,7 +37,7 @@ from online_3d_reconstruction_b200 import abi, synth  # noqa: E402
 # (workload, kernel) -> dram__bytes_read.sum + dram__bytes_write.sum per launch, from the COMMITTED `ncu --set full` capture of
 # the same command (profiles/r02_ncu_full.txt) — a constant of that capture, not a property of this run (roofline.traffic_source)
 NCU_TRAFFIC = {
-    ("config2_semidense_720p", "k_tv"): 180.4e6,
+    ("config2_semidense_720p", "k_tv"): 181.9e6,
 }
 NCU_TRAFFIC_SOURCE = "profiles/r02_ncu_full.txt (ncu --set full --clock-control none, cold caches, one launch)"
 
