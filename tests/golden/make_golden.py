@@ -9,6 +9,10 @@ Sources (relative to /root/reference/build):
   output/medianBlurred_{15,31}.png cv::medianBlur outputs of images/1248.png written by the reference
   output/bilateralFiltered_{15,31}.png cv::bilateralFilter(img, k, 2k, k/2) outputs written by the reference
   cloud.ply                        a combined-grid VoxelGrid output of the reference (voxel_size 0.05)
+plus one fixture that comes from OpenCV (cv2 4.13 of the build container) rather than from the reference's files:
+  reproject_cv2.npz                cv2.gemm(Q, [x y d 1]^T) for a generic Q over a small frame's scan ROI
+  planefit_cv2.npz                 per-label plane coefficients of the three real frames computed the reference's way with
+                                   cv2.gemm / cv2.invert(DECOMP_SVD)
 Decoding PNGs needs cv2 (present in the build container only).
 """
 import os
@@ -61,6 +65,41 @@ def main():
     np.savez_compressed(os.path.join(OUT, "cloud_ply.npz"), header=np.frombuffer(raw[:h], dtype=np.uint8),
                         xyz=np.stack([v["x"], v["y"], v["z"]], 1), rgb=np.stack([v["r"], v["g"], v["b"]], 1),
                         trailer=np.frombuffer(raw[h + 15 * n:], dtype=np.uint8))
+    # --- the reprojection's matrix product through OpenCV itself: cv::Mat_<double>(4x4) * (4x1) = cv::gemm, for a GENERIC Q
+    #     (every entry non-zero: with the rectified-stereo Q at most two terms per row are non-zero and any summation order
+    #     gives the same bits).  Pins the oracle's left-to-right row sums (pose_functions.cpp:1074, :1111) on OpenCV 4.x.
+    rng = np.random.default_rng(77)
+    rows, cols, bb = 60, 100, 20
+    x0 = cols // 8
+    Qg = rng.normal(size=(4, 4)) * np.array([1.0, 1.0, 1.0, 100.0])
+    Qg[3] = [1e-4, -2e-4, 1.7, 0.3]          # keeps the homogeneous coordinate away from 0
+    dimg = rng.integers(65, 128, (rows, cols)).astype(np.uint8)
+    ys, xs = np.mgrid[bb:rows - bb, x0:cols - bb]
+    vecs = np.stack([xs.ravel(), ys.ravel(), dimg[ys.ravel(), xs.ravel()], np.ones(xs.size)], 1).astype(np.float64)
+    prod = np.stack([cv2.gemm(Qg, v.reshape(4, 1).copy(), 1.0, None, 0.0).ravel() for v in vecs])
+    np.savez_compressed(os.path.join(OUT, "reproject_cv2.npz"), Q=Qg, disp=dimg, gemm=prod, cv2_version=np.array(cv2.__version__))
+    # --- the plane fit the way the reference writes it (pose_functions.cpp:940-965), through OpenCV: A (N x 3), At * A by cv::gemm,
+    #     cv::invert(DECOMP_SVD), (AtAinv * At) * b — the oracle solves the same normal equations from exact integer sums with its
+    #     own 3 x 3 inverse, so its coefficients differ from these in the last digits (tests bound the difference and its effect)
+    rows, cols, bb = 720, 1280, 20
+    x0 = cols // 8
+    coefs = np.zeros((3, 8, 3))
+    n_planes = []
+    for i in range(3):
+        cc = []
+        for cl in range(1, 1024):
+            ys, xs = np.nonzero(labels[i] == cl)
+            if len(xs) == 0:
+                break
+            m = (xs > x0) & (xs < cols - bb) & (ys > bb) & (ys < rows - bb)
+            A = np.stack([xs[m].astype(np.float64), ys[m].astype(np.float64), np.ones(int(m.sum()))], 1)
+            b = disp[i][ys[m], xs[m]].astype(np.float64).reshape(-1, 1)
+            At = np.ascontiguousarray(A.T)
+            _, inv = cv2.invert(cv2.gemm(At, A, 1.0, None, 0.0), flags=cv2.DECOMP_SVD)
+            cc.append(cv2.gemm(cv2.gemm(inv, At, 1.0, None, 0.0), b, 1.0, None, 0.0).ravel())
+        coefs[i, :len(cc)] = np.array(cc)
+        n_planes.append(len(cc))
+    np.savez_compressed(os.path.join(OUT, "planefit_cv2.npz"), coef=coefs, n_planes=np.array(n_planes), cv2_version=np.array(cv2.__version__))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

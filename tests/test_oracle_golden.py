@@ -43,6 +43,36 @@ def test_plane_fit_variance_and_mask_count_match_reference_log(real):
         assert np.array_equal(pts, pts2)
 
 
+def test_plane_fit_against_opencv_gemm_and_svd_inverse(real, golden_dir):
+    """The reference fits each label's plane as (invert(At*A, DECOMP_SVD) * At) * b over the N x 3 design matrix
+    (pose_functions.cpp:940-965).  The fixture holds those coefficients computed with cv2 4.13 on the three shipped frames; the
+    oracle (exact integer normal equations + its own 3 x 3 inverse) must agree to 1e-9 relative, give the same validity mask
+    (the reference's logged point counts) and the same cloud except for a handful of coordinates that round the other way
+    (<= 1 ulp, <= 3 per 2.2 M): that is how far the label-mode cloud can sit from the true binary's."""
+    g = np.load(os.path.join(golden_dir, "planefit_cv2.npz"))
+    p = abi.make_params(jump_pixels=1, use_segment_labels=True, dont_downsample=True)
+    for i in range(3):
+        n = int(g["n_planes"][i])
+        cv = g["coef"][i, :n]
+        coef, _ = ob.plane_fit(p, real["labels"][i], real["disp"][i])
+        coef = np.asarray(coef).reshape(-1, 3)
+        assert coef.shape == cv.shape
+        assert np.max(np.abs(coef - cv) / np.abs(cv)) < 1e-9
+        keep = []
+        fa = abi.make_frame(None, real["bgr1248"], np.eye(4), labels=real["labels"][i], plane_coef=coef, keep=keep)
+        fb = abi.make_frame(None, real["bgr1248"], np.eye(4), labels=real["labels"][i], plane_coef=cv, keep=keep)
+        pa = ob.create_single_img_pt_cloud(p, fa, abi.DISP_F64)
+        pb = ob.create_single_img_pt_cloud(p, fb, abi.DISP_F64)
+        assert len(pa) == len(pb) == int(real["point_cloud_pts"][i])
+        assert np.array_equal(pa["rgb"], pb["rgb"])
+        differing = 0
+        for f in ("x", "y", "z"):
+            ulps = np.abs(pa[f].view(np.int32).astype(np.int64) - pb[f].view(np.int32))
+            assert ulps.max() <= 1
+            differing += int((ulps != 0).sum())
+        assert differing <= 3, differing
+
+
 def test_median_matches_reference_outputs(golden_dir):
     """cv::medianBlur(images/1248.png, 15|31) as written by the reference (output/medianBlurred_*.png)."""
     g = np.load(os.path.join(golden_dir, "median_ref.npz"))
@@ -157,6 +187,30 @@ def test_author_known_answer_frame():
     assert rgb[0, 0] == 0x00FF00 and rgb[100, 100] == 0xFF0000
     # first scanned pixel is (x0=160, y=20)
     assert pts["x"][0] == np.float32((160 + abi.Q_CAM13[3]) * (1.0 / (a * 128)))
+
+
+def test_generic_q_row_sums_match_cv_gemm(golden_dir):
+    """cv::Mat_<double> Q * vec (pose_functions.cpp:1074, :1111) is cv::gemm.  For a Q with sixteen non-zero entries the order of
+    the four products' sum matters in the last bit; the fixture holds cv2.gemm's own results (OpenCV 4.13, make_golden.py) for
+    every scan pixel of a small frame, and the oracle's points must equal (float)(v_i * (1.0 / v_3)) of exactly those doubles."""
+    g = np.load(os.path.join(golden_dir, "reproject_cv2.npz"))
+    rows, cols = g["disp"].shape
+    p = abi.make_params(rows=rows, cols=cols, jump_pixels=1, dont_downsample=True, Q=tuple(g["Q"].ravel()))
+    keep = []
+    fr = abi.make_frame(g["disp"], np.zeros((rows, cols, 3), np.uint8), np.eye(4), keep=keep)
+    pts = ob.create_single_img_pt_cloud(p, fr, abi.DISP_U8)
+    v = g["gemm"]
+    assert len(pts) == len(v)
+    r = 1.0 / v[:, 3]
+    for i, f in enumerate(("x", "y", "z")):
+        assert np.array_equal(pts[f], (v[:, i] * r).astype(np.float32)), f
+    # and the same products summed pairwise (what a two-accumulator gemm would do) do NOT reproduce them: the pin is not vacuous
+    q = g["Q"]
+    ys, xs = np.mgrid[20:rows - 20, cols // 8:cols - 20]
+    vec = np.stack([xs.ravel(), ys.ravel(), g["disp"][ys.ravel(), xs.ravel()], np.ones(xs.size)], 1).astype(np.float64)
+    a = q[None, :, :] * vec[:, None, :]
+    pair = (a[:, :, 0] + a[:, :, 2]) + (a[:, :, 1] + a[:, :, 3])
+    assert (pair != v).any()
 
 
 def test_voxelgrid_overflow_guard_passthrough():
