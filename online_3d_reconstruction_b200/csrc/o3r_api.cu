@@ -336,7 +336,10 @@ int o3r_cloud_append(o3r_ctx* ctx, const o3r_point* pts, size_t n) {
     CU(cudaMemcpyAsync(ctx->vox.p, pts, n * 16, cudaMemcpyHostToDevice, ctx->st));
     ctx->last_n = 0; ctx->last_total = 0; ctx->last_has_cellbb = false;   // the batch buffer was overwritten
     ctx->last_has_partials = false; ctx->last_partials = 0; ctx->last_bucketed = false; ctx->last_engine = 0;
-    return acc_merge_points(ctx, ctx->vox.as<float4>(), n, nullptr);
+    const int rc = acc_merge_points(ctx, ctx->vox.as<float4>(), n, nullptr);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->st));   // (a page-locked `pts` is read asynchronously) the caller may reuse or free it now
+    return O3R_OK;
 }
 
 int o3r_cloud_size(o3r_ctx* ctx, size_t* n) {
