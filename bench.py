@@ -259,7 +259,7 @@ def run_ours(args, rank, world, local_rank):
     d_bgr = [torch.from_numpy(a).to(dev) for a in bgr]
     # pinned host copies for the end-to-end leg
     # (the cycle's frames sit back to back in ONE pinned arena per plane type — a ring buffer of page-locked image slots, what
-    #  o3r_host_alloc is for — so the library can move groups of adjacent planes with one 2-D copy each)
+    #  o3r_host_alloc is for — so the library can move groups of adjacent planes with one 3-D copy each)
     h_disp_all = torch.from_numpy(np.stack(disp)).pin_memory()
     h_bgr_all = torch.from_numpy(np.stack(bgr)).pin_memory()
     h_disp = [h_disp_all[i] for i in range(len(disp))]
@@ -290,10 +290,10 @@ def run_ours(args, rank, world, local_rank):
         P.commInit(world, rank, box[0], slot_cells)
         stats["exchange_slot_cells"] = slot_cells
 
-    # bytes the library's copies move per step: groups of up to 16 adjacent frames, each group one pitched image per plane type
+    # bytes the library's copies move per step: exactly the scan ROI of every plane (groups of up to 16 adjacent frames move as
+    # one 3-D copy per plane type whose extent is the ROIs)
     roi_w, roi_h = cols - p.bounding_box - p.cols_start_aft_cutout, rows - 2 * p.bounding_box
-    h2d_rows = sum((min(16, F - a) - 1) * rows + roi_h for a in range(0, F, 16))
-    h2d_bytes = h2d_rows * roi_w * (bd + 3)
+    h2d_bytes = F * roi_h * roi_w * (bd + 3)
 
     def exchange():
         P.exchangeCycle()
@@ -495,9 +495,9 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clk, "wall_ms_per_step": wall / K,
         "e2e": {"value": frames_total / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h),
-                "h2d_note": ("only the scan ROI columns of each frame cross PCIe (x in [cols/8, cols-20)); the frames of a cycle sit back to "
-                             "back in one pinned arena, so up to 16 adjacent planes move as one 2-D copy (the 2 x 20 margin rows between "
-                             "two ROIs ride along and are counted here)"),
+                "h2d_note": ("only the scan ROI of each frame crosses PCIe (x in [cols/8, cols-20), y in [20, rows-20)); the frames of a cycle "
+                             "sit back to back in one pinned arena, so up to 16 adjacent planes move as one 3-D copy whose extent is exactly "
+                             "their ROIs"),
                 "h2d_ceiling_gbs_per_gpu": round(h2d_gbs, 2), "h2d_floor_ms_per_step": round(h2d_ms, 3),
                 "h2d_ceiling_note": f"a step's input bytes as two contiguous pinned->device copies on two streams, {world} rank(s) at once, slowest rank",
                 "compute_stream_ms_per_step": ms_e2e_ev / K, "timing": "wall clock around K steps incl. final sync",

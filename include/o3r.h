@@ -162,9 +162,8 @@ int o3r_frame_cloud(o3r_ctx* ctx, const o3r_frame* frame, int disp_type,
  * resident cloud.  Host pointers; only the scan ROI of each plane is copied, on the context's copy streams, overlapping
  * compute.  Consecutive frames whose disparity AND colour planes sit back to back in host memory with one row pitch
  * (frames[i+1].disp == frames[i].disp + rows * disp_step, same for bgr: a cycle kept in one o3r_host_alloc arena, the
- * equivalent of the reference's rawImageDataVec in page-locked memory) are moved with one 2-D copy per plane type and group
- * of up to 16 frames — ~10 % less copy time than one copy per plane; the rows between two ROIs are read too, so they must
- * be readable (they are: they belong to the planes).
+ * equivalent of the reference's rawImageDataVec in page-locked memory) are moved with one 3-D copy per plane type and group
+ * of up to 16 frames (extent = the ROIs of the group's planes) — ~13 % less copy time than one 2-D copy per plane.
  * If frame_counts != NULL it receives each frame's output record count (n entries). */
 int o3r_frames_cloud(o3r_ctx* ctx, const o3r_frame* frames, int n, int disp_type,
                      uint32_t* frame_counts);

@@ -103,11 +103,11 @@ int stage_copy(o3r_ctx* ctx, const o3r_frame* frames, const std::vector<FrameDev
     const int dx0 = std::max(0, cx0 - halo), dx1 = std::min(p.cols, cx1 + halo);
     const int dy0 = std::max(0, cy0 - halo), dy1 = std::min(p.rows, cy1 + halo);
     if (cx1 <= cx0 || cy1 <= cy0) return O3R_OK;   // empty ROI: nothing is ever read
-    // Frames whose planes sit back to back in host memory (a cycle held in one pinned arena, same row pitch) move as ONE 2-D
-    // copy per plane type and group: the rows of the group's frames form one pitched image on both sides (the staging planes
-    // are back to back as well), the margin rows between two ROIs ride along (+6 % bytes).  Measured on B200
-    // (profiles/scripts/h2d_shapes.py): 100 per-plane copies of a 50-frame 720p cycle 3.22 ms, groups of 5 frames 3.02 ms,
-    // one copy per plane type 2.97 ms — each copy costs ~5 us of set-up on the engine.
+    // Frames whose planes sit back to back in host memory (a cycle held in one pinned arena, same row pitch) move as ONE 3-D
+    // copy per plane type and group: the group's planes form a pitched volume on both sides (the staging planes are back to
+    // back as well) whose extent (ROI bytes per row, ROI rows, frames) is exactly the ROIs.  Measured on B200
+    // (profiles/scripts/h2d_shapes.py, 50-frame 720p cycle): 100 per-plane 2-D copies 3.21 ms (each costs ~5 us of set-up on the
+    // engine), one 2-D copy per plane type with the margin rows between the ROIs riding along 2.97 ms, one 3-D copy 2.81 ms.
     const int kGroup = 16;
     int gi = 0;
     for (int i = f0; i < f0 + nc; ++gi) {
@@ -118,14 +118,32 @@ int stage_copy(o3r_ctx* ctx, const o3r_frame* frames, const std::vector<FrameDev
                    frames[j].bgr == frames[j - 1].bgr + (size_t)p.rows * frames[i].bgr_step &&
                    (const uint8_t*)fd[j].disp == (const uint8_t*)fd[j - 1].disp + G.dplane && fd[j].bgr == fd[j - 1].bgr + G.cplane)
                 ++j;
-        const size_t span = (size_t)(j - i - 1) * p.rows;   // rows in front of the last frame's ROI
         const o3r_frame& f = frames[i];
         const FrameDev& d = fd[i];
         cudaStream_t cs = (gi & 1) ? ctx->st_copy2 : ctx->st_copy;
+        if (j - i > 1) {   // a group: ONE 3-D copy per plane type, extent (ROI bytes per row, ROI rows, frames) — exactly the ROIs
+            auto copy3d = [&](const void* src, size_t spitch, void* dst, size_t dpitch, size_t xb, size_t wb, int y0, int h) {
+                cudaMemcpy3DParms q;
+                memset(&q, 0, sizeof(q));
+                q.srcPtr = make_cudaPitchedPtr(const_cast<void*>(src), spitch, spitch, (size_t)p.rows);
+                q.dstPtr = make_cudaPitchedPtr(dst, dpitch, dpitch, (size_t)p.rows);
+                q.srcPos = make_cudaPos(xb, (size_t)y0, 0);
+                q.dstPos = make_cudaPos(xb, (size_t)y0, 0);
+                q.extent = make_cudaExtent(wb, (size_t)h, (size_t)(j - i));
+                q.kind = cudaMemcpyHostToDevice;
+                return cudaMemcpy3DAsync(&q, cs);
+            };
+            CU(copy3d(f.disp, f.disp_step, (void*)d.disp, G.dstep, (size_t)dx0 * G.es, (size_t)(dx1 - dx0) * G.es, dy0, dy1 - dy0));
+            CU(copy3d(f.bgr, f.bgr_step, (void*)d.bgr, G.cstep, (size_t)cx0 * 3, (size_t)(cx1 - cx0) * 3, cy0, cy1 - cy0));
+            for (int q = i; q < j; ++q)
+                if (fd[q].n_kp) CU(cudaMemcpyAsync((void*)fd[q].kp_xy, frames[q].kp_xy, (size_t)fd[q].n_kp * 8, cudaMemcpyHostToDevice, cs));
+            i = j;
+            continue;
+        }
         if (!label_mode) {
             CU(cudaMemcpy2DAsync((uint8_t*)d.disp + (size_t)dy0 * G.dstep + (size_t)dx0 * G.es, G.dstep,
                                  (const uint8_t*)f.disp + (size_t)dy0 * f.disp_step + (size_t)dx0 * G.es, f.disp_step,
-                                 (size_t)(dx1 - dx0) * G.es, span + (size_t)(dy1 - dy0), cudaMemcpyHostToDevice, cs));
+                                 (size_t)(dx1 - dx0) * G.es, dy1 - dy0, cudaMemcpyHostToDevice, cs));
         } else {
             CU(cudaMemcpy2DAsync((uint8_t*)d.labels + (size_t)cy0 * G.lstep + cx0, G.lstep,
                                  f.labels + (size_t)cy0 * f.labels_step + cx0, f.labels_step, (size_t)(cx1 - cx0), cy1 - cy0,
@@ -135,7 +153,7 @@ int stage_copy(o3r_ctx* ctx, const o3r_frame* frames, const std::vector<FrameDev
         }
         CU(cudaMemcpy2DAsync((uint8_t*)d.bgr + (size_t)cy0 * G.cstep + (size_t)cx0 * 3, G.cstep,
                              f.bgr + (size_t)cy0 * f.bgr_step + (size_t)cx0 * 3, f.bgr_step, (size_t)(cx1 - cx0) * 3,
-                             span + (size_t)(cy1 - cy0), cudaMemcpyHostToDevice, cs));
+                             cy1 - cy0, cudaMemcpyHostToDevice, cs));
         for (int q = i; q < j; ++q)
             if (fd[q].n_kp) CU(cudaMemcpyAsync((void*)fd[q].kp_xy, frames[q].kp_xy, (size_t)fd[q].n_kp * 8, cudaMemcpyHostToDevice, cs));
         i = j;

@@ -1,7 +1,8 @@
 """H2D microbenchmark behind the staging design: the same 150 MB of scan-ROI bytes of a 50-frame 720p cycle moved as
 (a) 100 cudaMemcpy2DAsync calls (one per plane, two streams: what the library issues for separately allocated frames),
 (b) 2 cudaMemcpy2DAsync calls over planes that sit back to back in one pinned arena (rows of all frames, margin rows included),
-(c) 100 contiguous copies of whole row ranges, (d) one contiguous copy of the same byte count.  Prints GB/s of ROI bytes."""
+(c) 2 cudaMemcpy3DAsync calls whose extent is (ROI width, ROI rows, frames): the exact ROI bytes, (d) 100 contiguous copies of
+whole row ranges.  Prints GB/s of ROI bytes."""
 import time
 
 import torch
@@ -54,16 +55,25 @@ def arena_groups(g):
         chk(rt.cudaMemcpy2DAsync(dev_c.data_ptr() + 3 * o, COLS * 3, host_c.data_ptr() + 3 * o, COLS * 3, W * 3, rows, K, st))
 
 
+def three_d():
+    """ONE cudaMemcpy3DAsync per plane type: extent = (ROI width, ROI rows, frames) — the exact ROI bytes, no margin rows."""
+    for (hp, dp, es, st) in ((host_d, dev_d, 1, s1), (host_c, dev_c, 3, s2)):
+        prm = rt.cudaMemcpy3DParms()
+        prm.srcPtr = rt.make_cudaPitchedPtr(hp.data_ptr(), COLS * es, COLS * es, ROWS)
+        prm.dstPtr = rt.make_cudaPitchedPtr(dp.data_ptr(), COLS * es, COLS * es, ROWS)
+        prm.srcPos = rt.make_cudaPos(X0 * es, BB, 0)
+        prm.dstPos = rt.make_cudaPos(X0 * es, BB, 0)
+        prm.extent = rt.make_cudaExtent(W * es, H, F)
+        prm.kind = K
+        chk(rt.cudaMemcpy3DAsync(prm, st.cuda_stream))
+
+
 def rows_contig():
     for i in range(F):
         st = (s1 if i % 2 == 0 else s2).cuda_stream
         o = i * ROWS * COLS + BB * COLS
         chk(rt.cudaMemcpyAsync(dev_d.data_ptr() + o, host_d.data_ptr() + o, H * COLS, K, st))
         chk(rt.cudaMemcpyAsync(dev_c.data_ptr() + 3 * o, host_c.data_ptr() + 3 * o, H * COLS * 3, K, st))
-
-
-def one():
-    chk(rt.cudaMemcpyAsync(dev_c.data_ptr(), host_c.data_ptr(), roi_bytes, K, s1.cuda_stream))
 
 
 def bench(name, fn, nbytes):
@@ -83,5 +93,5 @@ bench("100 x 2-D ROI copies, 2 streams", per_plane, roi_bytes)
 bench("2 x 2-D copies over one arena", arena, rows_all * W * 4)
 for g in (5, 10, 25):
     bench(f"2-D copies over groups of {g} frames", lambda g=g: arena_groups(g), 0)
+bench("2 x 3-D copies (exact ROI of every frame)", three_d, roi_bytes)
 bench("100 x contiguous row ranges", rows_contig, F * H * COLS * 4)
-bench("1 contiguous copy of the ROI byte count", one, roi_bytes)

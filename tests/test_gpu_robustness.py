@@ -156,8 +156,8 @@ def test_fused_tile_engine_takes_a_scaled_and_sheared_matrix():
 
 @pytest.mark.parametrize("disp_type,blur", [(abi.DISP_U8, 1), (abi.DISP_U16, 1), (abi.DISP_U8, 5)])
 def test_adjacent_host_planes_move_as_grouped_copies(disp_type, blur):
-    """Frames held back to back in one host arena are staged with ONE 2-D copy per plane type and group of <= 16 frames
-    (host_frames.cuh::stage_copy; the margin rows between two ROIs ride along) — the staged ROI, and with it every result, must
+    """Frames held back to back in one host arena are staged with ONE 3-D copy per plane type and group of <= 16 frames
+    (host_frames.cuh::stage_copy; extent = the ROIs of the group's planes) — the staged ROI, and with it every result, must
     equal the per-plane copies of separately allocated frames: 21 frames = groups of 16 + 5 when prefetched, 10 + 10 + 1 when
     chunked; frame 7 lives in its own buffer and splits its group."""
     keep = []
